@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""
+bench.py -- Mpix/s per 4K x 4K SFFT subtraction (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 50 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference algorithm's CPU port on the host cores
+
+A "step" is one GeneralSFFTSubtract.GSS (fit on the masked pair + Fourier-space apply on the unmasked pair) on the
+BASELINE config 2 workload: 4096 x 4096 DECam-like synthetic pair, KerHW=8, KerPolyOrder=2, BGPolyOrder=2, fp32
+images and fp32 spectra in HBM (all arithmetic fp64).  Every rank owns an independent pair (weak scaling; no
+data-path collective).  `value` is device-timed with inputs resident in HBM; `e2e` goes through the C-ABI call
+with pinned HOST buffers (H2D of the four images and D2H of the difference image inside the timed region).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N0, N1, KerHW, DK, DB, storage, seed-id)
+    'c2_4096_w8_dk2_db2_fp32': (4096, 4096, 8, 2, 2, 'fp32', 2),
+    'c2_4096_w8_dk2_db2_fp64': (4096, 4096, 8, 2, 2, 'fp64', 2),
+    'c1_512_w4_dk0_db0_fp64': (512, 512, 4, 0, 0, 'fp64', 1),
+    'c4_2048_w8_dk2_db2_fp32': (2048, 2048, 8, 2, 2, 'fp32', 4),
+    'dev_1024_w4_dk2_db2_fp32': (1024, 1024, 4, 2, 2, 'fp32', 2),
+}
+DEFAULT_WORKLOAD = 'c2_4096_w8_dk2_db2_fp32'
+HBM_FALLBACK_GBS = 6650.0     # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for k in ('hbm_gbs', 'hbm_gb_s', 'hbm'):
+                if k in d:
+                    return float(d[k]), 'measured'
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(',')]
+                if len(f) < 6:
+                    continue
+                try:
+                    sm.append(float(f[0]))
+                    mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out['sm_mhz'] = statistics.median(sm)
+            out['sm_max_mhz'] = max(mx)
+            out['samples'] = len(sm)
+        out['reasons'] = sorted(reasons)
+        return out
+
+
+def make_workload(name, rank):
+    from sfft_b200.synth import make_pair, CONFIG_SEEDS
+    N0, N1, w, DK, DB, storage, sid = WORKLOADS[name]
+    d = make_pair(N0, N1, CONFIG_SEEDS[sid] + 1000 * rank, varying_psf=(sid != 1))
+    return (N0, N1, w, DK, DB, storage), d
+
+
+def cpu_port_mpix(name, sample_side, repeats=1):
+    """The oracle (NumPy restatement of the reference NumPy backend, validated against the reference on the golden
+    fixtures) timed on the host cores on a bounded crop of the same workload."""
+    from oracle import sfft_oracle as orc
+    (N0, N1, w, DK, DB, storage), d = make_workload(name, 0)
+    s = min(sample_side, N0, N1)
+    crop = {k: np.ascontiguousarray(v[:s, :s]) for k, v in d.items()}
+    P = orc.ssc_params(s, s, w, DK, DB, True)
+    best = None
+    for _ in range(repeats):
+        t0 = time.time()
+        orc.gss(crop['REF'], crop['SCI'], crop['mREF'], crop['mSCI'], P)
+        dt = time.time() - t0
+        best = dt if best is None else min(best, dt)
+    return (s * s / 1e6) / best, best, s, orc.WORKERS
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    name = args.workload
+    N0, N1, w, DK, DB, storage, sid = WORKLOADS[name]
+    side = args.cpu_sample
+    # warmup + steps on the bounded sample; each step is one GSS of the crop
+    vals = []
+    for k in range(max(0, min(args.warmup, 1)) + max(1, min(args.steps, 3))):
+        v, dt, s, cores = cpu_port_mpix(name, side)
+        vals.append((v, dt))
+    vals = vals[max(0, min(args.warmup, 1)):]
+    v = max(x[0] for x in vals)
+    dt = min(x[1] for x in vals)
+    sample = '%dx%d crop of the %s pair, KerHW=%d DK=%d DB=%d, fp64 NumPy port of the reference NumPy backend' % (
+        s, s, name, w, DK, DB)
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'Mpix/s per 4Kx4K SFFT subtraction (GSS: fit + apply)', 'value': v,
+        'unit': 'Mpix/s', 'n_gpus': args.gpus, 'steps': len(vals), 'warmup': min(args.warmup, 1),
+        'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': {'workload': name, 'sample': sample},
+        'cpu_baseline': {'value': v, 'unit': 'Mpix/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument('--cpu-sample', type=int, default=1024, help='side of the crop timed by the CPU baseline')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--e2e-steps', type=int, default=0, help='steps of the host-buffer leg (0 = min(steps, 20))')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from sfft_b200 import _lib as B
+    from sfft_b200.plan import Plan
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+
+    (N0, N1, w, DK, DB, storage), d = make_workload(args.workload, rank)
+    npdt = np.float32 if storage == 'fp32' else np.float64
+    tdt = torch.float32 if storage == 'fp32' else torch.float64
+    code = B.F32 if storage == 'fp32' else B.F64
+    host = {k: torch.from_numpy(np.ascontiguousarray(v.astype(npdt))).pin_memory() for k, v in d.items()}
+    devt = {k: v.to(dev) for k, v in host.items()}
+    diff_d = torch.empty((N0, N1), dtype=tdt, device=dev)
+    diff_h = torch.empty((N0, N1), dtype=tdt).pin_memory()
+    sol_d = torch.empty(0, dtype=torch.float64, device=dev)
+
+    plan = Plan(N0, N1, w, w, DK, DB, True, device=local, storage=storage)
+    sol_d = torch.empty(plan.NEQ, dtype=torch.float64, device=dev)
+    sol_h = np.empty(plan.NEQ, np.float64)
+    stream = torch.cuda.current_stream(dev)
+    plan.set_stream(stream.cuda_stream)
+    plan.set_timing(True)
+    L = B.lib()
+
+    def step_device():
+        plan.gss_device(devt['REF'].data_ptr(), devt['SCI'].data_ptr(), devt['mREF'].data_ptr(), devt['mSCI'].data_ptr(),
+                        code, sol_d.data_ptr(), diff_d.data_ptr(), code)
+
+    def step_host():
+        B.check(L.sfftb_gss(plan._h, host['REF'].data_ptr(), host['SCI'].data_ptr(), host['mREF'].data_ptr(),
+                            host['mSCI'].data_ptr(), B.MEM_HOST, code, sol_h.ctypes.data, B.MEM_HOST,
+                            diff_h.data_ptr(), B.MEM_HOST, code))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(W):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = plan.launch_count
+    stage = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(K):
+        step_device()
+        for k, v in plan.timings().items():
+            stage[k] = stage.get(k, 0.0) + v
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1) / K
+    launches = plan.launch_count - l0
+    stage = {k: v / K for k, v in stage.items()}
+
+    # end-to-end leg: pinned host buffers in, host difference image out
+    KE = args.e2e_steps or min(K, 20)
+    for _ in range(2):
+        step_host()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for _ in range(KE):
+        step_host()
+    e3.record(stream)
+    barrier()
+    ms_e2e = e2.elapsed_time(e3) / KE
+    clocks = sampler.stop()
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    mpix = N0 * N1 / 1e6
+    value = world * mpix / (ms / 1e3)
+    e2e_value = world * mpix / (ms_e2e / 1e3)
+
+    if rank == 0:
+        esz = 4 if storage == 'fp32' else 8
+        csz = 2 * esz
+        NH = N1 // 2 + 1
+        Fij = (DK + 1) * (DK + 2) // 2
+        peak, which = hbm_peak()
+        # dominant kernel: the fit column pass.  Bytes it must move in this layout: read the (DK+1)+1 stored
+        # row-spectrum planes once, write the lag partials.
+        npairs = Fij * (Fij + 1) // 2
+        nrowsK = npairs * (4 * w + 1) + Fij * (2 * w + 1)
+        nrowsL = Fij * (DB + 1) * (2 * w + 1) + (DB + 1)
+        alg_bytes = (DK + 2) * NH * N0 * csz + (nrowsK + nrowsL) * NH * 16
+        t_kernel = stage.get('fit_cols', 0.0) / 1e3
+        achieved = alg_bytes / t_kernel / 1e9 if t_kernel > 0 else None
+        # whole-step algorithmic bytes: (4 n_pl + 7) * N0 * N1 * s with n_pl = Fij + 1
+        step_bytes = (4 * (Fij + 1) + 7) * N0 * N1 * esz
+        out = {
+            'metric': 'Mpix/s per 4Kx4K SFFT subtraction (GSS: fit + apply)', 'value': value, 'unit': 'Mpix/s',
+            'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': args.workload, 'image': [N0, N1], 'KerHW': w, 'KerPolyOrder': DK, 'BGPolyOrder': DB,
+                       'storage': storage, 'arithmetic': 'fp64', 'pairs_per_step_per_gpu': 1,
+                       'l2_policy': 'working set per step (inputs 4x%.0f MB + spectra %.0f MB) exceeds the 126 MB L2' % (
+                           N0 * N1 * esz / 1e6, (DK + 2) * NH * N0 * csz / 1e6),
+                       'fold': plan.dims['fold'], 'sub_len': plan.dims['sub_len']},
+            'stage_ms': stage,
+            'assembly_solve_ms': stage.get('fit_cols', 0) + stage.get('fit_reduce_fill', 0) + stage.get('fit_solve', 0),
+            'solver': plan.last_solver,
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': 'Mpix/s', 'ms_per_step': ms_e2e, 'steps': KE,
+                    'h2d_bytes_per_step': 4 * N0 * N1 * esz, 'd2h_bytes_per_step': N0 * N1 * esz + plan.NEQ * 8},
+            'gpu_launches': launches,
+            'roofline': {'bound': 'hbm', 'kernel': 'fit_col_kernel', 'achieved': achieved, 'peak': peak,
+                         'peak_source': which, 'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None,
+                         'traffic': None, 'algorithmic_bytes_per_launch': alg_bytes,
+                         'kernel_ms': stage.get('fit_cols'),
+                         'step_algorithmic_bytes': step_bytes,
+                         'step_frac': step_bytes / (ms / 1e3) / 1e9 / peak},
+        }
+        tr = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tr):
+            try:
+                out['roofline']['traffic'] = json.load(open(tr)).get(args.workload, {}).get('fit_col_kernel')
+            except Exception:
+                pass
+        if world == 1 and not args.no_cpu_baseline:
+            v, dt, s, cores = cpu_port_mpix(args.workload, args.cpu_sample)
+            out['cpu_baseline'] = {'value': v, 'unit': 'Mpix/s', 'cores': cores, 'kind': 'port', 'seconds': dt,
+                                   'sample': '%dx%d crop of the same pair, same KerHW/orders, fp64 NumPy port of the '
+                                             'reference NumPy backend (oracle/sfft_oracle.py)' % (s, s)}
+        else:
+            out['cpu_baseline'] = None
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,131 @@
+/*
+ * sfft_b200.h -- C ABI of libsfft_b200.so, the B200 (sm_100a) SFFT subtraction core.
+ *
+ * The reference (thomasvrussell/sfft @ fa820e8) has no FFI for this path: its boundary is
+ * Python and the backend is picked by the string BACKEND_4SUBTRACT in {'Cupy','Numpy'}
+ * (sfft/sfftcore/SFFTConfigure.py:1387-1395, sfft/sfftcore/SFFTSubtract.py:828-835).
+ * These entry points are what a third backend branch in those two dispatchers binds with
+ * ctypes.  Plain pointers and sizes only; no torch / cupy types.
+ *
+ * Conventions
+ *   - images are C-contiguous (N0, N1) arrays, N1 fastest, exactly the arrays the reference
+ *     hands to ElementalSFFTSubtract.ESS (i.e. FITS data after the `.T`,
+ *     sfft/CustomizedPacket.py:93-96);
+ *   - `memkind` says where a caller buffer lives, `dtype` what it holds;
+ *   - every function returns 0 on success and a negative SFFTB_E* code on failure;
+ *     sfftb_last_error() returns a thread-local message the Python shim re-raises as
+ *     Exception('MeLOn ERROR: ...') like the reference does;
+ *   - a plan is bound to one device and one stream and is not re-entrant; different plans
+ *     may be driven concurrently from different host threads (the one-thread-per-GPU model
+ *     of sfft/MultiEasySparsePacket.py:510-514, 937-940).  Every entry point sets the
+ *     plan's device itself.
+ */
+#ifndef SFFT_B200_H
+#define SFFT_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFFTB_VERSION 100
+
+#define SFFTB_OK            0
+#define SFFTB_EINVAL       -1   /* bad argument / unsupported configuration */
+#define SFFTB_ECUDA        -2   /* CUDA runtime error */
+#define SFFTB_ESINGULAR    -3   /* normal matrix not factorisable (numpy.linalg.LinAlgError analogue) */
+#define SFFTB_ENOTFINITE   -4   /* non-finite value reached the solver (lu_factor check_finite analogue,
+                                   sfft/sfftcore/SFFTSubtract.py:15-23) */
+#define SFFTB_ESTATE       -5   /* call sequence error (e.g. export before any fit) */
+
+#define SFFTB_MEM_HOST      0
+#define SFFTB_MEM_DEVICE    1
+
+#define SFFTB_F64           0
+#define SFFTB_F32           1
+
+/* storage precision of the intermediate spectra in HBM (all arithmetic is fp64 either way) */
+#define SFFTB_STORE_F64     0
+#define SFFTB_STORE_F32     1
+
+typedef struct sfftb_plan sfftb_plan;
+
+/* Plays the role of the arguments of SingleSFFTConfigure.SSC
+ * (sfft/sfftcore/SFFTConfigure.py:1371-1395: NX, NY, KerHW, KerPolyOrder, BGPolyOrder, ConstPhotRatio). */
+typedef struct sfftb_config {
+    int device;            /* CUDA ordinal (CUDA_DEVICE_4SUBTRACT, sfft/CustomizedPacket.py:128-131) */
+    int N0, N1;            /* image shape (NX, NY) */
+    int w0, w1;            /* kernel half widths (KerHW on both axes in sfftcore) */
+    int DK, DB;            /* KerPolyOrder, BGPolyOrder: 0..3 (SFFTConfigure.py:19-28) */
+    int const_phot_ratio;  /* ConstPhotRatio */
+    int storage;           /* SFFTB_STORE_F64 | SFFTB_STORE_F32 */
+    int fold;              /* column-pass fold factor V (0 = choose automatically) */
+    int reserved[6];       /* must be zero */
+} sfftb_config;
+
+/* Sizes derived exactly as SFFTParam_dict (SFFTConfigure.py:35-75). */
+typedef struct sfftb_dims {
+    int N0, N1, w0, w1, DK, DB, L0, L1, Fab, Fij, Fpq, Fijab, NEQ, NEQ_FSfree;
+    int fold, sub_len;     /* V and M = N0 / V actually used by the column pass */
+} sfftb_dims;
+
+int  sfftb_version(void);
+const char* sfftb_last_error(void);
+
+/* SSC: build the plan (tables, workspaces).  Replaces SingleSFFTConfigure.SSC's kernel JIT
+ * (SFFTConfigure.py:9-817). */
+int  sfftb_plan_create(sfftb_plan** out, const sfftb_config* cfg);
+int  sfftb_plan_destroy(sfftb_plan* plan);
+int  sfftb_plan_dims(const sfftb_plan* plan, sfftb_dims* out);
+/* Run all work of this plan on `cuda_stream` (a cudaStream_t; NULL = the plan's own stream). */
+int  sfftb_plan_set_stream(sfftb_plan* plan, void* cuda_stream);
+int  sfftb_plan_sync(sfftb_plan* plan);
+
+/* ESS(SFFTSolution=None, Subtract=False): fit the kernel + background coefficients
+ * (SFFTSubtract.py:10-412 / 479-752).  `solution` receives NEQ doubles. */
+int  sfftb_fit(sfftb_plan* plan, const void* PixA_I, const void* PixA_J, int img_memkind, int img_dtype,
+               double* solution, int sol_memkind);
+
+/* ESS(SFFTSolution=solution, Subtract=True): Fourier-space kernel apply + inverse transform
+ * (SFFTSubtract.py:429-461 / 754-807).  `diff` receives N0*N1 values of `diff_dtype`. */
+int  sfftb_apply(sfftb_plan* plan, const void* PixA_I, const void* PixA_J, int img_memkind, int img_dtype,
+                 const double* solution, int sol_memkind, void* diff, int diff_memkind, int diff_dtype);
+
+/* GeneralSFFTSubtract.GSS without the contamination branch (SFFTSubtract.py:841-904 / 1373-1430):
+ * fit on (mI, mJ), apply to (I, J), no host synchronisation in between. */
+int  sfftb_gss(sfftb_plan* plan, const void* PixA_I, const void* PixA_J, const void* PixA_mI, const void* PixA_mJ,
+               int img_memkind, int img_dtype, double* solution, int sol_memkind,
+               void* diff, int diff_memkind, int diff_dtype);
+
+/* Parity hook: the full (NEQ x NEQ) LHMAT and (NEQ) RHb of the last fit, before stripe removal,
+ * in the reference's layout (what FillLS_* produce, SFFTSubtract.py:244-380).  Host pointers. */
+int  sfftb_export_normal_eq(sfftb_plan* plan, double* LHMAT, double* RHb);
+
+/* Device-event stage timings of the last fit/apply, milliseconds.
+ * ms[0] row spectra (fit), [1] column pass (fit), [2] lag reductions + fill, [3] solve,
+ * [4] row spectra (apply), [5] column pass (apply), [6] inverse rows.  Enabled by sfftb_plan_set_timing. */
+int  sfftb_plan_set_timing(sfftb_plan* plan, int enable);
+int  sfftb_timings(sfftb_plan* plan, float* ms, int n);
+
+/* Which factorisation the last fit used: 1 = Cholesky, 2 = pivoted LU fallback. */
+int  sfftb_last_solver(const sfftb_plan* plan);
+
+/* Number of kernel launches issued by this plan since creation (bench.py's gpu_launches). */
+long long sfftb_launch_count(const sfftb_plan* plan);
+
+/* Debug / unit-test hooks (used by tests/ only). */
+/* batched 1-D complex FFT of `nbatch` rows of length n through the in-shared-memory engine;
+ * host pointers, interleaved re/im doubles; sign = -1 forward, +1 unnormalised inverse. */
+int  sfftb_dbg_fft1d(int device, int n, int nbatch, int sign, const double* in, double* out);
+/* row spectra of the last call as stored in HBM: out[(j*NH + k1)*N0 + r] complex128 (host), j = 0..DK for
+ * which = 0 (I planes), single plane for which = 1 (J). */
+int  sfftb_dbg_row_spectra(sfftb_plan* plan, int which, double* out);
+/* lag tables of the last fit: R (npairs, 4w0+1, 4w1+1), RJ (Fij, 2w0+1, 2w1+1), RT (Fij, Fpq, 2w0+1, 2w1+1),
+ * RJT (Fpq); any pointer may be NULL. */
+int  sfftb_dbg_lag_tables(sfftb_plan* plan, double* R, double* RJ, double* RT, double* RJT);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

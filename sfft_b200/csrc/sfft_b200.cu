@@ -1,0 +1,800 @@
+// sfft_b200.cu -- plan management and the C ABI of libsfft_b200.so (see include/sfft_b200.h).
+#include "../../include/sfft_b200.h"
+#include "common.cuh"
+#include "fft_smem.cuh"
+#include "kernels_row.cuh"
+#include "kernels_fit.cuh"
+#include "kernels_solve.cuh"
+#include "kernels_apply.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <algorithm>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(SFFTB_ECUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
+    } while (0)
+
+#define CKL(p)                                                                                           \
+    do {                                                                                                 \
+        (p)->launches++;                                                                                 \
+        cudaError_t e_ = cudaGetLastError();                                                             \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(SFFTB_ECUDA, "kernel launch failed: %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+enum { EV_START = 0, EV_ROWS, EV_COL, EV_RED, EV_SOLVE, EV_A0, EV_AROWS, EV_ACOL, EV_AINV, EV_COUNT };
+
+struct sfftb_plan {
+    sfftb_config cfg;
+    sfftb_dims d;
+    int device;
+    int nsm;
+    size_t max_smem;
+    cudaStream_t stream, own_stream;
+    // tables
+    cd *tw0, *tw1, *twMf, *twMa, *twH, *Q;
+    double* PHI;
+    int *idxmap, *ident;
+    // workspaces
+    void *gI, *gJ;               // transposed row spectra (storage type); gJ doubles as the FDIFF column buffer
+    void *stA, *stB;             // device staging for host images / host diff
+    cd *kap, *lam, *nuJ;
+    double *R, *RJ, *RT, *RJT;
+    double *Aug, *sc, *diagU, *sol;
+    double* exportbuf;
+    int ld, nsolve;
+    int* info;                   // device: [0] cholesky pivot, [1] non-finite, [2] lu pivot
+    int* info_h;                 // pinned
+    // kernel arguments
+    ColArgs cfit, capp;
+    RowArgs row;
+    RowInvArgs rinv;
+    ReduceArgs red;
+    PolyReduceArgs pred;
+    FillArgs fill;
+    size_t smem_fit, smem_app, smem_row;
+    int grid_fit, grid_app;
+    int nrowsK, nrowsL;
+    // state
+    cudaEvent_t ev[EV_COUNT];
+    int timing;
+    float ms[7];
+    long long launches;
+    int last_solver;
+    int have_fit;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+static bool make_fft_desc(int n, FftDesc* fd) {
+    static const int radices[] = {8, 4, 2, 3, 5, 7, 11, 13};
+    memset(fd, 0, sizeof *fd);
+    fd->n = n;
+    int m = n;
+    for (int R : radices) {
+        while (m % R == 0 && m > 1) {
+            if (fd->ns >= SFFTB_MAX_STAGES) return false;
+            fd->radix[fd->ns++] = R;
+            m /= R;
+        }
+    }
+    return m == 1;
+}
+
+static bool fft_fits_threads(const FftDesc& fd, int nthr) {
+    for (int s = 0; s < fd.ns; ++s) {
+        const int R = fd.radix[s];
+        const int mb = (16 / R) > 0 ? (16 / R) : 1;
+        if (fd.n / R > mb * nthr) return false;
+    }
+    return true;
+}
+
+static int upload_twiddles(int n, cd** out) {
+    std::vector<cd> h((size_t)n);
+    const long double tp = 6.283185307179586476925286766559005768L;
+    for (int e = 0; e < n; ++e) {
+        const long double ang = tp * (long double)e / (long double)n;
+        h[e].x = (double)cosl(ang);
+        h[e].y = (double)(-sinl(ang));
+    }
+    CK(cudaMalloc(out, sizeof(cd) * (size_t)n));
+    CK(cudaMemcpy(*out, h.data(), sizeof(cd) * (size_t)n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int init_generic_radix_tables() {
+    const int rad[4] = {5, 7, 11, 13};
+    double2 h[4][16];
+    memset(h, 0, sizeof h);
+    const long double tp = 6.283185307179586476925286766559005768L;
+    for (int k = 0; k < 4; ++k)
+        for (int q = 0; q < rad[k]; ++q) {
+            const long double ang = tp * q / rad[k];
+            h[k][q].x = (double)cosl(ang);
+            h[k][q].y = (double)(-sinl(ang));
+        }
+    CK(cudaMemcpyToSymbol(c_wgen, h, sizeof h));
+    return 0;
+}
+
+// Q[q][k1] = sum_c cy(c)^q exp(-2 pi i k1 c / N1): one warp per output
+__global__ void qtable_kernel(int N1, int NH, int nq, const cd* __restrict__ tw1, cd* __restrict__ Q) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (gw >= nq * NH) return;
+    const int q = gw / NH, k1 = gw - q * NH;
+    double sx = 0.0, sy = 0.0;
+    for (int c = lane; c < N1; c += 32) {
+        const cd w = tw1[(int)(((long long)k1 * c) % N1)];
+        const double v = ipow((c + 1) / (double)N1, q);
+        sx = fma(v, w.x, sx);
+        sy = fma(v, w.y, sy);
+    }
+    sx = warp_sum(sx);
+    sy = warp_sum(sy);
+    if (lane == 0) Q[(size_t)q * NH + k1] = cmake(sx, sy);
+}
+
+__global__ void dbg_fft_kernel(FftDesc fd, const cd* __restrict__ tw, const cd* __restrict__ in, cd* __restrict__ out,
+                               int nbatch, int ppc, int pitch, double sgn) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd* buf = reinterpret_cast<cd*>(smem_raw);
+    const int b0 = blockIdx.x * ppc;
+    const int np = min(ppc, nbatch - b0);
+    for (int idx = threadIdx.x; idx < np * fd.n; idx += blockDim.x) {
+        const int p = idx / fd.n, e = idx - p * fd.n;
+        buf[(size_t)p * pitch + e] = in[(size_t)(b0 + p) * fd.n + e];
+    }
+    __syncthreads();
+    fft_planes(buf, pitch, np, fd, tw, sgn);
+    for (int idx = threadIdx.x; idx < np * fd.n; idx += blockDim.x) {
+        const int p = idx / fd.n, e = idx - p * fd.n;
+        out[(size_t)(b0 + p) * fd.n + e] = buf[(size_t)p * pitch + e];
+    }
+}
+
+template <typename T>
+static int set_smem(T kernel, size_t bytes) {
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+static void fill_col_common(ColArgs& c, const sfftb_plan* p) {
+    const sfftb_dims& d = p->d;
+    memset(&c, 0, sizeof c);
+    c.N0 = d.N0; c.N1 = d.N1; c.NH = d.N1 / 2 + 1;
+    c.DK = d.DK; c.DB = d.DB; c.Fij = d.Fij; c.Fpq = d.Fpq; c.nj = d.DK + 1;
+    c.w0 = d.w0; c.w1 = d.w1;
+    c.npairs = d.Fij * (d.Fij + 1) / 2;
+    c.nl0 = 4 * d.w0 + 1; c.nlj0 = 2 * d.w0 + 1;
+    memset(c.plane_of, 0xff, sizeof c.plane_of);
+    int A = 0;
+    for (int i = 0; i <= d.DK; ++i)
+        for (int j = 0; j <= d.DK - i; ++j) { c.pl_i[A] = (unsigned char)i; c.pl_j[A] = (unsigned char)j; c.plane_of[i][j] = (unsigned char)A; ++A; }
+    int q = 0;
+    for (int a = 0; a < d.Fij; ++a)
+        for (int b = a; b < d.Fij; ++b) { c.pairA[q] = (unsigned char)a; c.pairB[q] = (unsigned char)b; ++q; }
+    c.tw0 = p->tw0;
+}
+
+static size_t fit_smem_bytes(const ColArgs& c, int PB) {
+    const size_t nacc = (size_t)c.npairs * c.nl0 + (size_t)c.Fij * c.nlj0;
+    return sizeof(cd) * ((size_t)(c.Fij + 1 + PB) * c.pitch + nacc + (size_t)(c.nj + 1) * SFFTB_MAXE + 16 * SFFTB_MAXE);
+}
+static size_t app_smem_bytes(const ColArgs& c) {
+    return sizeof(cd) * ((size_t)(2 * c.Fij + 1) * c.pitch + c.N0 + (size_t)c.Fij * (2 * c.w0 + 1) + c.Fij);
+}
+
+static int plan_free(sfftb_plan* p) {
+    if (!p) return 0;
+    cudaSetDevice(p->device);
+    void* ptrs[] = {p->tw0, p->tw1, p->twMf, p->twMa, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
+                    p->kap, p->lam, p->nuJ, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    if (p->info_h) cudaFreeHost(p->info_h);
+    for (int k = 0; k < EV_COUNT; ++k) if (p->ev[k]) cudaEventDestroy(p->ev[k]);
+    if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    delete p;
+    return 0;
+}
+
+extern "C" int sfftb_version(void) { return SFFTB_VERSION; }
+extern "C" const char* sfftb_last_error(void) { return g_err.c_str(); }
+
+static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
+    p->cfg = *cfg;
+    p->device = cfg->device;
+    CK(cudaSetDevice(p->device));
+    int v = 0;
+    CK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, p->device)); p->nsm = v;
+    CK(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device)); p->max_smem = (size_t)v;
+    CK(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
+    p->stream = p->own_stream;
+    for (int k = 0; k < EV_COUNT; ++k) CK(cudaEventCreate(&p->ev[k]));
+    if (init_generic_radix_tables()) return SFFTB_ECUDA;
+
+    sfftb_dims& d = p->d;
+    d.N0 = cfg->N0; d.N1 = cfg->N1; d.w0 = cfg->w0; d.w1 = cfg->w1; d.DK = cfg->DK; d.DB = cfg->DB;
+    d.L0 = 2 * d.w0 + 1; d.L1 = 2 * d.w1 + 1; d.Fab = d.L0 * d.L1;
+    d.Fij = (d.DK + 1) * (d.DK + 2) / 2; d.Fpq = (d.DB + 1) * (d.DB + 2) / 2;
+    d.Fijab = d.Fij * d.Fab; d.NEQ = d.Fijab + d.Fpq;
+    d.NEQ_FSfree = cfg->const_phot_ratio ? d.NEQ - (d.Fij - 1) : d.NEQ;
+    const int N0 = d.N0, N1 = d.N1, NH = N1 / 2 + 1;
+    const size_t csz = cfg->storage == SFFTB_STORE_F32 ? sizeof(float2) : sizeof(double2);
+
+    // ---- twiddle tables ----
+    if (upload_twiddles(N0, &p->tw0)) return SFFTB_ECUDA;
+    if (upload_twiddles(N1, &p->tw1)) return SFFTB_ECUDA;
+
+    // ---- row pass geometry ----
+    RowArgs& r = p->row;
+    memset(&r, 0, sizeof r);
+    r.N0 = N0; r.N1 = N1; r.NH = NH;
+    r.packed = (N1 % 2 == 0) ? 1 : 0;
+    r.H = r.packed ? N1 / 2 : N1;
+    if (!make_fft_desc(r.H, &r.fd) || !fft_fits_threads(r.fd, 512))
+        return fail(SFFTB_EINVAL, "unsupported image width N1=%d: row transform length %d needs prime factors <= 13", N1, r.H);
+    r.pitch = r.H + 1;
+    int RB = env_int("SFFTB_RB", 8);
+    while (RB > 1 && ((size_t)RB * r.pitch * sizeof(cd) > p->max_smem || RB > N0)) RB >>= 1;
+    if ((size_t)RB * r.pitch * sizeof(cd) > p->max_smem)
+        return fail(SFFTB_EINVAL, "image width N1=%d too large for the shared-memory row transform", N1);
+    r.RB = RB;
+    p->smem_row = (size_t)RB * r.pitch * sizeof(cd);
+    if (upload_twiddles(r.H, &p->twH)) return SFFTB_ECUDA;
+    r.twH = p->twH; r.tw1 = p->tw1;
+    p->rinv.r = r;
+    p->rinv.scale = (r.packed ? 2.0 : 1.0) / ((double)N0 * (double)N1);
+    p->rinv.DB = d.DB; p->rinv.Fpq = d.Fpq;
+    {
+        int k = 0;
+        for (int pp = 0; pp <= d.DB; ++pp)
+            for (int q = 0; q <= d.DB - pp; ++q) { p->rinv.p_of[k] = (unsigned char)pp; p->rinv.q_of[k] = (unsigned char)q; ++k; }
+    }
+
+    // ---- column pass geometry: fold factor V, slice length M ----
+    fill_col_common(p->cfit, p);
+    fill_col_common(p->capp, p);
+    const int Mmax = env_int("SFFTB_MMAX", 512);
+    const int ntot = p->cfit.npairs + d.Fij;
+    bool okf = false, oka = false;
+    for (int V = 1; V <= N0 && !(okf && oka); ++V) {
+        if (N0 % V) continue;
+        const int M = N0 / V;
+        if (cfg->fold > 0 && V != cfg->fold) continue;
+        if (cfg->fold <= 0 && M > Mmax) continue;
+        FftDesc fd;
+        if (!make_fft_desc(M, &fd) || !fft_fits_threads(fd, NT_COL)) continue;
+        if (!okf) {
+            ColArgs& c = p->cfit;
+            c.V = V; c.M = M; c.pitch = M + 1; c.fd = fd;
+            int PB = env_int("SFFTB_PB", ntot);
+            if (PB > ntot) PB = ntot;
+            while (PB > 1 && fit_smem_bytes(c, PB) > p->max_smem) --PB;
+            if (fit_smem_bytes(c, PB) <= p->max_smem) { c.PB = PB; okf = true; }
+        }
+        if (!oka) {
+            ColArgs& c = p->capp;
+            c.V = V; c.M = M; c.pitch = M + 1; c.fd = fd; c.PB = 0;
+            if (app_smem_bytes(c) <= p->max_smem) oka = true;
+        }
+    }
+    if (!okf || !oka)
+        return fail(SFFTB_EINVAL, "unsupported image height N0=%d (fold=%d): no slice length with prime factors <= 13 fits shared memory",
+                    N0, cfg->fold);
+    d.fold = p->cfit.V; d.sub_len = p->cfit.M;
+    if (upload_twiddles(p->cfit.M, &p->twMf)) return SFFTB_ECUDA;
+    if (upload_twiddles(p->capp.M, &p->twMa)) return SFFTB_ECUDA;
+    p->cfit.twM = p->twMf; p->capp.twM = p->twMa;
+    p->smem_fit = fit_smem_bytes(p->cfit, p->cfit.PB);
+    p->smem_app = app_smem_bytes(p->capp);
+
+    // ---- workspaces ----
+    CK(cudaMalloc(&p->gI, csz * (size_t)(d.DK + 1) * NH * N0));
+    CK(cudaMalloc(&p->gJ, csz * (size_t)NH * N0));
+    CK(cudaMalloc(&p->stA, sizeof(double) * (size_t)N0 * N1));
+    CK(cudaMalloc(&p->stB, sizeof(double) * (size_t)N0 * N1));
+    p->nrowsK = p->cfit.npairs * p->cfit.nl0 + d.Fij * p->cfit.nlj0;
+    p->nrowsL = d.Fij * (d.DB + 1) * p->cfit.nlj0;
+    CK(cudaMalloc(&p->kap, sizeof(cd) * (size_t)p->nrowsK * NH));
+    CK(cudaMalloc(&p->lam, sizeof(cd) * (size_t)p->nrowsL * NH));
+    CK(cudaMalloc(&p->nuJ, sizeof(cd) * (size_t)(d.DB + 1) * NH));
+    const int nl0 = 4 * d.w0 + 1, nl1 = 4 * d.w1 + 1, nlj0 = 2 * d.w0 + 1, nlj1 = 2 * d.w1 + 1;
+    CK(cudaMalloc(&p->R, sizeof(double) * (size_t)p->cfit.npairs * nl0 * nl1));
+    CK(cudaMalloc(&p->RJ, sizeof(double) * (size_t)d.Fij * nlj0 * nlj1));
+    CK(cudaMalloc(&p->RT, sizeof(double) * (size_t)d.Fij * d.Fpq * nlj0 * nlj1));
+    CK(cudaMalloc(&p->RJT, sizeof(double) * (size_t)d.Fpq));
+    p->nsolve = d.NEQ_FSfree;
+    p->ld = p->nsolve + 1;
+    CK(cudaMalloc(&p->Aug, sizeof(double) * (size_t)(p->nsolve + 1) * p->ld));
+    CK(cudaMalloc(&p->sc, sizeof(double) * (size_t)p->nsolve));
+    CK(cudaMalloc(&p->diagU, sizeof(double) * (size_t)p->nsolve));
+    CK(cudaMalloc(&p->sol, sizeof(double) * (size_t)d.NEQ));
+    CK(cudaMalloc(&p->info, sizeof(int) * 4));
+    CK(cudaMallocHost(&p->info_h, sizeof(int) * 4));
+    memset(p->info_h, 0, sizeof(int) * 4);
+
+    // ---- index maps (forbidden stripes: SFFTSubtract.py:82-90) ----
+    {
+        std::vector<int> ident(d.NEQ), idx;
+        for (int k = 0; k < d.NEQ; ++k) ident[k] = k;
+        for (int k = 0; k < d.NEQ; ++k) {
+            bool forbidden = false;
+            if (cfg->const_phot_ratio && k < d.Fijab) {
+                const int A = k / d.Fab, ab = k % d.Fab;
+                forbidden = (A >= 1) && (ab == d.w0 * d.L1 + d.w1);
+            }
+            if (!forbidden) idx.push_back(k);
+        }
+        if ((int)idx.size() != p->nsolve) return fail(SFFTB_EINVAL, "internal: index map size mismatch");
+        CK(cudaMalloc(&p->idxmap, sizeof(int) * idx.size()));
+        CK(cudaMalloc(&p->ident, sizeof(int) * ident.size()));
+        CK(cudaMemcpy(p->idxmap, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(p->ident, ident.data(), sizeof(int) * ident.size(), cudaMemcpyHostToDevice));
+    }
+
+    // ---- Phi block: sum_x T_p'q' T_pq from power sums ----
+    {
+        std::vector<long double> sx(2 * d.DB + 1, 0.0L), sy(2 * d.DB + 1, 0.0L);
+        for (int e = 0; e <= 2 * d.DB; ++e) {
+            for (int rr = 0; rr < N0; ++rr) sx[e] += powl((long double)(rr + 1) / N0, e);
+            for (int c = 0; c < N1; ++c) sy[e] += powl((long double)(c + 1) / N1, e);
+        }
+        std::vector<double> phi((size_t)d.Fpq * d.Fpq);
+        for (int a = 0; a < d.Fpq; ++a)
+            for (int b = 0; b < d.Fpq; ++b)
+                phi[(size_t)a * d.Fpq + b] = (double)(sx[p->rinv.p_of[a] + p->rinv.p_of[b]] * sy[p->rinv.q_of[a] + p->rinv.q_of[b]]);
+        CK(cudaMalloc(&p->PHI, sizeof(double) * phi.size()));
+        CK(cudaMemcpy(p->PHI, phi.data(), sizeof(double) * phi.size(), cudaMemcpyHostToDevice));
+    }
+
+    // ---- Q table ----
+    CK(cudaMalloc(&p->Q, sizeof(cd) * (size_t)(d.DB + 1) * NH));
+    {
+        const int nwarps = (d.DB + 1) * NH;
+        qtable_kernel<<<(nwarps * 32 + 255) / 256, 256, 0, p->stream>>>(N1, NH, d.DB + 1, p->tw1, p->Q);
+        CKL(p);
+    }
+
+    // ---- reduction / fill arguments ----
+    ReduceArgs& ra = p->red;
+    ra.N1 = N1; ra.NH = NH; ra.w1 = d.w1; ra.nOm = p->cfit.npairs * nl0; ra.nrows = p->nrowsK; ra.tw1 = p->tw1;
+    PolyReduceArgs& pa = p->pred;
+    memset(&pa, 0, sizeof pa);
+    pa.N1 = N1; pa.NH = NH; pa.w1 = d.w1; pa.DB = d.DB; pa.Fpq = d.Fpq; pa.Fij = d.Fij;
+    pa.nlj0 = nlj0; pa.nlj1 = nlj1; pa.nrowsL = p->nrowsL; pa.tw1 = p->tw1; pa.Q = p->Q;
+    memset(pa.pq_of, 0xff, sizeof pa.pq_of);
+    for (int k = 0; k < d.Fpq; ++k) pa.pq_of[p->rinv.p_of[k]][p->rinv.q_of[k]] = (signed char)k;
+    FillArgs& f = p->fill;
+    f.Fij = d.Fij; f.Fpq = d.Fpq; f.Fab = d.Fab; f.Fijab = d.Fijab; f.L0 = d.L0; f.L1 = d.L1; f.w0 = d.w0; f.w1 = d.w1;
+    f.nl0 = nl0; f.nl1 = nl1; f.nlj0 = nlj0; f.nlj1 = nlj1;
+    const double N = (double)N0 * (double)N1;
+    f.invN = 1.0 / N; f.invN2 = 1.0 / (N * N); f.invN3 = 1.0 / (N * N * N);
+    f.R = p->R; f.RJ = p->RJ; f.RT = p->RT; f.RJT = p->RJT; f.PHI = p->PHI;
+
+    // ---- kernel attributes ----
+    const bool f32 = cfg->storage == SFFTB_STORE_F32;
+    if (f32) {
+        if (set_smem(fit_col_kernel<float2>, p->smem_fit) || set_smem(apply_col_kernel<float2>, p->smem_app)) return SFFTB_ECUDA;
+        if (set_smem(row_fwd_kernel<float, float2>, p->smem_row) || set_smem(row_fwd_kernel<double, float2>, p->smem_row)) return SFFTB_ECUDA;
+        if (set_smem(row_inv_kernel<float2, float>, p->smem_row) || set_smem(row_inv_kernel<float2, double>, p->smem_row)) return SFFTB_ECUDA;
+    } else {
+        if (set_smem(fit_col_kernel<double2>, p->smem_fit) || set_smem(apply_col_kernel<double2>, p->smem_app)) return SFFTB_ECUDA;
+        if (set_smem(row_fwd_kernel<float, double2>, p->smem_row) || set_smem(row_fwd_kernel<double, double2>, p->smem_row)) return SFFTB_ECUDA;
+        if (set_smem(row_inv_kernel<double2, float>, p->smem_row) || set_smem(row_inv_kernel<double2, double>, p->smem_row)) return SFFTB_ECUDA;
+    }
+    const size_t red_smem = sizeof(cd) * (size_t)NH;
+    if (set_smem(lag_reduce_kernel, red_smem) || set_smem(poly_reduce_kernel, red_smem)) return SFFTB_ECUDA;
+    const size_t bs_smem = sizeof(double) * ((size_t)p->nsolve + CH_NB + CH_NB * (CH_NB + 1));
+    if (bs_smem > p->max_smem) return fail(SFFTB_EINVAL, "NEQ=%d too large for the back-substitution kernel", d.NEQ);
+    if (set_smem(chol_backsolve_kernel, bs_smem)) return SFFTB_ECUDA;
+    if (set_smem(lu_solve_kernel, sizeof(double) * (size_t)p->nsolve)) return SFFTB_ECUDA;
+
+    int occ = 1;
+    if (f32) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_col_kernel<float2>, NT_COL, p->smem_fit));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_col_kernel<double2>, NT_COL, p->smem_fit));
+    p->grid_fit = std::min(NH, std::max(1, occ) * p->nsm);
+    if (f32) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_col_kernel<float2>, NT_COL, p->smem_app));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_col_kernel<double2>, NT_COL, p->smem_app));
+    p->grid_app = std::min(NH, std::max(1, occ) * p->nsm);
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int sfftb_plan_create(sfftb_plan** out, const sfftb_config* cfg) {
+    if (!out || !cfg) return fail(SFFTB_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->N0 < 2 || cfg->N1 < 2) return fail(SFFTB_EINVAL, "image shape (%d, %d) too small", cfg->N0, cfg->N1);
+    if (cfg->DK < 0 || cfg->DK > 3) return fail(SFFTB_EINVAL, "Input KerPolyOrder should be 0/1/2/3!");
+    if (cfg->DB < 0 || cfg->DB > 3) return fail(SFFTB_EINVAL, "Input BGPolyOrder should be 0/1/2/3!");
+    if (cfg->w0 < 0 || cfg->w1 < 0 || 2 * cfg->w0 + 1 > cfg->N0 || 2 * cfg->w1 + 1 > cfg->N1)
+        return fail(SFFTB_EINVAL, "kernel half width (%d, %d) does not fit the image (%d, %d)", cfg->w0, cfg->w1, cfg->N0, cfg->N1);
+    if (cfg->storage != SFFTB_STORE_F64 && cfg->storage != SFFTB_STORE_F32) return fail(SFFTB_EINVAL, "bad storage precision");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(SFFTB_EINVAL, "CUDA device %d not available (%d visible)", cfg->device, ndev);
+    sfftb_plan* p = new sfftb_plan();
+    memset((void*)p, 0, sizeof *p);
+    const int rc = plan_create_impl(p, cfg);
+    if (rc) { std::string keep = g_err; plan_free(p); g_err = keep; return rc; }
+    *out = p;
+    return 0;
+}
+
+extern "C" int sfftb_plan_destroy(sfftb_plan* p) { return plan_free(p); }
+
+extern "C" int sfftb_plan_dims(const sfftb_plan* p, sfftb_dims* out) {
+    if (!p || !out) return fail(SFFTB_EINVAL, "null argument");
+    *out = p->d;
+    return 0;
+}
+
+extern "C" int sfftb_plan_set_stream(sfftb_plan* p, void* s) {
+    if (!p) return fail(SFFTB_EINVAL, "null plan");
+    p->stream = s ? (cudaStream_t)s : p->own_stream;
+    return 0;
+}
+
+extern "C" int sfftb_plan_sync(sfftb_plan* p) {
+    if (!p) return fail(SFFTB_EINVAL, "null plan");
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int sfftb_plan_set_timing(sfftb_plan* p, int enable) {
+    if (!p) return fail(SFFTB_EINVAL, "null plan");
+    p->timing = enable;
+    return 0;
+}
+
+extern "C" long long sfftb_launch_count(const sfftb_plan* p) { return p ? p->launches : 0; }
+extern "C" int sfftb_last_solver(const sfftb_plan* p) { return p ? p->last_solver : 0; }
+
+#define EVREC(p, k) do { if ((p)->timing) CK(cudaEventRecord((p)->ev[k], (p)->stream)); } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+static int stage_in(sfftb_plan* p, const void* src, int memkind, int dtype, void* staging, const void** dev) {
+    if (!src) return fail(SFFTB_EINVAL, "null image pointer");
+    if (dtype != SFFTB_F64 && dtype != SFFTB_F32) return fail(SFFTB_EINVAL, "bad image dtype");
+    if (memkind == SFFTB_MEM_DEVICE) { *dev = src; return 0; }
+    if (memkind != SFFTB_MEM_HOST) return fail(SFFTB_EINVAL, "bad memkind");
+    const size_t bytes = (size_t)p->d.N0 * p->d.N1 * (dtype == SFFTB_F64 ? 8 : 4);
+    CK(cudaMemcpyAsync(staging, src, bytes, cudaMemcpyHostToDevice, p->stream));
+    *dev = staging;
+    return 0;
+}
+
+template <typename TSt>
+static int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj) {
+    const int grid = (p->d.N0 + p->row.RB - 1) / p->row.RB;
+    if (dtype == SFFTB_F64)
+        row_fwd_kernel<double, TSt><<<grid, 512, p->smem_row, p->stream>>>(p->row, (const double*)img, out, nj);
+    else
+        row_fwd_kernel<float, TSt><<<grid, 512, p->smem_row, p->stream>>>(p->row, (const float*)img, out, nj);
+    CKL(p);
+    return 0;
+}
+
+static int run_cholesky(sfftb_plan* p) {
+    const int n = p->nsolve, ntot = n + 1;
+    for (int k0 = 0; k0 < n; k0 += CH_NB) {
+        const int kb = std::min(CH_NB, n - k0);
+        const int below = ntot - (k0 + kb);
+        const int gp = std::max(1, (below + 127) / 128);
+        chol_panel_kernel<<<gp, 128, 0, p->stream>>>(p->Aug, p->ld, ntot, n, k0, p->info);
+        CKL(p);
+        if (below > 0 && k0 + kb < n) {
+            const int nt = (below + 63) / 64;
+            chol_update_kernel<<<dim3(nt, nt), 256, 0, p->stream>>>(p->Aug, p->ld, ntot, n, k0);
+            CKL(p);
+        }
+    }
+    const size_t bs_smem = sizeof(double) * ((size_t)n + CH_NB + CH_NB * (CH_NB + 1));
+    chol_backsolve_kernel<<<1, 1024, bs_smem, p->stream>>>(p->Aug, p->ld, n, p->sc, p->idxmap, p->sol, p->d.NEQ);
+    CKL(p);
+    return 0;
+}
+
+static int fill_system(sfftb_plan* p) {
+    const int n = p->nsolve;
+    fill_diag_kernel<<<(n + 127) / 128, 128, 0, p->stream>>>(p->fill, p->idxmap, n, p->sc, p->info);
+    CKL(p);
+    dim3 blk(32, 8), grd((n + 1 + 31) / 32, (n + 1 + 7) / 8);
+    fill_matrix_kernel<<<grd, blk, 0, p->stream>>>(p->fill, p->idxmap, n, p->sc, p->Aug, p->ld, p->info);
+    CKL(p);
+    return 0;
+}
+
+static int run_lu(sfftb_plan* p) {
+    const int n = p->nsolve;
+    int occ = 0;
+    const size_t smem = sizeof(double) * (size_t)n;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lu_solve_kernel, 512, smem));
+    if (occ < 1) return fail(SFFTB_ECUDA, "LU fallback kernel cannot be made resident");
+    int grid = p->nsm;
+    double* A = p->Aug; int ld = p->ld; int nn = n; double* du = p->diagU; const double* sc = p->sc; const int* idx = p->idxmap;
+    double* sol = p->sol; int NEQ = p->d.NEQ; int* info = p->info;
+    void* args[] = {&A, &ld, &nn, &du, &sc, &idx, &sol, &NEQ, &info};
+    CK(cudaLaunchCooperativeKernel((void*)lu_solve_kernel, dim3(grid), dim3(512), args, smem, p->stream));
+    p->launches++;
+    return 0;
+}
+
+template <typename TSt>
+static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype) {
+    const sfftb_dims& d = p->d;
+    EVREC(p, EV_START);
+    if (launch_row_fwd<TSt>(p, dI, dtype, (TSt*)p->gI, d.DK + 1)) return SFFTB_ECUDA;
+    if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
+    EVREC(p, EV_ROWS);
+    fit_col_kernel<TSt><<<p->grid_fit, NT_COL, p->smem_fit, p->stream>>>(p->cfit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
+    CKL(p);
+    EVREC(p, EV_COL);
+    const size_t red_smem = sizeof(cd) * (size_t)(d.N1 / 2 + 1);
+    lag_reduce_kernel<<<p->nrowsK, 256, red_smem, p->stream>>>(p->red, p->kap, p->R, p->RJ);
+    CKL(p);
+    poly_reduce_kernel<<<p->nrowsL + d.DB + 1, 256, red_smem, p->stream>>>(p->pred, p->lam, p->nuJ, p->RT, p->RJT);
+    CKL(p);
+    CK(cudaMemsetAsync(p->info, 0, sizeof(int) * 4, p->stream));
+    if (fill_system(p)) return SFFTB_ECUDA;
+    EVREC(p, EV_RED);
+    if (run_cholesky(p)) return SFFTB_ECUDA;
+    EVREC(p, EV_SOLVE);
+    CK(cudaMemcpyAsync(p->info_h, p->info, sizeof(int) * 4, cudaMemcpyDeviceToHost, p->stream));
+    p->have_fit = 1;
+    p->last_solver = 1;
+    return 0;
+}
+
+// After a stream sync: inspect the solver flags; run the pivoted-LU fallback if Cholesky broke down.
+// Returns 0 (ok), 1 (fallback was run, solution replaced) or a negative error.
+static int check_solver(sfftb_plan* p) {
+    if (p->info_h[1]) return fail(SFFTB_ENOTFINITE, "array must not contain infs or NaNs (normal equations)");
+    if (p->info_h[0] == 0) return 0;
+    // Cholesky pivot not positive: refill and solve by LU with partial pivoting
+    CK(cudaMemsetAsync(p->info, 0, sizeof(int) * 4, p->stream));
+    if (fill_system(p)) return SFFTB_ECUDA;
+    if (run_lu(p)) return SFFTB_ECUDA;
+    CK(cudaMemcpyAsync(p->info_h, p->info, sizeof(int) * 4, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    p->last_solver = 2;
+    if (p->info_h[1]) return fail(SFFTB_ENOTFINITE, "array must not contain infs or NaNs (normal equations)");
+    if (p->info_h[2]) return fail(SFFTB_ESINGULAR, "Singular matrix (zero pivot at column %d of the normal equations)", p->info_h[2] - 1);
+    return 1;
+}
+
+template <typename TSt>
+static int apply_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, const double* dsol, void* ddiff, int diff_dtype) {
+    const sfftb_dims& d = p->d;
+    EVREC(p, EV_A0);
+    if (launch_row_fwd<TSt>(p, dI, dtype, (TSt*)p->gI, d.DK + 1)) return SFFTB_ECUDA;
+    if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
+    EVREC(p, EV_AROWS);
+    apply_col_kernel<TSt><<<p->grid_app, NT_COL, p->smem_app, p->stream>>>(p->capp, (const TSt*)p->gI, (const TSt*)p->gJ, dsol, p->tw1, (TSt*)p->gJ);
+    CKL(p);
+    EVREC(p, EV_ACOL);
+    const int grid = (d.N0 + p->row.RB - 1) / p->row.RB;
+    const double* bpq = dsol + d.Fijab;
+    if (diff_dtype == SFFTB_F64)
+        row_inv_kernel<TSt, double><<<grid, 512, p->smem_row, p->stream>>>(p->rinv, (const TSt*)p->gJ, bpq, (double*)ddiff);
+    else
+        row_inv_kernel<TSt, float><<<grid, 512, p->smem_row, p->stream>>>(p->rinv, (const TSt*)p->gJ, bpq, (float*)ddiff);
+    CKL(p);
+    EVREC(p, EV_AINV);
+    return 0;
+}
+
+static int collect_timings(sfftb_plan* p, bool fit, bool app) {
+    if (!p->timing) return 0;
+    if (fit) {
+        CK(cudaEventElapsedTime(&p->ms[0], p->ev[EV_START], p->ev[EV_ROWS]));
+        CK(cudaEventElapsedTime(&p->ms[1], p->ev[EV_ROWS], p->ev[EV_COL]));
+        CK(cudaEventElapsedTime(&p->ms[2], p->ev[EV_COL], p->ev[EV_RED]));
+        CK(cudaEventElapsedTime(&p->ms[3], p->ev[EV_RED], p->ev[EV_SOLVE]));
+    }
+    if (app) {
+        CK(cudaEventElapsedTime(&p->ms[4], p->ev[EV_A0], p->ev[EV_AROWS]));
+        CK(cudaEventElapsedTime(&p->ms[5], p->ev[EV_AROWS], p->ev[EV_ACOL]));
+        CK(cudaEventElapsedTime(&p->ms[6], p->ev[EV_ACOL], p->ev[EV_AINV]));
+    }
+    return 0;
+}
+
+extern "C" int sfftb_timings(sfftb_plan* p, float* ms, int n) {
+    if (!p || !ms) return fail(SFFTB_EINVAL, "null argument");
+    for (int k = 0; k < n && k < 7; ++k) ms[k] = p->ms[k];
+    return 0;
+}
+
+static int copy_out(sfftb_plan* p, void* dst, int memkind, const void* src_dev, size_t bytes) {
+    if (!dst) return 0;
+    CK(cudaMemcpyAsync(dst, src_dev, bytes, memkind == SFFTB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, p->stream));
+    return 0;
+}
+
+extern "C" int sfftb_fit(sfftb_plan* p, const void* I, const void* J, int memkind, int dtype, double* solution, int sol_memkind) {
+    if (!p) return fail(SFFTB_EINVAL, "null plan");
+    CK(cudaSetDevice(p->device));
+    const void *dI, *dJ;
+    int rc;
+    if ((rc = stage_in(p, I, memkind, dtype, p->stA, &dI))) return rc;
+    if ((rc = stage_in(p, J, memkind, dtype, p->stB, &dJ))) return rc;
+    rc = p->cfg.storage == SFFTB_STORE_F32 ? fit_device<float2>(p, dI, dJ, dtype) : fit_device<double2>(p, dI, dJ, dtype);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(p->stream));
+    if ((rc = check_solver(p)) < 0) return rc;
+    if ((rc = collect_timings(p, true, false))) return rc;
+    if ((rc = copy_out(p, solution, sol_memkind, p->sol, sizeof(double) * p->d.NEQ))) return rc;
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int sfftb_apply(sfftb_plan* p, const void* I, const void* J, int memkind, int dtype, const double* solution, int sol_memkind,
+                           void* diff, int diff_memkind, int diff_dtype) {
+    if (!p || !solution || !diff) return fail(SFFTB_EINVAL, "null argument");
+    if (diff_dtype != SFFTB_F64 && diff_dtype != SFFTB_F32) return fail(SFFTB_EINVAL, "bad diff dtype");
+    CK(cudaSetDevice(p->device));
+    const void *dI, *dJ;
+    int rc;
+    if ((rc = stage_in(p, I, memkind, dtype, p->stA, &dI))) return rc;
+    if ((rc = stage_in(p, J, memkind, dtype, p->stB, &dJ))) return rc;
+    const double* dsol = solution;
+    if (sol_memkind == SFFTB_MEM_HOST) {
+        CK(cudaMemcpyAsync(p->sol, solution, sizeof(double) * p->d.NEQ, cudaMemcpyHostToDevice, p->stream));
+        dsol = p->sol;
+    }
+    void* ddiff = diff_memkind == SFFTB_MEM_DEVICE ? diff : p->stA;   // stA is free again once the row pass has consumed it
+    rc = p->cfg.storage == SFFTB_STORE_F32 ? apply_device<float2>(p, dI, dJ, dtype, dsol, ddiff, diff_dtype)
+                                           : apply_device<double2>(p, dI, dJ, dtype, dsol, ddiff, diff_dtype);
+    if (rc) return rc;
+    if (diff_memkind == SFFTB_MEM_HOST) {
+        const size_t bytes = (size_t)p->d.N0 * p->d.N1 * (diff_dtype == SFFTB_F64 ? 8 : 4);
+        CK(cudaMemcpyAsync(diff, p->stA, bytes, cudaMemcpyDeviceToHost, p->stream));
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    return collect_timings(p, false, true);
+}
+
+extern "C" int sfftb_gss(sfftb_plan* p, const void* I, const void* J, const void* mI, const void* mJ, int memkind, int dtype,
+                         double* solution, int sol_memkind, void* diff, int diff_memkind, int diff_dtype) {
+    if (!p || !diff) return fail(SFFTB_EINVAL, "null argument");
+    if (diff_dtype != SFFTB_F64 && diff_dtype != SFFTB_F32) return fail(SFFTB_EINVAL, "bad diff dtype");
+    CK(cudaSetDevice(p->device));
+    const bool f32 = p->cfg.storage == SFFTB_STORE_F32;
+    const void *dI, *dJ;
+    int rc;
+    if ((rc = stage_in(p, mI, memkind, dtype, p->stA, &dI))) return rc;
+    if ((rc = stage_in(p, mJ, memkind, dtype, p->stB, &dJ))) return rc;
+    rc = f32 ? fit_device<float2>(p, dI, dJ, dtype) : fit_device<double2>(p, dI, dJ, dtype);
+    if (rc) return rc;
+    void* ddiff = diff_memkind == SFFTB_MEM_DEVICE ? diff : p->stA;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if ((rc = stage_in(p, I, memkind, dtype, p->stA, &dI))) return rc;
+        if ((rc = stage_in(p, J, memkind, dtype, p->stB, &dJ))) return rc;
+        rc = f32 ? apply_device<float2>(p, dI, dJ, dtype, p->sol, ddiff, diff_dtype) : apply_device<double2>(p, dI, dJ, dtype, p->sol, ddiff, diff_dtype);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(p->stream));
+        if (attempt == 1) break;
+        rc = check_solver(p);
+        if (rc < 0) return rc;
+        if (rc == 0) break;          // Cholesky was fine; rc == 1: solution replaced by the LU fallback -> apply again
+    }
+    if ((rc = collect_timings(p, true, true))) return rc;
+    if (diff_memkind == SFFTB_MEM_HOST) {
+        const size_t bytes = (size_t)p->d.N0 * p->d.N1 * (diff_dtype == SFFTB_F64 ? 8 : 4);
+        CK(cudaMemcpyAsync(diff, p->stA, bytes, cudaMemcpyDeviceToHost, p->stream));
+    }
+    if ((rc = copy_out(p, solution, sol_memkind, p->sol, sizeof(double) * p->d.NEQ))) return rc;
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int sfftb_export_normal_eq(sfftb_plan* p, double* LHMAT, double* RHb) {
+    if (!p) return fail(SFFTB_EINVAL, "null plan");
+    if (!p->have_fit) return fail(SFFTB_ESTATE, "no fit has been run on this plan");
+    CK(cudaSetDevice(p->device));
+    const int n = p->d.NEQ, ld = n + 1;
+    if (!p->exportbuf) CK(cudaMalloc(&p->exportbuf, sizeof(double) * (size_t)(n + 1) * ld));
+    dim3 blk(32, 8), grd((n + 1 + 31) / 32, (n + 1 + 7) / 8);
+    fill_matrix_kernel<<<grd, blk, 0, p->stream>>>(p->fill, p->ident, n, nullptr, p->exportbuf, ld, p->info + 3);
+    CKL(p);
+    if (LHMAT) CK(cudaMemcpy2DAsync(LHMAT, sizeof(double) * n, p->exportbuf, sizeof(double) * ld, sizeof(double) * n, n, cudaMemcpyDeviceToHost, p->stream));
+    if (RHb) CK(cudaMemcpyAsync(RHb, p->exportbuf + (size_t)n * ld, sizeof(double) * n, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int sfftb_dbg_lag_tables(sfftb_plan* p, double* R, double* RJ, double* RT, double* RJT) {
+    if (!p) return fail(SFFTB_EINVAL, "null plan");
+    if (!p->have_fit) return fail(SFFTB_ESTATE, "no fit has been run on this plan");
+    CK(cudaSetDevice(p->device));
+    const sfftb_dims& d = p->d;
+    const size_t nl0 = 4 * d.w0 + 1, nl1 = 4 * d.w1 + 1, nlj0 = 2 * d.w0 + 1, nlj1 = 2 * d.w1 + 1;
+    CK(cudaStreamSynchronize(p->stream));
+    if (R) CK(cudaMemcpy(R, p->R, sizeof(double) * p->cfit.npairs * nl0 * nl1, cudaMemcpyDeviceToHost));
+    if (RJ) CK(cudaMemcpy(RJ, p->RJ, sizeof(double) * d.Fij * nlj0 * nlj1, cudaMemcpyDeviceToHost));
+    if (RT) CK(cudaMemcpy(RT, p->RT, sizeof(double) * d.Fij * d.Fpq * nlj0 * nlj1, cudaMemcpyDeviceToHost));
+    if (RJT) CK(cudaMemcpy(RJT, p->RJT, sizeof(double) * d.Fpq, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+template <typename TSt>
+__global__ void widen_kernel(const TSt* __restrict__ in, cd* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = load_c(in + i);
+}
+
+extern "C" int sfftb_dbg_row_spectra(sfftb_plan* p, int which, double* out) {
+    if (!p || !out) return fail(SFFTB_EINVAL, "null argument");
+    CK(cudaSetDevice(p->device));
+    const sfftb_dims& d = p->d;
+    const size_t n = (size_t)(which == 0 ? d.DK + 1 : 1) * (d.N1 / 2 + 1) * d.N0;
+    cd* tmp = nullptr;
+    CK(cudaMalloc(&tmp, sizeof(cd) * n));
+    const void* src = which == 0 ? p->gI : p->gJ;
+    if (p->cfg.storage == SFFTB_STORE_F32) widen_kernel<float2><<<1024, 256, 0, p->stream>>>((const float2*)src, tmp, n);
+    else widen_kernel<double2><<<1024, 256, 0, p->stream>>>((const double2*)src, tmp, n);
+    cudaError_t e = cudaMemcpyAsync(out, tmp, sizeof(cd) * n, cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(SFFTB_ECUDA, "CUDA error %s in dbg_row_spectra", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int sfftb_dbg_fft1d(int device, int n, int nbatch, int sign, const double* in, double* out) {
+    if (!in || !out || n < 1 || nbatch < 1) return fail(SFFTB_EINVAL, "bad argument");
+    CK(cudaSetDevice(device));
+    FftDesc fd;
+    if (!make_fft_desc(n, &fd) || !fft_fits_threads(fd, 512)) return fail(SFFTB_EINVAL, "unsupported FFT length %d", n);
+    if (init_generic_radix_tables()) return SFFTB_ECUDA;
+    int v = 0;
+    CK(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    const int pitch = n + 1;
+    int ppc = 3;
+    while (ppc > 1 && sizeof(cd) * (size_t)ppc * pitch > (size_t)v) --ppc;
+    const size_t smem = sizeof(cd) * (size_t)ppc * pitch;
+    if (smem > (size_t)v) return fail(SFFTB_EINVAL, "FFT length %d does not fit shared memory", n);
+    cd *tw = nullptr, *din = nullptr, *dout = nullptr;
+    int rc = upload_twiddles(n, &tw);
+    if (rc) return rc;
+    const size_t bytes = sizeof(cd) * (size_t)n * nbatch;
+    cudaError_t e = cudaMalloc(&din, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&dout, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(din, in, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dbg_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        dbg_fft_kernel<<<(nbatch + ppc - 1) / ppc, 512, smem>>>(fd, tw, din, dout, nbatch, ppc, pitch, sign < 0 ? -1.0 : 1.0);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(tw); cudaFree(din); cudaFree(dout);
+    if (e != cudaSuccess) return fail(SFFTB_ECUDA, "CUDA error %s in dbg_fft1d", cudaGetErrorString(e));
+    return 0;
+}

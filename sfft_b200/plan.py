@@ -1,0 +1,166 @@
+"""Plan object: owns one native sfftb_plan (the role SFFTModule_dict plays in the reference,
+sfft/sfftcore/SFFTConfigure.py:50-75, :1371-1395)."""
+import ctypes as C
+import numpy as np
+
+from . import _lib as B
+
+
+def _ptr_of(a):
+    """(pointer, memkind, dtype_code, keepalive) of a host numpy array or a device array
+    (anything with __cuda_array_interface__, e.g. a torch CUDA tensor or a CuPy array)."""
+    if hasattr(a, '__cuda_array_interface__'):
+        cai = a.__cuda_array_interface__
+        if cai.get('strides') is not None:
+            raise Exception('MeLOn ERROR: device arrays must be C-contiguous')
+        ts = cai['typestr']
+        if ts not in ('<f8', '<f4'):
+            raise Exception('MeLOn ERROR: device arrays must be float64 or float32')
+        return cai['data'][0], B.MEM_DEVICE, (B.F64 if ts == '<f8' else B.F32), a
+    arr = np.asarray(a)
+    if arr.dtype != np.float32:
+        arr = arr.astype(np.float64, copy=False)
+    arr = np.ascontiguousarray(arr)
+    return arr.ctypes.data, B.MEM_HOST, (B.F64 if arr.dtype == np.float64 else B.F32), arr
+
+
+class Plan:
+    def __init__(self, N0, N1, w0, w1, DK, DB, ConstPhotRatio, device=0, storage='fp64', fold=0):
+        self._h = C.c_void_p()
+        self._L = B.lib()
+        cfg = B.Config()
+        cfg.device, cfg.N0, cfg.N1, cfg.w0, cfg.w1 = int(device), int(N0), int(N1), int(w0), int(w1)
+        cfg.DK, cfg.DB, cfg.const_phot_ratio = int(DK), int(DB), int(bool(ConstPhotRatio))
+        cfg.storage = {'fp64': B.STORE_F64, 'fp32': B.STORE_F32}[storage]
+        cfg.fold = int(fold)
+        B.check(self._L.sfftb_plan_create(C.byref(self._h), C.byref(cfg)))
+        d = B.Dims()
+        B.check(self._L.sfftb_plan_dims(self._h, C.byref(d)))
+        self.dims = {k: getattr(d, k) for k, _ in B.Dims._fields_}
+        self.device, self.storage = int(device), storage
+        self.shape = (int(N0), int(N1))
+        self.NEQ = self.dims['NEQ']
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            self._L.sfftb_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- plumbing --------------------------------------------------------------------------
+    def set_stream(self, stream_ptr):
+        B.check(self._L.sfftb_plan_set_stream(self._h, C.c_void_p(stream_ptr or 0)))
+
+    def sync(self):
+        B.check(self._L.sfftb_plan_sync(self._h))
+
+    def set_timing(self, on=True):
+        B.check(self._L.sfftb_plan_set_timing(self._h, int(bool(on))))
+
+    def timings(self):
+        ms = (C.c_float * 7)()
+        B.check(self._L.sfftb_timings(self._h, ms, 7))
+        keys = ('fit_rows', 'fit_cols', 'fit_reduce_fill', 'fit_solve', 'apply_rows', 'apply_cols', 'apply_inv_rows')
+        return dict(zip(keys, [float(v) for v in ms]))
+
+    @property
+    def launch_count(self):
+        return int(self._L.sfftb_launch_count(self._h))
+
+    @property
+    def last_solver(self):
+        return {0: None, 1: 'cholesky', 2: 'lu'}[int(self._L.sfftb_last_solver(self._h))]
+
+    def _check_pair(self, *imgs):
+        for a in imgs:
+            shp = tuple(a.shape)
+            if shp != self.shape:
+                raise Exception('MeLOn ERROR: INCONSISTENT shape of input images I & J, [%d, %d] required!' % self.shape)
+
+    # ---- host-array entry points (numpy in / numpy out) -----------------------------------------
+    def fit(self, PixA_I, PixA_J):
+        self._check_pair(PixA_I, PixA_J)
+        pI, mk, dt, kI = _ptr_of(PixA_I)
+        pJ, mk2, dt2, kJ = _ptr_of(PixA_J)
+        if (mk, dt) != (mk2, dt2):
+            raise Exception('MeLOn ERROR: I and J must live in the same memory and share a dtype')
+        sol = np.empty(self.NEQ, np.float64)
+        B.check(self._L.sfftb_fit(self._h, pI, pJ, mk, dt, sol.ctypes.data, B.MEM_HOST))
+        return sol
+
+    def apply(self, PixA_I, PixA_J, Solution, out_dtype=np.float64):
+        self._check_pair(PixA_I, PixA_J)
+        pI, mk, dt, kI = _ptr_of(PixA_I)
+        pJ, mk2, dt2, kJ = _ptr_of(PixA_J)
+        if (mk, dt) != (mk2, dt2):
+            raise Exception('MeLOn ERROR: I and J must live in the same memory and share a dtype')
+        sol = np.ascontiguousarray(np.asarray(Solution, np.float64))
+        if sol.shape != (self.NEQ,):
+            raise Exception('MeLOn ERROR: SFFTSolution must have shape (%d,)' % self.NEQ)
+        diff = np.empty(self.shape, out_dtype)
+        B.check(self._L.sfftb_apply(self._h, pI, pJ, mk, dt, sol.ctypes.data, B.MEM_HOST, diff.ctypes.data, B.MEM_HOST,
+                                    B.F64 if diff.dtype == np.float64 else B.F32))
+        return diff
+
+    def gss(self, PixA_I, PixA_J, PixA_mI, PixA_mJ, out_dtype=np.float64):
+        self._check_pair(PixA_I, PixA_J, PixA_mI, PixA_mJ)
+        ptrs = [_ptr_of(a) for a in (PixA_I, PixA_J, PixA_mI, PixA_mJ)]
+        if len({(p[1], p[2]) for p in ptrs}) != 1:
+            raise Exception('MeLOn ERROR: all four images must live in the same memory and share a dtype')
+        sol = np.empty(self.NEQ, np.float64)
+        diff = np.empty(self.shape, out_dtype)
+        B.check(self._L.sfftb_gss(self._h, ptrs[0][0], ptrs[1][0], ptrs[2][0], ptrs[3][0], ptrs[0][1], ptrs[0][2],
+                                  sol.ctypes.data, B.MEM_HOST, diff.ctypes.data, B.MEM_HOST,
+                                  B.F64 if diff.dtype == np.float64 else B.F32))
+        return sol, diff
+
+    # ---- device-array entry points (pointers in / pointers out; used by the PureCupy-style API) ----
+    def gss_device(self, pI, pJ, pmI, pmJ, img_dtype, psol, pdiff, diff_dtype):
+        B.check(self._L.sfftb_gss(self._h, pI, pJ, pmI, pmJ, B.MEM_DEVICE, img_dtype, psol, B.MEM_DEVICE,
+                                  pdiff, B.MEM_DEVICE, diff_dtype))
+
+    def fit_device(self, pI, pJ, img_dtype, psol):
+        B.check(self._L.sfftb_fit(self._h, pI, pJ, B.MEM_DEVICE, img_dtype, psol, B.MEM_DEVICE))
+
+    def apply_device(self, pI, pJ, img_dtype, psol, pdiff, diff_dtype):
+        B.check(self._L.sfftb_apply(self._h, pI, pJ, B.MEM_DEVICE, img_dtype, psol, B.MEM_DEVICE,
+                                    pdiff, B.MEM_DEVICE, diff_dtype))
+
+    # ---- parity hooks -----------------------------------------------------------------------------
+    def export_normal_eq(self):
+        n = self.NEQ
+        L = np.empty((n, n), np.float64)
+        b = np.empty(n, np.float64)
+        B.check(self._L.sfftb_export_normal_eq(self._h, L.ctypes.data, b.ctypes.data))
+        return L, b
+
+    def dbg_row_spectra(self, which):
+        N0, N1 = self.shape
+        nj = self.dims['DK'] + 1 if which == 0 else 1
+        out = np.empty((nj, N1 // 2 + 1, N0), np.complex128)
+        B.check(self._L.sfftb_dbg_row_spectra(self._h, which, out.ctypes.data))
+        return out
+
+    def dbg_lag_tables(self):
+        d = self.dims
+        npairs = d['Fij'] * (d['Fij'] + 1) // 2
+        R = np.empty((npairs, 4 * d['w0'] + 1, 4 * d['w1'] + 1))
+        RJ = np.empty((d['Fij'], 2 * d['w0'] + 1, 2 * d['w1'] + 1))
+        RT = np.empty((d['Fij'], d['Fpq'], 2 * d['w0'] + 1, 2 * d['w1'] + 1))
+        RJT = np.empty(d['Fpq'])
+        B.check(self._L.sfftb_dbg_lag_tables(self._h, R.ctypes.data, RJ.ctypes.data, RT.ctypes.data, RJT.ctypes.data))
+        return R, RJ, RT, RJT
+
+
+def dbg_fft1d(x, sign=-1, device=0):
+    """Batched 1-D complex FFT through the shared-memory engine (unit-test hook)."""
+    x = np.ascontiguousarray(np.asarray(x, np.complex128))
+    x2 = x.reshape(-1, x.shape[-1])
+    out = np.empty_like(x2)
+    B.check(B.lib().sfftb_dbg_fft1d(int(device), x2.shape[1], x2.shape[0], int(sign), x2.ctypes.data, out.ctypes.data))
+    return out.reshape(x.shape)
