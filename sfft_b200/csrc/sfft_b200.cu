@@ -54,7 +54,7 @@ struct sfftb_plan {
     size_t max_smem;
     cudaStream_t stream, own_stream;
     // tables
-    cd *tw0, *tw1, *twMf, *twMa, *twH, *Q;
+    cd *tw0, *tw1, *twMf, *twH, *Q;
     double* PHI;
     int *idxmap, *ident;
     // workspaces
@@ -68,14 +68,15 @@ struct sfftb_plan {
     int* info;                   // device: [0] cholesky pivot, [1] non-finite, [2] lu pivot
     int* info_h;                 // pinned
     // kernel arguments
-    ColArgs cfit, capp;
+    ColArgs cfit;
+    FirArgs fir;
     RowArgs row;
     RowInvArgs rinv;
     ReduceArgs red;
     PolyReduceArgs pred;
     FillArgs fill;
-    size_t smem_fit, smem_app, smem_row;
-    int grid_fit, grid_app;
+    size_t smem_fit, smem_fir, smem_row;
+    int grid_fit;
     int nrowsK, nrowsL;
     // state
     cudaEvent_t ev[EV_COUNT];
@@ -156,7 +157,7 @@ __global__ void qtable_kernel(int N1, int NH, int nq, const cd* __restrict__ tw1
     if (lane == 0) Q[(size_t)q * NH + k1] = cmake(sx, sy);
 }
 
-__global__ void dbg_fft_kernel(FftDesc fd, const cd* __restrict__ tw, const cd* __restrict__ in, cd* __restrict__ out,
+__global__ void __launch_bounds__(512) dbg_fft_kernel(FftDesc fd, const cd* __restrict__ tw, const cd* __restrict__ in, cd* __restrict__ out,
                                int nbatch, int ppc, int pitch, double sgn) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd* buf = reinterpret_cast<cd*>(smem_raw);
@@ -208,14 +209,11 @@ static size_t fit_smem_bytes(const ColArgs& c, int PB) {
     const size_t nacc = (size_t)c.npairs * c.nl0 + (size_t)c.Fij * c.nlj0;
     return sizeof(cd) * ((size_t)(c.Fij + 1 + PB) * c.pitch + nacc + (size_t)(c.nj + 1) * SFFTB_MAXE + 16 * SFFTB_MAXE);
 }
-static size_t app_smem_bytes(const ColArgs& c) {
-    return sizeof(cd) * ((size_t)(2 * c.Fij + 1) * c.pitch + c.N0 + (size_t)c.Fij * (2 * c.w0 + 1) + c.Fij);
-}
 
 static int plan_free(sfftb_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
-    void* ptrs[] = {p->tw0, p->tw1, p->twMf, p->twMa, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
+    void* ptrs[] = {p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
                     p->kap, p->lam, p->nuJ, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->info_h) cudaFreeHost(p->info_h);
@@ -271,7 +269,7 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
     if (upload_twiddles(r.H, &p->twH)) return SFFTB_ECUDA;
     r.twH = p->twH; r.tw1 = p->tw1;
     p->rinv.r = r;
-    p->rinv.scale = (r.packed ? 2.0 : 1.0) / ((double)N0 * (double)N1);
+    p->rinv.scale = (r.packed ? 2.0 : 1.0) / (double)N1;      // the FIR column pass already carries 1/N0
     p->rinv.DB = d.DB; p->rinv.Fpq = d.Fpq;
     {
         int k = 0;
@@ -281,11 +279,10 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
 
     // ---- column pass geometry: fold factor V, slice length M ----
     fill_col_common(p->cfit, p);
-    fill_col_common(p->capp, p);
     const int Mmax = env_int("SFFTB_MMAX", 512);
     const int ntot = p->cfit.npairs + d.Fij;
-    bool okf = false, oka = false;
-    for (int V = 1; V <= N0 && !(okf && oka); ++V) {
+    bool okf = false;
+    for (int V = 1; V <= N0 && !okf; ++V) {
         if (N0 % V) continue;
         const int M = N0 / V;
         if (cfg->fold > 0 && V != cfg->fold) continue;
@@ -300,21 +297,22 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
             while (PB > 1 && fit_smem_bytes(c, PB) > p->max_smem) --PB;
             if (fit_smem_bytes(c, PB) <= p->max_smem) { c.PB = PB; okf = true; }
         }
-        if (!oka) {
-            ColArgs& c = p->capp;
-            c.V = V; c.M = M; c.pitch = M + 1; c.fd = fd; c.PB = 0;
-            if (app_smem_bytes(c) <= p->max_smem) oka = true;
-        }
     }
-    if (!okf || !oka)
+    if (!okf)
         return fail(SFFTB_EINVAL, "unsupported image height N0=%d (fold=%d): no slice length with prime factors <= 13 fits shared memory",
                     N0, cfg->fold);
     d.fold = p->cfit.V; d.sub_len = p->cfit.M;
     if (upload_twiddles(p->cfit.M, &p->twMf)) return SFFTB_ECUDA;
-    if (upload_twiddles(p->capp.M, &p->twMa)) return SFFTB_ECUDA;
-    p->cfit.twM = p->twMf; p->capp.twM = p->twMa;
+    p->cfit.twM = p->twMf;
     p->smem_fit = fit_smem_bytes(p->cfit, p->cfit.PB);
-    p->smem_app = app_smem_bytes(p->capp);
+    {
+        FirArgs& fa = p->fir;
+        memset(&fa, 0, sizeof fa);
+        fa.N0 = N0; fa.N1 = N1; fa.NH = NH; fa.DK = d.DK; fa.Fij = d.Fij; fa.nj = d.DK + 1; fa.w0 = d.w0; fa.w1 = d.w1;
+        memcpy(fa.plane_of, p->cfit.plane_of, sizeof fa.plane_of);
+        fa.tw1 = p->tw1;
+        p->smem_fir = sizeof(cd) * (size_t)d.Fij * d.L0 + sizeof(double) * (size_t)d.Fij;
+    }
 
     // ---- workspaces ----
     CK(cudaMalloc(&p->gI, csz * (size_t)(d.DK + 1) * NH * N0));
@@ -402,11 +400,11 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
     // ---- kernel attributes ----
     const bool f32 = cfg->storage == SFFTB_STORE_F32;
     if (f32) {
-        if (set_smem(fit_col_kernel<float2>, p->smem_fit) || set_smem(apply_col_kernel<float2>, p->smem_app)) return SFFTB_ECUDA;
+        if (set_smem(fit_col_kernel<float2>, p->smem_fit) || set_smem(apply_fir_kernel<float2>, p->smem_fir)) return SFFTB_ECUDA;
         if (set_smem(row_fwd_kernel<float, float2>, p->smem_row) || set_smem(row_fwd_kernel<double, float2>, p->smem_row)) return SFFTB_ECUDA;
         if (set_smem(row_inv_kernel<float2, float>, p->smem_row) || set_smem(row_inv_kernel<float2, double>, p->smem_row)) return SFFTB_ECUDA;
     } else {
-        if (set_smem(fit_col_kernel<double2>, p->smem_fit) || set_smem(apply_col_kernel<double2>, p->smem_app)) return SFFTB_ECUDA;
+        if (set_smem(fit_col_kernel<double2>, p->smem_fit) || set_smem(apply_fir_kernel<double2>, p->smem_fir)) return SFFTB_ECUDA;
         if (set_smem(row_fwd_kernel<float, double2>, p->smem_row) || set_smem(row_fwd_kernel<double, double2>, p->smem_row)) return SFFTB_ECUDA;
         if (set_smem(row_inv_kernel<double2, float>, p->smem_row) || set_smem(row_inv_kernel<double2, double>, p->smem_row)) return SFFTB_ECUDA;
     }
@@ -421,9 +419,6 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
     if (f32) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_col_kernel<float2>, NT_COL, p->smem_fit));
     else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_col_kernel<double2>, NT_COL, p->smem_fit));
     p->grid_fit = std::min(NH, std::max(1, occ) * p->nsm);
-    if (f32) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_col_kernel<float2>, NT_COL, p->smem_app));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_col_kernel<double2>, NT_COL, p->smem_app));
-    p->grid_app = std::min(NH, std::max(1, occ) * p->nsm);
     CK(cudaStreamSynchronize(p->stream));
     return 0;
 }
@@ -598,7 +593,10 @@ static int apply_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype
     if (launch_row_fwd<TSt>(p, dI, dtype, (TSt*)p->gI, d.DK + 1)) return SFFTB_ECUDA;
     if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
     EVREC(p, EV_AROWS);
-    apply_col_kernel<TSt><<<p->grid_app, NT_COL, p->smem_app, p->stream>>>(p->capp, (const TSt*)p->gI, (const TSt*)p->gJ, dsol, p->tw1, (TSt*)p->gJ);
+    {
+        dim3 grd(d.N1 / 2 + 1, (d.N0 + FIR_CHUNK - 1) / FIR_CHUNK);
+        apply_fir_kernel<TSt><<<grd, FIR_NT, p->smem_fir, p->stream>>>(p->fir, (const TSt*)p->gI, (const TSt*)p->gJ, dsol, (TSt*)p->gJ);
+    }
     CKL(p);
     EVREC(p, EV_ACOL);
     const int grid = (d.N0 + p->row.RB - 1) / p->row.RB;
