@@ -45,6 +45,7 @@ __device__ __forceinline__ void butterfly16(cd* v, double sgn) {
 
 template <int R> __device__ __forceinline__ void bfly_r(cd* t, double sgn) { butterfly<R>(t, sgn); }
 template <> __device__ __forceinline__ void bfly_r<16>(cd* t, double sgn) { butterfly16(t, sgn); }
+template <> __device__ __forceinline__ void bfly_r<1>(cd*, double) {}
 
 // group synchronisation: a (sub-)warp mask, or a named barrier shared by T >= 64 threads
 struct GroupSync {

@@ -6,6 +6,8 @@
 #include "kernels_fit.cuh"
 #include "kernels_solve.cuh"
 #include "kernels_apply.cuh"
+#include "kernels_row_fast.cuh"
+#include "kernels_fit_fast.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -55,6 +57,7 @@ struct sfftb_plan {
     cudaStream_t stream, own_stream;
     // tables
     cd *tw0, *tw1, *twMf, *twH, *Q;
+    cd *tabA, *tabB_row, *tabC_row;   // register-engine twiddle tables
     double* PHI;
     int *idxmap, *ident;
     // workspaces
@@ -72,6 +75,13 @@ struct sfftb_plan {
     FirArgs fir;
     RowArgs row;
     RowInvArgs rinv;
+    RowFastArgs rowf;
+    RowInvFastArgs rinvf;
+    FastFitArgs ffit;
+    int row_fast;                // 0 or the engine length H
+    int fit_fast;                // 0 or VI
+    size_t smem_ffit;
+    int grid_ffit;
     ReduceArgs red;
     PolyReduceArgs pred;
     FillArgs fill;
@@ -122,6 +132,21 @@ static int upload_twiddles(int n, cd** out) {
     }
     CK(cudaMalloc(out, sizeof(cd) * (size_t)n));
     CK(cudaMemcpy(*out, h.data(), sizeof(cd) * (size_t)n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// engine table: tab[(r-1)*Ns + k] = exp(-2 pi i r k / (Ns R)),  r = 1..R-1, k = 0..Ns-1
+static int upload_engine_table(int Ns, int R, cd** out) {
+    std::vector<cd> h((size_t)(R - 1) * Ns);
+    const long double tp = 6.283185307179586476925286766559005768L;
+    for (int r = 1; r < R; ++r)
+        for (int k = 0; k < Ns; ++k) {
+            const long double ang = tp * (long double)r * (long double)k / ((long double)Ns * (long double)R);
+            h[(size_t)(r - 1) * Ns + k].x = (double)cosl(ang);
+            h[(size_t)(r - 1) * Ns + k].y = (double)(-sinl(ang));
+        }
+    CK(cudaMalloc(out, sizeof(cd) * h.size()));
+    CK(cudaMemcpy(*out, h.data(), sizeof(cd) * h.size(), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -213,7 +238,7 @@ static size_t fit_smem_bytes(const ColArgs& c, int PB) {
 static int plan_free(sfftb_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
-    void* ptrs[] = {p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
+    void* ptrs[] = {p->tabA, p->tabB_row, p->tabC_row, p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
                     p->kap, p->lam, p->nuJ, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->info_h) cudaFreeHost(p->info_h);
@@ -415,6 +440,72 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
     if (set_smem(chol_backsolve_kernel, bs_smem)) return SFFTB_ECUDA;
     if (set_smem(lu_solve_kernel, sizeof(double) * (size_t)p->nsolve)) return SFFTB_ECUDA;
 
+    // ---- fast paths on the register FFT engine ----
+    if (upload_engine_table(16, 16, &p->tabA)) return SFFTB_ECUDA;
+    p->row_fast = 0;
+    if (r.packed && !env_int("SFFTB_ROW_GENERIC", 0) &&
+        (r.H == 512 || r.H == 1024 || r.H == 2048 || r.H == 4096 || r.H == 8192)) {
+        const int R3 = reg_fft_tail_radix(r.H);
+        if (upload_engine_table(256, R3, &p->tabB_row)) return SFFTB_ECUDA;
+        if (r.H == 8192 && upload_engine_table(4096, 2, &p->tabC_row)) return SFFTB_ECUDA;
+        RowFastArgs& rf = p->rowf;
+        rf.N0 = N0; rf.N1 = N1; rf.NH = NH; rf.H = r.H;
+        rf.tabA = p->tabA; rf.tabB = p->tabB_row; rf.tabC = p->tabC_row; rf.tw1 = p->tw1;
+        p->rinvf.r = rf; p->rinvf.scale = p->rinv.scale; p->rinvf.Fpq = d.Fpq;
+        memcpy(p->rinvf.p_of, p->rinv.p_of, 16); memcpy(p->rinvf.q_of, p->rinv.q_of, 16);
+        p->row_fast = r.H;
+    }
+    p->fit_fast = 0;
+    if (N0 % 256 == 0 && 4 * d.w0 + 1 <= 256 && !env_int("SFFTB_FIT_GENERIC", 0) && d.Fij * (d.Fij - 1) / 2 <= 48) {
+        FastFitArgs& ff = p->ffit;
+        memset(&ff, 0, sizeof ff);
+        ff.c = p->cfit;
+        ff.c.M = 256; ff.c.pitch = FCF_PITCH;
+        int q2 = 0;
+        for (int a2 = 0; a2 < d.Fij; ++a2)
+            for (int b2 = a2 + 1; b2 < d.Fij; ++b2) { ff.offA[q2] = (unsigned char)a2; ff.offB[q2] = (unsigned char)b2; ++q2; }
+        ff.noff = q2; ff.ndg = (d.Fij + 1) / 2; ff.njob = ff.noff + ff.ndg + d.Fij;
+        ff.pack_rounds = ff.njob >= FCF_GROUPS ? 1 : 0;
+        ff.tabA = p->tabA;
+        const size_t nacc = (size_t)p->cfit.npairs * p->cfit.nl0 + (size_t)d.Fij * p->cfit.nlj0;
+        const int vi_max = env_int("SFFTB_VI", 4);
+        for (int VI = 4; VI >= 1; VI >>= 1) {
+            if (VI > vi_max || N0 % (256 * VI)) continue;
+            const size_t bytes = sizeof(cd) * ((size_t)VI * (d.Fij + 1) * FCF_PITCH + (size_t)FCF_GROUPS * FCF_PITCH + nacc +
+                                               (size_t)(d.DK + 2) * SFFTB_MAXE + 16 * SFFTB_MAXE + 240);
+            if (bytes > p->max_smem) continue;
+            ff.VI = VI; ff.Vo = N0 / (256 * VI); ff.c.V = ff.Vo * VI;
+            p->smem_ffit = bytes; p->fit_fast = VI;
+            break;
+        }
+        if (p->fit_fast) { d.fold = ff.c.V; d.sub_len = 256; }
+    }
+    if (p->row_fast) {
+        const size_t sm = sizeof(cd) * (size_t)(ROWF_NT / (r.H / 16)) * (r.H + r.H / 16);
+#define SET_ROWF(HH)                                                                                              \
+        if (r.H == HH) {                                                                                              \
+            if (f32) { if (set_smem(row_fwd_fast_kernel<float, float2, HH>, sm) || set_smem(row_fwd_fast_kernel<double, float2, HH>, sm) || \
+                           set_smem(row_inv_fast_kernel<float2, float, HH>, sm) || set_smem(row_inv_fast_kernel<float2, double, HH>, sm)) return SFFTB_ECUDA; } \
+            else     { if (set_smem(row_fwd_fast_kernel<float, double2, HH>, sm) || set_smem(row_fwd_fast_kernel<double, double2, HH>, sm) || \
+                           set_smem(row_inv_fast_kernel<double2, float, HH>, sm) || set_smem(row_inv_fast_kernel<double2, double, HH>, sm)) return SFFTB_ECUDA; } \
+        }
+        SET_ROWF(512) SET_ROWF(1024) SET_ROWF(2048) SET_ROWF(4096) SET_ROWF(8192)
+#undef SET_ROWF
+    }
+    if (p->fit_fast) {
+        int occ2 = 1;
+#define SET_FFIT(VV)                                                                                              \
+        if (p->fit_fast == VV) {                                                                                      \
+            if (f32) { if (set_smem(fit_col_fast_kernel<float2, VV>, p->smem_ffit)) return SFFTB_ECUDA;               \
+                       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, fit_col_fast_kernel<float2, VV>, FCF_NT, p->smem_ffit)); } \
+            else     { if (set_smem(fit_col_fast_kernel<double2, VV>, p->smem_ffit)) return SFFTB_ECUDA;              \
+                       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, fit_col_fast_kernel<double2, VV>, FCF_NT, p->smem_ffit)); } \
+        }
+        SET_FFIT(1) SET_FFIT(2) SET_FFIT(4)
+#undef SET_FFIT
+        p->grid_ffit = std::min(NH, std::max(1, occ2) * p->nsm);
+    }
+
     int occ = 1;
     if (f32) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_col_kernel<float2>, NT_COL, p->smem_fit));
     else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_col_kernel<double2>, NT_COL, p->smem_fit));
@@ -489,6 +580,21 @@ static int stage_in(sfftb_plan* p, const void* src, int memkind, int dtype, void
 
 template <typename TSt>
 static int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj) {
+    const size_t esz2 = dtype == SFFTB_F64 ? 16 : 8;
+    if (p->row_fast && ((uintptr_t)img % esz2) == 0) {
+        const int H = p->row_fast, RB = ROWF_NT / (H / 16);
+        const int grid = (p->d.N0 + RB - 1) / RB;
+        const size_t sm = sizeof(cd) * (size_t)RB * (H + H / 16);
+#define RUN_ROWF(HH)                                                                                                   \
+        if (H == HH) {                                                                                                 \
+            if (dtype == SFFTB_F64) row_fwd_fast_kernel<double, TSt, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rowf, (const double*)img, out, nj); \
+            else row_fwd_fast_kernel<float, TSt, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rowf, (const float*)img, out, nj);                     \
+        }
+        RUN_ROWF(512) RUN_ROWF(1024) RUN_ROWF(2048) RUN_ROWF(4096) RUN_ROWF(8192)
+#undef RUN_ROWF
+        CKL(p);
+        return 0;
+    }
     const int grid = (p->d.N0 + p->row.RB - 1) / p->row.RB;
     if (dtype == SFFTB_F64)
         row_fwd_kernel<double, TSt><<<grid, 512, p->smem_row, p->stream>>>(p->row, (const double*)img, out, nj);
@@ -550,7 +656,14 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype) 
     if (launch_row_fwd<TSt>(p, dI, dtype, (TSt*)p->gI, d.DK + 1)) return SFFTB_ECUDA;
     if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
     EVREC(p, EV_ROWS);
-    fit_col_kernel<TSt><<<p->grid_fit, NT_COL, p->smem_fit, p->stream>>>(p->cfit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
+    if (p->fit_fast == 4)
+        fit_col_fast_kernel<TSt, 4><<<p->grid_ffit, FCF_NT, p->smem_ffit, p->stream>>>(p->ffit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
+    else if (p->fit_fast == 2)
+        fit_col_fast_kernel<TSt, 2><<<p->grid_ffit, FCF_NT, p->smem_ffit, p->stream>>>(p->ffit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
+    else if (p->fit_fast == 1)
+        fit_col_fast_kernel<TSt, 1><<<p->grid_ffit, FCF_NT, p->smem_ffit, p->stream>>>(p->ffit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
+    else
+        fit_col_kernel<TSt><<<p->grid_fit, NT_COL, p->smem_fit, p->stream>>>(p->cfit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
     CKL(p);
     EVREC(p, EV_COL);
     const size_t red_smem = sizeof(cd) * (size_t)(d.N1 / 2 + 1);
@@ -599,12 +712,26 @@ static int apply_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype
     }
     CKL(p);
     EVREC(p, EV_ACOL);
-    const int grid = (d.N0 + p->row.RB - 1) / p->row.RB;
     const double* bpq = dsol + d.Fijab;
-    if (diff_dtype == SFFTB_F64)
-        row_inv_kernel<TSt, double><<<grid, 512, p->smem_row, p->stream>>>(p->rinv, (const TSt*)p->gJ, bpq, (double*)ddiff);
-    else
-        row_inv_kernel<TSt, float><<<grid, 512, p->smem_row, p->stream>>>(p->rinv, (const TSt*)p->gJ, bpq, (float*)ddiff);
+    const size_t osz2 = diff_dtype == SFFTB_F64 ? 16 : 8;
+    if (p->row_fast && ((uintptr_t)ddiff % osz2) == 0) {
+        const int H = p->row_fast, RB = ROWF_NT / (H / 16);
+        const int grid = (d.N0 + RB - 1) / RB;
+        const size_t sm = sizeof(cd) * (size_t)RB * (H + H / 16);
+#define RUN_RINVF(HH)                                                                                                  \
+        if (H == HH) {                                                                                                 \
+            if (diff_dtype == SFFTB_F64) row_inv_fast_kernel<TSt, double, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rinvf, (const TSt*)p->gJ, bpq, (double*)ddiff); \
+            else row_inv_fast_kernel<TSt, float, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rinvf, (const TSt*)p->gJ, bpq, (float*)ddiff);                            \
+        }
+        RUN_RINVF(512) RUN_RINVF(1024) RUN_RINVF(2048) RUN_RINVF(4096) RUN_RINVF(8192)
+#undef RUN_RINVF
+    } else {
+        const int grid = (d.N0 + p->row.RB - 1) / p->row.RB;
+        if (diff_dtype == SFFTB_F64)
+            row_inv_kernel<TSt, double><<<grid, 512, p->smem_row, p->stream>>>(p->rinv, (const TSt*)p->gJ, bpq, (double*)ddiff);
+        else
+            row_inv_kernel<TSt, float><<<grid, 512, p->smem_row, p->stream>>>(p->rinv, (const TSt*)p->gJ, bpq, (float*)ddiff);
+    }
     CKL(p);
     EVREC(p, EV_AINV);
     return 0;
