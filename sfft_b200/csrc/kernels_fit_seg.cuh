@@ -81,7 +81,27 @@ __device__ void column_poly_rows(const SegFitArgs& fa, const TSt* __restrict__ g
             kaprow[fa.nK + fa.nLT + fa.pq_of[p][q]] = cmulcj(mom[a.nj * SFFTB_MAXE + p], fa.Q[(size_t)q * a.NH + k1]);
 }
 
-// smem (cd): spec[FSG_NBUF * FSG_PITCH] | mom[(nj+1) * MAXE] | red[16 * MAXE] | tabA[240]
+// asynchronous element copy global -> shared (LDGSTS); 8 bytes for fp32 spectra, 16 for fp64
+__device__ __forceinline__ void cp_async_elem(float2* dst, const float2* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_elem(double2* dst, const double2* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ int wrap_row(int r, int N0) {
+    if (r < 0) { r += N0; if (r < 0) { r %= N0; if (r < 0) r += N0; } }
+    else if (r >= N0) { r -= N0; if (r >= N0) r %= N0; }
+    return r;
+}
+
+#define FSG_NMOM 48                  // threads of the idle transform groups that accumulate the column moments
+#define FSG_MSLOTS (4 * SFFTB_MAXE)  // (nj + 1 <= 4 source planes) x (e = 0 .. MAXE-1)
+
+// smem: spec[FSG_NBUF * FSG_PITCH] cd | mom[4 * MAXE] cd | macc[FSG_MSLOTS * FSG_NMOM] cd | tabA[240] cd |
+//       stage[2][nj + 1][FSG_M] TSt
 template <typename TSt, int DK>
 __global__ void __launch_bounds__(FSG_NT, 1) fit_seg_kernel(SegFitArgs fa, const TSt* __restrict__ gI, const TSt* __restrict__ gJ,
                                                             cd* __restrict__ kap)
@@ -90,13 +110,15 @@ __global__ void __launch_bounds__(FSG_NT, 1) fit_seg_kernel(SegFitArgs fa, const
     constexpr int NPAIR = Fij * (Fij + 1) / 2;
     constexpr int NACC = NPAIR + Fij;
     constexpr int NP = 2 * Fij + 1;
-    static_assert(NP <= FSG_NBUF, "KerPolyOrder too large for the segmented fit kernel");
+    constexpr int NSRC = DK + 2;             // stored row-spectrum planes: g_0 .. g_DK, J
+    static_assert(NP <= FSG_NBUF - 3, "KerPolyOrder too large for the segmented fit kernel");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const ColArgs& a = fa.c;
     cd* spec = reinterpret_cast<cd*>(smem_raw);
     cd* mom = spec + FSG_NBUF * FSG_PITCH;
-    cd* red = mom + (a.nj + 1) * SFFTB_MAXE;
-    cd* tabA = red + 16 * SFFTB_MAXE;
+    cd* macc = mom + 4 * SFFTB_MAXE;
+    cd* tabA = macc + FSG_MSLOTS * FSG_NMOM;
+    TSt* stage = reinterpret_cast<TSt*>(tabA + 240);
     const int tid = threadIdx.x;
     const int grp = tid >> 4, lane = tid & 15;
     GroupSync gs;
@@ -108,41 +130,83 @@ __global__ void __launch_bounds__(FSG_NT, 1) fit_seg_kernel(SegFitArgs fa, const
 
     for (int i = tid; i < 240; i += FSG_NT) tabA[i] = fa.tabA[i];
 
-    // role of this transform group: A-role plane grp | B-role plane grp - Fij | B-role J
+    // role of this transform group: A-role plane grp | B-role plane grp - Fij | B-role J | moment accumulation
     const bool roleA = grp < Fij, isJ = grp == 2 * Fij, active = grp < NP;
     const int pl = roleA ? grp : (grp < 2 * Fij ? grp - Fij : 0);
-    const int my_i = isJ ? 0 : a.pl_i[pl], my_j = isJ ? 0 : a.pl_j[pl];
-    const TSt* colbase = isJ ? gJ : gI + (size_t)my_j * a.NH * a.N0;
+    const int my_i = isJ ? 0 : a.pl_i[pl];
+    const int my_src = isJ ? DK + 1 : a.pl_j[pl];
+    const int mt = tid - (FSG_NT - FSG_NMOM);        // >= 0: this thread accumulates moments
 
     for (int k1 = blockIdx.x; k1 < a.NH; k1 += gridDim.x) {
         cd acc[NACC];
 #pragma unroll
         for (int q = 0; q < NACC; ++q) acc[q] = cmake(0.0, 0.0);
         cd* kaprow = kap + (size_t)k1 * fa.nrows;
-        column_moments(a, gI, gJ, k1, mom, red);
-        column_poly_rows(fa, gI, k1, mom, kaprow);
+        if (mt >= 0)
+            for (int s = 0; s < FSG_MSLOTS; ++s) macc[s * FSG_NMOM + mt] = cmake(0.0, 0.0);
 
-        const TSt* col = colbase + (size_t)k1 * a.N0;
+        // prefetch the window of segment 0 (element tid of every source plane)
+        {
+            const int r = wrap_row(-h + tid, a.N0);
+#pragma unroll
+            for (int jj = 0; jj < NSRC; ++jj) {
+                const TSt* col = (jj == DK + 1) ? gJ + (size_t)k1 * a.N0 : gI + ((size_t)jj * a.NH + k1) * a.N0;
+                cp_async_elem(stage + jj * FSG_M + tid, col + r);
+            }
+            cp_async_commit();
+        }
         for (int seg = 0; seg < fa.nseg; ++seg) {
             const int c0 = seg * S;
             const int Sc = min(S, a.N0 - c0);
+            const TSt* st = stage + (seg & 1) * NSRC * FSG_M;
+            if (seg + 1 < fa.nseg) {
+                TSt* nx = stage + ((seg + 1) & 1) * NSRC * FSG_M;
+                const int r = wrap_row(c0 + S - h + tid, a.N0);
+#pragma unroll
+                for (int jj = 0; jj < NSRC; ++jj) {
+                    const TSt* col = (jj == DK + 1) ? gJ + (size_t)k1 * a.N0 : gI + ((size_t)jj * a.NH + k1) * a.N0;
+                    cp_async_elem(nx + jj * FSG_M + tid, col + r);
+                }
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();          // window of this segment visible; products of the previous segment done
             if (active) {
                 cd v[16];
+                const TSt* src = st + my_src * FSG_M;
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const int n = lane + 16 * q;
-                    int r = (c0 - h + n) % a.N0;
-                    if (r < 0) r += a.N0;
                     cd g = cmake(0.0, 0.0);
                     if (!roleA || (n >= h && n < h + Sc)) {
-                        g = load_c(col + r);
-                        if (my_i > 0) g = cscale(g, ipow((r + 1) * inv0, my_i));
+                        g = load_c(src + n);
+                        if (my_i > 0) {
+                            const double cx = (wrap_row(c0 - h + n, a.N0) + 1) * inv0;
+                            g = cscale(g, my_i == 1 ? cx : (my_i == 2 ? cx * cx : cx * cx * cx));
+                        }
                     }
                     v[q] = g;
                 }
                 reg_fft<FSG_M>(v, plane, lane, tabA, nullptr, nullptr, -1.0, gs);
 #pragma unroll
                 for (int q = 0; q < 16; ++q) plane[RPAD(lane + 16 * q)] = v[q];
+            } else if (mt >= 0) {
+                // column moments nu[jj][e] += sum_{core rows} cx(r)^e g_jj[r]   (e <= DK - jj + DB for I planes, <= DB for J)
+                for (int n = h + mt; n < h + Sc; n += FSG_NMOM) {
+                    const double cx = (c0 + (n - h) + 1) * inv0;
+#pragma unroll
+                    for (int jj = 0; jj < NSRC; ++jj) {
+                        const int ne = (jj == DK + 1) ? a.DB + 1 : DK - jj + a.DB + 1;
+                        cd g = load_c(st + jj * FSG_M + n);
+                        for (int e = 0; e < ne; ++e) {
+                            cd* slot = macc + (jj * SFFTB_MAXE + e) * FSG_NMOM + mt;
+                            *slot = cadd(*slot, g);
+                            g = cscale(g, cx);
+                        }
+                    }
+                }
             }
             __syncthreads();
             {
@@ -169,8 +233,17 @@ __global__ void __launch_bounds__(FSG_NT, 1) fit_seg_kernel(SegFitArgs fa, const
                     acc[NPAIR + A].y = fma(fA[A].x, fJ.y, acc[NPAIR + A].y); acc[NPAIR + A].y = fma(-fA[A].y, fJ.x, acc[NPAIR + A].y);
                 }
             }
-            __syncthreads();
         }
+        __syncthreads();
+
+        // ---- column moments -> background cross-term rows ----
+        if (tid < FSG_MSLOTS) {
+            cd s = cmake(0.0, 0.0);
+            for (int t = 0; t < FSG_NMOM; ++t) s = cadd(s, macc[tid * FSG_NMOM + t]);
+            mom[tid] = s;
+        }
+        __syncthreads();
+        column_poly_rows(fa, gI, k1, mom, kaprow);
 
         // ---- one inverse transform per pair; keep the lags FillLS_* reads ----
         const double invM = 1.0 / (double)FSG_M;

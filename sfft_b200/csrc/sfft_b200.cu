@@ -8,6 +8,7 @@
 #include "kernels_apply.cuh"
 #include "kernels_row_fast.cuh"
 #include "kernels_fit_fast.cuh"
+#include "kernels_fit_seg.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -82,6 +83,15 @@ struct sfftb_plan {
     int fit_fast;                // 0 or VI
     size_t smem_ffit;
     int grid_ffit;
+    // segmented fit path
+    SegFitArgs sfit;
+    int fit_seg;                 // 1: fit_seg_kernel + lag_reduce2 path
+    size_t smem_sfit;
+    int grid_sfit;
+    cd* kap2;                    // [NH][nrows]
+    double* part;                // [ksplit][nrows][4 w1 + 1]
+    LagReduce2Args red2;
+    LagFinishArgs fin2;
     ReduceArgs red;
     PolyReduceArgs pred;
     FillArgs fill;
@@ -239,7 +249,7 @@ static int plan_free(sfftb_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     void* ptrs[] = {p->tabA, p->tabB_row, p->tabC_row, p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
-                    p->kap, p->lam, p->nuJ, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info};
+                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->info_h) cudaFreeHost(p->info_h);
     for (int k = 0; k < EV_COUNT; ++k) if (p->ev[k]) cudaEventDestroy(p->ev[k]);
@@ -323,13 +333,19 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
             if (fit_smem_bytes(c, PB) <= p->max_smem) { c.PB = PB; okf = true; }
         }
     }
-    if (!okf)
+    const bool want_seg = d.DK <= 2 && 4 * d.w0 + 32 <= FSG_M && cfg->fold <= 0 && !env_int("SFFTB_FIT_NOSEG", 0);
+    if (!okf && !want_seg)
         return fail(SFFTB_EINVAL, "unsupported image height N0=%d (fold=%d): no slice length with prime factors <= 13 fits shared memory",
                     N0, cfg->fold);
-    d.fold = p->cfit.V; d.sub_len = p->cfit.M;
-    if (upload_twiddles(p->cfit.M, &p->twMf)) return SFFTB_ECUDA;
-    p->cfit.twM = p->twMf;
-    p->smem_fit = fit_smem_bytes(p->cfit, p->cfit.PB);
+    if (okf) {
+        d.fold = p->cfit.V; d.sub_len = p->cfit.M;
+        if (upload_twiddles(p->cfit.M, &p->twMf)) return SFFTB_ECUDA;
+        p->cfit.twM = p->twMf;
+        p->smem_fit = fit_smem_bytes(p->cfit, p->cfit.PB);
+    } else {
+        p->cfit.V = 1; p->cfit.M = N0; p->cfit.pitch = N0 + 1; p->cfit.PB = 1;
+        p->smem_fit = 0;
+    }
     {
         FirArgs& fa = p->fir;
         memset(&fa, 0, sizeof fa);
@@ -425,11 +441,11 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
     // ---- kernel attributes ----
     const bool f32 = cfg->storage == SFFTB_STORE_F32;
     if (f32) {
-        if (set_smem(fit_col_kernel<float2>, p->smem_fit) || set_smem(apply_fir_kernel<float2>, p->smem_fir)) return SFFTB_ECUDA;
+        if ((okf && set_smem(fit_col_kernel<float2>, p->smem_fit)) || set_smem(apply_fir_kernel<float2>, p->smem_fir)) return SFFTB_ECUDA;
         if (set_smem(row_fwd_kernel<float, float2>, p->smem_row) || set_smem(row_fwd_kernel<double, float2>, p->smem_row)) return SFFTB_ECUDA;
         if (set_smem(row_inv_kernel<float2, float>, p->smem_row) || set_smem(row_inv_kernel<float2, double>, p->smem_row)) return SFFTB_ECUDA;
     } else {
-        if (set_smem(fit_col_kernel<double2>, p->smem_fit) || set_smem(apply_fir_kernel<double2>, p->smem_fir)) return SFFTB_ECUDA;
+        if ((okf && set_smem(fit_col_kernel<double2>, p->smem_fit)) || set_smem(apply_fir_kernel<double2>, p->smem_fir)) return SFFTB_ECUDA;
         if (set_smem(row_fwd_kernel<float, double2>, p->smem_row) || set_smem(row_fwd_kernel<double, double2>, p->smem_row)) return SFFTB_ECUDA;
         if (set_smem(row_inv_kernel<double2, float>, p->smem_row) || set_smem(row_inv_kernel<double2, double>, p->smem_row)) return SFFTB_ECUDA;
     }
@@ -480,6 +496,47 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         }
         if (p->fit_fast) { d.fold = ff.c.V; d.sub_len = 256; }
     }
+    // ---- segmented fit path (KerPolyOrder <= 2, halo 2 w0 well inside a 256-point window) ----
+    p->fit_seg = 0;
+    if (want_seg) {
+        SegFitArgs& sf = p->sfit;
+        memset(&sf, 0, sizeof sf);
+        sf.c = p->cfit;
+        sf.h = 2 * d.w0;
+        const int Smax = (FSG_M - 2 * sf.h) & ~1;
+        sf.nseg = (N0 + Smax - 1) / Smax;
+        sf.S = (((N0 + sf.nseg - 1) / sf.nseg) + 1) & ~1;       // balanced, even
+        if (sf.S > Smax) sf.S = Smax;
+        sf.nseg = (N0 + sf.S - 1) / sf.S;
+        sf.nOm = p->cfit.npairs * nl0;
+        sf.nK = sf.nOm + d.Fij * nlj0;
+        sf.nLT = d.Fij * d.Fpq * nlj0;
+        sf.nrows = sf.nK + sf.nLT + d.Fpq;
+        sf.tabA = p->tabA;
+        sf.Q = p->Q;
+        memcpy(sf.pq_of, pa.pq_of, sizeof sf.pq_of);
+        p->smem_sfit = sizeof(cd) * ((size_t)FSG_NBUF * FSG_PITCH + 4 * SFFTB_MAXE + (size_t)FSG_MSLOTS * FSG_NMOM + 240) +
+                       csz * 2 * (size_t)(d.DK + 2) * FSG_M;
+        CK(cudaMalloc(&p->kap2, sizeof(cd) * (size_t)NH * sf.nrows));
+        LagReduce2Args& r2 = p->red2;
+        r2.N1 = N1; r2.NH = NH; r2.nrows = sf.nrows; r2.w1 = d.w1; r2.tw1 = p->tw1;
+        const int rowblocks = (sf.nrows + 15) / 16;
+        r2.ksplit = std::max(1, std::min(16, (2 * p->nsm + rowblocks - 1) / rowblocks));
+        CK(cudaMalloc(&p->part, sizeof(double) * (size_t)r2.ksplit * sf.nrows * nl1));
+        LagFinishArgs& f2 = p->fin2;
+        f2.nrows = sf.nrows; f2.nOm = sf.nOm; f2.nK = sf.nK; f2.nLT = sf.nLT; f2.w1 = d.w1; f2.ksplit = r2.ksplit;
+        f2.R = p->R; f2.RJ = p->RJ; f2.RT = p->RT; f2.RJT = p->RJT;
+#define SET_SFIT(DKK)                                                                                             \
+        if (d.DK == DKK) {                                                                                            \
+            if (f32) { if (set_smem(fit_seg_kernel<float2, DKK>, p->smem_sfit)) return SFFTB_ECUDA; }                 \
+            else     { if (set_smem(fit_seg_kernel<double2, DKK>, p->smem_sfit)) return SFFTB_ECUDA; }                \
+        }
+        SET_SFIT(0) SET_SFIT(1) SET_SFIT(2)
+#undef SET_SFIT
+        p->grid_sfit = std::min(NH, p->nsm);
+        p->fit_seg = 1;
+        d.fold = sf.nseg; d.sub_len = sf.S;
+    }
     if (p->row_fast) {
         const size_t sm = sizeof(cd) * (size_t)(ROWF_NT / (r.H / 16)) * (r.H + r.H / 16);
 #define SET_ROWF(HH)                                                                                              \
@@ -507,8 +564,10 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
     }
 
     int occ = 1;
-    if (f32) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_col_kernel<float2>, NT_COL, p->smem_fit));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_col_kernel<double2>, NT_COL, p->smem_fit));
+    if (okf) {
+        if (f32) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_col_kernel<float2>, NT_COL, p->smem_fit));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_col_kernel<double2>, NT_COL, p->smem_fit));
+    }
     p->grid_fit = std::min(NH, std::max(1, occ) * p->nsm);
     CK(cudaStreamSynchronize(p->stream));
     return 0;
@@ -656,7 +715,12 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype) 
     if (launch_row_fwd<TSt>(p, dI, dtype, (TSt*)p->gI, d.DK + 1)) return SFFTB_ECUDA;
     if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
     EVREC(p, EV_ROWS);
-    if (p->fit_fast == 4)
+    if (p->fit_seg) {
+        const int DK = d.DK;
+        if (DK == 0) fit_seg_kernel<TSt, 0><<<p->grid_sfit, FSG_NT, p->smem_sfit, p->stream>>>(p->sfit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap2);
+        else if (DK == 1) fit_seg_kernel<TSt, 1><<<p->grid_sfit, FSG_NT, p->smem_sfit, p->stream>>>(p->sfit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap2);
+        else fit_seg_kernel<TSt, 2><<<p->grid_sfit, FSG_NT, p->smem_sfit, p->stream>>>(p->sfit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap2);
+    } else if (p->fit_fast == 4)
         fit_col_fast_kernel<TSt, 4><<<p->grid_ffit, FCF_NT, p->smem_ffit, p->stream>>>(p->ffit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
     else if (p->fit_fast == 2)
         fit_col_fast_kernel<TSt, 2><<<p->grid_ffit, FCF_NT, p->smem_ffit, p->stream>>>(p->ffit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
@@ -666,11 +730,20 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype) 
         fit_col_kernel<TSt><<<p->grid_fit, NT_COL, p->smem_fit, p->stream>>>(p->cfit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
     CKL(p);
     EVREC(p, EV_COL);
-    const size_t red_smem = sizeof(cd) * (size_t)(d.N1 / 2 + 1);
-    lag_reduce_kernel<<<p->nrowsK, 256, red_smem, p->stream>>>(p->red, p->kap, p->R, p->RJ);
-    CKL(p);
-    poly_reduce_kernel<<<p->nrowsL + d.DB + 1, 256, red_smem, p->stream>>>(p->pred, p->lam, p->nuJ, p->RT, p->RJT);
-    CKL(p);
+    if (p->fit_seg) {
+        dim3 grd((p->sfit.nrows + 15) / 16, p->red2.ksplit);
+        lag_reduce2_kernel<<<grd, 256, 0, p->stream>>>(p->red2, p->kap2, p->part);
+        CKL(p);
+        const int tot = p->sfit.nrows * (4 * d.w1 + 1);
+        lag_finish_kernel<<<(tot + 255) / 256, 256, 0, p->stream>>>(p->fin2, p->part);
+        CKL(p);
+    } else {
+        const size_t red_smem = sizeof(cd) * (size_t)(d.N1 / 2 + 1);
+        lag_reduce_kernel<<<p->nrowsK, 256, red_smem, p->stream>>>(p->red, p->kap, p->R, p->RJ);
+        CKL(p);
+        poly_reduce_kernel<<<p->nrowsL + d.DB + 1, 256, red_smem, p->stream>>>(p->pred, p->lam, p->nuJ, p->RT, p->RJT);
+        CKL(p);
+    }
     CK(cudaMemsetAsync(p->info, 0, sizeof(int) * 4, p->stream));
     if (fill_system(p)) return SFFTB_ECUDA;
     EVREC(p, EV_RED);
