@@ -1,0 +1,320 @@
+// kernels_chol.cuh -- dense fp64 Cholesky solve of the (diagonally scaled) normal equations in ONE persistent
+// cooperative kernel.
+//
+// Replaces LSSolver (cuSOLVER getrf/getrs through cupyx, sfft/sfftcore/SFFTSubtract.py:15-23, 397-408; CPU
+// np.linalg.solve :744-747).  LHMAT = D^T D / N is symmetric positive definite; the matrix is augmented with the
+// right-hand side as row n so that the panel solves deliver the forward substitution L y = b for free.
+//
+// Right-looking, 64-wide panels, one CTA per SM, two grid barriers per panel:
+//   (a) every CTA: 32-row slabs of the panel below the diagonal,  L_ik = A_ik W_k^T   (W_k = L_kk^{-1}, a GEMM)
+//   (b) every CTA: 64 x 64 tiles of the trailing matrix,          A_ij -= L_ik L_jk^T;
+//       the CTA that owns tile (k+1, k+1) updates it first and immediately factors it (look-ahead), producing
+//       L_{k+1,k+1} and W_{k+1} while the other CTAs finish the update.
+// All GEMMs run on the fp64 tensor path (mma.sync m8n8k4, DMMA) out of shared memory.  The back substitution
+// L^T x = y runs in the same kernel, one grid barrier per block, x_k = W_k^T y_k.
+// A non-positive or non-finite pivot sets info[0]; the host then falls back to the pivoted LU (kernels_solve.cuh).
+#pragma once
+#include "common.cuh"
+
+#define CC_NB 64
+#define CC_NT 256
+#define CC_PITCH 68          // operand pitch (doubles): conflict-free m8n8k4 fragment loads
+#define CC_DP 65             // pitch of the diagonal-block work arrays
+
+struct CholArgs {
+    double* A; int ld, n, ntot;      // augmented matrix, (n + 1) x ld row-major; ntot = n + 1
+    double* W;                       // nblk x 64 x 64: inverses of the diagonal blocks of L
+    double* yv;                      // n: running right-hand side of the back substitution
+    double* xs;                      // n: solution of the scaled system
+    unsigned* bar;                   // grid barrier counter, zeroed before the launch
+    int* info;
+    const double* sc; const int* idx; double* sol; int NEQ;
+};
+
+__device__ __forceinline__ unsigned cc_ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void cc_grid_barrier(unsigned* cnt, unsigned& target, unsigned G) {
+    target += G;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(cnt, 1u);
+        while (cc_ld_acquire(cnt) < target) {}
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void cc_dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// acc[r][c] (8 x 8 tiles) += As(16 rows) * Bs(8 WC rows)^T over K = 64; As / Bs point at the warp's first row
+template <int WC>
+__device__ __forceinline__ void cc_warp_gemm_nt(const double* As, const double* Bs, double (&acc)[2][WC][2], int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll 4
+    for (int kk = 0; kk < CC_NB; kk += 4) {
+        double a[2], b[WC];
+        a[0] = As[g * CC_PITCH + kk + t];
+        a[1] = As[(8 + g) * CC_PITCH + kk + t];
+#pragma unroll
+        for (int c = 0; c < WC; ++c) b[c] = Bs[(8 * c + g) * CC_PITCH + kk + t];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < WC; ++c) cc_dmma(acc[r][c][0], acc[r][c][1], a[r], b[c]);
+    }
+}
+
+// load rows [row0, row0 + nrows) x cols [col0, col0 + 64) of A into S (pitch CC_PITCH), zero outside [.., rmax) x [.., cmax)
+__device__ __forceinline__ void cc_load_tile(double* S, const double* __restrict__ A, int ld, int row0, int nrows, int rmax,
+                                             int col0, int cmax) {
+    for (int idx = threadIdx.x; idx < nrows * CC_NB; idx += CC_NT) {
+        const int r = idx >> 6, c = idx & 63;
+        const int gr = row0 + r, gc = col0 + c;
+        S[r * CC_PITCH + c] = (gr < rmax && gc < cmax) ? A[(size_t)gr * ld + gc] : 0.0;
+    }
+}
+
+__device__ __forceinline__ double cc_fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(fma(-x, y, 1.0), y, y);
+    y = fma(fma(-x, y, 1.0), y, y);
+    return y;
+}
+
+// Factor the diagonal block k (already updated): LDL^T-style elimination, register resident.  Thread (r, part) =
+// (tid >> 2, tid & 3) owns the entries j = part + 4 m of row r; a slot holds the matrix entry until its column is
+// eliminated and the entry of E = (unit lower factor)^{-1} afterwards (the same row operations applied to an
+// identity), so L and W = L^{-1} come out of one sweep.  Per column: one barrier; the pivot column and the E row of
+// the pivot are broadcast through a double-buffered 128-double strip of shared memory.
+__device__ void cc_potrf_inv(const CholArgs& a, int k, double* Dm, double* bufs) {
+    const int tid = threadIdx.x, r = tid >> 2, part = tid & 3;
+    const int k0 = k * CC_NB, kb = min(CC_NB, a.n - k0);
+    double V[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const int j = part + 4 * m;
+        double v = (r == j) ? 1.0 : 0.0;
+        if (r < kb && j <= r) v = a.A[(size_t)(k0 + r) * a.ld + k0 + j];
+        V[m] = v;
+    }
+    if (part == 0) bufs[r] = V[0];
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < CC_NB; ++c) {
+        const double* cb = bufs + (c & 1) * 128;
+        const double* rb = cb + 64;
+        double* cn = bufs + ((c + 1) & 1) * 128;
+        double* rn = cn + 64;
+        double piv = cb[c];
+        if (!(piv > 0.0) || !isfinite(piv)) {
+            if (tid == 0 && c < kb) atomicCAS(&a.info[0], 0, k0 + c + 1);
+            piv = 1.0;
+        }
+        const double rp = cc_fast_rcp(piv);
+        const double drc = cb[r];
+        if (part == (c & 3)) Dm[r * CC_DP + c] = (r > c) ? drc : (r == c ? piv : 0.0);
+        if (r > c) {
+            const double mm = drc * rp;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const int j = part + 4 * m;
+                if (m < (c >> 2)) V[m] = fma(-mm, rb[j], V[m]);
+                else if (m == (c >> 2)) {
+                    if (j < c) V[m] = fma(-mm, rb[j], V[m]);
+                    else if (j == c) V[m] = -mm;
+                    else if (j <= r) V[m] = fma(-mm, cb[j], V[m]);
+                } else if (j <= r) V[m] = fma(-mm, cb[j], V[m]);
+            }
+        } else if (r == c && part == (c & 3)) V[c >> 2] = 1.0;
+        if (c + 1 < CC_NB) {
+            if (part == ((c + 1) & 3) && r >= c + 1) cn[r] = V[(c + 1) >> 2];
+            if (r == c + 1) {
+#pragma unroll
+                for (int m = 0; m <= (c >> 2); ++m) {
+                    const int j = part + 4 * m;
+                    if (j <= c) rn[j] = V[m];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // L = (unscaled columns) diag(piv)^{-1/2},  W = diag(piv)^{-1/2} E
+    double* Wk = a.W + (size_t)k * CC_NB * CC_NB;
+    const double sr = 1.0 / sqrt(Dm[r * CC_DP + r]);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const int j = part + 4 * m;
+        Wk[r * CC_NB + j] = (j <= r) ? V[m] * sr : 0.0;
+    }
+    for (int idx = tid; idx < CC_NB * CC_NB; idx += CC_NT) {
+        const int rr = idx >> 6, c = idx & 63;
+        if (rr < kb && c <= rr) {
+            const double sc = sqrt(Dm[c * CC_DP + c]);
+            a.A[(size_t)(k0 + rr) * a.ld + k0 + c] = (rr == c) ? sc : Dm[rr * CC_DP + c] / sc;
+        }
+    }
+    __syncthreads();
+}
+
+// trailing tile (I, J) of panel k: A[i0.., j0..] -= L[i0.., k] L[j0.., k]^T
+__device__ void cc_update_tile(const CholArgs& a, int k0, int kb, int i0, int j0, double* As, double* Bs) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    cc_load_tile(As, a.A, a.ld, i0, CC_NB, a.ntot, k0, k0 + kb);
+    if (j0 != i0) cc_load_tile(Bs, a.A, a.ld, j0, CC_NB, a.n, k0, k0 + kb);
+    __syncthreads();
+    const double* Bq = (j0 != i0) ? Bs : As;
+    double acc[2][4][2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { acc[r][c][0] = 0.0; acc[r][c][1] = 0.0; }
+    const int wr = (warp >> 1) * 16, wc = (warp & 1) * 32;
+    cc_warp_gemm_nt<4>(As + wr * CC_PITCH, Bq + wc * CC_PITCH, acc, lane);
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int gi = i0 + wr + 8 * r + g;
+        if (gi >= a.ntot) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int gj = j0 + wc + 8 * c + 2 * t;
+            double* p = a.A + (size_t)gi * a.ld + gj;
+            if (gj < a.n && gj <= gi) p[0] -= acc[r][c][0];
+            if (gj + 1 < a.n && gj + 1 <= gi) p[1] -= acc[r][c][1];
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(CC_NT, 1) chol_coop_kernel(CholArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* As = reinterpret_cast<double*>(smem_raw);
+    double* Bs = As + CC_NB * CC_PITCH;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = gridDim.x, bid = blockIdx.x;
+    const int nblk = (a.n + CC_NB - 1) / CC_NB;
+    unsigned target = 0;
+
+    if (bid == 0) {
+        for (int c = tid; c < a.NEQ; c += CC_NT) a.sol[c] = 0.0;
+        cc_potrf_inv(a, 0, As, Bs);
+    }
+    cc_grid_barrier(a.bar, target, G);
+
+    for (int k = 0; k < nblk; ++k) {
+        const int k0 = k * CC_NB, kb = min(CC_NB, a.n - k0), r1 = k0 + kb;
+        // ---- (a) panel below the diagonal block: L_ik = A_ik W_k^T, 32-row slabs ----
+        const int nslab = (a.ntot - r1 + 31) / 32;
+        if (bid < nslab) {
+            const double* Wk = a.W + (size_t)k * CC_NB * CC_NB;
+            for (int idx = tid; idx < CC_NB * CC_NB; idx += CC_NT) Bs[(idx >> 6) * CC_PITCH + (idx & 63)] = Wk[idx];
+            for (int s = bid; s < nslab; s += G) {
+                const int row0 = r1 + 32 * s;
+                __syncthreads();
+                cc_load_tile(As, a.A, a.ld, row0, 32, a.ntot, k0, k0 + kb);
+                __syncthreads();
+                double acc[2][2][2];
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) { acc[r][c][0] = 0.0; acc[r][c][1] = 0.0; }
+                const int wr = (warp >> 2) * 16, wc = (warp & 3) * 16;
+                cc_warp_gemm_nt<2>(As + wr * CC_PITCH, Bs + wc * CC_PITCH, acc, lane);
+                const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int gi = row0 + wr + 8 * r + g;
+                    if (gi >= a.ntot) continue;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int cc = wc + 8 * c + 2 * t;
+                        double* p = a.A + (size_t)gi * a.ld + k0 + cc;
+                        if (cc < kb) p[0] = acc[r][c][0];
+                        if (cc + 1 < kb) p[1] = acc[r][c][1];
+                    }
+                }
+            }
+        }
+        cc_grid_barrier(a.bar, target, G);
+        // ---- (b) trailing update; the owner of tile (0, 0) factors the next diagonal block right away ----
+        const int T = (a.ntot - r1 + CC_NB - 1) / CC_NB, TC = (a.n - r1 + CC_NB - 1) / CC_NB;
+        if (TC > 0) {
+            const int dsg = (k + 1) % G;
+            if (bid == dsg) {
+                cc_update_tile(a, k0, kb, r1, r1, As, Bs);
+                if (G == 1) {
+                    for (int I = 1; I < T; ++I)
+                        for (int J = 0; J <= min(I, TC - 1); ++J) cc_update_tile(a, k0, kb, r1 + CC_NB * I, r1 + CC_NB * J, As, Bs);
+                }
+                cc_potrf_inv(a, k + 1, As, Bs);
+            } else {
+                // tiles in row-major order of the lower triangle, (0, 0) excluded: q' = I (I + 1) / 2 + J for I < TC,
+                // the extra block row I = TC (right-hand-side row) holds TC tiles
+                const int o = (bid - dsg - 1 + G) % G;          // 0 .. G-2
+                const int ntile = TC * (TC + 1) / 2 + (T > TC ? TC : 0);
+                for (int qq = 1 + o; qq < ntile; qq += G - 1) {
+                    int I = (int)((sqrtf(8.0f * (float)qq + 1.0f) - 1.0f) * 0.5f);
+                    while (I * (I + 1) / 2 > qq) --I;
+                    while ((I + 1) * (I + 2) / 2 <= qq) ++I;
+                    if (I > TC) I = TC;
+                    const int J = qq - I * (I + 1) / 2;
+                    cc_update_tile(a, k0, kb, r1 + CC_NB * I, r1 + CC_NB * J, As, Bs);
+                }
+            }
+        }
+        cc_grid_barrier(a.bar, target, G);
+    }
+
+    // ---- back substitution L^T x = y, y = row n ----
+    for (int c = bid * CC_NT + tid; c < a.n; c += G * CC_NT) a.yv[c] = a.A[(size_t)a.n * a.ld + c];
+    cc_grid_barrier(a.bar, target, G);
+    double* ys = As;                       // 64 staged right-hand-side entries
+    double* xk = As + 64;                  // 64 entries of the block solved last
+    for (int k = nblk - 1; k >= 0; --k) {
+        // x_{k+1} is final (none for k == nblk - 1).  The owner of block k applies it to y_k and solves x_k = W_k^T y_k;
+        // everyone else applies it to the rows above block k.
+        const int kn0 = (k + 1) * CC_NB, knb = (k + 1 < nblk) ? min(CC_NB, a.n - kn0) : 0;
+        const int k0 = k * CC_NB, kb = min(CC_NB, a.n - k0);
+        const bool owner = bid == k % G;
+        if (owner) {
+            if (tid < CC_NB) {
+                double s = 0.0;
+                if (tid < kb) {
+                    s = a.yv[k0 + tid];
+                    for (int c = 0; c < knb; ++c) s = fma(-a.A[(size_t)(kn0 + c) * a.ld + k0 + tid], a.xs[kn0 + c], s);
+                }
+                ys[tid] = s;
+            }
+            __syncthreads();
+            if (tid < kb) {
+                const double* Wk = a.W + (size_t)k * CC_NB * CC_NB;
+                double s = 0.0;
+                for (int r = tid; r < kb; ++r) s = fma(Wk[r * CC_NB + tid], ys[r], s);
+                a.xs[k0 + tid] = s;
+                a.sol[a.idx[k0 + tid]] = s * a.sc[k0 + tid];
+            }
+        }
+        if ((!owner || G == 1) && knb > 0 && k0 > 0) {
+            if (tid < CC_NB) xk[tid] = (tid < knb) ? a.xs[kn0 + tid] : 0.0;
+            __syncthreads();
+            const int o = (G > 1) ? (bid - (k % G) - 1 + G) % G : 0;
+            const int GO = (G > 1) ? G - 1 : 1;
+            for (int r = o * CC_NT + tid; r < k0; r += GO * CC_NT) {
+                double s = 0.0;
+                for (int c = 0; c < knb; ++c) s = fma(a.A[(size_t)(kn0 + c) * a.ld + r], xk[c], s);
+                a.yv[r] -= s;
+            }
+        }
+        cc_grid_barrier(a.bar, target, G);
+    }
+}

@@ -5,6 +5,7 @@
 #include "kernels_row.cuh"
 #include "kernels_fit.cuh"
 #include "kernels_solve.cuh"
+#include "kernels_chol.cuh"
 #include "kernels_apply.cuh"
 #include "kernels_row_fast.cuh"
 #include "kernels_fit_fast.cuh"
@@ -67,6 +68,9 @@ struct sfftb_plan {
     cd *kap, *lam, *nuJ;
     double *R, *RJ, *RT, *RJT;
     double *Aug, *sc, *diagU, *sol;
+    double *cholW, *cholY, *cholX;   // cooperative Cholesky: inverse diagonal blocks, back-substitution vectors
+    unsigned* cholBar;
+    int chol_coop;
     double* exportbuf;
     int ld, nsolve;
     int* info;                   // device: [0] cholesky pivot, [1] non-finite, [2] lu pivot
@@ -249,7 +253,7 @@ static int plan_free(sfftb_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     void* ptrs[] = {p->tabA, p->tabB_row, p->tabC_row, p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
-                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info};
+                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->info_h) cudaFreeHost(p->info_h);
     for (int k = 0; k < EV_COUNT; ++k) if (p->ev[k]) cudaEventDestroy(p->ev[k]);
@@ -376,6 +380,19 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
     CK(cudaMalloc(&p->sc, sizeof(double) * (size_t)p->nsolve));
     CK(cudaMalloc(&p->diagU, sizeof(double) * (size_t)p->nsolve));
     CK(cudaMalloc(&p->sol, sizeof(double) * (size_t)d.NEQ));
+    {
+        const int nblk = (p->nsolve + CC_NB - 1) / CC_NB;
+        CK(cudaMalloc(&p->cholW, sizeof(double) * (size_t)nblk * CC_NB * CC_NB));
+        CK(cudaMalloc(&p->cholY, sizeof(double) * (size_t)p->nsolve));
+        CK(cudaMalloc(&p->cholX, sizeof(double) * (size_t)p->nsolve));
+        CK(cudaMalloc(&p->cholBar, sizeof(unsigned) * 4));
+        const size_t csm = sizeof(double) * 2 * CC_NB * CC_PITCH;
+        CK(cudaFuncSetAttribute(chol_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+        int occ = 0, coop = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_coop_kernel, CC_NT, csm));
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
+        p->chol_coop = (occ >= 1 && coop && !env_int("SFFTB_CHOL_LEGACY", 0)) ? 1 : 0;
+    }
     CK(cudaMalloc(&p->info, sizeof(int) * 4));
     CK(cudaMallocHost(&p->info_h, sizeof(int) * 4));
     memset(p->info_h, 0, sizeof(int) * 4);
@@ -665,6 +682,17 @@ static int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, i
 
 static int run_cholesky(sfftb_plan* p) {
     const int n = p->nsolve, ntot = n + 1;
+    if (p->chol_coop) {
+        CholArgs ca;
+        ca.A = p->Aug; ca.ld = p->ld; ca.n = n; ca.ntot = ntot; ca.W = p->cholW; ca.yv = p->cholY; ca.xs = p->cholX;
+        ca.bar = p->cholBar; ca.info = p->info; ca.sc = p->sc; ca.idx = p->idxmap; ca.sol = p->sol; ca.NEQ = p->d.NEQ;
+        CK(cudaMemsetAsync(p->cholBar, 0, sizeof(unsigned) * 4, p->stream));
+        void* args[] = {&ca};
+        CK(cudaLaunchCooperativeKernel((void*)chol_coop_kernel, dim3(p->nsm), dim3(CC_NT), args,
+                                       sizeof(double) * 2 * CC_NB * CC_PITCH, p->stream));
+        p->launches++;
+        return 0;
+    }
     for (int k0 = 0; k0 < n; k0 += CH_NB) {
         const int kb = std::min(CH_NB, n - k0);
         const int below = ntot - (k0 + kb);
