@@ -8,6 +8,7 @@
 #include "kernels_chol.cuh"
 #include "kernels_apply.cuh"
 #include "kernels_row_fast.cuh"
+#include "kernels_row_v8.cuh"
 #include "kernels_fit_fast.cuh"
 #include "kernels_fit_seg.cuh"
 
@@ -60,6 +61,10 @@ struct sfftb_plan {
     // tables
     cd *tw0, *tw1, *twMf, *twH, *Q;
     cd *tabA, *tabB_row, *tabC_row;   // register-engine twiddle tables
+    cd *vt8_8, *vt64_8, *vt64_4, *vt256_4, *vt512_4;   // 8-values-per-thread engine tables
+    RowV8Args rowv;
+    int row_v8;                  // 0 or the engine length H
+    size_t smem_rowv;
     double* PHI;
     int *idxmap, *ident;
     // workspaces
@@ -99,7 +104,8 @@ struct sfftb_plan {
     ReduceArgs red;
     PolyReduceArgs pred;
     FillArgs fill;
-    size_t smem_fit, smem_fir, smem_row;
+    size_t smem_fit, smem_fir, smem_row, smem_fir2, smem_fir3;
+    cd* firTaps; double* firCA;
     int grid_fit;
     int nrowsK, nrowsL;
     // state
@@ -252,8 +258,8 @@ static size_t fit_smem_bytes(const ColArgs& c, int PB) {
 static int plan_free(sfftb_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
-    void* ptrs[] = {p->tabA, p->tabB_row, p->tabC_row, p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
-                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar};
+    void* ptrs[] = {p->vt8_8, p->vt64_8, p->vt64_4, p->vt256_4, p->vt512_4, p->tabA, p->tabB_row, p->tabC_row, p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
+                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->firTaps, p->firCA};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->info_h) cudaFreeHost(p->info_h);
     for (int k = 0; k < EV_COUNT; ++k) if (p->ev[k]) cudaEventDestroy(p->ev[k]);
@@ -357,6 +363,12 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         memcpy(fa.plane_of, p->cfit.plane_of, sizeof fa.plane_of);
         fa.tw1 = p->tw1;
         p->smem_fir = sizeof(cd) * (size_t)d.Fij * d.L0 + sizeof(double) * (size_t)d.Fij;
+        const size_t Wst = FIR2_CH + 2 * (size_t)d.w0;
+        const size_t WP3 = (FIR3_CH + 2 * (size_t)d.w0 + FIR3_R - 1) / FIR3_R;
+        p->smem_fir3 = sizeof(cd) * (size_t)d.Fij * d.L0 + 128 + sizeof(cd) * (size_t)(d.DK + 1) * FIR3_R * WP3 + sizeof(double) * FIR3_R * WP3;
+        CK(cudaMalloc(&p->firTaps, sizeof(cd) * (size_t)NH * d.Fij * d.L0));
+        CK(cudaMalloc(&p->firCA, sizeof(double) * 16));
+        p->smem_fir2 = sizeof(cd) * (size_t)d.Fij * d.L0 + 128 + sizeof(cd) * (size_t)(d.DK + 2) * Wst + sizeof(double) * Wst;
     }
 
     // ---- workspaces ----
@@ -466,6 +478,24 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         if (set_smem(row_fwd_kernel<float, double2>, p->smem_row) || set_smem(row_fwd_kernel<double, double2>, p->smem_row)) return SFFTB_ECUDA;
         if (set_smem(row_inv_kernel<double2, float>, p->smem_row) || set_smem(row_inv_kernel<double2, double>, p->smem_row)) return SFFTB_ECUDA;
     }
+    if (p->smem_fir3 <= p->max_smem) {
+#define SET_FIR3(DKK)                                                                                             \
+        if (d.DK == DKK) {                                                                                            \
+            if (f32) { if (set_smem(apply_fir3_kernel<float2, DKK>, p->smem_fir3)) return SFFTB_ECUDA; }               \
+            else     { if (set_smem(apply_fir3_kernel<double2, DKK>, p->smem_fir3)) return SFFTB_ECUDA; }              \
+        }
+        SET_FIR3(0) SET_FIR3(1) SET_FIR3(2) SET_FIR3(3)
+#undef SET_FIR3
+    }
+    if (p->smem_fir2 <= p->max_smem) {
+#define SET_FIR2(DKK)                                                                                             \
+        if (d.DK == DKK) {                                                                                            \
+            if (f32) { if (set_smem(apply_fir2_kernel<float2, DKK>, p->smem_fir2)) return SFFTB_ECUDA; }               \
+            else     { if (set_smem(apply_fir2_kernel<double2, DKK>, p->smem_fir2)) return SFFTB_ECUDA; }              \
+        }
+        SET_FIR2(0) SET_FIR2(1) SET_FIR2(2) SET_FIR2(3)
+#undef SET_FIR2
+    }
     const size_t red_smem = sizeof(cd) * (size_t)NH;
     if (set_smem(lag_reduce_kernel, red_smem) || set_smem(poly_reduce_kernel, red_smem)) return SFFTB_ECUDA;
     const size_t bs_smem = sizeof(double) * ((size_t)p->nsolve + CH_NB + CH_NB * (CH_NB + 1));
@@ -487,6 +517,26 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         p->rinvf.r = rf; p->rinvf.scale = p->rinv.scale; p->rinvf.Fpq = d.Fpq;
         memcpy(p->rinvf.p_of, p->rinv.p_of, 16); memcpy(p->rinvf.q_of, p->rinv.q_of, 16);
         p->row_fast = r.H;
+    }
+    p->row_v8 = 0;
+    if (r.packed && !env_int("SFFTB_ROW_NOV8", 0) && (r.H == 256 || r.H == 512 || r.H == 1024 || r.H == 2048)) {
+        if (upload_engine_table(8, 8, &p->vt8_8) || upload_engine_table(64, 8, &p->vt64_8) || upload_engine_table(64, 4, &p->vt64_4) ||
+            upload_engine_table(256, 4, &p->vt256_4) || upload_engine_table(512, 4, &p->vt512_4)) return SFFTB_ECUDA;
+        RowV8Args& rv = p->rowv;
+        rv.N0 = N0; rv.N1 = N1; rv.NH = NH; rv.H = r.H;
+        rv.nit = std::max(1, env_int("SFFTB_ROW_NIT", 2));
+        rv.tabs.t8_8 = p->vt8_8; rv.tabs.t64_8 = p->vt64_8; rv.tabs.t64_4 = p->vt64_4; rv.tabs.t256_4 = p->vt256_4; rv.tabs.t512_4 = p->vt512_4;
+        rv.tw1 = p->tw1;
+        const int RBI = ROWV_NT / (r.H / 8);
+        p->smem_rowv = sizeof(cd) * (size_t)RBI * (r.H + r.H / 8 + 8);
+#define SET_ROWV(HH)                                                                                              \
+        if (r.H == HH) {                                                                                              \
+            if (f32) { if (set_smem(row_fwd_v8_kernel<float, float2, HH>, p->smem_rowv) || set_smem(row_fwd_v8_kernel<double, float2, HH>, p->smem_rowv)) return SFFTB_ECUDA; } \
+            else     { if (set_smem(row_fwd_v8_kernel<float, double2, HH>, p->smem_rowv) || set_smem(row_fwd_v8_kernel<double, double2, HH>, p->smem_rowv)) return SFFTB_ECUDA; } \
+        }
+        SET_ROWV(256) SET_ROWV(512) SET_ROWV(1024) SET_ROWV(2048)
+#undef SET_ROWV
+        p->row_v8 = r.H;
     }
     p->fit_fast = 0;
     if (N0 % 256 == 0 && 4 * d.w0 + 1 <= 256 && !env_int("SFFTB_FIT_GENERIC", 0) && d.Fij * (d.Fij - 1) / 2 <= 48) {
@@ -657,6 +707,21 @@ static int stage_in(sfftb_plan* p, const void* src, int memkind, int dtype, void
 template <typename TSt>
 static int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj) {
     const size_t esz2 = dtype == SFFTB_F64 ? 16 : 8;
+    if (p->row_v8 && ((uintptr_t)img % esz2) == 0) {
+        const int H = p->row_v8, RBI = ROWV_NT / (H / 8);
+        const int ngroups = (p->d.N0 + RBI - 1) / RBI;
+        const int nbatch = (ngroups + p->rowv.nit - 1) / p->rowv.nit;
+        const int grid = std::min(nbatch, p->nsm);
+#define RUN_ROWV(HH)                                                                                                   \
+        if (H == HH) {                                                                                                 \
+            if (dtype == SFFTB_F64) row_fwd_v8_kernel<double, TSt, HH><<<grid, ROWV_NT, p->smem_rowv, p->stream>>>(p->rowv, (const double*)img, out, nj); \
+            else row_fwd_v8_kernel<float, TSt, HH><<<grid, ROWV_NT, p->smem_rowv, p->stream>>>(p->rowv, (const float*)img, out, nj);                     \
+        }
+        RUN_ROWV(256) RUN_ROWV(512) RUN_ROWV(1024) RUN_ROWV(2048)
+#undef RUN_ROWV
+        CKL(p);
+        return 0;
+    }
     if (p->row_fast && ((uintptr_t)img % esz2) == 0) {
         const int H = p->row_fast, RB = ROWF_NT / (H / 16);
         const int grid = (p->d.N0 + RB - 1) / RB;
@@ -807,7 +872,19 @@ static int apply_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype
     if (launch_row_fwd<TSt>(p, dI, dtype, (TSt*)p->gI, d.DK + 1)) return SFFTB_ECUDA;
     if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
     EVREC(p, EV_AROWS);
-    {
+    if (p->smem_fir3 <= p->max_smem && !env_int("SFFTB_FIR_V2", 0) && !env_int("SFFTB_FIR_V1", 0)) {
+        fir_taps_kernel<<<d.N1 / 2 + 1, 128, 0, p->stream>>>(p->fir, dsol, p->firTaps, p->firCA);
+        CKL(p);
+        dim3 grd(d.N1 / 2 + 1, (d.N0 + FIR3_CH - 1) / FIR3_CH);
+#define RUN_FIR3(DKK) if (d.DK == DKK) apply_fir3_kernel<TSt, DKK><<<grd, FIR3_NT, p->smem_fir3, p->stream>>>(p->fir, (const TSt*)p->gI, (const TSt*)p->gJ, p->firTaps, p->firCA, (TSt*)p->gJ);
+        RUN_FIR3(0) RUN_FIR3(1) RUN_FIR3(2) RUN_FIR3(3)
+#undef RUN_FIR3
+    } else if (p->smem_fir2 <= p->max_smem && !env_int("SFFTB_FIR_V1", 0)) {
+        dim3 grd(d.N1 / 2 + 1, (d.N0 + FIR2_CH - 1) / FIR2_CH);
+#define RUN_FIR2(DKK) if (d.DK == DKK) apply_fir2_kernel<TSt, DKK><<<grd, FIR2_NT, p->smem_fir2, p->stream>>>(p->fir, (const TSt*)p->gI, (const TSt*)p->gJ, dsol, (TSt*)p->gJ);
+        RUN_FIR2(0) RUN_FIR2(1) RUN_FIR2(2) RUN_FIR2(3)
+#undef RUN_FIR2
+    } else {
         dim3 grd(d.N1 / 2 + 1, (d.N0 + FIR_CHUNK - 1) / FIR_CHUNK);
         apply_fir_kernel<TSt><<<grd, FIR_NT, p->smem_fir, p->stream>>>(p->fir, (const TSt*)p->gI, (const TSt*)p->gJ, dsol, (TSt*)p->gJ);
     }
