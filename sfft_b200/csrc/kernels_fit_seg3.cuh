@@ -1,0 +1,299 @@
+// kernels_fit_seg3.cuh -- segmented fit column pass, warp-specialised (KerPolyOrder <= 2).
+//
+// Same mathematics, inputs and outputs as fit_seg_kernel (kernels_fit_seg.cuh).  The CTA has 16 warps:
+//   * warps 8..15 ("transform warps", 104 registers after setmaxnreg.dec): one 256-point forward FFT per warp at a
+//     time on the 8-values-per-thread engine (fft_vpt.cuh; no CTA barrier inside a transform), jobs
+//     (segment, plane-role) handed out round-robin, spectra written into a two-slot ring;
+//   * warps 0..7 ("product warps", 152 registers after setmaxnreg.inc): thread = frequency bin, keeps the
+//     Fij (Fij + 1) / 2 + Fij complex cross-spectrum accumulators in registers for the whole column, consumes a ring
+//     slot as soon as its 2 Fij + 1 spectra are complete, issues the cp.async prefetch of the row windows two
+//     segments ahead, and accumulates the column moments for the background cross terms.
+// The two groups are decoupled by mbarriers (slot full / slot empty / window landed), so transforms of segment s + 1
+// overlap the products of segment s and no warp waits on a CTA-wide barrier inside the segment loop.  One inverse
+// transform per pair per column (all 16 warps) yields the lags.
+#pragma once
+#include "fft_vpt.cuh"
+#include "kernels_fit_seg.cuh"
+
+#define FS3_NT 512
+#define FS3_M 256
+#define FS3_PITCH 288
+#define FS3_NSTG 4
+#define FS3_NMT 64           // product threads that also accumulate the column moments
+
+__device__ __forceinline__ unsigned fs3_saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fs3_mbar_init(unsigned long long* b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fs3_saddr(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fs3_mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fs3_saddr(b)) : "memory");
+}
+__device__ __forceinline__ void fs3_mbar_wait(unsigned long long* b, unsigned parity) {
+    unsigned done = 0;
+    int spins = 0;
+    while (true) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(fs3_saddr(b)), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > (1 << 24)) __trap();          // watchdog: a protocol error must abort, not hang the GPU
+    }
+}
+__device__ __forceinline__ void fs3_cp_async_arrive(unsigned long long* b) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(fs3_saddr(b)) : "memory");
+}
+__device__ __forceinline__ void fs3_bar0() { asm volatile("bar.sync 0;" ::: "memory"); }
+__device__ __forceinline__ void fs3_barP() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// column_poly_rows for an explicit thread subset
+template <typename TSt>
+__device__ void column_poly_rows_sub(const SegFitArgs& fa, const TSt* __restrict__ gI, int k1, const cd* mom, cd* __restrict__ kaprow,
+                                     int tid, int nthr)
+{
+    const ColArgs& a = fa.c;
+    const double inv0 = 1.0 / (double)a.N0;
+    const int np = a.DB + 1;
+    for (int idx = tid; idx < a.Fij * np * a.nlj0; idx += nthr) {
+        const int ia = idx % a.nlj0;
+        const int p = (idx / a.nlj0) % np;
+        const int A = idx / (a.nlj0 * np);
+        const int i = a.pl_i[A], j = a.pl_j[A];
+        const int sh = ia - a.w0;
+        const double beta = sh * inv0;
+        cd v = cmake(0, 0);
+        for (int e = 0; e <= p; ++e) {
+            const double c = binom_small(p, e) * ipow(beta, p - e);
+            const cd m = mom[j * SFFTB_MAXE + i + e];
+            v.x += c * m.x; v.y += c * m.y;
+        }
+        if (p > 0 && sh != 0) {
+            const TSt* col = gI + ((size_t)j * a.NH + k1) * a.N0;
+            const int rbeg = sh > 0 ? a.N0 - sh : 0;
+            const int rend = sh > 0 ? a.N0 : -sh;
+            const double wrap = sh > 0 ? -1.0 : 1.0;
+            for (int r = rbeg; r < rend; ++r) {
+                const double cx = (r + 1) * inv0;
+                const double corr = ipow(cx + beta + wrap, p) - ipow(cx + beta, p);
+                const double c = ipow(cx, i) * corr;
+                const cd g = load_c(col + r);
+                v.x += c * g.x; v.y += c * g.y;
+            }
+        }
+        for (int q = 0; q + p <= a.DB; ++q) {
+            const int pq = fa.pq_of[p][q];
+            kaprow[fa.nK + (A * a.Fpq + pq) * a.nlj0 + ia] = cmulcj(v, fa.Q[(size_t)q * a.NH + k1]);
+        }
+    }
+    for (int p = tid; p < np; p += nthr)
+        for (int q = 0; q + p <= a.DB; ++q)
+            kaprow[fa.nK + fa.nLT + fa.pq_of[p][q]] = cmulcj(mom[a.nj * SFFTB_MAXE + p], fa.Q[(size_t)q * a.NH + k1]);
+}
+
+// inverse transform of one accumulated cross spectrum (plane `pl` of the ring) by one warp; keeps the lags of pair `job`
+template <int NPAIR>
+__device__ __forceinline__ void fs3_inverse_job(const SegFitArgs& fa, const VTabs& vt, cd* plane, int job, int lane, cd* __restrict__ kaprow)
+{
+    const ColArgs& a = fa.c;
+    cd v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = plane[VPAD(lane + 32 * q)];
+    __syncwarp();
+    vfft<FS3_M>(v, plane, lane, vt, +1.0, 0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) plane[VPAD(lane + 32 * q)] = v[q];
+    __syncwarp();
+    const bool om = job < NPAIR;
+    const int lim = om ? 2 * a.w0 : a.w0;
+    const int rowbase = om ? job * a.nl0 : fa.nOm + (job - NPAIR) * a.nlj0;
+    const double invM = 1.0 / (double)FS3_M;
+    for (int l = lane; l <= 2 * lim; l += 32) {
+        const int m0 = l - lim;
+        kaprow[rowbase + l] = cscale(plane[VPAD(m0 & (FS3_M - 1))], invM);
+    }
+}
+
+template <typename TSt, int DK>
+__global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTabs vt_g, const TSt* __restrict__ gI, const TSt* __restrict__ gJ,
+                                                             cd* __restrict__ kap)
+{
+    constexpr int Fij = (DK + 1) * (DK + 2) / 2;
+    constexpr int NPAIR = Fij * (Fij + 1) / 2;
+    constexpr int NACC = NPAIR + Fij;
+    constexpr int NP = 2 * Fij + 1;
+    constexpr int NSRC = DK + 2;
+    constexpr int NPL = 2 * NP;                       // planes in the ring (two slots)
+    static_assert(NPL >= 16 || NACC <= NPL, "ring too small for the inverse batches");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const ColArgs& a = fa.c;
+    cd* spec = reinterpret_cast<cd*>(smem_raw);                                   // NPL (>= 16) planes
+    constexpr int NPLA = NPL > 16 ? NPL : 16;
+    cd* mom = spec + NPLA * FS3_PITCH;
+    cd* macc = mom + 4 * SFFTB_MAXE;
+    cd* tw8 = macc + FSG_MSLOTS * FS3_NMT;          // 56 entries  (Ns = 8,  R = 8)
+    cd* tw64 = tw8 + 56;                            // 192 entries (Ns = 64, R = 4)
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tw64 + 192);
+    TSt* stage = reinterpret_cast<TSt*>(bars + 8);
+    unsigned long long* full = bars;          // [2]  count NP   (one arrive per transform job)
+    unsigned long long* empty = bars + 2;     // [2]  count 8    (one arrive per product warp)
+    unsigned long long* landed = bars + 4;    // [4]  count 256  (cp.async arrivals of the product threads)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double inv0 = 1.0 / (double)a.N0;
+    const int h = fa.h, S = fa.S, nseg = fa.nseg;
+
+    if (tid == 0) {
+        fs3_mbar_init(full + 0, NP); fs3_mbar_init(full + 1, NP);
+        fs3_mbar_init(empty + 0, 8); fs3_mbar_init(empty + 1, 8);
+        for (int b = 0; b < FS3_NSTG; ++b) fs3_mbar_init(landed + b, 256);
+    }
+    // the engine's twiddle tables live in shared memory: with ~200 KB of shared memory carved out there is next to
+    // no L1 left, and a table miss costs an L2 round trip in the middle of a transform
+    for (int i = tid; i < 56; i += FS3_NT) tw8[i] = vt_g.t8_8[i];
+    for (int i = tid; i < 192; i += FS3_NT) tw64[i] = vt_g.t64_4[i];
+    VTabs vt = vt_g;
+    vt.t8_8 = tw8; vt.t64_4 = tw64;
+    __syncthreads();
+    int g = 0;                                // global segment counter (ring phases continue across columns)
+
+    if (warp < 8) {
+        // ======================================= product warps =======================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        for (int k1 = blockIdx.x; k1 < a.NH; k1 += gridDim.x, g += nseg) {
+            cd acc[NACC];
+#pragma unroll
+            for (int q = 0; q < NACC; ++q) acc[q] = cmake(0.0, 0.0);
+            cd* kaprow = kap + (size_t)k1 * fa.nrows;
+            if (tid < FS3_NMT)
+                for (int s = 0; s < FSG_MSLOTS; ++s) macc[s * FS3_NMT + tid] = cmake(0.0, 0.0);
+            // window prefetch: element tid of every stored plane, two segments ahead
+            auto issue = [&](int s) {
+                const int buf = (g + s) & (FS3_NSTG - 1);
+                const int r = wrap_row(s * S - h + tid, a.N0);
+#pragma unroll
+                for (int jj = 0; jj < NSRC; ++jj) {
+                    const TSt* col = (jj == DK + 1) ? gJ + (size_t)k1 * a.N0 : gI + ((size_t)jj * a.NH + k1) * a.N0;
+                    cp_async_elem(stage + ((size_t)buf * NSRC + jj) * FS3_M + tid, col + r);
+                }
+                fs3_cp_async_arrive(landed + buf);
+            };
+            for (int s = 0; s < 2 && s < nseg; ++s) issue(s);
+            for (int s = 0; s < nseg; ++s) {
+                const int gs = g + s, slot = gs & 1;
+                fs3_mbar_wait(full + slot, (gs >> 1) & 1);
+                {
+                    const cd* sp = spec + (size_t)slot * NP * FS3_PITCH + VPAD(tid);
+                    cd fA[Fij], fB[Fij];
+#pragma unroll
+                    for (int A = 0; A < Fij; ++A) {
+                        fA[A] = sp[A * FS3_PITCH];
+                        fB[A] = sp[(Fij + A) * FS3_PITCH];
+                    }
+                    const cd fJ = sp[2 * Fij * FS3_PITCH];
+                    int q = 0;
+#pragma unroll
+                    for (int A = 0; A < Fij; ++A)
+#pragma unroll
+                        for (int B = A; B < Fij; ++B) {
+                            acc[q].x = fma(fA[A].x, fB[B].x, acc[q].x); acc[q].x = fma(fA[A].y, fB[B].y, acc[q].x);
+                            acc[q].y = fma(fA[A].x, fB[B].y, acc[q].y); acc[q].y = fma(-fA[A].y, fB[B].x, acc[q].y);
+                            ++q;
+                        }
+#pragma unroll
+                    for (int A = 0; A < Fij; ++A) {
+                        acc[NPAIR + A].x = fma(fA[A].x, fJ.x, acc[NPAIR + A].x); acc[NPAIR + A].x = fma(fA[A].y, fJ.y, acc[NPAIR + A].x);
+                        acc[NPAIR + A].y = fma(fA[A].x, fJ.y, acc[NPAIR + A].y); acc[NPAIR + A].y = fma(-fA[A].y, fJ.x, acc[NPAIR + A].y);
+                    }
+                }
+                // column moments of this segment's core rows (64 threads, 4 rows each, private shared-memory slots)
+                if (tid < FS3_NMT) {
+                    fs3_mbar_wait(landed + (gs & (FS3_NSTG - 1)), (gs >> 2) & 1);
+                    const TSt* st = stage + (size_t)(gs & (FS3_NSTG - 1)) * NSRC * FS3_M;
+                    const int c0 = s * S, Sc = min(S, a.N0 - c0);
+                    for (int n = h + tid; n < h + Sc; n += FS3_NMT) {
+                        const double cx = (c0 + (n - h) + 1) * inv0;
+#pragma unroll
+                        for (int jj = 0; jj < NSRC; ++jj) {
+                            const int ne = (jj == DK + 1) ? a.DB + 1 : DK - jj + a.DB + 1;
+                            cd gg = load_c(st + jj * FS3_M + n);
+                            for (int e = 0; e < ne; ++e) {
+                                cd* sl = macc + (jj * SFFTB_MAXE + e) * FS3_NMT + tid;
+                                *sl = cadd(*sl, gg);
+                                gg = cscale(gg, cx);
+                            }
+                        }
+                    }
+                }
+                // the arrive certifies: slot consumed AND window buffer of segment s no longer read by this warp, so
+                // the prefetch of segment s + 2 (same buffer as s - 2) issued after the next full-wait is safe
+                __syncwarp();
+                if (lane == 0) fs3_mbar_arrive(empty + slot);
+                if (s + 2 < nseg) issue(s + 2);
+            }
+            // ---- column moments -> background cross-term rows (product warps only) ----
+            fs3_barP();
+            if (tid < FSG_MSLOTS) {
+                cd sm = cmake(0.0, 0.0);
+                for (int t = 0; t < FS3_NMT; ++t) sm = cadd(sm, macc[tid * FS3_NMT + t]);
+                mom[tid] = sm;
+            }
+            fs3_barP();
+            column_poly_rows_sub(fa, gI, k1, mom, kaprow, tid, 256);
+            fs3_bar0();                                    // (A) all transforms and products of the column are done
+#pragma unroll
+            for (int b0 = 0; b0 < NACC; b0 += 16) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                    if (b0 + q < NACC) spec[q * FS3_PITCH + VPAD(tid)] = acc[b0 + q];
+                fs3_bar0();
+                const int job = b0 + warp;
+                if (job < NACC) fs3_inverse_job<NPAIR>(fa, vt, spec + warp * FS3_PITCH, job, lane, kaprow);
+                fs3_bar0();
+            }
+        }
+    } else {
+        // ====================================== transform warps ======================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+        const int fw = warp - 8;
+        for (int k1 = blockIdx.x; k1 < a.NH; k1 += gridDim.x, g += nseg) {
+            cd* kaprow = kap + (size_t)k1 * fa.nrows;
+            for (int id = fw; id < nseg * NP; id += 8) {
+                const int s = id / NP, p = id - s * NP;
+                const int gs = g + s, slot = gs & 1;
+                const bool roleA = p < Fij, isJ = p == 2 * Fij;
+                const int pl = roleA ? p : (isJ ? 0 : p - Fij);
+                const int my_i = isJ ? 0 : a.pl_i[pl];
+                const int my_src = isJ ? DK + 1 : a.pl_j[pl];
+                const int c0 = s * S, Sc = min(S, a.N0 - c0);
+                fs3_mbar_wait(landed + (gs & (FS3_NSTG - 1)), (gs >> 2) & 1);
+                if (gs >= 2) fs3_mbar_wait(empty + slot, ((gs >> 1) - 1) & 1);
+                const TSt* src = stage + ((size_t)(gs & (FS3_NSTG - 1)) * NSRC + my_src) * FS3_M;
+                cd* plane = spec + ((size_t)slot * NP + p) * FS3_PITCH;
+                cd v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int n = lane + 32 * q;
+                    cd gg = cmake(0.0, 0.0);
+                    if (!roleA || (n >= h && n < h + Sc)) {
+                        gg = load_c(src + n);
+                        if (my_i > 0) {
+                            const double cx = (wrap_row(c0 - h + n, a.N0) + 1) * inv0;
+                            gg = cscale(gg, my_i == 1 ? cx : (my_i == 2 ? cx * cx : cx * cx * cx));
+                        }
+                    }
+                    v[q] = gg;
+                }
+                vfft<FS3_M>(v, plane, lane, vt, -1.0, 0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) plane[VPAD(lane + 32 * q)] = v[q];
+                __syncwarp();
+                if (lane == 0) fs3_mbar_arrive(full + slot);
+            }
+            fs3_bar0();                                    // (A)
+#pragma unroll
+            for (int b0 = 0; b0 < NACC; b0 += 16) {
+                fs3_bar0();
+                const int job = b0 + warp;
+                if (job < NACC) fs3_inverse_job<NPAIR>(fa, vt, spec + warp * FS3_PITCH, job, lane, kaprow);
+                fs3_bar0();
+            }
+        }
+    }
+}

@@ -11,6 +11,7 @@
 #include "kernels_row_v8.cuh"
 #include "kernels_fit_fast.cuh"
 #include "kernels_fit_seg.cuh"
+#include "kernels_fit_seg3.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -63,6 +64,8 @@ struct sfftb_plan {
     cd *tabA, *tabB_row, *tabC_row;   // register-engine twiddle tables
     cd *vt8_8, *vt64_8, *vt64_4, *vt256_4, *vt512_4;   // 8-values-per-thread engine tables
     RowV8Args rowv;
+    VTabs vtabs;
+    size_t smem_sfit3;
     int row_v8;                  // 0 or the engine length H
     size_t smem_rowv;
     double* PHI;
@@ -519,9 +522,10 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         p->row_fast = r.H;
     }
     p->row_v8 = 0;
+    if (upload_engine_table(8, 8, &p->vt8_8) || upload_engine_table(64, 8, &p->vt64_8) || upload_engine_table(64, 4, &p->vt64_4) ||
+        upload_engine_table(256, 4, &p->vt256_4) || upload_engine_table(512, 4, &p->vt512_4)) return SFFTB_ECUDA;
+    p->vtabs.t8_8 = p->vt8_8; p->vtabs.t64_8 = p->vt64_8; p->vtabs.t64_4 = p->vt64_4; p->vtabs.t256_4 = p->vt256_4; p->vtabs.t512_4 = p->vt512_4;
     if (r.packed && !env_int("SFFTB_ROW_NOV8", 0) && (r.H == 256 || r.H == 512 || r.H == 1024 || r.H == 2048)) {
-        if (upload_engine_table(8, 8, &p->vt8_8) || upload_engine_table(64, 8, &p->vt64_8) || upload_engine_table(64, 4, &p->vt64_4) ||
-            upload_engine_table(256, 4, &p->vt256_4) || upload_engine_table(512, 4, &p->vt512_4)) return SFFTB_ECUDA;
         RowV8Args& rv = p->rowv;
         rv.N0 = N0; rv.N1 = N1; rv.NH = NH; rv.H = r.H;
         rv.nit = std::max(1, env_int("SFFTB_ROW_NIT", 2));
@@ -602,6 +606,22 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
 #undef SET_SFIT
         p->grid_sfit = std::min(NH, p->nsm);
         p->fit_seg = 1;
+        {
+            const int NPs = 2 * d.Fij + 1;
+            const int npla = std::max(2 * NPs, 16);
+            p->smem_sfit3 = sizeof(cd) * ((size_t)npla * FS3_PITCH + 4 * SFFTB_MAXE + (size_t)FSG_MSLOTS * FS3_NMT + 56 + 192) + 64 +
+                            csz * FS3_NSTG * (size_t)(d.DK + 2) * FS3_M;
+            if (p->smem_sfit3 <= p->max_smem && !env_int("SFFTB_SEG_V2", 0)) {
+#define SET_SFIT3(DKK)                                                                                            \
+                if (d.DK == DKK) {                                                                                    \
+                    if (f32) { if (set_smem(fit_seg3_kernel<float2, DKK>, p->smem_sfit3)) return SFFTB_ECUDA; }       \
+                    else     { if (set_smem(fit_seg3_kernel<double2, DKK>, p->smem_sfit3)) return SFFTB_ECUDA; }      \
+                }
+                SET_SFIT3(0) SET_SFIT3(1) SET_SFIT3(2)
+#undef SET_SFIT3
+                p->fit_seg = 2;
+            }
+        }
         d.fold = sf.nseg; d.sub_len = sf.S;
     }
     if (p->row_fast) {
@@ -808,7 +828,12 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype) 
     if (launch_row_fwd<TSt>(p, dI, dtype, (TSt*)p->gI, d.DK + 1)) return SFFTB_ECUDA;
     if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
     EVREC(p, EV_ROWS);
-    if (p->fit_seg) {
+    if (p->fit_seg == 2) {
+        const int DK = d.DK;
+        if (DK == 0) fit_seg3_kernel<TSt, 0><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap2);
+        else if (DK == 1) fit_seg3_kernel<TSt, 1><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap2);
+        else fit_seg3_kernel<TSt, 2><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap2);
+    } else if (p->fit_seg) {
         const int DK = d.DK;
         if (DK == 0) fit_seg_kernel<TSt, 0><<<p->grid_sfit, FSG_NT, p->smem_sfit, p->stream>>>(p->sfit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap2);
         else if (DK == 1) fit_seg_kernel<TSt, 1><<<p->grid_sfit, FSG_NT, p->smem_sfit, p->stream>>>(p->sfit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap2);
