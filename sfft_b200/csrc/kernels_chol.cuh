@@ -17,6 +17,9 @@
 #include "common.cuh"
 
 #define CC_NB 64
+#ifndef CC_CTAS_PER_SM
+#define CC_CTAS_PER_SM 1
+#endif
 #define CC_NT 256
 #define CC_PITCH 68          // operand pitch (doubles): conflict-free m8n8k4 fragment loads
 #define CC_DP 65             // pitch of the diagonal-block work arrays
@@ -29,7 +32,11 @@ struct CholArgs {
     unsigned* bar;                   // grid barrier counter, zeroed before the launch
     int* info;
     const double* sc; const int* idx; double* sol; int NEQ;
+    unsigned long long* dbg;         // optional: globaltimer stamps of panel phases (NULL = off)
 };
+
+__device__ __forceinline__ unsigned long long cc_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define CC_STAMP(slot) do { if (a.dbg && tid == 0) a.dbg[(slot)] = cc_gtime(); } while (0)
 
 __device__ __forceinline__ unsigned cc_ld_acquire(const unsigned* p) {
     unsigned v;
@@ -90,77 +97,98 @@ __device__ __forceinline__ double cc_fast_rcp(double x) {
     return y;
 }
 
-// Factor the diagonal block k (already updated): LDL^T-style elimination, register resident.  Thread (r, part) =
-// (tid >> 2, tid & 3) owns the entries j = part + 4 m of row r; a slot holds the matrix entry until its column is
-// eliminated and the entry of E = (unit lower factor)^{-1} afterwards (the same row operations applied to an
-// identity), so L and W = L^{-1} come out of one sweep.  Per column: one barrier; the pivot column and the E row of
-// the pivot are broadcast through a double-buffered 128-double strip of shared memory.
+// Factor the diagonal block k (already updated): LDL^T-style elimination, register resident, compact code (the
+// column loop is NOT unrolled: a fully unrolled version is ~0.5 MB of SASS and runs out of the instruction cache).
+// Every thread plays two roles with 16 registers each, chosen so that no register is ever indexed dynamically:
+//   * D role, column owned: thread (j, part) = (tid >> 2, tid & 3) holds D[r][j], r = part + 4 m.  The pivot COLUMN c
+//     is needed by everybody; its four owners publish all their slots.
+//   * E role, row owned:    thread (r, part) holds E[r][j], j = part + 4 m, E = (unit lower factor)^{-1} built by
+//     applying the same row operations to an identity.  The pivot ROW c is needed; its four owners publish all slots.
+// One barrier per column; column and row strips are double buffered in shared memory.
+// Output: L (scaled) into A, W = L^{-1} into a.W.   Dm: 64 x 65 doubles of scratch, bufs: 2 x 128 doubles.
+// strips are stored padded (16 bytes after every 16 entries) so that the four 128-byte blocks a warp reads with one
+// LDS.128 land in different banks
+#define CC_SP(i) ((i) + 2 * ((i) >> 4))
+#define CC_STRIP 72                      // padded length of a 64-entry strip
 __device__ void cc_potrf_inv(const CholArgs& a, int k, double* Dm, double* bufs) {
-    const int tid = threadIdx.x, r = tid >> 2, part = tid & 3;
+    const int tid = threadIdx.x, own = tid >> 2, part = tid & 3;
+    const int eown = (own + 32) & 63;                    // E role owner index: the row strip is published by another warp
     const int k0 = k * CC_NB, kb = min(CC_NB, a.n - k0);
-    double V[16];
+    // slot m of a thread is index 16 part + m (row index in the D role, column index in the E role)
+    double Vd[16], Ve[16];
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
-        const int j = part + 4 * m;
-        double v = (r == j) ? 1.0 : 0.0;
-        if (r < kb && j <= r) v = a.A[(size_t)(k0 + r) * a.ld + k0 + j];
-        V[m] = v;
+        const int r = 16 * part + m;
+        double v = (r == own) ? 1.0 : 0.0;
+        if (r < kb && own < kb && r >= own) v = a.A[(size_t)(k0 + r) * a.ld + k0 + own];
+        Vd[m] = v;
+        Ve[m] = (r == eown) ? 1.0 : 0.0;
     }
-    if (part == 0) bufs[r] = V[0];
-    __syncthreads();
+    double2* b2 = reinterpret_cast<double2*>(bufs);      // strips as double2: [buffer][col strip | row strip][36]
+    double* pivs = bufs + 4 * CC_STRIP;                  // 64 pivots, then 64 reciprocal square roots
+    if (own == 0) {
 #pragma unroll
+        for (int m = 0; m < 8; ++m) b2[CC_SP(16 * part) / 2 + m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
+    }
+    if (eown == 0) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) b2[CC_STRIP / 2 + CC_SP(16 * part) / 2 + m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
+    }
+    __syncthreads();
+#pragma unroll 1
     for (int c = 0; c < CC_NB; ++c) {
-        const double* cb = bufs + (c & 1) * 128;
-        const double* rb = cb + 64;
-        double* cn = bufs + ((c + 1) & 1) * 128;
-        double* rn = cn + 64;
-        double piv = cb[c];
+        const double* cb = bufs + (c & 1) * 2 * CC_STRIP;        // pivot column c of D (padded)
+        const double2* cb2 = reinterpret_cast<const double2*>(cb) + CC_SP(16 * part) / 2;
+        const double2* rb2 = reinterpret_cast<const double2*>(cb + CC_STRIP) + CC_SP(16 * part) / 2;
+        double2* cn2 = b2 + ((c + 1) & 1) * CC_STRIP + CC_SP(16 * part) / 2;
+        double2* rn2 = cn2 + CC_STRIP / 2;
+        double piv = cb[CC_SP(c)];
         if (!(piv > 0.0) || !isfinite(piv)) {
             if (tid == 0 && c < kb) atomicCAS(&a.info[0], 0, k0 + c + 1);
             piv = 1.0;
         }
+        if (tid == 0) pivs[c] = piv;
         const double rp = cc_fast_rcp(piv);
-        const double drc = cb[r];
-        if (part == (c & 3)) Dm[r * CC_DP + c] = (r > c) ? drc : (r == c ? piv : 0.0);
-        if (r > c) {
-            const double mm = drc * rp;
+        if (own > c) {
+            // D role: column own > c,  D[r][own] -= D[r][c] D[own][c] / piv  (slots with r < own are don't-care and are
+            // updated too)
+            const double lj = cb[CC_SP(own)] * rp;
 #pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                const int j = part + 4 * m;
-                if (m < (c >> 2)) V[m] = fma(-mm, rb[j], V[m]);
-                else if (m == (c >> 2)) {
-                    if (j < c) V[m] = fma(-mm, rb[j], V[m]);
-                    else if (j == c) V[m] = -mm;
-                    else if (j <= r) V[m] = fma(-mm, cb[j], V[m]);
-                } else if (j <= r) V[m] = fma(-mm, cb[j], V[m]);
+            for (int m = 0; m < 8; ++m) {
+                const double2 x = cb2[m];
+                Vd[2 * m] = fma(-x.x, lj, Vd[2 * m]); Vd[2 * m + 1] = fma(-x.y, lj, Vd[2 * m + 1]);
             }
-        } else if (r == c && part == (c & 3)) V[c >> 2] = 1.0;
-        if (c + 1 < CC_NB) {
-            if (part == ((c + 1) & 3) && r >= c + 1) cn[r] = V[(c + 1) >> 2];
-            if (r == c + 1) {
+            if (own == c + 1) {
 #pragma unroll
-                for (int m = 0; m <= (c >> 2); ++m) {
-                    const int j = part + 4 * m;
-                    if (j <= c) rn[j] = V[m];
-                }
+                for (int m = 0; m < 8; ++m) cn2[m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
+            }
+        }
+        if (eown > c) {
+            // E role: row eown > c,  E[eown][j] -= (D[eown][c] / piv) E[c][j]  (E[c][j] = 0 for j > c)
+            const double le = cb[CC_SP(eown)] * rp;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const double2 y = rb2[m];
+                Ve[2 * m] = fma(-le, y.x, Ve[2 * m]); Ve[2 * m + 1] = fma(-le, y.y, Ve[2 * m + 1]);
+            }
+            if (eown == c + 1) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) rn2[m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
             }
         }
         __syncthreads();
     }
+    // column `own` of D was last touched at step own - 1, so Vd still holds the unscaled pivot column:
     // L = (unscaled columns) diag(piv)^{-1/2},  W = diag(piv)^{-1/2} E
+    if (tid < CC_NB) pivs[64 + tid] = 1.0 / sqrt(pivs[tid]);
+    __syncthreads();
     double* Wk = a.W + (size_t)k * CC_NB * CC_NB;
-    const double sr = 1.0 / sqrt(Dm[r * CC_DP + r]);
+    const double sd = pivs[64 + own], se = pivs[64 + eown];
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
-        const int j = part + 4 * m;
-        Wk[r * CC_NB + j] = (j <= r) ? V[m] * sr : 0.0;
-    }
-    for (int idx = tid; idx < CC_NB * CC_NB; idx += CC_NT) {
-        const int rr = idx >> 6, c = idx & 63;
-        if (rr < kb && c <= rr) {
-            const double sc = sqrt(Dm[c * CC_DP + c]);
-            a.A[(size_t)(k0 + rr) * a.ld + k0 + c] = (rr == c) ? sc : Dm[rr * CC_DP + c] / sc;
-        }
+        const int i = 16 * part + m;
+        Wk[eown * CC_NB + i] = (i <= eown) ? Ve[m] * se : 0.0;
+        if (i < kb && own < kb && i >= own) a.A[(size_t)(k0 + i) * a.ld + k0 + own] = (i == own) ? pivs[own] * sd : Vd[m] * sd;
     }
     __syncthreads();
 }
@@ -195,7 +223,7 @@ __device__ void cc_update_tile(const CholArgs& a, int k0, int kb, int i0, int j0
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(CC_NT, 1) chol_coop_kernel(CholArgs a)
+__global__ void __launch_bounds__(CC_NT, CC_CTAS_PER_SM) chol_coop_kernel(CholArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* As = reinterpret_cast<double*>(smem_raw);
@@ -213,6 +241,7 @@ __global__ void __launch_bounds__(CC_NT, 1) chol_coop_kernel(CholArgs a)
 
     for (int k = 0; k < nblk; ++k) {
         const int k0 = k * CC_NB, kb = min(CC_NB, a.n - k0), r1 = k0 + kb;
+        if (bid == 0) CC_STAMP(8 * k + 0);
         // ---- (a) panel below the diagonal block: L_ik = A_ik W_k^T, 32-row slabs ----
         const int nslab = (a.ntot - r1 + 31) / 32;
         if (bid < nslab) {
@@ -245,18 +274,22 @@ __global__ void __launch_bounds__(CC_NT, 1) chol_coop_kernel(CholArgs a)
                 }
             }
         }
+        if (bid == 0) CC_STAMP(8 * k + 1);
         cc_grid_barrier(a.bar, target, G);
+        if (bid == 0) CC_STAMP(8 * k + 2);
         // ---- (b) trailing update; the owner of tile (0, 0) factors the next diagonal block right away ----
         const int T = (a.ntot - r1 + CC_NB - 1) / CC_NB, TC = (a.n - r1 + CC_NB - 1) / CC_NB;
         if (TC > 0) {
             const int dsg = (k + 1) % G;
             if (bid == dsg) {
                 cc_update_tile(a, k0, kb, r1, r1, As, Bs);
+                CC_STAMP(8 * k + 3);
                 if (G == 1) {
                     for (int I = 1; I < T; ++I)
                         for (int J = 0; J <= min(I, TC - 1); ++J) cc_update_tile(a, k0, kb, r1 + CC_NB * I, r1 + CC_NB * J, As, Bs);
                 }
                 cc_potrf_inv(a, k + 1, As, Bs);
+                CC_STAMP(8 * k + 4);
             } else {
                 // tiles in row-major order of the lower triangle, (0, 0) excluded: q' = I (I + 1) / 2 + J for I < TC,
                 // the extra block row I = TC (right-hand-side row) holds TC tiles
@@ -270,9 +303,11 @@ __global__ void __launch_bounds__(CC_NT, 1) chol_coop_kernel(CholArgs a)
                     const int J = qq - I * (I + 1) / 2;
                     cc_update_tile(a, k0, kb, r1 + CC_NB * I, r1 + CC_NB * J, As, Bs);
                 }
+                if (o == 0) CC_STAMP(8 * k + 5);
             }
         }
         cc_grid_barrier(a.bar, target, G);
+        if (bid == 0) CC_STAMP(8 * k + 6);
     }
 
     // ---- back substitution L^T x = y, y = row n ----

@@ -406,7 +406,7 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         int occ = 0, coop = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_coop_kernel, CC_NT, csm));
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
-        p->chol_coop = (occ >= 1 && coop && !env_int("SFFTB_CHOL_LEGACY", 0)) ? 1 : 0;
+        p->chol_coop = (occ >= 1 && coop && !env_int("SFFTB_CHOL_LEGACY", 0)) ? std::min(occ, std::max(1, env_int("SFFTB_CHOL_CTAS", CC_CTAS_PER_SM))) : 0;
     }
     CK(cudaMalloc(&p->info, sizeof(int) * 4));
     CK(cudaMallocHost(&p->info_h, sizeof(int) * 4));
@@ -772,10 +772,32 @@ static int run_cholesky(sfftb_plan* p) {
         ca.A = p->Aug; ca.ld = p->ld; ca.n = n; ca.ntot = ntot; ca.W = p->cholW; ca.yv = p->cholY; ca.xs = p->cholX;
         ca.bar = p->cholBar; ca.info = p->info; ca.sc = p->sc; ca.idx = p->idxmap; ca.sol = p->sol; ca.NEQ = p->d.NEQ;
         CK(cudaMemsetAsync(p->cholBar, 0, sizeof(unsigned) * 4, p->stream));
+        ca.dbg = nullptr;
+        static unsigned long long* dbgbuf = nullptr;
+        const bool dbg = env_int("SFFTB_CHOL_DBG", 0) != 0;
+        if (dbg) {
+            if (!dbgbuf) CK(cudaMalloc(&dbgbuf, sizeof(unsigned long long) * 2048));
+            CK(cudaMemsetAsync(dbgbuf, 0, sizeof(unsigned long long) * 2048, p->stream));
+            ca.dbg = dbgbuf;
+        }
         void* args[] = {&ca};
-        CK(cudaLaunchCooperativeKernel((void*)chol_coop_kernel, dim3(p->nsm), dim3(CC_NT), args,
+        CK(cudaLaunchCooperativeKernel((void*)chol_coop_kernel, dim3(p->nsm * p->chol_coop), dim3(CC_NT), args,
                                        sizeof(double) * 2 * CC_NB * CC_PITCH, p->stream));
         p->launches++;
+        if (dbg) {
+            std::vector<unsigned long long> hst(2048);
+            CK(cudaStreamSynchronize(p->stream));
+            CK(cudaMemcpy(hst.data(), dbgbuf, sizeof(unsigned long long) * 2048, cudaMemcpyDeviceToHost));
+            const int nblk = (n + CC_NB - 1) / CC_NB;
+            fprintf(stderr, "chol dbg (us): k  trsm  bar1  dsg_tile  dsg_potrf  others_tiles  bar2_end\n");
+            for (int k = 0; k < nblk && k < 32; ++k) {
+                const unsigned long long* t = &hst[8 * k];
+                auto us = [&](int i) { return t[i] ? (double)(t[i] - t[0]) * 1e-3 : -1.0; };
+                const unsigned long long* u = &hst[1024 + 4 * (k + 1)];
+                fprintf(stderr, "  %2d  %6.1f %6.1f %6.1f %6.1f %6.1f %6.1f | potrf(k+1): loaded %6.1f loop_end %6.1f\n", k, us(1), us(2), us(3), us(4), us(5), us(6),
+                        u[0] ? (double)(u[0] - t[0]) * 1e-3 : -1.0, u[1] ? (double)(u[1] - t[0]) * 1e-3 : -1.0);
+            }
+        }
         return 0;
     }
     for (int k0 = 0; k0 < n; k0 += CH_NB) {
