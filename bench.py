@@ -35,6 +35,9 @@ WORKLOADS = {
     'c1_512_w4_dk0_db0_fp64': (512, 512, 4, 0, 0, 'fp64', 1),
     'c4_2048_w8_dk2_db2_fp32': (2048, 2048, 8, 2, 2, 'fp32', 4),
     'dev_1024_w4_dk2_db2_fp32': (1024, 1024, 4, 2, 2, 'fp32', 2),
+    # BASELINE config 4: science tiles against ONE shared template; the template row spectra are computed on rank 0
+    # and broadcast once (NCCL), a step is one tile through sfftb_gss_template
+    'c4_template_2048_w8_dk2_db2_fp32': (2048, 2048, 8, 2, 2, 'fp32', 4),
 }
 DEFAULT_WORKLOAD = 'c2_4096_w8_dk2_db2_fp32'
 HBM_FALLBACK_GBS = 6650.0     # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
@@ -204,11 +207,33 @@ def main():
     plan.set_timing(True)
     L = B.lib()
 
+    shared = args.workload.startswith('c4_template')
+    bcast_ms = None
+    if shared:
+        from sfft_b200.batch import TemplateBatch
+        tb = TemplateBatch(plan, rank, world)
+        torch.cuda.synchronize(dev)
+        t0 = time.time()
+        if rank == 0:
+            tb.set_template(devt['REF'], devt['mREF'])
+        else:
+            tb.set_template()
+        torch.cuda.synchronize(dev)
+        bcast_ms = (time.time() - t0) * 1e3
+
     def step_device():
+        if shared:
+            plan.gss_template_device(devt['SCI'].data_ptr(), devt['mSCI'].data_ptr(), code, sol_d.data_ptr(),
+                                     diff_d.data_ptr(), code)
+            return
         plan.gss_device(devt['REF'].data_ptr(), devt['SCI'].data_ptr(), devt['mREF'].data_ptr(), devt['mSCI'].data_ptr(),
                         code, sol_d.data_ptr(), diff_d.data_ptr(), code)
 
     def step_host():
+        if shared:
+            B.check(L.sfftb_gss_template(plan._h, host['SCI'].data_ptr(), host['mSCI'].data_ptr(), B.MEM_HOST, code,
+                                         sol_h.ctypes.data, B.MEM_HOST, diff_h.data_ptr(), B.MEM_HOST, code))
+            return
         B.check(L.sfftb_gss(plan._h, host['REF'].data_ptr(), host['SCI'].data_ptr(), host['mREF'].data_ptr(),
                             host['mSCI'].data_ptr(), B.MEM_HOST, code, sol_h.ctypes.data, B.MEM_HOST,
                             diff_h.data_ptr(), B.MEM_HOST, code))
@@ -284,13 +309,15 @@ def main():
                        'storage': storage, 'arithmetic': 'fp64', 'pairs_per_step_per_gpu': 1,
                        'l2_policy': 'working set per step (inputs 4x%.0f MB + spectra %.0f MB) exceeds the 126 MB L2' % (
                            N0 * N1 * esz / 1e6, (DK + 2) * NH * N0 * csz / 1e6),
-                       'fold': plan.dims['fold'], 'sub_len': plan.dims['sub_len']},
+                       'fold': plan.dims['fold'], 'sub_len': plan.dims['sub_len'],
+                       'shared_template': shared, 'template_prepare_broadcast_ms': bcast_ms},
             'stage_ms': stage,
             'assembly_solve_ms': stage.get('fit_cols', 0) + stage.get('fit_reduce_fill', 0) + stage.get('fit_solve', 0),
             'solver': plan.last_solver,
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'Mpix/s', 'ms_per_step': ms_e2e, 'steps': KE,
-                    'h2d_bytes_per_step': 4 * N0 * N1 * esz, 'd2h_bytes_per_step': N0 * N1 * esz + plan.NEQ * 8},
+                    'h2d_bytes_per_step': (2 if shared else 4) * N0 * N1 * esz,
+                    'd2h_bytes_per_step': N0 * N1 * esz + plan.NEQ * 8},
             'gpu_launches': launches,
             'roofline': {'bound': 'hbm', 'kernel': 'fit_col_kernel', 'achieved': achieved, 'peak': peak,
                          'peak_source': which, 'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None,

@@ -98,6 +98,22 @@ int  sfftb_gss(sfftb_plan* plan, const void* PixA_I, const void* PixA_J, const v
                int img_memkind, int img_dtype, double* solution, int sol_memkind,
                void* diff, int diff_memkind, int diff_dtype);
 
+/* Shared-template batch path (BASELINE config 4).  The reference re-transforms the template for every
+ * pair (ESS is called per pair, sfft/MultiEasySparsePacket.py:568-649); here the row spectra of the convolved image
+ * (I = template when ForceConv='REF', sfft/CustomizedPacket.py:148-162) are computed once:
+ *   sfftb_template_prepare : row spectra of (PixA_I, PixA_mI) into the plan's template state;
+ *   sfftb_template_state   : device pointer + size of that state (allocated on first use) -- the buffer a caller
+ *                            broadcasts to the other GPUs with ONE ncclBroadcast / torch.distributed.broadcast;
+ *   sfftb_template_mark_ready : on a receiving rank, after the broadcast landed in the state buffer;
+ *   sfftb_gss_template     : GSS for one science image (PixA_J, PixA_mJ) against the cached template.  LHMAT = D^T D / N
+ *                            involves the masked template only, so its Cholesky factor is kept from the first tile
+ *                            and later tiles assemble the right-hand side and run the two substitutions. */
+int  sfftb_template_prepare(sfftb_plan* plan, const void* PixA_I, const void* PixA_mI, int img_memkind, int img_dtype);
+int  sfftb_template_state(sfftb_plan* plan, void** device_ptr, size_t* bytes);
+int  sfftb_template_mark_ready(sfftb_plan* plan);
+int  sfftb_gss_template(sfftb_plan* plan, const void* PixA_J, const void* PixA_mJ, int img_memkind, int img_dtype,
+                        double* solution, int sol_memkind, void* diff, int diff_memkind, int diff_dtype);
+
 /* Parity hook: the full (NEQ x NEQ) LHMAT and (NEQ) RHb of the last fit, before stripe removal,
  * in the reference's layout (what FillLS_* produce, SFFTSubtract.py:244-380).  Host pointers. */
 int  sfftb_export_normal_eq(sfftb_plan* plan, double* LHMAT, double* RHb);
@@ -108,7 +124,8 @@ int  sfftb_export_normal_eq(sfftb_plan* plan, double* LHMAT, double* RHb);
 int  sfftb_plan_set_timing(sfftb_plan* plan, int enable);
 int  sfftb_timings(sfftb_plan* plan, float* ms, int n);
 
-/* Which factorisation the last fit used: 1 = Cholesky, 2 = pivoted LU fallback. */
+/* Which factorisation the last fit used: 1 = Cholesky, 2 = pivoted LU fallback, 3 = substitutions with the cached
+ * Cholesky factor (template path: LHMAT depends on the masked template only, so tiles after the first reuse it). */
 int  sfftb_last_solver(const sfftb_plan* plan);
 
 /* Number of kernel launches issued by this plan since creation (bench.py's gpu_launches). */

@@ -5,6 +5,7 @@
 #include "../../sfft_b200/csrc/kernels_chol.cuh"
 __device__ void pv0(const CholArgs& a, int k, double* Dm, double* bufs) {
     const int tid = threadIdx.x, own = tid >> 2, part = tid & 3;
+    const int eown = (own + 32) & 63;                    // E role owner index: the row strip is published by another warp
     const int k0 = k * CC_NB, kb = min(CC_NB, a.n - k0);
     // slot m of a thread is index 16 part + m (row index in the D role, column index in the E role)
     double Vd[16], Ve[16];
@@ -14,15 +15,17 @@ __device__ void pv0(const CholArgs& a, int k, double* Dm, double* bufs) {
         double v = (r == own) ? 1.0 : 0.0;
         if (r < kb && own < kb && r >= own) v = a.A[(size_t)(k0 + r) * a.ld + k0 + own];
         Vd[m] = v;
-        Ve[m] = (r == own) ? 1.0 : 0.0;
+        Ve[m] = (r == eown) ? 1.0 : 0.0;
     }
     double2* b2 = reinterpret_cast<double2*>(bufs);      // strips as double2: [buffer][col strip | row strip][36]
+    double* pivs = bufs + 4 * CC_STRIP;                  // 64 pivots, then 64 reciprocal square roots
     if (own == 0) {
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            b2[CC_SP(16 * part) / 2 + m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
-            b2[CC_STRIP / 2 + CC_SP(16 * part) / 2 + m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
-        }
+        for (int m = 0; m < 8; ++m) b2[CC_SP(16 * part) / 2 + m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
+    }
+    if (eown == 0) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) b2[CC_STRIP / 2 + CC_SP(16 * part) / 2 + m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
     }
     __syncthreads();
 #pragma unroll 1
@@ -37,45 +40,48 @@ __device__ void pv0(const CholArgs& a, int k, double* Dm, double* bufs) {
             if (tid == 0 && c < kb) atomicCAS(&a.info[0], 0, k0 + c + 1);
             piv = 1.0;
         }
+        if (tid == 0) pivs[c] = piv;
         const double rp = cc_fast_rcp(piv);
-        if (own == c) {                                   // keep the unscaled pivot column for the write-out
-#pragma unroll
-            for (int m = 0; m < 16; ++m) Dm[(16 * part + m) * CC_DP + c] = (16 * part + m == c) ? piv : Vd[m];
-        }
         if (own > c) {
             // D role: column own > c,  D[r][own] -= D[r][c] D[own][c] / piv  (slots with r < own are don't-care and are
-            // updated too).  E role: row own > c,  E[own][j] -= (D[own][c] / piv) E[c][j]  (E[c][j] = 0 for j > c).
+            // updated too)
             const double lj = cb[CC_SP(own)] * rp;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                const double2 x = cb2[m], y = rb2[m];
+                const double2 x = cb2[m];
                 Vd[2 * m] = fma(-x.x, lj, Vd[2 * m]); Vd[2 * m + 1] = fma(-x.y, lj, Vd[2 * m + 1]);
-                Ve[2 * m] = fma(-lj, y.x, Ve[2 * m]); Ve[2 * m + 1] = fma(-lj, y.y, Ve[2 * m + 1]);
+            }
+            if (own == c + 1) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) cn2[m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
             }
         }
-        if (own == c + 1) {
+        if (eown > c) {
+            // E role: row eown > c,  E[eown][j] -= (D[eown][c] / piv) E[c][j]  (E[c][j] = 0 for j > c)
+            const double le = cb[CC_SP(eown)] * rp;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                cn2[m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
-                rn2[m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
+                const double2 y = rb2[m];
+                Ve[2 * m] = fma(-le, y.x, Ve[2 * m]); Ve[2 * m + 1] = fma(-le, y.y, Ve[2 * m + 1]);
+            }
+            if (eown == c + 1) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) rn2[m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
             }
         }
         __syncthreads();
     }
+    // column `own` of D was last touched at step own - 1, so Vd still holds the unscaled pivot column:
     // L = (unscaled columns) diag(piv)^{-1/2},  W = diag(piv)^{-1/2} E
+    if (tid < CC_NB) pivs[64 + tid] = 1.0 / sqrt(pivs[tid]);
+    __syncthreads();
     double* Wk = a.W + (size_t)k * CC_NB * CC_NB;
-    const double sr = 1.0 / sqrt(Dm[own * CC_DP + own]);
+    const double sd = pivs[64 + own], se = pivs[64 + eown];
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
-        const int j = 16 * part + m;
-        Wk[own * CC_NB + j] = (j <= own) ? Ve[m] * sr : 0.0;
-    }
-    for (int idx = tid; idx < CC_NB * CC_NB; idx += CC_NT) {
-        const int rr = idx >> 6, c = idx & 63;
-        if (rr < kb && c <= rr) {
-            const double sc = sqrt(Dm[c * CC_DP + c]);
-            a.A[(size_t)(k0 + rr) * a.ld + k0 + c] = (rr == c) ? sc : Dm[rr * CC_DP + c] / sc;
-        }
+        const int i = 16 * part + m;
+        Wk[eown * CC_NB + i] = (i <= eown) ? Ve[m] * se : 0.0;
+        if (i < kb && own < kb && i >= own) a.A[(size_t)(k0 + i) * a.ld + k0 + own] = (i == own) ? pivs[own] * sd : Vd[m] * sd;
     }
     __syncthreads();
 }
@@ -83,6 +89,7 @@ __device__ void pv0(const CholArgs& a, int k, double* Dm, double* bufs) {
 
 __device__ void pv1(const CholArgs& a, int k, double* Dm, double* bufs) {
     const int tid = threadIdx.x, own = tid >> 2, part = tid & 3;
+    const int eown = (own + 32) & 63;                    // E role owner index: the row strip is published by another warp
     const int k0 = k * CC_NB, kb = min(CC_NB, a.n - k0);
     // slot m of a thread is index 16 part + m (row index in the D role, column index in the E role)
     double Vd[16], Ve[16];
@@ -92,15 +99,17 @@ __device__ void pv1(const CholArgs& a, int k, double* Dm, double* bufs) {
         double v = (r == own) ? 1.0 : 0.0;
         if (r < kb && own < kb && r >= own) v = a.A[(size_t)(k0 + r) * a.ld + k0 + own];
         Vd[m] = v;
-        Ve[m] = (r == own) ? 1.0 : 0.0;
+        Ve[m] = (r == eown) ? 1.0 : 0.0;
     }
     double2* b2 = reinterpret_cast<double2*>(bufs);      // strips as double2: [buffer][col strip | row strip][36]
+    double* pivs = bufs + 4 * CC_STRIP;                  // 64 pivots, then 64 reciprocal square roots
     if (own == 0) {
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            b2[CC_SP(16 * part) / 2 + m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
-            b2[CC_STRIP / 2 + CC_SP(16 * part) / 2 + m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
-        }
+        for (int m = 0; m < 8; ++m) b2[CC_SP(16 * part) / 2 + m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
+    }
+    if (eown == 0) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) b2[CC_STRIP / 2 + CC_SP(16 * part) / 2 + m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
     }
     __syncthreads();
 #pragma unroll 1
@@ -115,45 +124,48 @@ __device__ void pv1(const CholArgs& a, int k, double* Dm, double* bufs) {
             if (tid == 0 && c < kb) atomicCAS(&a.info[0], 0, k0 + c + 1);
             piv = 1.0;
         }
+        if (tid == 0) pivs[c] = piv;
         const double rp = cc_fast_rcp(piv);
-        if (own == c) {                                   // keep the unscaled pivot column for the write-out
-#pragma unroll
-            for (int m = 0; m < 16; ++m) Dm[(16 * part + m) * CC_DP + c] = (16 * part + m == c) ? piv : Vd[m];
-        }
         if (own > c) {
             // D role: column own > c,  D[r][own] -= D[r][c] D[own][c] / piv  (slots with r < own are don't-care and are
-            // updated too).  E role: row own > c,  E[own][j] -= (D[own][c] / piv) E[c][j]  (E[c][j] = 0 for j > c).
+            // updated too)
             const double lj = cb[CC_SP(own)] * rp;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                const double2 x = cb2[m], y = rb2[m];
+                const double2 x = cb2[m];
                 Vd[2 * m] = fma(-x.x, lj, Vd[2 * m]); Vd[2 * m + 1] = fma(-x.y, lj, Vd[2 * m + 1]);
-                Ve[2 * m] = fma(-lj, y.x, Ve[2 * m]); Ve[2 * m + 1] = fma(-lj, y.y, Ve[2 * m + 1]);
+            }
+            if (own == c + 1) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) cn2[m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
             }
         }
-        if (own == c + 1) {
+        if (eown > c) {
+            // E role: row eown > c,  E[eown][j] -= (D[eown][c] / piv) E[c][j]  (E[c][j] = 0 for j > c)
+            const double le = cb[CC_SP(eown)] * rp;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                cn2[m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
-                rn2[m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
+                const double2 y = rb2[m];
+                Ve[2 * m] = fma(-le, y.x, Ve[2 * m]); Ve[2 * m + 1] = fma(-le, y.y, Ve[2 * m + 1]);
+            }
+            if (eown == c + 1) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) rn2[m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
             }
         }
         __syncwarp();
     }
+    // column `own` of D was last touched at step own - 1, so Vd still holds the unscaled pivot column:
     // L = (unscaled columns) diag(piv)^{-1/2},  W = diag(piv)^{-1/2} E
+    if (tid < CC_NB) pivs[64 + tid] = 1.0 / sqrt(pivs[tid]);
+    __syncthreads();
     double* Wk = a.W + (size_t)k * CC_NB * CC_NB;
-    const double sr = 1.0 / sqrt(Dm[own * CC_DP + own]);
+    const double sd = pivs[64 + own], se = pivs[64 + eown];
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
-        const int j = 16 * part + m;
-        Wk[own * CC_NB + j] = (j <= own) ? Ve[m] * sr : 0.0;
-    }
-    for (int idx = tid; idx < CC_NB * CC_NB; idx += CC_NT) {
-        const int rr = idx >> 6, c = idx & 63;
-        if (rr < kb && c <= rr) {
-            const double sc = sqrt(Dm[c * CC_DP + c]);
-            a.A[(size_t)(k0 + rr) * a.ld + k0 + c] = (rr == c) ? sc : Dm[rr * CC_DP + c] / sc;
-        }
+        const int i = 16 * part + m;
+        Wk[eown * CC_NB + i] = (i <= eown) ? Ve[m] * se : 0.0;
+        if (i < kb && own < kb && i >= own) a.A[(size_t)(k0 + i) * a.ld + k0 + own] = (i == own) ? pivs[own] * sd : Vd[m] * sd;
     }
     __syncthreads();
 }
@@ -161,6 +173,7 @@ __device__ void pv1(const CholArgs& a, int k, double* Dm, double* bufs) {
 
 __device__ void pv2(const CholArgs& a, int k, double* Dm, double* bufs) {
     const int tid = threadIdx.x, own = tid >> 2, part = tid & 3;
+    const int eown = (own + 32) & 63;                    // E role owner index: the row strip is published by another warp
     const int k0 = k * CC_NB, kb = min(CC_NB, a.n - k0);
     // slot m of a thread is index 16 part + m (row index in the D role, column index in the E role)
     double Vd[16], Ve[16];
@@ -170,15 +183,17 @@ __device__ void pv2(const CholArgs& a, int k, double* Dm, double* bufs) {
         double v = (r == own) ? 1.0 : 0.0;
         if (r < kb && own < kb && r >= own) v = a.A[(size_t)(k0 + r) * a.ld + k0 + own];
         Vd[m] = v;
-        Ve[m] = (r == own) ? 1.0 : 0.0;
+        Ve[m] = (r == eown) ? 1.0 : 0.0;
     }
     double2* b2 = reinterpret_cast<double2*>(bufs);      // strips as double2: [buffer][col strip | row strip][36]
+    double* pivs = bufs + 4 * CC_STRIP;                  // 64 pivots, then 64 reciprocal square roots
     if (own == 0) {
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            b2[CC_SP(16 * part) / 2 + m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
-            b2[CC_STRIP / 2 + CC_SP(16 * part) / 2 + m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
-        }
+        for (int m = 0; m < 8; ++m) b2[CC_SP(16 * part) / 2 + m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
+    }
+    if (eown == 0) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) b2[CC_STRIP / 2 + CC_SP(16 * part) / 2 + m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
     }
     __syncthreads();
 #pragma unroll 1
@@ -193,45 +208,48 @@ __device__ void pv2(const CholArgs& a, int k, double* Dm, double* bufs) {
             if (tid == 0 && c < kb) atomicCAS(&a.info[0], 0, k0 + c + 1);
             piv = 1.0;
         }
+        if (tid == 0) pivs[c] = piv;
         const double rp = piv * 1e-3;
-        if (own == c) {                                   // keep the unscaled pivot column for the write-out
-#pragma unroll
-            for (int m = 0; m < 16; ++m) Dm[(16 * part + m) * CC_DP + c] = (16 * part + m == c) ? piv : Vd[m];
-        }
         if (own > c) {
             // D role: column own > c,  D[r][own] -= D[r][c] D[own][c] / piv  (slots with r < own are don't-care and are
-            // updated too).  E role: row own > c,  E[own][j] -= (D[own][c] / piv) E[c][j]  (E[c][j] = 0 for j > c).
+            // updated too)
             const double lj = cb[CC_SP(own)] * rp;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                const double2 x = cb2[m], y = rb2[m];
+                const double2 x = cb2[m];
                 Vd[2 * m] = fma(-x.x, lj, Vd[2 * m]); Vd[2 * m + 1] = fma(-x.y, lj, Vd[2 * m + 1]);
-                Ve[2 * m] = fma(-lj, y.x, Ve[2 * m]); Ve[2 * m + 1] = fma(-lj, y.y, Ve[2 * m + 1]);
+            }
+            if (own == c + 1) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) cn2[m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
             }
         }
-        if (own == c + 1) {
+        if (eown > c) {
+            // E role: row eown > c,  E[eown][j] -= (D[eown][c] / piv) E[c][j]  (E[c][j] = 0 for j > c)
+            const double le = cb[CC_SP(eown)] * rp;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                cn2[m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
-                rn2[m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
+                const double2 y = rb2[m];
+                Ve[2 * m] = fma(-le, y.x, Ve[2 * m]); Ve[2 * m + 1] = fma(-le, y.y, Ve[2 * m + 1]);
+            }
+            if (eown == c + 1) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) rn2[m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
             }
         }
         __syncthreads();
     }
+    // column `own` of D was last touched at step own - 1, so Vd still holds the unscaled pivot column:
     // L = (unscaled columns) diag(piv)^{-1/2},  W = diag(piv)^{-1/2} E
+    if (tid < CC_NB) pivs[64 + tid] = 1.0 / sqrt(pivs[tid]);
+    __syncthreads();
     double* Wk = a.W + (size_t)k * CC_NB * CC_NB;
-    const double sr = 1.0 / sqrt(Dm[own * CC_DP + own]);
+    const double sd = pivs[64 + own], se = pivs[64 + eown];
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
-        const int j = 16 * part + m;
-        Wk[own * CC_NB + j] = (j <= own) ? Ve[m] * sr : 0.0;
-    }
-    for (int idx = tid; idx < CC_NB * CC_NB; idx += CC_NT) {
-        const int rr = idx >> 6, c = idx & 63;
-        if (rr < kb && c <= rr) {
-            const double sc = sqrt(Dm[c * CC_DP + c]);
-            a.A[(size_t)(k0 + rr) * a.ld + k0 + c] = (rr == c) ? sc : Dm[rr * CC_DP + c] / sc;
-        }
+        const int i = 16 * part + m;
+        Wk[eown * CC_NB + i] = (i <= eown) ? Ve[m] * se : 0.0;
+        if (i < kb && own < kb && i >= own) a.A[(size_t)(k0 + i) * a.ld + k0 + own] = (i == own) ? pivs[own] * sd : Vd[m] * sd;
     }
     __syncthreads();
 }
@@ -239,6 +257,7 @@ __device__ void pv2(const CholArgs& a, int k, double* Dm, double* bufs) {
 
 __device__ void pv3(const CholArgs& a, int k, double* Dm, double* bufs) {
     const int tid = threadIdx.x, own = tid >> 2, part = tid & 3;
+    const int eown = (own + 32) & 63;                    // E role owner index: the row strip is published by another warp
     const int k0 = k * CC_NB, kb = min(CC_NB, a.n - k0);
     // slot m of a thread is index 16 part + m (row index in the D role, column index in the E role)
     double Vd[16], Ve[16];
@@ -248,15 +267,17 @@ __device__ void pv3(const CholArgs& a, int k, double* Dm, double* bufs) {
         double v = (r == own) ? 1.0 : 0.0;
         if (r < kb && own < kb && r >= own) v = a.A[(size_t)(k0 + r) * a.ld + k0 + own];
         Vd[m] = v;
-        Ve[m] = (r == own) ? 1.0 : 0.0;
+        Ve[m] = (r == eown) ? 1.0 : 0.0;
     }
     double2* b2 = reinterpret_cast<double2*>(bufs);      // strips as double2: [buffer][col strip | row strip][36]
+    double* pivs = bufs + 4 * CC_STRIP;                  // 64 pivots, then 64 reciprocal square roots
     if (own == 0) {
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            b2[CC_SP(16 * part) / 2 + m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
-            b2[CC_STRIP / 2 + CC_SP(16 * part) / 2 + m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
-        }
+        for (int m = 0; m < 8; ++m) b2[CC_SP(16 * part) / 2 + m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
+    }
+    if (eown == 0) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) b2[CC_STRIP / 2 + CC_SP(16 * part) / 2 + m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
     }
     __syncthreads();
 #pragma unroll 1
@@ -271,45 +292,48 @@ __device__ void pv3(const CholArgs& a, int k, double* Dm, double* bufs) {
             if (tid == 0 && c < kb) atomicCAS(&a.info[0], 0, k0 + c + 1);
             piv = 1.0;
         }
+        if (tid == 0) pivs[c] = piv;
         const double rp = cc_fast_rcp(piv);
-        if (own == c) {                                   // keep the unscaled pivot column for the write-out
-#pragma unroll
-            for (int m = 0; m < 16; ++m) Dm[(16 * part + m) * CC_DP + c] = (16 * part + m == c) ? piv : Vd[m];
-        }
         if (own > c) {
             // D role: column own > c,  D[r][own] -= D[r][c] D[own][c] / piv  (slots with r < own are don't-care and are
-            // updated too).  E role: row own > c,  E[own][j] -= (D[own][c] / piv) E[c][j]  (E[c][j] = 0 for j > c).
+            // updated too)
             const double lj = cb[CC_SP(own)] * rp;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                const double2 x = cb2[m], y = rb2[m];
+                const double2 x = cb2[m];
                 Vd[2 * m] = fma(-x.x, lj, Vd[2 * m]); Vd[2 * m + 1] = fma(-x.y, lj, Vd[2 * m + 1]);
-                Ve[2 * m] = fma(-lj, y.x, Ve[2 * m]); Ve[2 * m + 1] = fma(-lj, y.y, Ve[2 * m + 1]);
+            }
+            if (own == c + 1 && part == 7) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) cn2[m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
             }
         }
-        if (own == c + 1 && part == 7) {
+        if (eown > c) {
+            // E role: row eown > c,  E[eown][j] -= (D[eown][c] / piv) E[c][j]  (E[c][j] = 0 for j > c)
+            const double le = cb[CC_SP(eown)] * rp;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                cn2[m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
-                rn2[m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
+                const double2 y = rb2[m];
+                Ve[2 * m] = fma(-le, y.x, Ve[2 * m]); Ve[2 * m + 1] = fma(-le, y.y, Ve[2 * m + 1]);
+            }
+            if (eown == c + 1 && part == 7) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) rn2[m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
             }
         }
         __syncthreads();
     }
+    // column `own` of D was last touched at step own - 1, so Vd still holds the unscaled pivot column:
     // L = (unscaled columns) diag(piv)^{-1/2},  W = diag(piv)^{-1/2} E
+    if (tid < CC_NB) pivs[64 + tid] = 1.0 / sqrt(pivs[tid]);
+    __syncthreads();
     double* Wk = a.W + (size_t)k * CC_NB * CC_NB;
-    const double sr = 1.0 / sqrt(Dm[own * CC_DP + own]);
+    const double sd = pivs[64 + own], se = pivs[64 + eown];
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
-        const int j = 16 * part + m;
-        Wk[own * CC_NB + j] = (j <= own) ? Ve[m] * sr : 0.0;
-    }
-    for (int idx = tid; idx < CC_NB * CC_NB; idx += CC_NT) {
-        const int rr = idx >> 6, c = idx & 63;
-        if (rr < kb && c <= rr) {
-            const double sc = sqrt(Dm[c * CC_DP + c]);
-            a.A[(size_t)(k0 + rr) * a.ld + k0 + c] = (rr == c) ? sc : Dm[rr * CC_DP + c] / sc;
-        }
+        const int i = 16 * part + m;
+        Wk[eown * CC_NB + i] = (i <= eown) ? Ve[m] * se : 0.0;
+        if (i < kb && own < kb && i >= own) a.A[(size_t)(k0 + i) * a.ld + k0 + own] = (i == own) ? pivs[own] * sd : Vd[m] * sd;
     }
     __syncthreads();
 }
@@ -317,6 +341,7 @@ __device__ void pv3(const CholArgs& a, int k, double* Dm, double* bufs) {
 
 __device__ void pv4(const CholArgs& a, int k, double* Dm, double* bufs) {
     const int tid = threadIdx.x, own = tid >> 2, part = tid & 3;
+    const int eown = (own + 32) & 63;                    // E role owner index: the row strip is published by another warp
     const int k0 = k * CC_NB, kb = min(CC_NB, a.n - k0);
     // slot m of a thread is index 16 part + m (row index in the D role, column index in the E role)
     double Vd[16], Ve[16];
@@ -326,15 +351,17 @@ __device__ void pv4(const CholArgs& a, int k, double* Dm, double* bufs) {
         double v = (r == own) ? 1.0 : 0.0;
         if (r < kb && own < kb && r >= own) v = a.A[(size_t)(k0 + r) * a.ld + k0 + own];
         Vd[m] = v;
-        Ve[m] = (r == own) ? 1.0 : 0.0;
+        Ve[m] = (r == eown) ? 1.0 : 0.0;
     }
     double2* b2 = reinterpret_cast<double2*>(bufs);      // strips as double2: [buffer][col strip | row strip][36]
+    double* pivs = bufs + 4 * CC_STRIP;                  // 64 pivots, then 64 reciprocal square roots
     if (own == 0) {
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            b2[CC_SP(16 * part) / 2 + m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
-            b2[CC_STRIP / 2 + CC_SP(16 * part) / 2 + m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
-        }
+        for (int m = 0; m < 8; ++m) b2[CC_SP(16 * part) / 2 + m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
+    }
+    if (eown == 0) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) b2[CC_STRIP / 2 + CC_SP(16 * part) / 2 + m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
     }
     __syncthreads();
 #pragma unroll 1
@@ -349,45 +376,48 @@ __device__ void pv4(const CholArgs& a, int k, double* Dm, double* bufs) {
             if (tid == 0 && c < kb) atomicCAS(&a.info[0], 0, k0 + c + 1);
             piv = 1.0;
         }
+        if (tid == 0) pivs[c] = piv;
         const double rp = cc_fast_rcp(piv);
-        if (own == c && part == 7) {                                   // keep the unscaled pivot column for the write-out
-#pragma unroll
-            for (int m = 0; m < 16; ++m) Dm[(16 * part + m) * CC_DP + c] = (16 * part + m == c) ? piv : Vd[m];
-        }
-        if (own > c) {
+        if (own > c && part == 7) {
             // D role: column own > c,  D[r][own] -= D[r][c] D[own][c] / piv  (slots with r < own are don't-care and are
-            // updated too).  E role: row own > c,  E[own][j] -= (D[own][c] / piv) E[c][j]  (E[c][j] = 0 for j > c).
+            // updated too)
             const double lj = cb[CC_SP(own)] * rp;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                const double2 x = cb2[m], y = rb2[m];
+                const double2 x = cb2[m];
                 Vd[2 * m] = fma(-x.x, lj, Vd[2 * m]); Vd[2 * m + 1] = fma(-x.y, lj, Vd[2 * m + 1]);
-                Ve[2 * m] = fma(-lj, y.x, Ve[2 * m]); Ve[2 * m + 1] = fma(-lj, y.y, Ve[2 * m + 1]);
+            }
+            if (own == c + 1) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) cn2[m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
             }
         }
-        if (own == c + 1) {
+        if (eown > c) {
+            // E role: row eown > c,  E[eown][j] -= (D[eown][c] / piv) E[c][j]  (E[c][j] = 0 for j > c)
+            const double le = cb[CC_SP(eown)] * rp;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                cn2[m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
-                rn2[m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
+                const double2 y = rb2[m];
+                Ve[2 * m] = fma(-le, y.x, Ve[2 * m]); Ve[2 * m + 1] = fma(-le, y.y, Ve[2 * m + 1]);
+            }
+            if (eown == c + 1) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) rn2[m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
             }
         }
         __syncthreads();
     }
+    // column `own` of D was last touched at step own - 1, so Vd still holds the unscaled pivot column:
     // L = (unscaled columns) diag(piv)^{-1/2},  W = diag(piv)^{-1/2} E
+    if (tid < CC_NB) pivs[64 + tid] = 1.0 / sqrt(pivs[tid]);
+    __syncthreads();
     double* Wk = a.W + (size_t)k * CC_NB * CC_NB;
-    const double sr = 1.0 / sqrt(Dm[own * CC_DP + own]);
+    const double sd = pivs[64 + own], se = pivs[64 + eown];
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
-        const int j = 16 * part + m;
-        Wk[own * CC_NB + j] = (j <= own) ? Ve[m] * sr : 0.0;
-    }
-    for (int idx = tid; idx < CC_NB * CC_NB; idx += CC_NT) {
-        const int rr = idx >> 6, c = idx & 63;
-        if (rr < kb && c <= rr) {
-            const double sc = sqrt(Dm[c * CC_DP + c]);
-            a.A[(size_t)(k0 + rr) * a.ld + k0 + c] = (rr == c) ? sc : Dm[rr * CC_DP + c] / sc;
-        }
+        const int i = 16 * part + m;
+        Wk[eown * CC_NB + i] = (i <= eown) ? Ve[m] * se : 0.0;
+        if (i < kb && own < kb && i >= own) a.A[(size_t)(k0 + i) * a.ld + k0 + own] = (i == own) ? pivs[own] * sd : Vd[m] * sd;
     }
     __syncthreads();
 }
@@ -395,6 +425,7 @@ __device__ void pv4(const CholArgs& a, int k, double* Dm, double* bufs) {
 
 __device__ void pv5(const CholArgs& a, int k, double* Dm, double* bufs) {
     const int tid = threadIdx.x, own = tid >> 2, part = tid & 3;
+    const int eown = (own + 32) & 63;                    // E role owner index: the row strip is published by another warp
     const int k0 = k * CC_NB, kb = min(CC_NB, a.n - k0);
     // slot m of a thread is index 16 part + m (row index in the D role, column index in the E role)
     double Vd[16], Ve[16];
@@ -404,90 +435,17 @@ __device__ void pv5(const CholArgs& a, int k, double* Dm, double* bufs) {
         double v = (r == own) ? 1.0 : 0.0;
         if (r < kb && own < kb && r >= own) v = a.A[(size_t)(k0 + r) * a.ld + k0 + own];
         Vd[m] = v;
-        Ve[m] = (r == own) ? 1.0 : 0.0;
+        Ve[m] = (r == eown) ? 1.0 : 0.0;
     }
     double2* b2 = reinterpret_cast<double2*>(bufs);      // strips as double2: [buffer][col strip | row strip][36]
+    double* pivs = bufs + 4 * CC_STRIP;                  // 64 pivots, then 64 reciprocal square roots
     if (own == 0) {
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            b2[CC_SP(16 * part) / 2 + m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
-            b2[CC_STRIP / 2 + CC_SP(16 * part) / 2 + m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
-        }
+        for (int m = 0; m < 8; ++m) b2[CC_SP(16 * part) / 2 + m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
     }
-    __syncthreads();
-#pragma unroll 1
-    for (int c = 0; c < CC_NB; ++c) {
-        const double* cb = bufs + (c & 1) * 2 * CC_STRIP;        // pivot column c of D (padded)
-        const double2* cb2 = reinterpret_cast<const double2*>(cb) + CC_SP(16 * part) / 2;
-        const double2* rb2 = reinterpret_cast<const double2*>(cb + CC_STRIP) + CC_SP(16 * part) / 2;
-        double2* cn2 = b2 + ((c + 1) & 1) * CC_STRIP + CC_SP(16 * part) / 2;
-        double2* rn2 = cn2 + CC_STRIP / 2;
-        double piv = cb[CC_SP(c)];
-
-        const double rp = cc_fast_rcp(piv);
-        if (own == c) {                                   // keep the unscaled pivot column for the write-out
+    if (eown == 0) {
 #pragma unroll
-            for (int m = 0; m < 16; ++m) Dm[(16 * part + m) * CC_DP + c] = (16 * part + m == c) ? piv : Vd[m];
-        }
-        if (own > c) {
-            // D role: column own > c,  D[r][own] -= D[r][c] D[own][c] / piv  (slots with r < own are don't-care and are
-            // updated too).  E role: row own > c,  E[own][j] -= (D[own][c] / piv) E[c][j]  (E[c][j] = 0 for j > c).
-            const double lj = cb[CC_SP(own)] * rp;
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const double2 x = cb2[m], y = rb2[m];
-                Vd[2 * m] = fma(-x.x, lj, Vd[2 * m]); Vd[2 * m + 1] = fma(-x.y, lj, Vd[2 * m + 1]);
-                Ve[2 * m] = fma(-lj, y.x, Ve[2 * m]); Ve[2 * m + 1] = fma(-lj, y.y, Ve[2 * m + 1]);
-            }
-        }
-        if (own == c + 1) {
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                cn2[m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
-                rn2[m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
-            }
-        }
-        __syncthreads();
-    }
-    // L = (unscaled columns) diag(piv)^{-1/2},  W = diag(piv)^{-1/2} E
-    double* Wk = a.W + (size_t)k * CC_NB * CC_NB;
-    const double sr = 1.0 / sqrt(Dm[own * CC_DP + own]);
-#pragma unroll
-    for (int m = 0; m < 16; ++m) {
-        const int j = 16 * part + m;
-        Wk[own * CC_NB + j] = (j <= own) ? Ve[m] * sr : 0.0;
-    }
-    for (int idx = tid; idx < CC_NB * CC_NB; idx += CC_NT) {
-        const int rr = idx >> 6, c = idx & 63;
-        if (rr < kb && c <= rr) {
-            const double sc = sqrt(Dm[c * CC_DP + c]);
-            a.A[(size_t)(k0 + rr) * a.ld + k0 + c] = (rr == c) ? sc : Dm[rr * CC_DP + c] / sc;
-        }
-    }
-    __syncthreads();
-}
-
-
-__device__ void pv6(const CholArgs& a, int k, double* Dm, double* bufs) {
-    const int tid = threadIdx.x, own = tid >> 2, part = tid & 3;
-    const int k0 = k * CC_NB, kb = min(CC_NB, a.n - k0);
-    // slot m of a thread is index 16 part + m (row index in the D role, column index in the E role)
-    double Vd[16], Ve[16];
-#pragma unroll
-    for (int m = 0; m < 16; ++m) {
-        const int r = 16 * part + m;
-        double v = (r == own) ? 1.0 : 0.0;
-        if (r < kb && own < kb && r >= own) v = a.A[(size_t)(k0 + r) * a.ld + k0 + own];
-        Vd[m] = v;
-        Ve[m] = (r == own) ? 1.0 : 0.0;
-    }
-    double2* b2 = reinterpret_cast<double2*>(bufs);      // strips as double2: [buffer][col strip | row strip][36]
-    if (own == 0) {
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            b2[CC_SP(16 * part) / 2 + m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
-            b2[CC_STRIP / 2 + CC_SP(16 * part) / 2 + m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
-        }
+        for (int m = 0; m < 8; ++m) b2[CC_STRIP / 2 + CC_SP(16 * part) / 2 + m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
     }
     __syncthreads();
 #pragma unroll 1
@@ -502,52 +460,56 @@ __device__ void pv6(const CholArgs& a, int k, double* Dm, double* bufs) {
             if (tid == 0 && c < kb) atomicCAS(&a.info[0], 0, k0 + c + 1);
             piv = 1.0;
         }
+        if (tid == 0) pivs[c] = piv;
         const double rp = cc_fast_rcp(piv);
-        if (own == c) {                                   // keep the unscaled pivot column for the write-out
-#pragma unroll
-            for (int m = 0; m < 16; ++m) Dm[(16 * part + m) * CC_DP + c] = (16 * part + m == c) ? piv : Vd[m];
-        }
-        if (own > c && part == 7) {
+        if (own > c) {
             // D role: column own > c,  D[r][own] -= D[r][c] D[own][c] / piv  (slots with r < own are don't-care and are
-            // updated too).  E role: row own > c,  E[own][j] -= (D[own][c] / piv) E[c][j]  (E[c][j] = 0 for j > c).
+            // updated too)
             const double lj = cb[CC_SP(own)] * rp;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                const double2 x = cb2[m], y = rb2[m];
+                const double2 x = cb2[m];
                 Vd[2 * m] = fma(-x.x, lj, Vd[2 * m]); Vd[2 * m + 1] = fma(-x.y, lj, Vd[2 * m + 1]);
-                Ve[2 * m] = fma(-lj, y.x, Ve[2 * m]); Ve[2 * m + 1] = fma(-lj, y.y, Ve[2 * m + 1]);
+            }
+            if (own == c + 1) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) cn2[m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
             }
         }
-        if (own == c + 1) {
+        if (eown > c && part == 7) {
+            // E role: row eown > c,  E[eown][j] -= (D[eown][c] / piv) E[c][j]  (E[c][j] = 0 for j > c)
+            const double le = cb[CC_SP(eown)] * rp;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                cn2[m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
-                rn2[m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
+                const double2 y = rb2[m];
+                Ve[2 * m] = fma(-le, y.x, Ve[2 * m]); Ve[2 * m + 1] = fma(-le, y.y, Ve[2 * m + 1]);
+            }
+            if (eown == c + 1) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) rn2[m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
             }
         }
         __syncthreads();
     }
+    // column `own` of D was last touched at step own - 1, so Vd still holds the unscaled pivot column:
     // L = (unscaled columns) diag(piv)^{-1/2},  W = diag(piv)^{-1/2} E
+    if (tid < CC_NB) pivs[64 + tid] = 1.0 / sqrt(pivs[tid]);
+    __syncthreads();
     double* Wk = a.W + (size_t)k * CC_NB * CC_NB;
-    const double sr = 1.0 / sqrt(Dm[own * CC_DP + own]);
+    const double sd = pivs[64 + own], se = pivs[64 + eown];
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
-        const int j = 16 * part + m;
-        Wk[own * CC_NB + j] = (j <= own) ? Ve[m] * sr : 0.0;
-    }
-    for (int idx = tid; idx < CC_NB * CC_NB; idx += CC_NT) {
-        const int rr = idx >> 6, c = idx & 63;
-        if (rr < kb && c <= rr) {
-            const double sc = sqrt(Dm[c * CC_DP + c]);
-            a.A[(size_t)(k0 + rr) * a.ld + k0 + c] = (rr == c) ? sc : Dm[rr * CC_DP + c] / sc;
-        }
+        const int i = 16 * part + m;
+        Wk[eown * CC_NB + i] = (i <= eown) ? Ve[m] * se : 0.0;
+        if (i < kb && own < kb && i >= own) a.A[(size_t)(k0 + i) * a.ld + k0 + own] = (i == own) ? pivs[own] * sd : Vd[m] * sd;
     }
     __syncthreads();
 }
 
 
-__device__ void pv7(const CholArgs& a, int k, double* Dm, double* bufs) {
+__device__ void pv6(const CholArgs& a, int k, double* Dm, double* bufs) {
     const int tid = threadIdx.x, own = tid >> 2, part = tid & 3;
+    const int eown = (own + 32) & 63;                    // E role owner index: the row strip is published by another warp
     const int k0 = k * CC_NB, kb = min(CC_NB, a.n - k0);
     // slot m of a thread is index 16 part + m (row index in the D role, column index in the E role)
     double Vd[16], Ve[16];
@@ -557,15 +519,101 @@ __device__ void pv7(const CholArgs& a, int k, double* Dm, double* bufs) {
         double v = (r == own) ? 1.0 : 0.0;
         if (r < kb && own < kb && r >= own) v = a.A[(size_t)(k0 + r) * a.ld + k0 + own];
         Vd[m] = v;
-        Ve[m] = (r == own) ? 1.0 : 0.0;
+        Ve[m] = (r == eown) ? 1.0 : 0.0;
     }
     double2* b2 = reinterpret_cast<double2*>(bufs);      // strips as double2: [buffer][col strip | row strip][36]
+    double* pivs = bufs + 4 * CC_STRIP;                  // 64 pivots, then 64 reciprocal square roots
     if (own == 0) {
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            b2[CC_SP(16 * part) / 2 + m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
-            b2[CC_STRIP / 2 + CC_SP(16 * part) / 2 + m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
+        for (int m = 0; m < 8; ++m) b2[CC_SP(16 * part) / 2 + m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
+    }
+    if (eown == 0) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) b2[CC_STRIP / 2 + CC_SP(16 * part) / 2 + m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int c = 0; c < CC_NB; ++c) {
+        const double* cb = bufs + (c & 1) * 2 * CC_STRIP;        // pivot column c of D (padded)
+        const double2* cb2 = reinterpret_cast<const double2*>(cb) + CC_SP(16 * part) / 2;
+        const double2* rb2 = reinterpret_cast<const double2*>(cb + CC_STRIP) + CC_SP(16 * part) / 2;
+        double2* cn2 = b2 + ((c + 1) & 1) * CC_STRIP + CC_SP(16 * part) / 2;
+        double2* rn2 = cn2 + CC_STRIP / 2;
+        double piv = cb[CC_SP(c)];
+        if (!(piv > 0.0) || !isfinite(piv)) {
+            if (tid == 0 && c < kb) atomicCAS(&a.info[0], 0, k0 + c + 1);
+            piv = 1.0;
         }
+        if (tid == 0) pivs[c] = piv;
+        const double rp = cc_fast_rcp(piv);
+        if (own > c && part == 7) {
+            // D role: column own > c,  D[r][own] -= D[r][c] D[own][c] / piv  (slots with r < own are don't-care and are
+            // updated too)
+            const double lj = cb[CC_SP(own)] * rp;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const double2 x = cb2[m];
+                Vd[2 * m] = fma(-x.x, lj, Vd[2 * m]); Vd[2 * m + 1] = fma(-x.y, lj, Vd[2 * m + 1]);
+            }
+            if (own == c + 1) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) cn2[m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
+            }
+        }
+        if (eown > c && part == 7) {
+            // E role: row eown > c,  E[eown][j] -= (D[eown][c] / piv) E[c][j]  (E[c][j] = 0 for j > c)
+            const double le = cb[CC_SP(eown)] * rp;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const double2 y = rb2[m];
+                Ve[2 * m] = fma(-le, y.x, Ve[2 * m]); Ve[2 * m + 1] = fma(-le, y.y, Ve[2 * m + 1]);
+            }
+            if (eown == c + 1) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) rn2[m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
+            }
+        }
+        __syncthreads();
+    }
+    // column `own` of D was last touched at step own - 1, so Vd still holds the unscaled pivot column:
+    // L = (unscaled columns) diag(piv)^{-1/2},  W = diag(piv)^{-1/2} E
+    if (tid < CC_NB) pivs[64 + tid] = 1.0 / sqrt(pivs[tid]);
+    __syncthreads();
+    double* Wk = a.W + (size_t)k * CC_NB * CC_NB;
+    const double sd = pivs[64 + own], se = pivs[64 + eown];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const int i = 16 * part + m;
+        Wk[eown * CC_NB + i] = (i <= eown) ? Ve[m] * se : 0.0;
+        if (i < kb && own < kb && i >= own) a.A[(size_t)(k0 + i) * a.ld + k0 + own] = (i == own) ? pivs[own] * sd : Vd[m] * sd;
+    }
+    __syncthreads();
+}
+
+
+__device__ void pv7(const CholArgs& a, int k, double* Dm, double* bufs) {
+    const int tid = threadIdx.x, own = tid >> 2, part = tid & 3;
+    const int eown = (own + 32) & 63;                    // E role owner index: the row strip is published by another warp
+    const int k0 = k * CC_NB, kb = min(CC_NB, a.n - k0);
+    // slot m of a thread is index 16 part + m (row index in the D role, column index in the E role)
+    double Vd[16], Ve[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const int r = 16 * part + m;
+        double v = (r == own) ? 1.0 : 0.0;
+        if (r < kb && own < kb && r >= own) v = a.A[(size_t)(k0 + r) * a.ld + k0 + own];
+        Vd[m] = v;
+        Ve[m] = (r == eown) ? 1.0 : 0.0;
+    }
+    double2* b2 = reinterpret_cast<double2*>(bufs);      // strips as double2: [buffer][col strip | row strip][36]
+    double* pivs = bufs + 4 * CC_STRIP;                  // 64 pivots, then 64 reciprocal square roots
+    if (own == 0) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) b2[CC_SP(16 * part) / 2 + m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
+    }
+    if (eown == 0) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) b2[CC_STRIP / 2 + CC_SP(16 * part) / 2 + m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
     }
     __syncthreads();
 #pragma unroll 1
@@ -580,45 +628,48 @@ __device__ void pv7(const CholArgs& a, int k, double* Dm, double* bufs) {
             if (tid == 0 && c < kb) atomicCAS(&a.info[0], 0, k0 + c + 1);
             piv = 1.0;
         }
+        if (tid == 0) pivs[c] = piv;
         const double rp = cc_fast_rcp(piv);
-        if (own == c) {                                   // keep the unscaled pivot column for the write-out
-#pragma unroll
-            for (int m = 0; m < 16; ++m) Dm[(16 * part + m) * CC_DP + c] = (16 * part + m == c) ? piv : Vd[m];
-        }
         if (own > c) {
             // D role: column own > c,  D[r][own] -= D[r][c] D[own][c] / piv  (slots with r < own are don't-care and are
-            // updated too).  E role: row own > c,  E[own][j] -= (D[own][c] / piv) E[c][j]  (E[c][j] = 0 for j > c).
+            // updated too)
             const double lj = cb[CC_SP(own)] * rp;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                const double2 x = cb2[m], y = rb2[m];
+                const double2 x = cb2[m];
                 Vd[2 * m] = fma(-x.x, lj, Vd[2 * m]); Vd[2 * m + 1] = fma(-x.y, lj, Vd[2 * m + 1]);
-                Ve[2 * m] = fma(-lj, y.x, Ve[2 * m]); Ve[2 * m + 1] = fma(-lj, y.y, Ve[2 * m + 1]);
+            }
+            if (own == c + 1) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) cn2[m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
             }
         }
-        if (own == c + 1) {
+        if (eown > c) {
+            // E role: row eown > c,  E[eown][j] -= (D[eown][c] / piv) E[c][j]  (E[c][j] = 0 for j > c)
+            const double le = cb[CC_SP(eown)] * rp;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                cn2[m] = make_double2(Vd[2 * m], Vd[2 * m + 1]);
-                rn2[m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
+                const double2 y = rb2[m];
+                Ve[2 * m] = fma(-le, y.x, Ve[2 * m]); Ve[2 * m + 1] = fma(-le, y.y, Ve[2 * m + 1]);
+            }
+            if (eown == c + 1) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) rn2[m] = make_double2(Ve[2 * m], Ve[2 * m + 1]);
             }
         }
         __syncthreads();
     }
+    // column `own` of D was last touched at step own - 1, so Vd still holds the unscaled pivot column:
     // L = (unscaled columns) diag(piv)^{-1/2},  W = diag(piv)^{-1/2} E
+    if (tid < CC_NB) pivs[64 + tid] = 1.0 / sqrt(pivs[tid]);
+    __syncthreads();
     double* Wk = a.W + (size_t)k * CC_NB * CC_NB;
-    const double sr = 1.0 / sqrt(Dm[own * CC_DP + own]);
+    const double sd = pivs[64 + own], se = pivs[64 + eown];
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
-        const int j = 16 * part + m;
-        Wk[own * CC_NB + j] = (j <= own) ? Ve[m] * sr : 0.0;
-    }
-    for (int idx = tid; idx < CC_NB * CC_NB; idx += CC_NT) {
-        const int rr = idx >> 6, c = idx & 63;
-        if (rr < kb && c <= rr) {
-            const double sc = sqrt(Dm[c * CC_DP + c]);
-            a.A[(size_t)(k0 + rr) * a.ld + k0 + c] = (rr == c) ? sc : Dm[rr * CC_DP + c] / sc;
-        }
+        const int i = 16 * part + m;
+        Wk[eown * CC_NB + i] = (i <= eown) ? Ve[m] * se : 0.0;
+        if (i < kb && own < kb && i >= own) a.A[(size_t)(k0 + i) * a.ld + k0 + own] = (i == own) ? pivs[own] * sd : Vd[m] * sd;
     }
     __syncthreads();
 }

@@ -18,7 +18,8 @@ STORE_F64, STORE_F32 = 0, 1
 EXPORTS = ['sfftb_version', 'sfftb_last_error', 'sfftb_plan_create', 'sfftb_plan_destroy', 'sfftb_plan_dims',
            'sfftb_plan_set_stream', 'sfftb_plan_sync', 'sfftb_fit', 'sfftb_apply', 'sfftb_gss',
            'sfftb_export_normal_eq', 'sfftb_plan_set_timing', 'sfftb_timings', 'sfftb_last_solver',
-           'sfftb_launch_count', 'sfftb_dbg_fft1d', 'sfftb_dbg_row_spectra', 'sfftb_dbg_lag_tables']
+           'sfftb_launch_count', 'sfftb_template_prepare', 'sfftb_template_state',
+           'sfftb_template_mark_ready', 'sfftb_gss_template', 'sfftb_dbg_fft1d', 'sfftb_dbg_row_spectra', 'sfftb_dbg_lag_tables']
 
 
 class Config(C.Structure):
@@ -66,6 +67,10 @@ def lib():
     L.sfftb_apply.argtypes = [vp, vp, vp, ip, ip, vp, ip, vp, ip, ip]
     L.sfftb_gss.argtypes = [vp, vp, vp, vp, vp, ip, ip, vp, ip, vp, ip, ip]
     L.sfftb_export_normal_eq.argtypes = [vp, vp, vp]
+    L.sfftb_template_prepare.argtypes = [vp, vp, vp, ip, ip]
+    L.sfftb_template_state.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.sfftb_template_mark_ready.argtypes = [vp]
+    L.sfftb_gss_template.argtypes = [vp, vp, vp, ip, ip, vp, ip, vp, ip, ip]
     L.sfftb_plan_set_timing.argtypes = [vp, ip]
     L.sfftb_timings.argtypes = [vp, C.POINTER(C.c_float), ip]
     L.sfftb_last_solver.argtypes = [vp]

@@ -33,6 +33,8 @@ struct CholArgs {
     int* info;
     const double* sc; const int* idx; double* sol; int NEQ;
     unsigned long long* dbg;         // optional: globaltimer stamps of panel phases (NULL = off)
+    int resolve;                     // 1: A already holds L (and W its inverse diagonal blocks) from an earlier call
+                                     //    with the same matrix; yv holds a new scaled right-hand side -> substitutions only
 };
 
 __device__ __forceinline__ unsigned long long cc_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
@@ -235,11 +237,58 @@ __global__ void __launch_bounds__(CC_NT, CC_CTAS_PER_SM) chol_coop_kernel(CholAr
 
     if (bid == 0) {
         for (int c = tid; c < a.NEQ; c += CC_NT) a.sol[c] = 0.0;
-        cc_potrf_inv(a, 0, As, Bs);
+        if (!a.resolve) cc_potrf_inv(a, 0, As, Bs);
     }
     cc_grid_barrier(a.bar, target, G);
 
-    for (int k = 0; k < nblk; ++k) {
+    if (a.resolve) {
+        // ---- forward substitution L y = b with the stored factor, b in yv: y_k = W_k (b_k - sum_{j<k} L_kj y_j) ----
+        double* ysf = As;                      // 64 staged entries
+        double* ykf = As + 64;                 // y of the block solved last
+        for (int k = 0; k < nblk; ++k) {
+            // y_{k-1} is final (in xs).  The owner of block k applies it to b_k and solves y_k; the others apply it to
+            // the rows below block k.
+            const int kp0 = (k - 1) * CC_NB, kpb = (k > 0) ? CC_NB : 0;
+            const int k0 = k * CC_NB, kb = min(CC_NB, a.n - k0);
+            const bool owner = bid == k % G;
+            if (owner) {
+                if (tid < CC_NB) {
+                    double sacc = 0.0;
+                    if (tid < kb) {
+                        sacc = a.yv[k0 + tid];
+                        const double* Lrow = a.A + (size_t)(k0 + tid) * a.ld + kp0;
+                        for (int c = 0; c < kpb; ++c) sacc = fma(-Lrow[c], a.xs[kp0 + c], sacc);
+                    }
+                    ysf[tid] = sacc;
+                }
+                __syncthreads();
+                if (tid < kb) {
+                    const double* Wk = a.W + (size_t)k * CC_NB * CC_NB + (size_t)tid * CC_NB;
+                    double sacc = 0.0;
+                    for (int c = 0; c <= tid; ++c) sacc = fma(Wk[c], ysf[c], sacc);
+                    a.xs[k0 + tid] = sacc;
+                }
+            }
+            if ((!owner || G == 1) && kpb > 0 && k0 + kb < a.n) {
+                if (tid < CC_NB) ykf[tid] = a.xs[kp0 + tid];
+                __syncthreads();
+                const int o = (G > 1) ? (bid - (k % G) - 1 + G) % G : 0;
+                const int GO = (G > 1) ? G - 1 : 1;
+                for (int r = k0 + kb + o * CC_NT + tid; r < a.n; r += GO * CC_NT) {
+                    const double* Lrow = a.A + (size_t)r * a.ld + kp0;
+                    double sacc = 0.0;
+                    for (int c = 0; c < kpb; ++c) sacc = fma(Lrow[c], ykf[c], sacc);
+                    a.yv[r] -= sacc;
+                }
+            }
+            cc_grid_barrier(a.bar, target, G);
+        }
+        // y (in xs) becomes the right-hand side of the back substitution
+        for (int c = bid * CC_NT + tid; c < a.n; c += G * CC_NT) a.yv[c] = a.xs[c];
+        cc_grid_barrier(a.bar, target, G);
+    }
+
+    for (int k = 0; k < (a.resolve ? 0 : nblk); ++k) {
         const int k0 = k * CC_NB, kb = min(CC_NB, a.n - k0), r1 = k0 + kb;
         if (bid == 0) CC_STAMP(8 * k + 0);
         // ---- (a) panel below the diagonal block: L_ik = A_ik W_k^T, 32-row slabs ----
@@ -311,8 +360,10 @@ __global__ void __launch_bounds__(CC_NT, CC_CTAS_PER_SM) chol_coop_kernel(CholAr
     }
 
     // ---- back substitution L^T x = y, y = row n ----
-    for (int c = bid * CC_NT + tid; c < a.n; c += G * CC_NT) a.yv[c] = a.A[(size_t)a.n * a.ld + c];
-    cc_grid_barrier(a.bar, target, G);
+    if (!a.resolve) {
+        for (int c = bid * CC_NT + tid; c < a.n; c += G * CC_NT) a.yv[c] = a.A[(size_t)a.n * a.ld + c];
+        cc_grid_barrier(a.bar, target, G);
+    }
     double* ys = As;                       // 64 staged right-hand-side entries
     double* xk = As + 64;                  // 64 entries of the block solved last
     for (int k = nblk - 1; k >= 0; --k) {

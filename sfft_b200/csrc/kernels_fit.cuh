@@ -343,6 +343,17 @@ __global__ void fill_diag_kernel(FillArgs f, const int* __restrict__ idx, int n,
     else sc[rr] = rsqrt(d);
 }
 
+// scaled right-hand side only (cached-factor path): b[rr] = RHb[idx[rr]] * sc[rr]
+__global__ void fill_rhs_kernel(FillArgs f, const int* __restrict__ idx, int n, const double* __restrict__ sc,
+                                double* __restrict__ b, int* __restrict__ info)
+{
+    const int rr = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rr >= n) return;
+    const double v = fill_rhs_entry(f, idx[rr]) * sc[rr];
+    if (!isfinite(v)) atomicExch(&info[1], 1);
+    b[rr] = v;
+}
+
 // Aug is (n+1) x ld row-major: rows/cols 0..n-1 = scaled compact LHMAT, row n = scaled RHb (and column n mirrors it).
 // sc == nullptr -> unscaled (used for the export hook with idx = identity).
 __global__ void fill_matrix_kernel(FillArgs f, const int* __restrict__ idx, int n, const double* __restrict__ sc,

@@ -109,6 +109,11 @@ struct sfftb_plan {
     FillArgs fill;
     size_t smem_fit, smem_fir, smem_row, smem_fir2, smem_fir3;
     cd* firTaps; double* firCA;
+    void* tstate;                // cached template row spectra: [fit: mI planes | apply: I planes], storage type
+    size_t tstate_bytes;
+    int have_template;
+    int factor_cached;           // template path: Aug / cholW hold the Cholesky factor of the (tile independent) LHMAT
+    int resolves;                // number of solves served from the cached factor (diagnostics)
     int grid_fit;
     int nrowsK, nrowsL;
     // state
@@ -262,7 +267,7 @@ static int plan_free(sfftb_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     void* ptrs[] = {p->vt8_8, p->vt64_8, p->vt64_4, p->vt256_4, p->vt512_4, p->tabA, p->tabB_row, p->tabC_row, p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
-                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->firTaps, p->firCA};
+                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->firTaps, p->firCA, p->tstate};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->info_h) cudaFreeHost(p->info_h);
     for (int k = 0; k < EV_COUNT; ++k) if (p->ev[k]) cudaEventDestroy(p->ev[k]);
@@ -765,10 +770,11 @@ static int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, i
     return 0;
 }
 
-static int run_cholesky(sfftb_plan* p) {
+static int run_cholesky(sfftb_plan* p, int resolve = 0) {
     const int n = p->nsolve, ntot = n + 1;
     if (p->chol_coop) {
         CholArgs ca;
+        ca.resolve = resolve;
         ca.A = p->Aug; ca.ld = p->ld; ca.n = n; ca.ntot = ntot; ca.W = p->cholW; ca.yv = p->cholY; ca.xs = p->cholX;
         ca.bar = p->cholBar; ca.info = p->info; ca.sc = p->sc; ca.idx = p->idxmap; ca.sol = p->sol; ca.NEQ = p->d.NEQ;
         CK(cudaMemsetAsync(p->cholBar, 0, sizeof(unsigned) * 4, p->stream));
@@ -843,31 +849,33 @@ static int run_lu(sfftb_plan* p) {
     return 0;
 }
 
+// tI != NULL: cached template row spectra of the I image (sfftb_template_prepare); the I row pass is skipped
 template <typename TSt>
-static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype) {
+static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, const void* tI = nullptr) {
     const sfftb_dims& d = p->d;
     EVREC(p, EV_START);
-    if (launch_row_fwd<TSt>(p, dI, dtype, (TSt*)p->gI, d.DK + 1)) return SFFTB_ECUDA;
+    const TSt* gIsrc = tI ? (const TSt*)tI : (const TSt*)p->gI;
+    if (!tI && launch_row_fwd<TSt>(p, dI, dtype, (TSt*)p->gI, d.DK + 1)) return SFFTB_ECUDA;
     if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
     EVREC(p, EV_ROWS);
     if (p->fit_seg == 2) {
         const int DK = d.DK;
-        if (DK == 0) fit_seg3_kernel<TSt, 0><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap2);
-        else if (DK == 1) fit_seg3_kernel<TSt, 1><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap2);
-        else fit_seg3_kernel<TSt, 2><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap2);
+        if (DK == 0) fit_seg3_kernel<TSt, 0><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else if (DK == 1) fit_seg3_kernel<TSt, 1><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else fit_seg3_kernel<TSt, 2><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
     } else if (p->fit_seg) {
         const int DK = d.DK;
-        if (DK == 0) fit_seg_kernel<TSt, 0><<<p->grid_sfit, FSG_NT, p->smem_sfit, p->stream>>>(p->sfit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap2);
-        else if (DK == 1) fit_seg_kernel<TSt, 1><<<p->grid_sfit, FSG_NT, p->smem_sfit, p->stream>>>(p->sfit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap2);
-        else fit_seg_kernel<TSt, 2><<<p->grid_sfit, FSG_NT, p->smem_sfit, p->stream>>>(p->sfit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap2);
+        if (DK == 0) fit_seg_kernel<TSt, 0><<<p->grid_sfit, FSG_NT, p->smem_sfit, p->stream>>>(p->sfit, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else if (DK == 1) fit_seg_kernel<TSt, 1><<<p->grid_sfit, FSG_NT, p->smem_sfit, p->stream>>>(p->sfit, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else fit_seg_kernel<TSt, 2><<<p->grid_sfit, FSG_NT, p->smem_sfit, p->stream>>>(p->sfit, gIsrc, (const TSt*)p->gJ, p->kap2);
     } else if (p->fit_fast == 4)
-        fit_col_fast_kernel<TSt, 4><<<p->grid_ffit, FCF_NT, p->smem_ffit, p->stream>>>(p->ffit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
+        fit_col_fast_kernel<TSt, 4><<<p->grid_ffit, FCF_NT, p->smem_ffit, p->stream>>>(p->ffit, gIsrc, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
     else if (p->fit_fast == 2)
-        fit_col_fast_kernel<TSt, 2><<<p->grid_ffit, FCF_NT, p->smem_ffit, p->stream>>>(p->ffit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
+        fit_col_fast_kernel<TSt, 2><<<p->grid_ffit, FCF_NT, p->smem_ffit, p->stream>>>(p->ffit, gIsrc, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
     else if (p->fit_fast == 1)
-        fit_col_fast_kernel<TSt, 1><<<p->grid_ffit, FCF_NT, p->smem_ffit, p->stream>>>(p->ffit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
+        fit_col_fast_kernel<TSt, 1><<<p->grid_ffit, FCF_NT, p->smem_ffit, p->stream>>>(p->ffit, gIsrc, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
     else
-        fit_col_kernel<TSt><<<p->grid_fit, NT_COL, p->smem_fit, p->stream>>>(p->cfit, (const TSt*)p->gI, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
+        fit_col_kernel<TSt><<<p->grid_fit, NT_COL, p->smem_fit, p->stream>>>(p->cfit, gIsrc, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
     CKL(p);
     EVREC(p, EV_COL);
     if (p->fit_seg) {
@@ -885,13 +893,25 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype) 
         CKL(p);
     }
     CK(cudaMemsetAsync(p->info, 0, sizeof(int) * 4, p->stream));
-    if (fill_system(p)) return SFFTB_ECUDA;
-    EVREC(p, EV_RED);
-    if (run_cholesky(p)) return SFFTB_ECUDA;
+    bool used_cache = false;
+    if (tI && p->factor_cached && p->chol_coop) {
+        // LHMAT depends on the (masked) template only: reuse its factor, assemble just the right-hand side
+        fill_rhs_kernel<<<(p->nsolve + 127) / 128, 128, 0, p->stream>>>(p->fill, p->idxmap, p->nsolve, p->sc, p->cholY, p->info);
+        CKL(p);
+        EVREC(p, EV_RED);
+        if (run_cholesky(p, 1)) return SFFTB_ECUDA;
+        p->resolves++;
+        used_cache = true;
+    } else {
+        p->factor_cached = 0;            // Aug is about to be overwritten
+        if (fill_system(p)) return SFFTB_ECUDA;
+        EVREC(p, EV_RED);
+        if (run_cholesky(p)) return SFFTB_ECUDA;
+    }
     EVREC(p, EV_SOLVE);
     CK(cudaMemcpyAsync(p->info_h, p->info, sizeof(int) * 4, cudaMemcpyDeviceToHost, p->stream));
     p->have_fit = 1;
-    p->last_solver = 1;
+    p->last_solver = used_cache ? 3 : 1;
     return 0;
 }
 
@@ -913,27 +933,29 @@ static int check_solver(sfftb_plan* p) {
 }
 
 template <typename TSt>
-static int apply_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, const double* dsol, void* ddiff, int diff_dtype) {
+static int apply_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, const double* dsol, void* ddiff, int diff_dtype,
+                        const void* tI = nullptr) {
     const sfftb_dims& d = p->d;
     EVREC(p, EV_A0);
-    if (launch_row_fwd<TSt>(p, dI, dtype, (TSt*)p->gI, d.DK + 1)) return SFFTB_ECUDA;
+    const TSt* gIsrc = tI ? (const TSt*)tI : (const TSt*)p->gI;
+    if (!tI && launch_row_fwd<TSt>(p, dI, dtype, (TSt*)p->gI, d.DK + 1)) return SFFTB_ECUDA;
     if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
     EVREC(p, EV_AROWS);
     if (p->smem_fir3 <= p->max_smem && !env_int("SFFTB_FIR_V2", 0) && !env_int("SFFTB_FIR_V1", 0)) {
         fir_taps_kernel<<<d.N1 / 2 + 1, 128, 0, p->stream>>>(p->fir, dsol, p->firTaps, p->firCA);
         CKL(p);
         dim3 grd(d.N1 / 2 + 1, (d.N0 + FIR3_CH - 1) / FIR3_CH);
-#define RUN_FIR3(DKK) if (d.DK == DKK) apply_fir3_kernel<TSt, DKK><<<grd, FIR3_NT, p->smem_fir3, p->stream>>>(p->fir, (const TSt*)p->gI, (const TSt*)p->gJ, p->firTaps, p->firCA, (TSt*)p->gJ);
+#define RUN_FIR3(DKK) if (d.DK == DKK) apply_fir3_kernel<TSt, DKK><<<grd, FIR3_NT, p->smem_fir3, p->stream>>>(p->fir, gIsrc, (const TSt*)p->gJ, p->firTaps, p->firCA, (TSt*)p->gJ);
         RUN_FIR3(0) RUN_FIR3(1) RUN_FIR3(2) RUN_FIR3(3)
 #undef RUN_FIR3
     } else if (p->smem_fir2 <= p->max_smem && !env_int("SFFTB_FIR_V1", 0)) {
         dim3 grd(d.N1 / 2 + 1, (d.N0 + FIR2_CH - 1) / FIR2_CH);
-#define RUN_FIR2(DKK) if (d.DK == DKK) apply_fir2_kernel<TSt, DKK><<<grd, FIR2_NT, p->smem_fir2, p->stream>>>(p->fir, (const TSt*)p->gI, (const TSt*)p->gJ, dsol, (TSt*)p->gJ);
+#define RUN_FIR2(DKK) if (d.DK == DKK) apply_fir2_kernel<TSt, DKK><<<grd, FIR2_NT, p->smem_fir2, p->stream>>>(p->fir, gIsrc, (const TSt*)p->gJ, dsol, (TSt*)p->gJ);
         RUN_FIR2(0) RUN_FIR2(1) RUN_FIR2(2) RUN_FIR2(3)
 #undef RUN_FIR2
     } else {
         dim3 grd(d.N1 / 2 + 1, (d.N0 + FIR_CHUNK - 1) / FIR_CHUNK);
-        apply_fir_kernel<TSt><<<grd, FIR_NT, p->smem_fir, p->stream>>>(p->fir, (const TSt*)p->gI, (const TSt*)p->gJ, dsol, (TSt*)p->gJ);
+        apply_fir_kernel<TSt><<<grd, FIR_NT, p->smem_fir, p->stream>>>(p->fir, gIsrc, (const TSt*)p->gJ, dsol, (TSt*)p->gJ);
     }
     CKL(p);
     EVREC(p, EV_ACOL);
@@ -1056,6 +1078,90 @@ extern "C" int sfftb_gss(sfftb_plan* p, const void* I, const void* J, const void
         rc = check_solver(p);
         if (rc < 0) return rc;
         if (rc == 0) break;          // Cholesky was fine; rc == 1: solution replaced by the LU fallback -> apply again
+    }
+    if ((rc = collect_timings(p, true, true))) return rc;
+    if (diff_memkind == SFFTB_MEM_HOST) {
+        const size_t bytes = (size_t)p->d.N0 * p->d.N1 * (diff_dtype == SFFTB_F64 ? 8 : 4);
+        CK(cudaMemcpyAsync(diff, p->stA, bytes, cudaMemcpyDeviceToHost, p->stream));
+    }
+    if ((rc = copy_out(p, solution, sol_memkind, p->sol, sizeof(double) * p->d.NEQ))) return rc;
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+// ---- shared-template batch path (the reference re-transforms the template for every pair) ------------
+static int template_alloc(sfftb_plan* p) {
+    if (p->tstate) return 0;
+    const size_t csz = p->cfg.storage == SFFTB_STORE_F32 ? sizeof(float2) : sizeof(double2);
+    p->tstate_bytes = 2 * csz * (size_t)(p->d.DK + 1) * (p->d.N1 / 2 + 1) * p->d.N0;
+    CK(cudaMalloc(&p->tstate, p->tstate_bytes));
+    return 0;
+}
+
+extern "C" int sfftb_template_prepare(sfftb_plan* p, const void* I, const void* mI, int memkind, int dtype) {
+    if (!p || !I || !mI) return fail(SFFTB_EINVAL, "null argument");
+    CK(cudaSetDevice(p->device));
+    int rc;
+    if ((rc = template_alloc(p))) return rc;
+    const void *dI, *dmI;
+    if ((rc = stage_in(p, mI, memkind, dtype, p->stA, &dmI))) return rc;
+    if ((rc = stage_in(p, I, memkind, dtype, p->stB, &dI))) return rc;
+    char* half = (char*)p->tstate + p->tstate_bytes / 2;
+    if (p->cfg.storage == SFFTB_STORE_F32) {
+        if (launch_row_fwd<float2>(p, dmI, dtype, (float2*)p->tstate, p->d.DK + 1)) return SFFTB_ECUDA;
+        if (launch_row_fwd<float2>(p, dI, dtype, (float2*)half, p->d.DK + 1)) return SFFTB_ECUDA;
+    } else {
+        if (launch_row_fwd<double2>(p, dmI, dtype, (double2*)p->tstate, p->d.DK + 1)) return SFFTB_ECUDA;
+        if (launch_row_fwd<double2>(p, dI, dtype, (double2*)half, p->d.DK + 1)) return SFFTB_ECUDA;
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    p->have_template = 1;
+    p->factor_cached = 0;
+    return 0;
+}
+
+extern "C" int sfftb_template_state(sfftb_plan* p, void** dptr, size_t* bytes) {
+    if (!p || !dptr || !bytes) return fail(SFFTB_EINVAL, "null argument");
+    CK(cudaSetDevice(p->device));
+    int rc;
+    if ((rc = template_alloc(p))) return rc;
+    *dptr = p->tstate; *bytes = p->tstate_bytes;
+    return 0;
+}
+
+extern "C" int sfftb_template_mark_ready(sfftb_plan* p) {
+    if (!p || !p->tstate) return fail(SFFTB_ESTATE, "template state was never allocated");
+    p->have_template = 1;
+    p->factor_cached = 0;
+    return 0;
+}
+
+extern "C" int sfftb_gss_template(sfftb_plan* p, const void* J, const void* mJ, int memkind, int dtype,
+                                  double* solution, int sol_memkind, void* diff, int diff_memkind, int diff_dtype) {
+    if (!p || !diff || !J || !mJ) return fail(SFFTB_EINVAL, "null argument");
+    if (!p->have_template) return fail(SFFTB_ESTATE, "no template has been prepared on this plan");
+    if (diff_dtype != SFFTB_F64 && diff_dtype != SFFTB_F32) return fail(SFFTB_EINVAL, "bad diff dtype");
+    CK(cudaSetDevice(p->device));
+    const bool f32 = p->cfg.storage == SFFTB_STORE_F32;
+    const void* tfit = p->tstate;
+    const void* tapp = (const char*)p->tstate + p->tstate_bytes / 2;
+    const void* dJ;
+    int rc;
+    if ((rc = stage_in(p, mJ, memkind, dtype, p->stB, &dJ))) return rc;
+    rc = f32 ? fit_device<float2>(p, nullptr, dJ, dtype, tfit) : fit_device<double2>(p, nullptr, dJ, dtype, tfit);
+    if (rc) return rc;
+    void* ddiff = diff_memkind == SFFTB_MEM_DEVICE ? diff : p->stA;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if ((rc = stage_in(p, J, memkind, dtype, p->stB, &dJ))) return rc;
+        rc = f32 ? apply_device<float2>(p, nullptr, dJ, dtype, p->sol, ddiff, diff_dtype, tapp)
+                 : apply_device<double2>(p, nullptr, dJ, dtype, p->sol, ddiff, diff_dtype, tapp);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(p->stream));
+        if (attempt == 1) break;
+        rc = check_solver(p);
+        if (rc < 0) { p->factor_cached = 0; return rc; }
+        if (rc == 0) { p->factor_cached = (p->chol_coop && !env_int("SFFTB_NO_FACTOR_CACHE", 0)) ? 1 : 0; break; }
+        p->factor_cached = 0;            // the LU fallback ran: Aug no longer holds a Cholesky factor
     }
     if ((rc = collect_timings(p, true, true))) return rc;
     if (diff_memkind == SFFTB_MEM_HOST) {

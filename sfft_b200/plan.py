@@ -74,7 +74,7 @@ class Plan:
 
     @property
     def last_solver(self):
-        return {0: None, 1: 'cholesky', 2: 'lu'}[int(self._L.sfftb_last_solver(self._h))]
+        return {0: None, 1: 'cholesky', 2: 'lu', 3: 'cholesky-cached'}[int(self._L.sfftb_last_solver(self._h))]
 
     def _check_pair(self, *imgs):
         for a in imgs:
@@ -118,6 +118,52 @@ class Plan:
                                   sol.ctypes.data, B.MEM_HOST, diff.ctypes.data, B.MEM_HOST,
                                   B.F64 if diff.dtype == np.float64 else B.F32))
         return sol, diff
+
+    # ---- shared-template batch path (BASELINE config 4) ---------------------------
+    def template_prepare(self, PixA_I, PixA_mI):
+        """Row spectra of the convolved image (the template when ForceConv='REF') and of its masked version,
+        computed once and reused by every gss_template call."""
+        self._check_pair(PixA_I, PixA_mI)
+        pI, mk, dt, kI = _ptr_of(PixA_I)
+        pm, mk2, dt2, km = _ptr_of(PixA_mI)
+        if (mk, dt) != (mk2, dt2):
+            raise Exception('MeLOn ERROR: I and mI must live in the same memory and share a dtype')
+        B.check(self._L.sfftb_template_prepare(self._h, pI, pm, mk, dt))
+
+    def template_state(self):
+        """(device pointer, bytes) of the template state buffer -- what gets broadcast to the other GPUs."""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        B.check(self._L.sfftb_template_state(self._h, C.byref(ptr), C.byref(n)))
+        return int(ptr.value), int(n.value)
+
+    def template_state_tensor(self):
+        """The template state as a torch uint8 CUDA tensor aliasing the plan's buffer (for torch.distributed)."""
+        import torch
+        ptr, n = self.template_state()
+
+        class _Alias:
+            __cuda_array_interface__ = {'shape': (n,), 'typestr': '|u1', 'data': (ptr, False), 'version': 2, 'strides': None}
+        with torch.cuda.device(self.device):
+            return torch.as_tensor(_Alias(), device=torch.device('cuda', self.device))
+
+    def template_mark_ready(self):
+        B.check(self._L.sfftb_template_mark_ready(self._h))
+
+    def gss_template(self, PixA_J, PixA_mJ, out_dtype=np.float64):
+        self._check_pair(PixA_J, PixA_mJ)
+        pJ, mk, dt, kJ = _ptr_of(PixA_J)
+        pm, mk2, dt2, km = _ptr_of(PixA_mJ)
+        if (mk, dt) != (mk2, dt2):
+            raise Exception('MeLOn ERROR: J and mJ must live in the same memory and share a dtype')
+        sol = np.empty(self.NEQ, np.float64)
+        diff = np.empty(self.shape, out_dtype)
+        B.check(self._L.sfftb_gss_template(self._h, pJ, pm, mk, dt, sol.ctypes.data, B.MEM_HOST, diff.ctypes.data,
+                                           B.MEM_HOST, B.F64 if diff.dtype == np.float64 else B.F32))
+        return sol, diff
+
+    def gss_template_device(self, pJ, pmJ, img_dtype, psol, pdiff, diff_dtype):
+        B.check(self._L.sfftb_gss_template(self._h, pJ, pmJ, B.MEM_DEVICE, img_dtype, psol, B.MEM_DEVICE,
+                                           pdiff, B.MEM_DEVICE, diff_dtype))
 
     # ---- device-array entry points (pointers in / pointers out; used by the PureCupy-style API) ----
     def gss_device(self, pI, pJ, pmI, pmJ, img_dtype, psol, pdiff, diff_dtype):
