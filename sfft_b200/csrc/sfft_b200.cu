@@ -59,6 +59,11 @@ struct sfftb_plan {
     int nsm;
     size_t max_smem;
     cudaStream_t stream, own_stream;
+    cudaStream_t stream2;        // side stream: forward row pass of the apply step overlapped with the solve
+    cudaEvent_t evFork, evJoin;
+    int overlap;                 // 1: sfftb_gss overlaps the apply row pass with the Cholesky solve (device images)
+    int row_grid_limit;          // > 0: cap of the persistent row-kernel grid (half the SMs while overlapped)
+    int chol_grid_limit;
     // tables
     cd *tw0, *tw1, *twMf, *twH, *Q;
     cd *tabA, *tabB_row, *tabC_row;   // register-engine twiddle tables
@@ -272,6 +277,9 @@ static int plan_free(sfftb_plan* p) {
     if (p->info_h) cudaFreeHost(p->info_h);
     for (int k = 0; k < EV_COUNT; ++k) if (p->ev[k]) cudaEventDestroy(p->ev[k]);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    if (p->stream2) cudaStreamDestroy(p->stream2);
+    if (p->evFork) cudaEventDestroy(p->evFork);
+    if (p->evJoin) cudaEventDestroy(p->evJoin);
     delete p;
     return 0;
 }
@@ -288,6 +296,10 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
     CK(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device)); p->max_smem = (size_t)v;
     CK(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
     p->stream = p->own_stream;
+    CK(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&p->evFork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&p->evJoin, cudaEventDisableTiming));
+    p->overlap = env_int("SFFTB_OVERLAP", 1);
     for (int k = 0; k < EV_COUNT; ++k) CK(cudaEventCreate(&p->ev[k]));
     if (init_generic_radix_tables()) return SFFTB_ECUDA;
 
@@ -736,7 +748,7 @@ static int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, i
         const int H = p->row_v8, RBI = ROWV_NT / (H / 8);
         const int ngroups = (p->d.N0 + RBI - 1) / RBI;
         const int nbatch = (ngroups + p->rowv.nit - 1) / p->rowv.nit;
-        const int grid = std::min(nbatch, p->nsm);
+        const int grid = std::min(nbatch, p->row_grid_limit > 0 ? p->row_grid_limit : p->nsm);
 #define RUN_ROWV(HH)                                                                                                   \
         if (H == HH) {                                                                                                 \
             if (dtype == SFFTB_F64) row_fwd_v8_kernel<double, TSt, HH><<<grid, ROWV_NT, p->smem_rowv, p->stream>>>(p->rowv, (const double*)img, out, nj); \
@@ -787,7 +799,7 @@ static int run_cholesky(sfftb_plan* p, int resolve = 0) {
             ca.dbg = dbgbuf;
         }
         void* args[] = {&ca};
-        CK(cudaLaunchCooperativeKernel((void*)chol_coop_kernel, dim3(p->nsm * p->chol_coop), dim3(CC_NT), args,
+        CK(cudaLaunchCooperativeKernel((void*)chol_coop_kernel, dim3(p->chol_grid_limit > 0 ? p->chol_grid_limit : p->nsm * p->chol_coop), dim3(CC_NT), args,
                                        sizeof(double) * 2 * CC_NB * CC_PITCH, p->stream));
         p->launches++;
         if (dbg) {
@@ -851,7 +863,15 @@ static int run_lu(sfftb_plan* p) {
 
 // tI != NULL: cached template row spectra of the I image (sfftb_template_prepare); the I row pass is skipped
 template <typename TSt>
-static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, const void* tI = nullptr) {
+static int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj);
+
+// ovI / ovJ != NULL (device images of the apply step): their forward row pass is issued on the side stream right
+// after the normal equations are assembled, on half of the SMs, while the Cholesky solve runs on the other half
+// (both kernels need a whole SM per CTA, so they cannot share one; the solve is latency bound and hardly notices).
+// The row spectra buffers gI / gJ are free at that point.  apply_device is then called with rows_done = true.
+template <typename TSt>
+static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, const void* tI = nullptr,
+                      const void* ovI = nullptr, const void* ovJ = nullptr) {
     const sfftb_dims& d = p->d;
     EVREC(p, EV_START);
     const TSt* gIsrc = tI ? (const TSt*)tI : (const TSt*)p->gI;
@@ -906,7 +926,25 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, 
         p->factor_cached = 0;            // Aug is about to be overwritten
         if (fill_system(p)) return SFFTB_ECUDA;
         EVREC(p, EV_RED);
-        if (run_cholesky(p)) return SFFTB_ECUDA;
+        const bool ov = ovI && ovJ && p->row_v8 && p->chol_coop && p->nsm >= 8;
+        if (ov) {
+            CK(cudaEventRecord(p->evFork, p->stream));
+            CK(cudaStreamWaitEvent(p->stream2, p->evFork, 0));
+            cudaStream_t main = p->stream;
+            p->stream = p->stream2;
+            p->row_grid_limit = p->nsm / 2;
+            int rc2 = launch_row_fwd<TSt>(p, ovI, dtype, (TSt*)p->gI, d.DK + 1);
+            if (!rc2) rc2 = launch_row_fwd<TSt>(p, ovJ, dtype, (TSt*)p->gJ, 1);
+            p->row_grid_limit = 0;
+            p->stream = main;
+            if (rc2) return SFFTB_ECUDA;
+            CK(cudaEventRecord(p->evJoin, p->stream2));
+            p->chol_grid_limit = p->nsm - p->nsm / 2;
+        }
+        const int rcc = run_cholesky(p);
+        p->chol_grid_limit = 0;
+        if (rcc) return SFFTB_ECUDA;
+        if (ov) CK(cudaStreamWaitEvent(p->stream, p->evJoin, 0));
     }
     EVREC(p, EV_SOLVE);
     CK(cudaMemcpyAsync(p->info_h, p->info, sizeof(int) * 4, cudaMemcpyDeviceToHost, p->stream));
@@ -934,12 +972,14 @@ static int check_solver(sfftb_plan* p) {
 
 template <typename TSt>
 static int apply_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, const double* dsol, void* ddiff, int diff_dtype,
-                        const void* tI = nullptr) {
+                        const void* tI = nullptr, bool rows_done = false) {
     const sfftb_dims& d = p->d;
     EVREC(p, EV_A0);
     const TSt* gIsrc = tI ? (const TSt*)tI : (const TSt*)p->gI;
-    if (!tI && launch_row_fwd<TSt>(p, dI, dtype, (TSt*)p->gI, d.DK + 1)) return SFFTB_ECUDA;
-    if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
+    if (!rows_done) {
+        if (!tI && launch_row_fwd<TSt>(p, dI, dtype, (TSt*)p->gI, d.DK + 1)) return SFFTB_ECUDA;
+        if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
+    }
     EVREC(p, EV_AROWS);
     if (p->smem_fir3 <= p->max_smem && !env_int("SFFTB_FIR_V2", 0) && !env_int("SFFTB_FIR_V1", 0)) {
         fir_taps_kernel<<<d.N1 / 2 + 1, 128, 0, p->stream>>>(p->fir, dsol, p->firTaps, p->firCA);
@@ -1065,13 +1105,17 @@ extern "C" int sfftb_gss(sfftb_plan* p, const void* I, const void* J, const void
     int rc;
     if ((rc = stage_in(p, mI, memkind, dtype, p->stA, &dI))) return rc;
     if ((rc = stage_in(p, mJ, memkind, dtype, p->stB, &dJ))) return rc;
-    rc = f32 ? fit_device<float2>(p, dI, dJ, dtype) : fit_device<double2>(p, dI, dJ, dtype);
+    const bool ov = p->overlap && memkind == SFFTB_MEM_DEVICE && I && J && p->row_v8 && p->chol_coop && p->nsm >= 8;
+    rc = f32 ? fit_device<float2>(p, dI, dJ, dtype, nullptr, ov ? I : nullptr, ov ? J : nullptr)
+             : fit_device<double2>(p, dI, dJ, dtype, nullptr, ov ? I : nullptr, ov ? J : nullptr);
     if (rc) return rc;
     void* ddiff = diff_memkind == SFFTB_MEM_DEVICE ? diff : p->stA;
     for (int attempt = 0; attempt < 2; ++attempt) {
         if ((rc = stage_in(p, I, memkind, dtype, p->stA, &dI))) return rc;
         if ((rc = stage_in(p, J, memkind, dtype, p->stB, &dJ))) return rc;
-        rc = f32 ? apply_device<float2>(p, dI, dJ, dtype, p->sol, ddiff, diff_dtype) : apply_device<double2>(p, dI, dJ, dtype, p->sol, ddiff, diff_dtype);
+        const bool rows_done = ov && attempt == 0;
+        rc = f32 ? apply_device<float2>(p, dI, dJ, dtype, p->sol, ddiff, diff_dtype, nullptr, rows_done)
+                 : apply_device<double2>(p, dI, dJ, dtype, p->sol, ddiff, diff_dtype, nullptr, rows_done);
         if (rc) return rc;
         CK(cudaStreamSynchronize(p->stream));
         if (attempt == 1) break;
