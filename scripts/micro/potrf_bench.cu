@@ -12,7 +12,7 @@ __global__ void __launch_bounds__(CC_NT, 1) kbench(CholArgs a, long long* cyc, i
         for (int i = threadIdx.x; i < 64 * 64; i += CC_NT) a.A[(i >> 6) * a.ld + (i & 63)] = a.yv[i];
         __syncthreads();
         long long t0 = clock64();
-        cc_potrf_inv(a, 0, As, Bs);
+        cc_potrf_inv(a, 0, As, Bs, Bs + CC_NB * CC_PITCH);
         long long t1 = clock64();
         if (threadIdx.x == 0) cyc[rep] = t1 - t0;
     }
@@ -27,7 +27,7 @@ int main() {
     cudaMalloc(&info, 16); cudaMemset(info, 0, 16); cudaMalloc(&cyc, 8 * 16);
     cudaMemcpy(dM, M.data(), sizeof(double) * 4096, cudaMemcpyHostToDevice);
     a.A = dA; a.ld = ld; a.n = n; a.ntot = n + 1; a.W = dW; a.yv = dM; a.info = info;
-    size_t sm = sizeof(double) * 2 * CC_NB * CC_PITCH;
+    size_t sm = sizeof(double) * (2 * CC_NB * CC_PITCH + 512);
     cudaFuncSetAttribute(kbench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     kbench<<<1, CC_NT, sm>>>(a, cyc, 8);
     long long h[8]; cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost);

@@ -112,7 +112,7 @@ __device__ __forceinline__ double cc_fast_rcp(double x) {
 // LDS.128 land in different banks
 #define CC_SP(i) ((i) + 2 * ((i) >> 4))
 #define CC_STRIP 72                      // padded length of a 64-entry strip
-__device__ void cc_potrf_inv(const CholArgs& a, int k, double* Dm, double* bufs) {
+__device__ void cc_potrf_inv_v1(const CholArgs& a, int k, double* Dm, double* bufs) {
     const int tid = threadIdx.x, own = tid >> 2, part = tid & 3;
     const int eown = (own + 32) & 63;                    // E role owner index: the row strip is published by another warp
     const int k0 = k * CC_NB, kb = min(CC_NB, a.n - k0);
@@ -195,6 +195,128 @@ __device__ void cc_potrf_inv(const CholArgs& a, int k, double* Dm, double* bufs)
     __syncthreads();
 }
 
+// ---- blocked diagonal factorisation: 8 x 8 micro blocks, DMMA for everything off the micro diagonal -----------------
+// The pivot-to-pivot chain is what bounds the look-ahead path, and a rank-1 formulation spends ~650 cycles per pivot
+// on issue and barrier overheads of a whole CTA.  Here a micro block is factored (and inverted) by a single warp
+// with shuffles (lane = row, ~130 cycles per pivot, no barrier), the 8-column panel below it is solved with
+// L21 = A21 W8^T and the trailing part of the 64 x 64 tile updated with mma.sync m8n8k4 by all warps; the full
+// inverse W = L^{-1} follows from the micro inverses by block forward substitution, one column block per warp.
+// D: 64 x CC_PITCH doubles (the tile, becomes L), Wf: 64 x CC_PITCH doubles (becomes W), scr: 8 x 64 doubles.
+__device__ void cc_potrf_inv(const CholArgs& a, int k, double* D, double* Wf, double* scr) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int k0 = k * CC_NB, kb = min(CC_NB, a.n - k0);
+    for (int idx = tid; idx < CC_NB * CC_NB; idx += CC_NT) {
+        const int r = idx >> 6, c = idx & 63;
+        double v = (r == c) ? 1.0 : 0.0;
+        if (r < kb && c < kb && c <= r) v = a.A[(size_t)(k0 + r) * a.ld + k0 + c];
+        D[r * CC_PITCH + c] = v;
+        Wf[r * CC_PITCH + c] = 0.0;
+    }
+    __syncthreads();
+    for (int jb = 0; jb < 8; ++jb) {
+        const int d0 = 8 * jb;
+        // (1) micro block: LDL^T elimination with the row operations mirrored on an identity, one warp, lane = row
+        if (warp == 0) {
+            const int r = lane & 7;
+            double av[8], ev[8], pv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { av[j] = (j <= r) ? D[(d0 + r) * CC_PITCH + d0 + j] : 0.0; ev[j] = (j == r) ? 1.0 : 0.0; }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                double piv = __shfl_sync(0xffffffffu, av[c], c, 8);
+                const bool bad = !(piv > 0.0) || !isfinite(piv);
+                if (bad) { if (lane == 0 && d0 + c < kb) atomicCAS(&a.info[0], 0, k0 + d0 + c + 1); piv = 1.0; }
+                pv[c] = piv;
+                const double m = (r > c) ? -av[c] * cc_fast_rcp(piv) : 0.0;
+#pragma unroll
+                for (int j = c + 1; j < 8; ++j) { const double dj = __shfl_sync(0xffffffffu, av[c], j, 8); av[j] = fma(m, dj, av[j]); }
+#pragma unroll
+                for (int j = 0; j <= c; ++j) { const double ej = __shfl_sync(0xffffffffu, ev[j], c, 8); ev[j] = fma(m, ej, ev[j]); }
+            }
+            double rs[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) rs[c] = rsqrt(pv[c]);
+            double rr = rs[0];
+#pragma unroll
+            for (int c = 1; c < 8; ++c) rr = (r == c) ? rs[c] : rr;
+            if (lane < 8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j <= r) {
+                        D[(d0 + r) * CC_PITCH + d0 + j] = (j == r) ? pv[j] * rs[j] : av[j] * rs[j];
+                        Wf[(d0 + r) * CC_PITCH + d0 + j] = ev[j] * rr;
+                    } else {
+                        D[(d0 + r) * CC_PITCH + d0 + j] = 0.0;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // (2) panel below the micro block: L21 = A21 W8^T, one 8-row tile per warp
+        if (warp < 7 - jb) {
+            const int r0 = d0 + 8 + 8 * warp;
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 8; kk += 4)
+                cc_dmma(c0, c1, D[(r0 + g) * CC_PITCH + d0 + kk + t], Wf[(d0 + g) * CC_PITCH + d0 + kk + t]);
+            __syncwarp();
+            D[(r0 + g) * CC_PITCH + d0 + 2 * t] = c0;
+            D[(r0 + g) * CC_PITCH + d0 + 2 * t + 1] = c1;
+        }
+        __syncthreads();
+        // (3) trailing update of the tile: D[ti][tj] -= L[ti][jb] L[tj][jb]^T for jb < tj <= ti
+        {
+            const int nt = 7 - jb;
+            const int ntile = nt * (nt + 1) / 2;
+            for (int q = warp; q < ntile; q += 8) {
+                int ti = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
+                while (ti * (ti + 1) / 2 > q) --ti;
+                while ((ti + 1) * (ti + 2) / 2 <= q) ++ti;
+                const int tj = q - ti * (ti + 1) / 2;
+                const int ri = d0 + 8 + 8 * ti, rj = d0 + 8 + 8 * tj;
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < 8; kk += 4)
+                    cc_dmma(c0, c1, D[(ri + g) * CC_PITCH + d0 + kk + t], D[(rj + g) * CC_PITCH + d0 + kk + t]);
+                D[(ri + g) * CC_PITCH + rj + 2 * t] -= c0;
+                D[(ri + g) * CC_PITCH + rj + 2 * t + 1] -= c1;
+            }
+        }
+        __syncthreads();
+    }
+    // (4) W = L^{-1}: column block `warp`; W_ij = -W8_i sum_{k=j}^{i-1} L_ik W_kj  for i > j
+    {
+        const int j = warp, c0b = 8 * j;
+        double* S = scr + warp * 64;
+        for (int i = j + 1; i < 8; ++i) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int kb8 = j; kb8 < i; ++kb8) {
+#pragma unroll
+                for (int kk = 0; kk < 8; kk += 4)
+                    cc_dmma(s0, s1, D[(8 * i + g) * CC_PITCH + 8 * kb8 + kk + t], Wf[(8 * kb8 + kk + t) * CC_PITCH + c0b + g]);
+            }
+            S[g * 8 + 2 * t] = s0; S[g * 8 + 2 * t + 1] = s1;
+            __syncwarp();
+            double w0 = 0.0, w1 = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 8; kk += 4)
+                cc_dmma(w0, w1, Wf[(8 * i + g) * CC_PITCH + 8 * i + kk + t], S[(kk + t) * 8 + g]);
+            Wf[(8 * i + g) * CC_PITCH + c0b + 2 * t] = -w0;
+            Wf[(8 * i + g) * CC_PITCH + c0b + 2 * t + 1] = -w1;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    double* Wk = a.W + (size_t)k * CC_NB * CC_NB;
+    for (int idx = tid; idx < CC_NB * CC_NB; idx += CC_NT) {
+        const int r = idx >> 6, c = idx & 63;
+        Wk[idx] = (c <= r) ? Wf[r * CC_PITCH + c] : 0.0;
+        if (r < kb && c <= r) a.A[(size_t)(k0 + r) * a.ld + k0 + c] = D[r * CC_PITCH + c];
+    }
+    __syncthreads();
+}
+
 // trailing tile (I, J) of panel k: A[i0.., j0..] -= L[i0.., k] L[j0.., k]^T
 __device__ void cc_update_tile(const CholArgs& a, int k0, int kb, int i0, int j0, double* As, double* Bs) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -237,7 +359,7 @@ __global__ void __launch_bounds__(CC_NT, CC_CTAS_PER_SM) chol_coop_kernel(CholAr
 
     if (bid == 0) {
         for (int c = tid; c < a.NEQ; c += CC_NT) a.sol[c] = 0.0;
-        if (!a.resolve) cc_potrf_inv(a, 0, As, Bs);
+        if (!a.resolve) cc_potrf_inv(a, 0, As, Bs, Bs + CC_NB * CC_PITCH);
     }
     cc_grid_barrier(a.bar, target, G);
 
@@ -337,7 +459,7 @@ __global__ void __launch_bounds__(CC_NT, CC_CTAS_PER_SM) chol_coop_kernel(CholAr
                     for (int I = 1; I < T; ++I)
                         for (int J = 0; J <= min(I, TC - 1); ++J) cc_update_tile(a, k0, kb, r1 + CC_NB * I, r1 + CC_NB * J, As, Bs);
                 }
-                cc_potrf_inv(a, k + 1, As, Bs);
+                cc_potrf_inv(a, k + 1, As, Bs, Bs + CC_NB * CC_PITCH);
                 CC_STAMP(8 * k + 4);
             } else {
                 // tiles in row-major order of the lower triangle, (0, 0) excluded: q' = I (I + 1) / 2 + J for I < TC,
