@@ -47,6 +47,22 @@ __global__ void __launch_bounds__(ROWV_NT, 1) row_fwd_v8_kernel(RowV8Args a, con
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd* buf = reinterpret_cast<cd*>(smem_raw);
     const int tid = threadIdx.x;
+    // twiddle tables of the engine and the untangle factors live in shared memory (an L1 hit still costs a long
+    // scoreboard round trip in the middle of a pass)
+    cd* tabs = buf + (size_t)RBI * PITCH;
+    VTabs vt = a.tabs;
+    {
+        cd* p8 = tabs; cd* p64_8 = p8 + 56; cd* p64_4 = p64_8 + 448; cd* p256 = p64_4 + 192; cd* p512 = p256 + 768;
+        for (int i = tid; i < 56; i += ROWV_NT) p8[i] = a.tabs.t8_8[i];
+        if (H == 512 || H == 2048) for (int i = tid; i < 448; i += ROWV_NT) p64_8[i] = a.tabs.t64_8[i];
+        if (H == 256 || H == 1024) for (int i = tid; i < 192; i += ROWV_NT) p64_4[i] = a.tabs.t64_4[i];
+        if (H == 1024) for (int i = tid; i < 768; i += ROWV_NT) p256[i] = a.tabs.t256_4[i];
+        if (H == 2048) for (int i = tid; i < 1536; i += ROWV_NT) p512[i] = a.tabs.t512_4[i];
+        vt.t8_8 = p8; vt.t64_8 = p64_8; vt.t64_4 = p64_4; vt.t256_4 = p256; vt.t512_4 = p512;
+    }
+    cd* tw1s = tabs + 3000;
+    for (int i = tid; i <= H / 2; i += ROWV_NT) tw1s[i] = a.tw1[i];
+    __syncthreads();
     const int grp = tid / T, lane = tid - grp * T;
     cd* scratch = buf + (size_t)grp * PITCH;
     const int bar_id = 1 + grp;
@@ -91,14 +107,14 @@ __global__ void __launch_bounds__(ROWV_NT, 1) row_fwd_v8_kernel(RowV8Args a, con
                     }
                     v[q] = cmake(x0, x1);
                 }
-                vfft<H>(v, scratch, lane, a.tabs, -1.0, bar_id);
+                vfft<H>(v, scratch, lane, vt, -1.0, bar_id);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) scratch[VPAD(lane + q * T)] = v[q];
                 __syncthreads();
                 // untangle k and H - k together for all RBI rows of the group
                 const int nvalid = min(RBI, a.N0 - r0);
                 for (int k = tid; k <= H / 2; k += ROWV_NT) {
-                    const cd w = a.tw1[k];
+                    const cd w = tw1s[k];
                     cd gk[RBI], gm[RBI];
 #pragma unroll
                     for (int p = 0; p < RBI; ++p) {

@@ -549,7 +549,7 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         rv.tabs.t8_8 = p->vt8_8; rv.tabs.t64_8 = p->vt64_8; rv.tabs.t64_4 = p->vt64_4; rv.tabs.t256_4 = p->vt256_4; rv.tabs.t512_4 = p->vt512_4;
         rv.tw1 = p->tw1;
         const int RBI = ROWV_NT / (r.H / 8);
-        p->smem_rowv = sizeof(cd) * (size_t)RBI * (r.H + r.H / 8 + 8);
+        p->smem_rowv = sizeof(cd) * ((size_t)RBI * (r.H + r.H / 8 + 8) + 3000 + r.H / 2 + 1);
 #define SET_ROWV(HH)                                                                                              \
         if (r.H == HH) {                                                                                              \
             if (f32) { if (set_smem(row_fwd_v8_kernel<float, float2, HH>, p->smem_rowv) || set_smem(row_fwd_v8_kernel<double, float2, HH>, p->smem_rowv)) return SFFTB_ECUDA; } \
