@@ -12,13 +12,18 @@
 // overlap the products of segment s and no warp waits on a CTA-wide barrier inside the segment loop.  One inverse
 // transform per pair per column (all 16 warps) yields the lags.
 #pragma once
+#include <stdio.h>
 #include "fft_vpt.cuh"
 #include "kernels_fit_seg.cuh"
 
 #define FS3_NT 512
 #define FS3_M 256
 #define FS3_PITCH 288
-#define FS3_NSTG 4
+// window ring: 8 buffers for fp32 spectra, 4 for fp64 (shared-memory budget); prefetch distance = depth - 2
+template <typename TSt> struct Fs3Ring { static const int depth = sizeof(TSt) == 8 ? 8 : 4; };
+#ifndef FS3_SLEEP_NS
+#define FS3_SLEEP_NS 200
+#endif
 #define FS3_NMT 64           // product threads that also accumulate the column moments
 
 __device__ __forceinline__ unsigned fs3_saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -35,7 +40,8 @@ __device__ __forceinline__ void fs3_mbar_wait(unsigned long long* b, unsigned pa
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                      : "=r"(done) : "r"(fs3_saddr(b)), "r"(parity) : "memory");
         if (done) break;
-        if (++spins > (1 << 24)) __trap();          // watchdog: a protocol error must abort, not hang the GPU
+        __nanosleep(FS3_SLEEP_NS);                  // idle waiters must not eat the issue slots of the transform warps
+        if (++spins > (1 << 22)) __trap();          // watchdog: a protocol error must abort, not hang the GPU
     }
 }
 __device__ __forceinline__ void fs3_cp_async_arrive(unsigned long long* b) {
@@ -121,6 +127,7 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
     constexpr int NP = 2 * Fij + 1;
     constexpr int NSRC = DK + 2;
     constexpr int NPL = 2 * NP;                       // planes in the ring (two slots)
+    constexpr int NSTG = Fs3Ring<TSt>::depth, LOG2STG = NSTG == 8 ? 3 : 2, PFD = NSTG - 2;
     static_assert(NPL >= 16 || NACC <= NPL, "ring too small for the inverse batches");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const ColArgs& a = fa.c;
@@ -131,10 +138,10 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
     cd* tw8 = macc + FSG_MSLOTS * FS3_NMT;          // 56 entries  (Ns = 8,  R = 8)
     cd* tw64 = tw8 + 56;                            // 192 entries (Ns = 64, R = 4)
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(tw64 + 192);
-    TSt* stage = reinterpret_cast<TSt*>(bars + 8);
+    TSt* stage = reinterpret_cast<TSt*>(bars + 12);
     unsigned long long* full = bars;          // [2]  count NP   (one arrive per transform job)
     unsigned long long* empty = bars + 2;     // [2]  count 8    (one arrive per product warp)
-    unsigned long long* landed = bars + 4;    // [4]  count 256  (cp.async arrivals of the product threads)
+    unsigned long long* landed = bars + 4;    // [NSTG] count 256  (cp.async arrivals of the product threads)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double inv0 = 1.0 / (double)a.N0;
     const int h = fa.h, S = fa.S, nseg = fa.nseg;
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
     if (tid == 0) {
         fs3_mbar_init(full + 0, NP); fs3_mbar_init(full + 1, NP);
         fs3_mbar_init(empty + 0, 8); fs3_mbar_init(empty + 1, 8);
-        for (int b = 0; b < FS3_NSTG; ++b) fs3_mbar_init(landed + b, 256);
+        for (int b = 0; b < NSTG; ++b) fs3_mbar_init(landed + b, 256);
     }
     // the engine's twiddle tables live in shared memory: with ~200 KB of shared memory carved out there is next to
     // no L1 left, and a table miss costs an L2 round trip in the middle of a transform
@@ -161,11 +168,10 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
 #pragma unroll
             for (int q = 0; q < NACC; ++q) acc[q] = cmake(0.0, 0.0);
             cd* kaprow = kap + (size_t)k1 * fa.nrows;
-            if (tid < FS3_NMT)
-                for (int s = 0; s < FSG_MSLOTS; ++s) macc[s * FS3_NMT + tid] = cmake(0.0, 0.0);
+            for (int e = 0; e < SFFTB_MAXE; ++e) macc[((tid >> 6) * SFFTB_MAXE + e) * FS3_NMT + (tid & 63)] = cmake(0.0, 0.0);
             // window prefetch: element tid of every stored plane, two segments ahead
             auto issue = [&](int s) {
-                const int buf = (g + s) & (FS3_NSTG - 1);
+                const int buf = (g + s) & (NSTG - 1);
                 const int r = wrap_row(s * S - h + tid, a.N0);
 #pragma unroll
                 for (int jj = 0; jj < NSRC; ++jj) {
@@ -174,10 +180,19 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
                 }
                 fs3_cp_async_arrive(landed + buf);
             };
-            for (int s = 0; s < 2 && s < nseg; ++s) issue(s);
+            for (int s = 0; s < PFD && s < nseg; ++s) issue(s);
+#ifdef FS3_DEBUG
+            long long dWaitFull = 0, dProd = 0, dMom = 0, dT0 = clock64();
+#endif
             for (int s = 0; s < nseg; ++s) {
                 const int gs = g + s, slot = gs & 1;
+#ifdef FS3_DEBUG
+                long long q0 = clock64();
+#endif
                 fs3_mbar_wait(full + slot, (gs >> 1) & 1);
+#ifdef FS3_DEBUG
+                long long q1 = clock64(); dWaitFull += q1 - q0;
+#endif
                 {
                     const cd* sp = spec + (size_t)slot * NP * FS3_PITCH + VPAD(tid);
                     cd fA[Fij], fB[Fij];
@@ -202,31 +217,51 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
                         acc[NPAIR + A].y = fma(fA[A].x, fJ.y, acc[NPAIR + A].y); acc[NPAIR + A].y = fma(-fA[A].y, fJ.x, acc[NPAIR + A].y);
                     }
                 }
-                // column moments of this segment's core rows (64 threads, 4 rows each, private shared-memory slots)
-                if (tid < FS3_NMT) {
-                    fs3_mbar_wait(landed + (gs & (FS3_NSTG - 1)), (gs >> 2) & 1);
-                    const TSt* st = stage + (size_t)(gs & (FS3_NSTG - 1)) * NSRC * FS3_M;
-                    const int c0 = s * S, Sc = min(S, a.N0 - c0);
-                    for (int n = h + tid; n < h + Sc; n += FS3_NMT) {
-                        const double cx = (c0 + (n - h) + 1) * inv0;
+#ifdef FS3_DEBUG
+                long long q2 = clock64(); dProd += q2 - q1;
+#endif
+                // column moments of this segment's core rows: 64 threads per stored plane, <= 4 rows each; the slots of
+                // a thread are loaded once, updated in registers and stored back (no read-modify-write chains)
+                {
+                    const int jj = tid >> 6, mt = tid & 63;
+                    if (jj < NSRC) {
+                        fs3_mbar_wait(landed + (gs & (NSTG - 1)), (gs >> LOG2STG) & 1);
+                        const TSt* st = stage + ((size_t)(gs & (NSTG - 1)) * NSRC + jj) * FS3_M;
+                        const int c0 = s * S, Sc = min(S, a.N0 - c0);
+                        const int ne = (jj == DK + 1) ? a.DB + 1 : DK - jj + a.DB + 1;
+                        cd ma[6];
 #pragma unroll
-                        for (int jj = 0; jj < NSRC; ++jj) {
-                            const int ne = (jj == DK + 1) ? a.DB + 1 : DK - jj + a.DB + 1;
-                            cd gg = load_c(st + jj * FS3_M + n);
-                            for (int e = 0; e < ne; ++e) {
-                                cd* sl = macc + (jj * SFFTB_MAXE + e) * FS3_NMT + tid;
-                                *sl = cadd(*sl, gg);
-                                gg = cscale(gg, cx);
+                        for (int e = 0; e < 6; ++e) ma[e] = (e < ne) ? macc[(jj * SFFTB_MAXE + e) * FS3_NMT + mt] : cmake(0.0, 0.0);
+#pragma unroll
+                        for (int rr = 0; rr < FS3_M / FS3_NMT; ++rr) {
+                            // rows are independent; powers of cx first so that only one FMA level depends on the load
+                            const int n = h + mt + rr * FS3_NMT;
+                            const bool live = n < h + Sc;
+                            const double cx = (c0 + (n - h) + 1) * inv0;
+                            const double cx2 = cx * cx, cx3 = cx2 * cx, cx4 = cx2 * cx2, cx5 = cx4 * cx;
+                            const cd gg = live ? load_c(st + (live ? n : 0)) : cmake(0.0, 0.0);
+                            const double pw[6] = {1.0, cx, cx2, cx3, cx4, cx5};
+#pragma unroll
+                            for (int e = 0; e < 6; ++e) {
+                                if (e < ne) { ma[e].x = fma(gg.x, pw[e], ma[e].x); ma[e].y = fma(gg.y, pw[e], ma[e].y); }
                             }
                         }
+#pragma unroll
+                        for (int e = 0; e < 6; ++e)
+                            if (e < ne) macc[(jj * SFFTB_MAXE + e) * FS3_NMT + mt] = ma[e];
                     }
                 }
-                // the arrive certifies: slot consumed AND window buffer of segment s no longer read by this warp, so
-                // the prefetch of segment s + 2 (same buffer as s - 2) issued after the next full-wait is safe
+#ifdef FS3_DEBUG
+                dMom += clock64() - q2;
+#endif
                 __syncwarp();
                 if (lane == 0) fs3_mbar_arrive(empty + slot);
-                if (s + 2 < nseg) issue(s + 2);
+                if (s + PFD < nseg) issue(s + PFD);
             }
+#ifdef FS3_DEBUG
+            if (blockIdx.x == 0 && k1 == blockIdx.x && (tid == 0 || tid == 128))
+                printf("P tid %d: loop %lld cycles, wait_full %lld, product %lld, moments %lld (nseg %d)\n", tid, clock64() - dT0, dWaitFull, dProd, dMom, nseg);
+#endif
             // ---- column moments -> background cross-term rows (product warps only) ----
             fs3_barP();
             if (tid < FSG_MSLOTS) {
@@ -254,6 +289,9 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
         const int fw = warp - 8;
         for (int k1 = blockIdx.x; k1 < a.NH; k1 += gridDim.x, g += nseg) {
             cd* kaprow = kap + (size_t)k1 * fa.nrows;
+#ifdef FS3_DEBUG
+            long long fWaitL = 0, fWaitE = 0, fWork = 0, fT0 = clock64(); int fJobs = 0;
+#endif
             for (int id = fw; id < nseg * NP; id += 8) {
                 const int s = id / NP, p = id - s * NP;
                 const int gs = g + s, slot = gs & 1;
@@ -262,9 +300,18 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
                 const int my_i = isJ ? 0 : a.pl_i[pl];
                 const int my_src = isJ ? DK + 1 : a.pl_j[pl];
                 const int c0 = s * S, Sc = min(S, a.N0 - c0);
-                fs3_mbar_wait(landed + (gs & (FS3_NSTG - 1)), (gs >> 2) & 1);
+#ifdef FS3_DEBUG
+                long long f0 = clock64();
+#endif
+                fs3_mbar_wait(landed + (gs & (NSTG - 1)), (gs >> LOG2STG) & 1);
+#ifdef FS3_DEBUG
+                long long f1 = clock64(); fWaitL += f1 - f0;
+#endif
                 if (gs >= 2) fs3_mbar_wait(empty + slot, ((gs >> 1) - 1) & 1);
-                const TSt* src = stage + ((size_t)(gs & (FS3_NSTG - 1)) * NSRC + my_src) * FS3_M;
+#ifdef FS3_DEBUG
+                long long f2 = clock64(); fWaitE += f2 - f1;
+#endif
+                const TSt* src = stage + ((size_t)(gs & (NSTG - 1)) * NSRC + my_src) * FS3_M;
                 cd* plane = spec + ((size_t)slot * NP + p) * FS3_PITCH;
                 cd v[8];
 #pragma unroll
@@ -285,7 +332,14 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
                 for (int q = 0; q < 8; ++q) plane[VPAD(lane + 32 * q)] = v[q];
                 __syncwarp();
                 if (lane == 0) fs3_mbar_arrive(full + slot);
+#ifdef FS3_DEBUG
+                fWork += clock64() - f2; ++fJobs;
+#endif
             }
+#ifdef FS3_DEBUG
+            if (blockIdx.x == 0 && k1 == blockIdx.x && lane == 0 && (fw == 0 || fw == 7))
+                printf("F warp %d: loop %lld cycles, %d jobs, wait_landed %lld, wait_empty %lld, work %lld\n", fw, clock64() - fT0, fJobs, fWaitL, fWaitE, fWork);
+#endif
             fs3_bar0();                                    // (A)
 #pragma unroll
             for (int b0 = 0; b0 < NACC; b0 += 16) {

@@ -626,8 +626,8 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         {
             const int NPs = 2 * d.Fij + 1;
             const int npla = std::max(2 * NPs, 16);
-            p->smem_sfit3 = sizeof(cd) * ((size_t)npla * FS3_PITCH + 4 * SFFTB_MAXE + (size_t)FSG_MSLOTS * FS3_NMT + 56 + 192) + 64 +
-                            csz * FS3_NSTG * (size_t)(d.DK + 2) * FS3_M;
+            p->smem_sfit3 = sizeof(cd) * ((size_t)npla * FS3_PITCH + 4 * SFFTB_MAXE + (size_t)FSG_MSLOTS * FS3_NMT + 56 + 192) + 96 +
+                            csz * (f32 ? 8 : 4) * (size_t)(d.DK + 2) * FS3_M;
             if (p->smem_sfit3 <= p->max_smem && !env_int("SFFTB_SEG_V2", 0)) {
 #define SET_SFIT3(DKK)                                                                                            \
                 if (d.DK == DKK) {                                                                                    \
