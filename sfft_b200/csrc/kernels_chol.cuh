@@ -202,15 +202,17 @@ __device__ void cc_potrf_inv_v1(const CholArgs& a, int k, double* Dm, double* bu
 // L21 = A21 W8^T and the trailing part of the 64 x 64 tile updated with mma.sync m8n8k4 by all warps; the full
 // inverse W = L^{-1} follows from the micro inverses by block forward substitution, one column block per warp.
 // D: 64 x CC_PITCH doubles (the tile, becomes L), Wf: 64 x CC_PITCH doubles (becomes W), scr: 8 x 64 doubles.
-__device__ void cc_potrf_inv(const CholArgs& a, int k, double* D, double* Wf, double* scr) {
+__device__ void cc_potrf_inv(const CholArgs& a, int k, double* D, double* Wf, double* scr, bool preloaded = false) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int k0 = k * CC_NB, kb = min(CC_NB, a.n - k0);
     for (int idx = tid; idx < CC_NB * CC_NB; idx += CC_NT) {
         const int r = idx >> 6, c = idx & 63;
-        double v = (r == c) ? 1.0 : 0.0;
-        if (r < kb && c < kb && c <= r) v = a.A[(size_t)(k0 + r) * a.ld + k0 + c];
-        D[r * CC_PITCH + c] = v;
+        if (!preloaded) {
+            double v = (r == c) ? 1.0 : 0.0;
+            if (r < kb && c < kb && c <= r) v = a.A[(size_t)(k0 + r) * a.ld + k0 + c];
+            D[r * CC_PITCH + c] = v;
+        }
         Wf[r * CC_PITCH + c] = 0.0;
     }
     __syncthreads();
@@ -347,6 +349,146 @@ __device__ void cc_update_tile(const CholArgs& a, int k0, int kb, int i0, int j0
     __syncthreads();
 }
 
+// Look-ahead path: update the next diagonal tile (rows / columns r1 ..) with panel k and leave it in shared memory
+// (Dout, identity padded, upper triangle zero) for cc_potrf_inv -- no round trip through global memory.
+__device__ void cc_update_diag_to_smem(const CholArgs& a, int k0, int kb, int r1, double* As, double* Dout) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wr = (warp >> 1) * 16, wc = (warp & 1) * 32;
+    const int kbn = min(CC_NB, a.n - r1);
+    const int lrhs = a.n - r1;                 // local row of the right-hand-side row if it falls into this tile (else >= 64)
+    cc_load_tile(As, a.A, a.ld, r1, CC_NB, a.ntot, k0, k0 + kb);
+    double cv[2][4][2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int lr = wr + 8 * r + g;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int lc = wc + 8 * c + 2 * t;
+            const double* p = a.A + (size_t)(r1 + lr) * a.ld + r1 + lc;
+            const bool in0 = (lr < kbn && lc <= lr) || (lr == lrhs && lc < kbn);
+            const bool in1 = (lr < kbn && lc + 1 <= lr) || (lr == lrhs && lc + 1 < kbn);
+            cv[r][c][0] = in0 ? p[0] : ((lr == lc) ? 1.0 : 0.0);
+            cv[r][c][1] = in1 ? p[1] : ((lr == lc + 1) ? 1.0 : 0.0);
+        }
+    }
+    __syncthreads();
+    double acc[2][4][2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { acc[r][c][0] = 0.0; acc[r][c][1] = 0.0; }
+    cc_warp_gemm_nt<4>(As + wr * CC_PITCH, As + wc * CC_PITCH, acc, lane);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int lr = wr + 8 * r + g;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int lc = wc + 8 * c + 2 * t;
+            if (lr == lrhs) {
+                // the right-hand-side row rides along in global memory; in the tile it is identity padding
+                double* p = a.A + (size_t)(r1 + lr) * a.ld + r1 + lc;
+                if (lc < kbn) p[0] = cv[r][c][0] - acc[r][c][0];
+                if (lc + 1 < kbn) p[1] = cv[r][c][1] - acc[r][c][1];
+                Dout[lr * CC_PITCH + lc] = (lr == lc) ? 1.0 : 0.0;
+                Dout[lr * CC_PITCH + lc + 1] = (lr == lc + 1) ? 1.0 : 0.0;
+            } else {
+                Dout[lr * CC_PITCH + lc] = (lr < kbn && lc <= lr) ? cv[r][c][0] - acc[r][c][0] : cv[r][c][0];
+                Dout[lr * CC_PITCH + lc + 1] = (lr < kbn && lc + 1 <= lr) ? cv[r][c][1] - acc[r][c][1] : cv[r][c][1];
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ---- pipelined trailing update of a CTA's tile list ---------------------------------------------------------------
+// Operands of tile n + 1 stream into the second shared-memory buffer pair with cp.async (8-byte copies, zero fill out of
+// range) while tile n runs on the DMMA path; the C tile is prefetched into registers before the MMAs and written back
+// after them, so a tile costs about its MMA time instead of three dependent L2 round trips.
+__device__ __forceinline__ void cc_cp8(double* dst, const double* src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cc_issue_tile(const CholArgs& a, int k0, int kb, int i0, int j0, double* As, double* Bs) {
+    for (int idx = threadIdx.x; idx < CC_NB * CC_NB; idx += CC_NT) {
+        const int r = idx >> 6, c = idx & 63;
+        const bool vc = c < kb;
+        const int gi = i0 + r, gj = j0 + r;
+        const bool vi = vc && gi < a.ntot, vj = vc && gj < a.n;
+        cc_cp8(As + r * CC_PITCH + c, a.A + (size_t)(vi ? gi : 0) * a.ld + k0 + (vc ? c : 0), vi);
+        if (j0 != i0) cc_cp8(Bs + r * CC_PITCH + c, a.A + (size_t)(vj ? gj : 0) * a.ld + k0 + (vc ? c : 0), vj);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void cc_tile_of(int qq, int TC, int& I, int& J) {
+    I = (int)((sqrtf(8.0f * (float)qq + 1.0f) - 1.0f) * 0.5f);
+    while (I * (I + 1) / 2 > qq) --I;
+    while ((I + 1) * (I + 2) / 2 <= qq) ++I;
+    if (I > TC) I = TC;
+    J = qq - I * (I + 1) / 2;
+}
+// tiles qq = q0, q0 + qs, ... < ntile of panel k (row-major lower-triangle numbering, see chol_coop_kernel)
+__device__ void cc_update_tiles(const CholArgs& a, int k0, int kb, int r1, int TC, int q0, int qs, int ntile, double* buf) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wr = (warp >> 1) * 16, wc = (warp & 1) * 32;
+    if (q0 >= ntile) return;
+    int I, J;
+    cc_tile_of(q0, TC, I, J);
+    cc_issue_tile(a, k0, kb, r1 + CC_NB * I, r1 + CC_NB * J, buf, buf + CC_NB * CC_PITCH);
+    int cur = 0;
+    for (int qq = q0; qq < ntile; qq += qs, cur ^= 1) {
+        double* As = buf + cur * 2 * CC_NB * CC_PITCH;
+        double* Bs = As + CC_NB * CC_PITCH;
+        const int i0 = r1 + CC_NB * I, j0 = r1 + CC_NB * J;
+        int In = 0, Jn = 0;
+        const bool more = qq + qs < ntile;
+        if (more) {
+            cc_tile_of(qq + qs, TC, In, Jn);
+            double* An = buf + (cur ^ 1) * 2 * CC_NB * CC_PITCH;
+            cc_issue_tile(a, k0, kb, r1 + CC_NB * In, r1 + CC_NB * Jn, An, An + CC_NB * CC_PITCH);
+        }
+        // C tile -> registers (independent loads, in flight during the MMAs)
+        double cv[2][4][2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int gi = i0 + wr + 8 * r + g;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int gj = j0 + wc + 8 * c + 2 * t;
+                const double* p = a.A + (size_t)gi * a.ld + gj;
+                cv[r][c][0] = (gi < a.ntot && gj < a.n && gj <= gi) ? p[0] : 0.0;
+                cv[r][c][1] = (gi < a.ntot && gj + 1 < a.n && gj + 1 <= gi) ? p[1] : 0.0;
+            }
+        }
+        if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const double* Bq = (j0 != i0) ? Bs : As;
+        double acc[2][4][2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { acc[r][c][0] = 0.0; acc[r][c][1] = 0.0; }
+        cc_warp_gemm_nt<4>(As + wr * CC_PITCH, Bq + wc * CC_PITCH, acc, lane);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int gi = i0 + wr + 8 * r + g;
+            if (gi >= a.ntot) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int gj = j0 + wc + 8 * c + 2 * t;
+                double* p = a.A + (size_t)gi * a.ld + gj;
+                if (gj < a.n && gj <= gi) p[0] = cv[r][c][0] - acc[r][c][0];
+                if (gj + 1 < a.n && gj + 1 <= gi) p[1] = cv[r][c][1] - acc[r][c][1];
+            }
+        }
+        __syncthreads();          // the buffer pair just read is the prefetch target of the next iteration
+        I = In; J = Jn;
+    }
+}
+
 __global__ void __launch_bounds__(CC_NT, CC_CTAS_PER_SM) chol_coop_kernel(CholArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -453,27 +595,21 @@ __global__ void __launch_bounds__(CC_NT, CC_CTAS_PER_SM) chol_coop_kernel(CholAr
         if (TC > 0) {
             const int dsg = (k + 1) % G;
             if (bid == dsg) {
-                cc_update_tile(a, k0, kb, r1, r1, As, Bs);
-                CC_STAMP(8 * k + 3);
                 if (G == 1) {
                     for (int I = 1; I < T; ++I)
                         for (int J = 0; J <= min(I, TC - 1); ++J) cc_update_tile(a, k0, kb, r1 + CC_NB * I, r1 + CC_NB * J, As, Bs);
                 }
-                cc_potrf_inv(a, k + 1, As, Bs, Bs + CC_NB * CC_PITCH);
+                double* R2 = As + 2 * CC_NB * CC_PITCH;
+                cc_update_diag_to_smem(a, k0, kb, r1, As, R2);
+                CC_STAMP(8 * k + 3);
+                cc_potrf_inv(a, k + 1, R2, R2 + CC_NB * CC_PITCH, Bs, true);
                 CC_STAMP(8 * k + 4);
             } else {
                 // tiles in row-major order of the lower triangle, (0, 0) excluded: q' = I (I + 1) / 2 + J for I < TC,
                 // the extra block row I = TC (right-hand-side row) holds TC tiles
                 const int o = (bid - dsg - 1 + G) % G;          // 0 .. G-2
                 const int ntile = TC * (TC + 1) / 2 + (T > TC ? TC : 0);
-                for (int qq = 1 + o; qq < ntile; qq += G - 1) {
-                    int I = (int)((sqrtf(8.0f * (float)qq + 1.0f) - 1.0f) * 0.5f);
-                    while (I * (I + 1) / 2 > qq) --I;
-                    while ((I + 1) * (I + 2) / 2 <= qq) ++I;
-                    if (I > TC) I = TC;
-                    const int J = qq - I * (I + 1) / 2;
-                    cc_update_tile(a, k0, kb, r1 + CC_NB * I, r1 + CC_NB * J, As, Bs);
-                }
+                cc_update_tiles(a, k0, kb, r1, TC, 1 + o, G - 1, ntile, As);
                 if (o == 0) CC_STAMP(8 * k + 5);
             }
         }

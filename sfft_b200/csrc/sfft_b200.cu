@@ -418,7 +418,7 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         CK(cudaMalloc(&p->cholY, sizeof(double) * (size_t)p->nsolve));
         CK(cudaMalloc(&p->cholX, sizeof(double) * (size_t)p->nsolve));
         CK(cudaMalloc(&p->cholBar, sizeof(unsigned) * 4));
-        const size_t csm = sizeof(double) * (2 * CC_NB * CC_PITCH + 8 * 64);
+        const size_t csm = sizeof(double) * (4 * CC_NB * CC_PITCH);
         CK(cudaFuncSetAttribute(chol_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
         int occ = 0, coop = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_coop_kernel, CC_NT, csm));
@@ -800,7 +800,7 @@ static int run_cholesky(sfftb_plan* p, int resolve = 0) {
         }
         void* args[] = {&ca};
         CK(cudaLaunchCooperativeKernel((void*)chol_coop_kernel, dim3(p->chol_grid_limit > 0 ? p->chol_grid_limit : p->nsm * p->chol_coop), dim3(CC_NT), args,
-                                       sizeof(double) * (2 * CC_NB * CC_PITCH + 8 * 64), p->stream));
+                                       sizeof(double) * (4 * CC_NB * CC_PITCH), p->stream));
         p->launches++;
         if (dbg) {
             std::vector<unsigned long long> hst(2048);
