@@ -78,6 +78,9 @@ struct sfftb_plan {
     // workspaces
     void *gI, *gJ;               // transposed row spectra (storage type); gJ doubles as the FDIFF column buffer
     void *stA, *stB;             // device staging for host images / host diff
+    void *stC, *stD;             // second staging pair (host GSS: the apply images are copied while the fit computes)
+    cudaEvent_t evCopy[4], evStart;
+    cudaEvent_t pendI, pendJ;    // events the next row pass of I / J has to wait for (host pipeline), or NULL
     cd *kap, *lam, *nuJ;
     double *R, *RJ, *RT, *RJT;
     double *Aug, *sc, *diagU, *sol;
@@ -272,13 +275,15 @@ static int plan_free(sfftb_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     void* ptrs[] = {p->vt8_8, p->vt64_8, p->vt64_4, p->vt256_4, p->vt512_4, p->tabA, p->tabB_row, p->tabC_row, p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
-                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->firTaps, p->firCA, p->tstate};
+                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->firTaps, p->firCA, p->tstate, p->stC, p->stD};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->info_h) cudaFreeHost(p->info_h);
     for (int k = 0; k < EV_COUNT; ++k) if (p->ev[k]) cudaEventDestroy(p->ev[k]);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     if (p->stream2) cudaStreamDestroy(p->stream2);
     if (p->evFork) cudaEventDestroy(p->evFork);
+    for (int k = 0; k < 4; ++k) if (p->evCopy[k]) cudaEventDestroy(p->evCopy[k]);
+    if (p->evStart) cudaEventDestroy(p->evStart);
     if (p->evJoin) cudaEventDestroy(p->evJoin);
     delete p;
     return 0;
@@ -299,6 +304,8 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
     CK(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&p->evFork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&p->evJoin, cudaEventDisableTiming));
+    for (int k = 0; k < 4; ++k) CK(cudaEventCreateWithFlags(&p->evCopy[k], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&p->evStart, cudaEventDisableTiming));
     p->overlap = env_int("SFFTB_OVERLAP", 1);
     for (int k = 0; k < EV_COUNT; ++k) CK(cudaEventCreate(&p->ev[k]));
     if (init_generic_radix_tables()) return SFFTB_ECUDA;
@@ -875,7 +882,9 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, 
     const sfftb_dims& d = p->d;
     EVREC(p, EV_START);
     const TSt* gIsrc = tI ? (const TSt*)tI : (const TSt*)p->gI;
+    if (p->pendI) { CK(cudaStreamWaitEvent(p->stream, p->pendI, 0)); p->pendI = nullptr; }
     if (!tI && launch_row_fwd<TSt>(p, dI, dtype, (TSt*)p->gI, d.DK + 1)) return SFFTB_ECUDA;
+    if (p->pendJ) { CK(cudaStreamWaitEvent(p->stream, p->pendJ, 0)); p->pendJ = nullptr; }
     if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
     EVREC(p, EV_ROWS);
     if (p->fit_seg == 2) {
@@ -977,7 +986,9 @@ static int apply_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype
     EVREC(p, EV_A0);
     const TSt* gIsrc = tI ? (const TSt*)tI : (const TSt*)p->gI;
     if (!rows_done) {
+        if (p->pendI) { CK(cudaStreamWaitEvent(p->stream, p->pendI, 0)); p->pendI = nullptr; }
         if (!tI && launch_row_fwd<TSt>(p, dI, dtype, (TSt*)p->gI, d.DK + 1)) return SFFTB_ECUDA;
+        if (p->pendJ) { CK(cudaStreamWaitEvent(p->stream, p->pendJ, 0)); p->pendJ = nullptr; }
         if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
     }
     EVREC(p, EV_AROWS);
@@ -1103,6 +1114,47 @@ extern "C" int sfftb_gss(sfftb_plan* p, const void* I, const void* J, const void
     const bool f32 = p->cfg.storage == SFFTB_STORE_F32;
     const void *dI, *dJ;
     int rc;
+    // host images: all four H2D copies are queued on the side stream up front, so the copies of the apply pair run
+    // under the fit and every row pass starts as soon as its own image has landed
+    const bool hostpipe = memkind == SFFTB_MEM_HOST && I && J && mI && mJ && (dtype == SFFTB_F64 || dtype == SFFTB_F32) &&
+                          !env_int("SFFTB_NO_HOSTPIPE", 0);
+    if (hostpipe) {
+        const size_t bytes = (size_t)p->d.N0 * p->d.N1 * (dtype == SFFTB_F64 ? 8 : 4);
+        if (!p->stC) { CK(cudaMalloc(&p->stC, sizeof(double) * (size_t)p->d.N0 * p->d.N1)); CK(cudaMalloc(&p->stD, sizeof(double) * (size_t)p->d.N0 * p->d.N1)); }
+        CK(cudaEventRecord(p->evStart, p->stream));
+        CK(cudaStreamWaitEvent(p->stream2, p->evStart, 0));
+        const void* srcs[4] = {mI, mJ, I, J};
+        void* dsts[4] = {p->stA, p->stB, p->stC, p->stD};
+        for (int k = 0; k < 4; ++k) {
+            CK(cudaMemcpyAsync(dsts[k], srcs[k], bytes, cudaMemcpyHostToDevice, p->stream2));
+            CK(cudaEventRecord(p->evCopy[k], p->stream2));
+        }
+        p->pendI = p->evCopy[0]; p->pendJ = p->evCopy[1];
+        rc = f32 ? fit_device<float2>(p, p->stA, p->stB, dtype) : fit_device<double2>(p, p->stA, p->stB, dtype);
+        if (rc) return rc;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            if (attempt == 0) { p->pendI = p->evCopy[2]; p->pendJ = p->evCopy[3]; }
+            rc = f32 ? apply_device<float2>(p, p->stC, p->stD, dtype, p->sol, p->stA, diff_dtype)
+                     : apply_device<double2>(p, p->stC, p->stD, dtype, p->sol, p->stA, diff_dtype);
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(p->stream));
+            if (attempt == 1) break;
+            rc = check_solver(p);
+            if (rc < 0) return rc;
+            if (rc == 0) break;
+        }
+        if ((rc = collect_timings(p, true, true))) return rc;
+        if (diff_memkind == SFFTB_MEM_HOST) {
+            const size_t ob = (size_t)p->d.N0 * p->d.N1 * (diff_dtype == SFFTB_F64 ? 8 : 4);
+            CK(cudaMemcpyAsync(diff, p->stA, ob, cudaMemcpyDeviceToHost, p->stream));
+        } else {
+            const size_t ob = (size_t)p->d.N0 * p->d.N1 * (diff_dtype == SFFTB_F64 ? 8 : 4);
+            CK(cudaMemcpyAsync(diff, p->stA, ob, cudaMemcpyDeviceToDevice, p->stream));
+        }
+        if ((rc = copy_out(p, solution, sol_memkind, p->sol, sizeof(double) * p->d.NEQ))) return rc;
+        CK(cudaStreamSynchronize(p->stream));
+        return 0;
+    }
     if ((rc = stage_in(p, mI, memkind, dtype, p->stA, &dI))) return rc;
     if ((rc = stage_in(p, mJ, memkind, dtype, p->stB, &dJ))) return rc;
     const bool ov = p->overlap && memkind == SFFTB_MEM_DEVICE && I && J && p->row_v8 && p->chol_coop && p->nsm >= 8;
