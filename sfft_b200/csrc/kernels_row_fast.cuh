@@ -86,6 +86,7 @@ struct RowInvFastArgs {
     RowFastArgs r;
     double scale;
     int Fpq;
+    int row0;                       // first row of this launch (chunked launches overlap the D2H copy of finished rows)
     unsigned char p_of[16], q_of[16];
 };
 
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(ROWF_NT) row_inv_fast_kernel(RowInvFastArgs ia
     const RowFastArgs& a = ia.r;
     const int tid = threadIdx.x;
     const int grp = tid / T, lane = tid - grp * T;
-    const int r0 = blockIdx.x * RB;
+    const int r0 = ia.row0 + blockIdx.x * RB;
     const int r = r0 + grp;
     cd* scratch = buf + (size_t)grp * PITCH;
     const GroupSync gs = row_group_sync<H>(grp, lane);

@@ -981,7 +981,7 @@ static int check_solver(sfftb_plan* p) {
 
 template <typename TSt>
 static int apply_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, const double* dsol, void* ddiff, int diff_dtype,
-                        const void* tI = nullptr, bool rows_done = false) {
+                        const void* tI = nullptr, bool rows_done = false, void* hdiff = nullptr) {
     const sfftb_dims& d = p->d;
     EVREC(p, EV_A0);
     const TSt* gIsrc = tI ? (const TSt*)tI : (const TSt*)p->gI;
@@ -1014,15 +1014,39 @@ static int apply_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype
     const size_t osz2 = diff_dtype == SFFTB_F64 ? 16 : 8;
     if (p->row_fast && ((uintptr_t)ddiff % osz2) == 0) {
         const int H = p->row_fast, RB = ROWF_NT / (H / 16);
-        const int grid = (d.N0 + RB - 1) / RB;
         const size_t sm = sizeof(cd) * (size_t)RB * (H + H / 16);
+        // hdiff != NULL (host GSS): the rows are produced in chunks and every finished chunk is copied to the host on
+        // the side stream while the next one is computed
+        const int nchunk = (hdiff && d.N0 >= 8 * RB) ? 4 : 1;
+        const int rows_per = ((d.N0 + nchunk - 1) / nchunk + RB - 1) / RB * RB;
+        const size_t esz = diff_dtype == SFFTB_F64 ? 8 : 4;
+        for (int c = 0; c < nchunk; ++c) {
+            const int row0 = c * rows_per, nrow = std::min(rows_per, d.N0 - row0);
+            if (nrow <= 0) break;
+            const int grid = (nrow + RB - 1) / RB;
+            p->rinvf.row0 = row0;
 #define RUN_RINVF(HH)                                                                                                  \
-        if (H == HH) {                                                                                                 \
-            if (diff_dtype == SFFTB_F64) row_inv_fast_kernel<TSt, double, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rinvf, (const TSt*)p->gJ, bpq, (double*)ddiff); \
-            else row_inv_fast_kernel<TSt, float, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rinvf, (const TSt*)p->gJ, bpq, (float*)ddiff);                            \
-        }
-        RUN_RINVF(512) RUN_RINVF(1024) RUN_RINVF(2048) RUN_RINVF(4096) RUN_RINVF(8192)
+            if (H == HH) {                                                                                             \
+                if (diff_dtype == SFFTB_F64) row_inv_fast_kernel<TSt, double, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rinvf, (const TSt*)p->gJ, bpq, (double*)ddiff); \
+                else row_inv_fast_kernel<TSt, float, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rinvf, (const TSt*)p->gJ, bpq, (float*)ddiff);                            \
+            }
+            RUN_RINVF(512) RUN_RINVF(1024) RUN_RINVF(2048) RUN_RINVF(4096) RUN_RINVF(8192)
 #undef RUN_RINVF
+            if (c + 1 < nchunk || hdiff) CKL(p);
+            if (hdiff) {
+                CK(cudaEventRecord(p->evCopy[c & 3], p->stream));
+                CK(cudaStreamWaitEvent(p->stream2, p->evCopy[c & 3], 0));
+                CK(cudaMemcpyAsync((char*)hdiff + (size_t)row0 * d.N1 * esz, (const char*)ddiff + (size_t)row0 * d.N1 * esz,
+                                   (size_t)nrow * d.N1 * esz, cudaMemcpyDeviceToHost, p->stream2));
+            }
+        }
+        p->rinvf.row0 = 0;
+        if (hdiff) {
+            CK(cudaEventRecord(p->evJoin, p->stream2));
+            CK(cudaStreamWaitEvent(p->stream, p->evJoin, 0));
+            EVREC(p, EV_AINV);
+            return 0;
+        }
     } else {
         const int grid = (d.N0 + p->row.RB - 1) / p->row.RB;
         if (diff_dtype == SFFTB_F64)
@@ -1134,8 +1158,9 @@ extern "C" int sfftb_gss(sfftb_plan* p, const void* I, const void* J, const void
         if (rc) return rc;
         for (int attempt = 0; attempt < 2; ++attempt) {
             if (attempt == 0) { p->pendI = p->evCopy[2]; p->pendJ = p->evCopy[3]; }
-            rc = f32 ? apply_device<float2>(p, p->stC, p->stD, dtype, p->sol, p->stA, diff_dtype)
-                     : apply_device<double2>(p, p->stC, p->stD, dtype, p->sol, p->stA, diff_dtype);
+            void* hd = (diff_memkind == SFFTB_MEM_HOST && p->row_fast) ? diff : nullptr;
+            rc = f32 ? apply_device<float2>(p, p->stC, p->stD, dtype, p->sol, p->stA, diff_dtype, nullptr, false, hd)
+                     : apply_device<double2>(p, p->stC, p->stD, dtype, p->sol, p->stA, diff_dtype, nullptr, false, hd);
             if (rc) return rc;
             CK(cudaStreamSynchronize(p->stream));
             if (attempt == 1) break;
@@ -1145,8 +1170,10 @@ extern "C" int sfftb_gss(sfftb_plan* p, const void* I, const void* J, const void
         }
         if ((rc = collect_timings(p, true, true))) return rc;
         if (diff_memkind == SFFTB_MEM_HOST) {
-            const size_t ob = (size_t)p->d.N0 * p->d.N1 * (diff_dtype == SFFTB_F64 ? 8 : 4);
-            CK(cudaMemcpyAsync(diff, p->stA, ob, cudaMemcpyDeviceToHost, p->stream));
+            if (!p->row_fast) {
+                const size_t ob = (size_t)p->d.N0 * p->d.N1 * (diff_dtype == SFFTB_F64 ? 8 : 4);
+                CK(cudaMemcpyAsync(diff, p->stA, ob, cudaMemcpyDeviceToHost, p->stream));
+            }
         } else {
             const size_t ob = (size_t)p->d.N0 * p->d.N1 * (diff_dtype == SFFTB_F64 ? 8 : 4);
             CK(cudaMemcpyAsync(diff, p->stA, ob, cudaMemcpyDeviceToDevice, p->stream));
