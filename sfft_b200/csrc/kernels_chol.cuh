@@ -94,9 +94,11 @@ __device__ __forceinline__ void cc_load_tile(double* S, const double* __restrict
 __device__ __forceinline__ double cc_fast_rcp(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    y = fma(fma(-x, y, 1.0), y, y);
-    y = fma(fma(-x, y, 1.0), y, y);
-    return y;
+    // seed error e ~ 2^-23; 1/x = y (1 + e)(1 + e^2) to fp64 accuracy with a three-deep dependent chain
+    const double e = fma(-x, y, 1.0);
+    const double e2 = e * e;
+    const double y1 = fma(y, e, y);
+    return fma(y1, e2, y1);
 }
 
 // Factor the diagonal block k (already updated): LDL^T-style elimination, register resident, compact code (the
@@ -226,9 +228,8 @@ __device__ void cc_potrf_inv(const CholArgs& a, int k, double* D, double* Wf, do
             for (int j = 0; j < 8; ++j) { av[j] = (j <= r) ? D[(d0 + r) * CC_PITCH + d0 + j] : 0.0; ev[j] = (j == r) ? 1.0 : 0.0; }
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                double piv = __shfl_sync(0xffffffffu, av[c], c, 8);
-                const bool bad = !(piv > 0.0) || !isfinite(piv);
-                if (bad) { if (lane == 0 && d0 + c < kb) atomicCAS(&a.info[0], 0, k0 + d0 + c + 1); piv = 1.0; }
+                // (the pivot check is off the dependent chain: a bad pivot only raises the flag, see below)
+                const double piv = __shfl_sync(0xffffffffu, av[c], c, 8);
                 pv[c] = piv;
                 const double m = (r > c) ? -av[c] * cc_fast_rcp(piv) : 0.0;
 #pragma unroll
@@ -238,7 +239,11 @@ __device__ void cc_potrf_inv(const CholArgs& a, int k, double* D, double* Wf, do
             }
             double rs[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) rs[c] = rsqrt(pv[c]);
+            for (int c = 0; c < 8; ++c) {
+                const bool bad = !(pv[c] > 0.0) || !isfinite(pv[c]);
+                if (bad) { if (lane == 0 && d0 + c < kb) atomicCAS(&a.info[0], 0, k0 + d0 + c + 1); pv[c] = 1.0; }
+                rs[c] = rsqrt(pv[c]);
+            }
             double rr = rs[0];
 #pragma unroll
             for (int c = 1; c < 8; ++c) rr = (r == c) ? rs[c] : rr;

@@ -941,14 +941,15 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, 
             CK(cudaStreamWaitEvent(p->stream2, p->evFork, 0));
             cudaStream_t main = p->stream;
             p->stream = p->stream2;
-            p->row_grid_limit = p->nsm / 2;
+            const int rowsm = std::max(1, std::min(p->nsm - 1, p->nsm * env_int("SFFTB_OVERLAP_ROWS_PCT", 50) / 100));
+            p->row_grid_limit = rowsm;
             int rc2 = launch_row_fwd<TSt>(p, ovI, dtype, (TSt*)p->gI, d.DK + 1);
             if (!rc2) rc2 = launch_row_fwd<TSt>(p, ovJ, dtype, (TSt*)p->gJ, 1);
             p->row_grid_limit = 0;
             p->stream = main;
             if (rc2) return SFFTB_ECUDA;
             CK(cudaEventRecord(p->evJoin, p->stream2));
-            p->chol_grid_limit = p->nsm - p->nsm / 2;
+            p->chol_grid_limit = p->nsm - rowsm;
         }
         const int rcc = run_cholesky(p);
         p->chol_grid_limit = 0;
