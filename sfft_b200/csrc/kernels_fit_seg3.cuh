@@ -314,18 +314,28 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
                 const TSt* src = stage + ((size_t)(gs & (NSTG - 1)) * NSRC + my_src) * FS3_M;
                 cd* plane = spec + ((size_t)slot * NP + p) * FS3_PITCH;
                 cd v[8];
+                // cx of window position n = lane + 32 q: one int->double conversion per job, the rest by FMA; rows that
+                // wrapped around the column ends (first / last segments only) are shifted by one period
+                const int row_l = c0 - h + lane;
+                const double cx_l = (double)(row_l + 1) * inv0;
+                const bool simple = (a.N0 >= 2 * FS3_M);          // at most one wrap per window
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const int n = lane + 32 * q;
-                    cd gg = cmake(0.0, 0.0);
-                    if (!roleA || (n >= h && n < h + Sc)) {
-                        gg = load_c(src + n);
-                        if (my_i > 0) {
-                            const double cx = (wrap_row(c0 - h + n, a.N0) + 1) * inv0;
-                            gg = cscale(gg, my_i == 1 ? cx : (my_i == 2 ? cx * cx : cx * cx * cx));
+                    cd gg = load_c(src + n);
+                    if (my_i > 0) {
+                        double cx;
+                        if (simple) {
+                            const int row = row_l + 32 * q;
+                            cx = fma((double)(32 * q), inv0, cx_l);
+                            cx += (row < 0) ? 1.0 : ((row >= a.N0) ? -1.0 : 0.0);
+                        } else {
+                            cx = (wrap_row(row_l + 32 * q, a.N0) + 1) * inv0;
                         }
+                        gg = cscale(gg, my_i == 1 ? cx : (my_i == 2 ? cx * cx : cx * cx * cx));
                     }
-                    v[q] = gg;
+                    const bool keep = !roleA || (n >= h && n < h + Sc);
+                    v[q] = keep ? gg : cmake(0.0, 0.0);
                 }
                 vfft<FS3_M>(v, plane, lane, vt, -1.0, 0);
 #pragma unroll
