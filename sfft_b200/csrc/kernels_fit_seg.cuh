@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(FSG_NT, 1) fit_seg_kernel(SegFitArgs fa, const
 // (wt = 1 for k1 = 0 and the Nyquist column, 2 otherwise: Hermitian half spectrum).  Every row gets all 4 w1 + 1 lags;
 // lag_finish_kernel sums the chunks and scatters the lags each table needs.
 #define LR2_LB 9          // lags per pass: m = mb .. mb + LB - 1, both signs
+#define LR2_KC 512        // k1 columns per CTA (chunk); their twiddles for the lags of a pass are staged in shared memory
 struct LagReduce2Args {
     int N1, NH, nrows, w1, ksplit;
     const cd* tw1;
@@ -289,30 +290,36 @@ struct LagReduce2Args {
 __global__ void __launch_bounds__(256) lag_reduce2_kernel(LagReduce2Args a, const cd* __restrict__ kap, double* __restrict__ part)
 {
     __shared__ double red[16][16][2 * LR2_LB + 1];
+    extern __shared__ __align__(16) unsigned char lr2_smem[];
+    cd (*twc)[LR2_LB] = reinterpret_cast<cd (*)[LR2_LB]>(lr2_smem);   // twc[k - kbeg][t] = wt(k)/N1 exp(-2 pi i k (mb + t) / N1)
     const int tid = threadIdx.x;
     const int rl = tid & 15, kl = tid >> 4;
     const int row = blockIdx.x * 16 + rl;
     const int ks = blockIdx.y;
-    const int chunk = (a.NH + a.ksplit - 1) / a.ksplit;
-    const int kbeg = ks * chunk, kend = min(a.NH, kbeg + chunk);
+    const int kbeg = ks * LR2_KC, kend = min(a.NH, kbeg + LR2_KC);
     const double inv1 = 1.0 / (double)a.N1;
     const int nl = 4 * a.w1 + 1;
     for (int mb = 0; mb <= 2 * a.w1; mb += LR2_LB) {
+        for (int idx = tid; idx < (kend - kbeg) * LR2_LB; idx += 256) {
+            const int kk = idx / LR2_LB, t = idx - kk * LR2_LB;
+            const int k = kbeg + kk;
+            const double wt = (k == 0 || 2 * k == a.N1) ? inv1 : 2.0 * inv1;
+            const int e = (int)(((long long)k * (mb + t)) % a.N1);
+            twc[kk][t] = cscale(a.tw1[e], wt);
+        }
+        __syncthreads();
         double accP[LR2_LB], accN[LR2_LB];
 #pragma unroll
         for (int t = 0; t < LR2_LB; ++t) { accP[t] = 0.0; accN[t] = 0.0; }
         if (row < a.nrows) {
             for (int k = kbeg + kl; k < kend; k += 16) {
-                const double wt = (k == 0 || 2 * k == a.N1) ? inv1 : 2.0 * inv1;
-                const cd v = cscale(kap[(size_t)k * a.nrows + row], wt);
-                int e = (int)(((long long)k * mb) % a.N1);
+                const cd v = kap[(size_t)k * a.nrows + row];
 #pragma unroll
                 for (int t = 0; t < LR2_LB; ++t) {
-                    const cd w = a.tw1[e];                    // (cos, -sin) of 2 pi k m / N1
+                    const cd w = twc[k - kbeg][t];            // (cos, -sin) of 2 pi k m / N1, weighted
                     const double t1 = v.x * w.x, t2 = v.y * w.y;
                     accP[t] += t1 + t2;                       // Re(v e^{+i th m}) = vr cos - vi sin = vr w.x + vi w.y
                     accN[t] += t1 - t2;                       // Re(v e^{-i th m})
-                    e += k; if (e >= a.N1) e -= a.N1;
                 }
             }
         }

@@ -616,7 +616,9 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         LagReduce2Args& r2 = p->red2;
         r2.N1 = N1; r2.NH = NH; r2.nrows = sf.nrows; r2.w1 = d.w1; r2.tw1 = p->tw1;
         const int rowblocks = (sf.nrows + 15) / 16;
-        r2.ksplit = std::max(1, std::min(16, (2 * p->nsm + rowblocks - 1) / rowblocks));
+        r2.ksplit = (NH + LR2_KC - 1) / LR2_KC;
+        if (set_smem(lag_reduce2_kernel, sizeof(cd) * LR2_KC * LR2_LB)) return SFFTB_ECUDA;
+        (void)rowblocks;
         CK(cudaMalloc(&p->part, sizeof(double) * (size_t)r2.ksplit * sf.nrows * nl1));
         LagFinishArgs& f2 = p->fin2;
         f2.nrows = sf.nrows; f2.nOm = sf.nOm; f2.nK = sf.nK; f2.nLT = sf.nLT; f2.w1 = d.w1; f2.ksplit = r2.ksplit;
@@ -909,7 +911,7 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, 
     EVREC(p, EV_COL);
     if (p->fit_seg) {
         dim3 grd((p->sfit.nrows + 15) / 16, p->red2.ksplit);
-        lag_reduce2_kernel<<<grd, 256, 0, p->stream>>>(p->red2, p->kap2, p->part);
+        lag_reduce2_kernel<<<grd, 256, sizeof(cd) * LR2_KC * LR2_LB, p->stream>>>(p->red2, p->kap2, p->part);
         CKL(p);
         const int tot = p->sfit.nrows * (4 * d.w1 + 1);
         lag_finish_kernel<<<(tot + 255) / 256, 256, 0, p->stream>>>(p->fin2, p->part);
