@@ -667,3 +667,119 @@ __global__ void __launch_bounds__(CC_NT, CC_CTAS_PER_SM) chol_coop_kernel(CholAr
         cc_grid_barrier(a.bar, target, G);
     }
 }
+
+// ---- triangular substitutions with a stored factor, dataflow style -------------------------------------------------
+// Used when the Cholesky factor of LHMAT is already resident (shared-template batches: LHMAT depends on the masked
+// template only).  One CTA per 64-row block (block-cyclic if there are more blocks than CTAs); a block waits for the
+// blocks it depends on through epoch-tagged flags in global memory instead of grid-wide barriers, and streams the
+// 64 x 64 blocks of L it needs through a cp.async double buffer so that they are already in shared memory when the
+// vector they multiply arrives.  Forward: y_j = W_j (b_j - sum_{k<j} L_jk y_k); backward: x_j = W_j^T (y_j - sum_{k>j}
+// L_kj^T x_k).  Launch cooperatively (all CTAs must be co-resident: they spin on each other's flags).
+struct SubstArgs {
+    const double* A; int ld, n;          // factor L in the lower triangle (row-major, leading dimension ld)
+    const double* W;                     // inverse diagonal blocks
+    double* yv;                          // in: scaled right-hand side b;  work: y (forward result)
+    double* xs;                          // out: solution of the scaled system
+    unsigned* flags;                     // 2 * nblk epoch tags (forward | backward)
+    unsigned epoch;
+    const double* sc; const int* idx; double* sol; int NEQ;
+};
+
+__device__ __forceinline__ void cs_wait_flag(const unsigned* f, unsigned epoch) {
+    if (threadIdx.x == 0) {
+        int spins = 0;
+        while (cc_ld_acquire(f) != epoch) { if (++spins > (1 << 26)) __trap(); }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void cs_set_flag(unsigned* f, unsigned epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory"); }
+}
+// stream block (rb, cb) of L (64 x 64, zero outside the matrix) into S (pitch CC_DP)
+__device__ __forceinline__ void cs_issue_block(const SubstArgs& a, int rb, int cb, double* S) {
+    for (int idx = threadIdx.x; idx < CC_NB * CC_NB; idx += CC_NT) {
+        const int r = idx >> 6, c = idx & 63;
+        const int gr = rb * CC_NB + r, gc = cb * CC_NB + c;
+        const bool v = gr < a.n && gc < a.n;
+        const unsigned d = (unsigned)__cvta_generic_to_shared(S + r * CC_DP + c);
+        const int sz = v ? 8 : 0;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(a.A + (size_t)(v ? gr : 0) * a.ld + (v ? gc : 0)), "r"(sz) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(CC_NT, 1) chol_subst_kernel(SubstArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* Lb = reinterpret_cast<double*>(smem_raw);       // 2 x 64 x CC_DP
+    double* Wb = Lb + 2 * CC_NB * CC_DP;                    // 64 x CC_DP
+    double* sv = Wb + CC_NB * CC_DP;                        // 64: running right-hand side of the block
+    double* vk = sv + 64;                                   // 64: the vector that just arrived
+    double* red = vk + 64;                                  // 256 partial sums
+    const int tid = threadIdx.x, G = gridDim.x, bid = blockIdx.x;
+    const int nblk = (a.n + CC_NB - 1) / CC_NB;
+    const int r = tid >> 2, part = tid & 3;                 // 4 threads per row / column, 16 entries each
+    unsigned* fF = a.flags;
+    unsigned* fB = a.flags + nblk;
+    if (bid == 0) for (int c = tid; c < a.NEQ; c += CC_NT) a.sol[c] = 0.0;
+
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool fwd = pass == 0;
+        // owned blocks in dependency order: increasing for the forward pass, decreasing for the backward pass
+        for (int jj = 0; jj < nblk; ++jj) {
+            const int j = fwd ? jj : nblk - 1 - jj;
+            if (j % G != bid) continue;
+            const int j0 = j * CC_NB, jb = min(CC_NB, a.n - j0);
+            const int ndep = fwd ? j : nblk - 1 - j;        // number of blocks this one waits for
+            // diagonal inverse and the first dependency block stream in while the right-hand side is fetched
+            for (int idx = tid; idx < CC_NB * CC_NB; idx += CC_NT) Wb[(idx >> 6) * CC_DP + (idx & 63)] = a.W[(size_t)j * CC_NB * CC_NB + idx];
+            if (ndep > 0) { const int k = fwd ? 0 : nblk - 1; if (fwd) cs_issue_block(a, j, k, Lb); else cs_issue_block(a, k, j, Lb); }
+            if (!fwd) cs_wait_flag(fF + j, a.epoch);        // y_j of the forward pass (possibly from another CTA)
+            if (tid < CC_NB) sv[tid] = (tid < jb) ? a.yv[j0 + tid] : 0.0;
+            __syncthreads();
+            for (int d = 0; d < ndep; ++d) {
+                const int k = fwd ? d : nblk - 1 - d;
+                double* Lc = Lb + (d & 1) * CC_NB * CC_DP;
+                if (d + 1 < ndep) {
+                    const int kn = fwd ? d + 1 : nblk - 2 - d;
+                    if (fwd) cs_issue_block(a, j, kn, Lb + ((d + 1) & 1) * CC_NB * CC_DP); else cs_issue_block(a, kn, j, Lb + ((d + 1) & 1) * CC_NB * CC_DP);
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                } else {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                }
+                cs_wait_flag((fwd ? fF : fB) + k, a.epoch);
+                if (tid < CC_NB) { const int gk = k * CC_NB + tid; vk[tid] = (gk < a.n) ? (fwd ? a.yv[gk] : a.xs[gk]) : 0.0; }
+                __syncthreads();
+                // forward: s[r] -= sum_c L_jk[r][c] y_k[c];  backward: s[c] -= sum_r L_kj[r][c] x_k[r]
+                double acc = 0.0;
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const int q = part * 16 + m;
+                    acc = fma(fwd ? Lc[r * CC_DP + q] : Lc[q * CC_DP + r], vk[q], acc);
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                __syncthreads();
+                if (part == 0) sv[r] -= acc;
+                __syncthreads();
+            }
+            // y_j = W_j s (forward) / x_j = W_j^T s (backward)
+            {
+                double acc = 0.0;
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const int q = part * 16 + m;
+                    acc = fma(fwd ? Wb[r * CC_DP + q] : Wb[q * CC_DP + r], sv[q], acc);
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                if (part == 0 && r < jb) {
+                    if (fwd) a.yv[j0 + r] = acc;
+                    else { a.xs[j0 + r] = acc; a.sol[a.idx[j0 + r]] = acc * a.sc[j0 + r]; }
+                }
+            }
+            cs_set_flag((fwd ? fF : fB) + j, a.epoch);
+        }
+    }
+}

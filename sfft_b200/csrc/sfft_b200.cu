@@ -86,6 +86,9 @@ struct sfftb_plan {
     double *Aug, *sc, *diagU, *sol;
     double *cholW, *cholY, *cholX;   // cooperative Cholesky: inverse diagonal blocks, back-substitution vectors
     unsigned* cholBar;
+    unsigned* substFlags;        // 2 * nblk epoch tags of the dataflow substitution kernel
+    unsigned substEpoch;
+    int subst_ok;
     int chol_coop;
     double* exportbuf;
     int ld, nsolve;
@@ -275,7 +278,7 @@ static int plan_free(sfftb_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     void* ptrs[] = {p->vt8_8, p->vt64_8, p->vt64_4, p->vt256_4, p->vt512_4, p->tabA, p->tabB_row, p->tabC_row, p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
-                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->firTaps, p->firCA, p->tstate, p->stC, p->stD};
+                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->firTaps, p->firCA, p->tstate, p->stC, p->stD};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->info_h) cudaFreeHost(p->info_h);
     for (int k = 0; k < EV_COUNT; ++k) if (p->ev[k]) cudaEventDestroy(p->ev[k]);
@@ -430,6 +433,15 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         int occ = 0, coop = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_coop_kernel, CC_NT, csm));
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
+        {
+            CK(cudaMalloc(&p->substFlags, sizeof(unsigned) * 2 * (size_t)nblk));
+            CK(cudaMemset(p->substFlags, 0, sizeof(unsigned) * 2 * (size_t)nblk));
+            const size_t ssm = sizeof(double) * (3 * CC_NB * CC_DP + 64 + 64 + 256);
+            CK(cudaFuncSetAttribute(chol_subst_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+            int occs = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occs, chol_subst_kernel, CC_NT, ssm));
+            p->subst_ok = (occs >= 1 && coop && !env_int("SFFTB_RESOLVE_V1", 0)) ? 1 : 0;
+        }
         p->chol_coop = (occ >= 1 && coop && !env_int("SFFTB_CHOL_LEGACY", 0)) ? std::min(occ, std::max(1, env_int("SFFTB_CHOL_CTAS", CC_CTAS_PER_SM))) : 0;
     }
     CK(cudaMalloc(&p->info, sizeof(int) * 4));
@@ -793,6 +805,18 @@ static int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, i
 
 static int run_cholesky(sfftb_plan* p, int resolve = 0) {
     const int n = p->nsolve, ntot = n + 1;
+    if (p->chol_coop && resolve && p->subst_ok) {
+        SubstArgs sa;
+        sa.A = p->Aug; sa.ld = p->ld; sa.n = n; sa.W = p->cholW; sa.yv = p->cholY; sa.xs = p->cholX;
+        sa.flags = p->substFlags; sa.epoch = ++p->substEpoch;
+        sa.sc = p->sc; sa.idx = p->idxmap; sa.sol = p->sol; sa.NEQ = p->d.NEQ;
+        const int nblk = (n + CC_NB - 1) / CC_NB;
+        void* args[] = {&sa};
+        CK(cudaLaunchCooperativeKernel((void*)chol_subst_kernel, dim3(std::min(nblk, p->nsm)), dim3(CC_NT), args,
+                                       sizeof(double) * (3 * CC_NB * CC_DP + 64 + 64 + 256), p->stream));
+        p->launches++;
+        return 0;
+    }
     if (p->chol_coop) {
         CholArgs ca;
         ca.resolve = resolve;
