@@ -114,6 +114,14 @@ int  sfftb_template_mark_ready(sfftb_plan* plan);
 int  sfftb_gss_template(sfftb_plan* plan, const void* PixA_J, const void* PixA_mJ, int img_memkind, int img_dtype,
                         double* solution, int sol_memkind, void* diff, int diff_memkind, int diff_dtype);
 
+/* Consumers of the Solution that every Easy*Packet calls right after GSS (sfft/EasySparsePacket.py:417-436):
+ * Realize_MatchingKernel(XY_q).FromArray and Realize_FluxScaling(XY_q).FromArray
+ * (sfft/utils/SFFTSolutionReader.py:116-196).  `xy` holds nq (x, y) pairs in FortranCoor (pixel centre (r, c) ->
+ * (r + 1, c + 1)); `kerstack` receives (nq, L0, L1) kernels in the Cartesian-delta basis, `fscal` the nq flux
+ * scalings; either output may be NULL.  With device pointers throughout nothing is copied and nothing synchronises. */
+int  sfftb_realize(sfftb_plan* plan, const double* solution, int sol_memkind, const double* xy, int xy_memkind, int nq,
+                   double* kerstack, double* fscal, int out_memkind);
+
 /* Parity hook: the full (NEQ x NEQ) LHMAT and (NEQ) RHb of the last fit, before stripe removal,
  * in the reference's layout (what FillLS_* produce, SFFTSubtract.py:244-380).  Host pointers. */
 int  sfftb_export_normal_eq(sfftb_plan* plan, double* LHMAT, double* RHb);

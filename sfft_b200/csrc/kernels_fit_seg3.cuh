@@ -53,12 +53,12 @@ __device__ __forceinline__ void fs3_barP() { asm volatile("bar.sync 1, 256;" :::
 // column_poly_rows for an explicit thread subset
 template <typename TSt>
 __device__ void column_poly_rows_sub(const SegFitArgs& fa, const TSt* __restrict__ gI, int k1, const cd* mom, cd* __restrict__ kaprow,
-                                     int tid, int nthr)
+                                     int tid, int nthr, bool jonly = false)
 {
     const ColArgs& a = fa.c;
     const double inv0 = 1.0 / (double)a.N0;
     const int np = a.DB + 1;
-    for (int idx = tid; idx < a.Fij * np * a.nlj0; idx += nthr) {
+    for (int idx = tid; idx < (jonly ? 0 : a.Fij * np * a.nlj0); idx += nthr) {
         const int ia = idx % a.nlj0;
         const int p = (idx / a.nlj0) % np;
         const int A = idx / (a.nlj0 * np);
@@ -117,14 +117,19 @@ __device__ __forceinline__ void fs3_inverse_job(const SegFitArgs& fa, const VTab
     }
 }
 
-template <typename TSt, int DK>
+// JONLY (shared-template tiles after the first): the template is unchanged, so only the cross spectra with J and the
+// moments of J are recomputed -- Fij "A role" transforms + one of J per segment, Fij accumulators; the rows of the other
+// pairs and of the I x T terms stay in `kap` from the first tile of the batch.
+template <typename TSt, int DK, bool JONLY = false>
 __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTabs vt_g, const TSt* __restrict__ gI, const TSt* __restrict__ gJ,
                                                              cd* __restrict__ kap)
 {
     constexpr int Fij = (DK + 1) * (DK + 2) / 2;
     constexpr int NPAIR = Fij * (Fij + 1) / 2;
-    constexpr int NACC = NPAIR + Fij;
-    constexpr int NP = 2 * Fij + 1;
+    constexpr int NACC = JONLY ? Fij : NPAIR + Fij;     // accumulators kept per product thread
+    constexpr int JOB0 = JONLY ? NPAIR : 0;               // lag-row job id of accumulator 0
+    constexpr int NP = JONLY ? Fij + 1 : 2 * Fij + 1;
+    constexpr int PJ = NP - 1;                            // ring plane of the spectrum of J
     constexpr int NSRC = DK + 2;
     constexpr int NPL = 2 * NP;                       // planes in the ring (two slots)
     constexpr int NSTG = Fs3Ring<TSt>::depth, LOG2STG = NSTG == 8 ? 3 : 2, PFD = NSTG - 2;
@@ -195,26 +200,29 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
 #endif
                 {
                     const cd* sp = spec + (size_t)slot * NP * FS3_PITCH + VPAD(tid);
-                    cd fA[Fij], fB[Fij];
+                    cd fA[Fij];
 #pragma unroll
-                    for (int A = 0; A < Fij; ++A) {
-                        fA[A] = sp[A * FS3_PITCH];
-                        fB[A] = sp[(Fij + A) * FS3_PITCH];
+                    for (int A = 0; A < Fij; ++A) fA[A] = sp[A * FS3_PITCH];
+                    const cd fJ = sp[PJ * FS3_PITCH];
+                    if constexpr (!JONLY) {
+                        cd fB[Fij];
+#pragma unroll
+                        for (int A = 0; A < Fij; ++A) fB[A] = sp[(Fij + A) * FS3_PITCH];
+                        int q = 0;
+#pragma unroll
+                        for (int A = 0; A < Fij; ++A)
+#pragma unroll
+                            for (int B = A; B < Fij; ++B) {
+                                acc[q].x = fma(fA[A].x, fB[B].x, acc[q].x); acc[q].x = fma(fA[A].y, fB[B].y, acc[q].x);
+                                acc[q].y = fma(fA[A].x, fB[B].y, acc[q].y); acc[q].y = fma(-fA[A].y, fB[B].x, acc[q].y);
+                                ++q;
+                            }
                     }
-                    const cd fJ = sp[2 * Fij * FS3_PITCH];
-                    int q = 0;
-#pragma unroll
-                    for (int A = 0; A < Fij; ++A)
-#pragma unroll
-                        for (int B = A; B < Fij; ++B) {
-                            acc[q].x = fma(fA[A].x, fB[B].x, acc[q].x); acc[q].x = fma(fA[A].y, fB[B].y, acc[q].x);
-                            acc[q].y = fma(fA[A].x, fB[B].y, acc[q].y); acc[q].y = fma(-fA[A].y, fB[B].x, acc[q].y);
-                            ++q;
-                        }
+                    constexpr int QJ = NACC - Fij;
 #pragma unroll
                     for (int A = 0; A < Fij; ++A) {
-                        acc[NPAIR + A].x = fma(fA[A].x, fJ.x, acc[NPAIR + A].x); acc[NPAIR + A].x = fma(fA[A].y, fJ.y, acc[NPAIR + A].x);
-                        acc[NPAIR + A].y = fma(fA[A].x, fJ.y, acc[NPAIR + A].y); acc[NPAIR + A].y = fma(-fA[A].y, fJ.x, acc[NPAIR + A].y);
+                        acc[QJ + A].x = fma(fA[A].x, fJ.x, acc[QJ + A].x); acc[QJ + A].x = fma(fA[A].y, fJ.y, acc[QJ + A].x);
+                        acc[QJ + A].y = fma(fA[A].x, fJ.y, acc[QJ + A].y); acc[QJ + A].y = fma(-fA[A].y, fJ.x, acc[QJ + A].y);
                     }
                 }
 #ifdef FS3_DEBUG
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
                 // a thread are loaded once, updated in registers and stored back (no read-modify-write chains)
                 {
                     const int jj = tid >> 6, mt = tid & 63;
-                    if (jj < NSRC) {
+                    if (jj < NSRC && (!JONLY || jj == DK + 1)) {
                         fs3_mbar_wait(landed + (gs & (NSTG - 1)), (gs >> LOG2STG) & 1);
                         const TSt* st = stage + ((size_t)(gs & (NSTG - 1)) * NSRC + jj) * FS3_M;
                         const int c0 = s * S, Sc = min(S, a.N0 - c0);
@@ -270,7 +278,7 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
                 mom[tid] = sm;
             }
             fs3_barP();
-            column_poly_rows_sub(fa, gI, k1, mom, kaprow, tid, 256);
+            column_poly_rows_sub(fa, gI, k1, mom, kaprow, tid, 256, JONLY);
             fs3_bar0();                                    // (A) all transforms and products of the column are done
 #pragma unroll
             for (int b0 = 0; b0 < NACC; b0 += 16) {
@@ -279,7 +287,7 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
                     if (b0 + q < NACC) spec[q * FS3_PITCH + VPAD(tid)] = acc[b0 + q];
                 fs3_bar0();
                 const int job = b0 + warp;
-                if (job < NACC) fs3_inverse_job<NPAIR>(fa, vt, spec + warp * FS3_PITCH, job, lane, kaprow);
+                if (job < NACC) fs3_inverse_job<NPAIR>(fa, vt, spec + warp * FS3_PITCH, JOB0 + job, lane, kaprow);
                 fs3_bar0();
             }
         }
@@ -295,7 +303,7 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
             for (int id = fw; id < nseg * NP; id += 8) {
                 const int s = id / NP, p = id - s * NP;
                 const int gs = g + s, slot = gs & 1;
-                const bool roleA = p < Fij, isJ = p == 2 * Fij;
+                const bool roleA = p < Fij, isJ = p == PJ;
                 const int pl = roleA ? p : (isJ ? 0 : p - Fij);
                 const int my_i = isJ ? 0 : a.pl_i[pl];
                 const int my_src = isJ ? DK + 1 : a.pl_j[pl];
@@ -355,7 +363,7 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
             for (int b0 = 0; b0 < NACC; b0 += 16) {
                 fs3_bar0();
                 const int job = b0 + warp;
-                if (job < NACC) fs3_inverse_job<NPAIR>(fa, vt, spec + warp * FS3_PITCH, job, lane, kaprow);
+                if (job < NACC) fs3_inverse_job<NPAIR>(fa, vt, spec + warp * FS3_PITCH, JOB0 + job, lane, kaprow);
                 fs3_bar0();
             }
         }

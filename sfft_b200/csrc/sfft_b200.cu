@@ -12,6 +12,7 @@
 #include "kernels_fit_fast.cuh"
 #include "kernels_fit_seg.cuh"
 #include "kernels_fit_seg3.cuh"
+#include "kernels_reader.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -652,8 +653,8 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
             if (p->smem_sfit3 <= p->max_smem && !env_int("SFFTB_SEG_V2", 0)) {
 #define SET_SFIT3(DKK)                                                                                            \
                 if (d.DK == DKK) {                                                                                    \
-                    if (f32) { if (set_smem(fit_seg3_kernel<float2, DKK>, p->smem_sfit3)) return SFFTB_ECUDA; }       \
-                    else     { if (set_smem(fit_seg3_kernel<double2, DKK>, p->smem_sfit3)) return SFFTB_ECUDA; }      \
+                    if (f32) { if (set_smem(fit_seg3_kernel<float2, DKK>, p->smem_sfit3) || set_smem(fit_seg3_kernel<float2, DKK, true>, p->smem_sfit3)) return SFFTB_ECUDA; }       \
+                    else     { if (set_smem(fit_seg3_kernel<double2, DKK>, p->smem_sfit3) || set_smem(fit_seg3_kernel<double2, DKK, true>, p->smem_sfit3)) return SFFTB_ECUDA; }      \
                 }
                 SET_SFIT3(0) SET_SFIT3(1) SET_SFIT3(2)
 #undef SET_SFIT3
@@ -913,7 +914,14 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, 
     if (p->pendJ) { CK(cudaStreamWaitEvent(p->stream, p->pendJ, 0)); p->pendJ = nullptr; }
     if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
     EVREC(p, EV_ROWS);
-    if (p->fit_seg == 2) {
+    const bool jonly = tI && p->factor_cached && p->chol_coop && p->fit_seg == 2 && !env_int("SFFTB_TEMPLATE_FULLFIT", 0);
+    if (jonly) {
+        // tiles after the first of a shared-template batch: the rows of the template-only pairs are already in kap2
+        const int DK = d.DK;
+        if (DK == 0) fit_seg3_kernel<TSt, 0, true><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else if (DK == 1) fit_seg3_kernel<TSt, 1, true><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else fit_seg3_kernel<TSt, 2, true><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+    } else if (p->fit_seg == 2) {
         const int DK = d.DK;
         if (DK == 0) fit_seg3_kernel<TSt, 0><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
         else if (DK == 1) fit_seg3_kernel<TSt, 1><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
@@ -1320,6 +1328,47 @@ extern "C" int sfftb_gss_template(sfftb_plan* p, const void* J, const void* mJ, 
     }
     if ((rc = copy_out(p, solution, sol_memkind, p->sol, sizeof(double) * p->d.NEQ))) return rc;
     CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+// Realize_MatchingKernel / Realize_FluxScaling (sfft/utils/SFFTSolutionReader.py:116-196) on the device.
+extern "C" int sfftb_realize(sfftb_plan* p, const double* solution, int sol_memkind, const double* xy, int xy_memkind, int nq,
+                             double* kerstack, double* fscal, int out_memkind) {
+    if (!p || !solution || !xy) return fail(SFFTB_EINVAL, "null argument");
+    if (nq <= 0) return fail(SFFTB_EINVAL, "no coordinates requested");
+    if (!kerstack && !fscal) return 0;
+    CK(cudaSetDevice(p->device));
+    const int Fab = p->d.Fab;
+    double *dsol = nullptr, *dxy = nullptr, *dks = nullptr, *dfs = nullptr;
+    std::vector<void*> tmp;
+    auto cleanup = [&]() { for (void* q : tmp) cudaFree(q); };
+    auto dev_in = [&](const double* src, int kind, size_t n, double** out) -> int {
+        if (kind == SFFTB_MEM_DEVICE) { *out = const_cast<double*>(src); return 0; }
+        CK(cudaMalloc(out, sizeof(double) * n));
+        tmp.push_back(*out);
+        CK(cudaMemcpyAsync(*out, src, sizeof(double) * n, cudaMemcpyHostToDevice, p->stream));
+        return 0;
+    };
+    int rc;
+    if ((rc = dev_in(solution, sol_memkind, p->d.NEQ, &dsol)) || (rc = dev_in(xy, xy_memkind, 2 * (size_t)nq, &dxy))) { cleanup(); return rc; }
+    if (out_memkind == SFFTB_MEM_DEVICE) { dks = kerstack; dfs = fscal; }
+    else {
+        if (kerstack) { if (cudaMalloc(&dks, sizeof(double) * (size_t)nq * Fab) != cudaSuccess) { cleanup(); return fail(SFFTB_ECUDA, "cudaMalloc failed"); } tmp.push_back(dks); }
+        if (fscal) { if (cudaMalloc(&dfs, sizeof(double) * (size_t)nq) != cudaSuccess) { cleanup(); return fail(SFFTB_ECUDA, "cudaMalloc failed"); } tmp.push_back(dfs); }
+    }
+    ReaderArgs ra;
+    ra.sol = dsol; ra.xy = dxy; ra.nq = nq; ra.N0 = p->d.N0; ra.N1 = p->d.N1; ra.L0 = p->d.L0; ra.L1 = p->d.L1;
+    ra.DK = p->d.DK; ra.Fij = p->d.Fij; ra.Fab = Fab; ra.kerstack = dks; ra.fscal = dfs;
+    realize_kernel<<<nq, 256, 0, p->stream>>>(ra);
+    p->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && out_memkind == SFFTB_MEM_HOST) {
+        if (kerstack) e = cudaMemcpyAsync(kerstack, dks, sizeof(double) * (size_t)nq * Fab, cudaMemcpyDeviceToHost, p->stream);
+        if (e == cudaSuccess && fscal) e = cudaMemcpyAsync(fscal, dfs, sizeof(double) * (size_t)nq, cudaMemcpyDeviceToHost, p->stream);
+    }
+    if (e == cudaSuccess && !tmp.empty()) e = cudaStreamSynchronize(p->stream);
+    cleanup();
+    if (e != cudaSuccess) return fail(SFFTB_ECUDA, "sfftb_realize: %s", cudaGetErrorString(e));
     return 0;
 }
 
