@@ -1,4 +1,4 @@
-// kernels_fit_seg3.cuh -- segmented fit column pass, warp-specialised (KerPolyOrder <= 2).
+// kernels_fit_seg3.cuh -- segmented fit column pass, warp-specialised (KerPolyOrder <= 2 in one launch, 3 in three).
 //
 // Same mathematics, inputs and outputs as fit_seg_kernel (kernels_fit_seg.cuh).  The CTA has 16 warps:
 //   * warps 8..15 ("transform warps", 104 registers after setmaxnreg.dec): one 256-point forward FFT per warp at a
@@ -24,7 +24,12 @@ template <typename TSt> struct Fs3Ring { static const int depth = sizeof(TSt) ==
 #ifndef FS3_SLEEP_NS
 #define FS3_SLEEP_NS 200
 #endif
-#define FS3_NMT 64           // product threads that also accumulate the column moments
+#define FS3_NMT 64           // product threads per stored plane that also accumulate the column moments (DK <= 2)
+// KerPolyOrder = 3 has 5 stored planes and needs the shared memory for the window ring: 32 moment threads per plane
+template <int DK> struct Fs3Mom { static const int nmt = DK == 3 ? 32 : 64, npl = DK == 3 ? 5 : 4; };
+// the launches ("passes") that cover all plane pairs: planes [A0, A1) in the "A role" against all planes >= A0.
+// KerPolyOrder <= 2: one pass; 3 (Fij = 10, 65 accumulators): three passes of 21 / 24 / 20 accumulators
+#define FS3_DK3_PASSES {0, 2, 5, 10}
 
 __device__ __forceinline__ unsigned fs3_saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void fs3_mbar_init(unsigned long long* b, unsigned count) {
@@ -120,16 +125,32 @@ __device__ __forceinline__ void fs3_inverse_job(const SegFitArgs& fa, const VTab
 // JONLY (shared-template tiles after the first): the template is unchanged, so only the cross spectra with J and the
 // moments of J are recomputed -- Fij "A role" transforms + one of J per segment, Fij accumulators; the rows of the other
 // pairs and of the I x T terms stay in `kap` from the first tile of the batch.
-template <typename TSt, int DK, bool JONLY = false>
+// A0 / A1: this launch accumulates the pairs (A, B >= A) and (A, J) for the planes A in [A0, A1) (register budget of the
+// product threads); the launch with A0 == 0 also accumulates the column moments and writes the background rows.
+template <typename TSt, int DK, bool JONLY = false, int A0 = 0, int A1 = (DK + 1) * (DK + 2) / 2>
 __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTabs vt_g, const TSt* __restrict__ gI, const TSt* __restrict__ gJ,
                                                              cd* __restrict__ kap)
 {
     constexpr int Fij = (DK + 1) * (DK + 2) / 2;
     constexpr int NPAIR = Fij * (Fij + 1) / 2;
-    constexpr int NACC = JONLY ? Fij : NPAIR + Fij;     // accumulators kept per product thread
-    constexpr int JOB0 = JONLY ? NPAIR : 0;               // lag-row job id of accumulator 0
-    constexpr int NP = JONLY ? Fij + 1 : 2 * Fij + 1;
+    constexpr int NA = A1 - A0;                           // planes transformed in the A role (zero-padded segment)
+    constexpr int NB = JONLY ? 0 : Fij - A0;              // planes transformed in the B role (segment + halo)
+    constexpr int NPR = JONLY ? 0 : NA * (Fij - A0) - NA * (NA - 1) / 2;   // pairs (A, B >= A) of this launch
+    constexpr int NACC = NPR + NA;                        // accumulators kept per product thread
+    constexpr int QJ = NPR;                               // first (A, J) accumulator
+    constexpr int NP = NA + NB + 1;                       // spectra per segment: A roles | B roles | J
     constexpr int PJ = NP - 1;                            // ring plane of the spectrum of J
+    constexpr bool DO_MOM = A0 == 0;
+    constexpr int NMT = Fs3Mom<DK>::nmt, NMPL = Fs3Mom<DK>::npl, NMS = NMPL * SFFTB_MAXE;
+    static_assert(DK + 2 <= NMPL && NMPL * NMT <= 256, "moment threads");
+    // lag-row job of accumulator q: pairs are enumerated `for A for B >= A` over all planes, then the Fij (A, J) rows
+    auto job_of = [](int q) -> int {
+        if (q >= QJ) return NPAIR + A0 + (q - QJ);
+        int ai = 0;
+        while (q >= NB - ai) { q -= NB - ai; ++ai; }
+        const int A = A0 + ai;
+        return A * Fij - A * (A - 1) / 2 + q;
+    };
     constexpr int NSRC = DK + 2;
     constexpr int NPL = 2 * NP;                       // planes in the ring (two slots)
     constexpr int NSTG = Fs3Ring<TSt>::depth, LOG2STG = NSTG == 8 ? 3 : 2, PFD = NSTG - 2;
@@ -139,8 +160,8 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
     cd* spec = reinterpret_cast<cd*>(smem_raw);                                   // NPL (>= 16) planes
     constexpr int NPLA = NPL > 16 ? NPL : 16;
     cd* mom = spec + NPLA * FS3_PITCH;
-    cd* macc = mom + 4 * SFFTB_MAXE;
-    cd* tw8 = macc + FSG_MSLOTS * FS3_NMT;          // 56 entries  (Ns = 8,  R = 8)
+    cd* macc = mom + NMS;
+    cd* tw8 = macc + NMS * NMT;                     // 56 entries  (Ns = 8,  R = 8)
     cd* tw64 = tw8 + 56;                            // 192 entries (Ns = 64, R = 4)
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(tw64 + 192);
     TSt* stage = reinterpret_cast<TSt*>(bars + 12);
@@ -173,7 +194,7 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
 #pragma unroll
             for (int q = 0; q < NACC; ++q) acc[q] = cmake(0.0, 0.0);
             cd* kaprow = kap + (size_t)k1 * fa.nrows;
-            for (int e = 0; e < SFFTB_MAXE; ++e) macc[((tid >> 6) * SFFTB_MAXE + e) * FS3_NMT + (tid & 63)] = cmake(0.0, 0.0);
+            if (DO_MOM) for (int e = tid; e < NMS * NMT; e += 256) macc[e] = cmake(0.0, 0.0);
             // window prefetch: element tid of every stored plane, two segments ahead
             auto issue = [&](int s) {
                 const int buf = (g + s) & (NSTG - 1);
@@ -200,27 +221,26 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
 #endif
                 {
                     const cd* sp = spec + (size_t)slot * NP * FS3_PITCH + VPAD(tid);
-                    cd fA[Fij];
+                    cd fA[NA];
 #pragma unroll
-                    for (int A = 0; A < Fij; ++A) fA[A] = sp[A * FS3_PITCH];
+                    for (int A = 0; A < NA; ++A) fA[A] = sp[A * FS3_PITCH];
                     const cd fJ = sp[PJ * FS3_PITCH];
                     if constexpr (!JONLY) {
-                        cd fB[Fij];
+                        cd fB[NB];                    // fB[bi] is plane A0 + bi, fA[ai] plane A0 + ai: B >= A <=> bi >= ai
 #pragma unroll
-                        for (int A = 0; A < Fij; ++A) fB[A] = sp[(Fij + A) * FS3_PITCH];
+                        for (int B = 0; B < NB; ++B) fB[B] = sp[(NA + B) * FS3_PITCH];
                         int q = 0;
 #pragma unroll
-                        for (int A = 0; A < Fij; ++A)
+                        for (int A = 0; A < NA; ++A)
 #pragma unroll
-                            for (int B = A; B < Fij; ++B) {
+                            for (int B = A; B < NB; ++B) {
                                 acc[q].x = fma(fA[A].x, fB[B].x, acc[q].x); acc[q].x = fma(fA[A].y, fB[B].y, acc[q].x);
                                 acc[q].y = fma(fA[A].x, fB[B].y, acc[q].y); acc[q].y = fma(-fA[A].y, fB[B].x, acc[q].y);
                                 ++q;
                             }
                     }
-                    constexpr int QJ = NACC - Fij;
 #pragma unroll
-                    for (int A = 0; A < Fij; ++A) {
+                    for (int A = 0; A < NA; ++A) {
                         acc[QJ + A].x = fma(fA[A].x, fJ.x, acc[QJ + A].x); acc[QJ + A].x = fma(fA[A].y, fJ.y, acc[QJ + A].x);
                         acc[QJ + A].y = fma(fA[A].x, fJ.y, acc[QJ + A].y); acc[QJ + A].y = fma(-fA[A].y, fJ.x, acc[QJ + A].y);
                     }
@@ -230,33 +250,33 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
 #endif
                 // column moments of this segment's core rows: 64 threads per stored plane, <= 4 rows each; the slots of
                 // a thread are loaded once, updated in registers and stored back (no read-modify-write chains)
-                {
-                    const int jj = tid >> 6, mt = tid & 63;
+                if constexpr (DO_MOM) {
+                    const int jj = tid / NMT, mt = tid - jj * NMT;
                     if (jj < NSRC && (!JONLY || jj == DK + 1)) {
                         fs3_mbar_wait(landed + (gs & (NSTG - 1)), (gs >> LOG2STG) & 1);
                         const TSt* st = stage + ((size_t)(gs & (NSTG - 1)) * NSRC + jj) * FS3_M;
                         const int c0 = s * S, Sc = min(S, a.N0 - c0);
                         const int ne = (jj == DK + 1) ? a.DB + 1 : DK - jj + a.DB + 1;
-                        cd ma[6];
+                        cd ma[SFFTB_MAXE];
 #pragma unroll
-                        for (int e = 0; e < 6; ++e) ma[e] = (e < ne) ? macc[(jj * SFFTB_MAXE + e) * FS3_NMT + mt] : cmake(0.0, 0.0);
+                        for (int e = 0; e < SFFTB_MAXE; ++e) ma[e] = (e < ne) ? macc[(jj * SFFTB_MAXE + e) * NMT + mt] : cmake(0.0, 0.0);
 #pragma unroll
-                        for (int rr = 0; rr < FS3_M / FS3_NMT; ++rr) {
+                        for (int rr = 0; rr < FS3_M / NMT; ++rr) {
                             // rows are independent; powers of cx first so that only one FMA level depends on the load
-                            const int n = h + mt + rr * FS3_NMT;
+                            const int n = h + mt + rr * NMT;
                             const bool live = n < h + Sc;
                             const double cx = (c0 + (n - h) + 1) * inv0;
                             const double cx2 = cx * cx, cx3 = cx2 * cx, cx4 = cx2 * cx2, cx5 = cx4 * cx;
                             const cd gg = live ? load_c(st + (live ? n : 0)) : cmake(0.0, 0.0);
-                            const double pw[6] = {1.0, cx, cx2, cx3, cx4, cx5};
+                            const double pw[SFFTB_MAXE] = {1.0, cx, cx2, cx3, cx4, cx5, cx3 * cx3};
 #pragma unroll
-                            for (int e = 0; e < 6; ++e) {
+                            for (int e = 0; e < SFFTB_MAXE; ++e) {
                                 if (e < ne) { ma[e].x = fma(gg.x, pw[e], ma[e].x); ma[e].y = fma(gg.y, pw[e], ma[e].y); }
                             }
                         }
 #pragma unroll
-                        for (int e = 0; e < 6; ++e)
-                            if (e < ne) macc[(jj * SFFTB_MAXE + e) * FS3_NMT + mt] = ma[e];
+                        for (int e = 0; e < SFFTB_MAXE; ++e)
+                            if (e < ne) macc[(jj * SFFTB_MAXE + e) * NMT + mt] = ma[e];
                     }
                 }
 #ifdef FS3_DEBUG
@@ -271,14 +291,16 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
                 printf("P tid %d: loop %lld cycles, wait_full %lld, product %lld, moments %lld (nseg %d)\n", tid, clock64() - dT0, dWaitFull, dProd, dMom, nseg);
 #endif
             // ---- column moments -> background cross-term rows (product warps only) ----
-            fs3_barP();
-            if (tid < FSG_MSLOTS) {
-                cd sm = cmake(0.0, 0.0);
-                for (int t = 0; t < FS3_NMT; ++t) sm = cadd(sm, macc[tid * FS3_NMT + t]);
-                mom[tid] = sm;
+            if constexpr (DO_MOM) {
+                fs3_barP();
+                if (tid < NMS) {
+                    cd sm = cmake(0.0, 0.0);
+                    for (int t = 0; t < NMT; ++t) sm = cadd(sm, macc[tid * NMT + t]);
+                    mom[tid] = sm;
+                }
+                fs3_barP();
+                column_poly_rows_sub(fa, gI, k1, mom, kaprow, tid, 256, JONLY);
             }
-            fs3_barP();
-            column_poly_rows_sub(fa, gI, k1, mom, kaprow, tid, 256, JONLY);
             fs3_bar0();                                    // (A) all transforms and products of the column are done
 #pragma unroll
             for (int b0 = 0; b0 < NACC; b0 += 16) {
@@ -287,7 +309,7 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
                     if (b0 + q < NACC) spec[q * FS3_PITCH + VPAD(tid)] = acc[b0 + q];
                 fs3_bar0();
                 const int job = b0 + warp;
-                if (job < NACC) fs3_inverse_job<NPAIR>(fa, vt, spec + warp * FS3_PITCH, JOB0 + job, lane, kaprow);
+                if (job < NACC) fs3_inverse_job<NPAIR>(fa, vt, spec + warp * FS3_PITCH, job_of(job), lane, kaprow);
                 fs3_bar0();
             }
         }
@@ -303,8 +325,8 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
             for (int id = fw; id < nseg * NP; id += 8) {
                 const int s = id / NP, p = id - s * NP;
                 const int gs = g + s, slot = gs & 1;
-                const bool roleA = p < Fij, isJ = p == PJ;
-                const int pl = roleA ? p : (isJ ? 0 : p - Fij);
+                const bool roleA = p < NA, isJ = p == PJ;
+                const int pl = roleA ? A0 + p : (isJ ? 0 : A0 + (p - NA));
                 const int my_i = isJ ? 0 : a.pl_i[pl];
                 const int my_src = isJ ? DK + 1 : a.pl_j[pl];
                 const int c0 = s * S, Sc = min(S, a.N0 - c0);
@@ -363,7 +385,7 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
             for (int b0 = 0; b0 < NACC; b0 += 16) {
                 fs3_bar0();
                 const int job = b0 + warp;
-                if (job < NACC) fs3_inverse_job<NPAIR>(fa, vt, spec + warp * FS3_PITCH, JOB0 + job, lane, kaprow);
+                if (job < NACC) fs3_inverse_job<NPAIR>(fa, vt, spec + warp * FS3_PITCH, job_of(job), lane, kaprow);
                 fs3_bar0();
             }
         }

@@ -374,7 +374,8 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
             if (fit_smem_bytes(c, PB) <= p->max_smem) { c.PB = PB; okf = true; }
         }
     }
-    const bool want_seg = d.DK <= 2 && 4 * d.w0 + 32 <= FSG_M && cfg->fold <= 0 && !env_int("SFFTB_FIT_NOSEG", 0);
+    // KerPolyOrder = 3 exists only as the warp-specialised kernel (three launches); it needs the folded path as fallback
+    const bool want_seg = (d.DK <= 2 || okf) && 4 * d.w0 + 32 <= FSG_M && cfg->fold <= 0 && !env_int("SFFTB_FIT_NOSEG", 0);
     if (!okf && !want_seg)
         return fail(SFFTB_EINVAL, "unsupported image height N0=%d (fold=%d): no slice length with prime factors <= 13 fits shared memory",
                     N0, cfg->fold);
@@ -644,13 +645,22 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         SET_SFIT(0) SET_SFIT(1) SET_SFIT(2)
 #undef SET_SFIT
         p->grid_sfit = std::min(NH, p->nsm);
-        p->fit_seg = 1;
+        p->fit_seg = d.DK <= 2 ? 1 : 0;
         {
-            const int NPs = 2 * d.Fij + 1;
+            const int NPs = d.DK == 3 ? 13 : 2 * d.Fij + 1;      // DK = 3: the largest of the three passes (2 + 10 + 1)
             const int npla = std::max(2 * NPs, 16);
-            p->smem_sfit3 = sizeof(cd) * ((size_t)npla * FS3_PITCH + 4 * SFFTB_MAXE + (size_t)FSG_MSLOTS * FS3_NMT + 56 + 192) + 96 +
+            const int nms = (d.DK == 3 ? 5 : 4) * SFFTB_MAXE, nmt = d.DK == 3 ? 32 : 64;
+            p->smem_sfit3 = sizeof(cd) * ((size_t)npla * FS3_PITCH + nms + (size_t)nms * nmt + 56 + 192) + 96 +
                             csz * (f32 ? 8 : 4) * (size_t)(d.DK + 2) * FS3_M;
-            if (p->smem_sfit3 <= p->max_smem && !env_int("SFFTB_SEG_V2", 0)) {
+            if (d.DK == 3 && p->smem_sfit3 <= p->max_smem && !env_int("SFFTB_SEG_V2", 0)) {
+                const bool bad = f32 ? (set_smem(fit_seg3_kernel<float2, 3, false, 0, 2>, p->smem_sfit3) || set_smem(fit_seg3_kernel<float2, 3, false, 2, 5>, p->smem_sfit3) ||
+                                        set_smem(fit_seg3_kernel<float2, 3, false, 5, 10>, p->smem_sfit3))
+                                     : (set_smem(fit_seg3_kernel<double2, 3, false, 0, 2>, p->smem_sfit3) || set_smem(fit_seg3_kernel<double2, 3, false, 2, 5>, p->smem_sfit3) ||
+                                        set_smem(fit_seg3_kernel<double2, 3, false, 5, 10>, p->smem_sfit3));
+                if (bad) return SFFTB_ECUDA;
+                p->fit_seg = 2;
+            }
+            if (d.DK <= 2 && p->smem_sfit3 <= p->max_smem && !env_int("SFFTB_SEG_V2", 0)) {
 #define SET_SFIT3(DKK)                                                                                            \
                 if (d.DK == DKK) {                                                                                    \
                     if (f32) { if (set_smem(fit_seg3_kernel<float2, DKK>, p->smem_sfit3) || set_smem(fit_seg3_kernel<float2, DKK, true>, p->smem_sfit3)) return SFFTB_ECUDA; }       \
@@ -661,7 +671,7 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
                 p->fit_seg = 2;
             }
         }
-        d.fold = sf.nseg; d.sub_len = sf.S;
+        if (p->fit_seg) { d.fold = sf.nseg; d.sub_len = sf.S; }
     }
     if (p->row_fast) {
         const size_t sm = sizeof(cd) * (size_t)(ROWF_NT / (r.H / 16)) * (r.H + r.H / 16);
@@ -914,7 +924,7 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, 
     if (p->pendJ) { CK(cudaStreamWaitEvent(p->stream, p->pendJ, 0)); p->pendJ = nullptr; }
     if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
     EVREC(p, EV_ROWS);
-    const bool jonly = tI && p->factor_cached && p->chol_coop && p->fit_seg == 2 && !env_int("SFFTB_TEMPLATE_FULLFIT", 0);
+    const bool jonly = tI && p->factor_cached && p->chol_coop && p->fit_seg == 2 && d.DK <= 2 && !env_int("SFFTB_TEMPLATE_FULLFIT", 0);
     if (jonly) {
         // tiles after the first of a shared-template batch: the rows of the template-only pairs are already in kap2
         const int DK = d.DK;
@@ -925,7 +935,15 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, 
         const int DK = d.DK;
         if (DK == 0) fit_seg3_kernel<TSt, 0><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
         else if (DK == 1) fit_seg3_kernel<TSt, 1><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
-        else fit_seg3_kernel<TSt, 2><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else if (DK == 2) fit_seg3_kernel<TSt, 2><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else {
+            // KerPolyOrder = 3: 65 accumulators do not fit the product threads' registers; three launches over plane ranges
+            fit_seg3_kernel<TSt, 3, false, 0, 2><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+            CKL(p);
+            fit_seg3_kernel<TSt, 3, false, 2, 5><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+            CKL(p);
+            fit_seg3_kernel<TSt, 3, false, 5, 10><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        }
     } else if (p->fit_seg) {
         const int DK = d.DK;
         if (DK == 0) fit_seg_kernel<TSt, 0><<<p->grid_sfit, FSG_NT, p->smem_sfit, p->stream>>>(p->sfit, gIsrc, (const TSt*)p->gJ, p->kap2);
