@@ -783,3 +783,123 @@ __global__ void __launch_bounds__(CC_NT, 1) chol_subst_kernel(SubstArgs a)
         }
     }
 }
+
+
+// ---- the same substitutions with the vector and its ready tag in ONE 16-byte message (two 8-byte packets
+// {value word | epoch}, each stored atomically): a consumer polls the data itself, so the critical path from "y_k
+// computed" to "y_k in the consumer's shared memory" is one store and one load instead of store + fence + flag store
+// + flag load + data load.  The running right-hand side of a block lives in registers, the matrix-vector products
+// run on four independent accumulators per thread, and there is one CTA barrier per dependency block.
+struct SubstArgs2 {
+    const double* A; int ld, n;
+    const double* W;
+    double* yv;                          // in: scaled right-hand side b;  out: y (plain copy, read back by the owner CTA)
+    double* xs;                          // out: solution of the scaled system
+    ulonglong2* msg;                     // 2 * nblk * 64 messages (forward | backward)
+    unsigned epoch;
+    const double* sc; const int* idx; double* sol; int NEQ;
+};
+
+__device__ __forceinline__ void cs2_send(ulonglong2* m, double v, unsigned epoch) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v), e = (unsigned long long)epoch << 32;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(m), "l"((b & 0xffffffffull) | e), "l"((b >> 32) | e) : "memory");
+}
+__device__ __forceinline__ double cs2_recv(const ulonglong2* m, unsigned epoch) {
+    unsigned long long x, y;
+    int spins = 0;
+    while (true) {
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "l"(m) : "memory");
+        if ((unsigned)(x >> 32) == epoch && (unsigned)(y >> 32) == epoch) break;
+        if (++spins > (1 << 26)) __trap();
+    }
+    return __longlong_as_double((long long)((x & 0xffffffffull) | (y << 32)));
+}
+__device__ __forceinline__ void cs2_issue_block(const SubstArgs2& a, int rb, int cb, double* S) {
+    for (int idx = threadIdx.x; idx < CC_NB * CC_NB; idx += CC_NT) {
+        const int r = idx >> 6, c = idx & 63;
+        const int gr = rb * CC_NB + r, gc = cb * CC_NB + c;
+        const bool v = gr < a.n && gc < a.n;
+        const unsigned d = (unsigned)__cvta_generic_to_shared(S + r * CC_DP + c);
+        const int sz = v ? 8 : 0;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(a.A + (size_t)(v ? gr : 0) * a.ld + (v ? gc : 0)), "r"(sz) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(CC_NT, 1) chol_subst2_kernel(SubstArgs2 a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* Lb = reinterpret_cast<double*>(smem_raw);       // 2 x 64 x CC_DP
+    double* Wb = Lb + 2 * CC_NB * CC_DP;                    // 64 x CC_DP
+    double* sv = Wb + CC_NB * CC_DP;                        // 64: right-hand side of the block for the W product
+    double* vk = sv + 64;                                   // 2 x 64: the vectors that arrived (double buffered)
+    const int tid = threadIdx.x, G = gridDim.x, bid = blockIdx.x;
+    const int nblk = (a.n + CC_NB - 1) / CC_NB;
+    const int r = tid >> 2, part = tid & 3;                 // 4 threads per row / column, 16 entries each
+    if (bid == 0) {
+        for (int c = tid; c < a.NEQ; c += CC_NT) a.sol[c] = 0.0;
+        __threadfence();                                    // ordered before anything another CTA does after hearing from block 0
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool fwd = pass == 0;
+        ulonglong2* mout = a.msg + (size_t)pass * nblk * CC_NB;
+        for (int jj = 0; jj < nblk; ++jj) {
+            const int j = fwd ? jj : nblk - 1 - jj;
+            if (j % G != bid) continue;
+            const int j0 = j * CC_NB, jb = min(CC_NB, a.n - j0);
+            const int ndep = fwd ? j : nblk - 1 - j;
+            __syncthreads();                                // previous block of this CTA is done with the buffers
+            if (ndep > 0) { const int k = fwd ? 0 : nblk - 1; if (fwd) cs2_issue_block(a, j, k, Lb); else cs2_issue_block(a, k, j, Lb); }
+            for (int idx = tid; idx < CC_NB * CC_NB; idx += CC_NT) Wb[(idx >> 6) * CC_DP + (idx & 63)] = a.W[(size_t)j * CC_NB * CC_NB + idx];
+            double s_reg = (part == 0 && r < jb) ? a.yv[j0 + r] : 0.0;   // b_j (forward) / y_j written by this CTA (backward)
+            for (int d = 0; d < ndep; ++d) {
+                const int k = fwd ? d : nblk - 1 - d;
+                double* Lc = Lb + (d & 1) * CC_NB * CC_DP;
+                double* vc = vk + (d & 1) * 64;
+                if (tid < CC_NB) { const int gk = k * CC_NB + tid; vc[tid] = (gk < a.n) ? cs2_recv(mout + gk, a.epoch) : 0.0; }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncthreads();                            // L block d and vector d are in shared memory; step d - 1 is finished
+                if (d + 1 < ndep) {
+                    const int kn = fwd ? d + 1 : nblk - 2 - d;
+                    if (fwd) cs2_issue_block(a, j, kn, Lb + ((d + 1) & 1) * CC_NB * CC_DP); else cs2_issue_block(a, kn, j, Lb + ((d + 1) & 1) * CC_NB * CC_DP);
+                }
+                // forward: s[r] -= sum_c L_jk[r][c] y_k[c];  backward: s[c] -= sum_r L_kj[r][c] x_k[r]
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                for (int m = 0; m < 16; m += 4) {
+                    const int q = part * 16 + m;
+                    a0 = fma(fwd ? Lc[r * CC_DP + q] : Lc[q * CC_DP + r], vc[q], a0);
+                    a1 = fma(fwd ? Lc[r * CC_DP + q + 1] : Lc[(q + 1) * CC_DP + r], vc[q + 1], a1);
+                    a2 = fma(fwd ? Lc[r * CC_DP + q + 2] : Lc[(q + 2) * CC_DP + r], vc[q + 2], a2);
+                    a3 = fma(fwd ? Lc[r * CC_DP + q + 3] : Lc[(q + 3) * CC_DP + r], vc[q + 3], a3);
+                }
+                double acc = (a0 + a1) + (a2 + a3);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                s_reg -= acc;
+            }
+            if (part == 0) sv[r] = s_reg;
+            __syncthreads();
+            // y_j = W_j s (forward) / x_j = W_j^T s (backward)
+            {
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                for (int m = 0; m < 16; m += 4) {
+                    const int q = part * 16 + m;
+                    a0 = fma(fwd ? Wb[r * CC_DP + q] : Wb[q * CC_DP + r], sv[q], a0);
+                    a1 = fma(fwd ? Wb[r * CC_DP + q + 1] : Wb[(q + 1) * CC_DP + r], sv[q + 1], a1);
+                    a2 = fma(fwd ? Wb[r * CC_DP + q + 2] : Wb[(q + 2) * CC_DP + r], sv[q + 2], a2);
+                    a3 = fma(fwd ? Wb[r * CC_DP + q + 3] : Wb[(q + 3) * CC_DP + r], sv[q + 3], a3);
+                }
+                double acc = (a0 + a1) + (a2 + a3);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                if (part == 0 && r < jb) {
+                    cs2_send(mout + j0 + r, acc, a.epoch);
+                    if (fwd) a.yv[j0 + r] = acc;
+                    else { a.xs[j0 + r] = acc; a.sol[a.idx[j0 + r]] = acc * a.sc[j0 + r]; }
+                }
+            }
+        }
+    }
+}

@@ -90,6 +90,7 @@ struct sfftb_plan {
     unsigned* substFlags;        // 2 * nblk epoch tags of the dataflow substitution kernel
     unsigned substEpoch;
     int subst_ok;
+    ulonglong2* substMsg;        // 2 * nblk * 64 {value | epoch} messages of chol_subst2_kernel
     int chol_coop;
     double* exportbuf;
     int ld, nsolve;
@@ -279,7 +280,7 @@ static int plan_free(sfftb_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     void* ptrs[] = {p->vt8_8, p->vt64_8, p->vt64_4, p->vt256_4, p->vt512_4, p->tabA, p->tabB_row, p->tabC_row, p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
-                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->firTaps, p->firCA, p->tstate, p->stC, p->stD};
+                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->substMsg, p->firTaps, p->firCA, p->tstate, p->stC, p->stD};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->info_h) cudaFreeHost(p->info_h);
     for (int k = 0; k < EV_COUNT; ++k) if (p->ev[k]) cudaEventDestroy(p->ev[k]);
@@ -443,6 +444,11 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
             int occs = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occs, chol_subst_kernel, CC_NT, ssm));
             p->subst_ok = (occs >= 1 && coop && !env_int("SFFTB_RESOLVE_V1", 0)) ? 1 : 0;
+            CK(cudaMalloc(&p->substMsg, sizeof(ulonglong2) * 2 * (size_t)nblk * CC_NB));
+            CK(cudaMemset(p->substMsg, 0, sizeof(ulonglong2) * 2 * (size_t)nblk * CC_NB));
+            const size_t ssm2 = sizeof(double) * (3 * CC_NB * CC_DP + 64 + 128);
+            CK(cudaFuncSetAttribute(chol_subst2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm2));
+            if (p->subst_ok && !env_int("SFFTB_RESOLVE_V2", 0)) p->subst_ok = 2;
         }
         p->chol_coop = (occ >= 1 && coop && !env_int("SFFTB_CHOL_LEGACY", 0)) ? std::min(occ, std::max(1, env_int("SFFTB_CHOL_CTAS", CC_CTAS_PER_SM))) : 0;
     }
@@ -816,6 +822,18 @@ static int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, i
 
 static int run_cholesky(sfftb_plan* p, int resolve = 0) {
     const int n = p->nsolve, ntot = n + 1;
+    if (p->chol_coop && resolve && p->subst_ok == 2) {
+        SubstArgs2 sa;
+        sa.A = p->Aug; sa.ld = p->ld; sa.n = n; sa.W = p->cholW; sa.yv = p->cholY; sa.xs = p->cholX;
+        sa.msg = p->substMsg; sa.epoch = ++p->substEpoch;
+        sa.sc = p->sc; sa.idx = p->idxmap; sa.sol = p->sol; sa.NEQ = p->d.NEQ;
+        const int nblk = (n + CC_NB - 1) / CC_NB;
+        void* args[] = {&sa};
+        CK(cudaLaunchCooperativeKernel((void*)chol_subst2_kernel, dim3(std::min(nblk, p->nsm)), dim3(CC_NT), args,
+                                       sizeof(double) * (3 * CC_NB * CC_DP + 64 + 128), p->stream));
+        p->launches++;
+        return 0;
+    }
     if (p->chol_coop && resolve && p->subst_ok) {
         SubstArgs sa;
         sa.A = p->Aug; sa.ld = p->ld; sa.n = n; sa.W = p->cholW; sa.yv = p->cholY; sa.xs = p->cholX;
