@@ -298,7 +298,7 @@ def main():
         npairs = Fij * (Fij + 1) // 2
         Fpq = (DB + 1) * (DB + 2) // 2
         nrowsK = npairs * (4 * w + 1) + Fij * (2 * w + 1)
-        seg_path = DK <= 2 and 4 * w + 32 <= 256
+        seg_path = 4 * w + 32 <= 256      # fit_seg3_kernel (one launch for DK <= 2, three plane-range launches for DK = 3)
         nrowsL = (Fij * Fpq * (2 * w + 1) + Fpq) if seg_path else (Fij * (DB + 1) * (2 * w + 1) + (DB + 1))
         kname = 'fit_seg3_kernel' if seg_path else 'fit_col_fast_kernel'
         alg_bytes = (DK + 2) * NH * N0 * csz + (nrowsK + nrowsL) * NH * 16
