@@ -301,9 +301,10 @@ def main():
         seg_path = 4 * w + 32 <= 256      # fit_seg3_kernel (one launch for DK <= 2, three plane-range launches for DK = 3)
         nrowsL = (Fij * Fpq * (2 * w + 1) + Fpq) if seg_path else (Fij * (DB + 1) * (2 * w + 1) + (DB + 1))
         kname = 'fit_seg3_kernel' if seg_path else 'fit_col_fast_kernel'
-        alg_bytes = (DK + 2) * NH * N0 * csz + (nrowsK + nrowsL) * NH * 16
+        npass = 3 if (seg_path and DK == 3) else 1          # every plane-range launch streams the stored planes once
+        alg_bytes = npass * (DK + 2) * NH * N0 * csz + (nrowsK + nrowsL) * NH * 16
         t_kernel = stage.get('fit_cols', 0.0) / 1e3
-        achieved = alg_bytes / t_kernel / 1e9 if t_kernel > 0 else None
+        achieved = alg_bytes / t_kernel / 1e9 if t_kernel > 0 else None      # = bytes per launch / average launch time
         # whole-step algorithmic bytes: (4 n_pl + 7) * N0 * N1 * s with n_pl = Fij + 1
         step_bytes = (4 * (Fij + 1) + 7) * N0 * N1 * esz
         out = {
@@ -328,7 +329,7 @@ def main():
                          'note': 'the path is fp64-issue bound on B200 (64 DFMA/clk/SM, DESIGN.md section 4); the HBM '
                                  'fraction is reported as the contract asks',
                          'peak_source': which, 'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None,
-                         'traffic': None, 'algorithmic_bytes_per_launch': alg_bytes,
+                         'traffic': None, 'algorithmic_bytes_per_launch': alg_bytes / npass, 'launches_per_step_of_kernel': npass,
                          'kernel_ms': stage.get('fit_cols'),
                          'step_algorithmic_bytes': step_bytes,
                          'step_frac': step_bytes / (ms / 1e3) / 1e9 / peak},
