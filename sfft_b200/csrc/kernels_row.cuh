@@ -18,7 +18,46 @@ struct RowArgs {
     FftDesc fd;       // plan for length H
     const cd* twH;    // exp(-2 pi i e / H)
     const cd* tw1;    // exp(-2 pi i e / N1)
+    // Bluestein (chirp-z) path for lengths H with a prime factor > 13: blu_M = power of two >= 2 H - 1 (0 = unused)
+    int blu_M;
+    FftDesc blu_fd;       // plan for length blu_M
+    const cd* blu_tw;     // exp(-2 pi i e / blu_M)
+    const cd* blu_c;      // chirp c[n] = exp(-pi i n^2 / H), n < H
+    const cd* blu_B;      // FFT_M of conj(c) wrapped to length M (the chirp filter), already divided by M
 };
+
+// Length-H transform of `nplanes` planes through Bluestein's identity n k = (n^2 + k^2 - (k - n)^2) / 2:
+//   X[k] = c[k] * sum_n (x[n] c[n]) conj(c)[k - n]      (forward);  inverse = conj(forward(conj(x))).
+// Planes must have room for blu_M elements.  Same barrier contract as fft_planes.
+__device__ __forceinline__ void row_transform(cd* buf, int nplanes, const RowArgs& a, double sgn) {
+    if (a.blu_M == 0) { fft_planes(buf, a.pitch, nplanes, a.fd, a.twH, sgn); return; }
+    const int tid = threadIdx.x, nthr = blockDim.x, M = a.blu_M;
+    const bool inv = sgn > 0.0;
+    for (int idx = tid; idx < nplanes * M; idx += nthr) {
+        const int pl = idx / M, n = idx - pl * M;
+        cd* q = buf + (size_t)pl * a.pitch + n;
+        cd v = cmake(0.0, 0.0);
+        if (n < a.H) { v = *q; if (inv) v.y = -v.y; v = cmul(v, a.blu_c[n]); }
+        *q = v;
+    }
+    __syncthreads();
+    fft_planes(buf, a.pitch, nplanes, a.blu_fd, a.blu_tw, -1.0);
+    for (int idx = tid; idx < nplanes * M; idx += nthr) {
+        const int pl = idx / M, n = idx - pl * M;
+        cd* q = buf + (size_t)pl * a.pitch + n;
+        *q = cmul(*q, a.blu_B[n]);
+    }
+    __syncthreads();
+    fft_planes(buf, a.pitch, nplanes, a.blu_fd, a.blu_tw, +1.0);
+    for (int idx = tid; idx < nplanes * a.H; idx += nthr) {
+        const int pl = idx / a.H, n = idx - pl * a.H;
+        cd* q = buf + (size_t)pl * a.pitch + n;
+        cd v = cmul(*q, a.blu_c[n]);
+        if (inv) v.y = -v.y;
+        *q = v;
+    }
+    __syncthreads();
+}
 
 template <typename TIn, typename TSt>
 __global__ void __launch_bounds__(512) row_fwd_kernel(RowArgs a, const TIn* __restrict__ img, TSt* __restrict__ out, int nj)
@@ -59,7 +98,7 @@ __global__ void __launch_bounds__(512) row_fwd_kernel(RowArgs a, const TIn* __re
             }
         }
         __syncthreads();
-        fft_planes(buf, a.pitch, a.RB, a.fd, a.twH, -1.0);
+        row_transform(buf, a.RB, a, -1.0);
         // untangle + transposed store: consecutive threads -> consecutive rows of the same k1
         for (int idx = tid; idx < a.RB * a.NH; idx += nthr) {
             const int k = idx / a.RB, row = idx - k * a.RB;
@@ -130,7 +169,7 @@ __global__ void __launch_bounds__(512) row_inv_kernel(RowInvArgs ia, const TSt* 
         }
     }
     __syncthreads();
-    fft_planes(buf, a.pitch, a.RB, a.fd, a.twH, +1.0);
+    row_transform(buf, a.RB, a, +1.0);
 
     double b[16];
 #pragma unroll

@@ -90,6 +90,7 @@ struct sfftb_plan {
     unsigned* substFlags;        // 2 * nblk epoch tags of the dataflow substitution kernel
     unsigned substEpoch;
     int subst_ok;
+    cd *bluTw, *bluC, *bluB;     // Bluestein tables of the generic row pass (row lengths with a prime factor > 13)
     ulonglong2* substMsg;        // 2 * nblk * 64 {value | epoch} messages of chol_subst2_kernel
     int chol_coop;
     double* exportbuf;
@@ -191,6 +192,49 @@ static int upload_engine_table(int Ns, int R, cd** out) {
     return 0;
 }
 
+// Bluestein tables for length H through a power-of-two M >= 2 H - 1: chirp c[n] = exp(-pi i n^2 / H) with n^2 reduced
+// mod 2 H in integers, and B = FFT_M(conj(c) wrapped) / M (radix-2 in long double on the host; once per plan).
+static int upload_bluestein(int H, int M, cd** outC, cd** outB) {
+    typedef long double ld;
+    const ld pi = 3.141592653589793238462643383279502884L;
+    std::vector<cd> c((size_t)H);
+    std::vector<ld> br((size_t)M, 0.0L), bi((size_t)M, 0.0L);
+    for (int n = 0; n < H; ++n) {
+        const long long q = ((long long)n * n) % (2LL * H);
+        const ld ang = pi * (ld)q / (ld)H;
+        const ld cr = cosl(ang), ci = -sinl(ang);
+        c[n].x = (double)cr; c[n].y = (double)ci;
+        br[n] = cr; bi[n] = -ci;                                   // conj(c[n])
+        if (n > 0) { br[M - n] = cr; bi[M - n] = -ci; }
+    }
+    // iterative radix-2 decimation-in-time FFT, sign -1
+    for (int i = 1, j = 0; i < M; ++i) {
+        int bit = M >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) { std::swap(br[i], br[j]); std::swap(bi[i], bi[j]); }
+    }
+    for (int len = 2; len <= M; len <<= 1) {
+        for (int k = 0; k < len / 2; ++k) {
+            const ld ang = 2.0L * pi * (ld)k / (ld)len;
+            const ld wr = cosl(ang), wi = -sinl(ang);
+            for (int i = k; i < M; i += len) {
+                const int j2 = i + len / 2;
+                const ld xr = br[j2] * wr - bi[j2] * wi, xi = br[j2] * wi + bi[j2] * wr;
+                br[j2] = br[i] - xr; bi[j2] = bi[i] - xi;
+                br[i] += xr; bi[i] += xi;
+            }
+        }
+    }
+    std::vector<cd> B((size_t)M);
+    for (int m = 0; m < M; ++m) { B[m].x = (double)(br[m] / (ld)M); B[m].y = (double)(bi[m] / (ld)M); }
+    CK(cudaMalloc(outC, sizeof(cd) * (size_t)H));
+    CK(cudaMemcpy(*outC, c.data(), sizeof(cd) * (size_t)H, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(outB, sizeof(cd) * (size_t)M));
+    CK(cudaMemcpy(*outB, B.data(), sizeof(cd) * (size_t)M, cudaMemcpyHostToDevice));
+    return 0;
+}
+
 static int init_generic_radix_tables() {
     const int rad[4] = {5, 7, 11, 13};
     double2 h[4][16];
@@ -280,7 +324,7 @@ static int plan_free(sfftb_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     void* ptrs[] = {p->vt8_8, p->vt64_8, p->vt64_4, p->vt256_4, p->vt512_4, p->tabA, p->tabB_row, p->tabC_row, p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
-                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->substMsg, p->firTaps, p->firCA, p->tstate, p->stC, p->stD};
+                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->substMsg, p->bluTw, p->bluC, p->bluB, p->firTaps, p->firCA, p->tstate, p->stC, p->stD};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->info_h) cudaFreeHost(p->info_h);
     for (int k = 0; k < EV_COUNT; ++k) if (p->ev[k]) cudaEventDestroy(p->ev[k]);
@@ -334,16 +378,27 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
     r.N0 = N0; r.N1 = N1; r.NH = NH;
     r.packed = (N1 % 2 == 0) ? 1 : 0;
     r.H = r.packed ? N1 / 2 : N1;
-    if (!make_fft_desc(r.H, &r.fd) || !fft_fits_threads(r.fd, 512))
-        return fail(SFFTB_EINVAL, "unsupported image width N1=%d: row transform length %d needs prime factors <= 13", N1, r.H);
     r.pitch = r.H + 1;
+    if (!make_fft_desc(r.H, &r.fd) || !fft_fits_threads(r.fd, 512) || env_int("SFFTB_ROW_BLUESTEIN", 0)) {
+        // a prime factor > 13 (e.g. a trimmed 4094-pixel DECam row: 2047 = 23 * 89): chirp-z through a power of two
+        int M = 1;
+        while (M < 2 * r.H - 1) M <<= 1;
+        if (!make_fft_desc(M, &r.blu_fd) || !fft_fits_threads(r.blu_fd, 512) || (size_t)(M + 1) * sizeof(cd) > p->max_smem)
+            return fail(SFFTB_EINVAL, "unsupported image width N1=%d: row transform length %d has a prime factor > 13 and its "
+                                      "chirp-z length %d does not fit shared memory", N1, r.H, M);
+        r.blu_M = M;
+        r.pitch = M + 1;
+        if (upload_twiddles(M, &p->bluTw) || upload_bluestein(r.H, M, &p->bluC, &p->bluB)) return SFFTB_ECUDA;
+        r.blu_tw = p->bluTw; r.blu_c = p->bluC; r.blu_B = p->bluB;
+        memset(&r.fd, 0, sizeof r.fd);
+    }
     int RB = env_int("SFFTB_RB", 8);
     while (RB > 1 && ((size_t)RB * r.pitch * sizeof(cd) > p->max_smem || RB > N0)) RB >>= 1;
     if ((size_t)RB * r.pitch * sizeof(cd) > p->max_smem)
         return fail(SFFTB_EINVAL, "image width N1=%d too large for the shared-memory row transform", N1);
     r.RB = RB;
     p->smem_row = (size_t)RB * r.pitch * sizeof(cd);
-    if (upload_twiddles(r.H, &p->twH)) return SFFTB_ECUDA;
+    if (!r.blu_M && upload_twiddles(r.H, &p->twH)) return SFFTB_ECUDA;
     r.twH = p->twH; r.tw1 = p->tw1;
     p->rinv.r = r;
     p->rinv.scale = (r.packed ? 2.0 : 1.0) / (double)N1;      // the FIR column pass already carries 1/N0
