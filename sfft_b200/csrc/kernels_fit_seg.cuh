@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(FSG_NT, 1) fit_seg_kernel(SegFitArgs fa, const
 #define LR2_KC 512        // k1 columns per CTA (chunk); their twiddles for the lags of a pass are staged in shared memory
 struct LagReduce2Args {
     int N1, NH, nrows, w1, ksplit;
+    int rb0;                 // first 16-row block of this launch (shared-template tiles reduce only the rows that changed)
     const cd* tw1;
 };
 
@@ -294,7 +295,8 @@ __global__ void __launch_bounds__(256) lag_reduce2_kernel(LagReduce2Args a, cons
     cd (*twc)[LR2_LB] = reinterpret_cast<cd (*)[LR2_LB]>(lr2_smem);   // twc[k - kbeg][t] = wt(k)/N1 exp(-2 pi i k (mb + t) / N1)
     const int tid = threadIdx.x;
     const int rl = tid & 15, kl = tid >> 4;
-    const int row = blockIdx.x * 16 + rl;
+    const int rb = blockIdx.x + a.rb0;
+    const int row = rb * 16 + rl;
     const int ks = blockIdx.y;
     const int kbeg = ks * LR2_KC, kend = min(a.NH, kbeg + LR2_KC);
     const double inv1 = 1.0 / (double)a.N1;
@@ -328,7 +330,7 @@ __global__ void __launch_bounds__(256) lag_reduce2_kernel(LagReduce2Args a, cons
         __syncthreads();
         for (int idx = tid; idx < 16 * 2 * LR2_LB; idx += 256) {
             const int r2 = idx / (2 * LR2_LB), t2 = idx - r2 * (2 * LR2_LB);
-            const int rr = blockIdx.x * 16 + r2;
+            const int rr = rb * 16 + r2;
             const bool neg = t2 >= LR2_LB;
             const int m = mb + (neg ? t2 - LR2_LB : t2);
             if (rr < a.nrows && m <= 2 * a.w1 && !(neg && m == 0)) {

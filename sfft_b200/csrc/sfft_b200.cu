@@ -689,7 +689,7 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
                        csz * 2 * (size_t)(d.DK + 2) * FSG_M;
         CK(cudaMalloc(&p->kap2, sizeof(cd) * (size_t)NH * sf.nrows));
         LagReduce2Args& r2 = p->red2;
-        r2.N1 = N1; r2.NH = NH; r2.nrows = sf.nrows; r2.w1 = d.w1; r2.tw1 = p->tw1;
+        r2.N1 = N1; r2.NH = NH; r2.nrows = sf.nrows; r2.w1 = d.w1; r2.tw1 = p->tw1; r2.rb0 = 0;
         const int rowblocks = (sf.nrows + 15) / 16;
         r2.ksplit = (NH + LR2_KC - 1) / LR2_KC;
         if (set_smem(lag_reduce2_kernel, sizeof(cd) * LR2_KC * LR2_LB)) return SFFTB_ECUDA;
@@ -1032,7 +1032,21 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, 
         fit_col_kernel<TSt><<<p->grid_fit, NT_COL, p->smem_fit, p->stream>>>(p->cfit, gIsrc, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
     CKL(p);
     EVREC(p, EV_COL);
-    if (p->fit_seg) {
+    if (p->fit_seg && jonly) {
+        // only the I x J rows [nOm, nK) and the J x T rows [nK + nLT, nrows) changed; `part` keeps the rest
+        LagReduce2Args ra = p->red2;
+        ra.rb0 = p->sfit.nOm / 16;
+        dim3 g1((p->sfit.nK + 15) / 16 - ra.rb0, ra.ksplit);
+        lag_reduce2_kernel<<<g1, 256, sizeof(cd) * LR2_KC * LR2_LB, p->stream>>>(ra, p->kap2, p->part);
+        CKL(p);
+        ra.rb0 = (p->sfit.nK + p->sfit.nLT) / 16;
+        dim3 g2((p->sfit.nrows + 15) / 16 - ra.rb0, ra.ksplit);
+        lag_reduce2_kernel<<<g2, 256, sizeof(cd) * LR2_KC * LR2_LB, p->stream>>>(ra, p->kap2, p->part);
+        CKL(p);
+        const int tot = p->sfit.nrows * (4 * d.w1 + 1);
+        lag_finish_kernel<<<(tot + 255) / 256, 256, 0, p->stream>>>(p->fin2, p->part);
+        CKL(p);
+    } else if (p->fit_seg) {
         dim3 grd((p->sfit.nrows + 15) / 16, p->red2.ksplit);
         lag_reduce2_kernel<<<grd, 256, sizeof(cd) * LR2_KC * LR2_LB, p->stream>>>(p->red2, p->kap2, p->part);
         CKL(p);
