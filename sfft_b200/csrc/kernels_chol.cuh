@@ -52,7 +52,8 @@ __device__ __forceinline__ void cc_grid_barrier(unsigned* cnt, unsigned& target,
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(cnt, 1u);
-        while (cc_ld_acquire(cnt) < target) {}
+        int spins = 0;
+        while (cc_ld_acquire(cnt) < target) { if (++spins > (1 << 25)) __trap(); }   // watchdog: never hang the device
         __threadfence();
     }
     __syncthreads();
