@@ -98,6 +98,16 @@ int  sfftb_gss(sfftb_plan* plan, const void* PixA_I, const void* PixA_J, const v
                int img_memkind, int img_dtype, double* solution, int sol_memkind,
                void* diff, int diff_memkind, int diff_dtype);
 
+/* Asynchronous form of sfftb_gss for HOST buffers (pinned memory recommended): submit queues the four H2D copies on
+ * the plan's copy stream, the fit, the apply and the D2H of `diff` / `solution`, and returns; finish waits for this
+ * plan's work only, runs the LU fallback if the Cholesky broke down, and reports errors like sfftb_gss.  One submission
+ * per plan may be in flight.  Two plans bound to ONE compute stream (sfftb_plan_set_stream) and driven alternately keep
+ * the PCIe link busy in both directions while the kernels of the other pair run -- the way a queue of pairs coming
+ * from host memory (sfft/MultiEasySparsePacket.py:568-649 feeds one GPU from a host-side task queue) should be fed. */
+int  sfftb_gss_submit(sfftb_plan* plan, const void* PixA_I, const void* PixA_J, const void* PixA_mI, const void* PixA_mJ,
+                      int img_dtype, double* solution, void* diff, int diff_dtype);
+int  sfftb_gss_finish(sfftb_plan* plan);
+
 /* Shared-template batch path (BASELINE config 4).  The reference re-transforms the template for every
  * pair (ESS is called per pair, sfft/MultiEasySparsePacket.py:568-649); here the row spectra of the convolved image
  * (I = template when ForceConv='REF', sfft/CustomizedPacket.py:148-162) are computed once:

@@ -72,3 +72,59 @@ class TemplateBatch:
             J, mJ = get(k)
             out[k] = self.backend.gss_template(J, mJ)
         return out
+
+
+class PairPipeline:
+    """A queue of independent image pairs in host memory through ONE GPU (what a worker thread of
+    sfft/MultiEasySparsePacket.py:568-649 does pair after pair): two plans share one compute stream and are driven
+    alternately through sfftb_gss_submit / sfftb_gss_finish, so the host-to-device copies of pair k + 1 run while the
+    kernels and the device-to-host copy of pair k are in flight.  Results come back in submission order."""
+
+    def __init__(self, N0, N1, KerHW, KerPolyOrder=2, BGPolyOrder=2, ConstPhotRatio=True, device=0, storage='fp64',
+                 stream_ptr=None, depth=2):
+        from .plan import Plan
+        self.plans = [Plan(N0, N1, KerHW, KerHW, KerPolyOrder, BGPolyOrder, ConstPhotRatio, device=device, storage=storage)
+                      for _ in range(depth)]
+        if stream_ptr is None:
+            import torch
+            stream_ptr = torch.cuda.current_stream(torch.device('cuda', device)).cuda_stream
+        for pl in self.plans:
+            pl.set_stream(stream_ptr)
+        self._busy = [False] * depth
+        self._k = 0
+
+    def submit(self, PixA_I, PixA_J, PixA_mI, PixA_mJ, out_dtype=np.float64, Solution_out=None, DIFF_out=None):
+        """Returns the result of the pair that had to leave its slot to make room (or None)."""
+        slot = self._k % len(self.plans)
+        done = None
+        if self._busy[slot]:
+            done = self.plans[slot].gss_finish()
+        self.plans[slot].gss_submit(PixA_I, PixA_J, PixA_mI, PixA_mJ, out_dtype, Solution_out, DIFF_out)
+        self._busy[slot] = True
+        self._k += 1
+        return done
+
+    def drain(self):
+        """Finish everything in flight, oldest first."""
+        out = []
+        n = len(self.plans)
+        for d in range(n):
+            slot = (self._k + d) % n
+            if self._busy[slot]:
+                out.append(self.plans[slot].gss_finish())
+                self._busy[slot] = False
+        return out
+
+    def run(self, pairs, out_dtype=np.float64):
+        """pairs: iterable of (I, J, mI, mJ) host arrays -> list of (Solution, DIFF) in order."""
+        res = []
+        for (I, J, mI, mJ) in pairs:
+            r = self.submit(I, J, mI, mJ, out_dtype)
+            if r is not None:
+                res.append(r)
+        res.extend(self.drain())
+        return res
+
+    def close(self):
+        for pl in self.plans:
+            pl.close()

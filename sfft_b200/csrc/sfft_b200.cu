@@ -81,6 +81,9 @@ struct sfftb_plan {
     void *stA, *stB;             // device staging for host images / host diff
     void *stC, *stD;             // second staging pair (host GSS: the apply images are copied while the fit computes)
     cudaEvent_t evCopy[4], evStart;
+    cudaEvent_t evDone;          // end of the work queued by sfftb_gss_submit
+    int pending;                 // a submitted GSS has not been finished yet
+    void* pend_diff; double* pend_sol; int pend_dtype, pend_diff_dtype;
     cudaEvent_t pendI, pendJ;    // events the next row pass of I / J has to wait for (host pipeline), or NULL
     cd *kap, *lam, *nuJ;
     double *R, *RJ, *RT, *RJT;
@@ -333,6 +336,7 @@ static int plan_free(sfftb_plan* p) {
     if (p->evFork) cudaEventDestroy(p->evFork);
     for (int k = 0; k < 4; ++k) if (p->evCopy[k]) cudaEventDestroy(p->evCopy[k]);
     if (p->evStart) cudaEventDestroy(p->evStart);
+    if (p->evDone) cudaEventDestroy(p->evDone);
     if (p->evJoin) cudaEventDestroy(p->evJoin);
     delete p;
     return 0;
@@ -355,6 +359,7 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
     CK(cudaEventCreateWithFlags(&p->evJoin, cudaEventDisableTiming));
     for (int k = 0; k < 4; ++k) CK(cudaEventCreateWithFlags(&p->evCopy[k], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&p->evStart, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&p->evDone, cudaEventDisableTiming));
     p->overlap = env_int("SFFTB_OVERLAP", 1);
     for (int k = 0; k < EV_COUNT; ++k) CK(cudaEventCreate(&p->ev[k]));
     if (init_generic_radix_tables()) return SFFTB_ECUDA;
@@ -1338,6 +1343,68 @@ extern "C" int sfftb_gss(sfftb_plan* p, const void* I, const void* J, const void
     if ((rc = copy_out(p, solution, sol_memkind, p->sol, sizeof(double) * p->d.NEQ))) return rc;
     CK(cudaStreamSynchronize(p->stream));
     return 0;
+}
+
+// ---- asynchronous host-buffer GSS: submit queues the H2D copies (side stream), the fit, the apply and the D2H of the
+// difference image and returns; finish waits for THIS plan's work only.  Two plans that share one compute stream
+// (sfftb_plan_set_stream) and are driven alternately overlap the H2D copies of pair k + 1 with the kernels and the D2H
+// of pair k (PCIe is full duplex), which is what bounds a stream of pairs coming from host memory.
+extern "C" int sfftb_gss_submit(sfftb_plan* p, const void* I, const void* J, const void* mI, const void* mJ, int dtype,
+                                double* solution, void* diff, int diff_dtype) {
+    if (!p || !I || !J || !mI || !mJ || !diff) return fail(SFFTB_EINVAL, "null argument");
+    if ((dtype != SFFTB_F64 && dtype != SFFTB_F32) || (diff_dtype != SFFTB_F64 && diff_dtype != SFFTB_F32)) return fail(SFFTB_EINVAL, "bad dtype");
+    if (p->pending) return fail(SFFTB_ESTATE, "sfftb_gss_submit: the previous submission of this plan has not been finished");
+    CK(cudaSetDevice(p->device));
+    const bool f32 = p->cfg.storage == SFFTB_STORE_F32;
+    const size_t bytes = (size_t)p->d.N0 * p->d.N1 * (dtype == SFFTB_F64 ? 8 : 4);
+    if (!p->stC) { CK(cudaMalloc(&p->stC, sizeof(double) * (size_t)p->d.N0 * p->d.N1)); CK(cudaMalloc(&p->stD, sizeof(double) * (size_t)p->d.N0 * p->d.N1)); }
+    // no wait on the compute stream here: the staging buffers are free (the previous submission was finished), and the
+    // copies must not queue behind another plan's kernels on a shared compute stream
+    const void* srcs[4] = {mI, mJ, I, J};
+    void* dsts[4] = {p->stA, p->stB, p->stC, p->stD};
+    for (int k = 0; k < 4; ++k) {
+        CK(cudaMemcpyAsync(dsts[k], srcs[k], bytes, cudaMemcpyHostToDevice, p->stream2));
+        CK(cudaEventRecord(p->evCopy[k], p->stream2));
+    }
+    // evCopy[2..3] are re-recorded by the chunked D2H of the apply step, so the apply pair gets its own wait now
+    p->pendI = p->evCopy[0]; p->pendJ = p->evCopy[1];
+    int rc = f32 ? fit_device<float2>(p, p->stA, p->stB, dtype) : fit_device<double2>(p, p->stA, p->stB, dtype);
+    if (rc) return rc;
+    p->pendI = p->evCopy[2]; p->pendJ = p->evCopy[3];
+    void* hd = p->row_fast ? diff : nullptr;
+    rc = f32 ? apply_device<float2>(p, p->stC, p->stD, dtype, p->sol, p->stA, diff_dtype, nullptr, false, hd)
+             : apply_device<double2>(p, p->stC, p->stD, dtype, p->sol, p->stA, diff_dtype, nullptr, false, hd);
+    if (rc) return rc;
+    if (!p->row_fast) {
+        const size_t ob = (size_t)p->d.N0 * p->d.N1 * (diff_dtype == SFFTB_F64 ? 8 : 4);
+        CK(cudaMemcpyAsync(diff, p->stA, ob, cudaMemcpyDeviceToHost, p->stream));
+    }
+    if (solution) CK(cudaMemcpyAsync(solution, p->sol, sizeof(double) * p->d.NEQ, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaEventRecord(p->evDone, p->stream));
+    p->pending = 1; p->pend_diff = diff; p->pend_sol = solution; p->pend_dtype = dtype; p->pend_diff_dtype = diff_dtype;
+    return 0;
+}
+
+extern "C" int sfftb_gss_finish(sfftb_plan* p) {
+    if (!p) return fail(SFFTB_EINVAL, "null plan");
+    if (!p->pending) return fail(SFFTB_ESTATE, "sfftb_gss_finish: nothing was submitted");
+    CK(cudaSetDevice(p->device));
+    p->pending = 0;
+    CK(cudaEventSynchronize(p->evDone));
+    int rc = check_solver(p);
+    if (rc < 0) return rc;
+    if (rc == 1) {
+        // the Cholesky broke down and the LU fallback replaced the solution: apply again (rare; synchronous)
+        const bool f32 = p->cfg.storage == SFFTB_STORE_F32;
+        rc = f32 ? apply_device<float2>(p, p->stC, p->stD, p->pend_dtype, p->sol, p->stA, p->pend_diff_dtype, nullptr, false, nullptr)
+                 : apply_device<double2>(p, p->stC, p->stD, p->pend_dtype, p->sol, p->stA, p->pend_diff_dtype, nullptr, false, nullptr);
+        if (rc) return rc;
+        const size_t ob = (size_t)p->d.N0 * p->d.N1 * (p->pend_diff_dtype == SFFTB_F64 ? 8 : 4);
+        CK(cudaMemcpyAsync(p->pend_diff, p->stA, ob, cudaMemcpyDeviceToHost, p->stream));
+        if (p->pend_sol) CK(cudaMemcpyAsync(p->pend_sol, p->sol, sizeof(double) * p->d.NEQ, cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+    }
+    return collect_timings(p, true, true);
 }
 
 // ---- shared-template batch path (the reference re-transforms the template for every pair) ------------

@@ -119,6 +119,29 @@ class Plan:
                                   B.F64 if diff.dtype == np.float64 else B.F32))
         return sol, diff
 
+    # ---- asynchronous host-buffer GSS (sfftb_gss_submit / sfftb_gss_finish) -------------------------
+    def gss_submit(self, PixA_I, PixA_J, PixA_mI, PixA_mJ, out_dtype=np.float64, Solution_out=None, DIFF_out=None):
+        """Queue one GSS on host arrays and return at once; gss_finish() waits for it and returns (Solution, DIFF).
+        Arrays are used in place when they are C-contiguous float64 / float32 (pinned memory makes the copies
+        asynchronous); optional preallocated (pinned) outputs may be passed."""
+        self._check_pair(PixA_I, PixA_J, PixA_mI, PixA_mJ)
+        ptrs = [_ptr_of(a) for a in (PixA_I, PixA_J, PixA_mI, PixA_mJ)]
+        if len({(q[1], q[2]) for q in ptrs}) != 1 or ptrs[0][1] != B.MEM_HOST:
+            raise Exception('MeLOn ERROR: gss_submit takes four host arrays of one dtype')
+        sol = np.empty(self.NEQ, np.float64) if Solution_out is None else Solution_out
+        diff = np.empty(self.shape, out_dtype) if DIFF_out is None else DIFF_out
+        dptr = diff.ctypes.data if isinstance(diff, np.ndarray) else diff.data_ptr()
+        sptr = sol.ctypes.data if isinstance(sol, np.ndarray) else sol.data_ptr()
+        ddt = B.F64 if str(diff.dtype).endswith('float64') else B.F32
+        B.check(self._L.sfftb_gss_submit(self._h, ptrs[0][0], ptrs[1][0], ptrs[2][0], ptrs[3][0], ptrs[0][2], sptr, dptr, ddt))
+        self._inflight = (sol, diff, [q[3] for q in ptrs])          # keep the buffers alive until finish
+
+    def gss_finish(self):
+        B.check(self._L.sfftb_gss_finish(self._h))
+        sol, diff, _ = self._inflight
+        self._inflight = None
+        return sol, diff
+
     # ---- shared-template batch path (BASELINE config 4; SURVEY.md 8e) ---------------------------
     def template_prepare(self, PixA_I, PixA_mI):
         """Row spectra of the convolved image (the template when ForceConv='REF') and of its masked version,
