@@ -132,6 +132,12 @@ int  sfftb_gss_template(sfftb_plan* plan, const void* PixA_J, const void* PixA_m
 int  sfftb_realize(sfftb_plan* plan, const double* solution, int sol_memkind, const double* xy, int xy_memkind, int nq,
                    double* kerstack, double* fscal, int out_memkind);
 
+/* Kernel regularisation (sfft/BSplineSFFT.py:3570-3700, REGULARIZE_KERNEL / LAMBDA_REGULARIZE): every following fit solves
+ * (LHMAT + lambda * REGMAT) x = RHb with REGMAT[(k,c),(k',c')] = SCALE^2 * SST[k,k'] * iREG[c,c'] (fill_regmat, :2091-2119).
+ * SST is the (Fij x Fij) Gram matrix of the kernel basis at the regularisation coordinates, iREG the (Fab x Fab)
+ * Laplacian penalty in the modified-delta basis; host pointers, row-major.  SST == NULL switches it off. */
+int  sfftb_set_regularizer(sfftb_plan* plan, const double* SST, const double* iREG, double lambda);
+
 /* Parity hook: the full (NEQ x NEQ) LHMAT and (NEQ) RHb of the last fit, before stripe removal,
  * in the reference's layout (what FillLS_* produce, SFFTSubtract.py:244-380).  Host pointers. */
 int  sfftb_export_normal_eq(sfftb_plan* plan, double* LHMAT, double* RHb);

@@ -1,0 +1,216 @@
+"""
+sfft/BSplineSFFT.py on the B200 core -- the part of it the native plan covers today.
+
+`BSplineSFFT.py` generalises sfftcore: the kernel, the scaling and the background may vary as total-degree
+polynomials or as tensor-product B-splines, the photometric scaling can be entangled with the kernel or separate
+(constant / varying), and the kernel can be regularised by a Laplacian penalty (:3570-3700).  This module keeps its
+call signatures (`SingleSFFTConfigure.SSC` :2538, `ElementalSFFTSubtract.ESS`, `GeneralSFFTSubtract.GSS` :3882,
+`BSpline_Packet.BSP` :3969) and serves:
+
+  * KerSpType = BkgSpType = 'Polynomial', degrees 0..3;
+  * SEPARATE_SCALING=False (ENTANGLED == sfftcore ConstPhotRatio=False) and SEPARATE_SCALING=True with
+    ScaSpDegree=0 (SEPARATE-CONSTANT == ConstPhotRatio=True: for a polynomial kernel TweakLS drops the stripes, :2204-2233);
+  * REGULARIZE_KERNEL with XY_REGULARIZE / WEIGHT_REGULARIZE / LAMBDA_REGULARIZE / IGNORE_LAPLACIAN_KERCENT:
+    the two Kronecker factors of REGMAT are built here and added inside the native matrix fill (sfftb_set_regularizer).
+
+B-spline bases and SEPARATE-VARYING scaling are refused with a clear error: their CUDA path is not built yet
+(the CPU oracle and golden fixtures for them are in oracle/bspline_oracle.py, tests/golden).
+"""
+import os.path as pa
+import time
+import numpy as np
+
+from . import fitsio
+from .plan import Plan
+from .sfftcore.SFFTConfigure import _current_device
+from .sfftcore.SFFTSubtract import ElementalSFFTSubtract as _ESS, GeneralSFFTSubtract as _GSS
+
+__all__ = ['SingleSFFTConfigure', 'ElementalSFFTSubtract', 'GeneralSFFTSubtract', 'BSpline_Packet', 'regularizer_factors']
+
+
+def _laplacian_penalty(w0, w1, IGNORE_LAPLACIAN_KERCENT):
+    """iREGMAT (Fab, Fab) of fill_iregmat (:2051-2086): 2 M^T (Lap^T Lap) M with Lap the 5-point Laplacian on the
+    (L0, L1) kernel stamp (neighbour count on the diagonal, -1 on the 4-neighbours, zero-filled border, :3641-3666) and
+    M the map from modified-delta coefficients to kernel pixels (every non-centre tap also subtracts from the centre)."""
+    L0, L1 = 2 * w0 + 1, 2 * w1 + 1
+    Fab = L0 * L1
+    rr, cc = np.divmod(np.arange(Fab), L1)
+    adj = ((np.abs(rr[:, None] - rr[None, :]) + np.abs(cc[:, None] - cc[None, :])) == 1)
+    LAP = np.diag(adj.sum(axis=1).astype(float)) - adj.astype(float)
+    c0 = w0 * L1 + w1
+    if IGNORE_LAPLACIAN_KERCENT:                                                       # :3670-3676
+        LAP[[c0 - L1, c0 - 1, c0, c0 + 1, c0 + L1], :] = 0.0
+    M = np.eye(Fab)
+    M[c0, :] = -1.0
+    M[c0, c0] = 1.0
+    return 2.0 * (M.T @ (LAP.T @ LAP) @ M)
+
+
+def regularizer_factors(N0, N1, w0, w1, DK, XY_REGULARIZE, WEIGHT_REGULARIZE=None, IGNORE_LAPLACIAN_KERCENT=True):
+    """(SST, iREG) with REGMAT = SCALE^2 * kron(SST, iREG) on the kernel block (fill_regmat, :2091-2119), polynomial
+    kernel basis: SST = SPMAT W SPMAT^T, SPMAT[k, n] = cx_n^i cy_n^j at the requested coordinates (:3576-3582, 3624-3633)."""
+    XY = np.asarray(XY_REGULARIZE, float)
+    if XY.ndim != 2 or XY.shape[1] != 2 or XY.shape[0] < 1:
+        raise Exception('MeLOn ERROR: XY_REGULARIZE must have shape (N_points, 2)')
+    cx, cy = XY[:, 0] / N0, XY[:, 1] / N1
+    SP = np.array([cx ** i * cy ** j for i in range(DK + 1) for j in range(DK + 1 - i)])
+    if WEIGHT_REGULARIZE is None:
+        Wd = np.full(XY.shape[0], 1.0 / XY.shape[0])
+    else:
+        Wd = np.asarray(WEIGHT_REGULARIZE, float)
+        if Wd.shape != (XY.shape[0],):
+            raise Exception('MeLOn ERROR: WEIGHT_REGULARIZE must have shape (N_points,)')
+        Wd = Wd / Wd.sum()
+    return (SP * Wd) @ SP.T, _laplacian_penalty(w0, w1, IGNORE_LAPLACIAN_KERCENT)
+
+
+class SingleSFFTConfigure:
+    @staticmethod
+    def SSC(NX, NY, KerHW=8, KerSpType='Polynomial', KerSpDegree=2, KerIntKnotX=[], KerIntKnotY=[],
+            SEPARATE_SCALING=True, ScaSpType='Polynomial', ScaSpDegree=0, ScaIntKnotX=[], ScaIntKnotY=[],
+            BkgSpType='Polynomial', BkgSpDegree=2, BkgIntKnotX=[], BkgIntKnotY=[],
+            REGULARIZE_KERNEL=False, IGNORE_LAPLACIAN_KERCENT=True, XY_REGULARIZE=None, WEIGHT_REGULARIZE=None,
+            LAMBDA_REGULARIZE=1e-6, BACKEND_4SUBTRACT='B200', MAX_THREADS_PER_BLOCK=8,
+            MINIMIZE_GPU_MEMORY_USAGE=False, NUM_CPU_THREADS_4SUBTRACT=8, VERBOSE_LEVEL=2,
+            CUDA_DEVICE=None, STORAGE='fp64'):
+        """Arguments as BSplineSFFT.SingleSFFTConfigure.SSC (:2538-2545); MAX_THREADS_PER_BLOCK, MINIMIZE_GPU_MEMORY_USAGE and
+        NUM_CPU_THREADS_4SUBTRACT are accepted and ignored.  Returns (SFFTParam_dict, SFFTModule_dict) with the keys of
+        :204-273."""
+        if BACKEND_4SUBTRACT not in ('B200', 'Cupy'):
+            raise Exception("MeLOn ERROR: BACKEND_4SUBTRACT=%r is not available in sfft_b200 (use 'B200')" % (BACKEND_4SUBTRACT,))
+        N0, N1, w0, w1 = int(NX), int(NY), int(KerHW), int(KerHW)
+        DK, DB = int(KerSpDegree), int(BkgSpDegree)
+        assert DK >= 0 and DB >= 0                                                       # :33, :79
+        assert KerSpType in ['Polynomial', 'B-Spline'] and BkgSpType in ['Polynomial', 'B-Spline']
+        if SEPARATE_SCALING:
+            DS = int(ScaSpDegree)
+            assert DS >= 0 and ScaSpType in ['Polynomial', 'B-Spline']
+        if not SEPARATE_SCALING:
+            SCALING_MODE = 'ENTANGLED'
+        elif int(ScaSpDegree) == 0:
+            SCALING_MODE = 'SEPARATE-CONSTANT'
+        else:
+            SCALING_MODE = 'SEPARATE-VARYING'
+        if KerSpType != 'Polynomial' or BkgSpType != 'Polynomial':
+            raise Exception('MeLOn ERROR: B-Spline spatial variation is not available in sfft_b200 yet '
+                            '(polynomial kernel / background only)')
+        if SCALING_MODE == 'SEPARATE-VARYING':
+            raise Exception('MeLOn ERROR: SEPARATE-VARYING scaling (ScaSpDegree > 0) is not available in sfft_b200 yet')
+        if DK > 3 or DB > 3:
+            raise Exception('MeLOn ERROR: polynomial degrees above 3 are not available in sfft_b200')
+        if VERBOSE_LEVEL in [1, 2]:
+            print('\n --//--//--//--//-- TRIGGER SFFT COMPILATION --//--//--//--//-- ')
+            print('\n ---//--- Polynomial Kernel | KerSpDegree %d | KerHW %d ---//---' % (DK, w0))
+            print('\n ---//--- [%s] Polynomial Scaling ---//---' % SCALING_MODE)
+            print('\n ---//--- Polynomial Background | BkgSpDegree %d ---//---' % DB)
+        L0, L1 = 2 * w0 + 1, 2 * w1 + 1
+        Fab = L0 * L1
+        Fij, Fpq = ((DK + 1) * (DK + 2)) // 2, ((DB + 1) * (DB + 2)) // 2
+        Fijab, NEQ = Fij * Fab, Fij * Fab + Fpq
+        NEQt = NEQ - Fij + 1 if SCALING_MODE == 'SEPARATE-CONSTANT' else NEQ            # :199-200
+        SCALE = np.float64(1 / (N0 * N1))
+        P = dict(KerHW=KerHW, KerSpType=KerSpType, KerSpDegree=KerSpDegree, KerIntKnotX=KerIntKnotX, KerIntKnotY=KerIntKnotY,
+                 SEPARATE_SCALING=SEPARATE_SCALING, BkgSpType=BkgSpType, BkgSpDegree=BkgSpDegree, BkgIntKnotX=BkgIntKnotX,
+                 BkgIntKnotY=BkgIntKnotY, REGULARIZE_KERNEL=REGULARIZE_KERNEL, IGNORE_LAPLACIAN_KERCENT=IGNORE_LAPLACIAN_KERCENT,
+                 XY_REGULARIZE=XY_REGULARIZE, WEIGHT_REGULARIZE=WEIGHT_REGULARIZE, LAMBDA_REGULARIZE=LAMBDA_REGULARIZE,
+                 MAX_THREADS_PER_BLOCK=MAX_THREADS_PER_BLOCK, MINIMIZE_GPU_MEMORY_USAGE=MINIMIZE_GPU_MEMORY_USAGE,
+                 N0=N0, N1=N1, w0=w0, w1=w1, DK=DK, DB=DB, SCALE=SCALE, SCALE_L=np.float64(1 / SCALE), L0=L0, L1=L1, Fab=Fab,
+                 Fi=-1, Fj=-1, Fij=Fij, Fp=-1, Fq=-1, Fpq=Fpq, Fijab=Fijab, FOMG=Fij ** 2, FGAM=Fij * Fpq, FTHE=Fij,
+                 FPSI=Fpq * Fij, FPHI=Fpq ** 2, FDEL=Fpq, NEQ=NEQ, NEQt=NEQt, SCALING_MODE=SCALING_MODE)
+        if SEPARATE_SCALING:
+            P.update(ScaSpType=ScaSpType, ScaSpDegree=ScaSpDegree, ScaIntKnotX=ScaIntKnotX, ScaIntKnotY=ScaIntKnotY, DS=DS)
+        device = _current_device() if CUDA_DEVICE is None else int(CUDA_DEVICE)
+        plan = Plan(N0, N1, w0, w1, DK, DB, SCALING_MODE == 'SEPARATE-CONSTANT', device=device, storage=STORAGE)
+        if REGULARIZE_KERNEL:
+            if XY_REGULARIZE is None:
+                raise Exception('MeLOn ERROR: REGULARIZE_KERNEL needs XY_REGULARIZE')
+            SST, iREG = regularizer_factors(N0, N1, w0, w1, DK, XY_REGULARIZE, WEIGHT_REGULARIZE, IGNORE_LAPLACIAN_KERCENT)
+            plan.set_regularizer(SST, iREG, float(LAMBDA_REGULARIZE))
+        if VERBOSE_LEVEL in [1, 2]:
+            print('\n --//--//--//--//-- EXIT SFFT COMPILATION --//--//--//--//-- ')
+        return (P, {'BACKEND': 'B200', 'plan': plan, 'device': device, 'storage': STORAGE})
+
+
+class ElementalSFFTSubtract:
+    ESS = staticmethod(_ESS.ESS)            # same contract as sfftcore's ESS once the plan exists (:3855-3877)
+
+
+class GeneralSFFTSubtract:
+    GSS = staticmethod(_GSS.GSS)            # :3882-3964 (fit on the masked pair, subtract, optional contamination mask)
+
+
+def _read_T(path):
+    return np.ascontiguousarray(fitsio.getdata(path).T, np.float64)
+
+
+class BSpline_Packet:
+    @staticmethod
+    def BSP(FITS_REF, FITS_SCI, FITS_mREF, FITS_mSCI, FITS_DIFF=None, FITS_Solution=None, ForceConv='REF', GKerHW=8,
+            KerSpType='Polynomial', KerSpDegree=2, KerIntKnotX=[], KerIntKnotY=[], SEPARATE_SCALING=True,
+            ScaSpType='Polynomial', ScaSpDegree=0, ScaIntKnotX=[], ScaIntKnotY=[], BkgSpType='Polynomial', BkgSpDegree=2,
+            BkgIntKnotX=[], BkgIntKnotY=[], REGULARIZE_KERNEL=False, IGNORE_LAPLACIAN_KERCENT=True, XY_REGULARIZE=None,
+            WEIGHT_REGULARIZE=None, LAMBDA_REGULARIZE=1e-6, BACKEND_4SUBTRACT='B200', CUDA_DEVICE_4SUBTRACT='0',
+            MAX_THREADS_PER_BLOCK=8, MINIMIZE_GPU_MEMORY_USAGE=False, NUM_CPU_THREADS_4SUBTRACT=8, VERBOSE_LEVEL=2,
+            STORAGE='fp64'):
+        """FITS in -> FITS out, as BSpline_Packet.BSP (:3969-4260)."""
+        arrays = [_read_T(f) for f in (FITS_REF, FITS_SCI, FITS_mREF, FITS_mSCI)]
+        Solution, PixA_DIFF, SFFTConfig = BSpline_Packet.BSP_arrays(
+            *arrays, ForceConv=ForceConv, GKerHW=GKerHW, KerSpType=KerSpType, KerSpDegree=KerSpDegree,
+            KerIntKnotX=KerIntKnotX, KerIntKnotY=KerIntKnotY, SEPARATE_SCALING=SEPARATE_SCALING, ScaSpType=ScaSpType,
+            ScaSpDegree=ScaSpDegree, ScaIntKnotX=ScaIntKnotX, ScaIntKnotY=ScaIntKnotY, BkgSpType=BkgSpType,
+            BkgSpDegree=BkgSpDegree, BkgIntKnotX=BkgIntKnotX, BkgIntKnotY=BkgIntKnotY, REGULARIZE_KERNEL=REGULARIZE_KERNEL,
+            IGNORE_LAPLACIAN_KERCENT=IGNORE_LAPLACIAN_KERCENT, XY_REGULARIZE=XY_REGULARIZE, WEIGHT_REGULARIZE=WEIGHT_REGULARIZE,
+            LAMBDA_REGULARIZE=LAMBDA_REGULARIZE, BACKEND_4SUBTRACT=BACKEND_4SUBTRACT, CUDA_DEVICE_4SUBTRACT=CUDA_DEVICE_4SUBTRACT,
+            VERBOSE_LEVEL=VERBOSE_LEVEL, STORAGE=STORAGE, _return_config=True)
+        if FITS_DIFF is not None:                                                      # :4218-4236
+            cards, _ = fitsio.read_header(FITS_SCI)
+            fitsio.writeto(FITS_DIFF, PixA_DIFF.T, base_cards=cards, updates=[
+                ('NAME_REF', pa.basename(FITS_REF), 'MeLOn: SFFT'), ('NAME_SCI', pa.basename(FITS_SCI), 'MeLOn: SFFT'),
+                ('KERHW', GKerHW, 'MeLOn: SFFT'), ('CONVD', ForceConv, 'MeLOn: SFFT'),
+                ('KSPTYPE', str(KerSpType), 'MeLOn: SFFT'), ('KSPDEG', KerSpDegree, 'MeLOn: SFFT'),
+                ('BSPTYPE', str(BkgSpType), 'MeLOn: SFFT'), ('BSPDEG', BkgSpDegree, 'MeLOn: SFFT'),
+                ('SEPSCA', str(SEPARATE_SCALING), 'MeLOn: SFFT'), ('REGKER', str(REGULARIZE_KERNEL), 'MeLOn: SFFT')])
+        if FITS_Solution is not None:                                                  # :4238-4258
+            P = SFFTConfig[0]
+            ups = [(k, P[v], 'MeLOn: SFFT') for k, v in (('N0', 'N0'), ('N1', 'N1'), ('DK', 'DK'), ('DB', 'DB'), ('L0', 'L0'),
+                   ('L1', 'L1'), ('FIJ', 'Fij'), ('FAB', 'Fab'), ('FPQ', 'Fpq'), ('FIJAB', 'Fijab'))]
+            fitsio.writeto(FITS_Solution, Solution.reshape((-1, 1)).T, base_cards=None, updates=ups)
+        return Solution, PixA_DIFF
+
+    @staticmethod
+    def BSP_arrays(PixA_REF, PixA_SCI, PixA_mREF, PixA_mSCI, ForceConv='REF', GKerHW=8, CUDA_DEVICE_4SUBTRACT='0',
+                   BACKEND_4SUBTRACT='B200', VERBOSE_LEVEL=2, STORAGE='fp64', _return_config=False, **ssc_kwargs):
+        """The array-level body of BSP (:4100-4216): NaN-union fill from the masked images, role swap, sign flip."""
+        PixA_REF, PixA_SCI = np.asarray(PixA_REF, np.float64), np.asarray(PixA_SCI, np.float64)
+        PixA_mREF, PixA_mSCI = np.asarray(PixA_mREF, np.float64), np.asarray(PixA_mSCI, np.float64)
+        NaNmask_U = None
+        NaNmask_REF, NaNmask_SCI = np.isnan(PixA_REF), np.isnan(PixA_SCI)
+        if NaNmask_REF.any() or NaNmask_SCI.any():
+            NaNmask_U = np.logical_or(NaNmask_REF, NaNmask_SCI)
+        assert np.sum(np.isnan(PixA_mREF)) == 0
+        assert np.sum(np.isnan(PixA_mSCI)) == 0
+        assert ForceConv in ['REF', 'SCI']
+        t0 = time.time()
+        SFFTConfig = SingleSFFTConfigure.SSC(NX=PixA_REF.shape[0], NY=PixA_REF.shape[1], KerHW=GKerHW,
+                                             BACKEND_4SUBTRACT=BACKEND_4SUBTRACT, VERBOSE_LEVEL=VERBOSE_LEVEL,
+                                             CUDA_DEVICE=int(CUDA_DEVICE_4SUBTRACT), STORAGE=STORAGE, **ssc_kwargs)
+        if VERBOSE_LEVEL in [1, 2]:
+            print('\nMeLOn Report: FUNCTION COMPILATIONS OF SFFT-SUBTRACTION TAKES [%.3f s] \n' % (time.time() - t0))
+        if ForceConv == 'REF':
+            PixA_mI, PixA_mJ, PixA_I, PixA_J = PixA_mREF, PixA_mSCI, PixA_REF, PixA_SCI
+        else:
+            PixA_mI, PixA_mJ, PixA_I, PixA_J = PixA_mSCI, PixA_mREF, PixA_SCI, PixA_REF
+        if NaNmask_U is not None:
+            PixA_I, PixA_J = PixA_I.copy(), PixA_J.copy()
+            PixA_I[NaNmask_U] = PixA_mI[NaNmask_U]
+            PixA_J[NaNmask_U] = PixA_mJ[NaNmask_U]
+        Solution, PixA_DIFF = GeneralSFFTSubtract.GSS(PixA_I=PixA_I, PixA_J=PixA_J, PixA_mI=PixA_mI, PixA_mJ=PixA_mJ,
+                                                      SFFTConfig=SFFTConfig, ContamMask_I=None,
+                                                      BACKEND_4SUBTRACT=BACKEND_4SUBTRACT, VERBOSE_LEVEL=VERBOSE_LEVEL)[:2]
+        if NaNmask_U is not None:
+            PixA_DIFF[NaNmask_U] = np.nan
+        if ForceConv == 'SCI':
+            PixA_DIFF = -PixA_DIFF
+        if _return_config:
+            return Solution, PixA_DIFF, SFFTConfig
+        return Solution, PixA_DIFF

@@ -290,6 +290,9 @@ struct FillArgs {
     int nl0, nl1, nlj0, nlj1;
     double invN, invN2, invN3;
     const double* R; const double* RJ; const double* RT; const double* RJT; const double* PHI;
+    // kernel regulariser (sfft/BSplineSFFT.py:3570-3700): LHMAT[(k,c),(k',c')] += regw * SST[k,k'] * iREG[c,c'],
+    // regw = LAMBDA_REGULARIZE * SCALE^2; null pointers = off
+    const double* SST; const double* iREG; double regw;
 };
 
 __device__ __forceinline__ double fill_R(const FillArgs& f, int A, int B, int m0, int m1) {
@@ -309,7 +312,9 @@ __device__ double fill_lh_entry(const FillArgs& f, int fr, int fc) {
         if (nz) v -= fill_R(f, A, B, a8, b8);
         if (nz8) v -= fill_R(f, A, B, -a0, -b0);
         if (nz && nz8) v += fill_R(f, A, B, 0, 0);
-        return v * f.invN3;
+        v *= f.invN3;
+        if (f.SST) v = fma(f.regw * f.SST[A * f.Fij + B], f.iREG[(size_t)ab8 * f.Fab + ab], v);
+        return v;
     }
     if (fr >= f.Fijab && fc >= f.Fijab) return f.PHI[(fr - f.Fijab) * f.Fpq + (fc - f.Fijab)] * f.invN;
     if (fr >= f.Fijab) { int t = fr; fr = fc; fc = t; }

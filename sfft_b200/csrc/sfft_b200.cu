@@ -93,6 +93,7 @@ struct sfftb_plan {
     unsigned* substFlags;        // 2 * nblk epoch tags of the dataflow substitution kernel
     unsigned substEpoch;
     int subst_ok;
+    double *regSST, *regI;       // kernel regulariser factors (sfftb_set_regularizer)
     cd *bluTw, *bluC, *bluB;     // Bluestein tables of the generic row pass (row lengths with a prime factor > 13)
     ulonglong2* substMsg;        // 2 * nblk * 64 {value | epoch} messages of chol_subst2_kernel
     int chol_coop;
@@ -327,7 +328,7 @@ static int plan_free(sfftb_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     void* ptrs[] = {p->vt8_8, p->vt64_8, p->vt64_4, p->vt256_4, p->vt512_4, p->tabA, p->tabB_row, p->tabC_row, p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
-                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->substMsg, p->bluTw, p->bluC, p->bluB, p->firTaps, p->firCA, p->tstate, p->stC, p->stD};
+                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->substMsg, p->regSST, p->regI, p->bluTw, p->bluC, p->bluB, p->firTaps, p->firCA, p->tstate, p->stC, p->stD};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->info_h) cudaFreeHost(p->info_h);
     for (int k = 0; k < EV_COUNT; ++k) if (p->ev[k]) cudaEventDestroy(p->ev[k]);
@@ -1488,6 +1489,25 @@ extern "C" int sfftb_gss_template(sfftb_plan* p, const void* J, const void* mJ, 
     }
     if ((rc = copy_out(p, solution, sol_memkind, p->sol, sizeof(double) * p->d.NEQ))) return rc;
     CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+// Kernel regularisation of sfft/BSplineSFFT.py:3570-3700: LHMAT += LAMBDA * REGMAT with the Kronecker structure
+// REGMAT[(k,c),(k',c')] = SCALE^2 * SST[k,k'] * iREG[c,c'] (fill_regmat, :2091-2119).  The two small factors are kept on
+// the device and added inside the matrix fill.  SST == NULL switches it off.
+extern "C" int sfftb_set_regularizer(sfftb_plan* p, const double* SST, const double* iREG, double lambda) {
+    if (!p) return fail(SFFTB_EINVAL, "null plan");
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    p->factor_cached = 0;
+    if (!SST || !iREG) { p->fill.SST = nullptr; p->fill.iREG = nullptr; p->fill.regw = 0.0; return 0; }
+    if (!(lambda >= 0.0)) return fail(SFFTB_EINVAL, "LAMBDA_REGULARIZE must be >= 0");
+    const size_t nS = (size_t)p->d.Fij * p->d.Fij, nI = (size_t)p->d.Fab * p->d.Fab;
+    if (!p->regSST) { CK(cudaMalloc(&p->regSST, sizeof(double) * nS)); CK(cudaMalloc(&p->regI, sizeof(double) * nI)); }
+    CK(cudaMemcpy(p->regSST, SST, sizeof(double) * nS, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->regI, iREG, sizeof(double) * nI, cudaMemcpyHostToDevice));
+    const double N = (double)p->d.N0 * (double)p->d.N1;
+    p->fill.SST = p->regSST; p->fill.iREG = p->regI; p->fill.regw = lambda / (N * N);
     return 0;
 }
 

@@ -119,6 +119,18 @@ class Plan:
                                   B.F64 if diff.dtype == np.float64 else B.F32))
         return sol, diff
 
+    def set_regularizer(self, SST=None, iREG=None, lam=0.0):
+        """Kernel regularisation (BSplineSFFT.py:3570-3700): LHMAT += lam * SCALE^2 * kron(SST, iREG) on the kernel block."""
+        if SST is None:
+            B.check(self._L.sfftb_set_regularizer(self._h, None, None, 0.0))
+            return
+        S = np.ascontiguousarray(SST, np.float64)
+        R = np.ascontiguousarray(iREG, np.float64)
+        d = self.dims
+        if S.shape != (d['Fij'], d['Fij']) or R.shape != (d['Fab'], d['Fab']):
+            raise Exception('MeLOn ERROR: regulariser factors must have shapes (Fij, Fij) and (Fab, Fab)')
+        B.check(self._L.sfftb_set_regularizer(self._h, S.ctypes.data, R.ctypes.data, float(lam)))
+
     # ---- asynchronous host-buffer GSS (sfftb_gss_submit / sfftb_gss_finish) -------------------------
     def gss_submit(self, PixA_I, PixA_J, PixA_mI, PixA_mJ, out_dtype=np.float64, Solution_out=None, DIFF_out=None):
         """Queue one GSS on host arrays and return at once; gss_finish() waits for it and returns (Solution, DIFF).
