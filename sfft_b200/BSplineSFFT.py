@@ -14,7 +14,7 @@ call signatures (`SingleSFFTConfigure.SSC` :2538, `ElementalSFFTSubtract.ESS`, `
     the two Kronecker factors of REGMAT are built here and added inside the native matrix fill (sfftb_set_regularizer).
 
 B-spline bases and SEPARATE-VARYING scaling are refused with a clear error: their CUDA path is not built yet
-(the CPU oracle and golden fixtures for them are in oracle/bspline_oracle.py, tests/golden).
+(DESIGN.md section 7).
 """
 import os.path as pa
 import time
