@@ -61,7 +61,10 @@ typedef struct sfftb_config {
     int const_phot_ratio;  /* ConstPhotRatio */
     int storage;           /* SFFTB_STORE_F64 | SFFTB_STORE_F32 */
     int fold;              /* column-pass fold factor V (0 = choose automatically) */
-    int reserved[6];       /* must be zero */
+    int sca_degree;        /* with const_phot_ratio: 0 = one constant photometric scaling (SEPARATE-CONSTANT of
+                              sfft/BSplineSFFT.py:77-86; sfftcore's ConstPhotRatio=True), DS > 0 = the scaling varies as a
+                              polynomial of degree DS <= DK (SEPARATE-VARYING, :176-190, :3733-3747) */
+    int reserved[5];       /* must be zero */
 } sfftb_config;
 
 /* Sizes derived exactly as SFFTParam_dict (SFFTConfigure.py:35-75). */

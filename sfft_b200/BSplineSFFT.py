@@ -8,13 +8,15 @@ call signatures (`SingleSFFTConfigure.SSC` :2538, `ElementalSFFTSubtract.ESS`, `
 `BSpline_Packet.BSP` :3969) and serves:
 
   * KerSpType = BkgSpType = 'Polynomial', degrees 0..3;
-  * SEPARATE_SCALING=False (ENTANGLED == sfftcore ConstPhotRatio=False) and SEPARATE_SCALING=True with
-    ScaSpDegree=0 (SEPARATE-CONSTANT == ConstPhotRatio=True: for a polynomial kernel TweakLS drops the stripes, :2204-2233);
+  * SEPARATE_SCALING=False (ENTANGLED == sfftcore ConstPhotRatio=False), SEPARATE_SCALING=True with
+    ScaSpDegree=0 (SEPARATE-CONSTANT == ConstPhotRatio=True: for a polynomial kernel TweakLS drops the stripes, :2204-2233)
+    and with a polynomial ScaSpDegree in 1..KerSpDegree (SEPARATE-VARYING: the centre-tap unknown of plane k scales the
+    image times the k-th scaling basis function, :2487-2495; planes beyond ScaFij lose that unknown, :3733-3747);
   * REGULARIZE_KERNEL with XY_REGULARIZE / WEIGHT_REGULARIZE / LAMBDA_REGULARIZE / IGNORE_LAPLACIAN_KERCENT:
     the two Kronecker factors of REGMAT are built here and added inside the native matrix fill (sfftb_set_regularizer).
 
-B-spline bases and SEPARATE-VARYING scaling are refused with a clear error: their CUDA path is not built yet
-(DESIGN.md section 7).
+B-spline bases (kernel, scaling or background) and the regulariser combined with SEPARATE-VARYING scaling are refused with
+a clear error: their CUDA path is not built yet.
 """
 import os.path as pa
 import time
@@ -94,8 +96,15 @@ class SingleSFFTConfigure:
         if KerSpType != 'Polynomial' or BkgSpType != 'Polynomial':
             raise Exception('MeLOn ERROR: B-Spline spatial variation is not available in sfft_b200 yet '
                             '(polynomial kernel / background only)')
+        ScaFij = None
         if SCALING_MODE == 'SEPARATE-VARYING':
-            raise Exception('MeLOn ERROR: SEPARATE-VARYING scaling (ScaSpDegree > 0) is not available in sfft_b200 yet')
+            if ScaSpType != 'Polynomial':
+                raise Exception('MeLOn ERROR: B-Spline spatial variation is not available in sfft_b200 yet '
+                                '(polynomial scaling only)')
+            ScaFij = ((DS + 1) * (DS + 2)) // 2
+            assert ScaFij <= ((DK + 1) * (DK + 2)) // 2                                 # :190
+            if REGULARIZE_KERNEL:
+                raise Exception('MeLOn ERROR: REGULARIZE_KERNEL with SEPARATE-VARYING scaling is not available in sfft_b200 yet')
         if DK > 3 or DB > 3:
             raise Exception('MeLOn ERROR: polynomial degrees above 3 are not available in sfft_b200')
         if VERBOSE_LEVEL in [1, 2]:
@@ -108,6 +117,8 @@ class SingleSFFTConfigure:
         Fij, Fpq = ((DK + 1) * (DK + 2)) // 2, ((DB + 1) * (DB + 2)) // 2
         Fijab, NEQ = Fij * Fab, Fij * Fab + Fpq
         NEQt = NEQ - Fij + 1 if SCALING_MODE == 'SEPARATE-CONSTANT' else NEQ            # :199-200
+        if SCALING_MODE == 'SEPARATE-VARYING':
+            NEQt = NEQ - Fij + ScaFij                                                   # :201-202
         SCALE = np.float64(1 / (N0 * N1))
         P = dict(KerHW=KerHW, KerSpType=KerSpType, KerSpDegree=KerSpDegree, KerIntKnotX=KerIntKnotX, KerIntKnotY=KerIntKnotY,
                  SEPARATE_SCALING=SEPARATE_SCALING, BkgSpType=BkgSpType, BkgSpDegree=BkgSpDegree, BkgIntKnotX=BkgIntKnotX,
@@ -119,8 +130,11 @@ class SingleSFFTConfigure:
                  FPSI=Fpq * Fij, FPHI=Fpq ** 2, FDEL=Fpq, NEQ=NEQ, NEQt=NEQt, SCALING_MODE=SCALING_MODE)
         if SEPARATE_SCALING:
             P.update(ScaSpType=ScaSpType, ScaSpDegree=ScaSpDegree, ScaIntKnotX=ScaIntKnotX, ScaIntKnotY=ScaIntKnotY, DS=DS)
+        if SCALING_MODE == 'SEPARATE-VARYING':
+            P.update(ScaFi=-1, ScaFj=-1, ScaFij=ScaFij)
         device = _current_device() if CUDA_DEVICE is None else int(CUDA_DEVICE)
-        plan = Plan(N0, N1, w0, w1, DK, DB, SCALING_MODE == 'SEPARATE-CONSTANT', device=device, storage=STORAGE)
+        plan = Plan(N0, N1, w0, w1, DK, DB, SCALING_MODE != 'ENTANGLED', device=device, storage=STORAGE,
+                    sca_degree=DS if SCALING_MODE == 'SEPARATE-VARYING' else 0)
         if REGULARIZE_KERNEL:
             if XY_REGULARIZE is None:
                 raise Exception('MeLOn ERROR: REGULARIZE_KERNEL needs XY_REGULARIZE')

@@ -26,7 +26,7 @@ EXPORTS = ['sfftb_version', 'sfftb_last_error', 'sfftb_plan_create', 'sfftb_plan
 class Config(C.Structure):
     _fields_ = [('device', C.c_int), ('N0', C.c_int), ('N1', C.c_int), ('w0', C.c_int), ('w1', C.c_int),
                 ('DK', C.c_int), ('DB', C.c_int), ('const_phot_ratio', C.c_int), ('storage', C.c_int),
-                ('fold', C.c_int), ('reserved', C.c_int * 6)]
+                ('fold', C.c_int), ('sca_degree', C.c_int), ('reserved', C.c_int * 5)]
 
 
 class Dims(C.Structure):

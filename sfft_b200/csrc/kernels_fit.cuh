@@ -293,12 +293,27 @@ struct FillArgs {
     // kernel regulariser (sfft/BSplineSFFT.py:3570-3700): LHMAT[(k,c),(k',c')] += regw * SST[k,k'] * iREG[c,c'],
     // regw = LAMBDA_REGULARIZE * SCALE^2; null pointers = off
     const double* SST; const double* iREG; double regw;
+    // SEPARATE-VARYING scaling with polynomial bases (sfft/BSplineSFFT.py:2487-2495, 3733-3747): the centre-tap unknown of
+    // plane k scales the image times the k-th SCALING basis function, i.e. the unshifted plane sca[k] of the kernel's own
+    // plane set (-1: no such unknown; its row / column of the exported LHMAT is zero like the reference's placeholder)
+    int sca_on; signed char sca[16];
 };
 
 __device__ __forceinline__ double fill_R(const FillArgs& f, int A, int B, int m0, int m1) {
     if (A > B) { int t = A; A = B; B = t; m0 = -m0; m1 = -m1; }
     const int pidx = A * f.Fij - (A * (A - 1)) / 2 + (B - A);
     return f.R[((size_t)pidx * f.nl0 + (m0 + 2 * f.w0)) * f.nl1 + (m1 + 2 * f.w1)];
+}
+
+__device__ __forceinline__ double fill_lh_kernel_block(const FillArgs& f, int A, int B, int Ak, int Bk, int ab8, int ab,
+                                                        int a8, int b8, int a0, int b0, bool nz8, bool nz) {
+    double v = fill_R(f, A, B, a8 - a0, b8 - b0);
+    if (nz) v -= fill_R(f, A, B, a8, b8);
+    if (nz8) v -= fill_R(f, A, B, -a0, -b0);
+    if (nz && nz8) v += fill_R(f, A, B, 0, 0);
+    v *= f.invN3;
+    if (f.SST) v = fma(f.regw * f.SST[Ak * f.Fij + Bk], f.iREG[(size_t)ab8 * f.Fab + ab], v);
+    return v;
 }
 
 __device__ double fill_lh_entry(const FillArgs& f, int fr, int fc) {
@@ -308,19 +323,23 @@ __device__ double fill_lh_entry(const FillArgs& f, int fr, int fc) {
         const int a8 = ab8 / f.L1 - f.w0, b8 = ab8 % f.L1 - f.w1;
         const int a0 = ab / f.L1 - f.w0, b0 = ab % f.L1 - f.w1;
         const bool nz8 = (a8 != 0) || (b8 != 0), nz = (a0 != 0) || (b0 != 0);
-        double v = fill_R(f, A, B, a8 - a0, b8 - b0);
-        if (nz) v -= fill_R(f, A, B, a8, b8);
-        if (nz8) v -= fill_R(f, A, B, -a0, -b0);
-        if (nz && nz8) v += fill_R(f, A, B, 0, 0);
-        v *= f.invN3;
-        if (f.SST) v = fma(f.regw * f.SST[A * f.Fij + B], f.iREG[(size_t)ab8 * f.Fab + ab], v);
-        return v;
+        const int Ak = A, Bk = B;                      // kernel-plane indices (the regulariser acts on those)
+        int Ap = A, Bp = B;
+        if (f.sca_on) {
+            if (!nz8) Ap = f.sca[A];
+            if (!nz) Bp = f.sca[B];
+            if (Ap < 0 || Bp < 0) return 0.0;
+        }
+        return fill_lh_kernel_block(f, Ap, Bp, Ak, Bk, ab8, ab, a8, b8, a0, b0, nz8, nz);
     }
+
     if (fr >= f.Fijab && fc >= f.Fijab) return f.PHI[(fr - f.Fijab) * f.Fpq + (fc - f.Fijab)] * f.invN;
     if (fr >= f.Fijab) { int t = fr; fr = fc; fc = t; }
-    const int A = fr / f.Fab, ab8 = fr - A * f.Fab;
+    int A = fr / f.Fab;
+    const int ab8 = fr - A * f.Fab;
     const int a8 = ab8 / f.L1, b8 = ab8 % f.L1;
     const int pq = fc - f.Fijab;
+    if (f.sca_on && a8 == f.w0 && b8 == f.w1) { A = f.sca[A]; if (A < 0) return 0.0; }
     const double* T = f.RT + ((size_t)A * f.Fpq + pq) * f.nlj0 * f.nlj1;
     double v = T[a8 * f.nlj1 + b8];
     if (a8 != f.w0 || b8 != f.w1) v -= T[f.w0 * f.nlj1 + f.w1];
@@ -329,8 +348,10 @@ __device__ double fill_lh_entry(const FillArgs& f, int fr, int fc) {
 
 __device__ double fill_rhs_entry(const FillArgs& f, int fr) {
     if (fr >= f.Fijab) return f.RJT[fr - f.Fijab] * f.invN;
-    const int A = fr / f.Fab, ab = fr - A * f.Fab;
+    int A = fr / f.Fab;
+    const int ab = fr - A * f.Fab;
     const int a0 = ab / f.L1, b0 = ab % f.L1;
+    if (f.sca_on && a0 == f.w0 && b0 == f.w1) { A = f.sca[A]; if (A < 0) return 0.0; }
     const double* T = f.RJ + (size_t)A * f.nlj0 * f.nlj1;
     double v = T[a0 * f.nlj1 + b0];
     if (a0 != f.w0 || b0 != f.w1) v -= T[f.w0 * f.nlj1 + f.w1];

@@ -93,6 +93,8 @@ struct sfftb_plan {
     unsigned* substFlags;        // 2 * nblk epoch tags of the dataflow substitution kernel
     unsigned substEpoch;
     int subst_ok;
+    int sca_n;                   // SEPARATE-VARYING polynomial scaling: number of scaling basis functions (0 = off)
+    double* solEff;              // solution with the centre taps moved onto the planes of the scaling basis (apply step)
     double *regSST, *regI;       // kernel regulariser factors (sfftb_set_regularizer)
     cd *bluTw, *bluC, *bluB;     // Bluestein tables of the generic row pass (row lengths with a prime factor > 13)
     ulonglong2* substMsg;        // 2 * nblk * 64 {value | epoch} messages of chol_subst2_kernel
@@ -328,7 +330,7 @@ static int plan_free(sfftb_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     void* ptrs[] = {p->vt8_8, p->vt64_8, p->vt64_4, p->vt256_4, p->vt512_4, p->tabA, p->tabB_row, p->tabC_row, p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
-                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->substMsg, p->regSST, p->regI, p->bluTw, p->bluC, p->bluB, p->firTaps, p->firCA, p->tstate, p->stC, p->stD};
+                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->substMsg, p->solEff, p->regSST, p->regI, p->bluTw, p->bluC, p->bluB, p->firTaps, p->firCA, p->tstate, p->stC, p->stD};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->info_h) cudaFreeHost(p->info_h);
     for (int k = 0; k < EV_COUNT; ++k) if (p->ev[k]) cudaEventDestroy(p->ev[k]);
@@ -370,7 +372,12 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
     d.L0 = 2 * d.w0 + 1; d.L1 = 2 * d.w1 + 1; d.Fab = d.L0 * d.L1;
     d.Fij = (d.DK + 1) * (d.DK + 2) / 2; d.Fpq = (d.DB + 1) * (d.DB + 2) / 2;
     d.Fijab = d.Fij * d.Fab; d.NEQ = d.Fijab + d.Fpq;
-    d.NEQ_FSfree = cfg->const_phot_ratio ? d.NEQ - (d.Fij - 1) : d.NEQ;
+    // sca_degree: with const_phot_ratio set, 0 ties the centre taps to ONE constant (stripes dropped) and
+    // DS > 0 gives them their own polynomial of degree DS <= DK (SEPARATE-VARYING, sfft/BSplineSFFT.py:77-86, 176-190)
+    const int DS = cfg->const_phot_ratio ? cfg->sca_degree : 0;
+    if (DS < 0 || DS > d.DK) return fail(SFFTB_EINVAL, "scaling degree %d must lie in 0..KerPolyOrder", DS);
+    p->sca_n = DS > 0 ? (DS + 1) * (DS + 2) / 2 : 0;
+    d.NEQ_FSfree = cfg->const_phot_ratio ? d.NEQ - (d.Fij - (p->sca_n ? p->sca_n : 1)) : d.NEQ;
     const int N0 = d.N0, N1 = d.N1, NH = N1 / 2 + 1;
     const size_t csz = cfg->storage == SFFTB_STORE_F32 ? sizeof(float2) : sizeof(double2);
 
@@ -525,7 +532,7 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
             bool forbidden = false;
             if (cfg->const_phot_ratio && k < d.Fijab) {
                 const int A = k / d.Fab, ab = k % d.Fab;
-                forbidden = (A >= 1) && (ab == d.w0 * d.L1 + d.w1);
+                forbidden = (A >= (p->sca_n ? p->sca_n : 1)) && (ab == d.w0 * d.L1 + d.w1);
             }
             if (!forbidden) idx.push_back(k);
         }
@@ -574,6 +581,15 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
     const double N = (double)N0 * (double)N1;
     f.invN = 1.0 / N; f.invN2 = 1.0 / (N * N); f.invN3 = 1.0 / (N * N * N);
     f.R = p->R; f.RJ = p->RJ; f.RT = p->RT; f.RJT = p->RJT; f.PHI = p->PHI;
+    f.sca_on = p->sca_n > 0 ? 1 : 0;
+    memset(f.sca, 0xff, sizeof f.sca);
+    if (p->sca_n) {
+        // k-th scaling basis function (i, j), enumerated like the kernel's but up to degree DS (ScaREF_ij, :2779-2786)
+        int k = 0;
+        for (int i = 0; i <= DS; ++i)
+            for (int j = 0; j <= DS - i; ++j) f.sca[k++] = (signed char)p->cfit.plane_of[i][j];
+        CK(cudaMalloc(&p->solEff, sizeof(double) * (size_t)d.NEQ));
+    }
 
     // ---- kernel attributes ----
     const bool f32 = cfg->storage == SFFTB_STORE_F32;
@@ -1113,11 +1129,33 @@ static int check_solver(sfftb_plan* p) {
     return 1;
 }
 
+// SEPARATE-VARYING scaling: the centre-tap coefficient of plane k multiplies the image times the k-th scaling basis
+// function, which is the unshifted plane sca[k] of the kernel's plane set.  Moving those coefficients onto the centre
+// taps of their planes turns the model into the standard form the FIR apply evaluates (Construct_FDIFF, :2487-2507).
+__global__ void sca_remap_kernel(FillArgs f, int NEQ, const double* __restrict__ sol, double* __restrict__ eff) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= NEQ) return;
+    double v = sol[k];
+    const int c0 = f.w0 * f.L1 + f.w1;
+    if (k < f.Fijab && k % f.Fab == c0) {
+        const int A = k / f.Fab;
+        v = 0.0;
+        for (int q = 0; q < f.Fij; ++q)
+            if (f.sca[q] == A) v += sol[q * f.Fab + c0];
+    }
+    eff[k] = v;
+}
+
 template <typename TSt>
 static int apply_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, const double* dsol, void* ddiff, int diff_dtype,
                         const void* tI = nullptr, bool rows_done = false, void* hdiff = nullptr) {
     const sfftb_dims& d = p->d;
     EVREC(p, EV_A0);
+    if (p->sca_n) {
+        sca_remap_kernel<<<(d.NEQ + 255) / 256, 256, 0, p->stream>>>(p->fill, d.NEQ, dsol, p->solEff);
+        CKL(p);
+        dsol = p->solEff;
+    }
     const TSt* gIsrc = tI ? (const TSt*)tI : (const TSt*)p->gI;
     if (!rows_done) {
         if (p->pendI) { CK(cudaStreamWaitEvent(p->stream, p->pendI, 0)); p->pendI = nullptr; }

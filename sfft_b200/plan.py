@@ -25,7 +25,7 @@ def _ptr_of(a):
 
 
 class Plan:
-    def __init__(self, N0, N1, w0, w1, DK, DB, ConstPhotRatio, device=0, storage='fp64', fold=0):
+    def __init__(self, N0, N1, w0, w1, DK, DB, ConstPhotRatio, device=0, storage='fp64', fold=0, sca_degree=0):
         self._h = C.c_void_p()
         self._L = B.lib()
         cfg = B.Config()
@@ -33,6 +33,7 @@ class Plan:
         cfg.DK, cfg.DB, cfg.const_phot_ratio = int(DK), int(DB), int(bool(ConstPhotRatio))
         cfg.storage = {'fp64': B.STORE_F64, 'fp32': B.STORE_F32}[storage]
         cfg.fold = int(fold)
+        cfg.sca_degree = int(sca_degree)
         B.check(self._L.sfftb_plan_create(C.byref(self._h), C.byref(cfg)))
         d = B.Dims()
         B.check(self._L.sfftb_plan_dims(self._h, C.byref(d)))

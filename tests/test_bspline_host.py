@@ -16,8 +16,13 @@ def test_unsupported_modes_are_refused_loudly():
         SingleSFFTConfigure.SSC(64, 64, KerHW=2, KerSpType='B-Spline', KerSpDegree=2, VERBOSE_LEVEL=0)
     with pytest.raises(Exception, match='B-Spline spatial variation is not available'):
         SingleSFFTConfigure.SSC(64, 64, KerHW=2, BkgSpType='B-Spline', BkgSpDegree=1, VERBOSE_LEVEL=0)
-    with pytest.raises(Exception, match='SEPARATE-VARYING'):
-        SingleSFFTConfigure.SSC(64, 64, KerHW=2, SEPARATE_SCALING=True, ScaSpDegree=1, VERBOSE_LEVEL=0)
+    with pytest.raises(Exception, match='polynomial scaling only'):
+        SingleSFFTConfigure.SSC(64, 64, KerHW=2, SEPARATE_SCALING=True, ScaSpType='B-Spline', ScaSpDegree=1, VERBOSE_LEVEL=0)
+    with pytest.raises(Exception, match='REGULARIZE_KERNEL with SEPARATE-VARYING'):
+        SingleSFFTConfigure.SSC(64, 64, KerHW=2, SEPARATE_SCALING=True, ScaSpDegree=1, REGULARIZE_KERNEL=True,
+                                XY_REGULARIZE=np.array([[3.0, 4.0]]), VERBOSE_LEVEL=0)
+    with pytest.raises(AssertionError):
+        SingleSFFTConfigure.SSC(64, 64, KerHW=2, KerSpDegree=1, SEPARATE_SCALING=True, ScaSpDegree=2, VERBOSE_LEVEL=0)
     with pytest.raises(Exception, match='not available in sfft_b200'):
         SingleSFFTConfigure.SSC(64, 64, KerHW=2, BACKEND_4SUBTRACT='Numpy', VERBOSE_LEVEL=0)
     with pytest.raises(AssertionError):
@@ -107,3 +112,35 @@ def test_bsp_packet_fits_roundtrip(tmp_path):
     assert relrms(diff[ok], odiff[ok]) < 1e-8
     assert relrms(fitsio.getdata(out).T[ok], odiff[ok]) < 1e-8
     assert np.array_equal(np.asarray(fitsio.getdata(solp), np.float64)[0], sol)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('DK,DS,DB', [(2, 1, 1), (2, 2, 2), (3, 1, 0), (1, 1, 1)])
+def test_separate_varying_polynomial_scaling_matches_oracle(DK, DS, DB):
+    """SEPARATE-VARYING with polynomial bases (BSplineSFFT.py:2487-2495, 3733-3747; no executable reference here -- the
+    oracle restates it in design-matrix form, parity unpinned): normal equations, solution layout and DIFF."""
+    from sfft_b200.BSplineSFFT import SingleSFFTConfigure, GeneralSFFTSubtract
+    from sfft_b200.synth import make_pair
+    N0, N1, w = 88, 96, 2
+    d = make_pair(N0, N1, seed=31 + DK + DS, density=8e-3)
+    kw = dict(KerSpType='Polynomial', KerSpDegree=DK, SEPARATE_SCALING=True, ScaSpType='Polynomial', ScaSpDegree=DS,
+              BkgSpType='Polynomial', BkgSpDegree=DB)
+    cfg = SingleSFFTConfigure.SSC(N0, N1, KerHW=w, VERBOSE_LEVEL=0, **kw)
+    P = bo.ssc_params(N0, N1, w, **kw)
+    assert P['SCALING_MODE'] == 'SEPARATE-VARYING'
+    for k in ('Fij', 'Fpq', 'Fijab', 'NEQ', 'NEQt', 'ScaFij', 'DS'):
+        assert cfg[0][k] == P[k], k
+    assert cfg[1]['plan'].dims['NEQ_FSfree'] == P['NEQt']
+    sol, diff, _ = GeneralSFFTSubtract.GSS(d['REF'], d['SCI'], d['mREF'], d['mSCI'], cfg, VERBOSE_LEVEL=0)
+    ex = {}
+    osol, _ = bo.ess(d['mREF'], d['mSCI'], P, None, False, export=ex)
+    _, odiff = bo.ess(d['REF'], d['SCI'], P, osol, True)
+    L, b = cfg[1]['plan'].export_normal_eq()
+    assert np.max(np.abs(L - ex['LHMAT'])) <= 1e-10 * np.max(np.abs(ex['LHMAT']))
+    assert np.max(np.abs(b - ex['RHb'])) <= 1e-10 * np.max(np.abs(ex['RHb']))
+    ij00 = np.arange(w * P['L1'] + w, P['Fijab'], P['Fab'])
+    assert np.all(sol[ij00[P['ScaFij']:]] == 0.0)
+    assert relrms(diff, odiff) < 1e-8
+    # apply with the oracle's own solution isolates the apply step (solution remap + FIR)
+    d2 = cfg[1]['plan'].apply(d['REF'], d['SCI'], osol)
+    assert relrms(d2, odiff) < 1e-10
