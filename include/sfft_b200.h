@@ -140,6 +140,10 @@ int  sfftb_realize(sfftb_plan* plan, const double* solution, int sol_memkind, co
  * SST is the (Fij x Fij) Gram matrix of the kernel basis at the regularisation coordinates, iREG the (Fab x Fab)
  * Laplacian penalty in the modified-delta basis; host pointers, row-major.  SST == NULL switches it off. */
 int  sfftb_set_regularizer(sfftb_plan* plan, const double* SST, const double* iREG, double lambda);
+/* Plans with sca_degree > 0: where a centre tap is involved REGMAT uses the scaling basis instead (fill_regmat of the
+ * SEPARATE-VARYING mode, :2122-2166): CSST = kernel x scaling Gram matrix, DSST = scaling x scaling, both (Fij x Fij) with
+ * zero rows / columns beyond ScaFij.  Call after sfftb_set_regularizer. */
+int  sfftb_set_regularizer_varying(sfftb_plan* plan, const double* CSST, const double* DSST);
 
 /* Parity hook: the full (NEQ x NEQ) LHMAT and (NEQ) RHb of the last fit, before stripe removal,
  * in the reference's layout (what FillLS_* produce, SFFTSubtract.py:244-380).  Host pointers. */

@@ -15,8 +15,8 @@ call signatures (`SingleSFFTConfigure.SSC` :2538, `ElementalSFFTSubtract.ESS`, `
   * REGULARIZE_KERNEL with XY_REGULARIZE / WEIGHT_REGULARIZE / LAMBDA_REGULARIZE / IGNORE_LAPLACIAN_KERCENT:
     the two Kronecker factors of REGMAT are built here and added inside the native matrix fill (sfftb_set_regularizer).
 
-B-spline bases (kernel, scaling or background) and the regulariser combined with SEPARATE-VARYING scaling are refused with
-a clear error: their CUDA path is not built yet.
+B-spline bases (kernel, scaling or background) are refused with a clear error: their CUDA path is not built yet
+(DESIGN.md section 7).
 """
 import os.path as pa
 import time
@@ -48,9 +48,10 @@ def _laplacian_penalty(w0, w1, IGNORE_LAPLACIAN_KERCENT):
     return 2.0 * (M.T @ (LAP.T @ LAP) @ M)
 
 
-def regularizer_factors(N0, N1, w0, w1, DK, XY_REGULARIZE, WEIGHT_REGULARIZE=None, IGNORE_LAPLACIAN_KERCENT=True):
+def regularizer_factors(N0, N1, w0, w1, DK, XY_REGULARIZE, WEIGHT_REGULARIZE=None, IGNORE_LAPLACIAN_KERCENT=True, DS=None):
     """(SST, iREG) with REGMAT = SCALE^2 * kron(SST, iREG) on the kernel block (fill_regmat, :2091-2119), polynomial
-    kernel basis: SST = SPMAT W SPMAT^T, SPMAT[k, n] = cx_n^i cy_n^j at the requested coordinates (:3576-3582, 3624-3633)."""
+    kernel basis: SST = SPMAT W SPMAT^T, SPMAT[k, n] = cx_n^i cy_n^j at the requested coordinates (:3576-3582, 3624-3633).
+    With DS (SEPARATE-VARYING) also (CSST, DSST): the Gram matrices with the scaling basis, zero-padded to Fij (:3594-3637)."""
     XY = np.asarray(XY_REGULARIZE, float)
     if XY.ndim != 2 or XY.shape[1] != 2 or XY.shape[0] < 1:
         raise Exception('MeLOn ERROR: XY_REGULARIZE must have shape (N_points, 2)')
@@ -63,7 +64,12 @@ def regularizer_factors(N0, N1, w0, w1, DK, XY_REGULARIZE, WEIGHT_REGULARIZE=Non
         if Wd.shape != (XY.shape[0],):
             raise Exception('MeLOn ERROR: WEIGHT_REGULARIZE must have shape (N_points,)')
         Wd = Wd / Wd.sum()
-    return (SP * Wd) @ SP.T, _laplacian_penalty(w0, w1, IGNORE_LAPLACIAN_KERCENT)
+    SST, iREG = (SP * Wd) @ SP.T, _laplacian_penalty(w0, w1, IGNORE_LAPLACIAN_KERCENT)
+    if DS is None:
+        return SST, iREG
+    Sca = np.array([cx ** i * cy ** j for i in range(DS + 1) for j in range(DS + 1 - i)])
+    Sca = np.concatenate([Sca, np.zeros((SP.shape[0] - Sca.shape[0], XY.shape[0]))], axis=0)
+    return SST, iREG, (SP * Wd) @ Sca.T, (Sca * Wd) @ Sca.T
 
 
 class SingleSFFTConfigure:
@@ -103,8 +109,6 @@ class SingleSFFTConfigure:
                                 '(polynomial scaling only)')
             ScaFij = ((DS + 1) * (DS + 2)) // 2
             assert ScaFij <= ((DK + 1) * (DK + 2)) // 2                                 # :190
-            if REGULARIZE_KERNEL:
-                raise Exception('MeLOn ERROR: REGULARIZE_KERNEL with SEPARATE-VARYING scaling is not available in sfft_b200 yet')
         if DK > 3 or DB > 3:
             raise Exception('MeLOn ERROR: polynomial degrees above 3 are not available in sfft_b200')
         if VERBOSE_LEVEL in [1, 2]:
@@ -138,8 +142,13 @@ class SingleSFFTConfigure:
         if REGULARIZE_KERNEL:
             if XY_REGULARIZE is None:
                 raise Exception('MeLOn ERROR: REGULARIZE_KERNEL needs XY_REGULARIZE')
-            SST, iREG = regularizer_factors(N0, N1, w0, w1, DK, XY_REGULARIZE, WEIGHT_REGULARIZE, IGNORE_LAPLACIAN_KERCENT)
-            plan.set_regularizer(SST, iREG, float(LAMBDA_REGULARIZE))
+            if SCALING_MODE == 'SEPARATE-VARYING':
+                SST, iREG, CSST, DSST = regularizer_factors(N0, N1, w0, w1, DK, XY_REGULARIZE, WEIGHT_REGULARIZE,
+                                                            IGNORE_LAPLACIAN_KERCENT, DS=DS)
+                plan.set_regularizer(SST, iREG, float(LAMBDA_REGULARIZE), CSST, DSST)
+            else:
+                SST, iREG = regularizer_factors(N0, N1, w0, w1, DK, XY_REGULARIZE, WEIGHT_REGULARIZE, IGNORE_LAPLACIAN_KERCENT)
+                plan.set_regularizer(SST, iREG, float(LAMBDA_REGULARIZE))
         if VERBOSE_LEVEL in [1, 2]:
             print('\n --//--//--//--//-- EXIT SFFT COMPILATION --//--//--//--//-- ')
         return (P, {'BACKEND': 'B200', 'plan': plan, 'device': device, 'storage': STORAGE})

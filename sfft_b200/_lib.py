@@ -19,7 +19,7 @@ EXPORTS = ['sfftb_version', 'sfftb_last_error', 'sfftb_plan_create', 'sfftb_plan
            'sfftb_plan_set_stream', 'sfftb_plan_sync', 'sfftb_fit', 'sfftb_apply', 'sfftb_gss',
            'sfftb_export_normal_eq', 'sfftb_plan_set_timing', 'sfftb_timings', 'sfftb_last_solver',
            'sfftb_launch_count', 'sfftb_template_prepare', 'sfftb_template_state',
-           'sfftb_template_mark_ready', 'sfftb_gss_template', 'sfftb_realize', 'sfftb_set_regularizer', 'sfftb_gss_submit', 'sfftb_gss_finish', 'sfftb_dbg_fft1d',
+           'sfftb_template_mark_ready', 'sfftb_gss_template', 'sfftb_realize', 'sfftb_set_regularizer', 'sfftb_set_regularizer_varying', 'sfftb_gss_submit', 'sfftb_gss_finish', 'sfftb_dbg_fft1d',
            'sfftb_dbg_row_spectra', 'sfftb_dbg_lag_tables']
 
 
@@ -80,6 +80,7 @@ def lib():
     L.sfftb_gss_submit.argtypes = [vp, vp, vp, vp, vp, ip, vp, vp, ip]
     L.sfftb_gss_finish.argtypes = [vp]
     L.sfftb_set_regularizer.argtypes = [vp, vp, vp, C.c_double]
+    L.sfftb_set_regularizer_varying.argtypes = [vp, vp, vp]
     L.sfftb_realize.argtypes = [vp, vp, ip, vp, ip, ip, vp, vp, ip]
     L.sfftb_dbg_fft1d.argtypes = [ip, ip, ip, ip, vp, vp]
     L.sfftb_dbg_row_spectra.argtypes = [vp, ip, vp]

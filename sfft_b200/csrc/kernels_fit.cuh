@@ -293,6 +293,9 @@ struct FillArgs {
     // kernel regulariser (sfft/BSplineSFFT.py:3570-3700): LHMAT[(k,c),(k',c')] += regw * SST[k,k'] * iREG[c,c'],
     // regw = LAMBDA_REGULARIZE * SCALE^2; null pointers = off
     const double* SST; const double* iREG; double regw;
+    // SEPARATE-VARYING scaling: the centre taps are penalised through the scaling basis (fill_regmat, :2122-2166):
+    // CSST[k][k'] = kernel basis k x scaling basis k' (one tap is a centre tap), DSST = scaling x scaling (both are)
+    const double* CSST; const double* DSST;
     // SEPARATE-VARYING scaling with polynomial bases (sfft/BSplineSFFT.py:2487-2495, 3733-3747): the centre-tap unknown of
     // plane k scales the image times the k-th SCALING basis function, i.e. the unshifted plane sca[k] of the kernel's own
     // plane set (-1: no such unknown; its row / column of the exported LHMAT is zero like the reference's placeholder)
@@ -312,7 +315,15 @@ __device__ __forceinline__ double fill_lh_kernel_block(const FillArgs& f, int A,
     if (nz8) v -= fill_R(f, A, B, -a0, -b0);
     if (nz && nz8) v += fill_R(f, A, B, 0, 0);
     v *= f.invN3;
-    if (f.SST) v = fma(f.regw * f.SST[Ak * f.Fij + Bk], f.iREG[(size_t)ab8 * f.Fab + ab], v);
+    if (f.SST) {
+        double g = f.SST[Ak * f.Fij + Bk];
+        if (f.CSST) {
+            if (!nz8 && !nz) g = f.DSST[Ak * f.Fij + Bk];
+            else if (!nz) g = f.CSST[Ak * f.Fij + Bk];          // row tap off-centre, column tap = centre
+            else if (!nz8) g = f.CSST[Bk * f.Fij + Ak];
+        }
+        v = fma(f.regw * g, f.iREG[(size_t)ab8 * f.Fab + ab], v);
+    }
     return v;
 }
 

@@ -95,7 +95,7 @@ struct sfftb_plan {
     int subst_ok;
     int sca_n;                   // SEPARATE-VARYING polynomial scaling: number of scaling basis functions (0 = off)
     double* solEff;              // solution with the centre taps moved onto the planes of the scaling basis (apply step)
-    double *regSST, *regI;       // kernel regulariser factors (sfftb_set_regularizer)
+    double *regSST, *regI, *regC, *regD;       // kernel regulariser factors (sfftb_set_regularizer)
     cd *bluTw, *bluC, *bluB;     // Bluestein tables of the generic row pass (row lengths with a prime factor > 13)
     ulonglong2* substMsg;        // 2 * nblk * 64 {value | epoch} messages of chol_subst2_kernel
     int chol_coop;
@@ -330,7 +330,7 @@ static int plan_free(sfftb_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     void* ptrs[] = {p->vt8_8, p->vt64_8, p->vt64_4, p->vt256_4, p->vt512_4, p->tabA, p->tabB_row, p->tabC_row, p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
-                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->substMsg, p->solEff, p->regSST, p->regI, p->bluTw, p->bluC, p->bluB, p->firTaps, p->firCA, p->tstate, p->stC, p->stD};
+                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->substMsg, p->solEff, p->regC, p->regD, p->regSST, p->regI, p->bluTw, p->bluC, p->bluB, p->firTaps, p->firCA, p->tstate, p->stC, p->stD};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->info_h) cudaFreeHost(p->info_h);
     for (int k = 0; k < EV_COUNT; ++k) if (p->ev[k]) cudaEventDestroy(p->ev[k]);
@@ -1533,11 +1533,13 @@ extern "C" int sfftb_gss_template(sfftb_plan* p, const void* J, const void* mJ, 
 // Kernel regularisation of sfft/BSplineSFFT.py:3570-3700: LHMAT += LAMBDA * REGMAT with the Kronecker structure
 // REGMAT[(k,c),(k',c')] = SCALE^2 * SST[k,k'] * iREG[c,c'] (fill_regmat, :2091-2119).  The two small factors are kept on
 // the device and added inside the matrix fill.  SST == NULL switches it off.
+extern "C" int sfftb_set_regularizer_varying(sfftb_plan* p, const double* CSST, const double* DSST);
 extern "C" int sfftb_set_regularizer(sfftb_plan* p, const double* SST, const double* iREG, double lambda) {
     if (!p) return fail(SFFTB_EINVAL, "null plan");
     CK(cudaSetDevice(p->device));
     CK(cudaStreamSynchronize(p->stream));
     p->factor_cached = 0;
+    p->fill.CSST = nullptr; p->fill.DSST = nullptr;
     if (!SST || !iREG) { p->fill.SST = nullptr; p->fill.iREG = nullptr; p->fill.regw = 0.0; return 0; }
     if (!(lambda >= 0.0)) return fail(SFFTB_EINVAL, "LAMBDA_REGULARIZE must be >= 0");
     const size_t nS = (size_t)p->d.Fij * p->d.Fij, nI = (size_t)p->d.Fab * p->d.Fab;
@@ -1546,6 +1548,23 @@ extern "C" int sfftb_set_regularizer(sfftb_plan* p, const double* SST, const dou
     CK(cudaMemcpy(p->regI, iREG, sizeof(double) * nI, cudaMemcpyHostToDevice));
     const double N = (double)p->d.N0 * (double)p->d.N1;
     p->fill.SST = p->regSST; p->fill.iREG = p->regI; p->fill.regw = lambda / (N * N);
+    return 0;
+}
+
+// SEPARATE-VARYING plans: the Gram matrices that replace SST where a centre tap is involved (fill_regmat, :2122-2166).
+// Call after sfftb_set_regularizer; (Fij x Fij) host arrays, rows / columns beyond ScaFij zero (the placeholder basis).
+extern "C" int sfftb_set_regularizer_varying(sfftb_plan* p, const double* CSST, const double* DSST) {
+    if (!p || !CSST || !DSST) return fail(SFFTB_EINVAL, "null argument");
+    if (!p->sca_n) return fail(SFFTB_ESTATE, "the plan was not created with a varying scaling (sca_degree > 0)");
+    if (!p->fill.SST) return fail(SFFTB_ESTATE, "call sfftb_set_regularizer first");
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    p->factor_cached = 0;
+    const size_t nS = (size_t)p->d.Fij * p->d.Fij;
+    if (!p->regC) { CK(cudaMalloc(&p->regC, sizeof(double) * nS)); CK(cudaMalloc(&p->regD, sizeof(double) * nS)); }
+    CK(cudaMemcpy(p->regC, CSST, sizeof(double) * nS, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->regD, DSST, sizeof(double) * nS, cudaMemcpyHostToDevice));
+    p->fill.CSST = p->regC; p->fill.DSST = p->regD;
     return 0;
 }
 

@@ -120,7 +120,7 @@ class Plan:
                                   B.F64 if diff.dtype == np.float64 else B.F32))
         return sol, diff
 
-    def set_regularizer(self, SST=None, iREG=None, lam=0.0):
+    def set_regularizer(self, SST=None, iREG=None, lam=0.0, CSST=None, DSST=None):
         """Kernel regularisation (BSplineSFFT.py:3570-3700): LHMAT += lam * SCALE^2 * kron(SST, iREG) on the kernel block."""
         if SST is None:
             B.check(self._L.sfftb_set_regularizer(self._h, None, None, 0.0))
@@ -131,6 +131,12 @@ class Plan:
         if S.shape != (d['Fij'], d['Fij']) or R.shape != (d['Fab'], d['Fab']):
             raise Exception('MeLOn ERROR: regulariser factors must have shapes (Fij, Fij) and (Fab, Fab)')
         B.check(self._L.sfftb_set_regularizer(self._h, S.ctypes.data, R.ctypes.data, float(lam)))
+        if CSST is not None:           # SEPARATE-VARYING: scaling-basis Gram matrices for the centre taps
+            Cm = np.ascontiguousarray(CSST, np.float64)
+            Dm = np.ascontiguousarray(DSST, np.float64)
+            if Cm.shape != S.shape or Dm.shape != S.shape:
+                raise Exception('MeLOn ERROR: CSST / DSST must have shape (Fij, Fij)')
+            B.check(self._L.sfftb_set_regularizer_varying(self._h, Cm.ctypes.data, Dm.ctypes.data))
 
     # ---- asynchronous host-buffer GSS (sfftb_gss_submit / sfftb_gss_finish) -------------------------
     def gss_submit(self, PixA_I, PixA_J, PixA_mI, PixA_mJ, out_dtype=np.float64, Solution_out=None, DIFF_out=None):

@@ -18,9 +18,6 @@ def test_unsupported_modes_are_refused_loudly():
         SingleSFFTConfigure.SSC(64, 64, KerHW=2, BkgSpType='B-Spline', BkgSpDegree=1, VERBOSE_LEVEL=0)
     with pytest.raises(Exception, match='polynomial scaling only'):
         SingleSFFTConfigure.SSC(64, 64, KerHW=2, SEPARATE_SCALING=True, ScaSpType='B-Spline', ScaSpDegree=1, VERBOSE_LEVEL=0)
-    with pytest.raises(Exception, match='REGULARIZE_KERNEL with SEPARATE-VARYING'):
-        SingleSFFTConfigure.SSC(64, 64, KerHW=2, SEPARATE_SCALING=True, ScaSpDegree=1, REGULARIZE_KERNEL=True,
-                                XY_REGULARIZE=np.array([[3.0, 4.0]]), VERBOSE_LEVEL=0)
     with pytest.raises(AssertionError):
         SingleSFFTConfigure.SSC(64, 64, KerHW=2, KerSpDegree=1, SEPARATE_SCALING=True, ScaSpDegree=2, VERBOSE_LEVEL=0)
     with pytest.raises(Exception, match='not available in sfft_b200'):
@@ -115,8 +112,9 @@ def test_bsp_packet_fits_roundtrip(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('DK,DS,DB', [(2, 1, 1), (2, 2, 2), (3, 1, 0), (1, 1, 1)])
-def test_separate_varying_polynomial_scaling_matches_oracle(DK, DS, DB):
+@pytest.mark.parametrize('DK,DS,DB,regularize', [(2, 1, 1, False), (2, 2, 2, False), (3, 1, 0, False), (1, 1, 1, False),
+                                                  (2, 1, 1, True), (2, 2, 0, True)])
+def test_separate_varying_polynomial_scaling_matches_oracle(DK, DS, DB, regularize):
     """SEPARATE-VARYING with polynomial bases (BSplineSFFT.py:2487-2495, 3733-3747; no executable reference here -- the
     oracle restates it in design-matrix form, parity unpinned): normal equations, solution layout and DIFF."""
     from sfft_b200.BSplineSFFT import SingleSFFTConfigure, GeneralSFFTSubtract
@@ -125,6 +123,14 @@ def test_separate_varying_polynomial_scaling_matches_oracle(DK, DS, DB):
     d = make_pair(N0, N1, seed=31 + DK + DS, density=8e-3)
     kw = dict(KerSpType='Polynomial', KerSpDegree=DK, SEPARATE_SCALING=True, ScaSpType='Polynomial', ScaSpDegree=DS,
               BkgSpType='Polynomial', BkgSpDegree=DB)
+    if regularize:
+        rng = np.random.default_rng(DK + 7 * DS)
+        XY = np.stack([rng.uniform(0.5, N0 + 0.5, 30), rng.uniform(0.5, N1 + 0.5, 30)], axis=1)
+        P0 = bo.ssc_params(N0, N1, w, REGULARIZE_KERNEL=True, XY_REGULARIZE=XY, LAMBDA_REGULARIZE=1.0, **kw)
+        ex0 = {}
+        bo.ess(d['mREF'], d['mSCI'], dict(P0, REGULARIZE_KERNEL=False), None, False, export=ex0)
+        lam = 0.1 * np.max(np.abs(ex0['LHMAT'][:P0['Fijab'], :P0['Fijab']])) / np.max(np.abs(bo.regularizer(P0)))
+        kw.update(REGULARIZE_KERNEL=True, XY_REGULARIZE=XY, WEIGHT_REGULARIZE=rng.uniform(0.5, 2.0, 30), LAMBDA_REGULARIZE=lam)
     cfg = SingleSFFTConfigure.SSC(N0, N1, KerHW=w, VERBOSE_LEVEL=0, **kw)
     P = bo.ssc_params(N0, N1, w, **kw)
     assert P['SCALING_MODE'] == 'SEPARATE-VARYING'
