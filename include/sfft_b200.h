@@ -135,6 +135,18 @@ int  sfftb_gss_template(sfftb_plan* plan, const void* PixA_J, const void* PixA_m
 int  sfftb_realize(sfftb_plan* plan, const double* solution, int sol_memkind, const double* xy, int xy_memkind, int nq,
                    double* kerstack, double* fscal, int out_memkind);
 
+/* The I/O edge of the packets on the device (sfft/CustomizedPacket.py:93-126, 183-203): the raw big-endian FITS data
+ * block (NAXIS2 x NAXIS1, as in the file) is decoded -- byte swap, BITPIX conversion, BSCALE / BZERO -- straight into the
+ * transposed (NAXIS1, NAXIS2) array the plan reads (the reference's `fits.getdata(..).T` + float64 copy on the host), the
+ * difference image is encoded back; NaN union fill and NaN restore / sign flip of the packets as elementwise kernels.
+ * All pointers are DEVICE pointers; work is queued on `cuda_stream`; nothing synchronises. */
+int  sfftb_fits_decode(int device, void* cuda_stream, const void* raw, int bitpix, int naxis1, int naxis2, double bscale, double bzero,
+                       void* out, int out_dtype);
+int  sfftb_fits_encode(int device, void* cuda_stream, const void* img, int img_dtype, int naxis1, int naxis2, int bitpix, void* raw);
+int  sfftb_nan_union_fill(int device, void* cuda_stream, void* A, void* B, const void* mA, const void* mB, int dtype, size_t n,
+                          unsigned char* mask, int* flags);
+int  sfftb_nan_mask_apply(int device, void* cuda_stream, void* D, int dtype, const unsigned char* mask, size_t n, double sign);
+
 /* Kernel regularisation (sfft/BSplineSFFT.py:3570-3700, REGULARIZE_KERNEL / LAMBDA_REGULARIZE): every following fit solves
  * (LHMAT + lambda * REGMAT) x = RHb with REGMAT[(k,c),(k',c')] = SCALE^2 * SST[k,k'] * iREG[c,c'] (fill_regmat, :2091-2119).
  * SST is the (Fij x Fij) Gram matrix of the kernel basis at the regularisation coordinates, iREG the (Fab x Fab)

@@ -22,12 +22,87 @@ def _read_T(path):
     return np.ascontiguousarray(fitsio.getdata(path).T, np.float64)                    # CP :93-112
 
 
+def _cp_on_device(FITS_REF, FITS_SCI, FITS_mREF, FITS_mSCI, ForceConv, GKerHW, KerPolyOrder, BGPolyOrder, ConstPhotRatio,
+                  BACKEND_4SUBTRACT, CUDA_DEVICE_4SUBTRACT, VERBOSE_LEVEL, STORAGE, want_raw_diff):
+    """CP with the I/O edge on the device: the raw FITS data blocks are uploaded as they are in the
+    files and decoded / transposed by sfftb_fits_decode; the NaN union fill, the subtraction, the NaN restore, the sign
+    flip and the encoding of the difference image all stay on the GPU (CustomizedPacket.py:93-203 without its host-side
+    `.T` + float64 copies).  Returns (Solution, PixA_DIFF, SFFTConfig, raw difference block or None)."""
+    import torch
+    from . import _lib as B
+    L = B.lib()
+    dev_i = int(CUDA_DEVICE_4SUBTRACT)
+    dev = torch.device('cuda', dev_i)
+    imgs, shape = {}, None
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev)
+        for name, path in (('REF', FITS_REF), ('SCI', FITS_SCI), ('mREF', FITS_mREF), ('mSCI', FITS_mSCI)):
+            cards, raw, bp, n1, n2, bscale, bzero = fitsio.read_raw(path)
+            if shape is None:
+                shape = (n1, n2)
+            elif shape != (n1, n2):
+                raise Exception('MeLOn ERROR: Input images should have same size!')
+            raw_d = torch.from_numpy(raw).to(dev, non_blocking=True)
+            out = torch.empty(shape, dtype=torch.float64, device=dev)
+            B.check(L.sfftb_fits_decode(dev_i, stream.cuda_stream, raw_d.data_ptr(), bp, n1, n2, bscale, bzero, out.data_ptr(), B.F64))
+            imgs[name] = out
+            del raw_d
+        n = shape[0] * shape[1]
+        mask = torch.empty(n, dtype=torch.uint8, device=dev)
+        flags = torch.zeros(2, dtype=torch.int32, device=dev)
+        B.check(L.sfftb_nan_union_fill(dev_i, stream.cuda_stream, imgs['REF'].data_ptr(), imgs['SCI'].data_ptr(),
+                                       imgs['mREF'].data_ptr(), imgs['mSCI'].data_ptr(), B.F64, n, mask.data_ptr(), flags.data_ptr()))
+        fl = flags.cpu().numpy()
+        assert fl[1] == 0, 'masked images must be NaN-free'                               # CP :118-119
+        assert ForceConv in ['REF', 'SCI']
+        SFFTConfig = SingleSFFTConfigure.SSC(NX=shape[0], NY=shape[1], KerHW=GKerHW, KerPolyOrder=KerPolyOrder,
+                                             BGPolyOrder=BGPolyOrder, ConstPhotRatio=ConstPhotRatio,
+                                             BACKEND_4SUBTRACT=BACKEND_4SUBTRACT, VERBOSE_LEVEL=VERBOSE_LEVEL,
+                                             CUDA_DEVICE=dev_i, STORAGE=STORAGE)
+        plan = SFFTConfig[1]['plan']
+        if ForceConv == 'REF':
+            I, J, mI, mJ = imgs['REF'], imgs['SCI'], imgs['mREF'], imgs['mSCI']
+        else:
+            I, J, mI, mJ = imgs['SCI'], imgs['REF'], imgs['mSCI'], imgs['mREF']
+        sol_d = torch.empty(plan.NEQ, dtype=torch.float64, device=dev)
+        diff_d = torch.empty(shape, dtype=torch.float64, device=dev)
+        plan.set_stream(stream.cuda_stream)
+        plan.gss_device(I.data_ptr(), J.data_ptr(), mI.data_ptr(), mJ.data_ptr(), B.F64, sol_d.data_ptr(), diff_d.data_ptr(), B.F64)
+        B.check(L.sfftb_nan_mask_apply(dev_i, stream.cuda_stream, diff_d.data_ptr(), B.F64, mask.data_ptr() if fl[0] else None, n,
+                                       -1.0 if ForceConv == 'SCI' else 1.0))
+        raw_out = None
+        if want_raw_diff:
+            raw_dd = torch.empty(n * 8, dtype=torch.uint8, device=dev)
+            B.check(L.sfftb_fits_encode(dev_i, stream.cuda_stream, diff_d.data_ptr(), B.F64, shape[0], shape[1], -64, raw_dd.data_ptr()))
+            raw_out = raw_dd.cpu().numpy()
+        return sol_d.cpu().numpy(), diff_d.cpu().numpy(), SFFTConfig, raw_out
+
+
 class Customized_Packet:
     @staticmethod
     def CP(FITS_REF, FITS_SCI, FITS_mREF, FITS_mSCI, ForceConv, GKerHW, FITS_DIFF=None, FITS_Solution=None,
            KerPolyOrder=2, BGPolyOrder=2, ConstPhotRatio=True, BACKEND_4SUBTRACT='B200',
            CUDA_DEVICE_4SUBTRACT='0', NUM_CPU_THREADS_4SUBTRACT=8, NUMBA_CACHE=True, VERBOSE_LEVEL=2,
-           STORAGE='fp64'):
+           STORAGE='fp64', FITS_ON_DEVICE=False):
+        """FITS_ON_DEVICE=True decodes the FITS data blocks and encodes the difference image on the GPU (no host-side
+        transpose / float64 copies; needs torch for the device buffers); the default keeps the host route."""
+        if FITS_ON_DEVICE:
+            Solution, PixA_DIFF, SFFTConfig, raw_diff = _cp_on_device(
+                FITS_REF, FITS_SCI, FITS_mREF, FITS_mSCI, ForceConv, GKerHW, KerPolyOrder, BGPolyOrder, ConstPhotRatio,
+                BACKEND_4SUBTRACT, CUDA_DEVICE_4SUBTRACT, VERBOSE_LEVEL, STORAGE, FITS_DIFF is not None)
+            if FITS_DIFF is not None:
+                cards, _ = fitsio.read_header(FITS_SCI)
+                fitsio.writeto(FITS_DIFF, (raw_diff, -64, PixA_DIFF.shape[0], PixA_DIFF.shape[1]), base_cards=cards, updates=[
+                    ('NAME_REF', pa.basename(FITS_REF), 'MeLOn: SFFT'), ('NAME_SCI', pa.basename(FITS_SCI), 'MeLOn: SFFT'),
+                    ('KERORDER', KerPolyOrder, 'MeLOn: SFFT'), ('BGORDER', BGPolyOrder, 'MeLOn: SFFT'),
+                    ('CPHOTR', str(ConstPhotRatio), 'MeLOn: SFFT'), ('KERHW', GKerHW, 'MeLOn: SFFT'),
+                    ('CONVD', ForceConv, 'MeLOn: SFFT')])
+            if FITS_Solution is not None:
+                P = SFFTConfig[0]
+                ups = [(k, P[v], 'MeLOn: SFFT') for k, v in (('N0', 'N0'), ('N1', 'N1'), ('DK', 'DK'), ('DB', 'DB'),
+                       ('L0', 'L0'), ('L1', 'L1'), ('FIJ', 'Fij'), ('FAB', 'Fab'), ('FPQ', 'Fpq'), ('FIJAB', 'Fijab'))]
+                fitsio.writeto(FITS_Solution, Solution.reshape((-1, 1)).T, base_cards=None, updates=ups)
+            return Solution, PixA_DIFF
         PixA_REF, PixA_SCI = _read_T(FITS_REF), _read_T(FITS_SCI)
         PixA_mREF, PixA_mSCI = _read_T(FITS_mREF), _read_T(FITS_mSCI)
         Solution, PixA_DIFF, SFFTConfig = Customized_Packet.CP_arrays(

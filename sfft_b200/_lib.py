@@ -19,7 +19,8 @@ EXPORTS = ['sfftb_version', 'sfftb_last_error', 'sfftb_plan_create', 'sfftb_plan
            'sfftb_plan_set_stream', 'sfftb_plan_sync', 'sfftb_fit', 'sfftb_apply', 'sfftb_gss',
            'sfftb_export_normal_eq', 'sfftb_plan_set_timing', 'sfftb_timings', 'sfftb_last_solver',
            'sfftb_launch_count', 'sfftb_template_prepare', 'sfftb_template_state',
-           'sfftb_template_mark_ready', 'sfftb_gss_template', 'sfftb_realize', 'sfftb_set_regularizer', 'sfftb_set_regularizer_varying', 'sfftb_gss_submit', 'sfftb_gss_finish', 'sfftb_dbg_fft1d',
+           'sfftb_template_mark_ready', 'sfftb_gss_template', 'sfftb_realize', 'sfftb_fits_decode', 'sfftb_fits_encode', 'sfftb_nan_union_fill', 'sfftb_nan_mask_apply',
+           'sfftb_set_regularizer', 'sfftb_set_regularizer_varying', 'sfftb_gss_submit', 'sfftb_gss_finish', 'sfftb_dbg_fft1d',
            'sfftb_dbg_row_spectra', 'sfftb_dbg_lag_tables']
 
 
@@ -79,6 +80,10 @@ def lib():
     L.sfftb_launch_count.restype = C.c_longlong
     L.sfftb_gss_submit.argtypes = [vp, vp, vp, vp, vp, ip, vp, vp, ip]
     L.sfftb_gss_finish.argtypes = [vp]
+    L.sfftb_fits_decode.argtypes = [ip, vp, vp, ip, ip, ip, C.c_double, C.c_double, vp, ip]
+    L.sfftb_fits_encode.argtypes = [ip, vp, vp, ip, ip, ip, ip, vp]
+    L.sfftb_nan_union_fill.argtypes = [ip, vp, vp, vp, vp, vp, ip, C.c_size_t, vp, vp]
+    L.sfftb_nan_mask_apply.argtypes = [ip, vp, vp, ip, vp, C.c_size_t, C.c_double]
     L.sfftb_set_regularizer.argtypes = [vp, vp, vp, C.c_double]
     L.sfftb_set_regularizer_varying.argtypes = [vp, vp, vp]
     L.sfftb_realize.argtypes = [vp, vp, ip, vp, ip, ip, vp, vp, ip]

@@ -13,6 +13,7 @@
 #include "kernels_fit_seg.cuh"
 #include "kernels_fit_seg3.cuh"
 #include "kernels_reader.cuh"
+#include "kernels_fitsio.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -1527,6 +1528,61 @@ extern "C" int sfftb_gss_template(sfftb_plan* p, const void* J, const void* mJ, 
     }
     if ((rc = copy_out(p, solution, sol_memkind, p->sol, sizeof(double) * p->d.NEQ))) return rc;
     CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+// ---- packet I/O edge on the device; all pointers are DEVICE pointers, work is queued on `stream` -----
+static int fio_check(int device, int n1, int n2) {
+    if (n1 <= 0 || n2 <= 0) return fail(SFFTB_EINVAL, "bad image shape");
+    CK(cudaSetDevice(device));
+    return 0;
+}
+extern "C" int sfftb_fits_decode(int device, void* stream, const void* raw, int bitpix, int naxis1, int naxis2, double bscale, double bzero,
+                                 void* out, int out_dtype) {
+    if (!raw || !out) return fail(SFFTB_EINVAL, "null argument");
+    if (bitpix != 8 && bitpix != 16 && bitpix != 32 && bitpix != 64 && bitpix != -32 && bitpix != -64) return fail(SFFTB_EINVAL, "unsupported BITPIX %d", bitpix);
+    int rc = fio_check(device, naxis1, naxis2);
+    if (rc) return rc;
+    dim3 blk(32, 8), grd((naxis1 + 31) / 32, (naxis2 + 31) / 32);
+    if (out_dtype == SFFTB_F64) fits_decode_T_kernel<double><<<grd, blk, 0, (cudaStream_t)stream>>>((const unsigned char*)raw, bitpix, naxis1, naxis2, bscale, bzero, (double*)out);
+    else if (out_dtype == SFFTB_F32) fits_decode_T_kernel<float><<<grd, blk, 0, (cudaStream_t)stream>>>((const unsigned char*)raw, bitpix, naxis1, naxis2, bscale, bzero, (float*)out);
+    else return fail(SFFTB_EINVAL, "bad dtype");
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int sfftb_fits_encode(int device, void* stream, const void* img, int img_dtype, int naxis1, int naxis2, int bitpix, void* raw) {
+    if (!raw || !img) return fail(SFFTB_EINVAL, "null argument");
+    if (bitpix != -32 && bitpix != -64) return fail(SFFTB_EINVAL, "the difference image is written as BITPIX -32 or -64");
+    int rc = fio_check(device, naxis1, naxis2);
+    if (rc) return rc;
+    dim3 blk(32, 8), grd((naxis1 + 31) / 32, (naxis2 + 31) / 32);
+    if (img_dtype == SFFTB_F64) fits_encode_T_kernel<double><<<grd, blk, 0, (cudaStream_t)stream>>>((const double*)img, bitpix, naxis1, naxis2, (unsigned char*)raw);
+    else if (img_dtype == SFFTB_F32) fits_encode_T_kernel<float><<<grd, blk, 0, (cudaStream_t)stream>>>((const float*)img, bitpix, naxis1, naxis2, (unsigned char*)raw);
+    else return fail(SFFTB_EINVAL, "bad dtype");
+    CK(cudaGetLastError());
+    return 0;
+}
+// flags[0] = a NaN was found in the unmasked pair, flags[1] = a NaN in the masked pair (the packets assert there is none)
+extern "C" int sfftb_nan_union_fill(int device, void* stream, void* A, void* B, const void* mA, const void* mB, int dtype, size_t n,
+                                    unsigned char* mask, int* flags) {
+    if (!A || !B || !mA || !mB || !mask || !flags) return fail(SFFTB_EINVAL, "null argument");
+    CK(cudaSetDevice(device));
+    CK(cudaMemsetAsync(flags, 0, 2 * sizeof(int), (cudaStream_t)stream));
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (dtype == SFFTB_F64) nan_union_fill_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)A, (double*)B, (const double*)mA, (const double*)mB, n, mask, flags);
+    else if (dtype == SFFTB_F32) nan_union_fill_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)A, (float*)B, (const float*)mA, (const float*)mB, n, mask, flags);
+    else return fail(SFFTB_EINVAL, "bad dtype");
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int sfftb_nan_mask_apply(int device, void* stream, void* D, int dtype, const unsigned char* mask, size_t n, double sign) {
+    if (!D) return fail(SFFTB_EINVAL, "null argument");
+    CK(cudaSetDevice(device));
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (dtype == SFFTB_F64) nan_mask_apply_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)D, mask, n, sign);
+    else if (dtype == SFFTB_F32) nan_mask_apply_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)D, mask, n, sign);
+    else return fail(SFFTB_EINVAL, "bad dtype");
+    CK(cudaGetLastError());
     return 0;
 }
 

@@ -73,6 +73,18 @@ def getdata(path):
     return a.astype(a.dtype.newbyteorder('='))
 
 
+def read_raw(path):
+    """The primary image as it is in the file: (cards, raw uint8 array of the data block, bitpix, naxis1, naxis2, bscale,
+    bzero).  No byte swap, no conversion -- the device decodes it (sfftb_fits_decode)."""
+    cards, off = read_header(path)
+    h = header_dict(cards)
+    if h.get('NAXIS') != 2:
+        raise ValueError('only 2-D primary images are supported: %s' % path)
+    n1, n2, bp = int(h['NAXIS1']), int(h['NAXIS2']), int(h['BITPIX'])
+    raw = np.fromfile(path, dtype=np.uint8, count=n1 * n2 * abs(bp) // 8, offset=off)
+    return cards, raw, bp, n1, n2, float(h.get('BSCALE', 1)), float(h.get('BZERO', 0))
+
+
 def _card(key, value, comment=None):
     if isinstance(value, bool):
         v = '%20s' % ('T' if value else 'F')
@@ -99,11 +111,19 @@ def writeto(path, data, base_cards=None, updates=None):
     base_cards: raw cards of a header to carry over (structural keywords are regenerated).
     updates   : list of (key, value, comment) appended/replaced after the carried-over cards.
     """
-    data = np.asarray(data)
-    if data.ndim != 2:
-        raise ValueError('2-D image required')
-    bitpix = {np.dtype('float64'): -64, np.dtype('float32'): -32,
-              np.dtype('int32'): 32, np.dtype('int16'): 16, np.dtype('uint8'): 8}[np.dtype(data.dtype.name)]
+    raw_block = None
+    if isinstance(data, tuple):          # (raw big-endian data block, bitpix, naxis1, naxis2): already encoded on the device
+        raw_block, bitpix, n1_, n2_ = data
+
+        class _Shape:
+            shape = (n2_, n1_)
+        data = _Shape()
+    else:
+        data = np.asarray(data)
+        if data.ndim != 2:
+            raise ValueError('2-D image required')
+        bitpix = {np.dtype('float64'): -64, np.dtype('float32'): -32,
+                  np.dtype('int32'): 32, np.dtype('int16'): 16, np.dtype('uint8'): 8}[np.dtype(data.dtype.name)]
     struct = ('SIMPLE', 'BITPIX', 'NAXIS', 'NAXIS1', 'NAXIS2', 'EXTEND', 'BSCALE', 'BZERO')
     cards = [_card('SIMPLE', True, 'conforms to FITS standard'), _card('BITPIX', bitpix, 'array data type'),
              _card('NAXIS', 2, 'number of array dimensions'), _card('NAXIS1', data.shape[1]),
@@ -119,7 +139,10 @@ def writeto(path, data, base_cards=None, updates=None):
         cards.append(_card(k, v, cm))
     cards.append('%-80s' % 'END')
     hb = _pad(''.join(cards).encode('ascii'), b' ')
-    db = _pad(np.ascontiguousarray(data, dtype=_DTYPES[bitpix]).tobytes(), b'\0')
+    if raw_block is not None:
+        db = _pad(np.asarray(raw_block, np.uint8).tobytes(), b'\0')
+    else:
+        db = _pad(np.ascontiguousarray(data, dtype=_DTYPES[bitpix]).tobytes(), b'\0')
     with open(path, 'wb') as f:
         f.write(hb)
         f.write(db)
