@@ -386,7 +386,11 @@ def main():
         tr = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(tr):
             try:
-                out['roofline']['traffic'] = json.load(open(tr)).get(args.workload, {}).get(kname)
+                trd = json.load(open(tr)).get(args.workload, {})
+                out['roofline']['traffic'] = trd.get(kname)
+                if trd.get('limiters', {}).get(kname):
+                    # what actually limits the kernel (from the committed ncu capture, not measured in this run)
+                    out['roofline']['ncu_limiters'] = trd['limiters'][kname]
             except Exception:
                 pass
         if world == 1 and not args.no_cpu_baseline:
