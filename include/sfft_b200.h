@@ -109,6 +109,10 @@ int  sfftb_gss(sfftb_plan* plan, const void* PixA_I, const void* PixA_J, const v
  * from host memory (sfft/MultiEasySparsePacket.py:568-649 feeds one GPU from a host-side task queue) should be fed. */
 int  sfftb_gss_submit(sfftb_plan* plan, const void* PixA_I, const void* PixA_J, const void* PixA_mI, const void* PixA_mJ,
                       int img_dtype, double* solution, void* diff, int diff_dtype);
+/* The same for one science tile against the cached template (sfftb_gss_template with host buffers); completes inside the
+ * call until the plan holds the template's Cholesky factor (first tile). */
+int  sfftb_gss_template_submit(sfftb_plan* plan, const void* PixA_J, const void* PixA_mJ, int img_dtype,
+                               double* solution, void* diff, int diff_dtype);
 int  sfftb_gss_finish(sfftb_plan* plan);
 
 /* Shared-template batch path (BASELINE config 4).  The reference re-transforms the template for every

@@ -20,7 +20,7 @@ EXPORTS = ['sfftb_version', 'sfftb_last_error', 'sfftb_plan_create', 'sfftb_plan
            'sfftb_export_normal_eq', 'sfftb_plan_set_timing', 'sfftb_timings', 'sfftb_last_solver',
            'sfftb_launch_count', 'sfftb_template_prepare', 'sfftb_template_state',
            'sfftb_template_mark_ready', 'sfftb_gss_template', 'sfftb_realize', 'sfftb_fits_decode', 'sfftb_fits_encode', 'sfftb_nan_union_fill', 'sfftb_nan_mask_apply',
-           'sfftb_set_regularizer', 'sfftb_set_regularizer_varying', 'sfftb_gss_submit', 'sfftb_gss_finish', 'sfftb_dbg_fft1d',
+           'sfftb_set_regularizer', 'sfftb_set_regularizer_varying', 'sfftb_gss_submit', 'sfftb_gss_template_submit', 'sfftb_gss_finish', 'sfftb_dbg_fft1d',
            'sfftb_dbg_row_spectra', 'sfftb_dbg_lag_tables']
 
 
@@ -79,6 +79,7 @@ def lib():
     L.sfftb_launch_count.argtypes = [vp]
     L.sfftb_launch_count.restype = C.c_longlong
     L.sfftb_gss_submit.argtypes = [vp, vp, vp, vp, vp, ip, vp, vp, ip]
+    L.sfftb_gss_template_submit.argtypes = [vp, vp, vp, ip, vp, vp, ip]
     L.sfftb_gss_finish.argtypes = [vp]
     L.sfftb_fits_decode.argtypes = [ip, vp, vp, ip, ip, ip, C.c_double, C.c_double, vp, ip]
     L.sfftb_fits_encode.argtypes = [ip, vp, vp, ip, ip, ip, ip, vp]

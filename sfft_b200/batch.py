@@ -128,3 +128,68 @@ class PairPipeline:
     def close(self):
         for pl in self.plans:
             pl.close()
+
+
+class TemplatePipeline:
+    """Science tiles in host memory against ONE shared template on one GPU (BASELINE config 4): two plans hold the same
+    template state and share one compute stream; tiles go through sfftb_gss_template_submit / sfftb_gss_finish
+    alternately, so the copies of tile k + 1 run under the kernels and the device-to-host copy of tile k.  Under
+    torch.distributed the template state comes from TemplateBatch's single broadcast (pass `state_from`)."""
+
+    def __init__(self, N0, N1, KerHW, KerPolyOrder=2, BGPolyOrder=2, ConstPhotRatio=True, device=0, storage='fp64',
+                 stream_ptr=None, first_plan=None):
+        import torch
+        from .plan import Plan
+        self.device = device
+        mk = lambda: Plan(N0, N1, KerHW, KerHW, KerPolyOrder, BGPolyOrder, ConstPhotRatio, device=device, storage=storage)
+        self.plans = [first_plan if first_plan is not None else mk(), mk()]
+        self._own = [first_plan is None, True]
+        if stream_ptr is None:
+            stream_ptr = torch.cuda.current_stream(torch.device('cuda', device)).cuda_stream
+        for pl in self.plans:
+            pl.set_stream(stream_ptr)
+        self._busy = [False, False]
+        self._k = 0
+
+    def set_template(self, PixA_I=None, PixA_mI=None):
+        """Prepare the template on the first plan (unless it already holds one, e.g. received by broadcast) and clone
+        its state into the second (device-to-device)."""
+        import torch
+        if PixA_I is not None:
+            self.plans[0].template_prepare(PixA_I, PixA_mI)
+        self.plans[1].template_state_tensor().copy_(self.plans[0].template_state_tensor())
+        torch.cuda.synchronize(torch.device('cuda', self.device))
+        self.plans[1].template_mark_ready()
+
+    def submit(self, PixA_J, PixA_mJ, out_dtype=np.float64, Solution_out=None, DIFF_out=None):
+        slot = self._k % 2
+        done = None
+        if self._busy[slot]:
+            done = self.plans[slot].gss_finish()
+        self.plans[slot].gss_template_submit(PixA_J, PixA_mJ, out_dtype, Solution_out, DIFF_out)
+        self._busy[slot] = True
+        self._k += 1
+        return done
+
+    def drain(self):
+        out = []
+        for d in range(2):
+            slot = (self._k + d) % 2
+            if self._busy[slot]:
+                out.append(self.plans[slot].gss_finish())
+                self._busy[slot] = False
+        return out
+
+    def run(self, tiles, out_dtype=np.float64):
+        res = []
+        for (J, mJ) in tiles:
+            r = self.submit(J, mJ, out_dtype)
+            if r is not None:
+                res.append(r)
+        res.extend(self.drain())
+        return res
+
+    def close(self):
+        for pl, own in zip(self.plans, self._own):
+            if own:
+                pl.close()

@@ -85,6 +85,8 @@ struct sfftb_plan {
     cudaEvent_t evDone;          // end of the work queued by sfftb_gss_submit
     int pending;                 // a submitted GSS has not been finished yet
     void* pend_diff; double* pend_sol; int pend_dtype, pend_diff_dtype;
+    int pend_mode;               // 1 = pair (sfftb_gss_submit), 2 = shared-template tile, 3 = already completed synchronously
+    const void *pend_J, *pend_mJ;
     cudaEvent_t pendI, pendJ;    // events the next row pass of I / J has to wait for (host pipeline), or NULL
     cd *kap, *lam, *nuJ;
     double *R, *RJ, *RT, *RJT;
@@ -1422,6 +1424,53 @@ extern "C" int sfftb_gss_submit(sfftb_plan* p, const void* I, const void* J, con
     if (solution) CK(cudaMemcpyAsync(solution, p->sol, sizeof(double) * p->d.NEQ, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaEventRecord(p->evDone, p->stream));
     p->pending = 1; p->pend_diff = diff; p->pend_sol = solution; p->pend_dtype = dtype; p->pend_diff_dtype = diff_dtype;
+    p->pend_mode = 1;
+    return 0;
+}
+
+extern "C" int sfftb_gss_template(sfftb_plan* p, const void* J, const void* mJ, int memkind, int dtype,
+                                  double* solution, int sol_memkind, void* diff, int diff_memkind, int diff_dtype);
+
+// Shared-template tile from HOST buffers, asynchronous (see sfftb_gss_submit).  Until the plan holds the cached Cholesky
+// factor of the template (first tile) the call completes synchronously; afterwards the two H2D copies run on the copy
+// stream, and sfftb_gss_finish waits for this plan's work only.
+extern "C" int sfftb_gss_template_submit(sfftb_plan* p, const void* J, const void* mJ, int dtype, double* solution, void* diff, int diff_dtype) {
+    if (!p || !J || !mJ || !diff) return fail(SFFTB_EINVAL, "null argument");
+    if ((dtype != SFFTB_F64 && dtype != SFFTB_F32) || (diff_dtype != SFFTB_F64 && diff_dtype != SFFTB_F32)) return fail(SFFTB_EINVAL, "bad dtype");
+    if (!p->have_template) return fail(SFFTB_ESTATE, "no template has been prepared on this plan");
+    if (p->pending) return fail(SFFTB_ESTATE, "sfftb_gss_template_submit: the previous submission of this plan has not been finished");
+    CK(cudaSetDevice(p->device));
+    p->pend_diff = diff; p->pend_sol = solution; p->pend_dtype = dtype; p->pend_diff_dtype = diff_dtype; p->pend_J = J; p->pend_mJ = mJ;
+    if (!p->factor_cached || !p->chol_coop) {
+        int rc = sfftb_gss_template(p, J, mJ, SFFTB_MEM_HOST, dtype, solution, SFFTB_MEM_HOST, diff, SFFTB_MEM_HOST, diff_dtype);
+        if (rc) return rc;
+        p->pending = 1; p->pend_mode = 3;
+        return 0;
+    }
+    const bool f32 = p->cfg.storage == SFFTB_STORE_F32;
+    const size_t bytes = (size_t)p->d.N0 * p->d.N1 * (dtype == SFFTB_F64 ? 8 : 4);
+    if (!p->stC) { CK(cudaMalloc(&p->stC, sizeof(double) * (size_t)p->d.N0 * p->d.N1)); CK(cudaMalloc(&p->stD, sizeof(double) * (size_t)p->d.N0 * p->d.N1)); }
+    CK(cudaMemcpyAsync(p->stB, mJ, bytes, cudaMemcpyHostToDevice, p->stream2));
+    CK(cudaEventRecord(p->evCopy[0], p->stream2));
+    CK(cudaMemcpyAsync(p->stD, J, bytes, cudaMemcpyHostToDevice, p->stream2));
+    CK(cudaEventRecord(p->evCopy[1], p->stream2));
+    const void* tfit = p->tstate;
+    const void* tapp = (const char*)p->tstate + p->tstate_bytes / 2;
+    p->pendI = nullptr; p->pendJ = p->evCopy[0];
+    int rc = f32 ? fit_device<float2>(p, nullptr, p->stB, dtype, tfit) : fit_device<double2>(p, nullptr, p->stB, dtype, tfit);
+    if (rc) return rc;
+    p->pendI = nullptr; p->pendJ = p->evCopy[1];
+    void* hd = p->row_fast ? diff : nullptr;
+    rc = f32 ? apply_device<float2>(p, nullptr, p->stD, dtype, p->sol, p->stA, diff_dtype, tapp, false, hd)
+             : apply_device<double2>(p, nullptr, p->stD, dtype, p->sol, p->stA, diff_dtype, tapp, false, hd);
+    if (rc) return rc;
+    if (!p->row_fast) {
+        const size_t ob = (size_t)p->d.N0 * p->d.N1 * (diff_dtype == SFFTB_F64 ? 8 : 4);
+        CK(cudaMemcpyAsync(diff, p->stA, ob, cudaMemcpyDeviceToHost, p->stream));
+    }
+    if (solution) CK(cudaMemcpyAsync(solution, p->sol, sizeof(double) * p->d.NEQ, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaEventRecord(p->evDone, p->stream));
+    p->pending = 1; p->pend_mode = 2;
     return 0;
 }
 
@@ -1430,9 +1479,16 @@ extern "C" int sfftb_gss_finish(sfftb_plan* p) {
     if (!p->pending) return fail(SFFTB_ESTATE, "sfftb_gss_finish: nothing was submitted");
     CK(cudaSetDevice(p->device));
     p->pending = 0;
+    if (p->pend_mode == 3) return 0;                       // completed inside the submit call
     CK(cudaEventSynchronize(p->evDone));
     int rc = check_solver(p);
-    if (rc < 0) return rc;
+    if (rc < 0) { if (p->pend_mode == 2) p->factor_cached = 0; return rc; }
+    if (rc == 1 && p->pend_mode == 2) {
+        // cannot happen with a cached factor (no factorisation ran); be safe: drop the cache and redo the tile synchronously
+        p->factor_cached = 0;
+        return sfftb_gss_template(p, p->pend_J, p->pend_mJ, SFFTB_MEM_HOST, p->pend_dtype, p->pend_sol, SFFTB_MEM_HOST,
+                                  p->pend_diff, SFFTB_MEM_HOST, p->pend_diff_dtype);
+    }
     if (rc == 1) {
         // the Cholesky broke down and the LU fallback replaced the solution: apply again (rare; synchronous)
         const bool f32 = p->cfg.storage == SFFTB_STORE_F32;

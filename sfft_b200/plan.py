@@ -155,6 +155,20 @@ class Plan:
         B.check(self._L.sfftb_gss_submit(self._h, ptrs[0][0], ptrs[1][0], ptrs[2][0], ptrs[3][0], ptrs[0][2], sptr, dptr, ddt))
         self._inflight = (sol, diff, [q[3] for q in ptrs])          # keep the buffers alive until finish
 
+    def gss_template_submit(self, PixA_J, PixA_mJ, out_dtype=np.float64, Solution_out=None, DIFF_out=None):
+        """Queue one science tile against the cached template (host arrays); gss_finish() returns (Solution, DIFF)."""
+        self._check_pair(PixA_J, PixA_mJ)
+        ptrs = [_ptr_of(a) for a in (PixA_J, PixA_mJ)]
+        if len({(q[1], q[2]) for q in ptrs}) != 1 or ptrs[0][1] != B.MEM_HOST:
+            raise Exception('MeLOn ERROR: gss_template_submit takes two host arrays of one dtype')
+        sol = np.empty(self.NEQ, np.float64) if Solution_out is None else Solution_out
+        diff = np.empty(self.shape, out_dtype) if DIFF_out is None else DIFF_out
+        dptr = diff.ctypes.data if isinstance(diff, np.ndarray) else diff.data_ptr()
+        sptr = sol.ctypes.data if isinstance(sol, np.ndarray) else sol.data_ptr()
+        ddt = B.F64 if str(diff.dtype).endswith('float64') else B.F32
+        B.check(self._L.sfftb_gss_template_submit(self._h, ptrs[0][0], ptrs[1][0], ptrs[0][2], sptr, dptr, ddt))
+        self._inflight = (sol, diff, [q[3] for q in ptrs])
+
     def gss_finish(self):
         B.check(self._L.sfftb_gss_finish(self._h))
         sol, diff, _ = self._inflight
