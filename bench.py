@@ -243,7 +243,35 @@ def main():
         torch.cuda.synchronize(dev)
         bcast_ms = (time.time() - t0) * 1e3
 
+    # shared-template tiles resident in HBM: queued back to back on two plans that share the template state and the
+    # compute stream (sfftb_gss_template_submit with device pointers), so there is no host round trip between tiles
+    dpipe = None
+    if shared and not args.no_pipeline:
+        from sfft_b200.batch import TemplatePipeline
+        dpipe = TemplatePipeline(N0, N1, w, DK, DB, True, device=local, storage=storage, stream_ptr=stream.cuda_stream, first_plan=plan)
+        dpipe.set_template()
+        dpipe.plans[1].set_timing(True)
+        d_diff = [diff_d, torch.empty_like(diff_d)]
+        d_sol = [sol_d, torch.empty_like(sol_d)]
+        d_state = {'k': 0, 'busy': [False, False]}
+
+    def drain_device():
+        if dpipe is not None:
+            for slot in range(2):
+                if d_state['busy'][slot]:
+                    dpipe.plans[slot].gss_finish()
+                    d_state['busy'][slot] = False
+
     def step_device():
+        if dpipe is not None:
+            slot = d_state['k'] % 2
+            if d_state['busy'][slot]:
+                dpipe.plans[slot].gss_finish()
+            dpipe.plans[slot].gss_template_submit_device(devt['SCI'].data_ptr(), devt['mSCI'].data_ptr(), code,
+                                                         d_sol[slot].data_ptr(), d_diff[slot].data_ptr(), code)
+            d_state['busy'][slot] = True
+            d_state['k'] += 1
+            return
         if shared:
             plan.gss_template_device(devt['SCI'].data_ptr(), devt['mSCI'].data_ptr(), code, sol_d.data_ptr(),
                                      diff_d.data_ptr(), code)
@@ -265,12 +293,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(W):
+    for _ in range(max(W, 4) if dpipe is not None else W):
         step_device()
+    drain_device()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = plan.launch_count
+    count_launches = lambda: plan.launch_count + (dpipe.plans[1].launch_count if dpipe is not None else 0)
+    l0 = count_launches()
     stage = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -279,10 +309,11 @@ def main():
         step_device()
         for k, v in plan.timings().items():
             stage[k] = stage.get(k, 0.0) + v
+    drain_device()                                     # every tile of the timed region has completed
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1) / K
-    launches = plan.launch_count - l0
+    launches = count_launches() - l0
     stage = {k: v / K for k, v in stage.items()}
 
     # end-to-end leg: pinned host buffers in, host difference image out, through the public host-buffer API.
@@ -327,8 +358,7 @@ def main():
         pipe.close()
     if shared and not args.no_pipeline:
         from sfft_b200.batch import TemplatePipeline
-        tp = TemplatePipeline(N0, N1, w, DK, DB, True, device=local, storage=storage, stream_ptr=stream.cuda_stream, first_plan=plan)
-        tp.set_template()                              # the bench plan already holds the (broadcast) template state
+        tp = dpipe                                     # the two plans of the device leg (template state already cloned)
         diff_hs = [diff_h, torch.empty((N0, N1), dtype=tdt).pin_memory()]
         sol_hs = [torch.empty(plan.NEQ, dtype=torch.float64).pin_memory() for _ in range(2)]
 
@@ -348,6 +378,7 @@ def main():
         wall_ms = (time.perf_counter() - t0) * 1e3 / KE
         ms_e2e, e2e_mode = max(wall_ms, e2.elapsed_time(e3) / KE), 'TemplatePipeline: sfftb_gss_template_submit/finish on two plans sharing the template state'
         tp.close()
+        dpipe = None
     clocks = sampler.stop()
 
     t = torch.tensor([ms, ms_e2e, ms_e2e_single], dtype=torch.float64, device=dev)
@@ -387,7 +418,8 @@ def main():
                        'l2_policy': 'working set per step (inputs 4x%.0f MB + spectra %.0f MB) exceeds the 126 MB L2' % (
                            N0 * N1 * esz / 1e6, (DK + 2) * NH * N0 * csz / 1e6),
                        'fold': plan.dims['fold'], 'sub_len': plan.dims['sub_len'],
-                       'shared_template': shared, 'template_prepare_broadcast_ms': bcast_ms},
+                       'shared_template': shared, 'template_prepare_broadcast_ms': bcast_ms,
+                       'tiles_in_flight': 2 if (shared and not args.no_pipeline) else 1},
             'stage_ms': stage,
             'assembly_solve_ms': stage.get('fit_cols', 0) + stage.get('fit_reduce_fill', 0) + stage.get('fit_solve', 0),
             'solver': plan.last_solver,

@@ -109,9 +109,10 @@ int  sfftb_gss(sfftb_plan* plan, const void* PixA_I, const void* PixA_J, const v
  * from host memory (sfft/MultiEasySparsePacket.py:568-649 feeds one GPU from a host-side task queue) should be fed. */
 int  sfftb_gss_submit(sfftb_plan* plan, const void* PixA_I, const void* PixA_J, const void* PixA_mI, const void* PixA_mJ,
                       int img_dtype, double* solution, void* diff, int diff_dtype);
-/* The same for one science tile against the cached template (sfftb_gss_template with host buffers); completes inside the
- * call until the plan holds the template's Cholesky factor (first tile). */
-int  sfftb_gss_template_submit(sfftb_plan* plan, const void* PixA_J, const void* PixA_mJ, int img_dtype,
+/* The same for one science tile against the cached template; completes inside the call until the plan holds the
+ * template's Cholesky factor (first tile).  `memkind` covers the images and both outputs: host buffers are copied on
+ * the plan's copy stream, device buffers are used in place (tiles queued back to back leave no launch gaps). */
+int  sfftb_gss_template_submit(sfftb_plan* plan, const void* PixA_J, const void* PixA_mJ, int memkind, int img_dtype,
                                double* solution, void* diff, int diff_dtype);
 int  sfftb_gss_finish(sfftb_plan* plan);
 

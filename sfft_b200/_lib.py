@@ -79,7 +79,7 @@ def lib():
     L.sfftb_launch_count.argtypes = [vp]
     L.sfftb_launch_count.restype = C.c_longlong
     L.sfftb_gss_submit.argtypes = [vp, vp, vp, vp, vp, ip, vp, vp, ip]
-    L.sfftb_gss_template_submit.argtypes = [vp, vp, vp, ip, vp, vp, ip]
+    L.sfftb_gss_template_submit.argtypes = [vp, vp, vp, ip, ip, vp, vp, ip]
     L.sfftb_gss_finish.argtypes = [vp]
     L.sfftb_fits_decode.argtypes = [ip, vp, vp, ip, ip, ip, C.c_double, C.c_double, vp, ip]
     L.sfftb_fits_encode.argtypes = [ip, vp, vp, ip, ip, ip, ip, vp]

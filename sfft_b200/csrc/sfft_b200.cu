@@ -86,7 +86,7 @@ struct sfftb_plan {
     int pending;                 // a submitted GSS has not been finished yet
     void* pend_diff; double* pend_sol; int pend_dtype, pend_diff_dtype;
     int pend_mode;               // 1 = pair (sfftb_gss_submit), 2 = shared-template tile, 3 = already completed synchronously
-    const void *pend_J, *pend_mJ;
+    const void *pend_J, *pend_mJ; int pend_memkind;
     cudaEvent_t pendI, pendJ;    // events the next row pass of I / J has to wait for (host pipeline), or NULL
     cd *kap, *lam, *nuJ;
     double *R, *RJ, *RT, *RJT;
@@ -1434,17 +1434,37 @@ extern "C" int sfftb_gss_template(sfftb_plan* p, const void* J, const void* mJ, 
 // Shared-template tile from HOST buffers, asynchronous (see sfftb_gss_submit).  Until the plan holds the cached Cholesky
 // factor of the template (first tile) the call completes synchronously; afterwards the two H2D copies run on the copy
 // stream, and sfftb_gss_finish waits for this plan's work only.
-extern "C" int sfftb_gss_template_submit(sfftb_plan* p, const void* J, const void* mJ, int dtype, double* solution, void* diff, int diff_dtype) {
+extern "C" int sfftb_gss_template_submit(sfftb_plan* p, const void* J, const void* mJ, int memkind, int dtype, double* solution, void* diff,
+                                         int diff_dtype) {
     if (!p || !J || !mJ || !diff) return fail(SFFTB_EINVAL, "null argument");
+    if (memkind != SFFTB_MEM_HOST && memkind != SFFTB_MEM_DEVICE) return fail(SFFTB_EINVAL, "bad memkind");
     if ((dtype != SFFTB_F64 && dtype != SFFTB_F32) || (diff_dtype != SFFTB_F64 && diff_dtype != SFFTB_F32)) return fail(SFFTB_EINVAL, "bad dtype");
     if (!p->have_template) return fail(SFFTB_ESTATE, "no template has been prepared on this plan");
     if (p->pending) return fail(SFFTB_ESTATE, "sfftb_gss_template_submit: the previous submission of this plan has not been finished");
     CK(cudaSetDevice(p->device));
     p->pend_diff = diff; p->pend_sol = solution; p->pend_dtype = dtype; p->pend_diff_dtype = diff_dtype; p->pend_J = J; p->pend_mJ = mJ;
+    p->pend_memkind = memkind;
     if (!p->factor_cached || !p->chol_coop) {
-        int rc = sfftb_gss_template(p, J, mJ, SFFTB_MEM_HOST, dtype, solution, SFFTB_MEM_HOST, diff, SFFTB_MEM_HOST, diff_dtype);
+        int rc = sfftb_gss_template(p, J, mJ, memkind, dtype, solution, memkind, diff, memkind, diff_dtype);
         if (rc) return rc;
         p->pending = 1; p->pend_mode = 3;
+        return 0;
+    }
+    if (memkind == SFFTB_MEM_DEVICE) {
+        // images and outputs already on the device: nothing to copy, the tile is queued behind whatever the compute
+        // stream holds (back-to-back tiles leave no launch gaps)
+        const bool f32d = p->cfg.storage == SFFTB_STORE_F32;
+        const void* tfitd = p->tstate;
+        const void* tappd = (const char*)p->tstate + p->tstate_bytes / 2;
+        p->pendI = nullptr; p->pendJ = nullptr;
+        int rcd = f32d ? fit_device<float2>(p, nullptr, mJ, dtype, tfitd) : fit_device<double2>(p, nullptr, mJ, dtype, tfitd);
+        if (rcd) return rcd;
+        rcd = f32d ? apply_device<float2>(p, nullptr, J, dtype, p->sol, diff, diff_dtype, tappd)
+                   : apply_device<double2>(p, nullptr, J, dtype, p->sol, diff, diff_dtype, tappd);
+        if (rcd) return rcd;
+        if (solution) CK(cudaMemcpyAsync(solution, p->sol, sizeof(double) * p->d.NEQ, cudaMemcpyDeviceToDevice, p->stream));
+        CK(cudaEventRecord(p->evDone, p->stream));
+        p->pending = 1; p->pend_mode = 2;
         return 0;
     }
     const bool f32 = p->cfg.storage == SFFTB_STORE_F32;
@@ -1486,8 +1506,8 @@ extern "C" int sfftb_gss_finish(sfftb_plan* p) {
     if (rc == 1 && p->pend_mode == 2) {
         // cannot happen with a cached factor (no factorisation ran); be safe: drop the cache and redo the tile synchronously
         p->factor_cached = 0;
-        return sfftb_gss_template(p, p->pend_J, p->pend_mJ, SFFTB_MEM_HOST, p->pend_dtype, p->pend_sol, SFFTB_MEM_HOST,
-                                  p->pend_diff, SFFTB_MEM_HOST, p->pend_diff_dtype);
+        return sfftb_gss_template(p, p->pend_J, p->pend_mJ, p->pend_memkind, p->pend_dtype, p->pend_sol, p->pend_memkind,
+                                  p->pend_diff, p->pend_memkind, p->pend_diff_dtype);
     }
     if (rc == 1) {
         // the Cholesky broke down and the LU fallback replaced the solution: apply again (rare; synchronous)

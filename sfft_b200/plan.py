@@ -166,8 +166,13 @@ class Plan:
         dptr = diff.ctypes.data if isinstance(diff, np.ndarray) else diff.data_ptr()
         sptr = sol.ctypes.data if isinstance(sol, np.ndarray) else sol.data_ptr()
         ddt = B.F64 if str(diff.dtype).endswith('float64') else B.F32
-        B.check(self._L.sfftb_gss_template_submit(self._h, ptrs[0][0], ptrs[1][0], ptrs[0][2], sptr, dptr, ddt))
+        B.check(self._L.sfftb_gss_template_submit(self._h, ptrs[0][0], ptrs[1][0], B.MEM_HOST, ptrs[0][2], sptr, dptr, ddt))
         self._inflight = (sol, diff, [q[3] for q in ptrs])
+
+    def gss_template_submit_device(self, pJ, pmJ, img_dtype, psol, pdiff, diff_dtype):
+        """Device pointers in / out, queued on the plan's stream without a host synchronisation; gss_finish() waits."""
+        B.check(self._L.sfftb_gss_template_submit(self._h, pJ, pmJ, B.MEM_DEVICE, img_dtype, psol, pdiff, diff_dtype))
+        self._inflight = (None, None, None)
 
     def gss_finish(self):
         B.check(self._L.sfftb_gss_finish(self._h))
