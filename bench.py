@@ -243,12 +243,13 @@ def main():
         torch.cuda.synchronize(dev)
         bcast_ms = (time.time() - t0) * 1e3
 
-    # shared-template tiles resident in HBM: queued back to back on two plans that share the template state and the
-    # compute stream (sfftb_gss_template_submit with device pointers), so there is no host round trip between tiles
+    # shared-template tiles resident in HBM: two tiles in flight on two plans that share the template state
+    # (sfftb_gss_template_submit with device pointers; each plan on its own stream), no host round trip between tiles
     dpipe = None
     if shared and not args.no_pipeline:
         from sfft_b200.batch import TemplatePipeline
-        dpipe = TemplatePipeline(N0, N1, w, DK, DB, True, device=local, storage=storage, stream_ptr=stream.cuda_stream, first_plan=plan)
+        dpipe = TemplatePipeline(N0, N1, w, DK, DB, True, device=local, storage=storage, stream_ptr=None, first_plan=plan)
+        plan.set_stream(0)                             # every plan on its own stream (see TemplatePipeline)
         dpipe.set_template()
         dpipe.plans[1].set_timing(True)
         d_diff = [diff_d, torch.empty_like(diff_d)]

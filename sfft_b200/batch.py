@@ -85,9 +85,12 @@ class PairPipeline:
         from .plan import Plan
         self.plans = [Plan(N0, N1, KerHW, KerHW, KerPolyOrder, BGPolyOrder, ConstPhotRatio, device=device, storage=storage)
                       for _ in range(depth)]
-        if stream_ptr is None:
+        if not stream_ptr:
+            # one dedicated compute stream for all plans: their kernels serialise (two full-grid cooperative Cholesky
+            # kernels must never wait for each other's SMs), only the copies on the plans' copy streams overlap
             import torch
-            stream_ptr = torch.cuda.current_stream(torch.device('cuda', device)).cuda_stream
+            self._stream = torch.cuda.Stream(device=torch.device('cuda', device))
+            stream_ptr = self._stream.cuda_stream
         for pl in self.plans:
             pl.set_stream(stream_ptr)
         self._busy = [False] * depth
@@ -131,10 +134,10 @@ class PairPipeline:
 
 
 class TemplatePipeline:
-    """Science tiles in host memory against ONE shared template on one GPU (BASELINE config 4): two plans hold the same
-    template state and share one compute stream; tiles go through sfftb_gss_template_submit / sfftb_gss_finish
-    alternately, so the copies of tile k + 1 run under the kernels and the device-to-host copy of tile k.  Under
-    torch.distributed the template state comes from TemplateBatch's single broadcast (pass `state_from`)."""
+    """Science tiles against ONE shared template on one GPU (BASELINE config 4): two plans hold the same template state;
+    tiles go through sfftb_gss_template_submit / sfftb_gss_finish alternately, so the copies (host tiles) and kernels of
+    tile k + 1 run under the kernels and the device-to-host copy of tile k.  Under torch.distributed the first plan is
+    the one that received TemplateBatch's single broadcast (`first_plan`)."""
 
     def __init__(self, N0, N1, KerHW, KerPolyOrder=2, BGPolyOrder=2, ConstPhotRatio=True, device=0, storage='fp64',
                  stream_ptr=None, first_plan=None):
@@ -144,10 +147,13 @@ class TemplatePipeline:
         mk = lambda: Plan(N0, N1, KerHW, KerHW, KerPolyOrder, BGPolyOrder, ConstPhotRatio, device=device, storage=storage)
         self.plans = [first_plan if first_plan is not None else mk(), mk()]
         self._own = [first_plan is None, True]
-        if stream_ptr is None:
-            stream_ptr = torch.cuda.current_stream(torch.device('cuda', device)).cuda_stream
-        for pl in self.plans:
-            pl.set_stream(stream_ptr)
+        # stream_ptr given: both plans queue on it (tiles strictly one after the other).  None / 0: every plan keeps its OWN
+        # stream, so the kernels of tile k + 1 also overlap the latency-bound substitutions of tile k; that is safe because
+        # the only cooperative kernel of a cached-factor tile is the substitution kernel, whose grid is capped at half of the
+        # SMs, and the factorising first tile of each plan completes synchronously inside its submit call
+        if stream_ptr:
+            for pl in self.plans:
+                pl.set_stream(stream_ptr)
         self._busy = [False, False]
         self._k = 0
 

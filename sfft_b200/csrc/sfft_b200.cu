@@ -909,7 +909,9 @@ static int run_cholesky(sfftb_plan* p, int resolve = 0) {
         sa.sc = p->sc; sa.idx = p->idxmap; sa.sol = p->sol; sa.NEQ = p->d.NEQ;
         const int nblk = (n + CC_NB - 1) / CC_NB;
         void* args[] = {&sa};
-        CK(cudaLaunchCooperativeKernel((void*)chol_subst2_kernel, dim3(std::min(nblk, p->nsm)), dim3(CC_NT), args,
+        // at most half of the SMs: two plans (TemplatePipeline) may run their substitutions at the same time, and two
+        // cooperative grids must be able to be resident together; blocks beyond the grid are owned cyclically
+        CK(cudaLaunchCooperativeKernel((void*)chol_subst2_kernel, dim3(std::min(nblk, std::max(1, p->nsm / 2))), dim3(CC_NT), args,
                                        sizeof(double) * (3 * CC_NB * CC_DP + 64 + 128), p->stream));
         p->launches++;
         return 0;
