@@ -10,7 +10,7 @@ own row transforms (BASELINE config 4).
 """
 import numpy as np
 
-__all__ = ['shard_indices', 'TemplateBatch', 'gather_results']
+__all__ = ['shard_indices', 'TemplateBatch', 'gather_results', 'PairPipeline', 'TemplatePipeline', 'run_pairs_threaded']
 
 
 def shard_indices(n_items, rank, world):
@@ -199,3 +199,51 @@ class TemplatePipeline:
         for pl, own in zip(self.plans, self._own):
             if own:
                 pl.close()
+
+
+def run_pairs_threaded(pairs, devices, KerHW, KerPolyOrder=2, BGPolyOrder=2, ConstPhotRatio=True, storage='fp64',
+                       out_dtype=np.float64):
+    """The reference's own multi-GPU model (MultiEasy_SparsePacket.MESP_Cupy, sfft/MultiEasySparsePacket.py:391-420,
+    510-552, 931-943): ONE process, one host thread per GPU, every thread pulls the next pair from a shared queue and
+    runs it on its device -- here through a PairPipeline per thread, so that the copies of the next pair overlap the
+    kernels of the current one.  `pairs`: list of (I, J, mI, mJ) host arrays of one shape; `devices`: CUDA ordinals (an
+    ordinal may appear twice).  Returns the list of (Solution, DIFF) in the order of `pairs`."""
+    import threading
+    import torch
+    if not pairs:
+        return []
+    N0, N1 = pairs[0][0].shape
+    results = [None] * len(pairs)
+    lock = threading.Lock()
+    state = {'next': 0}
+    errors = []
+
+    def worker(dev):
+        try:
+            with torch.cuda.device(dev):
+                pipe = PairPipeline(N0, N1, KerHW, KerPolyOrder, BGPolyOrder, ConstPhotRatio, device=dev, storage=storage)
+                order = []
+                while True:
+                    with lock:                       # the task-status dict of MESP_Cupy (:510-552) as a counter
+                        k = state['next']
+                        state['next'] += 1
+                    if k >= len(pairs):
+                        break
+                    done = pipe.submit(*pairs[k], out_dtype=out_dtype)
+                    order.append(k)
+                    if done is not None:
+                        results[order.pop(0)] = done
+                for done in pipe.drain():
+                    results[order.pop(0)] = done
+                pipe.close()
+        except BaseException as e:                    # noqa: BLE001 -- reported to the caller below
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(int(d),)) for d in devices]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results
