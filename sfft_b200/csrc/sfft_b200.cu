@@ -21,7 +21,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -294,9 +297,20 @@ __global__ void __launch_bounds__(512) dbg_fft_kernel(FftDesc fd, const cd* __re
     }
 }
 
+// The dynamic shared-memory limit of a kernel is a property of the FUNCTION (per device), not of a plan: plans of
+// different shapes live side by side (and are created from different host threads), so the limit is only ever raised.
 template <typename T>
 static int set_smem(T kernel, size_t bytes) {
-    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    static std::mutex mtx;
+    static std::map<std::pair<int, const void*>, size_t> cur;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mtx);
+    size_t& c = cur[std::make_pair(dev, (const void*)kernel)];
+    if (bytes > c) {
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        c = bytes;
+    }
     return 0;
 }
 
@@ -1814,7 +1828,7 @@ extern "C" int sfftb_dbg_fft1d(int device, int n, int nbatch, int sign, const do
     cudaError_t e = cudaMalloc(&din, bytes);
     if (e == cudaSuccess) e = cudaMalloc(&dout, bytes);
     if (e == cudaSuccess) e = cudaMemcpy(din, in, bytes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dbg_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && set_smem(dbg_fft_kernel, smem)) e = cudaErrorInvalidValue;
     if (e == cudaSuccess) {
         dbg_fft_kernel<<<(nbatch + ppc - 1) / ppc, 512, smem>>>(fd, tw, din, dout, nbatch, ppc, pitch, sign < 0 ? -1.0 : 1.0);
         e = cudaGetLastError();
