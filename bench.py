@@ -225,7 +225,7 @@ def main():
     sol_d = torch.empty(plan.NEQ, dtype=torch.float64, device=dev)
     sol_h = np.empty(plan.NEQ, np.float64)
     stream = torch.cuda.current_stream(dev)
-    plan.set_stream(stream.cuda_stream)
+    plan.bind_torch_stream(stream)
     plan.set_timing(True)
     L = B.lib()
 

@@ -81,7 +81,9 @@ const char* sfftb_last_error(void);
 int  sfftb_plan_create(sfftb_plan** out, const sfftb_config* cfg);
 int  sfftb_plan_destroy(sfftb_plan* plan);
 int  sfftb_plan_dims(const sfftb_plan* plan, sfftb_dims* out);
-/* Run all work of this plan on `cuda_stream` (a cudaStream_t; NULL = the plan's own stream). */
+/* Run all work of this plan on `cuda_stream` (a cudaStream_t; NULL = the plan's own stream, which is created
+ * cudaStreamNonBlocking and therefore does NOT synchronise with the legacy default stream: a caller that produces its
+ * inputs on the default stream passes cudaStreamLegacy, (cudaStream_t)0x1, or cudaStreamPerThread explicitly). */
 int  sfftb_plan_set_stream(sfftb_plan* plan, void* cuda_stream);
 int  sfftb_plan_sync(sfftb_plan* plan);
 

@@ -66,7 +66,7 @@ def _cp_on_device(FITS_REF, FITS_SCI, FITS_mREF, FITS_mSCI, ForceConv, GKerHW, K
             I, J, mI, mJ = imgs['SCI'], imgs['REF'], imgs['mSCI'], imgs['mREF']
         sol_d = torch.empty(plan.NEQ, dtype=torch.float64, device=dev)
         diff_d = torch.empty(shape, dtype=torch.float64, device=dev)
-        plan.set_stream(stream.cuda_stream)
+        plan.bind_torch_stream(stream)
         plan.gss_device(I.data_ptr(), J.data_ptr(), mI.data_ptr(), mJ.data_ptr(), B.F64, sol_d.data_ptr(), diff_d.data_ptr(), B.F64)
         B.check(L.sfftb_nan_mask_apply(dev_i, stream.cuda_stream, diff_d.data_ptr(), B.F64, mask.data_ptr() if fl[0] else None, n,
                                        -1.0 if ForceConv == 'SCI' else 1.0))

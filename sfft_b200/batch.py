@@ -56,6 +56,11 @@ class TemplateBatch:
             import torch.distributed as dist
             state = self.backend.template_state_tensor()
             dist.broadcast(state, src=self.src, group=self.group)
+            if state.is_cuda:
+                # NCCL broadcasts are ordered against torch's current stream only and do not block the host, while the
+                # plan works on its own stream: wait until the state has landed before any tile may read it
+                import torch
+                torch.cuda.synchronize(state.device)
             if self.rank != self.src:
                 self.backend.template_mark_ready()
         self.ready = True

@@ -99,114 +99,8 @@ __global__ void __launch_bounds__(FIR_NT) apply_fir_kernel(FirArgs a, const TSt*
     }
 }
 
-// ---- version 2: staged, conversion-free inner loop -------------------------------------------------------------------
-// One CTA = one column k1 x FIR2_CH output rows.  The four stored planes (g_0..g_DK, J) of the chunk plus the
-// w0-row halo are staged in shared memory as complex doubles (one fp32->fp64 conversion per element instead of one
-// per tap), together with cx of every staged row.  Threads own FIR2_CH / 256 outputs each (interleaved rows, so the
-// shared-memory reads of a warp are unit stride); the tap loop is outermost so that the Fij complex taps h_A[a;k1]
-// are read once per tap for all outputs of the thread.  Per (tap, output): DK + 2 shared loads, 18 fp64 FMAs (DK = 2).
-#define FIR2_NT 256
-#define FIR2_CH 512
-#define FIR2_R (FIR2_CH / FIR2_NT)
-
 // index of plane (i, j) in REF_ij order (i-major, j = 0 .. DK - i; sfft/sfftcore/SFFTSubtract.py:61-70)
 __host__ __device__ constexpr int fir_plane(int DK, int i, int j) { return i * (DK + 1) - (i * (i - 1)) / 2 + j; }
-
-// smem: h[Fij][L0] cd | cA[Fij] double (padded to cd) | st[nj + 1][CH + 2 w0] cd | cxs[CH + 2 w0] double
-template <typename TSt, int DK>
-__global__ void __launch_bounds__(FIR2_NT) apply_fir2_kernel(FirArgs a, const TSt* __restrict__ gI, const TSt* gJ,
-                                                             const double* __restrict__ sol, TSt* outD)
-{
-    constexpr int NJ = DK + 1, Fij = (DK + 1) * (DK + 2) / 2;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int L0 = 2 * a.w0 + 1, L1 = 2 * a.w1 + 1, Fab = L0 * L1;
-    const int W = FIR2_CH + 2 * a.w0;
-    cd* h = reinterpret_cast<cd*>(smem_raw);
-    double* cA = reinterpret_cast<double*>(h + Fij * L0);
-    cd* st = reinterpret_cast<cd*>(cA + 16);
-    double* cxs = reinterpret_cast<double*>(st + (size_t)(NJ + 1) * W);
-    const int tid = threadIdx.x;
-    const int k1 = blockIdx.x;
-    const int rbeg = blockIdx.y * FIR2_CH;
-    const double invN = 1.0 / ((double)a.N0 * (double)a.N1);
-    const double inv0 = 1.0 / (double)a.N0;
-
-    // stage rows rbeg - w0 .. rbeg + CH + w0 - 1 (circular) of every plane
-    for (int idx = tid; idx < W; idx += FIR2_NT) {
-        int r = rbeg - a.w0 + idx;
-        r %= a.N0; if (r < 0) r += a.N0;
-        cxs[idx] = (r + 1) * inv0;
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) st[(size_t)j * W + idx] = load_c(gI + ((size_t)j * a.NH + k1) * a.N0 + r);
-        if (idx >= a.w0 && idx < a.w0 + FIR2_CH && rbeg + idx - a.w0 < a.N0)      // J: own rows only (outD aliases gJ)
-            st[(size_t)NJ * W + idx] = load_c(gJ + (size_t)k1 * a.N0 + r);
-    }
-    for (int idx = tid; idx < Fij * L0; idx += FIR2_NT) {
-        const int A = idx / L0, ia = idx - A * L0;
-        const double* s = sol + (size_t)A * Fab + (size_t)ia * L1;
-        cd acc = cmake(0, 0);
-        for (int ib = 0; ib < L1; ++ib) {
-            const int b = ib - a.w1;
-            const cd w = a.tw1[imod((int)(((long long)b * k1) % a.N1), a.N1)];       // e^{-2 pi i b k1 / N1}
-            acc.x = fma(s[ib], w.x, acc.x);
-            acc.y = fma(s[ib], w.y, acc.y);
-        }
-        h[idx] = cscale(acc, invN);
-    }
-    for (int A = tid; A < Fij; A += FIR2_NT) {
-        const double* s = sol + (size_t)A * Fab;
-        double t = 0.0;
-        for (int ab = 0; ab < Fab; ++ab) t += s[ab];
-        cA[A] = (t - s[a.w0 * L1 + a.w1]) * invN;
-    }
-    __syncthreads();
-
-    // plane order (REF_ij): A = (i, j) enumerated i-major; index of (i, j) is a.plane_of[i][j]
-    cd acc[FIR2_R];
-#pragma unroll
-    for (int o = 0; o < FIR2_R; ++o) {
-        const int n = a.w0 + tid + FIR2_NT * o;          // staged index of the output row
-        const double cx = cxs[n];
-        cd v = st[(size_t)NJ * W + n];
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            double t = 0.0;
-#pragma unroll
-            for (int i = DK - j; i >= 0; --i) t = fma(t, cx, cA[fir_plane(DK, i, j)]);
-            const cd g = st[(size_t)j * W + n];
-            v.x = fma(t, g.x, v.x);
-            v.y = fma(t, g.y, v.y);
-        }
-        acc[o] = v;
-    }
-    for (int ia = 0; ia < L0; ++ia) {
-        cd hh[Fij];
-#pragma unroll
-        for (int A = 0; A < Fij; ++A) hh[A] = h[A * L0 + ia];
-#pragma unroll
-        for (int o = 0; o < FIR2_R; ++o) {
-            const int n = a.w0 + tid + FIR2_NT * o - (ia - a.w0);     // staged index of the source row r - a
-            const double cx = cxs[n];
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                cd t = cmake(0.0, 0.0);
-#pragma unroll
-                for (int i = DK - j; i >= 0; --i) {
-                    const cd c = hh[fir_plane(DK, i, j)];
-                    t = cmake(fma(t.x, cx, c.x), fma(t.y, cx, c.y));
-                }
-                const cd g = st[(size_t)j * W + n];
-                acc[o].x = fma(-t.x, g.x, acc[o].x); acc[o].x = fma(t.y, g.y, acc[o].x);
-                acc[o].y = fma(-t.x, g.y, acc[o].y); acc[o].y = fma(-t.y, g.x, acc[o].y);
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 0; o < FIR2_R; ++o) {
-        const int r = rbeg + tid + FIR2_NT * o;
-        if (r < a.N0) store_c(outD + (size_t)k1 * a.N0 + r, acc[o]);
-    }
-}
 
 // ---- version 3: register sliding window -----------------------------------------------------------------------------
 // h_A[a; k1] and c_A are tabulated once per apply by fir_taps_kernel (they depend on the solution and k1 only).
@@ -219,6 +113,7 @@ __global__ void __launch_bounds__(FIR2_NT) apply_fir2_kernel(FirArgs a, const TS
 #define FIR3_CH (FIR3_NT * FIR3_R)
 
 // taps[k1][A][ia] = (1/N) sum_b a_Aab e^{-2 pi i b k1 / N1};  cAout[A] = (sum_ab a_Aab - a_A00) / N
+#ifdef SFFTB_TU_APPLY
 __global__ void __launch_bounds__(128) fir_taps_kernel(FirArgs a, const double* __restrict__ sol, cd* __restrict__ taps,
                                                        double* __restrict__ cAout)
 {
@@ -245,6 +140,7 @@ __global__ void __launch_bounds__(128) fir_taps_kernel(FirArgs a, const double* 
             cAout[A] = (t - s[a.w0 * L1 + a.w1]) * invN;
         }
 }
+#endif  // SFFTB_TU_APPLY
 
 // smem: h[Fij][L0] cd | cA[16] double | st[nj][R * WP] cd | cxs[R * WP] double,  WP = ceil((CH + 2 w0) / R)
 template <typename TSt, int DK>

@@ -37,6 +37,7 @@ struct CholArgs {
                                      //    with the same matrix; yv holds a new scaled right-hand side -> substitutions only
 };
 
+#ifdef SFFTB_TU_CHOL
 __device__ __forceinline__ unsigned long long cc_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define CC_STAMP(slot) do { if (a.dbg && tid == 0) a.dbg[(slot)] = cc_gtime(); } while (0)
 
@@ -904,3 +905,4 @@ __global__ void __launch_bounds__(CC_NT, 1) chol_subst2_kernel(SubstArgs2 a)
         }
     }
 }
+#endif  // SFFTB_TU_CHOL

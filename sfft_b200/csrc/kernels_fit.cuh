@@ -202,6 +202,7 @@ struct ReduceArgs {
 };
 
 // R[row][l1] = (1/N1) sum_{k1} wt(k1) Re(kap[row][k1] e^{+2 pi i k1 m1 / N1})
+#ifdef SFFTB_TU_FIT
 __global__ void __launch_bounds__(256) lag_reduce_kernel(ReduceArgs a, const cd* __restrict__ kap, double* __restrict__ R,
                                                          double* __restrict__ RJ)
 {
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(256) lag_reduce_kernel(ReduceArgs a, const cd*
         if (lane == 0) out[l1] = s;
     }
 }
+#endif  // SFFTB_TU_FIT
 
 struct PolyReduceArgs {
     int N1, NH, w1, DB, Fpq, Fij;
@@ -243,6 +245,7 @@ struct PolyReduceArgs {
 };
 
 // RT[A][pq][ia][ib] = (1/N1) sum_k1 wt Re(lam[(A,p,ia)][k1] conj(Q_q[k1]) e^{-2 pi i k1 b / N1});  RJT[pq] likewise
+#ifdef SFFTB_TU_FIT
 __global__ void __launch_bounds__(256) poly_reduce_kernel(PolyReduceArgs a, const cd* __restrict__ lam, const cd* __restrict__ nuJ,
                                                           double* __restrict__ RT, double* __restrict__ RJT)
 {
@@ -283,6 +286,7 @@ __global__ void __launch_bounds__(256) poly_reduce_kernel(PolyReduceArgs a, cons
         }
     }
 }
+#endif  // SFFTB_TU_FIT
 
 // ---- normal-equation fill (FillLS_* + Remove_LSFStripes restated through LHMAT = D^T D / N) -------------------------
 struct FillArgs {
@@ -302,6 +306,7 @@ struct FillArgs {
     int sca_on; signed char sca[16];
 };
 
+#ifdef SFFTB_TU_MAIN
 __device__ __forceinline__ double fill_R(const FillArgs& f, int A, int B, int m0, int m1) {
     if (A > B) { int t = A; A = B; B = t; m0 = -m0; m1 = -m1; }
     const int pidx = A * f.Fij - (A * (A - 1)) / 2 + (B - A);
@@ -413,3 +418,4 @@ __global__ void fill_matrix_kernel(FillArgs f, const int* __restrict__ idx, int 
     if (!isfinite(v)) atomicExch(&info[1], 1);
     Aug[(size_t)rr * ld + cc] = v;
 }
+#endif  // SFFTB_TU_MAIN

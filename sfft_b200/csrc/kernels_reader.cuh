@@ -12,6 +12,7 @@ struct ReaderArgs {
     double* fscal;            // (nq) or null
 };
 
+#ifdef SFFTB_TU_MAIN
 // One CTA per requested coordinate.  K_q[a,b] = sum_ij x^i y^j s_ij[a,b] with s = a_ijab / N in the Cartesian-delta
 // basis: the centre tap of every (i,j) block becomes 2 s_ij[0,0] - sum_ab s_ij[a,b] (SVKDict_SFFT2ST.convert, :102-114);
 // the flux scaling is sum_ij s_ij[0,0] x^i y^j (:160-181).
@@ -52,3 +53,4 @@ __global__ void __launch_bounds__(256) realize_kernel(ReaderArgs a)
         a.fscal[q] = v;
     }
 }
+#endif  // SFFTB_TU_MAIN

@@ -11,6 +11,7 @@ namespace cg = cooperative_groups;
 
 #define CH_NB 64
 
+#ifdef SFFTB_TU_CHOL
 // Factor the kb x kb diagonal block at k0 (every CTA redundantly, in shared memory), then solve the rows below it:
 // X <- X L_kk^{-T}.  Matrix is row-major with leading dimension ld, ntot rows (n + 1 with the rhs row), n columns.
 __global__ void __launch_bounds__(128) chol_panel_kernel(double* __restrict__ A, int ld, int ntot, int n, int k0, int* __restrict__ info)
@@ -244,3 +245,4 @@ __global__ void __launch_bounds__(512) lu_solve_kernel(double* __restrict__ A, i
         for (int c = tid; c < n; c += nthr) sol[idx[c]] = lcol[c] * sc[c];
     }
 }
+#endif  // SFFTB_TU_CHOL

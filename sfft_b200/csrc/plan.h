@@ -1,0 +1,201 @@
+// plan.h -- the plan structure and the helpers shared by the translation units of libsfft_b200.so.
+//
+// The library is built from several .cu files (one per kernel family) so that they compile in parallel; every file
+// includes this header.  Kernel TEMPLATES are instantiated only where they are launched; the non-template kernels are
+// compiled in exactly one translation unit (guards SFFTB_TU_*).
+#pragma once
+#include "../../include/sfft_b200.h"
+#include "common.cuh"
+#include "fft_smem.cuh"
+#include "kernels_row.cuh"
+#include "kernels_fit.cuh"
+#include "kernels_solve.cuh"
+#include "kernels_chol.cuh"
+#include "kernels_apply.cuh"
+#include "kernels_row_fast.cuh"
+#include "kernels_row_v8.cuh"
+#include "kernels_fit_seg.cuh"
+#include "kernels_fit_seg3.cuh"
+#include "kernels_reader.cuh"
+#include "kernels_fitsio.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <algorithm>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <map>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+// thread-local error message (sfft_b200.cu); returns `code`
+int sfftb_fail(int code, const char* fmt, ...);
+#define fail sfftb_fail
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(SFFTB_ECUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
+    } while (0)
+
+#define CKL(p)                                                                                           \
+    do {                                                                                                 \
+        (p)->launches++;                                                                                 \
+        cudaError_t e_ = cudaGetLastError();                                                             \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(SFFTB_ECUDA, "kernel launch failed: %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+enum { EV_START = 0, EV_ROWS, EV_COL, EV_RED, EV_SOLVE, EV_A0, EV_AROWS, EV_ACOL, EV_AINV, EV_COUNT };
+
+struct sfftb_plan {
+    sfftb_config cfg;
+    sfftb_dims d;
+    int device;
+    int nsm;
+    size_t max_smem;
+    cudaStream_t stream, own_stream;
+    cudaStream_t stream2;        // side stream: forward row pass of the apply step overlapped with the solve
+    cudaEvent_t evFork, evJoin;
+    int overlap;                 // 1: sfftb_gss overlaps the apply row pass with the Cholesky solve (device images)
+    int row_grid_limit;          // > 0: cap of the persistent row-kernel grid (half the SMs while overlapped)
+    int chol_grid_limit;
+    // tables
+    cd *tw0, *tw1, *twMf, *twH, *Q;
+    cd *tabA, *tabB_row, *tabC_row;   // register-engine twiddle tables
+    cd *vt8_8, *vt64_8, *vt64_4, *vt256_4, *vt512_4;   // 8-values-per-thread engine tables
+    RowV8Args rowv;
+    VTabs vtabs;
+    size_t smem_sfit3;
+    int row_v8;                  // 0 or the engine length H
+    size_t smem_rowv;
+    double* PHI;
+    int *idxmap, *ident;
+    // workspaces
+    void *gI, *gJ;               // transposed row spectra (storage type); gJ doubles as the FDIFF column buffer
+    void *stA, *stB;             // device staging for host images / host diff
+    void *stC, *stD;             // second staging pair (host GSS: the apply images are copied while the fit computes)
+    cudaEvent_t evCopy[4], evStart;
+    cudaEvent_t evDone;          // end of the work queued by sfftb_gss_submit
+    int pending;                 // a submitted GSS has not been finished yet
+    void* pend_diff; double* pend_sol; int pend_dtype, pend_diff_dtype;
+    int pend_mode;               // 1 = pair (sfftb_gss_submit), 2 = shared-template tile, 3 = already completed synchronously
+    const void *pend_J, *pend_mJ; int pend_memkind;
+    cudaEvent_t pendI, pendJ;    // events the next row pass of I / J has to wait for (host pipeline), or NULL
+    cd *kap, *lam, *nuJ;
+    double *R, *RJ, *RT, *RJT;
+    double *Aug, *sc, *diagU, *sol;
+    double *cholW, *cholY, *cholX;   // cooperative Cholesky: inverse diagonal blocks, back-substitution vectors
+    unsigned* cholBar;
+    unsigned* substFlags;        // 2 * nblk epoch tags of the dataflow substitution kernel
+    unsigned substEpoch;
+    int subst_ok;
+    int sca_n;                   // SEPARATE-VARYING polynomial scaling: number of scaling basis functions (0 = off)
+    double* solEff;              // solution with the centre taps moved onto the planes of the scaling basis (apply step)
+    double *regSST, *regI, *regC, *regD;       // kernel regulariser factors (sfftb_set_regularizer)
+    cd *bluTw, *bluC, *bluB;     // Bluestein tables of the generic row pass (row lengths with a prime factor > 13)
+    ulonglong2* substMsg;        // 2 * nblk * 64 {value | epoch} messages of chol_subst2_kernel
+    int chol_coop;
+    double* exportbuf;
+    int ld, nsolve;
+    int* info;                   // device: [0] cholesky pivot, [1] non-finite, [2] lu pivot
+    int* info_h;                 // pinned
+    // kernel arguments
+    ColArgs cfit;
+    FirArgs fir;
+    RowArgs row;
+    RowInvArgs rinv;
+    RowFastArgs rowf;
+    RowInvFastArgs rinvf;
+    int row_fast;                // 0 or the engine length H
+    // segmented fit path
+    SegFitArgs sfit;
+    int fit_seg;                 // 2: fit_seg3_kernel + lag_reduce2 path, 0: folded-slice generic kernel
+    int fit_generic_ok;          // the folded-slice kernel has a valid geometry for this shape
+    int grid_sfit;
+    cd* kap2;                    // [NH][nrows]
+    double* part;                // [ksplit][nrows][4 w1 + 1]
+    LagReduce2Args red2;
+    LagFinishArgs fin2;
+    ReduceArgs red;
+    PolyReduceArgs pred;
+    FillArgs fill;
+    size_t smem_fit, smem_fir, smem_row, smem_fir3;
+    cd* firTaps; double* firCA;
+    void* tstate;                // cached template row spectra: [fit: mI planes | apply: I planes], storage type
+    size_t tstate_bytes;
+    int have_template;
+    int factor_cached;           // template path: Aug / cholW hold the Cholesky factor of the (tile independent) LHMAT
+    int resolves;                // number of solves served from the cached factor (diagnostics)
+    int grid_fit;
+    int nrowsK, nrowsL;
+    // state
+    cudaEvent_t ev[EV_COUNT];
+    int timing;
+    float ms[7];
+    long long launches;
+    int last_solver;
+    int have_fit;
+};
+
+static inline int init_generic_radix_tables() {
+    const int rad[4] = {5, 7, 11, 13};
+    double2 h[4][16];
+    memset(h, 0, sizeof h);
+    const long double tp = 6.283185307179586476925286766559005768L;
+    for (int k = 0; k < 4; ++k)
+        for (int q = 0; q < rad[k]; ++q) {
+            const long double ang = tp * q / rad[k];
+            h[k][q].x = (double)cosl(ang);
+            h[k][q].y = (double)(-sinl(ang));
+        }
+    CK(cudaMemcpyToSymbol(c_wgen, h, sizeof h));
+    return 0;
+}
+
+// The dynamic shared-memory limit of a kernel is a property of the FUNCTION (per device), not of a plan: plans of
+// different shapes live side by side (and are created from different host threads), so the limit is only ever raised.
+template <typename T>
+static int set_smem(T kernel, size_t bytes) {
+    static std::mutex mtx;
+    static std::map<std::pair<int, const void*>, size_t> cur;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mtx);
+    size_t& c = cur[std::make_pair(dev, (const void*)kernel)];
+    if (bytes > c) {
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        c = bytes;
+    }
+    return 0;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+#define EVREC(p, k) do { if ((p)->timing) CK(cudaEventRecord((p)->ev[k], (p)->stream)); } while (0)
+
+// ---- family entry points (one translation unit each) -----------------------------------------------------------------
+// tu_rows.cu
+int rows_setup(sfftb_plan* p);
+template <typename TSt> int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj);
+template <typename TSt> int launch_row_inv(sfftb_plan* p, const double* bpq, void* ddiff, int diff_dtype, void* hdiff);
+// tu_fit.cu
+int fit_setup(sfftb_plan* p);
+template <typename TSt> int launch_fit_cols(sfftb_plan* p, const TSt* gIsrc, bool jonly);
+// tu_chol.cu
+int chol_setup(sfftb_plan* p);
+int run_cholesky(sfftb_plan* p, int resolve = 0);
+int run_lu(sfftb_plan* p);
+// tu_apply.cu
+int apply_setup(sfftb_plan* p);
+template <typename TSt> int launch_fir(sfftb_plan* p, const TSt* gIsrc, const double* dsol);
+// sfft_b200.cu
+int upload_twiddles(int n, cd** out);
+int upload_engine_table(int Ns, int R, cd** out);

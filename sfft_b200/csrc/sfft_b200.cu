@@ -1,36 +1,11 @@
 // sfft_b200.cu -- plan management and the C ABI of libsfft_b200.so (see include/sfft_b200.h).
-#include "../../include/sfft_b200.h"
-#include "common.cuh"
-#include "fft_smem.cuh"
-#include "kernels_row.cuh"
-#include "kernels_fit.cuh"
-#include "kernels_solve.cuh"
-#include "kernels_chol.cuh"
-#include "kernels_apply.cuh"
-#include "kernels_row_fast.cuh"
-#include "kernels_row_v8.cuh"
-#include "kernels_fit_fast.cuh"
-#include "kernels_fit_seg.cuh"
-#include "kernels_fit_seg3.cuh"
-#include "kernels_reader.cuh"
-#include "kernels_fitsio.cuh"
-
-#include <math.h>
-#include <stdarg.h>
-#include <algorithm>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-#include <map>
-#include <mutex>
-#include <string>
-#include <utility>
-#include <vector>
+#define SFFTB_TU_MAIN
+#include "plan.h"
 
 // ---------------------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 
-static int fail(int code, const char* fmt, ...) {
+int sfftb_fail(int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -39,117 +14,6 @@ static int fail(int code, const char* fmt, ...) {
     g_err = buf;
     return code;
 }
-
-#define CK(call)                                                                                         \
-    do {                                                                                                 \
-        cudaError_t e_ = (call);                                                                         \
-        if (e_ != cudaSuccess)                                                                           \
-            return fail(SFFTB_ECUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
-    } while (0)
-
-#define CKL(p)                                                                                           \
-    do {                                                                                                 \
-        (p)->launches++;                                                                                 \
-        cudaError_t e_ = cudaGetLastError();                                                             \
-        if (e_ != cudaSuccess)                                                                           \
-            return fail(SFFTB_ECUDA, "kernel launch failed: %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
-
-enum { EV_START = 0, EV_ROWS, EV_COL, EV_RED, EV_SOLVE, EV_A0, EV_AROWS, EV_ACOL, EV_AINV, EV_COUNT };
-
-struct sfftb_plan {
-    sfftb_config cfg;
-    sfftb_dims d;
-    int device;
-    int nsm;
-    size_t max_smem;
-    cudaStream_t stream, own_stream;
-    cudaStream_t stream2;        // side stream: forward row pass of the apply step overlapped with the solve
-    cudaEvent_t evFork, evJoin;
-    int overlap;                 // 1: sfftb_gss overlaps the apply row pass with the Cholesky solve (device images)
-    int row_grid_limit;          // > 0: cap of the persistent row-kernel grid (half the SMs while overlapped)
-    int chol_grid_limit;
-    // tables
-    cd *tw0, *tw1, *twMf, *twH, *Q;
-    cd *tabA, *tabB_row, *tabC_row;   // register-engine twiddle tables
-    cd *vt8_8, *vt64_8, *vt64_4, *vt256_4, *vt512_4;   // 8-values-per-thread engine tables
-    RowV8Args rowv;
-    VTabs vtabs;
-    size_t smem_sfit3;
-    int row_v8;                  // 0 or the engine length H
-    size_t smem_rowv;
-    double* PHI;
-    int *idxmap, *ident;
-    // workspaces
-    void *gI, *gJ;               // transposed row spectra (storage type); gJ doubles as the FDIFF column buffer
-    void *stA, *stB;             // device staging for host images / host diff
-    void *stC, *stD;             // second staging pair (host GSS: the apply images are copied while the fit computes)
-    cudaEvent_t evCopy[4], evStart;
-    cudaEvent_t evDone;          // end of the work queued by sfftb_gss_submit
-    int pending;                 // a submitted GSS has not been finished yet
-    void* pend_diff; double* pend_sol; int pend_dtype, pend_diff_dtype;
-    int pend_mode;               // 1 = pair (sfftb_gss_submit), 2 = shared-template tile, 3 = already completed synchronously
-    const void *pend_J, *pend_mJ; int pend_memkind;
-    cudaEvent_t pendI, pendJ;    // events the next row pass of I / J has to wait for (host pipeline), or NULL
-    cd *kap, *lam, *nuJ;
-    double *R, *RJ, *RT, *RJT;
-    double *Aug, *sc, *diagU, *sol;
-    double *cholW, *cholY, *cholX;   // cooperative Cholesky: inverse diagonal blocks, back-substitution vectors
-    unsigned* cholBar;
-    unsigned* substFlags;        // 2 * nblk epoch tags of the dataflow substitution kernel
-    unsigned substEpoch;
-    int subst_ok;
-    int sca_n;                   // SEPARATE-VARYING polynomial scaling: number of scaling basis functions (0 = off)
-    double* solEff;              // solution with the centre taps moved onto the planes of the scaling basis (apply step)
-    double *regSST, *regI, *regC, *regD;       // kernel regulariser factors (sfftb_set_regularizer)
-    cd *bluTw, *bluC, *bluB;     // Bluestein tables of the generic row pass (row lengths with a prime factor > 13)
-    ulonglong2* substMsg;        // 2 * nblk * 64 {value | epoch} messages of chol_subst2_kernel
-    int chol_coop;
-    double* exportbuf;
-    int ld, nsolve;
-    int* info;                   // device: [0] cholesky pivot, [1] non-finite, [2] lu pivot
-    int* info_h;                 // pinned
-    // kernel arguments
-    ColArgs cfit;
-    FirArgs fir;
-    RowArgs row;
-    RowInvArgs rinv;
-    RowFastArgs rowf;
-    RowInvFastArgs rinvf;
-    FastFitArgs ffit;
-    int row_fast;                // 0 or the engine length H
-    int fit_fast;                // 0 or VI
-    size_t smem_ffit;
-    int grid_ffit;
-    // segmented fit path
-    SegFitArgs sfit;
-    int fit_seg;                 // 1: fit_seg_kernel + lag_reduce2 path
-    size_t smem_sfit;
-    int grid_sfit;
-    cd* kap2;                    // [NH][nrows]
-    double* part;                // [ksplit][nrows][4 w1 + 1]
-    LagReduce2Args red2;
-    LagFinishArgs fin2;
-    ReduceArgs red;
-    PolyReduceArgs pred;
-    FillArgs fill;
-    size_t smem_fit, smem_fir, smem_row, smem_fir2, smem_fir3;
-    cd* firTaps; double* firCA;
-    void* tstate;                // cached template row spectra: [fit: mI planes | apply: I planes], storage type
-    size_t tstate_bytes;
-    int have_template;
-    int factor_cached;           // template path: Aug / cholW hold the Cholesky factor of the (tile independent) LHMAT
-    int resolves;                // number of solves served from the cached factor (diagnostics)
-    int grid_fit;
-    int nrowsK, nrowsL;
-    // state
-    cudaEvent_t ev[EV_COUNT];
-    int timing;
-    float ms[7];
-    long long launches;
-    int last_solver;
-    int have_fit;
-};
 
 // ---------------------------------------------------------------------------------------------------------------
 static bool make_fft_desc(int n, FftDesc* fd) {
@@ -176,7 +40,7 @@ static bool fft_fits_threads(const FftDesc& fd, int nthr) {
     return true;
 }
 
-static int upload_twiddles(int n, cd** out) {
+int upload_twiddles(int n, cd** out) {
     std::vector<cd> h((size_t)n);
     const long double tp = 6.283185307179586476925286766559005768L;
     for (int e = 0; e < n; ++e) {
@@ -190,7 +54,7 @@ static int upload_twiddles(int n, cd** out) {
 }
 
 // engine table: tab[(r-1)*Ns + k] = exp(-2 pi i r k / (Ns R)),  r = 1..R-1, k = 0..Ns-1
-static int upload_engine_table(int Ns, int R, cd** out) {
+int upload_engine_table(int Ns, int R, cd** out) {
     std::vector<cd> h((size_t)(R - 1) * Ns);
     const long double tp = 6.283185307179586476925286766559005768L;
     for (int r = 1; r < R; ++r)
@@ -247,21 +111,6 @@ static int upload_bluestein(int H, int M, cd** outC, cd** outB) {
     return 0;
 }
 
-static int init_generic_radix_tables() {
-    const int rad[4] = {5, 7, 11, 13};
-    double2 h[4][16];
-    memset(h, 0, sizeof h);
-    const long double tp = 6.283185307179586476925286766559005768L;
-    for (int k = 0; k < 4; ++k)
-        for (int q = 0; q < rad[k]; ++q) {
-            const long double ang = tp * q / rad[k];
-            h[k][q].x = (double)cosl(ang);
-            h[k][q].y = (double)(-sinl(ang));
-        }
-    CK(cudaMemcpyToSymbol(c_wgen, h, sizeof h));
-    return 0;
-}
-
 // Q[q][k1] = sum_c cy(c)^q exp(-2 pi i k1 c / N1): one warp per output
 __global__ void qtable_kernel(int N1, int NH, int nq, const cd* __restrict__ tw1, cd* __restrict__ Q) {
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -295,28 +144,6 @@ __global__ void __launch_bounds__(512) dbg_fft_kernel(FftDesc fd, const cd* __re
         const int p = idx / fd.n, e = idx - p * fd.n;
         out[(size_t)(b0 + p) * fd.n + e] = buf[(size_t)p * pitch + e];
     }
-}
-
-// The dynamic shared-memory limit of a kernel is a property of the FUNCTION (per device), not of a plan: plans of
-// different shapes live side by side (and are created from different host threads), so the limit is only ever raised.
-template <typename T>
-static int set_smem(T kernel, size_t bytes) {
-    static std::mutex mtx;
-    static std::map<std::pair<int, const void*>, size_t> cur;
-    int dev = 0;
-    CK(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lock(mtx);
-    size_t& c = cur[std::make_pair(dev, (const void*)kernel)];
-    if (bytes > c) {
-        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        c = bytes;
-    }
-    return 0;
-}
-
-static int env_int(const char* name, int dflt) {
-    const char* s = getenv(name);
-    return (s && *s) ? atoi(s) : dflt;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -461,7 +288,7 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         }
     }
     // KerPolyOrder = 3 exists only as the warp-specialised kernel (three launches); it needs the folded path as fallback
-    const bool want_seg = (d.DK <= 2 || okf) && 4 * d.w0 + 32 <= FSG_M && cfg->fold <= 0 && !env_int("SFFTB_FIT_NOSEG", 0);
+    const bool want_seg = (d.DK <= 2 || okf) && 4 * d.w0 + 32 <= FS3_M && cfg->fold <= 0 && !env_int("SFFTB_FIT_NOSEG", 0);
     if (!okf && !want_seg)
         return fail(SFFTB_EINVAL, "unsupported image height N0=%d (fold=%d): no slice length with prime factors <= 13 fits shared memory",
                     N0, cfg->fold);
@@ -481,12 +308,10 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         memcpy(fa.plane_of, p->cfit.plane_of, sizeof fa.plane_of);
         fa.tw1 = p->tw1;
         p->smem_fir = sizeof(cd) * (size_t)d.Fij * d.L0 + sizeof(double) * (size_t)d.Fij;
-        const size_t Wst = FIR2_CH + 2 * (size_t)d.w0;
         const size_t WP3 = (FIR3_CH + 2 * (size_t)d.w0 + FIR3_R - 1) / FIR3_R;
         p->smem_fir3 = sizeof(cd) * (size_t)d.Fij * d.L0 + 128 + sizeof(cd) * (size_t)(d.DK + 1) * FIR3_R * WP3 + sizeof(double) * FIR3_R * WP3;
         CK(cudaMalloc(&p->firTaps, sizeof(cd) * (size_t)NH * d.Fij * d.L0));
         CK(cudaMalloc(&p->firCA, sizeof(double) * 16));
-        p->smem_fir2 = sizeof(cd) * (size_t)d.Fij * d.L0 + 128 + sizeof(cd) * (size_t)(d.DK + 2) * Wst + sizeof(double) * Wst;
     }
 
     // ---- workspaces ----
@@ -510,33 +335,7 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
     CK(cudaMalloc(&p->sc, sizeof(double) * (size_t)p->nsolve));
     CK(cudaMalloc(&p->diagU, sizeof(double) * (size_t)p->nsolve));
     CK(cudaMalloc(&p->sol, sizeof(double) * (size_t)d.NEQ));
-    {
-        const int nblk = (p->nsolve + CC_NB - 1) / CC_NB;
-        CK(cudaMalloc(&p->cholW, sizeof(double) * (size_t)nblk * CC_NB * CC_NB));
-        CK(cudaMalloc(&p->cholY, sizeof(double) * (size_t)p->nsolve));
-        CK(cudaMalloc(&p->cholX, sizeof(double) * (size_t)p->nsolve));
-        CK(cudaMalloc(&p->cholBar, sizeof(unsigned) * 4));
-        const size_t csm = sizeof(double) * (4 * CC_NB * CC_PITCH);
-        CK(cudaFuncSetAttribute(chol_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
-        int occ = 0, coop = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_coop_kernel, CC_NT, csm));
-        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
-        {
-            CK(cudaMalloc(&p->substFlags, sizeof(unsigned) * 2 * (size_t)nblk));
-            CK(cudaMemset(p->substFlags, 0, sizeof(unsigned) * 2 * (size_t)nblk));
-            const size_t ssm = sizeof(double) * (3 * CC_NB * CC_DP + 64 + 64 + 256);
-            CK(cudaFuncSetAttribute(chol_subst_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
-            int occs = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occs, chol_subst_kernel, CC_NT, ssm));
-            p->subst_ok = (occs >= 1 && coop && !env_int("SFFTB_RESOLVE_V1", 0)) ? 1 : 0;
-            CK(cudaMalloc(&p->substMsg, sizeof(ulonglong2) * 2 * (size_t)nblk * CC_NB));
-            CK(cudaMemset(p->substMsg, 0, sizeof(ulonglong2) * 2 * (size_t)nblk * CC_NB));
-            const size_t ssm2 = sizeof(double) * (3 * CC_NB * CC_DP + 64 + 128);
-            CK(cudaFuncSetAttribute(chol_subst2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm2));
-            if (p->subst_ok && !env_int("SFFTB_RESOLVE_V2", 0)) p->subst_ok = 2;
-        }
-        p->chol_coop = (occ >= 1 && coop && !env_int("SFFTB_CHOL_LEGACY", 0)) ? std::min(occ, std::max(1, env_int("SFFTB_CHOL_CTAS", CC_CTAS_PER_SM))) : 0;
-    }
+    if (chol_setup(p)) return SFFTB_ECUDA;
     CK(cudaMalloc(&p->info, sizeof(int) * 4));
     CK(cudaMallocHost(&p->info_h, sizeof(int) * 4));
     memset(p->info_h, 0, sizeof(int) * 4);
@@ -608,103 +407,9 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         CK(cudaMalloc(&p->solEff, sizeof(double) * (size_t)d.NEQ));
     }
 
-    // ---- kernel attributes ----
     const bool f32 = cfg->storage == SFFTB_STORE_F32;
-    if (f32) {
-        if ((okf && set_smem(fit_col_kernel<float2>, p->smem_fit)) || set_smem(apply_fir_kernel<float2>, p->smem_fir)) return SFFTB_ECUDA;
-        if (set_smem(row_fwd_kernel<float, float2>, p->smem_row) || set_smem(row_fwd_kernel<double, float2>, p->smem_row)) return SFFTB_ECUDA;
-        if (set_smem(row_inv_kernel<float2, float>, p->smem_row) || set_smem(row_inv_kernel<float2, double>, p->smem_row)) return SFFTB_ECUDA;
-    } else {
-        if ((okf && set_smem(fit_col_kernel<double2>, p->smem_fit)) || set_smem(apply_fir_kernel<double2>, p->smem_fir)) return SFFTB_ECUDA;
-        if (set_smem(row_fwd_kernel<float, double2>, p->smem_row) || set_smem(row_fwd_kernel<double, double2>, p->smem_row)) return SFFTB_ECUDA;
-        if (set_smem(row_inv_kernel<double2, float>, p->smem_row) || set_smem(row_inv_kernel<double2, double>, p->smem_row)) return SFFTB_ECUDA;
-    }
-    if (p->smem_fir3 <= p->max_smem) {
-#define SET_FIR3(DKK)                                                                                             \
-        if (d.DK == DKK) {                                                                                            \
-            if (f32) { if (set_smem(apply_fir3_kernel<float2, DKK>, p->smem_fir3)) return SFFTB_ECUDA; }               \
-            else     { if (set_smem(apply_fir3_kernel<double2, DKK>, p->smem_fir3)) return SFFTB_ECUDA; }              \
-        }
-        SET_FIR3(0) SET_FIR3(1) SET_FIR3(2) SET_FIR3(3)
-#undef SET_FIR3
-    }
-    if (p->smem_fir2 <= p->max_smem) {
-#define SET_FIR2(DKK)                                                                                             \
-        if (d.DK == DKK) {                                                                                            \
-            if (f32) { if (set_smem(apply_fir2_kernel<float2, DKK>, p->smem_fir2)) return SFFTB_ECUDA; }               \
-            else     { if (set_smem(apply_fir2_kernel<double2, DKK>, p->smem_fir2)) return SFFTB_ECUDA; }              \
-        }
-        SET_FIR2(0) SET_FIR2(1) SET_FIR2(2) SET_FIR2(3)
-#undef SET_FIR2
-    }
-    const size_t red_smem = sizeof(cd) * (size_t)NH;
-    if (set_smem(lag_reduce_kernel, red_smem) || set_smem(poly_reduce_kernel, red_smem)) return SFFTB_ECUDA;
-    const size_t bs_smem = sizeof(double) * ((size_t)p->nsolve + CH_NB + CH_NB * (CH_NB + 1));
-    if (bs_smem > p->max_smem) return fail(SFFTB_EINVAL, "NEQ=%d too large for the back-substitution kernel", d.NEQ);
-    if (set_smem(chol_backsolve_kernel, bs_smem)) return SFFTB_ECUDA;
-    if (set_smem(lu_solve_kernel, sizeof(double) * (size_t)p->nsolve)) return SFFTB_ECUDA;
+    if (apply_setup(p) || rows_setup(p)) return SFFTB_ECUDA;
 
-    // ---- fast paths on the register FFT engine ----
-    if (upload_engine_table(16, 16, &p->tabA)) return SFFTB_ECUDA;
-    p->row_fast = 0;
-    if (r.packed && !env_int("SFFTB_ROW_GENERIC", 0) &&
-        (r.H == 512 || r.H == 1024 || r.H == 2048 || r.H == 4096 || r.H == 8192)) {
-        const int R3 = reg_fft_tail_radix(r.H);
-        if (upload_engine_table(256, R3, &p->tabB_row)) return SFFTB_ECUDA;
-        if (r.H == 8192 && upload_engine_table(4096, 2, &p->tabC_row)) return SFFTB_ECUDA;
-        RowFastArgs& rf = p->rowf;
-        rf.N0 = N0; rf.N1 = N1; rf.NH = NH; rf.H = r.H;
-        rf.tabA = p->tabA; rf.tabB = p->tabB_row; rf.tabC = p->tabC_row; rf.tw1 = p->tw1;
-        p->rinvf.r = rf; p->rinvf.scale = p->rinv.scale; p->rinvf.Fpq = d.Fpq;
-        memcpy(p->rinvf.p_of, p->rinv.p_of, 16); memcpy(p->rinvf.q_of, p->rinv.q_of, 16);
-        p->row_fast = r.H;
-    }
-    p->row_v8 = 0;
-    if (upload_engine_table(8, 8, &p->vt8_8) || upload_engine_table(64, 8, &p->vt64_8) || upload_engine_table(64, 4, &p->vt64_4) ||
-        upload_engine_table(256, 4, &p->vt256_4) || upload_engine_table(512, 4, &p->vt512_4)) return SFFTB_ECUDA;
-    p->vtabs.t8_8 = p->vt8_8; p->vtabs.t64_8 = p->vt64_8; p->vtabs.t64_4 = p->vt64_4; p->vtabs.t256_4 = p->vt256_4; p->vtabs.t512_4 = p->vt512_4;
-    if (r.packed && !env_int("SFFTB_ROW_NOV8", 0) && (r.H == 256 || r.H == 512 || r.H == 1024 || r.H == 2048)) {
-        RowV8Args& rv = p->rowv;
-        rv.N0 = N0; rv.N1 = N1; rv.NH = NH; rv.H = r.H;
-        rv.nit = std::max(1, env_int("SFFTB_ROW_NIT", 2));
-        rv.tabs.t8_8 = p->vt8_8; rv.tabs.t64_8 = p->vt64_8; rv.tabs.t64_4 = p->vt64_4; rv.tabs.t256_4 = p->vt256_4; rv.tabs.t512_4 = p->vt512_4;
-        rv.tw1 = p->tw1;
-        const int RBI = ROWV_NT / (r.H / 8);
-        p->smem_rowv = sizeof(cd) * ((size_t)RBI * (r.H + r.H / 8 + 8) + 3000 + r.H / 2 + 1);
-#define SET_ROWV(HH)                                                                                              \
-        if (r.H == HH) {                                                                                              \
-            if (f32) { if (set_smem(row_fwd_v8_kernel<float, float2, HH>, p->smem_rowv) || set_smem(row_fwd_v8_kernel<double, float2, HH>, p->smem_rowv)) return SFFTB_ECUDA; } \
-            else     { if (set_smem(row_fwd_v8_kernel<float, double2, HH>, p->smem_rowv) || set_smem(row_fwd_v8_kernel<double, double2, HH>, p->smem_rowv)) return SFFTB_ECUDA; } \
-        }
-        SET_ROWV(256) SET_ROWV(512) SET_ROWV(1024) SET_ROWV(2048)
-#undef SET_ROWV
-        p->row_v8 = r.H;
-    }
-    p->fit_fast = 0;
-    if (N0 % 256 == 0 && 4 * d.w0 + 1 <= 256 && !env_int("SFFTB_FIT_GENERIC", 0) && d.Fij * (d.Fij - 1) / 2 <= 48) {
-        FastFitArgs& ff = p->ffit;
-        memset(&ff, 0, sizeof ff);
-        ff.c = p->cfit;
-        ff.c.M = 256; ff.c.pitch = FCF_PITCH;
-        int q2 = 0;
-        for (int a2 = 0; a2 < d.Fij; ++a2)
-            for (int b2 = a2 + 1; b2 < d.Fij; ++b2) { ff.offA[q2] = (unsigned char)a2; ff.offB[q2] = (unsigned char)b2; ++q2; }
-        ff.noff = q2; ff.ndg = (d.Fij + 1) / 2; ff.njob = ff.noff + ff.ndg + d.Fij;
-        ff.pack_rounds = ff.njob >= FCF_GROUPS ? 1 : 0;
-        ff.tabA = p->tabA;
-        const size_t nacc = (size_t)p->cfit.npairs * p->cfit.nl0 + (size_t)d.Fij * p->cfit.nlj0;
-        const int vi_max = env_int("SFFTB_VI", 4);
-        for (int VI = 4; VI >= 1; VI >>= 1) {
-            if (VI > vi_max || N0 % (256 * VI)) continue;
-            const size_t bytes = sizeof(cd) * ((size_t)VI * (d.Fij + 1) * FCF_PITCH + (size_t)FCF_GROUPS * FCF_PITCH + nacc +
-                                               (size_t)(d.DK + 2) * SFFTB_MAXE + 16 * SFFTB_MAXE + 240);
-            if (bytes > p->max_smem) continue;
-            ff.VI = VI; ff.Vo = N0 / (256 * VI); ff.c.V = ff.Vo * VI;
-            p->smem_ffit = bytes; p->fit_fast = VI;
-            break;
-        }
-        if (p->fit_fast) { d.fold = ff.c.V; d.sub_len = 256; }
-    }
     // ---- segmented fit path (KerPolyOrder <= 2, halo 2 w0 well inside a 256-point window) ----
     p->fit_seg = 0;
     if (want_seg) {
@@ -712,7 +417,7 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         memset(&sf, 0, sizeof sf);
         sf.c = p->cfit;
         sf.h = 2 * d.w0;
-        const int Smax = (FSG_M - 2 * sf.h) & ~1;
+        const int Smax = (FS3_M - 2 * sf.h) & ~1;
         sf.nseg = (N0 + Smax - 1) / Smax;
         sf.S = (((N0 + sf.nseg - 1) / sf.nseg) + 1) & ~1;       // balanced, even
         if (sf.S > Smax) sf.S = Smax;
@@ -724,90 +429,36 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         sf.tabA = p->tabA;
         sf.Q = p->Q;
         memcpy(sf.pq_of, pa.pq_of, sizeof sf.pq_of);
-        p->smem_sfit = sizeof(cd) * ((size_t)FSG_NBUF * FSG_PITCH + 4 * SFFTB_MAXE + (size_t)FSG_MSLOTS * FSG_NMOM + 240) +
-                       csz * 2 * (size_t)(d.DK + 2) * FSG_M;
         CK(cudaMalloc(&p->kap2, sizeof(cd) * (size_t)NH * sf.nrows));
         LagReduce2Args& r2 = p->red2;
         r2.N1 = N1; r2.NH = NH; r2.nrows = sf.nrows; r2.w1 = d.w1; r2.tw1 = p->tw1; r2.rb0 = 0;
         const int rowblocks = (sf.nrows + 15) / 16;
         r2.ksplit = (NH + LR2_KC - 1) / LR2_KC;
-        if (set_smem(lag_reduce2_kernel, sizeof(cd) * LR2_KC * LR2_LB)) return SFFTB_ECUDA;
         (void)rowblocks;
         CK(cudaMalloc(&p->part, sizeof(double) * (size_t)r2.ksplit * sf.nrows * nl1));
         LagFinishArgs& f2 = p->fin2;
         f2.nrows = sf.nrows; f2.nOm = sf.nOm; f2.nK = sf.nK; f2.nLT = sf.nLT; f2.w1 = d.w1; f2.ksplit = r2.ksplit;
         f2.R = p->R; f2.RJ = p->RJ; f2.RT = p->RT; f2.RJT = p->RJT;
-#define SET_SFIT(DKK)                                                                                             \
-        if (d.DK == DKK) {                                                                                            \
-            if (f32) { if (set_smem(fit_seg_kernel<float2, DKK>, p->smem_sfit)) return SFFTB_ECUDA; }                 \
-            else     { if (set_smem(fit_seg_kernel<double2, DKK>, p->smem_sfit)) return SFFTB_ECUDA; }                \
-        }
-        SET_SFIT(0) SET_SFIT(1) SET_SFIT(2)
-#undef SET_SFIT
         p->grid_sfit = std::min(NH, p->nsm);
-        p->fit_seg = d.DK <= 2 ? 1 : 0;
         {
             const int NPs = d.DK == 3 ? 13 : 2 * d.Fij + 1;      // DK = 3: the largest of the three passes (2 + 10 + 1)
             const int npla = std::max(2 * NPs, 16);
             const int nms = (d.DK == 3 ? 5 : 4) * SFFTB_MAXE, nmt = d.DK == 3 ? 32 : 64;
             p->smem_sfit3 = sizeof(cd) * ((size_t)npla * FS3_PITCH + nms + (size_t)nms * nmt + 56 + 192) + 96 +
                             csz * (f32 ? 8 : 4) * (size_t)(d.DK + 2) * FS3_M;
-            if (d.DK == 3 && p->smem_sfit3 <= p->max_smem && !env_int("SFFTB_SEG_V2", 0)) {
-                const bool bad = f32 ? (set_smem(fit_seg3_kernel<float2, 3, false, 0, 2>, p->smem_sfit3) || set_smem(fit_seg3_kernel<float2, 3, false, 2, 5>, p->smem_sfit3) ||
-                                        set_smem(fit_seg3_kernel<float2, 3, false, 5, 10>, p->smem_sfit3))
-                                     : (set_smem(fit_seg3_kernel<double2, 3, false, 0, 2>, p->smem_sfit3) || set_smem(fit_seg3_kernel<double2, 3, false, 2, 5>, p->smem_sfit3) ||
-                                        set_smem(fit_seg3_kernel<double2, 3, false, 5, 10>, p->smem_sfit3));
-                if (bad) return SFFTB_ECUDA;
-                p->fit_seg = 2;
-            }
-            if (d.DK <= 2 && p->smem_sfit3 <= p->max_smem && !env_int("SFFTB_SEG_V2", 0)) {
-#define SET_SFIT3(DKK)                                                                                            \
-                if (d.DK == DKK) {                                                                                    \
-                    if (f32) { if (set_smem(fit_seg3_kernel<float2, DKK>, p->smem_sfit3) || set_smem(fit_seg3_kernel<float2, DKK, true>, p->smem_sfit3)) return SFFTB_ECUDA; }       \
-                    else     { if (set_smem(fit_seg3_kernel<double2, DKK>, p->smem_sfit3) || set_smem(fit_seg3_kernel<double2, DKK, true>, p->smem_sfit3)) return SFFTB_ECUDA; }      \
-                }
-                SET_SFIT3(0) SET_SFIT3(1) SET_SFIT3(2)
-#undef SET_SFIT3
-                p->fit_seg = 2;
-            }
+            if (p->smem_sfit3 <= p->max_smem) p->fit_seg = 2;
         }
         if (p->fit_seg) { d.fold = sf.nseg; d.sub_len = sf.S; }
     }
-    if (p->row_fast) {
-        const size_t sm = sizeof(cd) * (size_t)(ROWF_NT / (r.H / 16)) * (r.H + r.H / 16);
-#define SET_ROWF(HH)                                                                                              \
-        if (r.H == HH) {                                                                                              \
-            if (f32) { if (set_smem(row_fwd_fast_kernel<float, float2, HH>, sm) || set_smem(row_fwd_fast_kernel<double, float2, HH>, sm) || \
-                           set_smem(row_inv_fast_kernel<float2, float, HH>, sm) || set_smem(row_inv_fast_kernel<float2, double, HH>, sm)) return SFFTB_ECUDA; } \
-            else     { if (set_smem(row_fwd_fast_kernel<float, double2, HH>, sm) || set_smem(row_fwd_fast_kernel<double, double2, HH>, sm) || \
-                           set_smem(row_inv_fast_kernel<double2, float, HH>, sm) || set_smem(row_inv_fast_kernel<double2, double, HH>, sm)) return SFFTB_ECUDA; } \
-        }
-        SET_ROWF(512) SET_ROWF(1024) SET_ROWF(2048) SET_ROWF(4096) SET_ROWF(8192)
-#undef SET_ROWF
-    }
-    if (p->fit_fast) {
-        int occ2 = 1;
-#define SET_FFIT(VV)                                                                                              \
-        if (p->fit_fast == VV) {                                                                                      \
-            if (f32) { if (set_smem(fit_col_fast_kernel<float2, VV>, p->smem_ffit)) return SFFTB_ECUDA;               \
-                       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, fit_col_fast_kernel<float2, VV>, FCF_NT, p->smem_ffit)); } \
-            else     { if (set_smem(fit_col_fast_kernel<double2, VV>, p->smem_ffit)) return SFFTB_ECUDA;              \
-                       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, fit_col_fast_kernel<double2, VV>, FCF_NT, p->smem_ffit)); } \
-        }
-        SET_FFIT(1) SET_FFIT(2) SET_FFIT(4)
-#undef SET_FFIT
-        p->grid_ffit = std::min(NH, std::max(1, occ2) * p->nsm);
-    }
-
-    int occ = 1;
-    if (okf) {
-        if (f32) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_col_kernel<float2>, NT_COL, p->smem_fit));
-        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_col_kernel<double2>, NT_COL, p->smem_fit));
-    }
-    p->grid_fit = std::min(NH, std::max(1, occ) * p->nsm);
+    if (!p->fit_seg && !okf)
+        return fail(SFFTB_EINVAL, "unsupported image height N0=%d (fold=%d): no slice length with prime factors <= 13 fits shared memory",
+                    N0, cfg->fold);
+    p->fit_generic_ok = okf ? 1 : 0;
+    if (fit_setup(p)) return SFFTB_ECUDA;
     CK(cudaStreamSynchronize(p->stream));
     return 0;
 }
+
 
 extern "C" int sfftb_plan_create(sfftb_plan** out, const sfftb_config* cfg) {
     if (!out || !cfg) return fail(SFFTB_EINVAL, "null argument");
@@ -859,7 +510,6 @@ extern "C" int sfftb_plan_set_timing(sfftb_plan* p, int enable) {
 extern "C" long long sfftb_launch_count(const sfftb_plan* p) { return p ? p->launches : 0; }
 extern "C" int sfftb_last_solver(const sfftb_plan* p) { return p ? p->last_solver : 0; }
 
-#define EVREC(p, k) do { if ((p)->timing) CK(cudaEventRecord((p)->ev[k], (p)->stream)); } while (0)
 
 // ---------------------------------------------------------------------------------------------------------------
 static int stage_in(sfftb_plan* p, const void* src, int memkind, int dtype, void* staging, const void** dev) {
@@ -873,126 +523,6 @@ static int stage_in(sfftb_plan* p, const void* src, int memkind, int dtype, void
     return 0;
 }
 
-template <typename TSt>
-static int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj) {
-    const size_t esz2 = dtype == SFFTB_F64 ? 16 : 8;
-    if (p->row_v8 && ((uintptr_t)img % esz2) == 0) {
-        const int H = p->row_v8, RBI = ROWV_NT / (H / 8);
-        const int ngroups = (p->d.N0 + RBI - 1) / RBI;
-        const int nbatch = (ngroups + p->rowv.nit - 1) / p->rowv.nit;
-        const int grid = std::min(nbatch, p->row_grid_limit > 0 ? p->row_grid_limit : p->nsm);
-#define RUN_ROWV(HH)                                                                                                   \
-        if (H == HH) {                                                                                                 \
-            if (dtype == SFFTB_F64) row_fwd_v8_kernel<double, TSt, HH><<<grid, ROWV_NT, p->smem_rowv, p->stream>>>(p->rowv, (const double*)img, out, nj); \
-            else row_fwd_v8_kernel<float, TSt, HH><<<grid, ROWV_NT, p->smem_rowv, p->stream>>>(p->rowv, (const float*)img, out, nj);                     \
-        }
-        RUN_ROWV(256) RUN_ROWV(512) RUN_ROWV(1024) RUN_ROWV(2048)
-#undef RUN_ROWV
-        CKL(p);
-        return 0;
-    }
-    if (p->row_fast && ((uintptr_t)img % esz2) == 0) {
-        const int H = p->row_fast, RB = ROWF_NT / (H / 16);
-        const int grid = (p->d.N0 + RB - 1) / RB;
-        const size_t sm = sizeof(cd) * (size_t)RB * (H + H / 16);
-#define RUN_ROWF(HH)                                                                                                   \
-        if (H == HH) {                                                                                                 \
-            if (dtype == SFFTB_F64) row_fwd_fast_kernel<double, TSt, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rowf, (const double*)img, out, nj); \
-            else row_fwd_fast_kernel<float, TSt, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rowf, (const float*)img, out, nj);                     \
-        }
-        RUN_ROWF(512) RUN_ROWF(1024) RUN_ROWF(2048) RUN_ROWF(4096) RUN_ROWF(8192)
-#undef RUN_ROWF
-        CKL(p);
-        return 0;
-    }
-    const int grid = (p->d.N0 + p->row.RB - 1) / p->row.RB;
-    if (dtype == SFFTB_F64)
-        row_fwd_kernel<double, TSt><<<grid, 512, p->smem_row, p->stream>>>(p->row, (const double*)img, out, nj);
-    else
-        row_fwd_kernel<float, TSt><<<grid, 512, p->smem_row, p->stream>>>(p->row, (const float*)img, out, nj);
-    CKL(p);
-    return 0;
-}
-
-static int run_cholesky(sfftb_plan* p, int resolve = 0) {
-    const int n = p->nsolve, ntot = n + 1;
-    if (p->chol_coop && resolve && p->subst_ok == 2) {
-        SubstArgs2 sa;
-        sa.A = p->Aug; sa.ld = p->ld; sa.n = n; sa.W = p->cholW; sa.yv = p->cholY; sa.xs = p->cholX;
-        sa.msg = p->substMsg; sa.epoch = ++p->substEpoch;
-        sa.sc = p->sc; sa.idx = p->idxmap; sa.sol = p->sol; sa.NEQ = p->d.NEQ;
-        const int nblk = (n + CC_NB - 1) / CC_NB;
-        void* args[] = {&sa};
-        // at most half of the SMs: two plans (TemplatePipeline) may run their substitutions at the same time, and two
-        // cooperative grids must be able to be resident together; blocks beyond the grid are owned cyclically
-        CK(cudaLaunchCooperativeKernel((void*)chol_subst2_kernel, dim3(std::min(nblk, std::max(1, p->nsm / 2))), dim3(CC_NT), args,
-                                       sizeof(double) * (3 * CC_NB * CC_DP + 64 + 128), p->stream));
-        p->launches++;
-        return 0;
-    }
-    if (p->chol_coop && resolve && p->subst_ok) {
-        SubstArgs sa;
-        sa.A = p->Aug; sa.ld = p->ld; sa.n = n; sa.W = p->cholW; sa.yv = p->cholY; sa.xs = p->cholX;
-        sa.flags = p->substFlags; sa.epoch = ++p->substEpoch;
-        sa.sc = p->sc; sa.idx = p->idxmap; sa.sol = p->sol; sa.NEQ = p->d.NEQ;
-        const int nblk = (n + CC_NB - 1) / CC_NB;
-        void* args[] = {&sa};
-        CK(cudaLaunchCooperativeKernel((void*)chol_subst_kernel, dim3(std::min(nblk, p->nsm)), dim3(CC_NT), args,
-                                       sizeof(double) * (3 * CC_NB * CC_DP + 64 + 64 + 256), p->stream));
-        p->launches++;
-        return 0;
-    }
-    if (p->chol_coop) {
-        CholArgs ca;
-        ca.resolve = resolve;
-        ca.A = p->Aug; ca.ld = p->ld; ca.n = n; ca.ntot = ntot; ca.W = p->cholW; ca.yv = p->cholY; ca.xs = p->cholX;
-        ca.bar = p->cholBar; ca.info = p->info; ca.sc = p->sc; ca.idx = p->idxmap; ca.sol = p->sol; ca.NEQ = p->d.NEQ;
-        CK(cudaMemsetAsync(p->cholBar, 0, sizeof(unsigned) * 4, p->stream));
-        ca.dbg = nullptr;
-        static unsigned long long* dbgbuf = nullptr;
-        const bool dbg = env_int("SFFTB_CHOL_DBG", 0) != 0;
-        if (dbg) {
-            if (!dbgbuf) CK(cudaMalloc(&dbgbuf, sizeof(unsigned long long) * 2048));
-            CK(cudaMemsetAsync(dbgbuf, 0, sizeof(unsigned long long) * 2048, p->stream));
-            ca.dbg = dbgbuf;
-        }
-        void* args[] = {&ca};
-        CK(cudaLaunchCooperativeKernel((void*)chol_coop_kernel, dim3(p->chol_grid_limit > 0 ? p->chol_grid_limit : p->nsm * p->chol_coop), dim3(CC_NT), args,
-                                       sizeof(double) * (4 * CC_NB * CC_PITCH), p->stream));
-        p->launches++;
-        if (dbg) {
-            std::vector<unsigned long long> hst(2048);
-            CK(cudaStreamSynchronize(p->stream));
-            CK(cudaMemcpy(hst.data(), dbgbuf, sizeof(unsigned long long) * 2048, cudaMemcpyDeviceToHost));
-            const int nblk = (n + CC_NB - 1) / CC_NB;
-            fprintf(stderr, "chol dbg (us): k  trsm  bar1  dsg_tile  dsg_potrf  others_tiles  bar2_end\n");
-            for (int k = 0; k < nblk && k < 32; ++k) {
-                const unsigned long long* t = &hst[8 * k];
-                auto us = [&](int i) { return t[i] ? (double)(t[i] - t[0]) * 1e-3 : -1.0; };
-                const unsigned long long* u = &hst[1024 + 4 * (k + 1)];
-                fprintf(stderr, "  %2d  %6.1f %6.1f %6.1f %6.1f %6.1f %6.1f | potrf(k+1): loaded %6.1f loop_end %6.1f\n", k, us(1), us(2), us(3), us(4), us(5), us(6),
-                        u[0] ? (double)(u[0] - t[0]) * 1e-3 : -1.0, u[1] ? (double)(u[1] - t[0]) * 1e-3 : -1.0);
-            }
-        }
-        return 0;
-    }
-    for (int k0 = 0; k0 < n; k0 += CH_NB) {
-        const int kb = std::min(CH_NB, n - k0);
-        const int below = ntot - (k0 + kb);
-        const int gp = std::max(1, (below + 127) / 128);
-        chol_panel_kernel<<<gp, 128, 0, p->stream>>>(p->Aug, p->ld, ntot, n, k0, p->info);
-        CKL(p);
-        if (below > 0 && k0 + kb < n) {
-            const int nt = (below + 63) / 64;
-            chol_update_kernel<<<dim3(nt, nt), 256, 0, p->stream>>>(p->Aug, p->ld, ntot, n, k0);
-            CKL(p);
-        }
-    }
-    const size_t bs_smem = sizeof(double) * ((size_t)n + CH_NB + CH_NB * (CH_NB + 1));
-    chol_backsolve_kernel<<<1, 1024, bs_smem, p->stream>>>(p->Aug, p->ld, n, p->sc, p->idxmap, p->sol, p->d.NEQ);
-    CKL(p);
-    return 0;
-}
 
 static int fill_system(sfftb_plan* p) {
     const int n = p->nsolve;
@@ -1004,24 +534,6 @@ static int fill_system(sfftb_plan* p) {
     return 0;
 }
 
-static int run_lu(sfftb_plan* p) {
-    const int n = p->nsolve;
-    int occ = 0;
-    const size_t smem = sizeof(double) * (size_t)n;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lu_solve_kernel, 512, smem));
-    if (occ < 1) return fail(SFFTB_ECUDA, "LU fallback kernel cannot be made resident");
-    int grid = p->nsm;
-    double* A = p->Aug; int ld = p->ld; int nn = n; double* du = p->diagU; const double* sc = p->sc; const int* idx = p->idxmap;
-    double* sol = p->sol; int NEQ = p->d.NEQ; int* info = p->info;
-    void* args[] = {&A, &ld, &nn, &du, &sc, &idx, &sol, &NEQ, &info};
-    CK(cudaLaunchCooperativeKernel((void*)lu_solve_kernel, dim3(grid), dim3(512), args, smem, p->stream));
-    p->launches++;
-    return 0;
-}
-
-// tI != NULL: cached template row spectra of the I image (sfftb_template_prepare); the I row pass is skipped
-template <typename TSt>
-static int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj);
 
 // ovI / ovJ != NULL (device images of the apply step): their forward row pass is issued on the side stream right
 // after the normal equations are assembled, on half of the SMs, while the Cholesky solve runs on the other half
@@ -1039,56 +551,7 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, 
     if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
     EVREC(p, EV_ROWS);
     const bool jonly = tI && p->factor_cached && p->chol_coop && p->fit_seg == 2 && d.DK <= 2 && !env_int("SFFTB_TEMPLATE_FULLFIT", 0);
-    if (jonly) {
-        // tiles after the first of a shared-template batch: the rows of the template-only pairs are already in kap2
-        const int DK = d.DK;
-        if (DK == 0) fit_seg3_kernel<TSt, 0, true><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
-        else if (DK == 1) fit_seg3_kernel<TSt, 1, true><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
-        else fit_seg3_kernel<TSt, 2, true><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
-    } else if (p->fit_seg == 2) {
-        const int DK = d.DK;
-        if (DK == 0) fit_seg3_kernel<TSt, 0><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
-        else if (DK == 1) fit_seg3_kernel<TSt, 1><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
-        else if (DK == 2) fit_seg3_kernel<TSt, 2><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
-        else {
-            // KerPolyOrder = 3: 65 accumulators do not fit the product threads' registers; three launches over plane ranges
-            fit_seg3_kernel<TSt, 3, false, 0, 2><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
-            CKL(p);
-            fit_seg3_kernel<TSt, 3, false, 2, 5><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
-            CKL(p);
-            fit_seg3_kernel<TSt, 3, false, 5, 10><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
-        }
-    } else if (p->fit_seg) {
-        const int DK = d.DK;
-        if (DK == 0) fit_seg_kernel<TSt, 0><<<p->grid_sfit, FSG_NT, p->smem_sfit, p->stream>>>(p->sfit, gIsrc, (const TSt*)p->gJ, p->kap2);
-        else if (DK == 1) fit_seg_kernel<TSt, 1><<<p->grid_sfit, FSG_NT, p->smem_sfit, p->stream>>>(p->sfit, gIsrc, (const TSt*)p->gJ, p->kap2);
-        else fit_seg_kernel<TSt, 2><<<p->grid_sfit, FSG_NT, p->smem_sfit, p->stream>>>(p->sfit, gIsrc, (const TSt*)p->gJ, p->kap2);
-    } else if (p->fit_fast == 4)
-        fit_col_fast_kernel<TSt, 4><<<p->grid_ffit, FCF_NT, p->smem_ffit, p->stream>>>(p->ffit, gIsrc, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
-    else if (p->fit_fast == 2)
-        fit_col_fast_kernel<TSt, 2><<<p->grid_ffit, FCF_NT, p->smem_ffit, p->stream>>>(p->ffit, gIsrc, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
-    else if (p->fit_fast == 1)
-        fit_col_fast_kernel<TSt, 1><<<p->grid_ffit, FCF_NT, p->smem_ffit, p->stream>>>(p->ffit, gIsrc, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
-    else
-        fit_col_kernel<TSt><<<p->grid_fit, NT_COL, p->smem_fit, p->stream>>>(p->cfit, gIsrc, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
-    CKL(p);
-    EVREC(p, EV_COL);
-    if (p->fit_seg) {
-        // (one launch over all rows also for shared-template tiles: the reduction is a single latency-bound wave, and
-        //  restricting it to the rows that changed measured slower: 0.082 vs 0.054 ms at 2048^2)
-        dim3 grd((p->sfit.nrows + 15) / 16, p->red2.ksplit);
-        lag_reduce2_kernel<<<grd, 256, sizeof(cd) * LR2_KC * LR2_LB, p->stream>>>(p->red2, p->kap2, p->part);
-        CKL(p);
-        const int tot = p->sfit.nrows * (4 * d.w1 + 1);
-        lag_finish_kernel<<<(tot + 255) / 256, 256, 0, p->stream>>>(p->fin2, p->part);
-        CKL(p);
-    } else {
-        const size_t red_smem = sizeof(cd) * (size_t)(d.N1 / 2 + 1);
-        lag_reduce_kernel<<<p->nrowsK, 256, red_smem, p->stream>>>(p->red, p->kap, p->R, p->RJ);
-        CKL(p);
-        poly_reduce_kernel<<<p->nrowsL + d.DB + 1, 256, red_smem, p->stream>>>(p->pred, p->lam, p->nuJ, p->RT, p->RJT);
-        CKL(p);
-    }
+    if (launch_fit_cols<TSt>(p, gIsrc, jonly)) return SFFTB_ECUDA;
     CK(cudaMemsetAsync(p->info, 0, sizeof(int) * 4, p->stream));
     bool used_cache = false;
     if (tI && p->factor_cached && p->chol_coop) {
@@ -1183,69 +646,10 @@ static int apply_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype
         if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
     }
     EVREC(p, EV_AROWS);
-    if (p->smem_fir3 <= p->max_smem && !env_int("SFFTB_FIR_V2", 0) && !env_int("SFFTB_FIR_V1", 0)) {
-        fir_taps_kernel<<<d.N1 / 2 + 1, 128, 0, p->stream>>>(p->fir, dsol, p->firTaps, p->firCA);
-        CKL(p);
-        dim3 grd(d.N1 / 2 + 1, (d.N0 + FIR3_CH - 1) / FIR3_CH);
-#define RUN_FIR3(DKK) if (d.DK == DKK) apply_fir3_kernel<TSt, DKK><<<grd, FIR3_NT, p->smem_fir3, p->stream>>>(p->fir, gIsrc, (const TSt*)p->gJ, p->firTaps, p->firCA, (TSt*)p->gJ);
-        RUN_FIR3(0) RUN_FIR3(1) RUN_FIR3(2) RUN_FIR3(3)
-#undef RUN_FIR3
-    } else if (p->smem_fir2 <= p->max_smem && !env_int("SFFTB_FIR_V1", 0)) {
-        dim3 grd(d.N1 / 2 + 1, (d.N0 + FIR2_CH - 1) / FIR2_CH);
-#define RUN_FIR2(DKK) if (d.DK == DKK) apply_fir2_kernel<TSt, DKK><<<grd, FIR2_NT, p->smem_fir2, p->stream>>>(p->fir, gIsrc, (const TSt*)p->gJ, dsol, (TSt*)p->gJ);
-        RUN_FIR2(0) RUN_FIR2(1) RUN_FIR2(2) RUN_FIR2(3)
-#undef RUN_FIR2
-    } else {
-        dim3 grd(d.N1 / 2 + 1, (d.N0 + FIR_CHUNK - 1) / FIR_CHUNK);
-        apply_fir_kernel<TSt><<<grd, FIR_NT, p->smem_fir, p->stream>>>(p->fir, gIsrc, (const TSt*)p->gJ, dsol, (TSt*)p->gJ);
-    }
-    CKL(p);
+    if (launch_fir<TSt>(p, gIsrc, dsol)) return SFFTB_ECUDA;
     EVREC(p, EV_ACOL);
     const double* bpq = dsol + d.Fijab;
-    const size_t osz2 = diff_dtype == SFFTB_F64 ? 16 : 8;
-    if (p->row_fast && ((uintptr_t)ddiff % osz2) == 0) {
-        const int H = p->row_fast, RB = ROWF_NT / (H / 16);
-        const size_t sm = sizeof(cd) * (size_t)RB * (H + H / 16);
-        // hdiff != NULL (host GSS): the rows are produced in chunks and every finished chunk is copied to the host on
-        // the side stream while the next one is computed
-        const int nchunk = (hdiff && d.N0 >= 8 * RB) ? 4 : 1;
-        const int rows_per = ((d.N0 + nchunk - 1) / nchunk + RB - 1) / RB * RB;
-        const size_t esz = diff_dtype == SFFTB_F64 ? 8 : 4;
-        for (int c = 0; c < nchunk; ++c) {
-            const int row0 = c * rows_per, nrow = std::min(rows_per, d.N0 - row0);
-            if (nrow <= 0) break;
-            const int grid = (nrow + RB - 1) / RB;
-            p->rinvf.row0 = row0;
-#define RUN_RINVF(HH)                                                                                                  \
-            if (H == HH) {                                                                                             \
-                if (diff_dtype == SFFTB_F64) row_inv_fast_kernel<TSt, double, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rinvf, (const TSt*)p->gJ, bpq, (double*)ddiff); \
-                else row_inv_fast_kernel<TSt, float, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rinvf, (const TSt*)p->gJ, bpq, (float*)ddiff);                            \
-            }
-            RUN_RINVF(512) RUN_RINVF(1024) RUN_RINVF(2048) RUN_RINVF(4096) RUN_RINVF(8192)
-#undef RUN_RINVF
-            if (c + 1 < nchunk || hdiff) CKL(p);
-            if (hdiff) {
-                CK(cudaEventRecord(p->evCopy[c & 3], p->stream));
-                CK(cudaStreamWaitEvent(p->stream2, p->evCopy[c & 3], 0));
-                CK(cudaMemcpyAsync((char*)hdiff + (size_t)row0 * d.N1 * esz, (const char*)ddiff + (size_t)row0 * d.N1 * esz,
-                                   (size_t)nrow * d.N1 * esz, cudaMemcpyDeviceToHost, p->stream2));
-            }
-        }
-        p->rinvf.row0 = 0;
-        if (hdiff) {
-            CK(cudaEventRecord(p->evJoin, p->stream2));
-            CK(cudaStreamWaitEvent(p->stream, p->evJoin, 0));
-            EVREC(p, EV_AINV);
-            return 0;
-        }
-    } else {
-        const int grid = (d.N0 + p->row.RB - 1) / p->row.RB;
-        if (diff_dtype == SFFTB_F64)
-            row_inv_kernel<TSt, double><<<grid, 512, p->smem_row, p->stream>>>(p->rinv, (const TSt*)p->gJ, bpq, (double*)ddiff);
-        else
-            row_inv_kernel<TSt, float><<<grid, 512, p->smem_row, p->stream>>>(p->rinv, (const TSt*)p->gJ, bpq, (float*)ddiff);
-    }
-    CKL(p);
+    if (launch_row_inv<TSt>(p, bpq, ddiff, diff_dtype, hdiff)) return SFFTB_ECUDA;
     EVREC(p, EV_AINV);
     return 0;
 }

@@ -1,0 +1,85 @@
+// tu_fit.cu -- fit column pass (segmented warp-specialised kernel; folded-slice generic fallback) and the lag reductions.
+#define SFFTB_TU_FIT
+#include "plan.h"
+
+int fit_setup(sfftb_plan* p) {
+    const sfftb_dims& d = p->d;
+    const bool f32 = p->cfg.storage == SFFTB_STORE_F32;
+    if (init_generic_radix_tables()) return SFFTB_ECUDA;
+    int occ = 1;
+    if (p->fit_generic_ok) {
+        if (f32) { if (set_smem(fit_col_kernel<float2>, p->smem_fit)) return SFFTB_ECUDA;
+                   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_col_kernel<float2>, NT_COL, p->smem_fit)); }
+        else     { if (set_smem(fit_col_kernel<double2>, p->smem_fit)) return SFFTB_ECUDA;
+                   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_col_kernel<double2>, NT_COL, p->smem_fit)); }
+    }
+    p->grid_fit = std::min(d.N1 / 2 + 1, std::max(1, occ) * p->nsm);
+    const size_t red_smem = sizeof(cd) * (size_t)(d.N1 / 2 + 1);
+    if (set_smem(lag_reduce_kernel, red_smem) || set_smem(poly_reduce_kernel, red_smem)) return SFFTB_ECUDA;
+    if (p->fit_seg) {
+        if (set_smem(lag_reduce2_kernel, sizeof(cd) * LR2_KC * LR2_LB)) return SFFTB_ECUDA;
+        if (d.DK == 3) {
+            const bool bad = f32 ? (set_smem(fit_seg3_kernel<float2, 3, false, 0, 2>, p->smem_sfit3) || set_smem(fit_seg3_kernel<float2, 3, false, 2, 5>, p->smem_sfit3) ||
+                                    set_smem(fit_seg3_kernel<float2, 3, false, 5, 10>, p->smem_sfit3))
+                                 : (set_smem(fit_seg3_kernel<double2, 3, false, 0, 2>, p->smem_sfit3) || set_smem(fit_seg3_kernel<double2, 3, false, 2, 5>, p->smem_sfit3) ||
+                                    set_smem(fit_seg3_kernel<double2, 3, false, 5, 10>, p->smem_sfit3));
+            if (bad) return SFFTB_ECUDA;
+        }
+#define SET_SFIT3(DKK)                                                                                            \
+        if (d.DK == DKK) {                                                                                            \
+            if (f32) { if (set_smem(fit_seg3_kernel<float2, DKK>, p->smem_sfit3) || set_smem(fit_seg3_kernel<float2, DKK, true>, p->smem_sfit3)) return SFFTB_ECUDA; }       \
+            else     { if (set_smem(fit_seg3_kernel<double2, DKK>, p->smem_sfit3) || set_smem(fit_seg3_kernel<double2, DKK, true>, p->smem_sfit3)) return SFFTB_ECUDA; }      \
+        }
+        SET_SFIT3(0) SET_SFIT3(1) SET_SFIT3(2)
+#undef SET_SFIT3
+    }
+    return 0;
+}
+
+// Column pass + contraction over k1 into the lag tables R, RJ, RT, RJT.
+// jonly: tiles after the first of a shared-template batch -- the rows of the template-only pairs are already in kap2.
+template <typename TSt>
+int launch_fit_cols(sfftb_plan* p, const TSt* gIsrc, bool jonly) {
+    const sfftb_dims& d = p->d;
+    const int DK = d.DK;
+    if (jonly) {
+        if (DK == 0) fit_seg3_kernel<TSt, 0, true><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else if (DK == 1) fit_seg3_kernel<TSt, 1, true><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else fit_seg3_kernel<TSt, 2, true><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+    } else if (p->fit_seg) {
+        if (DK == 0) fit_seg3_kernel<TSt, 0><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else if (DK == 1) fit_seg3_kernel<TSt, 1><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else if (DK == 2) fit_seg3_kernel<TSt, 2><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else {
+            // KerPolyOrder = 3: 65 accumulators do not fit the product threads' registers; three launches over plane ranges
+            fit_seg3_kernel<TSt, 3, false, 0, 2><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+            CKL(p);
+            fit_seg3_kernel<TSt, 3, false, 2, 5><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+            CKL(p);
+            fit_seg3_kernel<TSt, 3, false, 5, 10><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        }
+    } else
+        fit_col_kernel<TSt><<<p->grid_fit, NT_COL, p->smem_fit, p->stream>>>(p->cfit, gIsrc, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
+    CKL(p);
+    EVREC(p, EV_COL);
+    if (p->fit_seg) {
+        // (one launch over all rows also for shared-template tiles: the reduction is a single latency-bound wave, and
+        //  restricting it to the rows that changed measured slower: 0.082 vs 0.054 ms at 2048^2)
+        dim3 grd((p->sfit.nrows + 15) / 16, p->red2.ksplit);
+        lag_reduce2_kernel<<<grd, 256, sizeof(cd) * LR2_KC * LR2_LB, p->stream>>>(p->red2, p->kap2, p->part);
+        CKL(p);
+        const int tot = p->sfit.nrows * (4 * d.w1 + 1);
+        lag_finish_kernel<<<(tot + 255) / 256, 256, 0, p->stream>>>(p->fin2, p->part);
+        CKL(p);
+    } else {
+        const size_t red_smem = sizeof(cd) * (size_t)(d.N1 / 2 + 1);
+        lag_reduce_kernel<<<p->nrowsK, 256, red_smem, p->stream>>>(p->red, p->kap, p->R, p->RJ);
+        CKL(p);
+        poly_reduce_kernel<<<p->nrowsL + d.DB + 1, 256, red_smem, p->stream>>>(p->pred, p->lam, p->nuJ, p->RT, p->RJT);
+        CKL(p);
+    }
+    return 0;
+}
+
+template int launch_fit_cols<float2>(sfftb_plan*, const float2*, bool);
+template int launch_fit_cols<double2>(sfftb_plan*, const double2*, bool);

@@ -1,0 +1,160 @@
+// tu_rows.cu -- row passes: forward (real rows -> transposed half spectra) and inverse (FDIFF rows -> difference image).
+#define SFFTB_TU_ROWS
+#include "plan.h"
+
+int rows_setup(sfftb_plan* p) {
+    const sfftb_dims& d = p->d;
+    const RowArgs& r = p->row;
+    const bool f32 = p->cfg.storage == SFFTB_STORE_F32;
+    if (init_generic_radix_tables()) return SFFTB_ECUDA;
+    if (f32) {
+        if (set_smem(row_fwd_kernel<float, float2>, p->smem_row) || set_smem(row_fwd_kernel<double, float2>, p->smem_row)) return SFFTB_ECUDA;
+        if (set_smem(row_inv_kernel<float2, float>, p->smem_row) || set_smem(row_inv_kernel<float2, double>, p->smem_row)) return SFFTB_ECUDA;
+    } else {
+        if (set_smem(row_fwd_kernel<float, double2>, p->smem_row) || set_smem(row_fwd_kernel<double, double2>, p->smem_row)) return SFFTB_ECUDA;
+        if (set_smem(row_inv_kernel<double2, float>, p->smem_row) || set_smem(row_inv_kernel<double2, double>, p->smem_row)) return SFFTB_ECUDA;
+    }
+    // ---- fast paths on the register FFT engines ----
+    if (upload_engine_table(16, 16, &p->tabA)) return SFFTB_ECUDA;
+    p->row_fast = 0;
+    if (r.packed && !env_int("SFFTB_ROW_GENERIC", 0) &&
+        (r.H == 512 || r.H == 1024 || r.H == 2048 || r.H == 4096 || r.H == 8192)) {
+        const int R3 = reg_fft_tail_radix(r.H);
+        if (upload_engine_table(256, R3, &p->tabB_row)) return SFFTB_ECUDA;
+        if (r.H == 8192 && upload_engine_table(4096, 2, &p->tabC_row)) return SFFTB_ECUDA;
+        RowFastArgs& rf = p->rowf;
+        rf.N0 = d.N0; rf.N1 = d.N1; rf.NH = d.N1 / 2 + 1; rf.H = r.H;
+        rf.tabA = p->tabA; rf.tabB = p->tabB_row; rf.tabC = p->tabC_row; rf.tw1 = p->tw1;
+        p->rinvf.r = rf; p->rinvf.scale = p->rinv.scale; p->rinvf.Fpq = d.Fpq;
+        memcpy(p->rinvf.p_of, p->rinv.p_of, 16); memcpy(p->rinvf.q_of, p->rinv.q_of, 16);
+        p->row_fast = r.H;
+    }
+    p->row_v8 = 0;
+    if (upload_engine_table(8, 8, &p->vt8_8) || upload_engine_table(64, 8, &p->vt64_8) || upload_engine_table(64, 4, &p->vt64_4) ||
+        upload_engine_table(256, 4, &p->vt256_4) || upload_engine_table(512, 4, &p->vt512_4)) return SFFTB_ECUDA;
+    p->vtabs.t8_8 = p->vt8_8; p->vtabs.t64_8 = p->vt64_8; p->vtabs.t64_4 = p->vt64_4; p->vtabs.t256_4 = p->vt256_4; p->vtabs.t512_4 = p->vt512_4;
+    if (r.packed && !env_int("SFFTB_ROW_NOV8", 0) && (r.H == 256 || r.H == 512 || r.H == 1024 || r.H == 2048)) {
+        RowV8Args& rv = p->rowv;
+        rv.N0 = d.N0; rv.N1 = d.N1; rv.NH = d.N1 / 2 + 1; rv.H = r.H;
+        rv.nit = std::max(1, env_int("SFFTB_ROW_NIT", 2));
+        rv.tabs = p->vtabs;
+        rv.tw1 = p->tw1;
+        const int RBI = ROWV_NT / (r.H / 8);
+        p->smem_rowv = sizeof(cd) * ((size_t)RBI * (r.H + r.H / 8 + 8) + 3000 + r.H / 2 + 1);
+#define SET_ROWV(HH)                                                                                              \
+        if (r.H == HH) {                                                                                              \
+            if (f32) { if (set_smem(row_fwd_v8_kernel<float, float2, HH>, p->smem_rowv) || set_smem(row_fwd_v8_kernel<double, float2, HH>, p->smem_rowv)) return SFFTB_ECUDA; } \
+            else     { if (set_smem(row_fwd_v8_kernel<float, double2, HH>, p->smem_rowv) || set_smem(row_fwd_v8_kernel<double, double2, HH>, p->smem_rowv)) return SFFTB_ECUDA; } \
+        }
+        SET_ROWV(256) SET_ROWV(512) SET_ROWV(1024) SET_ROWV(2048)
+#undef SET_ROWV
+        p->row_v8 = r.H;
+    }
+    if (p->row_fast) {
+        const size_t sm = sizeof(cd) * (size_t)(ROWF_NT / (r.H / 16)) * (r.H + r.H / 16);
+#define SET_ROWF(HH)                                                                                              \
+        if (r.H == HH) {                                                                                              \
+            if (f32) { if (set_smem(row_fwd_fast_kernel<float, float2, HH>, sm) || set_smem(row_fwd_fast_kernel<double, float2, HH>, sm) || \
+                           set_smem(row_inv_fast_kernel<float2, float, HH>, sm) || set_smem(row_inv_fast_kernel<float2, double, HH>, sm)) return SFFTB_ECUDA; } \
+            else     { if (set_smem(row_fwd_fast_kernel<float, double2, HH>, sm) || set_smem(row_fwd_fast_kernel<double, double2, HH>, sm) || \
+                           set_smem(row_inv_fast_kernel<double2, float, HH>, sm) || set_smem(row_inv_fast_kernel<double2, double, HH>, sm)) return SFFTB_ECUDA; } \
+        }
+        SET_ROWF(512) SET_ROWF(1024) SET_ROWF(2048) SET_ROWF(4096) SET_ROWF(8192)
+#undef SET_ROWF
+    }
+    return 0;
+}
+
+template <typename TSt>
+int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj) {
+    const size_t esz2 = dtype == SFFTB_F64 ? 16 : 8;
+    if (p->row_v8 && ((uintptr_t)img % esz2) == 0) {
+        const int H = p->row_v8, RBI = ROWV_NT / (H / 8);
+        const int ngroups = (p->d.N0 + RBI - 1) / RBI;
+        const int nbatch = (ngroups + p->rowv.nit - 1) / p->rowv.nit;
+        const int grid = std::min(nbatch, p->row_grid_limit > 0 ? p->row_grid_limit : p->nsm);
+#define RUN_ROWV(HH)                                                                                                   \
+        if (H == HH) {                                                                                                 \
+            if (dtype == SFFTB_F64) row_fwd_v8_kernel<double, TSt, HH><<<grid, ROWV_NT, p->smem_rowv, p->stream>>>(p->rowv, (const double*)img, out, nj); \
+            else row_fwd_v8_kernel<float, TSt, HH><<<grid, ROWV_NT, p->smem_rowv, p->stream>>>(p->rowv, (const float*)img, out, nj);                     \
+        }
+        RUN_ROWV(256) RUN_ROWV(512) RUN_ROWV(1024) RUN_ROWV(2048)
+#undef RUN_ROWV
+        CKL(p);
+        return 0;
+    }
+    if (p->row_fast && ((uintptr_t)img % esz2) == 0) {
+        const int H = p->row_fast, RB = ROWF_NT / (H / 16);
+        const int grid = (p->d.N0 + RB - 1) / RB;
+        const size_t sm = sizeof(cd) * (size_t)RB * (H + H / 16);
+#define RUN_ROWF(HH)                                                                                                   \
+        if (H == HH) {                                                                                                 \
+            if (dtype == SFFTB_F64) row_fwd_fast_kernel<double, TSt, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rowf, (const double*)img, out, nj); \
+            else row_fwd_fast_kernel<float, TSt, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rowf, (const float*)img, out, nj);                     \
+        }
+        RUN_ROWF(512) RUN_ROWF(1024) RUN_ROWF(2048) RUN_ROWF(4096) RUN_ROWF(8192)
+#undef RUN_ROWF
+        CKL(p);
+        return 0;
+    }
+    const int grid = (p->d.N0 + p->row.RB - 1) / p->row.RB;
+    if (dtype == SFFTB_F64)
+        row_fwd_kernel<double, TSt><<<grid, 512, p->smem_row, p->stream>>>(p->row, (const double*)img, out, nj);
+    else
+        row_fwd_kernel<float, TSt><<<grid, 512, p->smem_row, p->stream>>>(p->row, (const float*)img, out, nj);
+    CKL(p);
+    return 0;
+}
+
+// Inverse row pass (C2R, scaling, background subtraction in real space).  hdiff != NULL (host GSS): the rows are
+// produced in chunks and every finished chunk is copied to the host on the side stream while the next one is computed.
+template <typename TSt>
+int launch_row_inv(sfftb_plan* p, const double* bpq, void* ddiff, int diff_dtype, void* hdiff) {
+    const sfftb_dims& d = p->d;
+    const size_t osz2 = diff_dtype == SFFTB_F64 ? 16 : 8;
+    if (p->row_fast && ((uintptr_t)ddiff % osz2) == 0) {
+        const int H = p->row_fast, RB = ROWF_NT / (H / 16);
+        const size_t sm = sizeof(cd) * (size_t)RB * (H + H / 16);
+        const int nchunk = (hdiff && d.N0 >= 8 * RB) ? 4 : 1;
+        const int rows_per = ((d.N0 + nchunk - 1) / nchunk + RB - 1) / RB * RB;
+        const size_t esz = diff_dtype == SFFTB_F64 ? 8 : 4;
+        for (int c = 0; c < nchunk; ++c) {
+            const int row0 = c * rows_per, nrow = std::min(rows_per, d.N0 - row0);
+            if (nrow <= 0) break;
+            const int grid = (nrow + RB - 1) / RB;
+            p->rinvf.row0 = row0;
+#define RUN_RINVF(HH)                                                                                                  \
+            if (H == HH) {                                                                                             \
+                if (diff_dtype == SFFTB_F64) row_inv_fast_kernel<TSt, double, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rinvf, (const TSt*)p->gJ, bpq, (double*)ddiff); \
+                else row_inv_fast_kernel<TSt, float, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rinvf, (const TSt*)p->gJ, bpq, (float*)ddiff);                            \
+            }
+            RUN_RINVF(512) RUN_RINVF(1024) RUN_RINVF(2048) RUN_RINVF(4096) RUN_RINVF(8192)
+#undef RUN_RINVF
+            CKL(p);
+            if (hdiff) {
+                CK(cudaEventRecord(p->evCopy[c & 3], p->stream));
+                CK(cudaStreamWaitEvent(p->stream2, p->evCopy[c & 3], 0));
+                CK(cudaMemcpyAsync((char*)hdiff + (size_t)row0 * d.N1 * esz, (const char*)ddiff + (size_t)row0 * d.N1 * esz,
+                                   (size_t)nrow * d.N1 * esz, cudaMemcpyDeviceToHost, p->stream2));
+            }
+        }
+        p->rinvf.row0 = 0;
+        if (hdiff) {
+            CK(cudaEventRecord(p->evJoin, p->stream2));
+            CK(cudaStreamWaitEvent(p->stream, p->evJoin, 0));
+        }
+        return 0;
+    }
+    const int grid = (d.N0 + p->row.RB - 1) / p->row.RB;
+    if (diff_dtype == SFFTB_F64)
+        row_inv_kernel<TSt, double><<<grid, 512, p->smem_row, p->stream>>>(p->rinv, (const TSt*)p->gJ, bpq, (double*)ddiff);
+    else
+        row_inv_kernel<TSt, float><<<grid, 512, p->smem_row, p->stream>>>(p->rinv, (const TSt*)p->gJ, bpq, (float*)ddiff);
+    CKL(p);
+    return 0;
+}
+
+template int launch_row_fwd<float2>(sfftb_plan*, const void*, int, float2*, int);
+template int launch_row_fwd<double2>(sfftb_plan*, const void*, int, double2*, int);
+template int launch_row_inv<float2>(sfftb_plan*, const double*, void*, int, void*);
+template int launch_row_inv<double2>(sfftb_plan*, const double*, void*, int, void*);

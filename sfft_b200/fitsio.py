@@ -81,7 +81,10 @@ def read_raw(path):
     if h.get('NAXIS') != 2:
         raise ValueError('only 2-D primary images are supported: %s' % path)
     n1, n2, bp = int(h['NAXIS1']), int(h['NAXIS2']), int(h['BITPIX'])
-    raw = np.fromfile(path, dtype=np.uint8, count=n1 * n2 * abs(bp) // 8, offset=off)
+    nbytes = n1 * n2 * abs(bp) // 8
+    raw = np.fromfile(path, dtype=np.uint8, count=nbytes, offset=off)
+    if raw.size != nbytes:                 # np.fromfile returns a short array for a truncated file; the device decode would
+        raise IOError('truncated FITS data block: %s (%d of %d bytes)' % (path, raw.size, nbytes))   # read out of bounds
     return cards, raw, bp, n1, n2, float(h.get('BSCALE', 1)), float(h.get('BZERO', 0))
 
 
@@ -93,11 +96,16 @@ def _card(key, value, comment=None):
     elif isinstance(value, (float, np.floating)):
         v = '%20s' % repr(float(value)).upper()
     else:
-        v = "'%-8s'" % str(value).replace("'", "''")
+        # a string value must keep its closing quote inside the 80 columns (no CONTINUE cards are written:
+        # longer values are truncated to the 68 characters a single card holds)
+        body = str(value).replace("'", "''")[:68]
+        if body.endswith("'") and (len(body) - len(body.rstrip("'"))) % 2 == 1:
+            body = body[:-1]               # do not cut an escaped quote pair in half
+        v = "'%-8s'" % body
     s = '%-8s= %s' % (key[:8].upper(), v)
-    if comment:
-        s += ' / ' + comment
-    return '%-80s' % s[:80]
+    if comment and len(s) + 3 < 80:
+        s = (s + ' / ' + comment)[:80]
+    return '%-80s' % s
 
 
 def _pad(b, fill):
@@ -110,6 +118,10 @@ def writeto(path, data, base_cards=None, updates=None):
 
     base_cards: raw cards of a header to carry over (structural keywords are regenerated).
     updates   : list of (key, value, comment) appended/replaced after the carried-over cards.
+
+    Differences from the reference's astropy writer (sfft/CustomizedPacket.py:191-203): only the primary HDU is written
+    (extensions of the source file are not carried over), the packets write the difference image as float64 whatever
+    the science image's BITPIX was, and non-ASCII bytes of a carried-over header are replaced by '?'.
     """
     raw_block = None
     if isinstance(data, tuple):          # (raw big-endian data block, bitpix, naxis1, naxis2): already encoded on the device
@@ -138,7 +150,7 @@ def writeto(path, data, base_cards=None, updates=None):
     for k, v, cm in upd:
         cards.append(_card(k, v, cm))
     cards.append('%-80s' % 'END')
-    hb = _pad(''.join(cards).encode('ascii'), b' ')
+    hb = _pad(''.join(cards).encode('ascii', errors='replace'), b' ')
     if raw_block is not None:
         db = _pad(np.asarray(raw_block, np.uint8).tobytes(), b'\0')
     else:

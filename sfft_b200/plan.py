@@ -55,7 +55,14 @@ class Plan:
 
     # ---- plumbing --------------------------------------------------------------------------
     def set_stream(self, stream_ptr):
+        """Raw cudaStream_t; 0 / None = the plan's own (non-blocking) stream."""
         B.check(self._L.sfftb_plan_set_stream(self._h, C.c_void_p(stream_ptr or 0)))
+
+    def bind_torch_stream(self, stream):
+        """Run the plan's work on a torch stream so that it is ordered after whatever the caller has queued there.
+        torch's default stream has the handle 0, which sfftb_plan_set_stream reads as "the plan's own stream" -- a
+        non-blocking stream that does NOT synchronise with the legacy default stream; bind cudaStreamLegacy (0x1) then."""
+        self.set_stream(stream.cuda_stream or 0x1)
 
     def sync(self):
         B.check(self._L.sfftb_plan_sync(self._h))

@@ -96,7 +96,7 @@ class GeneralSFFTSubtract_PureCupy:
         Solution_GPU = torch.empty(plan.NEQ, dtype=torch.float64, device=dev)
         PixA_DIFF_GPU = torch.empty(plan.shape, dtype=tdt, device=dev)
         stream = torch.cuda.current_stream(dev)
-        plan.set_stream(stream.cuda_stream)
+        plan.bind_torch_stream(stream)
         plan.gss_device(cais[0]['data'][0], cais[1]['data'][0], cais[2]['data'][0], cais[3]['data'][0], code,
                         Solution_GPU.data_ptr(), PixA_DIFF_GPU.data_ptr(), code)
         ContamMask_CI_GPU = None

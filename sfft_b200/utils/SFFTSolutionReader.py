@@ -92,7 +92,7 @@ def _device_realize(XY_q, Solution_GPU, SFFTConfig, want_kernel, want_fscal):
     d = plan.dims
     ker = torch.empty((nq, d['L0'], d['L1']), dtype=torch.float64, device=dev) if want_kernel else None
     fs = torch.empty(nq, dtype=torch.float64, device=dev) if want_fscal else None
-    plan.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    plan.bind_torch_stream(torch.cuda.current_stream(dev))
     B.check(B.lib().sfftb_realize(plan._h, sol.data_ptr(), B.MEM_DEVICE, xy.data_ptr(), B.MEM_DEVICE, nq,
                                   ker.data_ptr() if want_kernel else None, fs.data_ptr() if want_fscal else None,
                                   B.MEM_DEVICE))
