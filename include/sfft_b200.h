@@ -164,6 +164,39 @@ int  sfftb_set_regularizer(sfftb_plan* plan, const double* SST, const double* iR
  * zero rows / columns beyond ScaFij.  Call after sfftb_set_regularizer. */
 int  sfftb_set_regularizer_varying(sfftb_plan* plan, const double* CSST, const double* DSST);
 
+/* ---- general spatial bases: sfft/BSplineSFFT.py (B-spline or polynomial variation of the kernel, the photometric scaling and
+ * the background, any degree) --------------------------------------------------------------------------------------------
+ * Every 2-D basis function of the reference is a tensor product of two 1-D functions of the scaled pixel-centre
+ * coordinates (Create_BSplineBasis :2624-2634; KerSpatial / ScaSpatial / BkgSpatial :276-458), so a basis is handed over as
+ * its 1-D tables; the caller evaluates them (B-splines with any knot vector, monomials, ...).  Host pointers, copied. */
+typedef struct sfftb_basis {
+    int nu, nv;            /* number of 1-D functions along axis 0 (rows, x) / axis 1 (columns, y) */
+    int nf;                /* number of 2-D basis functions: Fij, ScaFij or Fpq */
+    const double* U;       /* (nu, N0) row-major: U_i at the pixel centres (r + 1) / N0 */
+    const double* V;       /* (nv, N1) row-major: V_j at (c + 1) / N1 */
+    const int* fu;         /* (nf): function k = U[fu[k]] (x) V[fv[k]], in the reference's ij / pq order */
+    const int* fv;
+} sfftb_basis;
+
+#define SFFTB_SCALING_ENTANGLED       0   /* SEPARATE_SCALING=False (:77-86) */
+#define SFFTB_SCALING_CONSTANT_DROP   1   /* SEPARATE-CONSTANT, polynomial kernel: the stripes (ij > 0, 00) are dropped (TweakLS :2204-2233) */
+#define SFFTB_SCALING_CONSTANT_SUM    2   /* SEPARATE-CONSTANT, B-spline kernel: the stripes are summed (:2235-2272) and the value is copied
+                                             back to every (ij, 00) (Restore_Solution :3764-3771) */
+#define SFFTB_SCALING_VARYING         3   /* SEPARATE-VARYING: the (ij, 00) unknown of ij < ScaFij scales I x ScaBasis_ij (:2487-2495), the
+                                             others are dropped (:3733-3747); `sca` gives that basis */
+
+/* BSplineSFFT.SingleSFFTConfigure.SSC (:2538-2611).  cfg->DK / DB are informational (the degrees), cfg->const_phot_ratio,
+ * sca_degree and fold are ignored; the Solution layout is the reference's: NEQ = ker->nf * Fab + bkg->nf.  `sca` may be NULL
+ * unless scaling_mode is SFFTB_SCALING_VARYING.  Such a plan serves sfftb_fit / sfftb_apply / sfftb_gss, the regulariser and
+ * the export hooks; the shared-template and asynchronous entry points return SFFTB_EINVAL for it. */
+int  sfftb_plan_create_general(sfftb_plan** out, const sfftb_config* cfg, const sfftb_basis* ker, const sfftb_basis* sca,
+                               const sfftb_basis* bkg, int scaling_mode);
+
+/* Parity hook for every kind of plan: the system that was actually solved by the last fit -- after the stripe tweak, in the
+ * order of the reference's tweaked system (TweakLS; what the reference hands to its solver): L (n x n, row-major) and b (n),
+ * n = NEQ_FSfree of sfftb_plan_dims.  Host pointers; either may be NULL. */
+int  sfftb_export_solved_system(sfftb_plan* plan, double* L, double* b);
+
 /* Parity hook: the full (NEQ x NEQ) LHMAT and (NEQ) RHb of the last fit, before stripe removal,
  * in the reference's layout (what FillLS_* produce, SFFTSubtract.py:244-380).  Host pointers. */
 int  sfftb_export_normal_eq(sfftb_plan* plan, double* LHMAT, double* RHb);

@@ -1,5 +1,5 @@
 """
-sfft/BSplineSFFT.py on the B200 core -- the part of it the native plan covers today.
+sfft/BSplineSFFT.py on the B200 core.
 
 `BSplineSFFT.py` generalises sfftcore: the kernel, the scaling and the background may vary as total-degree
 polynomials or as tensor-product B-splines, the photometric scaling can be entangled with the kernel or separate
@@ -15,8 +15,13 @@ call signatures (`SingleSFFTConfigure.SSC` :2538, `ElementalSFFTSubtract.ESS`, `
   * REGULARIZE_KERNEL with XY_REGULARIZE / WEIGHT_REGULARIZE / LAMBDA_REGULARIZE / IGNORE_LAPLACIAN_KERCENT:
     the two Kronecker factors of REGMAT are built here and added inside the native matrix fill (sfftb_set_regularizer).
 
-B-spline bases (kernel, scaling or background) are refused with a clear error: their CUDA path is not built yet
-(DESIGN.md section 7).
+  * KerSpType / ScaSpType / BkgSpType = 'B-Spline' with any internal knots, and polynomial degrees above 3, through the
+    general-basis plan (sfftb_plan_create_general): the 1-D basis tables are evaluated here exactly as Create_BSplineBasis
+    (:2624-2634) does and handed to the CUDA library, which treats every basis image as U_i(r) V_j(c)
+    (csrc/kernels_gen.cuh).  SEPARATE-CONSTANT sums the stripes for a B-spline kernel and drops them for a polynomial
+    one (TweakLS :2202-2272), SEPARATE-VARYING takes its own scaling basis, Restore_Solution (:3704-3783) is mirrored.
+
+Pure-polynomial configurations of degree <= 3 keep the specialised sfftcore kernels (same results, one fit launch).
 """
 import os.path as pa
 import time
@@ -46,6 +51,57 @@ def _laplacian_penalty(w0, w1, IGNORE_LAPLACIAN_KERCENT):
     M[c0, :] = -1.0
     M[c0, c0] = 1.0
     return 2.0 * (M.T @ (LAP.T @ LAP) @ M)
+
+
+def _bspline_basis(N, IntKnot, Degree, ReqCoord=None):
+    """Create_BSplineBasis / Create_BSplineBasis_Req (:2624-2646): clamped knots [0.5]*(k+1) ++ IntKnot ++ [N+0.5]*(k+1),
+    scaled by 1/N, evaluated at the pixel centres (1 + arange(N)) / N or at the requested scaled coordinates."""
+    from scipy.interpolate import BSpline
+    coord = (1.0 + np.arange(N)) / N if ReqCoord is None else np.asarray(ReqCoord, float)
+    knot = np.concatenate(([0.5] * (Degree + 1), np.asarray(IntKnot, float), [N + 0.5] * (Degree + 1))) / N
+    Nc = len(IntKnot) + Degree + 1
+    return np.array([BSpline(t=knot, c=(np.arange(Nc) == idx).astype(float), k=Degree, extrapolate=False)(coord)
+                     for idx in range(Nc)])
+
+
+def _basis_tables(SpType, Degree, KnotX, KnotY, N0, N1, CX=None, CY=None):
+    """(U, V, fu, fv): 1-D tables along x / y and the (i, j) of every 2-D basis function in the reference's order
+    (REF_ij / REF_pq, :2764-2772).  CX / CY: evaluate at requested scaled coordinates instead of the pixel grid."""
+    if SpType == 'Polynomial':
+        cx = (1.0 + np.arange(N0)) / N0 if CX is None else np.asarray(CX, float)
+        cy = (1.0 + np.arange(N1)) / N1 if CY is None else np.asarray(CY, float)
+        U = np.array([cx ** i for i in range(Degree + 1)])
+        V = np.array([cy ** j for j in range(Degree + 1)])
+        ij = [(i, j) for i in range(Degree + 1) for j in range(Degree + 1 - i)]
+    else:
+        U = _bspline_basis(N0, KnotX, Degree, CX)
+        V = _bspline_basis(N1, KnotY, Degree, CY)
+        ij = [(i, j) for i in range(U.shape[0]) for j in range(V.shape[0])]
+    return U, V, np.array([a for a, _ in ij], np.int32), np.array([b for _, b in ij], np.int32)
+
+
+def _gram_factors(P, N0, N1, w0, w1, XY_REGULARIZE, WEIGHT_REGULARIZE, IGNORE_LAPLACIAN_KERCENT):
+    """(SST, iREG[, CSST, DSST]) of fill_regmat (:2091-2166) for any kernel / scaling basis."""
+    XY = np.asarray(XY_REGULARIZE, float)
+    if XY.ndim != 2 or XY.shape[1] != 2 or XY.shape[0] < 1:
+        raise Exception('MeLOn ERROR: XY_REGULARIZE must have shape (N_points, 2)')
+    CX, CY = XY[:, 0] / N0, XY[:, 1] / N1
+    U, V, fu, fv = _basis_tables(P['KerSpType'], P['DK'], P['KerIntKnotX'], P['KerIntKnotY'], N0, N1, CX, CY)
+    SP = U[fu] * V[fv]                                                                # (Fij, NREG), :3576-3592
+    if WEIGHT_REGULARIZE is None:
+        Wd = np.full(XY.shape[0], 1.0 / XY.shape[0])
+    else:
+        Wd = np.asarray(WEIGHT_REGULARIZE, float)
+        if Wd.shape != (XY.shape[0],):
+            raise Exception('MeLOn ERROR: WEIGHT_REGULARIZE must have shape (N_points,)')
+        Wd = Wd / Wd.sum()
+    SST, iREG = (SP * Wd) @ SP.T, _laplacian_penalty(w0, w1, IGNORE_LAPLACIAN_KERCENT)
+    if P['SCALING_MODE'] != 'SEPARATE-VARYING':
+        return SST, iREG
+    U, V, fu, fv = _basis_tables(P['ScaSpType'], P['DS'], P['ScaIntKnotX'], P['ScaIntKnotY'], N0, N1, CX, CY)
+    Sca = U[fu] * V[fv]
+    Sca = np.concatenate([Sca, np.zeros((SP.shape[0] - Sca.shape[0], XY.shape[0]))], axis=0)   # placeholder rows :3614-3620
+    return SST, iREG, (SP * Wd) @ Sca.T, (Sca * Wd) @ Sca.T
 
 
 def regularizer_factors(N0, N1, w0, w1, DK, XY_REGULARIZE, WEIGHT_REGULARIZE=None, IGNORE_LAPLACIAN_KERCENT=True, DS=None):
@@ -80,9 +136,10 @@ class SingleSFFTConfigure:
             REGULARIZE_KERNEL=False, IGNORE_LAPLACIAN_KERCENT=True, XY_REGULARIZE=None, WEIGHT_REGULARIZE=None,
             LAMBDA_REGULARIZE=1e-6, BACKEND_4SUBTRACT='B200', MAX_THREADS_PER_BLOCK=8,
             MINIMIZE_GPU_MEMORY_USAGE=False, NUM_CPU_THREADS_4SUBTRACT=8, VERBOSE_LEVEL=2,
-            CUDA_DEVICE=None, STORAGE='fp64'):
+            CUDA_DEVICE=None, STORAGE='fp64', FORCE_GENERAL_PLAN=False):
         """Arguments as BSplineSFFT.SingleSFFTConfigure.SSC (:2538-2545); MAX_THREADS_PER_BLOCK, MINIMIZE_GPU_MEMORY_USAGE and
-        NUM_CPU_THREADS_4SUBTRACT are accepted and ignored.  Returns (SFFTParam_dict, SFFTModule_dict) with the keys of
+        NUM_CPU_THREADS_4SUBTRACT are accepted and ignored; FORCE_GENERAL_PLAN runs a polynomial configuration through the
+        table-driven kernels as well (test hook).  Returns (SFFTParam_dict, SFFTModule_dict) with the keys of
         :204-273."""
         if BACKEND_4SUBTRACT not in ('B200', 'Cupy'):
             raise Exception("MeLOn ERROR: BACKEND_4SUBTRACT=%r is not available in sfft_b200 (use 'B200')" % (BACKEND_4SUBTRACT,))
@@ -99,26 +156,32 @@ class SingleSFFTConfigure:
             SCALING_MODE = 'SEPARATE-CONSTANT'
         else:
             SCALING_MODE = 'SEPARATE-VARYING'
-        if KerSpType != 'Polynomial' or BkgSpType != 'Polynomial':
-            raise Exception('MeLOn ERROR: B-Spline spatial variation is not available in sfft_b200 yet '
-                            '(polynomial kernel / background only)')
-        ScaFij = None
+        if KerSpType == 'B-Spline' and DK == 0:
+            assert len(KerIntKnotX) == 0 and len(KerIntKnotY) == 0                      # :36-38
+        if BkgSpType == 'B-Spline' and DB == 0:
+            assert len(BkgIntKnotX) == 0 and len(BkgIntKnotY) == 0                      # :79-81
+
+        def dof(SpType, Degree, KX, KY):
+            if SpType == 'Polynomial':
+                return -1, -1, ((Degree + 1) * (Degree + 2)) // 2
+            return len(KX) + Degree + 1, len(KY) + Degree + 1, (len(KX) + Degree + 1) * (len(KY) + Degree + 1)
+        Fi, Fj, Fij = dof(KerSpType, DK, KerIntKnotX, KerIntKnotY)
+        Fp, Fq, Fpq = dof(BkgSpType, DB, BkgIntKnotX, BkgIntKnotY)
+        ScaFi = ScaFj = ScaFij = None
         if SCALING_MODE == 'SEPARATE-VARYING':
-            if ScaSpType != 'Polynomial':
-                raise Exception('MeLOn ERROR: B-Spline spatial variation is not available in sfft_b200 yet '
-                                '(polynomial scaling only)')
-            ScaFij = ((DS + 1) * (DS + 2)) // 2
-            assert ScaFij <= ((DK + 1) * (DK + 2)) // 2                                 # :190
-        if DK > 3 or DB > 3:
-            raise Exception('MeLOn ERROR: polynomial degrees above 3 are not available in sfft_b200')
+            if ScaSpType == 'B-Spline' and DS == 0:
+                assert len(ScaIntKnotX) == 0 and len(ScaIntKnotY) == 0
+            ScaFi, ScaFj, ScaFij = dof(ScaSpType, DS, ScaIntKnotX, ScaIntKnotY)
+            assert ScaFij <= Fij                                                        # :190
+        general = (FORCE_GENERAL_PLAN or KerSpType != 'Polynomial' or BkgSpType != 'Polynomial' or DK > 3 or DB > 3 or
+                   (SCALING_MODE == 'SEPARATE-VARYING' and (ScaSpType != 'Polynomial' or DS > DK)))
         if VERBOSE_LEVEL in [1, 2]:
             print('\n --//--//--//--//-- TRIGGER SFFT COMPILATION --//--//--//--//-- ')
-            print('\n ---//--- Polynomial Kernel | KerSpDegree %d | KerHW %d ---//---' % (DK, w0))
-            print('\n ---//--- [%s] Polynomial Scaling ---//---' % SCALING_MODE)
-            print('\n ---//--- Polynomial Background | BkgSpDegree %d ---//---' % DB)
+            print('\n ---//--- %s Kernel | KerSpDegree %d | KerHW %d ---//---' % (KerSpType, DK, w0))
+            print('\n ---//--- [%s] Scaling ---//---' % SCALING_MODE)
+            print('\n ---//--- %s Background | BkgSpDegree %d ---//---' % (BkgSpType, DB))
         L0, L1 = 2 * w0 + 1, 2 * w1 + 1
         Fab = L0 * L1
-        Fij, Fpq = ((DK + 1) * (DK + 2)) // 2, ((DB + 1) * (DB + 2)) // 2
         Fijab, NEQ = Fij * Fab, Fij * Fab + Fpq
         NEQt = NEQ - Fij + 1 if SCALING_MODE == 'SEPARATE-CONSTANT' else NEQ            # :199-200
         if SCALING_MODE == 'SEPARATE-VARYING':
@@ -130,25 +193,35 @@ class SingleSFFTConfigure:
                  XY_REGULARIZE=XY_REGULARIZE, WEIGHT_REGULARIZE=WEIGHT_REGULARIZE, LAMBDA_REGULARIZE=LAMBDA_REGULARIZE,
                  MAX_THREADS_PER_BLOCK=MAX_THREADS_PER_BLOCK, MINIMIZE_GPU_MEMORY_USAGE=MINIMIZE_GPU_MEMORY_USAGE,
                  N0=N0, N1=N1, w0=w0, w1=w1, DK=DK, DB=DB, SCALE=SCALE, SCALE_L=np.float64(1 / SCALE), L0=L0, L1=L1, Fab=Fab,
-                 Fi=-1, Fj=-1, Fij=Fij, Fp=-1, Fq=-1, Fpq=Fpq, Fijab=Fijab, FOMG=Fij ** 2, FGAM=Fij * Fpq, FTHE=Fij,
+                 Fi=Fi, Fj=Fj, Fij=Fij, Fp=Fp, Fq=Fq, Fpq=Fpq, Fijab=Fijab, FOMG=Fij ** 2, FGAM=Fij * Fpq, FTHE=Fij,
                  FPSI=Fpq * Fij, FPHI=Fpq ** 2, FDEL=Fpq, NEQ=NEQ, NEQt=NEQt, SCALING_MODE=SCALING_MODE)
         if SEPARATE_SCALING:
             P.update(ScaSpType=ScaSpType, ScaSpDegree=ScaSpDegree, ScaIntKnotX=ScaIntKnotX, ScaIntKnotY=ScaIntKnotY, DS=DS)
         if SCALING_MODE == 'SEPARATE-VARYING':
-            P.update(ScaFi=-1, ScaFj=-1, ScaFij=ScaFij)
+            P.update(ScaFi=ScaFi, ScaFj=ScaFj, ScaFij=ScaFij)
         device = _current_device() if CUDA_DEVICE is None else int(CUDA_DEVICE)
-        plan = Plan(N0, N1, w0, w1, DK, DB, SCALING_MODE != 'ENTANGLED', device=device, storage=STORAGE,
-                    sca_degree=DS if SCALING_MODE == 'SEPARATE-VARYING' else 0)
+        if general:
+            from . import _lib as B
+            ker = _basis_tables(KerSpType, DK, KerIntKnotX, KerIntKnotY, N0, N1)
+            bkg = _basis_tables(BkgSpType, DB, BkgIntKnotX, BkgIntKnotY, N0, N1)
+            sca = None
+            if SCALING_MODE == 'ENTANGLED':
+                mode = B.SCALING_ENTANGLED
+            elif SCALING_MODE == 'SEPARATE-CONSTANT':
+                mode = B.SCALING_CONSTANT_SUM if KerSpType == 'B-Spline' else B.SCALING_CONSTANT_DROP    # TweakLS :2204-2272
+            else:
+                mode = B.SCALING_VARYING
+                sca = _basis_tables(ScaSpType, DS, ScaIntKnotX, ScaIntKnotY, N0, N1)
+            plan = Plan.general(N0, N1, w0, w1, ker, bkg, mode, sca=sca, device=device, storage=STORAGE, DK=DK, DB=DB)
+            assert plan.dims['NEQ'] == NEQ and plan.dims['NEQ_FSfree'] == NEQt
+        else:
+            plan = Plan(N0, N1, w0, w1, DK, DB, SCALING_MODE != 'ENTANGLED', device=device, storage=STORAGE,
+                        sca_degree=DS if SCALING_MODE == 'SEPARATE-VARYING' else 0)
         if REGULARIZE_KERNEL:
             if XY_REGULARIZE is None:
                 raise Exception('MeLOn ERROR: REGULARIZE_KERNEL needs XY_REGULARIZE')
-            if SCALING_MODE == 'SEPARATE-VARYING':
-                SST, iREG, CSST, DSST = regularizer_factors(N0, N1, w0, w1, DK, XY_REGULARIZE, WEIGHT_REGULARIZE,
-                                                            IGNORE_LAPLACIAN_KERCENT, DS=DS)
-                plan.set_regularizer(SST, iREG, float(LAMBDA_REGULARIZE), CSST, DSST)
-            else:
-                SST, iREG = regularizer_factors(N0, N1, w0, w1, DK, XY_REGULARIZE, WEIGHT_REGULARIZE, IGNORE_LAPLACIAN_KERCENT)
-                plan.set_regularizer(SST, iREG, float(LAMBDA_REGULARIZE))
+            fac = _gram_factors(P, N0, N1, w0, w1, XY_REGULARIZE, WEIGHT_REGULARIZE, IGNORE_LAPLACIAN_KERCENT)
+            plan.set_regularizer(fac[0], fac[1], float(LAMBDA_REGULARIZE), *(fac[2:]))
         if VERBOSE_LEVEL in [1, 2]:
             print('\n --//--//--//--//-- EXIT SFFT COMPILATION --//--//--//--//-- ')
         return (P, {'BACKEND': 'B200', 'plan': plan, 'device': device, 'storage': STORAGE})

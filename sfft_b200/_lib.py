@@ -21,13 +21,22 @@ EXPORTS = ['sfftb_version', 'sfftb_last_error', 'sfftb_plan_create', 'sfftb_plan
            'sfftb_launch_count', 'sfftb_template_prepare', 'sfftb_template_state',
            'sfftb_template_mark_ready', 'sfftb_gss_template', 'sfftb_realize', 'sfftb_fits_decode', 'sfftb_fits_encode', 'sfftb_nan_union_fill', 'sfftb_nan_mask_apply',
            'sfftb_set_regularizer', 'sfftb_set_regularizer_varying', 'sfftb_gss_submit', 'sfftb_gss_template_submit', 'sfftb_gss_finish', 'sfftb_dbg_fft1d',
-           'sfftb_dbg_row_spectra', 'sfftb_dbg_lag_tables']
+           'sfftb_dbg_row_spectra', 'sfftb_dbg_lag_tables', 'sfftb_plan_create_general', 'sfftb_export_solved_system']
 
 
 class Config(C.Structure):
     _fields_ = [('device', C.c_int), ('N0', C.c_int), ('N1', C.c_int), ('w0', C.c_int), ('w1', C.c_int),
                 ('DK', C.c_int), ('DB', C.c_int), ('const_phot_ratio', C.c_int), ('storage', C.c_int),
                 ('fold', C.c_int), ('sca_degree', C.c_int), ('reserved', C.c_int * 5)]
+
+
+class Basis(C.Structure):
+    """sfftb_basis: one tensor-product spatial basis as its 1-D tables (include/sfft_b200.h)."""
+    _fields_ = [('nu', C.c_int), ('nv', C.c_int), ('nf', C.c_int), ('U', C.c_void_p), ('V', C.c_void_p),
+                ('fu', C.c_void_p), ('fv', C.c_void_p)]
+
+
+SCALING_ENTANGLED, SCALING_CONSTANT_DROP, SCALING_CONSTANT_SUM, SCALING_VARYING = 0, 1, 2, 3
 
 
 class Dims(C.Structure):
@@ -91,6 +100,8 @@ def lib():
     L.sfftb_dbg_fft1d.argtypes = [ip, ip, ip, ip, vp, vp]
     L.sfftb_dbg_row_spectra.argtypes = [vp, ip, vp]
     L.sfftb_dbg_lag_tables.argtypes = [vp, vp, vp, vp, vp]
+    L.sfftb_plan_create_general.argtypes = [C.POINTER(vp), C.POINTER(Config), C.POINTER(Basis), C.POINTER(Basis), C.POINTER(Basis), ip]
+    L.sfftb_export_solved_system.argtypes = [vp, vp, vp]
     for name in EXPORTS:
         if name not in ('sfftb_last_error', 'sfftb_launch_count'):
             getattr(L, name).restype = ip

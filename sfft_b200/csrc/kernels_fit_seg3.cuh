@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
         // ====================================== transform warps ======================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
         const int fw = warp - 8;
+        unsigned seenE0 = 0, seenE1 = 0;               // completed phases of empty[0] / empty[1] this warp has observed
         for (int k1 = blockIdx.x; k1 < a.NH; k1 += gridDim.x, g += nseg) {
             cd* kaprow = kap + (size_t)k1 * fa.nrows;
 #ifdef FS3_DEBUG
@@ -337,7 +338,14 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
 #ifdef FS3_DEBUG
                 long long f1 = clock64(); fWaitL += f1 - f0;
 #endif
-                if (gs >= 2) fs3_mbar_wait(empty + slot, ((gs >> 1) - 1) & 1);
+                // slot free?  A parity wait is only unambiguous one phase away, and with few spectra per segment (NP < 8)
+                // a warp's consecutive jobs lie more than two segments apart: observe EVERY phase of the slot in order
+                {
+                    const unsigned need = (unsigned)gs >> 1;          // completions of empty[slot] before segment gs may be written
+                    unsigned seen = slot ? seenE1 : seenE0;
+                    while (seen < need) { fs3_mbar_wait(empty + slot, seen & 1); ++seen; }
+                    if (slot) seenE1 = seen; else seenE0 = seen;
+                }
 #ifdef FS3_DEBUG
                 long long f2 = clock64(); fWaitE += f2 - f1;
 #endif

@@ -24,6 +24,9 @@ struct RowArgs {
     const cd* blu_tw;     // exp(-2 pi i e / blu_M)
     const cd* blu_c;      // chirp c[n] = exp(-pi i n^2 / H), n < H
     const cd* blu_B;      // FFT_M of conj(c) wrapped to length M (the chirp filter), already divided by M
+    // general-basis plans: plane j is the row times the table vtab[j][c] (B-spline or any other 1-D function of the
+    // column, kernels_gen.cuh) instead of cy(c)^j; NULL = powers
+    const double* vtab;
 };
 
 // Length-H transform of `nplanes` planes through Bluestein's identity n k = (n^2 + k^2 - (k - n)^2) / 2:
@@ -77,7 +80,10 @@ __global__ void __launch_bounds__(512) row_fwd_kernel(RowArgs a, const TIn* __re
                 if (r < a.N0) {
                     const TIn* p = img + (size_t)r * a.N1 + 2 * n;
                     double x0 = (double)p[0], x1 = (double)p[1];
-                    if (j > 0) {
+                    if (a.vtab) {
+                        const double* vt = a.vtab + (size_t)j * a.N1 + 2 * n;
+                        x0 *= vt[0]; x1 *= vt[1];
+                    } else if (j > 0) {
                         x0 *= ipow((2 * n + 1) * inv1, j);
                         x1 *= ipow((2 * n + 2) * inv1, j);
                     }
@@ -92,7 +98,8 @@ __global__ void __launch_bounds__(512) row_fwd_kernel(RowArgs a, const TIn* __re
                 double x0 = 0.0;
                 if (r < a.N0) {
                     x0 = (double)img[(size_t)r * a.N1 + n];
-                    if (j > 0) x0 *= ipow((n + 1) * inv1, j);
+                    if (a.vtab) x0 *= a.vtab[(size_t)j * a.N1 + n];
+                    else if (j > 0) x0 *= ipow((n + 1) * inv1, j);
                 }
                 buf[(size_t)row * a.pitch + n] = cmake(x0, 0.0);
             }

@@ -18,6 +18,7 @@ struct RowFastArgs {
     int N0, N1, NH, H;
     const cd* tabA; const cd* tabB; const cd* tabC;   // engine twiddle tables (global)
     const cd* tw1;                                     // exp(-2 pi i e / N1)
+    const double* vtab;                                // general-basis plans: column tables instead of cy^j (or NULL)
 };
 
 template <int H>
@@ -54,7 +55,10 @@ __global__ void __launch_bounds__(ROWF_NT) row_fwd_fast_kernel(RowFastArgs a, co
                 const TIn* p = img + (size_t)r * a.N1 + 2 * n;
                 double x0, x1;
                 load2(p, x0, x1);
-                if (j > 0) {
+                if (a.vtab) {
+                    const double* vt = a.vtab + (size_t)j * a.N1 + 2 * n;
+                    x0 *= vt[0]; x1 *= vt[1];
+                } else if (j > 0) {
                     x0 *= ipow((2 * n + 1) * inv1, j);
                     x1 *= ipow((2 * n + 2) * inv1, j);
                 }

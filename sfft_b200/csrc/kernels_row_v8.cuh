@@ -19,6 +19,7 @@ struct RowV8Args {
     int nit;                 // row groups per CTA
     VTabs tabs;
     const cd* tw1;           // exp(-2 pi i e / N1)
+    const double* vtab;      // general-basis plans: column tables instead of cy^j (or NULL)
 };
 
 template <typename TIn> struct In2;
@@ -100,7 +101,10 @@ __global__ void __launch_bounds__(ROWV_NT, 1) row_fwd_v8_kernel(RowV8Args a, con
                 for (int q = 0; q < 8; ++q) {
                     const int n = lane + q * T;
                     double x0 = (double)x[q].x, x1 = (double)x[q].y;
-                    if (j > 0) {
+                    if (a.vtab) {
+                        const double2 vv = *reinterpret_cast<const double2*>(a.vtab + (size_t)j * a.N1 + 2 * n);
+                        x0 *= vv.x; x1 *= vv.y;
+                    } else if (j > 0) {
                         const double c0 = (2 * n + 1) * inv1, c1 = (2 * n + 2) * inv1;
                         x0 *= (j == 1) ? c0 : (j == 2 ? c0 * c0 : c0 * c0 * c0);
                         x1 *= (j == 1) ? c1 : (j == 2 ? c1 * c1 : c1 * c1 * c1);

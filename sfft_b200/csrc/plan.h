@@ -18,6 +18,7 @@
 #include "kernels_fit_seg3.cuh"
 #include "kernels_reader.cuh"
 #include "kernels_fitsio.cuh"
+#include "kernels_gen.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -140,6 +141,8 @@ struct sfftb_plan {
     long long launches;
     int last_solver;
     int have_fit;
+    void* gen;                   // general-basis plans (tu_gen.cu): GenState*, NULL for the polynomial sfftcore plans
+    const double* vtab;          // general-basis plans: column tables multiplied into the row pass (device, [nVs][N1])
 };
 
 static inline int init_generic_radix_tables() {
@@ -199,3 +202,20 @@ template <typename TSt> int launch_fir(sfftb_plan* p, const TSt* gIsrc, const do
 // sfft_b200.cu
 int upload_twiddles(int n, cd** out);
 int upload_engine_table(int Ns, int R, cd** out);
+int plan_init_common(sfftb_plan* p, const sfftb_config* cfg);
+// tu_fit.cu (shared with the general-basis path)
+int lag_reduce2_setup();
+int launch_lag_reduce2(sfftb_plan* p, const LagReduce2Args& a, const cd* kap, double* part);
+// tu_gen.cu
+int gen_plan_create(sfftb_plan* p, const sfftb_config* cfg, const sfftb_basis* ker, const sfftb_basis* sca, const sfftb_basis* bkg, int mode);
+void gen_free(sfftb_plan* p);
+int gen_nvs(const sfftb_plan* p);
+void* gen_planes(const sfftb_plan* p);
+int gen_set_regularizer(sfftb_plan* p);
+int gen_rjt(sfftb_plan* p, const void* dJ, int dtype);
+template <typename TSt> int gen_fit_cols(sfftb_plan* p);
+int gen_fill_system(sfftb_plan* p);
+int gen_restore(sfftb_plan* p);
+int gen_export(sfftb_plan* p, double* buf);
+template <typename TSt> int gen_fir(sfftb_plan* p, const double* dsol);
+int gen_bkg_subtract(sfftb_plan* p, const double* bf, void* ddiff, int diff_dtype);

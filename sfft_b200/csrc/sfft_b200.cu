@@ -173,6 +173,7 @@ static size_t fit_smem_bytes(const ColArgs& c, int PB) {
 static int plan_free(sfftb_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
+    gen_free(p);
     void* ptrs[] = {p->vt8_8, p->vt64_8, p->vt64_4, p->vt256_4, p->vt512_4, p->tabA, p->tabB_row, p->tabC_row, p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
                     p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->substMsg, p->solEff, p->regC, p->regD, p->regSST, p->regI, p->bluTw, p->bluC, p->bluB, p->firTaps, p->firCA, p->tstate, p->stC, p->stD};
     for (void* q : ptrs) if (q) cudaFree(q);
@@ -192,7 +193,8 @@ static int plan_free(sfftb_plan* p) {
 extern "C" int sfftb_version(void) { return SFFTB_VERSION; }
 extern "C" const char* sfftb_last_error(void) { return g_err.c_str(); }
 
-static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
+// Streams, events, twiddles, the row-pass geometry and the image-sized buffers every kind of plan needs.
+int plan_init_common(sfftb_plan* p, const sfftb_config* cfg) {
     p->cfg = *cfg;
     p->device = cfg->device;
     CK(cudaSetDevice(p->device));
@@ -214,17 +216,8 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
     sfftb_dims& d = p->d;
     d.N0 = cfg->N0; d.N1 = cfg->N1; d.w0 = cfg->w0; d.w1 = cfg->w1; d.DK = cfg->DK; d.DB = cfg->DB;
     d.L0 = 2 * d.w0 + 1; d.L1 = 2 * d.w1 + 1; d.Fab = d.L0 * d.L1;
-    d.Fij = (d.DK + 1) * (d.DK + 2) / 2; d.Fpq = (d.DB + 1) * (d.DB + 2) / 2;
-    d.Fijab = d.Fij * d.Fab; d.NEQ = d.Fijab + d.Fpq;
-    // sca_degree: with const_phot_ratio set, 0 ties the centre taps to ONE constant (stripes dropped) and
-    // DS > 0 gives them their own polynomial of degree DS <= DK (SEPARATE-VARYING, sfft/BSplineSFFT.py:77-86, 176-190)
-    const int DS = cfg->const_phot_ratio ? cfg->sca_degree : 0;
-    if (DS < 0 || DS > d.DK) return fail(SFFTB_EINVAL, "scaling degree %d must lie in 0..KerPolyOrder", DS);
-    p->sca_n = DS > 0 ? (DS + 1) * (DS + 2) / 2 : 0;
-    d.NEQ_FSfree = cfg->const_phot_ratio ? d.NEQ - (d.Fij - (p->sca_n ? p->sca_n : 1)) : d.NEQ;
     const int N0 = d.N0, N1 = d.N1, NH = N1 / 2 + 1;
     const size_t csz = cfg->storage == SFFTB_STORE_F32 ? sizeof(float2) : sizeof(double2);
-
     // ---- twiddle tables ----
     if (upload_twiddles(N0, &p->tw0)) return SFFTB_ECUDA;
     if (upload_twiddles(N1, &p->tw1)) return SFFTB_ECUDA;
@@ -259,6 +252,30 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
     r.twH = p->twH; r.tw1 = p->tw1;
     p->rinv.r = r;
     p->rinv.scale = (r.packed ? 2.0 : 1.0) / (double)N1;      // the FIR column pass already carries 1/N0
+    CK(cudaMalloc(&p->gJ, csz * (size_t)NH * N0));
+    CK(cudaMalloc(&p->stA, sizeof(double) * (size_t)N0 * N1));
+    CK(cudaMalloc(&p->stB, sizeof(double) * (size_t)N0 * N1));
+    CK(cudaMalloc(&p->info, sizeof(int) * 4));
+    CK(cudaMallocHost(&p->info_h, sizeof(int) * 4));
+    memset(p->info_h, 0, sizeof(int) * 4);
+    return 0;
+}
+
+static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
+    int rc0 = plan_init_common(p, cfg);
+    if (rc0) return rc0;
+    sfftb_dims& d = p->d;
+    RowArgs& r = p->row;
+    d.Fij = (d.DK + 1) * (d.DK + 2) / 2; d.Fpq = (d.DB + 1) * (d.DB + 2) / 2;
+    d.Fijab = d.Fij * d.Fab; d.NEQ = d.Fijab + d.Fpq;
+    // sca_degree: with const_phot_ratio set, 0 ties the centre taps to ONE constant (stripes dropped) and
+    // DS > 0 gives them their own polynomial of degree DS <= DK (SEPARATE-VARYING, sfft/BSplineSFFT.py:77-86, 176-190)
+    const int DS = cfg->const_phot_ratio ? cfg->sca_degree : 0;
+    if (DS < 0 || DS > d.DK) return fail(SFFTB_EINVAL, "scaling degree %d must lie in 0..KerPolyOrder", DS);
+    p->sca_n = DS > 0 ? (DS + 1) * (DS + 2) / 2 : 0;
+    d.NEQ_FSfree = cfg->const_phot_ratio ? d.NEQ - (d.Fij - (p->sca_n ? p->sca_n : 1)) : d.NEQ;
+    const int N0 = d.N0, N1 = d.N1, NH = N1 / 2 + 1;
+    const size_t csz = cfg->storage == SFFTB_STORE_F32 ? sizeof(float2) : sizeof(double2);
     p->rinv.DB = d.DB; p->rinv.Fpq = d.Fpq;
     {
         int k = 0;
@@ -316,9 +333,6 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
 
     // ---- workspaces ----
     CK(cudaMalloc(&p->gI, csz * (size_t)(d.DK + 1) * NH * N0));
-    CK(cudaMalloc(&p->gJ, csz * (size_t)NH * N0));
-    CK(cudaMalloc(&p->stA, sizeof(double) * (size_t)N0 * N1));
-    CK(cudaMalloc(&p->stB, sizeof(double) * (size_t)N0 * N1));
     p->nrowsK = p->cfit.npairs * p->cfit.nl0 + d.Fij * p->cfit.nlj0;
     p->nrowsL = d.Fij * (d.DB + 1) * p->cfit.nlj0;
     CK(cudaMalloc(&p->kap, sizeof(cd) * (size_t)p->nrowsK * NH));
@@ -336,9 +350,6 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
     CK(cudaMalloc(&p->diagU, sizeof(double) * (size_t)p->nsolve));
     CK(cudaMalloc(&p->sol, sizeof(double) * (size_t)d.NEQ));
     if (chol_setup(p)) return SFFTB_ECUDA;
-    CK(cudaMalloc(&p->info, sizeof(int) * 4));
-    CK(cudaMallocHost(&p->info_h, sizeof(int) * 4));
-    memset(p->info_h, 0, sizeof(int) * 4);
 
     // ---- index maps (forbidden stripes: SFFTSubtract.py:82-90) ----
     {
@@ -480,6 +491,25 @@ extern "C" int sfftb_plan_create(sfftb_plan** out, const sfftb_config* cfg) {
     return 0;
 }
 
+extern "C" int sfftb_plan_create_general(sfftb_plan** out, const sfftb_config* cfg, const sfftb_basis* ker, const sfftb_basis* sca,
+                                         const sfftb_basis* bkg, int scaling_mode) {
+    if (!out || !cfg) return fail(SFFTB_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->N0 < 2 || cfg->N1 < 2) return fail(SFFTB_EINVAL, "image shape (%d, %d) too small", cfg->N0, cfg->N1);
+    if (cfg->w0 < 0 || cfg->w1 < 0 || 2 * cfg->w0 + 1 > cfg->N0 || 2 * cfg->w1 + 1 > cfg->N1)
+        return fail(SFFTB_EINVAL, "kernel half width (%d, %d) does not fit the image (%d, %d)", cfg->w0, cfg->w1, cfg->N0, cfg->N1);
+    if (cfg->storage != SFFTB_STORE_F64 && cfg->storage != SFFTB_STORE_F32) return fail(SFFTB_EINVAL, "bad storage precision");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(SFFTB_EINVAL, "CUDA device %d not available (%d visible)", cfg->device, ndev);
+    sfftb_plan* p = new sfftb_plan();
+    memset((void*)p, 0, sizeof *p);
+    const int rc = gen_plan_create(p, cfg, ker, sca, bkg, scaling_mode);
+    if (rc) { std::string keep = g_err; plan_free(p); g_err = keep; return rc; }
+    *out = p;
+    return 0;
+}
+
 extern "C" int sfftb_plan_destroy(sfftb_plan* p) { return plan_free(p); }
 
 extern "C" int sfftb_plan_dims(const sfftb_plan* p, sfftb_dims* out) {
@@ -544,6 +574,24 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, 
                       const void* ovI = nullptr, const void* ovJ = nullptr) {
     const sfftb_dims& d = p->d;
     EVREC(p, EV_START);
+    if (p->gen) {
+        // general-basis plan: stored planes through the column tables, block passes, descriptor-driven fill
+        if (launch_row_fwd<TSt>(p, dI, dtype, (TSt*)gen_planes(p), gen_nvs(p))) return SFFTB_ECUDA;
+        if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
+        if (gen_rjt(p, dJ, dtype)) return SFFTB_ECUDA;
+        EVREC(p, EV_ROWS);
+        if (gen_fit_cols<TSt>(p)) return SFFTB_ECUDA;
+        CK(cudaMemsetAsync(p->info, 0, sizeof(int) * 4, p->stream));
+        if (gen_fill_system(p)) return SFFTB_ECUDA;
+        EVREC(p, EV_RED);
+        if (run_cholesky(p)) return SFFTB_ECUDA;
+        if (gen_restore(p)) return SFFTB_ECUDA;
+        EVREC(p, EV_SOLVE);
+        CK(cudaMemcpyAsync(p->info_h, p->info, sizeof(int) * 4, cudaMemcpyDeviceToHost, p->stream));
+        p->have_fit = 1;
+        p->last_solver = 1;
+        return 0;
+    }
     const TSt* gIsrc = tI ? (const TSt*)tI : (const TSt*)p->gI;
     if (p->pendI) { CK(cudaStreamWaitEvent(p->stream, p->pendI, 0)); p->pendI = nullptr; }
     if (!tI && launch_row_fwd<TSt>(p, dI, dtype, (TSt*)p->gI, d.DK + 1)) return SFFTB_ECUDA;
@@ -601,8 +649,9 @@ static int check_solver(sfftb_plan* p) {
     if (p->info_h[0] == 0) return 0;
     // Cholesky pivot not positive: refill and solve by LU with partial pivoting
     CK(cudaMemsetAsync(p->info, 0, sizeof(int) * 4, p->stream));
-    if (fill_system(p)) return SFFTB_ECUDA;
+    if (p->gen ? gen_fill_system(p) : fill_system(p)) return SFFTB_ECUDA;
     if (run_lu(p)) return SFFTB_ECUDA;
+    if (p->gen && gen_restore(p)) return SFFTB_ECUDA;
     CK(cudaMemcpyAsync(p->info_h, p->info, sizeof(int) * 4, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     p->last_solver = 2;
@@ -633,6 +682,19 @@ static int apply_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype
                         const void* tI = nullptr, bool rows_done = false, void* hdiff = nullptr) {
     const sfftb_dims& d = p->d;
     EVREC(p, EV_A0);
+    if (p->gen) {
+        if (!rows_done) {
+            if (launch_row_fwd<TSt>(p, dI, dtype, (TSt*)gen_planes(p), gen_nvs(p))) return SFFTB_ECUDA;
+            if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
+        }
+        EVREC(p, EV_AROWS);
+        if (gen_fir<TSt>(p, dsol)) return SFFTB_ECUDA;
+        EVREC(p, EV_ACOL);
+        if (launch_row_inv<TSt>(p, dsol + d.Fijab, ddiff, diff_dtype, nullptr)) return SFFTB_ECUDA;
+        if (gen_bkg_subtract(p, dsol + d.Fijab, ddiff, diff_dtype)) return SFFTB_ECUDA;
+        EVREC(p, EV_AINV);
+        return 0;
+    }
     if (p->sca_n) {
         sca_remap_kernel<<<(d.NEQ + 255) / 256, 256, 0, p->stream>>>(p->fill, d.NEQ, dsol, p->solEff);
         CKL(p);
@@ -736,7 +798,7 @@ extern "C" int sfftb_gss(sfftb_plan* p, const void* I, const void* J, const void
     // host images: all four H2D copies are queued on the side stream up front, so the copies of the apply pair run
     // under the fit and every row pass starts as soon as its own image has landed
     const bool hostpipe = memkind == SFFTB_MEM_HOST && I && J && mI && mJ && (dtype == SFFTB_F64 || dtype == SFFTB_F32) &&
-                          !env_int("SFFTB_NO_HOSTPIPE", 0);
+                          !p->gen && !env_int("SFFTB_NO_HOSTPIPE", 0);
     if (hostpipe) {
         const size_t bytes = (size_t)p->d.N0 * p->d.N1 * (dtype == SFFTB_F64 ? 8 : 4);
         if (!p->stC) { CK(cudaMalloc(&p->stC, sizeof(double) * (size_t)p->d.N0 * p->d.N1)); CK(cudaMalloc(&p->stD, sizeof(double) * (size_t)p->d.N0 * p->d.N1)); }
@@ -779,7 +841,7 @@ extern "C" int sfftb_gss(sfftb_plan* p, const void* I, const void* J, const void
     }
     if ((rc = stage_in(p, mI, memkind, dtype, p->stA, &dI))) return rc;
     if ((rc = stage_in(p, mJ, memkind, dtype, p->stB, &dJ))) return rc;
-    const bool ov = p->overlap && memkind == SFFTB_MEM_DEVICE && I && J && p->row_v8 && p->chol_coop && p->nsm >= 8;
+    const bool ov = p->overlap && memkind == SFFTB_MEM_DEVICE && I && J && p->row_v8 && p->chol_coop && p->nsm >= 8 && !p->gen;
     rc = f32 ? fit_device<float2>(p, dI, dJ, dtype, nullptr, ov ? I : nullptr, ov ? J : nullptr)
              : fit_device<double2>(p, dI, dJ, dtype, nullptr, ov ? I : nullptr, ov ? J : nullptr);
     if (rc) return rc;
@@ -815,6 +877,7 @@ extern "C" int sfftb_gss_submit(sfftb_plan* p, const void* I, const void* J, con
                                 double* solution, void* diff, int diff_dtype) {
     if (!p || !I || !J || !mI || !mJ || !diff) return fail(SFFTB_EINVAL, "null argument");
     if ((dtype != SFFTB_F64 && dtype != SFFTB_F32) || (diff_dtype != SFFTB_F64 && diff_dtype != SFFTB_F32)) return fail(SFFTB_EINVAL, "bad dtype");
+    if (p->gen) return fail(SFFTB_EINVAL, "sfftb_gss_submit is not available for general-basis plans");
     if (p->pending) return fail(SFFTB_ESTATE, "sfftb_gss_submit: the previous submission of this plan has not been finished");
     CK(cudaSetDevice(p->device));
     const bool f32 = p->cfg.storage == SFFTB_STORE_F32;
@@ -859,6 +922,7 @@ extern "C" int sfftb_gss_template_submit(sfftb_plan* p, const void* J, const voi
     if (!p || !J || !mJ || !diff) return fail(SFFTB_EINVAL, "null argument");
     if (memkind != SFFTB_MEM_HOST && memkind != SFFTB_MEM_DEVICE) return fail(SFFTB_EINVAL, "bad memkind");
     if ((dtype != SFFTB_F64 && dtype != SFFTB_F32) || (diff_dtype != SFFTB_F64 && diff_dtype != SFFTB_F32)) return fail(SFFTB_EINVAL, "bad dtype");
+    if (p->gen) return fail(SFFTB_EINVAL, "the shared-template path is not available for general-basis plans");
     if (!p->have_template) return fail(SFFTB_ESTATE, "no template has been prepared on this plan");
     if (p->pending) return fail(SFFTB_ESTATE, "sfftb_gss_template_submit: the previous submission of this plan has not been finished");
     CK(cudaSetDevice(p->device));
@@ -945,6 +1009,7 @@ extern "C" int sfftb_gss_finish(sfftb_plan* p) {
 
 // ---- shared-template batch path (the reference re-transforms the template for every pair) ------------
 static int template_alloc(sfftb_plan* p) {
+    if (p->gen) return fail(SFFTB_EINVAL, "the shared-template path is not available for general-basis plans");
     if (p->tstate) return 0;
     const size_t csz = p->cfg.storage == SFFTB_STORE_F32 ? sizeof(float2) : sizeof(double2);
     p->tstate_bytes = 2 * csz * (size_t)(p->d.DK + 1) * (p->d.N1 / 2 + 1) * p->d.N0;
@@ -1092,7 +1157,7 @@ extern "C" int sfftb_set_regularizer(sfftb_plan* p, const double* SST, const dou
     CK(cudaStreamSynchronize(p->stream));
     p->factor_cached = 0;
     p->fill.CSST = nullptr; p->fill.DSST = nullptr;
-    if (!SST || !iREG) { p->fill.SST = nullptr; p->fill.iREG = nullptr; p->fill.regw = 0.0; return 0; }
+    if (!SST || !iREG) { p->fill.SST = nullptr; p->fill.iREG = nullptr; p->fill.regw = 0.0; if (p->gen) gen_set_regularizer(p); return 0; }
     if (!(lambda >= 0.0)) return fail(SFFTB_EINVAL, "LAMBDA_REGULARIZE must be >= 0");
     const size_t nS = (size_t)p->d.Fij * p->d.Fij, nI = (size_t)p->d.Fab * p->d.Fab;
     if (!p->regSST) { CK(cudaMalloc(&p->regSST, sizeof(double) * nS)); CK(cudaMalloc(&p->regI, sizeof(double) * nI)); }
@@ -1100,6 +1165,7 @@ extern "C" int sfftb_set_regularizer(sfftb_plan* p, const double* SST, const dou
     CK(cudaMemcpy(p->regI, iREG, sizeof(double) * nI, cudaMemcpyHostToDevice));
     const double N = (double)p->d.N0 * (double)p->d.N1;
     p->fill.SST = p->regSST; p->fill.iREG = p->regI; p->fill.regw = lambda / (N * N);
+    if (p->gen) gen_set_regularizer(p);
     return 0;
 }
 
@@ -1107,7 +1173,7 @@ extern "C" int sfftb_set_regularizer(sfftb_plan* p, const double* SST, const dou
 // Call after sfftb_set_regularizer; (Fij x Fij) host arrays, rows / columns beyond ScaFij zero (the placeholder basis).
 extern "C" int sfftb_set_regularizer_varying(sfftb_plan* p, const double* CSST, const double* DSST) {
     if (!p || !CSST || !DSST) return fail(SFFTB_EINVAL, "null argument");
-    if (!p->sca_n) return fail(SFFTB_ESTATE, "the plan was not created with a varying scaling (sca_degree > 0)");
+    if (!p->sca_n && !p->gen) return fail(SFFTB_ESTATE, "the plan was not created with a varying scaling (sca_degree > 0)");
     if (!p->fill.SST) return fail(SFFTB_ESTATE, "call sfftb_set_regularizer first");
     CK(cudaSetDevice(p->device));
     CK(cudaStreamSynchronize(p->stream));
@@ -1117,6 +1183,7 @@ extern "C" int sfftb_set_regularizer_varying(sfftb_plan* p, const double* CSST, 
     CK(cudaMemcpy(p->regC, CSST, sizeof(double) * nS, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(p->regD, DSST, sizeof(double) * nS, cudaMemcpyHostToDevice));
     p->fill.CSST = p->regC; p->fill.DSST = p->regD;
+    if (p->gen) gen_set_regularizer(p);
     return 0;
 }
 
@@ -1124,6 +1191,7 @@ extern "C" int sfftb_set_regularizer_varying(sfftb_plan* p, const double* CSST, 
 extern "C" int sfftb_realize(sfftb_plan* p, const double* solution, int sol_memkind, const double* xy, int xy_memkind, int nq,
                              double* kerstack, double* fscal, int out_memkind) {
     if (!p || !solution || !xy) return fail(SFFTB_EINVAL, "null argument");
+    if (p->gen) return fail(SFFTB_EINVAL, "general-basis plans realise kernels through sfftb_realize_general");
     if (nq <= 0) return fail(SFFTB_EINVAL, "no coordinates requested");
     if (!kerstack && !fscal) return 0;
     CK(cudaSetDevice(p->device));
@@ -1161,8 +1229,32 @@ extern "C" int sfftb_realize(sfftb_plan* p, const double* solution, int sol_memk
     return 0;
 }
 
+extern "C" int sfftb_export_solved_system(sfftb_plan* p, double* L, double* b) {
+    if (!p) return fail(SFFTB_EINVAL, "null plan");
+    if (!p->have_fit) return fail(SFFTB_ESTATE, "no fit has been run on this plan");
+    CK(cudaSetDevice(p->device));
+    const int n = p->nsolve, ld = n + 1;
+    double* buf = nullptr;
+    CK(cudaMalloc(&buf, sizeof(double) * (size_t)(n + 1) * ld));
+    int rc = 0;
+    if (p->gen) rc = gen_export(p, buf);
+    else {
+        dim3 blk(32, 8), grd((n + 1 + 31) / 32, (n + 1 + 7) / 8);
+        fill_matrix_kernel<<<grd, blk, 0, p->stream>>>(p->fill, p->idxmap, n, nullptr, buf, ld, p->info + 3);
+        p->launches++;
+    }
+    cudaError_t e = rc ? cudaErrorUnknown : cudaGetLastError();
+    if (e == cudaSuccess && L) e = cudaMemcpy2DAsync(L, sizeof(double) * n, buf, sizeof(double) * ld, sizeof(double) * n, n, cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess && b) e = cudaMemcpyAsync(b, buf + (size_t)n * ld, sizeof(double) * n, cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    cudaFree(buf);
+    if (e != cudaSuccess) return fail(SFFTB_ECUDA, "sfftb_export_solved_system: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 extern "C" int sfftb_export_normal_eq(sfftb_plan* p, double* LHMAT, double* RHb) {
     if (!p) return fail(SFFTB_EINVAL, "null plan");
+    if (p->gen) return fail(SFFTB_EINVAL, "general-basis plans export the solved system (sfftb_export_solved_system)");
     if (!p->have_fit) return fail(SFFTB_ESTATE, "no fit has been run on this plan");
     CK(cudaSetDevice(p->device));
     const int n = p->d.NEQ, ld = n + 1;
@@ -1178,6 +1270,7 @@ extern "C" int sfftb_export_normal_eq(sfftb_plan* p, double* LHMAT, double* RHb)
 
 extern "C" int sfftb_dbg_lag_tables(sfftb_plan* p, double* R, double* RJ, double* RT, double* RJT) {
     if (!p) return fail(SFFTB_EINVAL, "null plan");
+    if (p->gen) return fail(SFFTB_EINVAL, "not available for general-basis plans");
     if (!p->have_fit) return fail(SFFTB_ESTATE, "no fit has been run on this plan");
     CK(cudaSetDevice(p->device));
     const sfftb_dims& d = p->d;
@@ -1197,6 +1290,7 @@ __global__ void widen_kernel(const TSt* __restrict__ in, cd* __restrict__ out, s
 
 extern "C" int sfftb_dbg_row_spectra(sfftb_plan* p, int which, double* out) {
     if (!p || !out) return fail(SFFTB_EINVAL, "null argument");
+    if (p->gen) return fail(SFFTB_EINVAL, "not available for general-basis plans");
     CK(cudaSetDevice(p->device));
     const sfftb_dims& d = p->d;
     const size_t n = (size_t)(which == 0 ? d.DK + 1 : 1) * (d.N1 / 2 + 1) * d.N0;

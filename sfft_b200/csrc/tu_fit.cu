@@ -81,5 +81,14 @@ int launch_fit_cols(sfftb_plan* p, const TSt* gIsrc, bool jonly) {
     return 0;
 }
 
+int lag_reduce2_setup() { return set_smem(lag_reduce2_kernel, sizeof(cd) * LR2_KC * LR2_LB); }
+
+int launch_lag_reduce2(sfftb_plan* p, const LagReduce2Args& a, const cd* kap, double* part) {
+    dim3 grd((a.nrows + 15) / 16, a.ksplit);
+    lag_reduce2_kernel<<<grd, 256, sizeof(cd) * LR2_KC * LR2_LB, p->stream>>>(a, kap, part);
+    CKL(p);
+    return 0;
+}
+
 template int launch_fit_cols<float2>(sfftb_plan*, const float2*, bool);
 template int launch_fit_cols<double2>(sfftb_plan*, const double2*, bool);

@@ -7,6 +7,7 @@ int rows_setup(sfftb_plan* p) {
     const RowArgs& r = p->row;
     const bool f32 = p->cfg.storage == SFFTB_STORE_F32;
     if (init_generic_radix_tables()) return SFFTB_ECUDA;
+    p->row.vtab = p->vtab;
     if (f32) {
         if (set_smem(row_fwd_kernel<float, float2>, p->smem_row) || set_smem(row_fwd_kernel<double, float2>, p->smem_row)) return SFFTB_ECUDA;
         if (set_smem(row_inv_kernel<float2, float>, p->smem_row) || set_smem(row_inv_kernel<float2, double>, p->smem_row)) return SFFTB_ECUDA;
@@ -24,7 +25,7 @@ int rows_setup(sfftb_plan* p) {
         if (r.H == 8192 && upload_engine_table(4096, 2, &p->tabC_row)) return SFFTB_ECUDA;
         RowFastArgs& rf = p->rowf;
         rf.N0 = d.N0; rf.N1 = d.N1; rf.NH = d.N1 / 2 + 1; rf.H = r.H;
-        rf.tabA = p->tabA; rf.tabB = p->tabB_row; rf.tabC = p->tabC_row; rf.tw1 = p->tw1;
+        rf.tabA = p->tabA; rf.tabB = p->tabB_row; rf.tabC = p->tabC_row; rf.tw1 = p->tw1; rf.vtab = p->vtab;
         p->rinvf.r = rf; p->rinvf.scale = p->rinv.scale; p->rinvf.Fpq = d.Fpq;
         memcpy(p->rinvf.p_of, p->rinv.p_of, 16); memcpy(p->rinvf.q_of, p->rinv.q_of, 16);
         p->row_fast = r.H;
@@ -38,7 +39,7 @@ int rows_setup(sfftb_plan* p) {
         rv.N0 = d.N0; rv.N1 = d.N1; rv.NH = d.N1 / 2 + 1; rv.H = r.H;
         rv.nit = std::max(1, env_int("SFFTB_ROW_NIT", 2));
         rv.tabs = p->vtabs;
-        rv.tw1 = p->tw1;
+        rv.tw1 = p->tw1; rv.vtab = p->vtab;
         const int RBI = ROWV_NT / (r.H / 8);
         p->smem_rowv = sizeof(cd) * ((size_t)RBI * (r.H + r.H / 8 + 8) + 3000 + r.H / 2 + 1);
 #define SET_ROWV(HH)                                                                                              \

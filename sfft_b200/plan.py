@@ -42,6 +42,45 @@ class Plan:
         self.shape = (int(N0), int(N1))
         self.NEQ = self.dims['NEQ']
 
+    @classmethod
+    def general(cls, N0, N1, w0, w1, ker, bkg, scaling_mode, sca=None, device=0, storage='fp64', DK=0, DB=0):
+        """General-basis plan (sfftb_plan_create_general): `ker`, `bkg`, `sca` are (U, V, fu, fv) tuples -- the 1-D tables
+        U (nu, N0), V (nv, N1) and, per 2-D basis function, the rows it is the product of."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        self._L = B.lib()
+        cfg = B.Config()
+        cfg.device, cfg.N0, cfg.N1, cfg.w0, cfg.w1 = int(device), int(N0), int(N1), int(w0), int(w1)
+        cfg.DK, cfg.DB = int(DK), int(DB)
+        cfg.storage = {'fp64': B.STORE_F64, 'fp32': B.STORE_F32}[storage]
+        keep = []
+
+        def mk(b):
+            if b is None:
+                return None
+            U = np.ascontiguousarray(b[0], np.float64)
+            V = np.ascontiguousarray(b[1], np.float64)
+            fu = np.ascontiguousarray(b[2], np.int32)
+            fv = np.ascontiguousarray(b[3], np.int32)
+            if U.ndim != 2 or V.ndim != 2 or U.shape[1] != N0 or V.shape[1] != N1 or fu.shape != fv.shape or fu.ndim != 1:
+                raise Exception('MeLOn ERROR: basis tables must have shapes (nu, N0), (nv, N1) and index vectors of one length')
+            keep.extend([U, V, fu, fv])
+            s = B.Basis()
+            s.nu, s.nv, s.nf = U.shape[0], V.shape[0], fu.shape[0]
+            s.U, s.V, s.fu, s.fv = U.ctypes.data, V.ctypes.data, fu.ctypes.data, fv.ctypes.data
+            keep.append(s)
+            return s
+        bk, bs, bb = mk(ker), mk(sca), mk(bkg)
+        B.check(self._L.sfftb_plan_create_general(C.byref(self._h), C.byref(cfg), C.byref(bk), C.byref(bs) if bs is not None else None,
+                                                  C.byref(bb), int(scaling_mode)))
+        d = B.Dims()
+        B.check(self._L.sfftb_plan_dims(self._h, C.byref(d)))
+        self.dims = {k: getattr(d, k) for k, _ in B.Dims._fields_}
+        self.device, self.storage = int(device), storage
+        self.shape = (int(N0), int(N1))
+        self.NEQ = self.dims['NEQ']
+        return self
+
     def close(self):
         if getattr(self, '_h', None) is not None and self._h.value:
             self._L.sfftb_plan_destroy(self._h)
@@ -251,6 +290,14 @@ class Plan:
         L = np.empty((n, n), np.float64)
         b = np.empty(n, np.float64)
         B.check(self._L.sfftb_export_normal_eq(self._h, L.ctypes.data, b.ctypes.data))
+        return L, b
+
+    def export_solved_system(self):
+        """(L, b) of the system the last fit solved, after the stripe tweak (sfftb_export_solved_system)."""
+        n = self.dims['NEQ_FSfree']
+        L = np.empty((n, n), np.float64)
+        b = np.empty(n, np.float64)
+        B.check(self._L.sfftb_export_solved_system(self._h, L.ctypes.data, b.ctypes.data))
         return L, b
 
     def dbg_row_spectra(self, which):
