@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_gen_kernel(GenFitArgs fa, GenPa
                     const cd* sp = spec + (size_t)slot * NPMAX * FS3_PITCH + VPAD(tid);
                     cd fA[NA];
 #pragma unroll
-                    for (int A = 0; A < NA; ++A) fA[A] = sp[A * FS3_PITCH];
+                    for (int A = 0; A < NA; ++A) fA[A] = (A < ps.na) ? sp[A * FS3_PITCH] : cmake(0.0, 0.0);   // unused slots hold inverse-phase scratch
 #pragma unroll
                     for (int b = 0; b < NB; ++b)
                         if (b < ps.nbt) fB[b] = sp[(NA + b) * FS3_PITCH];
@@ -329,7 +329,7 @@ struct GenFillArgs {
     int n, NEQ, Fijab, Fab, Fij, Fpq, L0, L1, w0, w1, nl1, P;
     const int* u_plane; const signed char* u_a; const signed char* u_b; const signed char* u_mod;
     const int* u_ref0; const int* u_nref; const int* refs;
-    const int* pairrow;              // [P][P] first Rall row of pair (A <= B)
+    const int* pairrow;              // [P][P] first Rall row of the pair with plane A in the A role, -1 = stored as (B, A)
     const int* rowJ;                 // [P]
     const int* rowT;                 // [P][Fpq]
     const double* Rall; const double* PQ; const double* PHI;
@@ -340,8 +340,9 @@ struct GenFillArgs {
 
 #ifdef SFFTB_TU_GEN
 __device__ __forceinline__ double gen_R(const GenFillArgs& f, int A, int B, int m0, int m1) {
-    if (A > B) { const int t = A; A = B; B = t; m0 = -m0; m1 = -m1; }
-    const int rb = f.pairrow[A * f.P + B];
+    // the pair was computed with one of its planes in the A role (whichever the pass order put first): R_BA[m] = R_AB[-m]
+    int rb = f.pairrow[A * f.P + B];
+    if (rb < 0) { rb = f.pairrow[B * f.P + A]; m0 = -m0; m1 = -m1; }
     return f.Rall[((size_t)rb + (m0 + 2 * f.w0)) * f.nl1 + (m1 + 2 * f.w1)];
 }
 

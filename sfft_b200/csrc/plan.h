@@ -187,7 +187,7 @@ static int env_int(const char* name, int dflt) {
 // ---- family entry points (one translation unit each) -----------------------------------------------------------------
 // tu_rows.cu
 int rows_setup(sfftb_plan* p);
-template <typename TSt> int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj);
+template <typename TSt> int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj, const double* vtab = nullptr);
 template <typename TSt> int launch_row_inv(sfftb_plan* p, const double* bpq, void* ddiff, int diff_dtype, void* hdiff);
 // tu_fit.cu
 int fit_setup(sfftb_plan* p);

@@ -576,7 +576,7 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, 
     EVREC(p, EV_START);
     if (p->gen) {
         // general-basis plan: stored planes through the column tables, block passes, descriptor-driven fill
-        if (launch_row_fwd<TSt>(p, dI, dtype, (TSt*)gen_planes(p), gen_nvs(p))) return SFFTB_ECUDA;
+        if (launch_row_fwd<TSt>(p, dI, dtype, (TSt*)gen_planes(p), gen_nvs(p), p->vtab)) return SFFTB_ECUDA;
         if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
         if (gen_rjt(p, dJ, dtype)) return SFFTB_ECUDA;
         EVREC(p, EV_ROWS);
@@ -684,7 +684,7 @@ static int apply_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype
     EVREC(p, EV_A0);
     if (p->gen) {
         if (!rows_done) {
-            if (launch_row_fwd<TSt>(p, dI, dtype, (TSt*)gen_planes(p), gen_nvs(p))) return SFFTB_ECUDA;
+            if (launch_row_fwd<TSt>(p, dI, dtype, (TSt*)gen_planes(p), gen_nvs(p), p->vtab)) return SFFTB_ECUDA;
             if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
         }
         EVREC(p, EV_AROWS);

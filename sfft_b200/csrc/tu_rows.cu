@@ -7,7 +7,6 @@ int rows_setup(sfftb_plan* p) {
     const RowArgs& r = p->row;
     const bool f32 = p->cfg.storage == SFFTB_STORE_F32;
     if (init_generic_radix_tables()) return SFFTB_ECUDA;
-    p->row.vtab = p->vtab;
     if (f32) {
         if (set_smem(row_fwd_kernel<float, float2>, p->smem_row) || set_smem(row_fwd_kernel<double, float2>, p->smem_row)) return SFFTB_ECUDA;
         if (set_smem(row_inv_kernel<float2, float>, p->smem_row) || set_smem(row_inv_kernel<float2, double>, p->smem_row)) return SFFTB_ECUDA;
@@ -25,7 +24,7 @@ int rows_setup(sfftb_plan* p) {
         if (r.H == 8192 && upload_engine_table(4096, 2, &p->tabC_row)) return SFFTB_ECUDA;
         RowFastArgs& rf = p->rowf;
         rf.N0 = d.N0; rf.N1 = d.N1; rf.NH = d.N1 / 2 + 1; rf.H = r.H;
-        rf.tabA = p->tabA; rf.tabB = p->tabB_row; rf.tabC = p->tabC_row; rf.tw1 = p->tw1; rf.vtab = p->vtab;
+        rf.tabA = p->tabA; rf.tabB = p->tabB_row; rf.tabC = p->tabC_row; rf.tw1 = p->tw1;
         p->rinvf.r = rf; p->rinvf.scale = p->rinv.scale; p->rinvf.Fpq = d.Fpq;
         memcpy(p->rinvf.p_of, p->rinv.p_of, 16); memcpy(p->rinvf.q_of, p->rinv.q_of, 16);
         p->row_fast = r.H;
@@ -39,7 +38,7 @@ int rows_setup(sfftb_plan* p) {
         rv.N0 = d.N0; rv.N1 = d.N1; rv.NH = d.N1 / 2 + 1; rv.H = r.H;
         rv.nit = std::max(1, env_int("SFFTB_ROW_NIT", 2));
         rv.tabs = p->vtabs;
-        rv.tw1 = p->tw1; rv.vtab = p->vtab;
+        rv.tw1 = p->tw1;
         const int RBI = ROWV_NT / (r.H / 8);
         p->smem_rowv = sizeof(cd) * ((size_t)RBI * (r.H + r.H / 8 + 8) + 3000 + r.H / 2 + 1);
 #define SET_ROWV(HH)                                                                                              \
@@ -67,17 +66,21 @@ int rows_setup(sfftb_plan* p) {
 }
 
 template <typename TSt>
-int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj) {
+int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj, const double* vtab) {
+    // vtab != NULL (general-basis plans, the planes of I only): plane j = row x vtab[j][c] instead of cy^j
+    RowV8Args rowv = p->rowv; rowv.vtab = vtab;
+    RowFastArgs rowf = p->rowf; rowf.vtab = vtab;
+    RowArgs rowg = p->row; rowg.vtab = vtab;
     const size_t esz2 = dtype == SFFTB_F64 ? 16 : 8;
     if (p->row_v8 && ((uintptr_t)img % esz2) == 0) {
         const int H = p->row_v8, RBI = ROWV_NT / (H / 8);
         const int ngroups = (p->d.N0 + RBI - 1) / RBI;
-        const int nbatch = (ngroups + p->rowv.nit - 1) / p->rowv.nit;
+        const int nbatch = (ngroups + rowv.nit - 1) / rowv.nit;
         const int grid = std::min(nbatch, p->row_grid_limit > 0 ? p->row_grid_limit : p->nsm);
 #define RUN_ROWV(HH)                                                                                                   \
         if (H == HH) {                                                                                                 \
-            if (dtype == SFFTB_F64) row_fwd_v8_kernel<double, TSt, HH><<<grid, ROWV_NT, p->smem_rowv, p->stream>>>(p->rowv, (const double*)img, out, nj); \
-            else row_fwd_v8_kernel<float, TSt, HH><<<grid, ROWV_NT, p->smem_rowv, p->stream>>>(p->rowv, (const float*)img, out, nj);                     \
+            if (dtype == SFFTB_F64) row_fwd_v8_kernel<double, TSt, HH><<<grid, ROWV_NT, p->smem_rowv, p->stream>>>(rowv, (const double*)img, out, nj); \
+            else row_fwd_v8_kernel<float, TSt, HH><<<grid, ROWV_NT, p->smem_rowv, p->stream>>>(rowv, (const float*)img, out, nj);                     \
         }
         RUN_ROWV(256) RUN_ROWV(512) RUN_ROWV(1024) RUN_ROWV(2048)
 #undef RUN_ROWV
@@ -90,8 +93,8 @@ int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj) 
         const size_t sm = sizeof(cd) * (size_t)RB * (H + H / 16);
 #define RUN_ROWF(HH)                                                                                                   \
         if (H == HH) {                                                                                                 \
-            if (dtype == SFFTB_F64) row_fwd_fast_kernel<double, TSt, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rowf, (const double*)img, out, nj); \
-            else row_fwd_fast_kernel<float, TSt, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rowf, (const float*)img, out, nj);                     \
+            if (dtype == SFFTB_F64) row_fwd_fast_kernel<double, TSt, HH><<<grid, ROWF_NT, sm, p->stream>>>(rowf, (const double*)img, out, nj); \
+            else row_fwd_fast_kernel<float, TSt, HH><<<grid, ROWF_NT, sm, p->stream>>>(rowf, (const float*)img, out, nj);                     \
         }
         RUN_ROWF(512) RUN_ROWF(1024) RUN_ROWF(2048) RUN_ROWF(4096) RUN_ROWF(8192)
 #undef RUN_ROWF
@@ -100,9 +103,9 @@ int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj) 
     }
     const int grid = (p->d.N0 + p->row.RB - 1) / p->row.RB;
     if (dtype == SFFTB_F64)
-        row_fwd_kernel<double, TSt><<<grid, 512, p->smem_row, p->stream>>>(p->row, (const double*)img, out, nj);
+        row_fwd_kernel<double, TSt><<<grid, 512, p->smem_row, p->stream>>>(rowg, (const double*)img, out, nj);
     else
-        row_fwd_kernel<float, TSt><<<grid, 512, p->smem_row, p->stream>>>(p->row, (const float*)img, out, nj);
+        row_fwd_kernel<float, TSt><<<grid, 512, p->smem_row, p->stream>>>(rowg, (const float*)img, out, nj);
     CKL(p);
     return 0;
 }
@@ -155,7 +158,7 @@ int launch_row_inv(sfftb_plan* p, const double* bpq, void* ddiff, int diff_dtype
     return 0;
 }
 
-template int launch_row_fwd<float2>(sfftb_plan*, const void*, int, float2*, int);
-template int launch_row_fwd<double2>(sfftb_plan*, const void*, int, double2*, int);
+template int launch_row_fwd<float2>(sfftb_plan*, const void*, int, float2*, int, const double*);
+template int launch_row_fwd<double2>(sfftb_plan*, const void*, int, double2*, int, const double*);
 template int launch_row_inv<float2>(sfftb_plan*, const double*, void*, int, void*);
 template int launch_row_inv<double2>(sfftb_plan*, const double*, void*, int, void*);

@@ -10,20 +10,71 @@ from oracle import bspline_oracle as bo
 from util import relrms
 
 
-def test_unsupported_modes_are_refused_loudly():
+def test_argument_checks_mirror_the_reference():
+    """Argument validation that happens before any plan is built (BSplineSFFT.py:33-38, 79-81, 190)."""
     from sfft_b200.BSplineSFFT import SingleSFFTConfigure
-    with pytest.raises(Exception, match='B-Spline spatial variation is not available'):
-        SingleSFFTConfigure.SSC(64, 64, KerHW=2, KerSpType='B-Spline', KerSpDegree=2, VERBOSE_LEVEL=0)
-    with pytest.raises(Exception, match='B-Spline spatial variation is not available'):
-        SingleSFFTConfigure.SSC(64, 64, KerHW=2, BkgSpType='B-Spline', BkgSpDegree=1, VERBOSE_LEVEL=0)
-    with pytest.raises(Exception, match='polynomial scaling only'):
-        SingleSFFTConfigure.SSC(64, 64, KerHW=2, SEPARATE_SCALING=True, ScaSpType='B-Spline', ScaSpDegree=1, VERBOSE_LEVEL=0)
-    with pytest.raises(AssertionError):
+    with pytest.raises(AssertionError):          # ScaFij <= Fij
         SingleSFFTConfigure.SSC(64, 64, KerHW=2, KerSpDegree=1, SEPARATE_SCALING=True, ScaSpDegree=2, VERBOSE_LEVEL=0)
     with pytest.raises(Exception, match='not available in sfft_b200'):
         SingleSFFTConfigure.SSC(64, 64, KerHW=2, BACKEND_4SUBTRACT='Numpy', VERBOSE_LEVEL=0)
     with pytest.raises(AssertionError):
         SingleSFFTConfigure.SSC(64, 64, KerHW=2, KerSpType='Fourier', VERBOSE_LEVEL=0)
+    with pytest.raises(AssertionError):          # a degree-0 B-spline has no internal knots
+        SingleSFFTConfigure.SSC(64, 64, KerHW=2, KerSpType='B-Spline', KerSpDegree=0, KerIntKnotX=[30.0], VERBOSE_LEVEL=0)
+    with pytest.raises(AssertionError):
+        SingleSFFTConfigure.SSC(64, 64, KerHW=2, BkgSpType='B-Spline', BkgSpDegree=0, BkgIntKnotY=[30.0], VERBOSE_LEVEL=0)
+
+
+def test_basis_tables_match_oracle_basis_planes():
+    """The 1-D tables handed to the CUDA library reproduce the oracle's 2-D basis planes (Create_BSplineBasis :2624-2634,
+    REF_ij / REF_pq order :2764-2772), B-spline partition of unity included."""
+    from sfft_b200.BSplineSFFT import _basis_tables
+    N0, N1 = 37, 52
+    for SpType, deg, KX, KY in (('B-Spline', 2, [12.0, 25.0], [30.0]), ('B-Spline', 3, [], [20.0, 21.5]), ('B-Spline', 0, [], []),
+                                ('Polynomial', 3, [], []), ('Polynomial', 5, [], [])):
+        U, V, fu, fv = _basis_tables(SpType, deg, KX, KY, N0, N1)
+        planes = np.array([np.outer(U[i], V[j]) for i, j in zip(fu, fv)])
+        ref = bo._basis_planes(SpType, deg, KX, KY, N0, N1)
+        assert planes.shape == ref.shape and np.array_equal(planes, ref)
+        if SpType == 'B-Spline':
+            assert np.max(np.abs(planes.sum(axis=0) - 1.0)) < 1e-14
+            assert len(fu) == U.shape[0] * V.shape[0]
+
+
+@pytest.mark.parametrize('mode', ['ENTANGLED', 'SEPARATE-CONSTANT', 'SEPARATE-VARYING'])
+def test_gram_factors_match_oracle_regmat_bspline(mode):
+    """_gram_factors (the Kronecker factors handed to sfftb_set_regularizer[_varying]) against the oracle's dense REGMAT for a
+    B-spline kernel and, in SEPARATE-VARYING, a B-spline scaling basis (fill_regmat :2091-2166)."""
+    from sfft_b200.BSplineSFFT import _gram_factors
+    rng = np.random.default_rng(8)
+    N0, N1, w = 40, 36, 1
+    XY = np.stack([rng.uniform(0.5, N0 + 0.5, 9), rng.uniform(0.5, N1 + 0.5, 9)], axis=1)
+    W = rng.uniform(0.5, 2.0, 9)
+    kw = dict(KerSpType='B-Spline', KerSpDegree=2, KerIntKnotX=[15.0], KerIntKnotY=[], BkgSpType='Polynomial', BkgSpDegree=1)
+    if mode == 'ENTANGLED':
+        kw.update(SEPARATE_SCALING=False)
+    elif mode == 'SEPARATE-CONSTANT':
+        kw.update(SEPARATE_SCALING=True, ScaSpDegree=0)
+    else:
+        kw.update(SEPARATE_SCALING=True, ScaSpType='B-Spline', ScaSpDegree=1, ScaIntKnotX=[], ScaIntKnotY=[18.0])
+    P = bo.ssc_params(N0, N1, w, REGULARIZE_KERNEL=True, XY_REGULARIZE=XY, WEIGHT_REGULARIZE=W, IGNORE_LAPLACIAN_KERCENT=True, **kw)
+    assert P['SCALING_MODE'] == mode
+    R = bo.regularizer(P)
+    fac = _gram_factors(P, N0, N1, w, w, XY, W, True)
+    SST, iREG = fac[0], fac[1]
+    Fab, Fij, c0 = P['Fab'], P['Fij'], w * P['L1'] + w
+    K = np.kron(SST, iREG)
+    if mode == 'SEPARATE-VARYING':
+        CSST, DSST = fac[2], fac[3]
+        cen = np.zeros(Fab, bool)
+        cen[c0] = True
+        one = np.ones((Fij, Fij))
+        K = np.where(np.kron(one, np.outer(~cen, cen)).astype(bool), np.kron(CSST, iREG), K)
+        K = np.where(np.kron(one, np.outer(cen, ~cen)).astype(bool), np.kron(CSST.T, iREG), K)
+        K = np.where(np.kron(one, np.outer(cen, cen)).astype(bool), np.kron(DSST, iREG), K)
+    full = np.zeros_like(R)
+    full[:P['Fijab'], :P['Fijab']] = P['SCALE'] ** 2 * K
+    assert np.max(np.abs(full - R)) <= 1e-13 * np.max(np.abs(R))
 
 
 @pytest.mark.parametrize('ignore', [True, False])
