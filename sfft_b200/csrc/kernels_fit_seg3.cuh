@@ -52,6 +52,27 @@ __device__ __forceinline__ void fs3_mbar_wait(unsigned long long* b, unsigned pa
 __device__ __forceinline__ void fs3_cp_async_arrive(unsigned long long* b) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(fs3_saddr(b)) : "memory");
 }
+// "slot consumed" hand-shake product warps -> transform warps.  NOT an mbarrier: a parity wait is only unambiguous within
+// one phase of the barrier, and with few spectra per segment (NP < 8) the consecutive jobs of a transform warp lie more
+// than two segments apart (it would have to skip phases).  Every product warp publishes the number of segments it has
+// consumed (monotonic, global segment counter); a transform warp may overwrite the slot of segment gs once all eight
+// counters have reached gs - 1.
+__device__ __forceinline__ void fs3_publish(unsigned* cons_w, unsigned v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(fs3_saddr(cons_w)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fs3_wait_consumed(const unsigned* cons, unsigned need) {
+    int spins = 0;
+    while (true) {
+        unsigned a0, a1, a2, a3, b0, b1, b2, b3;
+        asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(fs3_saddr(cons)) : "memory");
+        asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(fs3_saddr(cons + 4)) : "memory");
+        const unsigned m = min(min(min(a0, a1), min(a2, a3)), min(min(b0, b1), min(b2, b3)));
+        if (m >= need) break;
+        __nanosleep(FS3_SLEEP_NS);
+        if (++spins > (1 << 22)) __trap();
+    }
+    __threadfence_block();
+}
 __device__ __forceinline__ void fs3_bar0() { asm volatile("bar.sync 0;" ::: "memory"); }
 __device__ __forceinline__ void fs3_barP() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -164,9 +185,9 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
     cd* tw8 = macc + NMS * NMT;                     // 56 entries  (Ns = 8,  R = 8)
     cd* tw64 = tw8 + 56;                            // 192 entries (Ns = 64, R = 4)
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(tw64 + 192);
-    TSt* stage = reinterpret_cast<TSt*>(bars + 12);
+    unsigned* cons = reinterpret_cast<unsigned*>(bars + 12);      // [8] segments consumed by product warp w (fs3_publish)
+    TSt* stage = reinterpret_cast<TSt*>(bars + 16);
     unsigned long long* full = bars;          // [2]  count NP   (one arrive per transform job)
-    unsigned long long* empty = bars + 2;     // [2]  count 8    (one arrive per product warp)
     unsigned long long* landed = bars + 4;    // [NSTG] count 256  (cp.async arrivals of the product threads)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double inv0 = 1.0 / (double)a.N0;
@@ -174,9 +195,9 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
 
     if (tid == 0) {
         fs3_mbar_init(full + 0, NP); fs3_mbar_init(full + 1, NP);
-        fs3_mbar_init(empty + 0, 8); fs3_mbar_init(empty + 1, 8);
         for (int b = 0; b < NSTG; ++b) fs3_mbar_init(landed + b, 256);
     }
+    if (tid < 8) cons[tid] = 0u;
     // the engine's twiddle tables live in shared memory: with ~200 KB of shared memory carved out there is next to
     // no L1 left, and a table miss costs an L2 round trip in the middle of a transform
     for (int i = tid; i < 56; i += FS3_NT) tw8[i] = vt_g.t8_8[i];
@@ -283,7 +304,7 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
                 dMom += clock64() - q2;
 #endif
                 __syncwarp();
-                if (lane == 0) fs3_mbar_arrive(empty + slot);
+                if (lane == 0) fs3_publish(cons + warp, (unsigned)(gs + 1));
                 if (s + PFD < nseg) issue(s + PFD);
             }
 #ifdef FS3_DEBUG
@@ -317,7 +338,6 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
         // ====================================== transform warps ======================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
         const int fw = warp - 8;
-        unsigned seenE0 = 0, seenE1 = 0;               // completed phases of empty[0] / empty[1] this warp has observed
         for (int k1 = blockIdx.x; k1 < a.NH; k1 += gridDim.x, g += nseg) {
             cd* kaprow = kap + (size_t)k1 * fa.nrows;
 #ifdef FS3_DEBUG
@@ -338,17 +358,7 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_seg3_kernel(SegFitArgs fa, VTab
 #ifdef FS3_DEBUG
                 long long f1 = clock64(); fWaitL += f1 - f0;
 #endif
-                // slot free?  A parity wait is only unambiguous one phase away, and with few spectra per segment (NP < 8)
-                // a warp's consecutive jobs lie more than two segments apart: observe EVERY phase of the slot in order
-                {
-                    const unsigned need = (unsigned)gs >> 1;          // completions of empty[slot] before segment gs may be written
-                    unsigned seen = slot ? seenE1 : seenE0;
-                    while (seen < need) { fs3_mbar_wait(empty + slot, seen & 1); ++seen; }
-                    if (slot) seenE1 = seen; else seenE0 = seen;
-                }
-#ifdef FS3_DEBUG
-                long long f2 = clock64(); fWaitE += f2 - f1;
-#endif
+                if (gs >= 2) fs3_wait_consumed(cons, (unsigned)(gs - 1));      // segment gs - 2 (same slot) consumed by every product warp
                 const TSt* src = stage + ((size_t)(gs & (NSTG - 1)) * NSRC + my_src) * FS3_M;
                 cd* plane = spec + ((size_t)slot * NP + p) * FS3_PITCH;
                 cd v[8];

@@ -62,9 +62,9 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_gen_kernel(GenFitArgs fa, GenPa
     cd* tw8 = spec + NPL * FS3_PITCH;               // 56 entries  (Ns = 8,  R = 8)
     cd* tw64 = tw8 + 56;                            // 192 entries (Ns = 64, R = 4)
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(tw64 + 192);
-    TSt* stage = reinterpret_cast<TSt*>(bars + 12);
+    unsigned* cons = reinterpret_cast<unsigned*>(bars + 12);      // [8] segments consumed by product warp w (fs3_publish)
+    TSt* stage = reinterpret_cast<TSt*>(bars + 16);
     unsigned long long* full = bars;          // [2]  count NP   (one arrive per transform job)
-    unsigned long long* empty = bars + 2;     // [2]  count 8    (one arrive per product warp)
     unsigned long long* landed = bars + 4;    // [NSTG] count 256  (cp.async arrivals of the product threads)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int h = fa.h, S = fa.S, nseg = fa.nseg, N0 = fa.N0;
@@ -73,9 +73,9 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_gen_kernel(GenFitArgs fa, GenPa
 
     if (tid == 0) {
         fs3_mbar_init(full + 0, NP); fs3_mbar_init(full + 1, NP);
-        fs3_mbar_init(empty + 0, 8); fs3_mbar_init(empty + 1, 8);
         for (int b = 0; b < NSTG; ++b) fs3_mbar_init(landed + b, 256);
     }
+    if (tid < 8) cons[tid] = 0u;
     for (int i = tid; i < 56; i += FS3_NT) tw8[i] = vt_g.t8_8[i];
     for (int i = tid; i < 192; i += FS3_NT) tw64[i] = vt_g.t64_4[i];
     for (int i = tid; i < NPL * FS3_PITCH; i += FS3_NT) spec[i] = cmake(0.0, 0.0);   // unused slots must stay finite
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_gen_kernel(GenFitArgs fa, GenPa
                         }
                 }
                 __syncwarp();
-                if (lane == 0) fs3_mbar_arrive(empty + slot);
+                if (lane == 0) fs3_publish(cons + warp, (unsigned)(gs + 1));
                 if (s + PFD < nseg) issue(s + PFD);
             }
             fs3_bar0();                                    // (A) all transforms and products of the column are done
@@ -182,7 +182,6 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_gen_kernel(GenFitArgs fa, GenPa
         // ====================================== transform warps ======================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
         const int fw = warp - 8;
-        unsigned seenE0 = 0, seenE1 = 0;               // completed phases of empty[0] / empty[1] this warp has observed
         for (int k1 = blockIdx.x; k1 < fa.NH; k1 += gridDim.x, g += nseg) {
             cd* kaprow = kap + (size_t)k1 * fa.nrows;
             for (int id = fw; id < nseg * NP; id += 8) {
@@ -195,12 +194,7 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_gen_kernel(GenFitArgs fa, GenPa
                 const int my_src = roleA ? ps.a_src[p] : ps.b_src[bs];
                 const int c0 = s * S, Sc = min(S, N0 - c0);
                 fs3_mbar_wait(landed + (gs & (NSTG - 1)), (gs >> LOG2STG) & 1);
-                {
-                    const unsigned need = (unsigned)gs >> 1;
-                    unsigned seen = slot ? seenE1 : seenE0;
-                    while (seen < need) { fs3_mbar_wait(empty + slot, seen & 1); ++seen; }
-                    if (slot) seenE1 = seen; else seenE0 = seen;
-                }
+                if (gs >= 2) fs3_wait_consumed(cons, (unsigned)(gs - 1));
                 const TSt* src = stage + ((size_t)(gs & (NSTG - 1)) * GEN_MAXSRC + my_src) * FS3_M;
                 cd* plane = spec + ((size_t)slot * NPMAX + (roleA ? p : NA + bs)) * FS3_PITCH;
                 const double* urow = fa.U + (size_t)my_u * N0;
