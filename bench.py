@@ -40,7 +40,15 @@ WORKLOADS = {
     # BASELINE config 4: science tiles against ONE shared template; the template row spectra are computed on rank 0
     # and broadcast once (NCCL), a step is one tile through sfftb_gss_template
     'c4_template_2048_w8_dk2_db2_fp32': (2048, 2048, 8, 2, 2, 'fp32', 4),
+    # BASELINE config 3: B-spline spatially varying kernel through sfft_b200.BSplineSFFT (general-basis plan); see C3_SPEC
+    'c3_6144_bspline_fp32': (6144, 6144, 8, 2, 2, 'fp32', 3),
+    'c3dev_1536_bspline_fp32': (1536, 1536, 8, 2, 2, 'fp32', 3),
 }
+# B-spline recipe of config 3 (SURVEY.md 8d assumed Fij = 25, ScaFij = 6): quadratic B-spline kernel with two internal knots
+# per axis (Fi = Fj = 5), SEPARATE-VARYING photometric scaling as a quadratic polynomial, quadratic polynomial background
+def c3_spec(N0, N1):
+    return dict(KerSpType='B-Spline', KerSpDegree=2, KerIntKnotX=[N0 / 3.0, 2.0 * N0 / 3.0], KerIntKnotY=[N1 / 3.0, 2.0 * N1 / 3.0],
+                SEPARATE_SCALING=True, ScaSpType='Polynomial', ScaSpDegree=2, BkgSpType='Polynomial', BkgSpDegree=2)
 DEFAULT_WORKLOAD = 'c2_4096_w8_dk2_db2_fp32'
 HBM_FALLBACK_GBS = 6650.0     # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
@@ -111,6 +119,329 @@ class ClockSampler:
         return out
 
 
+def pin_to_gpu_numa_node(local):
+    """Bind this process to the CPUs of the NUMA node its GPU hangs off (sysfs; no numactl in the image), so that the
+    pinned host buffers, which are first touched by this process, are allocated on that node.  Returns the node or None."""
+    try:
+        out = subprocess.run(['nvidia-smi', '-i', str(local), '--query-gpu=pci.bus_id', '--format=csv,noheader'],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=20).stdout.strip()
+        bus = out.lower()
+        if bus.startswith('00000000:'):
+            bus = bus[4:]
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+            a, _, b = part.partition('-')
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
+def link_probe(torch, dist, dev, world, nbytes, reps=4):
+    """Bare pinned-host <-> device copies of one image-sized buffer in both directions at once, on all ranks at the same
+    time: the ceiling the end-to-end leg can reach on this box at this N (PCIe link per GPU, shared root complexes and
+    host memory when N > 1).  GB/s per GPU = the slowest rank's."""
+    try:
+        h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        d_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        d_out = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        res = {}
+        for mode in ('h2d', 'd2h', 'duplex'):
+            for timed in (False, True):
+                torch.cuda.synchronize(dev)
+                if world > 1:
+                    dist.barrier()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    if mode in ('h2d', 'duplex'):
+                        with torch.cuda.stream(s1):
+                            d_in.copy_(h_in, non_blocking=True)
+                    if mode in ('d2h', 'duplex'):
+                        with torch.cuda.stream(s2):
+                            h_out.copy_(d_out, non_blocking=True)
+                torch.cuda.synchronize(dev)
+                dt = time.perf_counter() - t0
+                if timed:
+                    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                    if world > 1:
+                        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    res[mode] = reps * nbytes / float(t[0]) / 1e9
+        return {'h2d_gbs_per_gpu': res['h2d'], 'd2h_gbs_per_gpu': res['d2h'],
+                'duplex_each_way_gbs_per_gpu': res['duplex'], 'aggregate_h2d_gbs': world * res['h2d'],
+                'buffer_bytes': nbytes, 'ranks': world,
+                'how': 'pinned cudaMemcpyAsync of one image-sized buffer, %d repeats, all ranks at once, slowest rank' % reps}
+    except Exception as e:                      # the probe must never take the bench line down
+        return None
+
+
+def run_config4(torch, dist, B, world, rank, local, dev, ntiles=64, side=2048, w=8, DK=2, DB=2, storage='fp32'):
+    """BASELINE config 4 inside the default run: 64 science tiles of 2048^2 against ONE shared template, sharded over the
+    ranks; rank 0 transforms the template once, its state goes to the other GPUs with ONE NCCL broadcast (timed after a
+    warm-up collective, so communicator set-up is excluded), every rank then runs its tiles device-resident through
+    TemplatePipeline (two tiles in flight).  Returns the sub-object of the JSON line (rank 0) or None."""
+    from sfft_b200.plan import Plan
+    from sfft_b200.batch import TemplateBatch, TemplatePipeline, shard_indices
+    from sfft_b200.synth import make_pair, CONFIG_SEEDS
+    tdt = torch.float32 if storage == 'fp32' else torch.float64
+    code = B.F32 if storage == 'fp32' else B.F64
+    d = make_pair(side, side, CONFIG_SEEDS[4])                       # the same template on every rank (only rank 0 uses it)
+    rng = np.random.default_rng(4000 + rank)
+    npdt = np.float32 if storage == 'fp32' else np.float64
+    dev_of = lambda a: torch.from_numpy(np.ascontiguousarray(a.astype(npdt))).to(dev)
+    REF, mREF = dev_of(d['REF']), dev_of(d['mREF'])
+    masked = d['mSCI'] != d['SCI']
+    tiles = []
+    for k in range(2):                                               # two distinct science tiles per rank, cycled
+        sci = d['SCI'] + rng.normal(0.0, 0.5, d['SCI'].shape)
+        msci = np.where(masked, 0.0, sci)
+        tiles.append((dev_of(sci), dev_of(msci)))
+    plan = Plan(side, side, w, w, DK, DB, True, device=local, storage=storage)
+    tb = TemplateBatch(plan, rank, world)
+    if world > 1:
+        warm = torch.zeros(1024, device=dev)
+        dist.broadcast(warm, src=0)                                  # communicator warm-up, not part of the number
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    if rank == 0:
+        plan.template_prepare(REF, mREF)
+    t_prep = time.perf_counter() - t0
+    torch.cuda.synchronize(dev)
+    t1 = time.perf_counter()
+    tb.ready = False
+    if world > 1:
+        state = plan.template_state_tensor()
+        dist.broadcast(state, src=0)
+        torch.cuda.synchronize(dev)
+        if rank != 0:
+            plan.template_mark_ready()
+    t_bcast = time.perf_counter() - t1
+    tp = TemplatePipeline(side, side, w, DK, DB, True, device=local, storage=storage, stream_ptr=None, first_plan=plan)
+    tp.set_template()
+    mine = list(shard_indices(ntiles, rank, world))
+    diffs = [torch.empty((side, side), dtype=tdt, device=dev) for _ in range(2)]
+    sols = [torch.empty(plan.NEQ, dtype=torch.float64, device=dev) for _ in range(2)]
+    busy = [False, False]
+
+    def run_tiles(idxs):
+        for n_, k in enumerate(idxs):
+            slot = n_ % 2
+            if busy[slot]:
+                tp.plans[slot].gss_finish()
+            J, mJ = tiles[k % 2]
+            tp.plans[slot].gss_template_submit_device(J.data_ptr(), mJ.data_ptr(), code, sols[slot].data_ptr(), diffs[slot].data_ptr(), code)
+            busy[slot] = True
+        for slot in range(2):
+            if busy[slot]:
+                tp.plans[slot].gss_finish()
+                busy[slot] = False
+    run_tiles(range(4))                                              # first (factorising) tile of each plan + warm-up
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t2 = time.perf_counter()
+    run_tiles(mine)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t2
+    t = torch.tensor([dt, t_bcast, t_prep], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    state_bytes = plan.template_state()[1]
+    tp.close()
+    plan.close()
+    if rank != 0:
+        return None
+    dt, t_bcast = float(t[0]), float(t[1])
+    return {'workload': 'c4: %d science tiles of %dx%d against one shared template, KerHW=%d DK=%d DB=%d, %s storage' % (ntiles, side, side, w, DK, DB, storage),
+            'value': ntiles * side * side / 1e6 / dt, 'unit': 'Mpix/s', 'n_gpus': world, 'tiles': ntiles,
+            'tiles_per_gpu': len(mine), 'ms_per_tile_per_gpu': dt * 1e3 / max(1, len(mine)), 'tiles_in_flight': 2,
+            'template_prepare_ms': float(t[2]) * 1e3, 'template_broadcast_ms': t_bcast * 1e3 if world > 1 else None,
+            'template_state_bytes': state_bytes,
+            'collective': 'one torch.distributed.broadcast (NCCL) of the template row spectra, timed after a warm-up collective' if world > 1 else None,
+            'timing': 'host clock around the rank\'s tiles after a device synchronise, max over ranks'}
+
+
+def c3_make(name, rank):
+    from sfft_b200.synth import make_pair, CONFIG_SEEDS
+    N0, N1, w, DK, DB, storage, sid = WORKLOADS[name]
+    d = make_pair(N0, N1, CONFIG_SEEDS[sid] + 1000 * rank)
+    return (N0, N1, w, storage), d
+
+
+def run_c3(args, world, rank, local, numa):
+    """BASELINE config 3: 6144^2 pair, B-spline spatially varying kernel through sfft_b200.BSplineSFFT (general-basis
+    plan).  Same JSON contract as the default workload; every rank owns a pair (weak scaling, no collective)."""
+    import torch
+    import torch.distributed as dist
+    from sfft_b200 import _lib as B
+    import sfft_b200.BSplineSFFT as bs
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    W, K = max(3, args.warmup), max(1, args.steps)
+    (N0, N1, w, storage), d = c3_make(args.workload, rank)
+    spec = c3_spec(N0, N1)
+    npdt = np.float32 if storage == 'fp32' else np.float64
+    tdt = torch.float32 if storage == 'fp32' else torch.float64
+    code = B.F32 if storage == 'fp32' else B.F64
+    esz = 4 if storage == 'fp32' else 8
+    host = {k: torch.from_numpy(np.ascontiguousarray(v.astype(npdt))).pin_memory() for k, v in d.items()}
+    devt = {k: v.to(dev) for k, v in host.items()}
+    cfg = bs.SingleSFFTConfigure.SSC(NX=N0, NY=N1, KerHW=w, VERBOSE_LEVEL=0, CUDA_DEVICE=local, STORAGE=storage, **spec)
+    P, plan = cfg[0], cfg[1]['plan']
+    stream = torch.cuda.current_stream(dev)
+    plan.bind_torch_stream(stream)
+    plan.set_timing(True)
+    diff_d = torch.empty((N0, N1), dtype=tdt, device=dev)
+    diff_h = torch.empty((N0, N1), dtype=tdt).pin_memory()
+    sol_d = torch.empty(plan.NEQ, dtype=torch.float64, device=dev)
+    sol_h = np.empty(plan.NEQ, np.float64)
+    L = B.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_device():
+        plan.gss_device(devt['REF'].data_ptr(), devt['SCI'].data_ptr(), devt['mREF'].data_ptr(), devt['mSCI'].data_ptr(),
+                        code, sol_d.data_ptr(), diff_d.data_ptr(), code)
+
+    def step_host():
+        B.check(L.sfftb_gss(plan._h, host['REF'].data_ptr(), host['SCI'].data_ptr(), host['mREF'].data_ptr(),
+                            host['mSCI'].data_ptr(), B.MEM_HOST, code, sol_h.ctypes.data, B.MEM_HOST,
+                            diff_h.data_ptr(), B.MEM_HOST, code))
+    for _ in range(W):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = plan.launch_count
+    stage = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(K):
+        step_device()
+        for k, v in plan.timings().items():
+            stage[k] = stage.get(k, 0.0) + v
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1) / K
+    launches = plan.launch_count - l0
+    stage = {k: v / K for k, v in stage.items()}
+    KE = args.e2e_steps or min(K, 5)
+    step_host()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e2.record(stream)
+    for _ in range(KE):
+        step_host()
+    e3.record(stream)
+    barrier()
+    ms_e2e = max((time.perf_counter() - t0) * 1e3 / KE, e2.elapsed_time(e3) / KE)
+    clocks = sampler.stop()
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank == 0:
+        mpix = N0 * N1 / 1e6
+        info = plan.gen_info()
+        NH = N1 // 2 + 1
+        csz = 2 * esz
+        peak, which = hbm_peak()
+        # dominant kernel: the block passes of fit_gen_kernel.  Per launch a pass must read the stored planes it stages once
+        # and write its lag rows; summed over the passes of one fit: staged planes total x NH x N0 complex + all lag rows
+        alg_bytes = info['staged_planes_total'] * NH * N0 * csz + info['lag_rows'] * NH * 16
+        t_kernel = stage.get('fit_cols', 0.0) / 1e3
+        achieved = alg_bytes / t_kernel / 1e9 if t_kernel > 0 else None
+        n_pl = P['Fij'] + P.get('ScaFij', 0) + 1
+        step_bytes = (4 * n_pl + 7) * N0 * N1 * esz                  # SURVEY.md 8d, SEPARATE-VARYING: n_pl = Fij + ScaFij + 1
+        out = {
+            'metric': 'Mpix/s per 6Kx6K B-spline SFFT subtraction (GSS: fit + apply)', 'value': world * mpix / (ms / 1e3), 'unit': 'Mpix/s',
+            'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': args.workload, 'image': [N0, N1], 'KerHW': w, 'storage': storage, 'arithmetic': 'fp64',
+                       'spec': {k: (v if not isinstance(v, list) else [float(x) for x in v]) for k, v in spec.items()},
+                       'Fij': P['Fij'], 'ScaFij': P.get('ScaFij'), 'Fpq': P['Fpq'], 'NEQ': P['NEQ'], 'NEQt': P['NEQt'],
+                       'SCALING_MODE': P['SCALING_MODE'], 'plan': info, 'pairs_per_step_per_gpu': 1,
+                       'l2_policy': 'working set per step (inputs 4x%.0f MB, %d stored planes of %.0f MB) exceeds the 126 MB L2' % (
+                           N0 * N1 * esz / 1e6, info['stored_planes'], NH * N0 * csz / 1e6)},
+            'stage_ms': stage,
+            'assembly_solve_ms': stage.get('fit_cols', 0) + stage.get('fit_reduce_fill', 0) + stage.get('fit_solve', 0),
+            'solver': plan.last_solver, 'clocks': clocks,
+            'e2e': {'value': world * mpix / (ms_e2e / 1e3), 'unit': 'Mpix/s', 'ms_per_step': ms_e2e, 'steps': KE,
+                    'mode': 'one blocking sfftb_gss call per step (host buffers)', 'h2d_bytes_per_step': 4 * N0 * N1 * esz,
+                    'd2h_bytes_per_step': N0 * N1 * esz + plan.NEQ * 8, 'host_numa_node': numa},
+            'gpu_launches': launches,
+            'roofline': {'bound': 'hbm', 'kernel': 'fit_gen_kernel', 'achieved': achieved, 'peak': peak, 'peak_source': which, 'unit': 'GB/s',
+                         'frac': (achieved / peak) if achieved else None, 'traffic': None,
+                         'algorithmic_bytes_per_launch': alg_bytes / max(1, info['passes']), 'launches_per_step_of_kernel': info['passes'],
+                         'kernel_ms': stage.get('fit_cols'), 'step_algorithmic_bytes': step_bytes,
+                         'step_frac': step_bytes / (ms / 1e3) / 1e9 / peak,
+                         'note': 'fp64-issue / shared-memory bound like the polynomial fit kernel (DESIGN.md section 4); %d passes of up to '
+                                 '5 x 5 pair accumulators, n = %d Cholesky' % (info['passes'], info['unknowns'])},
+            'cpu_baseline': None,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out['cpu_baseline'] = cpu_port_c3(args.workload, min(args.cpu_sample, 256))
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_port_c3(name, side):
+    """The B-spline oracle (design-matrix restatement, dense D: small crops only) on the host cores."""
+    from oracle import bspline_oracle as bo
+    (N0, N1, w, storage), d = c3_make(name, 0)
+    s = min(side, N0, N1)
+    w2 = min(w, 2)                               # dense D = s^2 x NEQ doubles: the kernel half width is reduced with the crop
+    crop = {k: np.ascontiguousarray(v[:s, :s]) for k, v in d.items()}
+    P = bo.ssc_params(s, s, w2, **c3_spec(s, s))
+    t0 = time.time()
+    bo.gss(crop['REF'], crop['SCI'], crop['mREF'], crop['mSCI'], P)
+    dt = time.time() - t0
+    return {'value': (s * s / 1e6) / dt, 'unit': 'Mpix/s', 'cores': os.cpu_count(), 'kind': 'port', 'seconds': dt,
+            'sample': '%dx%d crop, KerHW=%d (reduced from %d: the oracle builds the dense design matrix), same B-spline recipe; '
+                      'oracle/bspline_oracle.py, BLAS threads of the host' % (s, s, w2, w)}
+
+
+def run_reference_c3(args, ncores):
+    W, K = max(0, args.warmup), max(1, args.steps)
+    side = min(args.cpu_sample, 256)
+    first = cpu_port_c3(args.workload, side)
+    while first['seconds'] * (K + W) > 240.0 and side > 64:
+        side //= 2
+        first = cpu_port_c3(args.workload, side)
+    for _ in range(W):
+        cpu_port_c3(args.workload, side)
+    t0 = time.time()
+    for _ in range(K):
+        last = cpu_port_c3(args.workload, side)
+    dt = (time.time() - t0) / K
+    v = side * side / 1e6 / dt
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'Mpix/s per 6Kx6K B-spline SFFT subtraction (GSS: fit + apply)', 'value': v, 'unit': 'Mpix/s',
+        'n_gpus': args.gpus, 'steps': K, 'warmup': W, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'sample': last['sample'], 'same_config': False},
+        'cpu_baseline': {'value': v, 'unit': 'Mpix/s', 'cores': ncores, 'kind': 'port', 'sample': last['sample']},
+        'e2e': {'value': v, 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}))
+
+
 def make_workload(name, rank):
     from sfft_b200.synth import make_pair, CONFIG_SEEDS
     N0, N1, w, DK, DB, storage, sid = WORKLOADS[name]
@@ -143,8 +474,20 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    # the same host threads at every N: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which would
+    # throttle the BLAS / FFT pools of this leg only when it is launched under torchrun
+    ncores = os.cpu_count() or 1
+    os.environ['SFFT_ORACLE_WORKERS'] = str(ncores)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=ncores)
+    except Exception:
+        pass
     from oracle import sfft_oracle as orc
+    orc.WORKERS = ncores
     name = args.workload
+    if name.startswith('c3'):
+        return run_reference_c3(args, ncores)
     N0, N1, w, DK, DB, storage, sid = WORKLOADS[name]
     W, K = max(0, args.warmup), max(1, args.steps)
     (_, _, _, _, _, _), d = make_workload(name, 0)
@@ -169,14 +512,14 @@ def run_reference(args):
         step()
     dt = (time.time() - t0) / K
     v = (side * side / 1e6) / dt
-    sample = '%dx%d crop of the %s pair, KerHW=%d DK=%d DB=%d, fp64 NumPy port of the reference NumPy backend' % (
-        side, side, name, w, DK, DB)
+    sample = '%dx%d crop of the %s pair (full size %dx%d: same_config %s), KerHW=%d DK=%d DB=%d, fp64 NumPy port of the reference NumPy backend, %d host threads' % (
+        side, side, name, N0, N1, str(side == N0 and side == N1).lower(), w, DK, DB, ncores)
     print(json.dumps({
         'impl': 'reference', 'metric': 'Mpix/s per 4Kx4K SFFT subtraction (GSS: fit + apply)', 'value': v,
         'unit': 'Mpix/s', 'n_gpus': args.gpus, 'steps': K, 'warmup': W,
         'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-        'data': 'synthetic', 'config': {'workload': name, 'sample': sample},
-        'cpu_baseline': {'value': v, 'unit': 'Mpix/s', 'cores': orc.WORKERS, 'kind': 'port', 'sample': sample},
+        'data': 'synthetic', 'config': {'workload': name, 'sample': sample, 'crop': [side, side], 'image': [N0, N1], 'same_config': side == N0 and side == N1},
+        'cpu_baseline': {'value': v, 'unit': 'Mpix/s', 'cores': ncores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}))
 
@@ -188,7 +531,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument('--cpu-sample', type=int, default=1024, help='side of the crop timed by the CPU baseline')
+    ap.add_argument('--cpu-sample', type=int, default=2048, help='side of the crop timed by the CPU legs (halved until K + W steps fit the budget)')
+    ap.add_argument('--no-config4', action='store_true', help='skip the shared-template sub-benchmark of the default run')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-pipeline', action='store_true', help='e2e leg: blocking sfftb_gss calls only')
     ap.add_argument('--e2e-steps', type=int, default=0, help='steps of the host-buffer leg (0 = min(steps, 20))')
@@ -204,6 +548,9 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    numa = pin_to_gpu_numa_node(local)          # before any pinned allocation: first touch places the host buffers
+    if args.workload.startswith('c3'):
+        return run_c3(args, world, rank, local, numa)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
@@ -257,13 +604,43 @@ def main():
         d_state = {'k': 0, 'busy': [False, False]}
 
     def drain_device():
+        if ppipe is not None:
+            for d_ in range(2):
+                slot = (ppipe['k'] + d_) % 2
+                if ppipe['busy'][slot]:
+                    ppipe['plans'][slot].gss_finish()
+                    ppipe['busy'][slot] = False
         if dpipe is not None:
             for slot in range(2):
                 if d_state['busy'][slot]:
                     dpipe.plans[slot].gss_finish()
                     d_state['busy'][slot] = False
 
+    # device-resident pairs of the plain workloads: two plans share the compute stream and are driven alternately through
+    # sfftb_gss_submit_device / sfftb_gss_finish, so the launches of pair k + 1 are queued while pair k computes and the
+    # GPU never drains between pairs (the kernels themselves still run one pair after the other)
+    ppipe = None
+    if not shared and not args.no_pipeline:
+        plan2 = Plan(N0, N1, w, w, DK, DB, True, device=local, storage=storage)
+        plan2.bind_torch_stream(stream)
+        plan2.set_timing(True)
+        ppipe = {'plans': [plan, plan2], 'busy': [False, False], 'k': 0,
+                 'diff': [diff_d, torch.empty_like(diff_d)], 'sol': [sol_d, torch.empty_like(sol_d)]}
+
     def step_device():
+        if ppipe is not None:
+            slot = ppipe['k'] % 2
+            pl = ppipe['plans'][slot]
+            if ppipe['busy'][slot]:
+                pl.gss_finish()
+                for k_, v_ in pl.timings().items():
+                    stage[k_] = stage.get(k_, 0.0) + v_
+                stage['_n'] = stage.get('_n', 0) + 1
+            pl.gss_submit_device(devt['REF'].data_ptr(), devt['SCI'].data_ptr(), devt['mREF'].data_ptr(), devt['mSCI'].data_ptr(),
+                                 code, ppipe['sol'][slot].data_ptr(), ppipe['diff'][slot].data_ptr(), code)
+            ppipe['busy'][slot] = True
+            ppipe['k'] += 1
+            return
         if dpipe is not None:
             slot = d_state['k'] % 2
             if d_state['busy'][slot]:
@@ -294,13 +671,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(W, 4) if dpipe is not None else W):
+    stage = {}
+    for _ in range(max(W, 4) if (dpipe is not None or ppipe is not None) else W):
         step_device()
     drain_device()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    count_launches = lambda: plan.launch_count + (dpipe.plans[1].launch_count if dpipe is not None else 0)
+    count_launches = lambda: (plan.launch_count + (dpipe.plans[1].launch_count if dpipe is not None else 0) +
+                              (ppipe['plans'][1].launch_count if ppipe is not None else 0))
     l0 = count_launches()
     stage = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -308,14 +687,17 @@ def main():
     e0.record(stream)
     for _ in range(K):
         step_device()
-        for k, v in plan.timings().items():
-            stage[k] = stage.get(k, 0.0) + v
-    drain_device()                                     # every tile of the timed region has completed
+        if ppipe is None:
+            for k, v in plan.timings().items():
+                stage[k] = stage.get(k, 0.0) + v
+            stage['_n'] = stage.get('_n', 0) + 1
+    drain_device()                                     # every pair / tile of the timed region has completed
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1) / K
     launches = count_launches() - l0
-    stage = {k: v / K for k, v in stage.items()}
+    nst = max(1, stage.pop('_n', 1))
+    stage = {k: v / nst for k, v in stage.items()}
 
     # end-to-end leg: pinned host buffers in, host difference image out, through the public host-buffer API.
     # (a) one blocking sfftb_gss call per step (latency of a single pair);  (b) the same steps through PairPipeline
@@ -333,6 +715,7 @@ def main():
     barrier()
     ms_e2e_single = e2.elapsed_time(e3) / KE
     ms_e2e, e2e_mode = ms_e2e_single, 'one blocking sfftb_gss call per step'
+    ms_e2e_full, ms_e2e_delta, delta_bytes = None, None, 0
     if not shared and not args.no_pipeline:
         from sfft_b200.batch import PairPipeline
         pipe = PairPipeline(N0, N1, w, DK, DB, True, device=local, storage=storage, stream_ptr=stream.cuda_stream)
@@ -355,7 +738,33 @@ def main():
         wall_ms = (time.perf_counter() - t0) * 1e3 / KE
         # the copies run on the plans' copy streams, so the honest clock is the host's (submit of the first step ->
         # last result in host memory); the events on the compute stream are kept as a cross-check
-        ms_e2e, e2e_mode = max(wall_ms, e2.elapsed_time(e3) / KE), 'PairPipeline: sfftb_gss_submit/finish on two plans, copies of step k+1 under step k'
+        ms_e2e_full = max(wall_ms, e2.elapsed_time(e3) / KE)
+        ms_e2e, e2e_mode = ms_e2e_full, 'PairPipeline: sfftb_gss_submit/finish on two plans, copies of step k+1 under step k'
+        # the same steps with the masked pair sent as sparse deltas against the unmasked pair (sfftb_gss_submit_delta): the
+        # masked images differ from the unmasked ones only inside the masked stamps, so two images instead of four cross
+        # the link; the deltas are part of the step's input and are copied inside the timed region like the images
+        from sfft_b200.batch import sparse_delta
+        dI = sparse_delta(host['REF'].numpy(), host['mREF'].numpy())
+        dJ = sparse_delta(host['SCI'].numpy(), host['mSCI'].numpy())
+        dI = tuple(torch.from_numpy(a).pin_memory().numpy() for a in dI)
+        dJ = tuple(torch.from_numpy(a).pin_memory().numpy() for a in dJ)
+        delta_bytes = sum(a.nbytes for a in dI + dJ)
+
+        def step_delta(k):
+            pipe.submit_delta(host['REF'], host['SCI'], dI, dJ, Solution_out=sol_hs[k % 2], DIFF_out=diff_hs[k % 2])
+        for k in range(3):
+            step_delta(k)
+        pipe.drain()
+        barrier()
+        t0 = time.perf_counter()
+        e2.record(stream)
+        for k in range(KE):
+            step_delta(k)
+        pipe.drain()
+        e3.record(stream)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3 / KE
+        ms_e2e_delta = max(wall_ms, e2.elapsed_time(e3) / KE)
         pipe.close()
     if shared and not args.no_pipeline:
         from sfft_b200.batch import TemplatePipeline
@@ -381,17 +790,23 @@ def main():
         tp.close()
         dpipe = None
     clocks = sampler.stop()
+    esz = 4 if storage == 'fp32' else 8
+    probe = link_probe(torch, dist, dev, world, N0 * N1 * esz)
+    c4 = None
+    if args.workload == DEFAULT_WORKLOAD and not args.no_config4:
+        c4 = run_config4(torch, dist, B, world, rank, local, dev)
 
-    t = torch.tensor([ms, ms_e2e, ms_e2e_single], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms_e2e, ms_e2e_single, ms_e2e_delta or 0.0, ms_e2e_full or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e, ms_e2e_single = float(t[0]), float(t[1]), float(t[2])
+    ms_e2e_delta = float(t[3]) if ms_e2e_delta else None
+    ms_e2e_full = float(t[4]) if ms_e2e_full else None
     mpix = N0 * N1 / 1e6
     value = world * mpix / (ms / 1e3)
     e2e_value = world * mpix / (ms_e2e / 1e3)
 
     if rank == 0:
-        esz = 4 if storage == 'fp32' else 8
         csz = 2 * esz
         NH = N1 // 2 + 1
         Fij = (DK + 1) * (DK + 2) // 2
@@ -403,13 +818,35 @@ def main():
         nrowsK = npairs * (4 * w + 1) + Fij * (2 * w + 1)
         seg_path = 4 * w + 32 <= 256      # fit_seg3_kernel (one launch for DK <= 2, three plane-range launches for DK = 3)
         nrowsL = (Fij * Fpq * (2 * w + 1) + Fpq) if seg_path else (Fij * (DB + 1) * (2 * w + 1) + (DB + 1))
-        kname = 'fit_seg3_kernel' if seg_path else 'fit_col_fast_kernel'
+        kname = 'fit_seg3_kernel' if seg_path else 'fit_col_kernel'
         npass = 3 if (seg_path and DK == 3) else 1          # every plane-range launch streams the stored planes once
         alg_bytes = npass * (DK + 2) * NH * N0 * csz + (nrowsK + nrowsL) * NH * 16
         t_kernel = stage.get('fit_cols', 0.0) / 1e3
         achieved = alg_bytes / t_kernel / 1e9 if t_kernel > 0 else None      # = bytes per launch / average launch time
         # whole-step algorithmic bytes: (4 n_pl + 7) * N0 * N1 * s with n_pl = Fij + 1
         step_bytes = (4 * (Fij + 1) + 7) * N0 * N1 * esz
+        # end to end: the four-image form is the headline (the reference's call shape); the sparse-delta form of the same
+        # step and the link ceiling measured in this run explain it
+        h2d_full = (2 if shared else 4) * N0 * N1 * esz
+        d2h = N0 * N1 * esz + plan.NEQ * 8
+        e2e_obj = {'value': e2e_value, 'unit': 'Mpix/s', 'ms_per_step': ms_e2e, 'steps': KE, 'mode': e2e_mode,
+                   'single_call_ms': ms_e2e_single, 'single_call_value': world * mpix / (ms_e2e_single / 1e3),
+                   'h2d_bytes_per_step': h2d_full, 'd2h_bytes_per_step': d2h, 'host_numa_node': numa}
+        if probe:
+            bound_ms = max(h2d_full / (probe['h2d_gbs_per_gpu'] * 1e6), d2h / (probe['d2h_gbs_per_gpu'] * 1e6))
+            e2e_obj['link_probe'] = probe
+            e2e_obj['link_bound_ms_per_step'] = bound_ms
+            e2e_obj['frac_of_link_bound'] = bound_ms / ms_e2e
+        if ms_e2e_delta:
+            h2d_delta = 2 * N0 * N1 * esz + delta_bytes
+            e2e_obj['sparse_mask_form'] = {
+                'value': world * mpix / (ms_e2e_delta / 1e3), 'unit': 'Mpix/s', 'ms_per_step': ms_e2e_delta,
+                'mode': 'PairPipeline.submit_delta: sfftb_gss_submit_delta (I, J + sparse deltas of mI, mJ)',
+                'h2d_bytes_per_step': h2d_delta, 'd2h_bytes_per_step': d2h}
+            if probe:
+                b2 = max(h2d_delta / (probe['h2d_gbs_per_gpu'] * 1e6), d2h / (probe['d2h_gbs_per_gpu'] * 1e6))
+                e2e_obj['sparse_mask_form']['link_bound_ms_per_step'] = b2
+                e2e_obj['sparse_mask_form']['frac_of_link_bound'] = b2 / ms_e2e_delta
         out = {
             'metric': 'Mpix/s per 4Kx4K SFFT subtraction (GSS: fit + apply)', 'value': value, 'unit': 'Mpix/s',
             'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
@@ -420,15 +857,14 @@ def main():
                            N0 * N1 * esz / 1e6, (DK + 2) * NH * N0 * csz / 1e6),
                        'fold': plan.dims['fold'], 'sub_len': plan.dims['sub_len'],
                        'shared_template': shared, 'template_prepare_broadcast_ms': bcast_ms,
-                       'tiles_in_flight': 2 if (shared and not args.no_pipeline) else 1},
+                       'tiles_in_flight': 2 if (shared and not args.no_pipeline) else 1,
+                       'device_leg': ('two plans on one stream, sfftb_gss_submit_device / sfftb_gss_finish alternately (no host '
+                                      'synchronisation between pairs)') if ppipe is not None else 'one blocking call per step'},
             'stage_ms': stage,
             'assembly_solve_ms': stage.get('fit_cols', 0) + stage.get('fit_reduce_fill', 0) + stage.get('fit_solve', 0),
             'solver': plan.last_solver,
             'clocks': clocks,
-            'e2e': {'value': e2e_value, 'unit': 'Mpix/s', 'ms_per_step': ms_e2e, 'steps': KE, 'mode': e2e_mode,
-                    'single_call_ms': ms_e2e_single, 'single_call_value': world * mpix / (ms_e2e_single / 1e3),
-                    'h2d_bytes_per_step': (2 if shared else 4) * N0 * N1 * esz,
-                    'd2h_bytes_per_step': N0 * N1 * esz + plan.NEQ * 8},
+            'e2e': e2e_obj,
             'gpu_launches': launches,
             'roofline': {'bound': 'hbm', 'kernel': kname, 'achieved': achieved, 'peak': peak,
                          'note': 'the path is fp64-issue bound on B200 (64 DFMA/clk/SM, DESIGN.md section 4); the HBM '
@@ -439,6 +875,8 @@ def main():
                          'step_algorithmic_bytes': step_bytes,
                          'step_frac': step_bytes / (ms / 1e3) / 1e9 / peak},
         }
+        if c4 is not None:
+            out['config4'] = c4
         tr = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(tr):
             try:
@@ -453,7 +891,7 @@ def main():
             v, dt, s, cores = cpu_port_mpix(args.workload, args.cpu_sample)
             out['cpu_baseline'] = {'value': v, 'unit': 'Mpix/s', 'cores': cores, 'kind': 'port', 'seconds': dt,
                                    'sample': '%dx%d crop of the same pair, same KerHW/orders, fp64 NumPy port of the '
-                                             'reference NumPy backend (oracle/sfft_oracle.py)' % (s, s)}
+                                             'reference NumPy backend (oracle/sfft_oracle.py), one GSS' % (s, s)}
         else:
             out['cpu_baseline'] = None
         print(json.dumps(out))

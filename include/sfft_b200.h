@@ -111,6 +111,19 @@ int  sfftb_gss(sfftb_plan* plan, const void* PixA_I, const void* PixA_J, const v
  * from host memory (sfft/MultiEasySparsePacket.py:568-649 feeds one GPU from a host-side task queue) should be fed. */
 int  sfftb_gss_submit(sfftb_plan* plan, const void* PixA_I, const void* PixA_J, const void* PixA_mI, const void* PixA_mJ,
                       int img_dtype, double* solution, void* diff, int diff_dtype);
+/* sfftb_gss_submit for a pair whose four images (and both outputs) already live on the DEVICE: nothing is copied, the fit
+ * and the apply are queued on the plan's stream without any host synchronisation (the forward row pass of the apply step
+ * overlaps the Cholesky like in sfftb_gss), sfftb_gss_finish waits and reports.  A queue of device-resident pairs driven
+ * through two plans alternately never drains the GPU between pairs. */
+int  sfftb_gss_submit_device(sfftb_plan* plan, const void* PixA_I, const void* PixA_J, const void* PixA_mI, const void* PixA_mJ,
+                             int img_dtype, double* solution, void* diff, int diff_dtype);
+/* sfftb_gss_submit with the masked pair given as SPARSE DELTAS against the unmasked pair: mI = I except mI[idxI[k]] = valI[k]
+ * (flat C-order pixel indices; values of the image dtype), likewise mJ.  The packets build their masked images exactly
+ * that way -- stamps of the same arrays set to zero or to a fill value (sfft/CustomizedPacket.py:114-162,
+ * sfft/EasySparsePacket.py) -- so two images instead of four cross the PCIe link per pair.  HOST pointers. */
+int  sfftb_gss_submit_delta(sfftb_plan* plan, const void* PixA_I, const void* PixA_J, long long nI, const long long* idxI, const void* valI,
+                            long long nJ, const long long* idxJ, const void* valJ, int img_dtype, double* solution, void* diff,
+                            int diff_dtype);
 /* The same for one science tile against the cached template; completes inside the call until the plan holds the
  * template's Cholesky factor (first tile).  `memkind` covers the images and both outputs: host buffers are copied on
  * the plan's copy stream, device buffers are used in place (tiles queued back to back leave no launch gaps). */
@@ -210,6 +223,11 @@ int  sfftb_timings(sfftb_plan* plan, float* ms, int n);
 /* Which factorisation the last fit used: 1 = Cholesky, 2 = pivoted LU fallback, 3 = substitutions with the cached
  * Cholesky factor (template path: LHMAT depends on the masked template only, so tiles after the first reuse it). */
 int  sfftb_last_solver(const sfftb_plan* plan);
+
+/* General-basis plans: out8 = { passes of the fit column kernel, stored planes staged summed over the passes, lag rows per
+ * column, stored planes, column planes, unknowns of the solved system, apply planes, stored planes read by the FIR }
+ * (bench.py's algorithmic-byte count). */
+int  sfftb_gen_info(const sfftb_plan* plan, int* out8);
 
 /* Number of kernel launches issued by this plan since creation (bench.py's gpu_launches). */
 long long sfftb_launch_count(const sfftb_plan* plan);

@@ -79,6 +79,15 @@ class TemplateBatch:
         return out
 
 
+def sparse_delta(unmasked, masked):
+    """(idx, val): flat C-order indices where `masked` differs from `unmasked` and the masked values there -- the form
+    sfftb_gss_submit_delta takes.  NaN == NaN counts as equal."""
+    u, m = np.asarray(unmasked), np.asarray(masked)
+    diff = ~((m == u) | (np.isnan(m) & np.isnan(u)))
+    idx = np.flatnonzero(diff.ravel()).astype(np.int64)
+    return idx, np.ascontiguousarray(m.ravel()[idx])
+
+
 class PairPipeline:
     """A queue of independent image pairs in host memory through ONE GPU (what a worker thread of
     sfft/MultiEasySparsePacket.py:568-649 does pair after pair): two plans share one compute stream and are driven
@@ -111,6 +120,26 @@ class PairPipeline:
         self._busy[slot] = True
         self._k += 1
         return done
+
+    def submit_delta(self, PixA_I, PixA_J, delta_I, delta_J, out_dtype=np.float64, Solution_out=None, DIFF_out=None):
+        """submit() with the masked pair as sparse deltas (see sparse_delta): half the host-to-device bytes."""
+        slot = self._k % len(self.plans)
+        done = None
+        if self._busy[slot]:
+            done = self.plans[slot].gss_finish()
+        self.plans[slot].gss_submit_delta(PixA_I, PixA_J, delta_I, delta_J, out_dtype, Solution_out, DIFF_out)
+        self._busy[slot] = True
+        self._k += 1
+        return done
+
+    def submit_device(self, pI, pJ, pmI, pmJ, img_dtype, psol, pdiff, diff_dtype):
+        """Device-resident pair (raw device pointers): queued without a host synchronisation."""
+        slot = self._k % len(self.plans)
+        if self._busy[slot]:
+            self.plans[slot].gss_finish()
+        self.plans[slot].gss_submit_device(pI, pJ, pmI, pmJ, img_dtype, psol, pdiff, diff_dtype)
+        self._busy[slot] = True
+        self._k += 1
 
     def drain(self):
         """Finish everything in flight, oldest first."""

@@ -86,6 +86,8 @@ struct sfftb_plan {
     void* pend_diff; double* pend_sol; int pend_dtype, pend_diff_dtype;
     int pend_mode;               // 1 = pair (sfftb_gss_submit), 2 = shared-template tile, 3 = already completed synchronously
     const void *pend_J, *pend_mJ; int pend_memkind;
+    const void* pend_I; int pend_mem;            // pair submissions: memory kind of the images (device pairs are re-applied in place)
+    long long* deltaIdx; void* deltaVal; size_t delta_cap;   // sfftb_gss_submit_delta: staged sparse deltas of the masked pair
     cudaEvent_t pendI, pendJ;    // events the next row pass of I / J has to wait for (host pipeline), or NULL
     cd *kap, *lam, *nuJ;
     double *R, *RJ, *RT, *RJT;
@@ -210,6 +212,7 @@ int launch_lag_reduce2(sfftb_plan* p, const LagReduce2Args& a, const cd* kap, do
 int gen_plan_create(sfftb_plan* p, const sfftb_config* cfg, const sfftb_basis* ker, const sfftb_basis* sca, const sfftb_basis* bkg, int mode);
 void gen_free(sfftb_plan* p);
 int gen_nvs(const sfftb_plan* p);
+void gen_info(const sfftb_plan* p, int* out);
 void* gen_planes(const sfftb_plan* p);
 int gen_set_regularizer(sfftb_plan* p);
 int gen_rjt(sfftb_plan* p, const void* dJ, int dtype);

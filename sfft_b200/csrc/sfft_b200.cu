@@ -175,7 +175,7 @@ static int plan_free(sfftb_plan* p) {
     cudaSetDevice(p->device);
     gen_free(p);
     void* ptrs[] = {p->vt8_8, p->vt64_8, p->vt64_4, p->vt256_4, p->vt512_4, p->tabA, p->tabB_row, p->tabC_row, p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
-                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->substMsg, p->solEff, p->regC, p->regD, p->regSST, p->regI, p->bluTw, p->bluC, p->bluB, p->firTaps, p->firCA, p->tstate, p->stC, p->stD};
+                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->substMsg, p->solEff, p->regC, p->regD, p->regSST, p->regI, p->bluTw, p->bluC, p->bluB, p->firTaps, p->firCA, p->tstate, p->stC, p->stD, p->deltaIdx, p->deltaVal};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->info_h) cudaFreeHost(p->info_h);
     for (int k = 0; k < EV_COUNT; ++k) if (p->ev[k]) cudaEventDestroy(p->ev[k]);
@@ -537,6 +537,12 @@ extern "C" int sfftb_plan_set_timing(sfftb_plan* p, int enable) {
     return 0;
 }
 
+extern "C" int sfftb_gen_info(const sfftb_plan* p, int* out8) {
+    if (!p || !out8) return fail(SFFTB_EINVAL, "null argument");
+    if (!p->gen) return fail(SFFTB_EINVAL, "not a general-basis plan");
+    gen_info(p, out8);
+    return 0;
+}
 extern "C" long long sfftb_launch_count(const sfftb_plan* p) { return p ? p->launches : 0; }
 extern "C" int sfftb_last_solver(const sfftb_plan* p) { return p ? p->last_solver : 0; }
 
@@ -873,27 +879,102 @@ extern "C" int sfftb_gss(sfftb_plan* p, const void* I, const void* J, const void
 // difference image and returns; finish waits for THIS plan's work only.  Two plans that share one compute stream
 // (sfftb_plan_set_stream) and are driven alternately overlap the H2D copies of pair k + 1 with the kernels and the D2H
 // of pair k (PCIe is full duplex), which is what bounds a stream of pairs coming from host memory.
-extern "C" int sfftb_gss_submit(sfftb_plan* p, const void* I, const void* J, const void* mI, const void* mJ, int dtype,
-                                double* solution, void* diff, int diff_dtype) {
-    if (!p || !I || !J || !mI || !mJ || !diff) return fail(SFFTB_EINVAL, "null argument");
+// mI = I, mI[idx[k]] = val[k]: the masked images of the packets differ from the unmasked ones only inside the masked
+// stamps (sfft/CustomizedPacket.py:114-162 fills / zeroes regions of the same arrays), so a host caller can send them as
+// sparse deltas and halve the host-to-device traffic of a pair.
+template <typename T>
+__global__ void delta_scatter_kernel(T* __restrict__ img, const long long* __restrict__ idx, const T* __restrict__ val, long long n, long long npix) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const long long i = idx[k];
+    if (i >= 0 && i < npix) img[i] = val[k];
+}
+
+struct DeltaSpec { long long nI, nJ; const long long *idxI, *idxJ; const void *valI, *valJ; };
+
+// shared body of the asynchronous pair submissions.
+//   memkind HOST  : the H2D copies run on the plan's copy stream; with `dl` the masked pair is rebuilt on the device
+//                   from I, J and the sparse deltas (two image copies instead of four);
+//   memkind DEVICE: the four images (and the outputs) are device buffers used in place; the forward row pass of the
+//                   apply step overlaps the Cholesky like in sfftb_gss.
+static int gss_submit_impl(sfftb_plan* p, const void* I, const void* J, const void* mI, const void* mJ, const DeltaSpec* dl, int memkind,
+                           int dtype, double* solution, void* diff, int diff_dtype) {
     if ((dtype != SFFTB_F64 && dtype != SFFTB_F32) || (diff_dtype != SFFTB_F64 && diff_dtype != SFFTB_F32)) return fail(SFFTB_EINVAL, "bad dtype");
-    if (p->gen) return fail(SFFTB_EINVAL, "sfftb_gss_submit is not available for general-basis plans");
+    if (p->gen) return fail(SFFTB_EINVAL, "the asynchronous pair submission is not available for general-basis plans");
     if (p->pending) return fail(SFFTB_ESTATE, "sfftb_gss_submit: the previous submission of this plan has not been finished");
     CK(cudaSetDevice(p->device));
     const bool f32 = p->cfg.storage == SFFTB_STORE_F32;
-    const size_t bytes = (size_t)p->d.N0 * p->d.N1 * (dtype == SFFTB_F64 ? 8 : 4);
-    if (!p->stC) { CK(cudaMalloc(&p->stC, sizeof(double) * (size_t)p->d.N0 * p->d.N1)); CK(cudaMalloc(&p->stD, sizeof(double) * (size_t)p->d.N0 * p->d.N1)); }
+    const size_t npix = (size_t)p->d.N0 * p->d.N1, esz = dtype == SFFTB_F64 ? 8 : 4;
+    const size_t bytes = npix * esz;
+    int rc;
+    p->pend_mem = memkind;
+    if (memkind == SFFTB_MEM_DEVICE) {
+        const bool ov = p->overlap && p->row_v8 && p->chol_coop && p->nsm >= 8;
+        p->pendI = nullptr; p->pendJ = nullptr;
+        rc = f32 ? fit_device<float2>(p, mI, mJ, dtype, nullptr, ov ? I : nullptr, ov ? J : nullptr)
+                 : fit_device<double2>(p, mI, mJ, dtype, nullptr, ov ? I : nullptr, ov ? J : nullptr);
+        if (rc) return rc;
+        rc = f32 ? apply_device<float2>(p, I, J, dtype, p->sol, diff, diff_dtype, nullptr, ov)
+                 : apply_device<double2>(p, I, J, dtype, p->sol, diff, diff_dtype, nullptr, ov);
+        if (rc) return rc;
+        if (solution) CK(cudaMemcpyAsync(solution, p->sol, sizeof(double) * p->d.NEQ, cudaMemcpyDeviceToDevice, p->stream));
+        CK(cudaEventRecord(p->evDone, p->stream));
+        p->pending = 1; p->pend_diff = diff; p->pend_sol = solution; p->pend_dtype = dtype; p->pend_diff_dtype = diff_dtype;
+        p->pend_mode = 1; p->pend_I = I; p->pend_J = J;
+        return 0;
+    }
+    if (!p->stC) { CK(cudaMalloc(&p->stC, sizeof(double) * npix)); CK(cudaMalloc(&p->stD, sizeof(double) * npix)); }
     // no wait on the compute stream here: the staging buffers are free (the previous submission was finished), and the
     // copies must not queue behind another plan's kernels on a shared compute stream
-    const void* srcs[4] = {mI, mJ, I, J};
-    void* dsts[4] = {p->stA, p->stB, p->stC, p->stD};
-    for (int k = 0; k < 4; ++k) {
-        CK(cudaMemcpyAsync(dsts[k], srcs[k], bytes, cudaMemcpyHostToDevice, p->stream2));
-        CK(cudaEventRecord(p->evCopy[k], p->stream2));
+    if (!dl) {
+        const void* srcs[4] = {mI, mJ, I, J};
+        void* dsts[4] = {p->stA, p->stB, p->stC, p->stD};
+        for (int k = 0; k < 4; ++k) {
+            CK(cudaMemcpyAsync(dsts[k], srcs[k], bytes, cudaMemcpyHostToDevice, p->stream2));
+            CK(cudaEventRecord(p->evCopy[k], p->stream2));
+        }
+    } else {
+        const long long nd = dl->nI + dl->nJ;
+        if ((size_t)nd > p->delta_cap) {
+            if (p->deltaIdx) { CK(cudaFree(p->deltaIdx)); CK(cudaFree(p->deltaVal)); p->deltaIdx = nullptr; p->deltaVal = nullptr; }
+            p->delta_cap = (size_t)nd + (size_t)nd / 4 + 1024;
+            CK(cudaMalloc(&p->deltaIdx, sizeof(long long) * p->delta_cap));
+            CK(cudaMalloc(&p->deltaVal, sizeof(double) * p->delta_cap));
+        }
+        char* dval = (char*)p->deltaVal;
+        // unmasked pair first (it is also the base of the masked pair), then the deltas
+        CK(cudaMemcpyAsync(p->stC, I, bytes, cudaMemcpyHostToDevice, p->stream2));
+        if (dl->nI) {
+            CK(cudaMemcpyAsync(p->deltaIdx, dl->idxI, sizeof(long long) * dl->nI, cudaMemcpyHostToDevice, p->stream2));
+            CK(cudaMemcpyAsync(dval, dl->valI, esz * dl->nI, cudaMemcpyHostToDevice, p->stream2));
+        }
+        CK(cudaMemcpyAsync(p->stA, p->stC, bytes, cudaMemcpyDeviceToDevice, p->stream2));
+        if (dl->nI) {
+            const unsigned grid = (unsigned)((dl->nI + 255) / 256);
+            if (dtype == SFFTB_F64) delta_scatter_kernel<double><<<grid, 256, 0, p->stream2>>>((double*)p->stA, p->deltaIdx, (const double*)dval, dl->nI, (long long)npix);
+            else delta_scatter_kernel<float><<<grid, 256, 0, p->stream2>>>((float*)p->stA, p->deltaIdx, (const float*)dval, dl->nI, (long long)npix);
+            CKL(p);
+        }
+        CK(cudaEventRecord(p->evCopy[0], p->stream2));
+        CK(cudaMemcpyAsync(p->stD, J, bytes, cudaMemcpyHostToDevice, p->stream2));
+        if (dl->nJ) {
+            CK(cudaMemcpyAsync(p->deltaIdx + dl->nI, dl->idxJ, sizeof(long long) * dl->nJ, cudaMemcpyHostToDevice, p->stream2));
+            CK(cudaMemcpyAsync(dval + esz * dl->nI, dl->valJ, esz * dl->nJ, cudaMemcpyHostToDevice, p->stream2));
+        }
+        CK(cudaMemcpyAsync(p->stB, p->stD, bytes, cudaMemcpyDeviceToDevice, p->stream2));
+        if (dl->nJ) {
+            const unsigned grid = (unsigned)((dl->nJ + 255) / 256);
+            if (dtype == SFFTB_F64) delta_scatter_kernel<double><<<grid, 256, 0, p->stream2>>>((double*)p->stB, p->deltaIdx + dl->nI, (const double*)(dval + esz * dl->nI), dl->nJ, (long long)npix);
+            else delta_scatter_kernel<float><<<grid, 256, 0, p->stream2>>>((float*)p->stB, p->deltaIdx + dl->nI, (const float*)(dval + esz * dl->nI), dl->nJ, (long long)npix);
+            CKL(p);
+        }
+        CK(cudaEventRecord(p->evCopy[1], p->stream2));
+        CK(cudaEventRecord(p->evCopy[2], p->stream2));
+        CK(cudaEventRecord(p->evCopy[3], p->stream2));
     }
     // evCopy[2..3] are re-recorded by the chunked D2H of the apply step, so the apply pair gets its own wait now
     p->pendI = p->evCopy[0]; p->pendJ = p->evCopy[1];
-    int rc = f32 ? fit_device<float2>(p, p->stA, p->stB, dtype) : fit_device<double2>(p, p->stA, p->stB, dtype);
+    rc = f32 ? fit_device<float2>(p, p->stA, p->stB, dtype) : fit_device<double2>(p, p->stA, p->stB, dtype);
     if (rc) return rc;
     p->pendI = p->evCopy[2]; p->pendJ = p->evCopy[3];
     void* hd = p->row_fast ? diff : nullptr;
@@ -901,7 +982,7 @@ extern "C" int sfftb_gss_submit(sfftb_plan* p, const void* I, const void* J, con
              : apply_device<double2>(p, p->stC, p->stD, dtype, p->sol, p->stA, diff_dtype, nullptr, false, hd);
     if (rc) return rc;
     if (!p->row_fast) {
-        const size_t ob = (size_t)p->d.N0 * p->d.N1 * (diff_dtype == SFFTB_F64 ? 8 : 4);
+        const size_t ob = npix * (diff_dtype == SFFTB_F64 ? 8 : 4);
         CK(cudaMemcpyAsync(diff, p->stA, ob, cudaMemcpyDeviceToHost, p->stream));
     }
     if (solution) CK(cudaMemcpyAsync(solution, p->sol, sizeof(double) * p->d.NEQ, cudaMemcpyDeviceToHost, p->stream));
@@ -909,6 +990,27 @@ extern "C" int sfftb_gss_submit(sfftb_plan* p, const void* I, const void* J, con
     p->pending = 1; p->pend_diff = diff; p->pend_sol = solution; p->pend_dtype = dtype; p->pend_diff_dtype = diff_dtype;
     p->pend_mode = 1;
     return 0;
+}
+
+extern "C" int sfftb_gss_submit(sfftb_plan* p, const void* I, const void* J, const void* mI, const void* mJ, int dtype,
+                                double* solution, void* diff, int diff_dtype) {
+    if (!p || !I || !J || !mI || !mJ || !diff) return fail(SFFTB_EINVAL, "null argument");
+    return gss_submit_impl(p, I, J, mI, mJ, nullptr, SFFTB_MEM_HOST, dtype, solution, diff, diff_dtype);
+}
+
+extern "C" int sfftb_gss_submit_device(sfftb_plan* p, const void* I, const void* J, const void* mI, const void* mJ, int dtype,
+                                       double* solution, void* diff, int diff_dtype) {
+    if (!p || !I || !J || !mI || !mJ || !diff) return fail(SFFTB_EINVAL, "null argument");
+    return gss_submit_impl(p, I, J, mI, mJ, nullptr, SFFTB_MEM_DEVICE, dtype, solution, diff, diff_dtype);
+}
+
+extern "C" int sfftb_gss_submit_delta(sfftb_plan* p, const void* I, const void* J, long long nI, const long long* idxI, const void* valI,
+                                      long long nJ, const long long* idxJ, const void* valJ, int dtype, double* solution, void* diff,
+                                      int diff_dtype) {
+    if (!p || !I || !J || !diff) return fail(SFFTB_EINVAL, "null argument");
+    if (nI < 0 || nJ < 0 || (nI && (!idxI || !valI)) || (nJ && (!idxJ || !valJ))) return fail(SFFTB_EINVAL, "bad delta arguments");
+    DeltaSpec dl = {nI, nJ, idxI, idxJ, valI, valJ};
+    return gss_submit_impl(p, I, J, nullptr, nullptr, &dl, SFFTB_MEM_HOST, dtype, solution, diff, diff_dtype);
 }
 
 extern "C" int sfftb_gss_template(sfftb_plan* p, const void* J, const void* mJ, int memkind, int dtype,
@@ -996,6 +1098,14 @@ extern "C" int sfftb_gss_finish(sfftb_plan* p) {
     if (rc == 1) {
         // the Cholesky broke down and the LU fallback replaced the solution: apply again (rare; synchronous)
         const bool f32 = p->cfg.storage == SFFTB_STORE_F32;
+        if (p->pend_mem == SFFTB_MEM_DEVICE) {
+            rc = f32 ? apply_device<float2>(p, p->pend_I, p->pend_J, p->pend_dtype, p->sol, p->pend_diff, p->pend_diff_dtype)
+                     : apply_device<double2>(p, p->pend_I, p->pend_J, p->pend_dtype, p->sol, p->pend_diff, p->pend_diff_dtype);
+            if (rc) return rc;
+            if (p->pend_sol) CK(cudaMemcpyAsync(p->pend_sol, p->sol, sizeof(double) * p->d.NEQ, cudaMemcpyDeviceToDevice, p->stream));
+            CK(cudaStreamSynchronize(p->stream));
+            return collect_timings(p, true, true);
+        }
         rc = f32 ? apply_device<float2>(p, p->stC, p->stD, p->pend_dtype, p->sol, p->stA, p->pend_diff_dtype, nullptr, false, nullptr)
                  : apply_device<double2>(p, p->stC, p->stD, p->pend_dtype, p->sol, p->stA, p->pend_diff_dtype, nullptr, false, nullptr);
         if (rc) return rc;

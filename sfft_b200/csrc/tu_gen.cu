@@ -377,6 +377,15 @@ int gen_plan_create(sfftb_plan* p, const sfftb_config* cfg, const sfftb_basis* k
     return 0;
 }
 
+// [0] passes of the fit column kernel, [1] stored planes staged summed over the passes, [2] lag rows per column,
+// [3] stored planes, [4] column planes, [5] unknowns of the solved system, [6] apply planes, [7] stored planes read by the FIR
+void gen_info(const sfftb_plan* p, int* out) {
+    const GenState* g = (const GenState*)p->gen;
+    int ns = 0;
+    for (const GenPass& ps : g->passes) ns += ps.nsrc;
+    out[0] = (int)g->passes.size(); out[1] = ns; out[2] = g->nrows; out[3] = g->nVs; out[4] = g->P; out[5] = p->nsolve;
+    out[6] = g->fir.nap; out[7] = g->fir.nvs;
+}
 int gen_nvs(const sfftb_plan* p) { return ((const GenState*)p->gen)->nVs; }
 void* gen_planes(const sfftb_plan* p) { return ((const GenState*)p->gen)->gP; }
 

@@ -201,6 +201,41 @@ class Plan:
         B.check(self._L.sfftb_gss_submit(self._h, ptrs[0][0], ptrs[1][0], ptrs[2][0], ptrs[3][0], ptrs[0][2], sptr, dptr, ddt))
         self._inflight = (sol, diff, [q[3] for q in ptrs])          # keep the buffers alive until finish
 
+    def gss_submit_delta(self, PixA_I, PixA_J, delta_I, delta_J, out_dtype=np.float64, Solution_out=None, DIFF_out=None):
+        """gss_submit with the masked pair as sparse deltas: delta_I = (idx, val) with mI = I except mI.flat[idx] = val
+        (sfftb_gss_submit_delta; see batch.sparse_delta).  Two images instead of four are copied to the device."""
+        self._check_pair(PixA_I, PixA_J)
+        ptrs = [_ptr_of(a) for a in (PixA_I, PixA_J)]
+        if len({(q[1], q[2]) for q in ptrs}) != 1 or ptrs[0][1] != B.MEM_HOST:
+            raise Exception('MeLOn ERROR: gss_submit_delta takes two host arrays of one dtype')
+        vdt = np.float64 if ptrs[0][2] == B.F64 else np.float32
+        ds = []
+        for (idx, val) in (delta_I, delta_J):
+            idx = np.ascontiguousarray(idx, np.int64)
+            val = np.ascontiguousarray(val, vdt)
+            if idx.shape != val.shape or idx.ndim != 1:
+                raise Exception('MeLOn ERROR: a delta is a pair of 1-D arrays (flat pixel indices, values)')
+            ds.append((idx, val))
+        sol = np.empty(self.NEQ, np.float64) if Solution_out is None else Solution_out
+        diff = np.empty(self.shape, out_dtype) if DIFF_out is None else DIFF_out
+        dptr = diff.ctypes.data if isinstance(diff, np.ndarray) else diff.data_ptr()
+        sptr = sol.ctypes.data if isinstance(sol, np.ndarray) else sol.data_ptr()
+        ddt = B.F64 if str(diff.dtype).endswith('float64') else B.F32
+        B.check(self._L.sfftb_gss_submit_delta(self._h, ptrs[0][0], ptrs[1][0], ds[0][0].size, ds[0][0].ctypes.data, ds[0][1].ctypes.data,
+                                               ds[1][0].size, ds[1][0].ctypes.data, ds[1][1].ctypes.data, ptrs[0][2], sptr, dptr, ddt))
+        self._inflight = (sol, diff, [q[3] for q in ptrs] + ds)
+
+    def gss_submit_device(self, pI, pJ, pmI, pmJ, img_dtype, psol, pdiff, diff_dtype):
+        """Device pointers in / out, queued on the plan's stream without a host synchronisation; gss_finish() waits."""
+        B.check(self._L.sfftb_gss_submit_device(self._h, pI, pJ, pmI, pmJ, img_dtype, psol, pdiff, diff_dtype))
+        self._inflight = (None, None, None)
+
+    def gen_info(self):
+        out = (C.c_int * 8)()
+        B.check(self._L.sfftb_gen_info(self._h, out))
+        keys = ('passes', 'staged_planes_total', 'lag_rows', 'stored_planes', 'column_planes', 'unknowns', 'apply_planes', 'fir_planes')
+        return dict(zip(keys, [int(v) for v in out]))
+
     def gss_template_submit(self, PixA_J, PixA_mJ, out_dtype=np.float64, Solution_out=None, DIFF_out=None):
         """Queue one science tile against the cached template (host arrays); gss_finish() returns (Solution, DIFF)."""
         self._check_pair(PixA_J, PixA_mJ)
