@@ -77,12 +77,17 @@ struct sfftb_plan {
     double* PHI;
     int *idxmap, *ident;
     // workspaces
-    void *gI, *gJ;               // transposed row spectra (storage type); gJ doubles as the FDIFF column buffer
+    void *gI, *gJ;               // transposed row spectra of the FIT step (storage type)
+    void *gIa, *gJa;             // row spectra of the APPLY step, always fp64 (alias gI / gJ for fp64 storage); gJa doubles as the
+                                 // FDIFF column buffer.  fp32 storage rounds only the spectra the normal equations are built
+                                 // from: rounding the spectra of the subtraction itself is amplified by the kernel gain
+                                 // (2e-5 on a deconvolution-direction pair), see DESIGN.md
     void *stA, *stB;             // device staging for host images / host diff
     void *stC, *stD;             // second staging pair (host GSS: the apply images are copied while the fit computes)
     cudaEvent_t evCopy[4], evStart;
     cudaEvent_t evDone;          // end of the work queued by sfftb_gss_submit
     int pending;                 // a submitted GSS has not been finished yet
+    int defer_join;              // asynchronous submissions: the chunked D2H of the difference image is not joined into the compute stream
     void* pend_diff; double* pend_sol; int pend_dtype, pend_diff_dtype;
     int pend_mode;               // 1 = pair (sfftb_gss_submit), 2 = shared-template tile, 3 = already completed synchronously
     const void *pend_J, *pend_mJ; int pend_memkind;
@@ -130,7 +135,7 @@ struct sfftb_plan {
     size_t smem_fit, smem_fir, smem_row, smem_fir3;
     cd* firTaps; double* firCA;
     void* tstate;                // cached template row spectra: [fit: mI planes | apply: I planes], storage type
-    size_t tstate_bytes;
+    size_t tstate_bytes, tstate_fit_bytes;   // [fit half: mI planes, storage type | apply half: I planes, fp64]
     int have_template;
     int factor_cached;           // template path: Aug / cholW hold the Cholesky factor of the (tile independent) LHMAT
     int resolves;                // number of solves served from the cached factor (diagnostics)
@@ -190,7 +195,7 @@ static int env_int(const char* name, int dflt) {
 // tu_rows.cu
 int rows_setup(sfftb_plan* p);
 template <typename TSt> int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj, const double* vtab = nullptr);
-template <typename TSt> int launch_row_inv(sfftb_plan* p, const double* bpq, void* ddiff, int diff_dtype, void* hdiff);
+int launch_row_inv(sfftb_plan* p, const double* bpq, void* ddiff, int diff_dtype, void* hdiff);
 // tu_fit.cu
 int fit_setup(sfftb_plan* p);
 template <typename TSt> int launch_fit_cols(sfftb_plan* p, const TSt* gIsrc, bool jonly);
@@ -200,7 +205,7 @@ int run_cholesky(sfftb_plan* p, int resolve = 0);
 int run_lu(sfftb_plan* p);
 // tu_apply.cu
 int apply_setup(sfftb_plan* p);
-template <typename TSt> int launch_fir(sfftb_plan* p, const TSt* gIsrc, const double* dsol);
+int launch_fir(sfftb_plan* p, const double2* gIsrc, const double* dsol);
 // sfft_b200.cu
 int upload_twiddles(int n, cd** out);
 int upload_engine_table(int Ns, int R, cd** out);
@@ -220,5 +225,6 @@ template <typename TSt> int gen_fit_cols(sfftb_plan* p);
 int gen_fill_system(sfftb_plan* p);
 int gen_restore(sfftb_plan* p);
 int gen_export(sfftb_plan* p, double* buf);
-template <typename TSt> int gen_fir(sfftb_plan* p, const double* dsol);
+int gen_fir(sfftb_plan* p, const double* dsol);
+void* gen_planes_apply(const sfftb_plan* p);
 int gen_bkg_subtract(sfftb_plan* p, const double* bf, void* ddiff, int diff_dtype);

@@ -177,6 +177,8 @@ static int plan_free(sfftb_plan* p) {
     void* ptrs[] = {p->vt8_8, p->vt64_8, p->vt64_4, p->vt256_4, p->vt512_4, p->tabA, p->tabB_row, p->tabC_row, p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
                     p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->substMsg, p->solEff, p->regC, p->regD, p->regSST, p->regI, p->bluTw, p->bluC, p->bluB, p->firTaps, p->firCA, p->tstate, p->stC, p->stD, p->deltaIdx, p->deltaVal};
     for (void* q : ptrs) if (q) cudaFree(q);
+    if (p->gIa && p->gIa != p->gI) cudaFree(p->gIa);
+    if (p->gJa && p->gJa != p->gJ) cudaFree(p->gJa);
     if (p->info_h) cudaFreeHost(p->info_h);
     for (int k = 0; k < EV_COUNT; ++k) if (p->ev[k]) cudaEventDestroy(p->ev[k]);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
@@ -253,6 +255,8 @@ int plan_init_common(sfftb_plan* p, const sfftb_config* cfg) {
     p->rinv.r = r;
     p->rinv.scale = (r.packed ? 2.0 : 1.0) / (double)N1;      // the FIR column pass already carries 1/N0
     CK(cudaMalloc(&p->gJ, csz * (size_t)NH * N0));
+    if (cfg->storage == SFFTB_STORE_F32) CK(cudaMalloc(&p->gJa, sizeof(double2) * (size_t)NH * N0));
+    else p->gJa = p->gJ;
     CK(cudaMalloc(&p->stA, sizeof(double) * (size_t)N0 * N1));
     CK(cudaMalloc(&p->stB, sizeof(double) * (size_t)N0 * N1));
     CK(cudaMalloc(&p->info, sizeof(int) * 4));
@@ -333,6 +337,8 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
 
     // ---- workspaces ----
     CK(cudaMalloc(&p->gI, csz * (size_t)(d.DK + 1) * NH * N0));
+    if (cfg->storage == SFFTB_STORE_F32) CK(cudaMalloc(&p->gIa, sizeof(double2) * (size_t)(d.DK + 1) * NH * N0));
+    else p->gIa = p->gI;
     p->nrowsK = p->cfit.npairs * p->cfit.nl0 + d.Fij * p->cfit.nlj0;
     p->nrowsL = d.Fij * (d.DB + 1) * p->cfit.nlj0;
     CK(cudaMalloc(&p->kap, sizeof(cd) * (size_t)p->nrowsK * NH));
@@ -628,8 +634,8 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, 
             p->stream = p->stream2;
             const int rowsm = std::max(1, std::min(p->nsm - 1, p->nsm * env_int("SFFTB_OVERLAP_ROWS_PCT", 50) / 100));
             p->row_grid_limit = rowsm;
-            int rc2 = launch_row_fwd<TSt>(p, ovI, dtype, (TSt*)p->gI, d.DK + 1);
-            if (!rc2) rc2 = launch_row_fwd<TSt>(p, ovJ, dtype, (TSt*)p->gJ, 1);
+            int rc2 = launch_row_fwd<double2>(p, ovI, dtype, (double2*)p->gIa, d.DK + 1);
+            if (!rc2) rc2 = launch_row_fwd<double2>(p, ovJ, dtype, (double2*)p->gJa, 1);
             p->row_grid_limit = 0;
             p->stream = main;
             if (rc2) return SFFTB_ECUDA;
@@ -690,13 +696,13 @@ static int apply_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype
     EVREC(p, EV_A0);
     if (p->gen) {
         if (!rows_done) {
-            if (launch_row_fwd<TSt>(p, dI, dtype, (TSt*)gen_planes(p), gen_nvs(p), p->vtab)) return SFFTB_ECUDA;
-            if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
+            if (launch_row_fwd<double2>(p, dI, dtype, (double2*)gen_planes_apply(p), gen_nvs(p), p->vtab)) return SFFTB_ECUDA;
+            if (launch_row_fwd<double2>(p, dJ, dtype, (double2*)p->gJa, 1)) return SFFTB_ECUDA;
         }
         EVREC(p, EV_AROWS);
-        if (gen_fir<TSt>(p, dsol)) return SFFTB_ECUDA;
+        if (gen_fir(p, dsol)) return SFFTB_ECUDA;
         EVREC(p, EV_ACOL);
-        if (launch_row_inv<TSt>(p, dsol + d.Fijab, ddiff, diff_dtype, nullptr)) return SFFTB_ECUDA;
+        if (launch_row_inv(p, dsol + d.Fijab, ddiff, diff_dtype, nullptr)) return SFFTB_ECUDA;
         if (gen_bkg_subtract(p, dsol + d.Fijab, ddiff, diff_dtype)) return SFFTB_ECUDA;
         EVREC(p, EV_AINV);
         return 0;
@@ -706,18 +712,19 @@ static int apply_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype
         CKL(p);
         dsol = p->solEff;
     }
-    const TSt* gIsrc = tI ? (const TSt*)tI : (const TSt*)p->gI;
+    // (the apply step works on fp64 spectra whatever the storage of the fit spectra: TSt is not used here)
+    const double2* gIsrc = tI ? (const double2*)tI : (const double2*)p->gIa;
     if (!rows_done) {
         if (p->pendI) { CK(cudaStreamWaitEvent(p->stream, p->pendI, 0)); p->pendI = nullptr; }
-        if (!tI && launch_row_fwd<TSt>(p, dI, dtype, (TSt*)p->gI, d.DK + 1)) return SFFTB_ECUDA;
+        if (!tI && launch_row_fwd<double2>(p, dI, dtype, (double2*)p->gIa, d.DK + 1)) return SFFTB_ECUDA;
         if (p->pendJ) { CK(cudaStreamWaitEvent(p->stream, p->pendJ, 0)); p->pendJ = nullptr; }
-        if (launch_row_fwd<TSt>(p, dJ, dtype, (TSt*)p->gJ, 1)) return SFFTB_ECUDA;
+        if (launch_row_fwd<double2>(p, dJ, dtype, (double2*)p->gJa, 1)) return SFFTB_ECUDA;
     }
     EVREC(p, EV_AROWS);
-    if (launch_fir<TSt>(p, gIsrc, dsol)) return SFFTB_ECUDA;
+    if (launch_fir(p, gIsrc, dsol)) return SFFTB_ECUDA;
     EVREC(p, EV_ACOL);
     const double* bpq = dsol + d.Fijab;
-    if (launch_row_inv<TSt>(p, bpq, ddiff, diff_dtype, hdiff)) return SFFTB_ECUDA;
+    if (launch_row_inv(p, bpq, ddiff, diff_dtype, hdiff)) return SFFTB_ECUDA;
     EVREC(p, EV_AINV);
     return 0;
 }
@@ -942,18 +949,13 @@ static int gss_submit_impl(sfftb_plan* p, const void* I, const void* J, const vo
             CK(cudaMalloc(&p->deltaVal, sizeof(double) * p->delta_cap));
         }
         char* dval = (char*)p->deltaVal;
-        // unmasked pair first (it is also the base of the masked pair), then the deltas
+        // copy stream: the unmasked pair and the deltas.  The masked pair is rebuilt on the COMPUTE stream (a device copy and a
+        // scatter per image, ~0.07 ms per 4096^2 pair): kernels queued on the copy stream would have to wait for a free SM
+        // behind the persistent compute kernels of the pair in flight.
         CK(cudaMemcpyAsync(p->stC, I, bytes, cudaMemcpyHostToDevice, p->stream2));
         if (dl->nI) {
             CK(cudaMemcpyAsync(p->deltaIdx, dl->idxI, sizeof(long long) * dl->nI, cudaMemcpyHostToDevice, p->stream2));
             CK(cudaMemcpyAsync(dval, dl->valI, esz * dl->nI, cudaMemcpyHostToDevice, p->stream2));
-        }
-        CK(cudaMemcpyAsync(p->stA, p->stC, bytes, cudaMemcpyDeviceToDevice, p->stream2));
-        if (dl->nI) {
-            const unsigned grid = (unsigned)((dl->nI + 255) / 256);
-            if (dtype == SFFTB_F64) delta_scatter_kernel<double><<<grid, 256, 0, p->stream2>>>((double*)p->stA, p->deltaIdx, (const double*)dval, dl->nI, (long long)npix);
-            else delta_scatter_kernel<float><<<grid, 256, 0, p->stream2>>>((float*)p->stA, p->deltaIdx, (const float*)dval, dl->nI, (long long)npix);
-            CKL(p);
         }
         CK(cudaEventRecord(p->evCopy[0], p->stream2));
         CK(cudaMemcpyAsync(p->stD, J, bytes, cudaMemcpyHostToDevice, p->stream2));
@@ -961,32 +963,55 @@ static int gss_submit_impl(sfftb_plan* p, const void* I, const void* J, const vo
             CK(cudaMemcpyAsync(p->deltaIdx + dl->nI, dl->idxJ, sizeof(long long) * dl->nJ, cudaMemcpyHostToDevice, p->stream2));
             CK(cudaMemcpyAsync(dval + esz * dl->nI, dl->valJ, esz * dl->nJ, cudaMemcpyHostToDevice, p->stream2));
         }
-        CK(cudaMemcpyAsync(p->stB, p->stD, bytes, cudaMemcpyDeviceToDevice, p->stream2));
-        if (dl->nJ) {
-            const unsigned grid = (unsigned)((dl->nJ + 255) / 256);
-            if (dtype == SFFTB_F64) delta_scatter_kernel<double><<<grid, 256, 0, p->stream2>>>((double*)p->stB, p->deltaIdx + dl->nI, (const double*)(dval + esz * dl->nI), dl->nJ, (long long)npix);
-            else delta_scatter_kernel<float><<<grid, 256, 0, p->stream2>>>((float*)p->stB, p->deltaIdx + dl->nI, (const float*)(dval + esz * dl->nI), dl->nJ, (long long)npix);
+        CK(cudaEventRecord(p->evCopy[1], p->stream2));
+        CK(cudaStreamWaitEvent(p->stream, p->evCopy[0], 0));
+        CK(cudaMemcpyAsync(p->stA, p->stC, bytes, cudaMemcpyDeviceToDevice, p->stream));
+        if (dl->nI) {
+            const unsigned grid = (unsigned)((dl->nI + 255) / 256);
+            if (dtype == SFFTB_F64) delta_scatter_kernel<double><<<grid, 256, 0, p->stream>>>((double*)p->stA, p->deltaIdx, (const double*)dval, dl->nI, (long long)npix);
+            else delta_scatter_kernel<float><<<grid, 256, 0, p->stream>>>((float*)p->stA, p->deltaIdx, (const float*)dval, dl->nI, (long long)npix);
             CKL(p);
         }
-        CK(cudaEventRecord(p->evCopy[1], p->stream2));
-        CK(cudaEventRecord(p->evCopy[2], p->stream2));
-        CK(cudaEventRecord(p->evCopy[3], p->stream2));
+        CK(cudaStreamWaitEvent(p->stream, p->evCopy[1], 0));
+        CK(cudaMemcpyAsync(p->stB, p->stD, bytes, cudaMemcpyDeviceToDevice, p->stream));
+        if (dl->nJ) {
+            const unsigned grid = (unsigned)((dl->nJ + 255) / 256);
+            if (dtype == SFFTB_F64) delta_scatter_kernel<double><<<grid, 256, 0, p->stream>>>((double*)p->stB, p->deltaIdx + dl->nI, (const double*)(dval + esz * dl->nI), dl->nJ, (long long)npix);
+            else delta_scatter_kernel<float><<<grid, 256, 0, p->stream>>>((float*)p->stB, p->deltaIdx + dl->nI, (const float*)(dval + esz * dl->nI), dl->nJ, (long long)npix);
+            CKL(p);
+        }
     }
-    // evCopy[2..3] are re-recorded by the chunked D2H of the apply step, so the apply pair gets its own wait now
-    p->pendI = p->evCopy[0]; p->pendJ = p->evCopy[1];
-    rc = f32 ? fit_device<float2>(p, p->stA, p->stB, dtype) : fit_device<double2>(p, p->stA, p->stB, dtype);
+    if (dl) {
+        p->pendI = nullptr; p->pendJ = nullptr;          // the compute stream already waits for both images
+    } else {
+        // evCopy[2..3] are re-recorded by the chunked D2H of the apply step, so the apply pair gets its own wait now
+        p->pendI = p->evCopy[0]; p->pendJ = p->evCopy[1];
+    }
+    // the forward row pass of the apply pair runs on the copy stream (behind the copies of I and J, which were queued there
+    // first) while the Cholesky runs on the compute stream, like in sfftb_gss
+    const bool ovh = p->overlap && p->row_v8 && p->chol_coop && p->nsm >= 8;
+    rc = f32 ? fit_device<float2>(p, p->stA, p->stB, dtype, nullptr, ovh ? p->stC : nullptr, ovh ? p->stD : nullptr)
+             : fit_device<double2>(p, p->stA, p->stB, dtype, nullptr, ovh ? p->stC : nullptr, ovh ? p->stD : nullptr);
     if (rc) return rc;
-    p->pendI = p->evCopy[2]; p->pendJ = p->evCopy[3];
+    if (dl || ovh) { p->pendI = nullptr; p->pendJ = nullptr; } else { p->pendI = p->evCopy[2]; p->pendJ = p->evCopy[3]; }
     void* hd = p->row_fast ? diff : nullptr;
-    rc = f32 ? apply_device<float2>(p, p->stC, p->stD, dtype, p->sol, p->stA, diff_dtype, nullptr, false, hd)
-             : apply_device<double2>(p, p->stC, p->stD, dtype, p->sol, p->stA, diff_dtype, nullptr, false, hd);
+    p->defer_join = 1;
+    rc = f32 ? apply_device<float2>(p, p->stC, p->stD, dtype, p->sol, p->stA, diff_dtype, nullptr, ovh, hd)
+             : apply_device<double2>(p, p->stC, p->stD, dtype, p->sol, p->stA, diff_dtype, nullptr, ovh, hd);
+    p->defer_join = 0;
     if (rc) return rc;
     if (!p->row_fast) {
         const size_t ob = npix * (diff_dtype == SFFTB_F64 ? 8 : 4);
         CK(cudaMemcpyAsync(diff, p->stA, ob, cudaMemcpyDeviceToHost, p->stream));
     }
-    if (solution) CK(cudaMemcpyAsync(solution, p->sol, sizeof(double) * p->d.NEQ, cudaMemcpyDeviceToHost, p->stream));
-    CK(cudaEventRecord(p->evDone, p->stream));
+    // completion = compute stream done AND the chunked copies of the difference image (copy stream) done; the compute stream
+    // itself does not wait for those copies, so the next pair's kernels start while this image is still going home.  The
+    // Solution goes home on the copy stream too: a device-to-host copy queued on the compute stream would sit in the copy
+    // engine's queue behind the image chunks and stall the compute stream just the same.
+    CK(cudaEventRecord(p->evFork, p->stream));
+    CK(cudaStreamWaitEvent(p->stream2, p->evFork, 0));
+    if (solution) CK(cudaMemcpyAsync(solution, p->sol, sizeof(double) * p->d.NEQ, cudaMemcpyDeviceToHost, p->stream2));
+    CK(cudaEventRecord(p->evDone, p->stream2));
     p->pending = 1; p->pend_diff = diff; p->pend_sol = solution; p->pend_dtype = dtype; p->pend_diff_dtype = diff_dtype;
     p->pend_mode = 1;
     return 0;
@@ -1041,7 +1066,7 @@ extern "C" int sfftb_gss_template_submit(sfftb_plan* p, const void* J, const voi
         // stream holds (back-to-back tiles leave no launch gaps)
         const bool f32d = p->cfg.storage == SFFTB_STORE_F32;
         const void* tfitd = p->tstate;
-        const void* tappd = (const char*)p->tstate + p->tstate_bytes / 2;
+        const void* tappd = (const char*)p->tstate + p->tstate_fit_bytes;
         p->pendI = nullptr; p->pendJ = nullptr;
         int rcd = f32d ? fit_device<float2>(p, nullptr, mJ, dtype, tfitd) : fit_device<double2>(p, nullptr, mJ, dtype, tfitd);
         if (rcd) return rcd;
@@ -1061,21 +1086,25 @@ extern "C" int sfftb_gss_template_submit(sfftb_plan* p, const void* J, const voi
     CK(cudaMemcpyAsync(p->stD, J, bytes, cudaMemcpyHostToDevice, p->stream2));
     CK(cudaEventRecord(p->evCopy[1], p->stream2));
     const void* tfit = p->tstate;
-    const void* tapp = (const char*)p->tstate + p->tstate_bytes / 2;
+    const void* tapp = (const char*)p->tstate + p->tstate_fit_bytes;
     p->pendI = nullptr; p->pendJ = p->evCopy[0];
     int rc = f32 ? fit_device<float2>(p, nullptr, p->stB, dtype, tfit) : fit_device<double2>(p, nullptr, p->stB, dtype, tfit);
     if (rc) return rc;
     p->pendI = nullptr; p->pendJ = p->evCopy[1];
     void* hd = p->row_fast ? diff : nullptr;
+    p->defer_join = 1;
     rc = f32 ? apply_device<float2>(p, nullptr, p->stD, dtype, p->sol, p->stA, diff_dtype, tapp, false, hd)
              : apply_device<double2>(p, nullptr, p->stD, dtype, p->sol, p->stA, diff_dtype, tapp, false, hd);
+    p->defer_join = 0;
     if (rc) return rc;
     if (!p->row_fast) {
         const size_t ob = (size_t)p->d.N0 * p->d.N1 * (diff_dtype == SFFTB_F64 ? 8 : 4);
         CK(cudaMemcpyAsync(diff, p->stA, ob, cudaMemcpyDeviceToHost, p->stream));
     }
-    if (solution) CK(cudaMemcpyAsync(solution, p->sol, sizeof(double) * p->d.NEQ, cudaMemcpyDeviceToHost, p->stream));
-    CK(cudaEventRecord(p->evDone, p->stream));
+    CK(cudaEventRecord(p->evFork, p->stream));
+    CK(cudaStreamWaitEvent(p->stream2, p->evFork, 0));
+    if (solution) CK(cudaMemcpyAsync(solution, p->sol, sizeof(double) * p->d.NEQ, cudaMemcpyDeviceToHost, p->stream2));
+    CK(cudaEventRecord(p->evDone, p->stream2));
     p->pending = 1; p->pend_mode = 2;
     return 0;
 }
@@ -1122,7 +1151,9 @@ static int template_alloc(sfftb_plan* p) {
     if (p->gen) return fail(SFFTB_EINVAL, "the shared-template path is not available for general-basis plans");
     if (p->tstate) return 0;
     const size_t csz = p->cfg.storage == SFFTB_STORE_F32 ? sizeof(float2) : sizeof(double2);
-    p->tstate_bytes = 2 * csz * (size_t)(p->d.DK + 1) * (p->d.N1 / 2 + 1) * p->d.N0;
+    const size_t nel = (size_t)(p->d.DK + 1) * (p->d.N1 / 2 + 1) * p->d.N0;
+    p->tstate_fit_bytes = csz * nel;
+    p->tstate_bytes = p->tstate_fit_bytes + sizeof(double2) * nel;
     CK(cudaMalloc(&p->tstate, p->tstate_bytes));
     return 0;
 }
@@ -1135,14 +1166,13 @@ extern "C" int sfftb_template_prepare(sfftb_plan* p, const void* I, const void* 
     const void *dI, *dmI;
     if ((rc = stage_in(p, mI, memkind, dtype, p->stA, &dmI))) return rc;
     if ((rc = stage_in(p, I, memkind, dtype, p->stB, &dI))) return rc;
-    char* half = (char*)p->tstate + p->tstate_bytes / 2;
+    char* half = (char*)p->tstate + p->tstate_fit_bytes;
     if (p->cfg.storage == SFFTB_STORE_F32) {
         if (launch_row_fwd<float2>(p, dmI, dtype, (float2*)p->tstate, p->d.DK + 1)) return SFFTB_ECUDA;
-        if (launch_row_fwd<float2>(p, dI, dtype, (float2*)half, p->d.DK + 1)) return SFFTB_ECUDA;
     } else {
         if (launch_row_fwd<double2>(p, dmI, dtype, (double2*)p->tstate, p->d.DK + 1)) return SFFTB_ECUDA;
-        if (launch_row_fwd<double2>(p, dI, dtype, (double2*)half, p->d.DK + 1)) return SFFTB_ECUDA;
     }
+    if (launch_row_fwd<double2>(p, dI, dtype, (double2*)half, p->d.DK + 1)) return SFFTB_ECUDA;
     CK(cudaStreamSynchronize(p->stream));
     p->have_template = 1;
     p->factor_cached = 0;
@@ -1173,7 +1203,7 @@ extern "C" int sfftb_gss_template(sfftb_plan* p, const void* J, const void* mJ, 
     CK(cudaSetDevice(p->device));
     const bool f32 = p->cfg.storage == SFFTB_STORE_F32;
     const void* tfit = p->tstate;
-    const void* tapp = (const char*)p->tstate + p->tstate_bytes / 2;
+    const void* tapp = (const char*)p->tstate + p->tstate_fit_bytes;
     const void* dJ;
     int rc;
     if ((rc = stage_in(p, mJ, memkind, dtype, p->stB, &dJ))) return rc;

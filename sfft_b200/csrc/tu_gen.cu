@@ -23,7 +23,8 @@ struct GenState {
     std::vector<void*> owned;        // device allocations released with the plan
     GenFirArgs fir; size_t smem_fir; cd* taps; double* cA;
     GenBkg bkg;
-    void* gP;                        // stored planes [nVs][NH][N0] (storage type)
+    void* gP;                        // stored planes of the fit step [nVs][NH][N0] (storage type)
+    void* gPa;                       // stored planes of the apply step, fp64 (alias of gP for fp64 storage)
 };
 
 template <typename T>
@@ -140,6 +141,8 @@ int gen_plan_create(sfftb_plan* p, const sfftb_config* cfg, const sfftb_basis* k
     p->rinv.DB = 0; p->rinv.Fpq = 0;
     if (rows_setup(p)) return SFFTB_ECUDA;
     if (dev_alloc(g, csz * (size_t)g->nVs * NH * N0 / sizeof(char), (char**)&g->gP)) return SFFTB_ECUDA;
+    g->gPa = g->gP;
+    if (f32 && dev_alloc(g, sizeof(double2) * (size_t)g->nVs * NH * N0, (char**)&g->gPa)) return SFFTB_ECUDA;
 
     // ---- segment geometry (as the polynomial segmented kernel) ----
     GenFitArgs& fa = g->fit;
@@ -369,8 +372,7 @@ int gen_plan_create(sfftb_plan* p, const sfftb_config* cfg, const sfftb_basis* k
         g->smem_fir = sizeof(cd) * (size_t)fr.nap * d.L0 + sizeof(double) * (((size_t)fr.nap + 1) & ~(size_t)1) + sizeof(double) * (nuw + (nuw & 1)) +
                       sizeof(cd) * (size_t)fr.nvs * W;
         if (g->smem_fir > p->max_smem) return fail(SFFTB_EINVAL, "the general FIR kernel needs %zu bytes of shared memory", g->smem_fir);
-        if (f32) { if (set_smem(gen_fir_kernel<float2>, g->smem_fir)) return SFFTB_ECUDA; }
-        else     { if (set_smem(gen_fir_kernel<double2>, g->smem_fir)) return SFFTB_ECUDA; }
+        if (set_smem(gen_fir_kernel<double2>, g->smem_fir)) return SFFTB_ECUDA;
     }
     p->grid_sfit = std::min(NH, p->nsm);
     CK(cudaStreamSynchronize(p->stream));
@@ -388,6 +390,7 @@ void gen_info(const sfftb_plan* p, int* out) {
 }
 int gen_nvs(const sfftb_plan* p) { return ((const GenState*)p->gen)->nVs; }
 void* gen_planes(const sfftb_plan* p) { return ((const GenState*)p->gen)->gP; }
+void* gen_planes_apply(const sfftb_plan* p) { return ((const GenState*)p->gen)->gPa; }
 
 int gen_set_regularizer(sfftb_plan* p) {
     GenState* g = (GenState*)p->gen;
@@ -453,20 +456,18 @@ int gen_export(sfftb_plan* p, double* buf) {
     return 0;
 }
 
-template <typename TSt>
 int gen_fir(sfftb_plan* p, const double* dsol) {
+    typedef double2 TSt;                           // the apply step always works on fp64 spectra
     GenState* g = (GenState*)p->gen;
     const sfftb_dims& d = p->d;
     const int NH = d.N1 / 2 + 1;
     gen_taps_kernel<<<NH, 128, 0, p->stream>>>(g->fir, dsol, g->taps, g->cA);
     CKL(p);
     dim3 grd(NH, (d.N0 + GFIR_CH - 1) / GFIR_CH);
-    gen_fir_kernel<TSt><<<grd, GFIR_NT, g->smem_fir, p->stream>>>(g->fir, (const TSt*)g->gP, (const TSt*)p->gJ, g->taps, g->cA, (TSt*)p->gJ);
+    gen_fir_kernel<TSt><<<grd, GFIR_NT, g->smem_fir, p->stream>>>(g->fir, (const TSt*)g->gPa, (const TSt*)p->gJa, g->taps, g->cA, (TSt*)p->gJa);
     CKL(p);
     return 0;
 }
-template int gen_fir<float2>(sfftb_plan*, const double*);
-template int gen_fir<double2>(sfftb_plan*, const double*);
 
 int gen_bkg_subtract(sfftb_plan* p, const double* bf, void* ddiff, int diff_dtype) {
     GenState* g = (GenState*)p->gen;

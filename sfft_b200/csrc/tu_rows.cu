@@ -7,13 +7,10 @@ int rows_setup(sfftb_plan* p) {
     const RowArgs& r = p->row;
     const bool f32 = p->cfg.storage == SFFTB_STORE_F32;
     if (init_generic_radix_tables()) return SFFTB_ECUDA;
-    if (f32) {
-        if (set_smem(row_fwd_kernel<float, float2>, p->smem_row) || set_smem(row_fwd_kernel<double, float2>, p->smem_row)) return SFFTB_ECUDA;
-        if (set_smem(row_inv_kernel<float2, float>, p->smem_row) || set_smem(row_inv_kernel<float2, double>, p->smem_row)) return SFFTB_ECUDA;
-    } else {
-        if (set_smem(row_fwd_kernel<float, double2>, p->smem_row) || set_smem(row_fwd_kernel<double, double2>, p->smem_row)) return SFFTB_ECUDA;
-        if (set_smem(row_inv_kernel<double2, float>, p->smem_row) || set_smem(row_inv_kernel<double2, double>, p->smem_row)) return SFFTB_ECUDA;
-    }
+    // forward: fp64 spectra always (apply step), fp32 spectra in addition for fp32 storage (fit step); inverse: fp64 only
+    if (set_smem(row_fwd_kernel<float, double2>, p->smem_row) || set_smem(row_fwd_kernel<double, double2>, p->smem_row)) return SFFTB_ECUDA;
+    if (f32 && (set_smem(row_fwd_kernel<float, float2>, p->smem_row) || set_smem(row_fwd_kernel<double, float2>, p->smem_row))) return SFFTB_ECUDA;
+    if (set_smem(row_inv_kernel<double2, float>, p->smem_row) || set_smem(row_inv_kernel<double2, double>, p->smem_row)) return SFFTB_ECUDA;
     // ---- fast paths on the register FFT engines ----
     if (upload_engine_table(16, 16, &p->tabA)) return SFFTB_ECUDA;
     p->row_fast = 0;
@@ -43,8 +40,8 @@ int rows_setup(sfftb_plan* p) {
         p->smem_rowv = sizeof(cd) * ((size_t)RBI * (r.H + r.H / 8 + 8) + 3000 + r.H / 2 + 1);
 #define SET_ROWV(HH)                                                                                              \
         if (r.H == HH) {                                                                                              \
-            if (f32) { if (set_smem(row_fwd_v8_kernel<float, float2, HH>, p->smem_rowv) || set_smem(row_fwd_v8_kernel<double, float2, HH>, p->smem_rowv)) return SFFTB_ECUDA; } \
-            else     { if (set_smem(row_fwd_v8_kernel<float, double2, HH>, p->smem_rowv) || set_smem(row_fwd_v8_kernel<double, double2, HH>, p->smem_rowv)) return SFFTB_ECUDA; } \
+            if (f32 && (set_smem(row_fwd_v8_kernel<float, float2, HH>, p->smem_rowv) || set_smem(row_fwd_v8_kernel<double, float2, HH>, p->smem_rowv))) return SFFTB_ECUDA; \
+            if (set_smem(row_fwd_v8_kernel<float, double2, HH>, p->smem_rowv) || set_smem(row_fwd_v8_kernel<double, double2, HH>, p->smem_rowv)) return SFFTB_ECUDA; \
         }
         SET_ROWV(256) SET_ROWV(512) SET_ROWV(1024) SET_ROWV(2048)
 #undef SET_ROWV
@@ -54,10 +51,9 @@ int rows_setup(sfftb_plan* p) {
         const size_t sm = sizeof(cd) * (size_t)(ROWF_NT / (r.H / 16)) * (r.H + r.H / 16);
 #define SET_ROWF(HH)                                                                                              \
         if (r.H == HH) {                                                                                              \
-            if (f32) { if (set_smem(row_fwd_fast_kernel<float, float2, HH>, sm) || set_smem(row_fwd_fast_kernel<double, float2, HH>, sm) || \
-                           set_smem(row_inv_fast_kernel<float2, float, HH>, sm) || set_smem(row_inv_fast_kernel<float2, double, HH>, sm)) return SFFTB_ECUDA; } \
-            else     { if (set_smem(row_fwd_fast_kernel<float, double2, HH>, sm) || set_smem(row_fwd_fast_kernel<double, double2, HH>, sm) || \
-                           set_smem(row_inv_fast_kernel<double2, float, HH>, sm) || set_smem(row_inv_fast_kernel<double2, double, HH>, sm)) return SFFTB_ECUDA; } \
+            if (f32 && (set_smem(row_fwd_fast_kernel<float, float2, HH>, sm) || set_smem(row_fwd_fast_kernel<double, float2, HH>, sm))) return SFFTB_ECUDA; \
+            if (set_smem(row_fwd_fast_kernel<float, double2, HH>, sm) || set_smem(row_fwd_fast_kernel<double, double2, HH>, sm) || \
+                set_smem(row_inv_fast_kernel<double2, float, HH>, sm) || set_smem(row_inv_fast_kernel<double2, double, HH>, sm)) return SFFTB_ECUDA; \
         }
         SET_ROWF(512) SET_ROWF(1024) SET_ROWF(2048) SET_ROWF(4096) SET_ROWF(8192)
 #undef SET_ROWF
@@ -112,8 +108,8 @@ int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj, 
 
 // Inverse row pass (C2R, scaling, background subtraction in real space).  hdiff != NULL (host GSS): the rows are
 // produced in chunks and every finished chunk is copied to the host on the side stream while the next one is computed.
-template <typename TSt>
 int launch_row_inv(sfftb_plan* p, const double* bpq, void* ddiff, int diff_dtype, void* hdiff) {
+    typedef double2 TSt;                           // the apply step always works on fp64 spectra
     const sfftb_dims& d = p->d;
     const size_t osz2 = diff_dtype == SFFTB_F64 ? 16 : 8;
     if (p->row_fast && ((uintptr_t)ddiff % osz2) == 0) {
@@ -129,8 +125,8 @@ int launch_row_inv(sfftb_plan* p, const double* bpq, void* ddiff, int diff_dtype
             p->rinvf.row0 = row0;
 #define RUN_RINVF(HH)                                                                                                  \
             if (H == HH) {                                                                                             \
-                if (diff_dtype == SFFTB_F64) row_inv_fast_kernel<TSt, double, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rinvf, (const TSt*)p->gJ, bpq, (double*)ddiff); \
-                else row_inv_fast_kernel<TSt, float, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rinvf, (const TSt*)p->gJ, bpq, (float*)ddiff);                            \
+                if (diff_dtype == SFFTB_F64) row_inv_fast_kernel<TSt, double, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rinvf, (const TSt*)p->gJa, bpq, (double*)ddiff); \
+                else row_inv_fast_kernel<TSt, float, HH><<<grid, ROWF_NT, sm, p->stream>>>(p->rinvf, (const TSt*)p->gJa, bpq, (float*)ddiff);                            \
             }
             RUN_RINVF(512) RUN_RINVF(1024) RUN_RINVF(2048) RUN_RINVF(4096) RUN_RINVF(8192)
 #undef RUN_RINVF
@@ -144,21 +140,21 @@ int launch_row_inv(sfftb_plan* p, const double* bpq, void* ddiff, int diff_dtype
         }
         p->rinvf.row0 = 0;
         if (hdiff) {
+            // blocking calls join the copy stream back; the asynchronous submissions (defer_join) leave the device-to-host
+            // copies off the compute stream's critical path and record their completion event on the copy stream instead
             CK(cudaEventRecord(p->evJoin, p->stream2));
-            CK(cudaStreamWaitEvent(p->stream, p->evJoin, 0));
+            if (!p->defer_join) CK(cudaStreamWaitEvent(p->stream, p->evJoin, 0));
         }
         return 0;
     }
     const int grid = (d.N0 + p->row.RB - 1) / p->row.RB;
     if (diff_dtype == SFFTB_F64)
-        row_inv_kernel<TSt, double><<<grid, 512, p->smem_row, p->stream>>>(p->rinv, (const TSt*)p->gJ, bpq, (double*)ddiff);
+        row_inv_kernel<TSt, double><<<grid, 512, p->smem_row, p->stream>>>(p->rinv, (const TSt*)p->gJa, bpq, (double*)ddiff);
     else
-        row_inv_kernel<TSt, float><<<grid, 512, p->smem_row, p->stream>>>(p->rinv, (const TSt*)p->gJ, bpq, (float*)ddiff);
+        row_inv_kernel<TSt, float><<<grid, 512, p->smem_row, p->stream>>>(p->rinv, (const TSt*)p->gJa, bpq, (float*)ddiff);
     CKL(p);
     return 0;
 }
 
 template int launch_row_fwd<float2>(sfftb_plan*, const void*, int, float2*, int, const double*);
 template int launch_row_fwd<double2>(sfftb_plan*, const void*, int, double2*, int, const double*);
-template int launch_row_inv<float2>(sfftb_plan*, const double*, void*, int, void*);
-template int launch_row_inv<double2>(sfftb_plan*, const double*, void*, int, void*);
