@@ -86,6 +86,12 @@ int  sfftb_plan_dims(const sfftb_plan* plan, sfftb_dims* out);
  * inputs on the default stream passes cudaStreamLegacy, (cudaStream_t)0x1, or cudaStreamPerThread explicitly). */
 int  sfftb_plan_set_stream(sfftb_plan* plan, void* cuda_stream);
 int  sfftb_plan_sync(sfftb_plan* plan);
+/* SM partition for several pairs in flight on one GPU (plans on different streams; the reference keeps a queue of pairs per
+ * GPU, sfft/MultiEasySparsePacket.py:568-649): the latency-bound Cholesky of LSSolver (SFFTSubtract.py:15-23) is launched on
+ * `solver_sms` SMs and every persistent throughput kernel of this plan (row passes, fit column pass) on the remaining ones,
+ * so the solve of pair k runs beside the transforms of pair k + 1 instead of idling most of the GPU.  0 = off (default:
+ * one pair at a time owns the whole GPU).  Results do not depend on the partition. */
+int  sfftb_plan_set_partition(sfftb_plan* plan, int solver_sms);
 
 /* ESS(SFFTSolution=None, Subtract=False): fit the kernel + background coefficients
  * (SFFTSubtract.py:10-412 / 479-752).  `solution` receives NEQ doubles. */

@@ -95,18 +95,25 @@ class PairPipeline:
     kernels and the device-to-host copy of pair k are in flight.  Results come back in submission order."""
 
     def __init__(self, N0, N1, KerHW, KerPolyOrder=2, BGPolyOrder=2, ConstPhotRatio=True, device=0, storage='fp64',
-                 stream_ptr=None, depth=2):
+                 stream_ptr=None, depth=2, solver_sms=0):
         from .plan import Plan
         self.plans = [Plan(N0, N1, KerHW, KerHW, KerPolyOrder, BGPolyOrder, ConstPhotRatio, device=device, storage=storage)
                       for _ in range(depth)]
-        if not stream_ptr:
+        if solver_sms:
+            # SM partition: every plan on its OWN stream; the Cholesky of pair k occupies `solver_sms` SMs while the row
+            # and column passes of pair k + 1 run on the others (sfftb_plan_set_partition)
+            for pl in self.plans:
+                pl.set_stream(0)
+                pl.set_partition(solver_sms)
+        elif not stream_ptr:
             # one dedicated compute stream for all plans: their kernels serialise (two full-grid cooperative Cholesky
             # kernels must never wait for each other's SMs), only the copies on the plans' copy streams overlap
             import torch
             self._stream = torch.cuda.Stream(device=torch.device('cuda', device))
             stream_ptr = self._stream.cuda_stream
-        for pl in self.plans:
-            pl.set_stream(stream_ptr)
+        if not solver_sms:
+            for pl in self.plans:
+                pl.set_stream(stream_ptr)
         self._busy = [False] * depth
         self._k = 0
 

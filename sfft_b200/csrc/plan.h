@@ -65,6 +65,8 @@ struct sfftb_plan {
     int overlap;                 // 1: sfftb_gss overlaps the apply row pass with the Cholesky solve (device images)
     int row_grid_limit;          // > 0: cap of the persistent row-kernel grid (half the SMs while overlapped)
     int chol_grid_limit;
+    int solver_sms;              // > 0: SM partition (sfftb_plan_set_partition): the Cholesky runs on this many SMs, every persistent
+                                 // throughput kernel on the others, so pairs in flight on different streams overlap
     // tables
     cd *tw0, *tw1, *twMf, *twH, *Q;
     cd *tabA, *tabB_row, *tabC_row;   // register-engine twiddle tables
@@ -188,6 +190,9 @@ static int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
     return (s && *s) ? atoi(s) : dflt;
 }
+
+// SMs the persistent throughput kernels (row passes, fit column pass) may occupy
+static inline int work_sms(const sfftb_plan* p) { return p->solver_sms > 0 ? std::max(1, p->nsm - p->solver_sms) : p->nsm; }
 
 #define EVREC(p, k) do { if ((p)->timing) CK(cudaEventRecord((p)->ev[k], (p)->stream)); } while (0)
 

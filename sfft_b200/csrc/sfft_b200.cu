@@ -212,6 +212,7 @@ int plan_init_common(sfftb_plan* p, const sfftb_config* cfg) {
     CK(cudaEventCreateWithFlags(&p->evStart, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&p->evDone, cudaEventDisableTiming));
     p->overlap = env_int("SFFTB_OVERLAP", 1);
+    p->solver_sms = std::max(0, std::min(p->nsm - 1, env_int("SFFTB_SOLVER_SMS", 0)));
     for (int k = 0; k < EV_COUNT; ++k) CK(cudaEventCreate(&p->ev[k]));
     if (init_generic_radix_tables()) return SFFTB_ECUDA;
 
@@ -530,6 +531,13 @@ extern "C" int sfftb_plan_set_stream(sfftb_plan* p, void* s) {
     return 0;
 }
 
+extern "C" int sfftb_plan_set_partition(sfftb_plan* p, int solver_sms) {
+    if (!p) return fail(SFFTB_EINVAL, "null plan");
+    if (solver_sms < 0 || solver_sms >= p->nsm) return fail(SFFTB_EINVAL, "solver partition of %d SMs does not fit a device with %d", solver_sms, p->nsm);
+    p->solver_sms = solver_sms;
+    return 0;
+}
+
 extern "C" int sfftb_plan_sync(sfftb_plan* p) {
     if (!p) return fail(SFFTB_EINVAL, "null plan");
     CK(cudaSetDevice(p->device));
@@ -632,7 +640,8 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, 
             CK(cudaStreamWaitEvent(p->stream2, p->evFork, 0));
             cudaStream_t main = p->stream;
             p->stream = p->stream2;
-            const int rowsm = std::max(1, std::min(p->nsm - 1, p->nsm * env_int("SFFTB_OVERLAP_ROWS_PCT", 50) / 100));
+            const int rowsm = p->solver_sms > 0 ? work_sms(p)
+                                                : std::max(1, std::min(p->nsm - 1, p->nsm * env_int("SFFTB_OVERLAP_ROWS_PCT", 50) / 100));
             p->row_grid_limit = rowsm;
             int rc2 = launch_row_fwd<double2>(p, ovI, dtype, (double2*)p->gIa, d.DK + 1);
             if (!rc2) rc2 = launch_row_fwd<double2>(p, ovJ, dtype, (double2*)p->gJa, 1);
@@ -642,6 +651,7 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, 
             CK(cudaEventRecord(p->evJoin, p->stream2));
             p->chol_grid_limit = p->nsm - rowsm;
         }
+        if (p->solver_sms > 0) p->chol_grid_limit = p->solver_sms;
         const int rcc = run_cholesky(p);
         p->chol_grid_limit = 0;
         if (rcc) return SFFTB_ECUDA;

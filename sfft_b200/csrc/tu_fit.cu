@@ -42,21 +42,22 @@ template <typename TSt>
 int launch_fit_cols(sfftb_plan* p, const TSt* gIsrc, bool jonly) {
     const sfftb_dims& d = p->d;
     const int DK = d.DK;
+    const int grid_sfit = std::min(p->grid_sfit, work_sms(p));
     if (jonly) {
-        if (DK == 0) fit_seg3_kernel<TSt, 0, true><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
-        else if (DK == 1) fit_seg3_kernel<TSt, 1, true><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
-        else fit_seg3_kernel<TSt, 2, true><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        if (DK == 0) fit_seg3_kernel<TSt, 0, true><<<grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else if (DK == 1) fit_seg3_kernel<TSt, 1, true><<<grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else fit_seg3_kernel<TSt, 2, true><<<grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
     } else if (p->fit_seg) {
-        if (DK == 0) fit_seg3_kernel<TSt, 0><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
-        else if (DK == 1) fit_seg3_kernel<TSt, 1><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
-        else if (DK == 2) fit_seg3_kernel<TSt, 2><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        if (DK == 0) fit_seg3_kernel<TSt, 0><<<grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else if (DK == 1) fit_seg3_kernel<TSt, 1><<<grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else if (DK == 2) fit_seg3_kernel<TSt, 2><<<grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
         else {
             // KerPolyOrder = 3: 65 accumulators do not fit the product threads' registers; three launches over plane ranges
-            fit_seg3_kernel<TSt, 3, false, 0, 2><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+            fit_seg3_kernel<TSt, 3, false, 0, 2><<<grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
             CKL(p);
-            fit_seg3_kernel<TSt, 3, false, 2, 5><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+            fit_seg3_kernel<TSt, 3, false, 2, 5><<<grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
             CKL(p);
-            fit_seg3_kernel<TSt, 3, false, 5, 10><<<p->grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+            fit_seg3_kernel<TSt, 3, false, 5, 10><<<grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
         }
     } else
         fit_col_kernel<TSt><<<p->grid_fit, NT_COL, p->smem_fit, p->stream>>>(p->cfit, gIsrc, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);

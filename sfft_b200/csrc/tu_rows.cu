@@ -72,7 +72,7 @@ int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj, 
         const int H = p->row_v8, RBI = ROWV_NT / (H / 8);
         const int ngroups = (p->d.N0 + RBI - 1) / RBI;
         const int nbatch = (ngroups + rowv.nit - 1) / rowv.nit;
-        const int grid = std::min(nbatch, p->row_grid_limit > 0 ? p->row_grid_limit : p->nsm);
+        const int grid = std::min(nbatch, p->row_grid_limit > 0 ? p->row_grid_limit : work_sms(p));
 #define RUN_ROWV(HH)                                                                                                   \
         if (H == HH) {                                                                                                 \
             if (dtype == SFFTB_F64) row_fwd_v8_kernel<double, TSt, HH><<<grid, ROWV_NT, p->smem_rowv, p->stream>>>(rowv, (const double*)img, out, nj); \

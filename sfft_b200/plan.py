@@ -103,6 +103,11 @@ class Plan:
         non-blocking stream that does NOT synchronise with the legacy default stream; bind cudaStreamLegacy (0x1) then."""
         self.set_stream(stream.cuda_stream or 0x1)
 
+    def set_partition(self, solver_sms):
+        """SM partition for several pairs in flight on one GPU (sfftb_plan_set_partition): the Cholesky on `solver_sms` SMs,
+        the persistent throughput kernels on the others; 0 = off."""
+        B.check(self._L.sfftb_plan_set_partition(self._h, int(solver_sms)))
+
     def sync(self):
         B.check(self._L.sfftb_plan_sync(self._h))
 
