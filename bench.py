@@ -666,345 +666,6 @@ def main():
                         code, sol_d.data_ptr(), diff_d.data_ptr(), code)
 
     def step_host():
-        B.check(L.sfftb_gss(plan._h, host['REF'].data_ptr(), host['SCI'].data_ptr(), host['mREF'].data_ptr(),
-                            host['mSCI'].data_ptr(), B.MEM_HOST, code, sol_h.ctypes.data, B.MEM_HOST,
-                            diff_h.data_ptr(), B.MEM_HOST, code))
-    for _ in range(W):
-        step_device()
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    l0 = plan.launch_count
-    stage = {}
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(K):
-        step_device()
-        for k, v in plan.timings().items():
-            stage[k] = stage.get(k, 0.0) + v
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1) / K
-    launches = plan.launch_count - l0
-    stage = {k: v / K for k, v in stage.items()}
-    KE = args.e2e_steps or min(K, 5)
-    step_host()
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e2.record(stream)
-    for _ in range(KE):
-        step_host()
-    e3.record(stream)
-    barrier()
-    ms_e2e = max((time.perf_counter() - t0) * 1e3 / KE, e2.elapsed_time(e3) / KE)
-    clocks = sampler.stop()
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
-    if rank == 0:
-        mpix = N0 * N1 / 1e6
-        info = plan.gen_info()
-        NH = N1 // 2 + 1
-        csz = 2 * esz
-        peak, which = hbm_peak()
-        # dominant kernel: the block passes of fit_gen_kernel.  Per launch a pass must read the stored planes it stages once
-        # and write its lag rows; summed over the passes of one fit: staged planes total x NH x N0 complex + all lag rows
-        alg_bytes = info['staged_planes_total'] * NH * N0 * csz + info['lag_rows'] * NH * 16
-        t_kernel = stage.get('fit_cols', 0.0) / 1e3
-        achieved = alg_bytes / t_kernel / 1e9 if t_kernel > 0 else None
-        n_pl = P['Fij'] + P.get('ScaFij', 0) + 1
-        step_bytes = (4 * n_pl + 7) * N0 * N1 * esz                  # SURVEY.md 8d, SEPARATE-VARYING: n_pl = Fij + ScaFij + 1
-        out = {
-            'metric': 'Mpix/s per 6Kx6K B-spline SFFT subtraction (GSS: fit + apply)', 'value': world * mpix / (ms / 1e3), 'unit': 'Mpix/s',
-            'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': args.workload, 'image': [N0, N1], 'KerHW': w, 'storage': storage, 'arithmetic': 'fp64',
-                       'spec': {k: (v if not isinstance(v, list) else [float(x) for x in v]) for k, v in spec.items()},
-                       'Fij': P['Fij'], 'ScaFij': P.get('ScaFij'), 'Fpq': P['Fpq'], 'NEQ': P['NEQ'], 'NEQt': P['NEQt'],
-                       'SCALING_MODE': P['SCALING_MODE'], 'plan': info, 'pairs_per_step_per_gpu': 1,
-                       'l2_policy': 'working set per step (inputs 4x%.0f MB, %d stored planes of %.0f MB) exceeds the 126 MB L2' % (
-                           N0 * N1 * esz / 1e6, info['stored_planes'], NH * N0 * csz / 1e6)},
-            'stage_ms': stage,
-            'assembly_solve_ms': stage.get('fit_cols', 0) + stage.get('fit_reduce_fill', 0) + stage.get('fit_solve', 0),
-            'solver': plan.last_solver, 'clocks': clocks,
-            'e2e': {'value': world * mpix / (ms_e2e / 1e3), 'unit': 'Mpix/s', 'ms_per_step': ms_e2e, 'steps': KE,
-                    'mode': 'one blocking sfftb_gss call per step (host buffers)', 'h2d_bytes_per_step': 4 * N0 * N1 * esz,
-                    'd2h_bytes_per_step': N0 * N1 * esz + plan.NEQ * 8, 'host_numa_node': numa},
-            'gpu_launches': launches,
-            'roofline': {'bound': 'hbm', 'kernel': 'fit_gen_kernel', 'achieved': achieved, 'peak': peak, 'peak_source': which, 'unit': 'GB/s',
-                         'frac': (achieved / peak) if achieved else None, 'traffic': None,
-                         'algorithmic_bytes_per_launch': alg_bytes / max(1, info['passes']), 'launches_per_step_of_kernel': info['passes'],
-                         'kernel_ms': stage.get('fit_cols'), 'step_algorithmic_bytes': step_bytes,
-                         'step_frac': step_bytes / (ms / 1e3) / 1e9 / peak,
-                         'note': 'fp64-issue / shared-memory bound like the polynomial fit kernel (DESIGN.md section 4); %d passes of up to '
-                                 '5 x 5 pair accumulators, n = %d Cholesky' % (info['passes'], info['unknowns'])},
-            'cpu_baseline': None,
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            out['cpu_baseline'] = cpu_port_c3(args.workload, min(args.cpu_sample, 256))
-        print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
-
-
-def cpu_port_c3(name, side):
-    """The B-spline oracle (design-matrix restatement, dense D: small crops only) on the host cores."""
-    from oracle import bspline_oracle as bo
-    (N0, N1, w, storage), d = c3_make(name, 0)
-    s = min(side, N0, N1)
-    w2 = min(w, 2)                               # dense D = s^2 x NEQ doubles: the kernel half width is reduced with the crop
-    crop = {k: np.ascontiguousarray(v[:s, :s]) for k, v in d.items()}
-    P = bo.ssc_params(s, s, w2, **c3_spec(s, s))
-    t0 = time.time()
-    bo.gss(crop['REF'], crop['SCI'], crop['mREF'], crop['mSCI'], P)
-    dt = time.time() - t0
-    return {'value': (s * s / 1e6) / dt, 'unit': 'Mpix/s', 'cores': os.cpu_count(), 'kind': 'port', 'seconds': dt,
-            'sample': '%dx%d crop, KerHW=%d (reduced from %d: the oracle builds the dense design matrix), same B-spline recipe; '
-                      'oracle/bspline_oracle.py, BLAS threads of the host' % (s, s, w2, w)}
-
-
-def run_reference_c3(args, ncores):
-    W, K = max(0, args.warmup), max(1, args.steps)
-    side = min(args.cpu_sample, 256)
-    first = cpu_port_c3(args.workload, side)
-    while first['seconds'] * (K + W) > 240.0 and side > 64:
-        side //= 2
-        first = cpu_port_c3(args.workload, side)
-    for _ in range(W):
-        cpu_port_c3(args.workload, side)
-    t0 = time.time()
-    for _ in range(K):
-        last = cpu_port_c3(args.workload, side)
-    dt = (time.time() - t0) / K
-    v = side * side / 1e6 / dt
-    print(json.dumps({
-        'impl': 'reference', 'metric': 'Mpix/s per 6Kx6K B-spline SFFT subtraction (GSS: fit + apply)', 'value': v, 'unit': 'Mpix/s',
-        'n_gpus': args.gpus, 'steps': K, 'warmup': W, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': args.workload, 'sample': last['sample'], 'same_config': False},
-        'cpu_baseline': {'value': v, 'unit': 'Mpix/s', 'cores': ncores, 'kind': 'port', 'sample': last['sample']},
-        'e2e': {'value': v, 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}))
-
-
-def make_workload(name, rank):
-    from sfft_b200.synth import make_pair, CONFIG_SEEDS
-    N0, N1, w, DK, DB, storage, sid = WORKLOADS[name]
-    d = make_pair(N0, N1, CONFIG_SEEDS[sid] + 1000 * rank, varying_psf=(sid != 1))
-    return (N0, N1, w, DK, DB, storage), d
-
-
-def cpu_port_mpix(name, sample_side, repeats=1):
-    """The oracle (NumPy restatement of the reference NumPy backend, validated against the reference on the golden
-    fixtures) timed on the host cores on a bounded crop of the same workload."""
-    from oracle import sfft_oracle as orc
-    (N0, N1, w, DK, DB, storage), d = make_workload(name, 0)
-    s = min(sample_side, N0, N1)
-    crop = {k: np.ascontiguousarray(v[:s, :s]) for k, v in d.items()}
-    P = orc.ssc_params(s, s, w, DK, DB, True)
-    best = None
-    for _ in range(repeats):
-        t0 = time.time()
-        orc.gss(crop['REF'], crop['SCI'], crop['mREF'], crop['mSCI'], P)
-        dt = time.time() - t0
-        best = dt if best is None else min(best, dt)
-    return (s * s / 1e6) / best, best, s, orc.WORKERS
-
-
-def run_reference(args):
-    """The reference arm: the reference's algorithm for this path on the host cores (the NumPy port in oracle/, which is
-    validated against the unmodified reference on the golden fixtures; the reference itself is Python + numba + pyFFTW
-    and OOMs above 2048^2).  W warm-up steps, then exactly K timed steps; a step is one GSS of a bounded
-    crop of the workload's pair (the crop is halved if K + W steps would not finish within a few minutes)."""
-    rank = int(os.environ.get('RANK', '0'))
-    if rank != 0:
-        return
-    # the same host threads at every N: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which would
-    # throttle the BLAS / FFT pools of this leg only when it is launched under torchrun
-    ncores = os.cpu_count() or 1
-    os.environ['SFFT_ORACLE_WORKERS'] = str(ncores)
-    try:
-        from threadpoolctl import threadpool_limits
-        threadpool_limits(limits=ncores)
-    except Exception:
-        pass
-    from oracle import sfft_oracle as orc
-    orc.WORKERS = ncores
-    name = args.workload
-    if name.startswith('c3'):
-        return run_reference_c3(args, ncores)
-    N0, N1, w, DK, DB, storage, sid = WORKLOADS[name]
-    W, K = max(0, args.warmup), max(1, args.steps)
-    (_, _, _, _, _, _), d = make_workload(name, 0)
-    side = min(args.cpu_sample, N0, N1)
-    budget_s = 240.0
-    while True:
-        crop = {k: np.ascontiguousarray(v[:side, :side]) for k, v in d.items()}
-        P = orc.ssc_params(side, side, w, DK, DB, True)
-
-        def step():
-            t0 = time.time()
-            orc.gss(crop['REF'], crop['SCI'], crop['mREF'], crop['mSCI'], P)
-            return time.time() - t0
-        t_first = step()                                   # untimed probe (also warms the FFT plans)
-        if t_first * (K + W) <= budget_s or side <= max(64, 8 * w):
-            break
-        side //= 2
-    for _ in range(W):
-        step()
-    t0 = time.time()
-    for _ in range(K):
-        step()
-    dt = (time.time() - t0) / K
-    v = (side * side / 1e6) / dt
-    sample = '%dx%d crop of the %s pair (full size %dx%d: same_config %s), KerHW=%d DK=%d DB=%d, fp64 NumPy port of the reference NumPy backend, %d host threads' % (
-        side, side, name, N0, N1, str(side == N0 and side == N1).lower(), w, DK, DB, ncores)
-    print(json.dumps({
-        'impl': 'reference', 'metric': 'Mpix/s per 4Kx4K SFFT subtraction (GSS: fit + apply)', 'value': v,
-        'unit': 'Mpix/s', 'n_gpus': args.gpus, 'steps': K, 'warmup': W,
-        'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-        'data': 'synthetic', 'config': {'workload': name, 'sample': sample, 'crop': [side, side], 'image': [N0, N1], 'same_config': side == N0 and side == N1},
-        'cpu_baseline': {'value': v, 'unit': 'Mpix/s', 'cores': ncores, 'kind': 'port', 'sample': sample},
-        'e2e': {'value': v, 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0}))
-
-
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
-    ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument('--cpu-sample', type=int, default=2048, help='side of the crop timed by the CPU legs (halved until K + W steps fit the budget)')
-    ap.add_argument('--no-config4', action='store_true', help='skip the shared-template sub-benchmark of the default run')
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-pipeline', action='store_true', help='e2e leg: blocking sfftb_gss calls only')
-    ap.add_argument('--e2e-steps', type=int, default=0, help='steps of the host-buffer leg (0 = min(steps, 20))')
-    args = ap.parse_args()
-    if args.impl == 'reference':
-        return run_reference(args)
-
-    import torch
-    import torch.distributed as dist
-    from sfft_b200 import _lib as B
-    from sfft_b200.plan import Plan
-
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    numa = pin_to_gpu_numa_node(local)          # before any pinned allocation: first touch places the host buffers
-    if args.workload.startswith('c3'):
-        return run_c3(args, world, rank, local, numa)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    dev = torch.device('cuda', local)
-    torch.cuda.set_device(dev)
-    W = max(3, args.warmup)
-    K = max(1, args.steps)
-
-    (N0, N1, w, DK, DB, storage), d = make_workload(args.workload, rank)
-    npdt = np.float32 if storage == 'fp32' else np.float64
-    tdt = torch.float32 if storage == 'fp32' else torch.float64
-    code = B.F32 if storage == 'fp32' else B.F64
-    host = {k: torch.from_numpy(np.ascontiguousarray(v.astype(npdt))).pin_memory() for k, v in d.items()}
-    devt = {k: v.to(dev) for k, v in host.items()}
-    diff_d = torch.empty((N0, N1), dtype=tdt, device=dev)
-    diff_h = torch.empty((N0, N1), dtype=tdt).pin_memory()
-    sol_d = torch.empty(0, dtype=torch.float64, device=dev)
-
-    plan = Plan(N0, N1, w, w, DK, DB, True, device=local, storage=storage)
-    sol_d = torch.empty(plan.NEQ, dtype=torch.float64, device=dev)
-    sol_h = np.empty(plan.NEQ, np.float64)
-    stream = torch.cuda.current_stream(dev)
-    plan.bind_torch_stream(stream)
-    plan.set_timing(True)
-    L = B.lib()
-
-    shared = args.workload.startswith('c4_template')
-    bcast_ms = None
-    if shared:
-        from sfft_b200.batch import TemplateBatch
-        tb = TemplateBatch(plan, rank, world)
-        torch.cuda.synchronize(dev)
-        t0 = time.time()
-        if rank == 0:
-            tb.set_template(devt['REF'], devt['mREF'])
-        else:
-            tb.set_template()
-        torch.cuda.synchronize(dev)
-        bcast_ms = (time.time() - t0) * 1e3
-
-    # shared-template tiles resident in HBM: two tiles in flight on two plans that share the template state
-    # (sfftb_gss_template_submit with device pointers; each plan on its own stream), no host round trip between tiles
-    dpipe = None
-    if shared and not args.no_pipeline:
-        from sfft_b200.batch import TemplatePipeline
-        dpipe = TemplatePipeline(N0, N1, w, DK, DB, True, device=local, storage=storage, stream_ptr=None, first_plan=plan)
-        plan.set_stream(0)                             # every plan on its own stream (see TemplatePipeline)
-        dpipe.set_template()
-        dpipe.plans[1].set_timing(True)
-        d_diff = [diff_d, torch.empty_like(diff_d)]
-        d_sol = [sol_d, torch.empty_like(sol_d)]
-        d_state = {'k': 0, 'busy': [False, False]}
-
-    def drain_device():
-        if ppipe is not None:
-            for d_ in range(2):
-                slot = (ppipe['k'] + d_) % 2
-                if ppipe['busy'][slot]:
-                    ppipe['plans'][slot].gss_finish()
-                    ppipe['busy'][slot] = False
-        if dpipe is not None:
-            for slot in range(2):
-                if d_state['busy'][slot]:
-                    dpipe.plans[slot].gss_finish()
-                    d_state['busy'][slot] = False
-
-    # device-resident pairs of the plain workloads: two plans share the compute stream and are driven alternately through
-    # sfftb_gss_submit_device / sfftb_gss_finish, so the launches of pair k + 1 are queued while pair k computes and the
-    # GPU never drains between pairs (the kernels themselves still run one pair after the other)
-    ppipe = None
-    if not shared and not args.no_pipeline:
-        plan2 = Plan(N0, N1, w, w, DK, DB, True, device=local, storage=storage)
-        plan2.bind_torch_stream(stream)
-        plan2.set_timing(True)
-        ppipe = {'plans': [plan, plan2], 'busy': [False, False], 'k': 0,
-                 'diff': [diff_d, torch.empty_like(diff_d)], 'sol': [sol_d, torch.empty_like(sol_d)]}
-
-    def step_device():
-        if ppipe is not None:
-            slot = ppipe['k'] % 2
-            pl = ppipe['plans'][slot]
-            if ppipe['busy'][slot]:
-                pl.gss_finish()
-                for k_, v_ in pl.timings().items():
-                    stage[k_] = stage.get(k_, 0.0) + v_
-                stage['_n'] = stage.get('_n', 0) + 1
-            pl.gss_submit_device(devt['REF'].data_ptr(), devt['SCI'].data_ptr(), devt['mREF'].data_ptr(), devt['mSCI'].data_ptr(),
-                                 code, ppipe['sol'][slot].data_ptr(), ppipe['diff'][slot].data_ptr(), code)
-            ppipe['busy'][slot] = True
-            ppipe['k'] += 1
-            return
-        if dpipe is not None:
-            slot = d_state['k'] % 2
-            if d_state['busy'][slot]:
-                dpipe.plans[slot].gss_finish()
-            dpipe.plans[slot].gss_template_submit_device(devt['SCI'].data_ptr(), devt['mSCI'].data_ptr(), code,
-                                                         d_sol[slot].data_ptr(), d_diff[slot].data_ptr(), code)
-            d_state['busy'][slot] = True
-            d_state['k'] += 1
-            return
-        if shared:
-            plan.gss_template_device(devt['SCI'].data_ptr(), devt['mSCI'].data_ptr(), code, sol_d.data_ptr(),
-                                     diff_d.data_ptr(), code)
-            return
-        plan.gss_device(devt['REF'].data_ptr(), devt['SCI'].data_ptr(), devt['mREF'].data_ptr(), devt['mSCI'].data_ptr(),
-                        code, sol_d.data_ptr(), diff_d.data_ptr(), code)
-
-    def step_host():
         if shared:
             B.check(L.sfftb_gss_template(plan._h, host['SCI'].data_ptr(), host['mSCI'].data_ptr(), B.MEM_HOST, code,
                                          sol_h.ctypes.data, B.MEM_HOST, diff_h.data_ptr(), B.MEM_HOST, code))

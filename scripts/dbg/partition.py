@@ -11,9 +11,10 @@ d = make_pair(N, N, 20261019)
 dev = torch.device('cuda', 0)
 devt = {k: torch.from_numpy(np.ascontiguousarray(v.astype(np.float32))).to(dev) for k, v in d.items()}
 ref = {}
-def run(depth, sms, K=24, env=None):
+def run(depth, sms, K=24, env=None, timing=False):
     for k, v in (env or {}).items(): os.environ[k] = v
     pipe = PairPipeline(N, N, 8, 2, 2, True, device=0, storage='fp32', depth=depth, solver_sms=sms)
+    for pl in pipe.plans: pl.set_timing(timing)
     diffs = [torch.empty((N, N), dtype=torch.float32, device=dev) for _ in range(depth)]
     sols = [torch.empty(pipe.plans[0].NEQ, dtype=torch.float64, device=dev) for _ in range(depth)]
     def step(k):
@@ -29,9 +30,15 @@ def run(depth, sms, K=24, env=None):
     if 's' not in ref: ref['s'], ref['d'] = s, df
     print('depth %d solver_sms %3d %s ms/pair %.3f  (%.0f Mpix/s)  sol maxdiff %.2e diff maxdiff %.2e solver %s' % (
         depth, sms, env or '', dt, N * N / 1e3 / dt, np.abs(s - ref['s']).max(), np.abs(df - ref['d']).max(), pipe.plans[0].last_solver), flush=True)
+    if timing: print('   stage ms', {k: round(v, 3) for k, v in pipe.plans[0].timings().items()})
     pipe.close()
     for k in (env or {}): os.environ.pop(k)
-run(2, 0)
-for depth in (2, 3):
-    for sms in (8, 12, 16, 24, 32, 48):
-        run(depth, sms)
+import sys as _s
+if len(_s.argv) > 1 and _s.argv[1] == 'timing':
+    run(2, 0); run(3, 16); run(3, 16, timing=True); run(2, 16, timing=True); run(1, 0, timing=True)
+    print(pipe_t if 0 else '')
+else:
+    run(2, 0)
+    for depth in (2, 3):
+        for sms in (8, 12, 16, 24, 32, 48):
+            run(depth, sms)

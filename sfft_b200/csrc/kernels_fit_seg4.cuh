@@ -1,0 +1,342 @@
+// kernels_fit_seg4.cuh -- segmented fit column pass, warp-specialised, on the half-warp 16-value FFT engine (fft_h16.cuh).
+//
+// Same mathematics, inputs, outputs, ring protocol and shared-memory layout as fit_seg3_kernel (kernels_fit_seg3.cuh, which
+// stays as the engine of the general-basis path).  What changed is the transform side: fit_seg3 is bound by the shared-memory
+// exchanges of its warp-wide 8-value transforms (two exchanges per transform, 250 cycles per transform per SM); here a
+// transform belongs to HALF a warp (16 lanes x 16 values, ONE exchange, twiddles in registers: 126 cycles per transform per
+// SM with eight half-warp pairs in flight, scripts/micro/hfft_bench.cu), so the CTA has
+//   * warps 0..7  ("product warps"): thread = frequency bin, cross-spectrum accumulators in registers, window prefetch
+//     (cp.async ring), column moments -- unchanged;
+//   * warps 8..11 ("transform warps"): 8 half-warp workers, jobs (segment, plane-role) handed out round-robin; the two halves
+//     of a warp run their transforms in lockstep (__syncwarp only).
+// 384 threads, 168 registers each (no setmaxnreg).  The inverse transforms at the end of a column run on all 24 half warps,
+// and the lags are written straight from registers.
+#pragma once
+#include "fft_h16.cuh"
+#include "kernels_fit_seg3.cuh"
+
+#ifndef FS4_NTW
+#define FS4_NTW 8
+#endif
+#define FS4_NT (256 + 32 * FS4_NTW)
+#ifndef FS4_REGT
+#define FS4_REGT 112
+#endif
+#define FS4_REGP (256 - FS4_REGT)
+#define FS4_NTW_UNUSED                 // transform warps
+#define FS4_NWK (2 * FS4_NTW)     // half-warp transform workers
+#define FS4_NHW (2 * (FS4_NT / 32))   // half warps of the CTA (inverse phase)
+
+// inverse transform of one accumulated cross spectrum (plane of the ring) by one half warp; keeps the lags of pair `job`
+template <int NPAIR>
+__device__ __forceinline__ void fs4_inverse_job(const SegFitArgs& fa, const H16Tw& tw, cd* plane, int job, int hl, bool active,
+                                                cd* __restrict__ kaprow)
+{
+    const ColArgs& a = fa.c;
+    cd v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = active ? plane[HPAD(hl + 16 * q)] : cmake(0.0, 0.0);
+    __syncwarp();
+    hfft256(v, plane, hl, tw, +1.0, active);
+    if (!active) return;
+    const bool om = job < NPAIR;
+    const int lim = om ? 2 * a.w0 : a.w0;
+    const int rowbase = om ? job * a.nl0 : fa.nOm + (job - NPAIR) * a.nlj0;
+    const double invM = 1.0 / (double)FS3_M;
+    // v[q] = X[hl + 16 q]; lag m0 lives at index m0 & 255, |m0| <= lim < 128
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int idx = hl + 16 * q;
+        const int m0 = idx < FS3_M / 2 ? idx : idx - FS3_M;
+        if (m0 >= -lim && m0 <= lim) kaprow[rowbase + m0 + lim] = cscale(v[q], invM);
+    }
+}
+
+// Column moments  mom[k1][jj][e] = sum_r cx(r)^e g_jj[k1][r]  of the stored planes (jj <= DK: planes of I, jj = DK + 1: J) for
+// the cross terms with the background basis (column_poly_rows_sub): one warp per (column, plane), coalesced reads, shuffle
+// reduction.  fit_seg3_kernel sums them from the staged windows inside its product warps; here they are a kernel of their own
+// (0.05 ms at 4096^2), which takes 40 % of the instructions, 42 registers and the read-modify-write traffic out of the product
+// loop.  nms = planes-per-column stride * SFFTB_MAXE of the fit kernel's layout; jonly: the moments of J only.
+template <typename TSt>
+__global__ void __launch_bounds__(256) col_moments_kernel(int N0, int NH, int DK, int DB, int nms, int jonly, const TSt* __restrict__ gI,
+                                                          const TSt* __restrict__ gJ, cd* __restrict__ momg)
+{
+    const int nsrc = DK + 2;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (gw >= NH * nsrc) return;
+    const int k1 = gw / nsrc, jj = gw - k1 * nsrc;
+    if (jonly && jj != DK + 1) return;
+    const TSt* col = (jj == DK + 1) ? gJ + (size_t)k1 * N0 : gI + ((size_t)jj * NH + k1) * N0;
+    const int ne = (jj == DK + 1) ? DB + 1 : DK - jj + DB + 1;
+    const double inv0 = 1.0 / (double)N0;
+    cd m[SFFTB_MAXE];
+#pragma unroll
+    for (int e = 0; e < SFFTB_MAXE; ++e) m[e] = cmake(0.0, 0.0);
+#pragma unroll 4
+    for (int r = lane; r < N0; r += 32) {
+        const cd g = load_c(col + r);
+        const double cx = (double)(r + 1) * inv0;
+        double pw = 1.0;
+#pragma unroll
+        for (int e = 0; e < SFFTB_MAXE; ++e) {
+            if (e < ne) { m[e].x = fma(g.x, pw, m[e].x); m[e].y = fma(g.y, pw, m[e].y); pw *= cx; }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < SFFTB_MAXE; ++e) {
+        if (e < ne) {
+            const double sx = warp_sum(m[e].x), sy = warp_sum(m[e].y);
+            if (lane == 0) momg[(size_t)k1 * nms + jj * SFFTB_MAXE + e] = cmake(sx, sy);
+        }
+    }
+}
+
+// JONLY (shared-template tiles after the first): the template is unchanged, so only the cross spectra with J and the
+// moments of J are recomputed -- Fij "A role" transforms + one of J per segment, Fij accumulators; the rows of the other
+// pairs and of the I x T terms stay in `kap` from the first tile of the batch.
+// A0 / A1: this launch accumulates the pairs (A, B >= A) and (A, J) for the planes A in [A0, A1) (register budget of the
+// product threads); the launch with A0 == 0 also accumulates the column moments and writes the background rows.
+template <typename TSt, int DK, bool JONLY = false, int A0 = 0, int A1 = (DK + 1) * (DK + 2) / 2>
+__global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTabs vt_g, const TSt* __restrict__ gI, const TSt* __restrict__ gJ,
+                                                             cd* __restrict__ kap)
+{
+    constexpr int Fij = (DK + 1) * (DK + 2) / 2;
+    constexpr int NPAIR = Fij * (Fij + 1) / 2;
+    constexpr int NA = A1 - A0;                           // planes transformed in the A role (zero-padded segment)
+    constexpr int NB = JONLY ? 0 : Fij - A0;              // planes transformed in the B role (segment + halo)
+    constexpr int NPR = JONLY ? 0 : NA * (Fij - A0) - NA * (NA - 1) / 2;   // pairs (A, B >= A) of this launch
+    constexpr int NACC = NPR + NA;                        // accumulators kept per product thread
+    constexpr int QJ = NPR;                               // first (A, J) accumulator
+    constexpr int NP = NA + NB + 1;                       // spectra per segment: A roles | B roles | J
+    constexpr int PJ = NP - 1;                            // ring plane of the spectrum of J
+    constexpr bool DO_MOM = A0 == 0;
+    constexpr int NMT = Fs3Mom<DK>::nmt, NMPL = Fs3Mom<DK>::npl, NMS = NMPL * SFFTB_MAXE;
+    static_assert(DK + 2 <= NMPL && NMPL * NMT <= 256, "moment threads");
+    // lag-row job of accumulator q: pairs are enumerated `for A for B >= A` over all planes, then the Fij (A, J) rows
+    auto job_of = [](int q) -> int {
+        if (q >= QJ) return NPAIR + A0 + (q - QJ);
+        int ai = 0;
+        while (q >= NB - ai) { q -= NB - ai; ++ai; }
+        const int A = A0 + ai;
+        return A * Fij - A * (A - 1) / 2 + q;
+    };
+    constexpr int NSRC = DK + 2;
+    constexpr int NPL = 2 * NP;                       // planes in the ring (two slots)
+    constexpr int NSTG = Fs3Ring<TSt>::depth, LOG2STG = NSTG == 8 ? 3 : 2, PFD = NSTG - 2;
+    static_assert(NACC <= FS4_NHW, "one half warp per accumulator in the inverse phase");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const ColArgs& a = fa.c;
+    cd* spec = reinterpret_cast<cd*>(smem_raw);                                   // NPL (>= 16) planes
+    constexpr int NPLA = NPL > NACC ? NPL : NACC;     // every accumulator gets a plane: ONE inverse batch per column
+    cd* mom = spec + NPLA * FS3_PITCH;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(mom + NMS);     // (less than the fit_seg3 layout the host sizes)
+    unsigned* cons = reinterpret_cast<unsigned*>(bars + 12);      // [8] segments consumed by product warp w (fs3_publish)
+    TSt* stage = reinterpret_cast<TSt*>(bars + 16);
+    unsigned long long* full = bars;          // [2]  count NP   (one arrive per transform job)
+    unsigned long long* landed = bars + 4;    // [NSTG] count 256  (cp.async arrivals of the product threads)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double inv0 = 1.0 / (double)a.N0;
+    const int h = fa.h, S = fa.S, nseg = fa.nseg;
+
+    if (tid == 0) {
+        fs3_mbar_init(full + 0, NP); fs3_mbar_init(full + 1, NP);
+        for (int b = 0; b < NSTG; ++b) fs3_mbar_init(landed + b, 256);
+    }
+    if (tid < 8) cons[tid] = 0u;
+    // the engine's twiddle tables live in shared memory: with ~200 KB of shared memory carved out there is next to
+    // no L1 left, and a table miss costs an L2 round trip in the middle of a transform
+    (void)vt_g;
+    const int half = lane >> 4, hl = lane & 15;
+    __syncthreads();
+    int g = 0;                                // global segment counter (ring phases continue across columns)
+
+    if (warp < 8) {
+        // ======================================= product warps =======================================
+#if FS4_NTW == 8
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FS4_REGP));
+#endif
+        for (int k1 = blockIdx.x; k1 < a.NH; k1 += gridDim.x, g += nseg) {
+            cd acc[NACC];
+#pragma unroll
+            for (int q = 0; q < NACC; ++q) acc[q] = cmake(0.0, 0.0);
+            cd* kaprow = kap + (size_t)k1 * fa.nrows;
+            // window prefetch: element tid of every stored plane, two segments ahead
+            auto issue = [&](int s) {
+                const int buf = (g + s) & (NSTG - 1);
+                const int r = wrap_row(s * S - h + tid, a.N0);
+#pragma unroll
+                for (int jj = 0; jj < NSRC; ++jj) {
+                    const TSt* col = (jj == DK + 1) ? gJ + (size_t)k1 * a.N0 : gI + ((size_t)jj * a.NH + k1) * a.N0;
+                    cp_async_elem(stage + ((size_t)buf * NSRC + jj) * FS3_M + tid, col + r);
+                }
+                fs3_cp_async_arrive(landed + buf);
+            };
+            for (int s = 0; s < PFD && s < nseg; ++s) issue(s);
+#ifdef FS4_DEBUG
+            long long dWaitFull = 0, dProd = 0, dMom = 0, dT0 = clock64();
+#endif
+            for (int s = 0; s < nseg; ++s) {
+                const int gs = g + s, slot = gs & 1;
+#ifdef FS4_DEBUG
+                long long q0 = clock64();
+#endif
+                fs3_mbar_wait(full + slot, (gs >> 1) & 1);
+#ifdef FS4_DEBUG
+                long long q1 = clock64(); dWaitFull += q1 - q0;
+#endif
+                {
+                    const cd* sp = spec + (size_t)slot * NP * FS3_PITCH + HPAD(tid);
+                    cd fA[NA];
+#pragma unroll
+                    for (int A = 0; A < NA; ++A) fA[A] = sp[A * FS3_PITCH];
+                    const cd fJ = sp[PJ * FS3_PITCH];
+                    if constexpr (!JONLY) {
+                        cd fB[NB];                    // fB[bi] is plane A0 + bi, fA[ai] plane A0 + ai: B >= A <=> bi >= ai
+#pragma unroll
+                        for (int B = 0; B < NB; ++B) fB[B] = sp[(NA + B) * FS3_PITCH];
+                        int q = 0;
+#pragma unroll
+                        for (int A = 0; A < NA; ++A)
+#pragma unroll
+                            for (int B = A; B < NB; ++B) {
+                                acc[q].x = fma(fA[A].x, fB[B].x, acc[q].x); acc[q].x = fma(fA[A].y, fB[B].y, acc[q].x);
+                                acc[q].y = fma(fA[A].x, fB[B].y, acc[q].y); acc[q].y = fma(-fA[A].y, fB[B].x, acc[q].y);
+                                ++q;
+                            }
+                    }
+#pragma unroll
+                    for (int A = 0; A < NA; ++A) {
+                        acc[QJ + A].x = fma(fA[A].x, fJ.x, acc[QJ + A].x); acc[QJ + A].x = fma(fA[A].y, fJ.y, acc[QJ + A].x);
+                        acc[QJ + A].y = fma(fA[A].x, fJ.y, acc[QJ + A].y); acc[QJ + A].y = fma(-fA[A].y, fJ.x, acc[QJ + A].y);
+                    }
+                }
+#ifdef FS4_DEBUG
+                dProd += clock64() - q1;
+#endif
+                // the spectra of this slot are in registers / accumulated: release the slot BEFORE the moments, so that the
+                // transform warps start on segment gs + 2 while the moments of gs are still being summed
+                __syncwarp();
+                if (lane == 0) fs3_publish(cons + warp, (unsigned)(gs + 1));
+                if (s + PFD < nseg) issue(s + PFD);
+            }
+#ifdef FS4_DEBUG
+            if (blockIdx.x == 0 && k1 == blockIdx.x + gridDim.x && (tid == 0 || tid == 128))
+                printf("P tid %d: loop %lld cycles, wait_full %lld, product %lld, moments %lld (nseg %d)\n", tid, clock64() - dT0, dWaitFull, dProd, dMom, nseg);
+#endif
+            // ---- column moments -> background cross-term rows (product warps only) ----
+            if constexpr (DO_MOM) {
+                // the column moments come from col_moments_kernel (one warp per column and stored plane, before this launch)
+                if (tid < NMS) mom[tid] = fa.momg[(size_t)k1 * NMS + tid];
+                fs3_barP();
+                column_poly_rows_sub(fa, gI, k1, mom, kaprow, tid, 256, JONLY);
+            }
+            fs3_bar0();                                    // (A) all transforms and products of the column are done
+            H16Tw htw;                                     // (recomputed per column: 16 registers the product loop cannot spare)
+            h16_init(htw, hl);
+#pragma unroll
+            for (int q = 0; q < NACC; ++q) spec[q * FS3_PITCH + HPAD(tid)] = acc[q];
+            fs3_bar0();
+            {
+                const int wk = 2 * warp + half;
+                const bool act = wk < NACC;
+                if (__any_sync(0xffffffffu, act))
+                    fs4_inverse_job<NPAIR>(fa, htw, spec + (act ? wk : 0) * FS3_PITCH, job_of(act ? wk : 0), hl, act, kaprow);
+            }
+            fs3_bar0();
+        }
+    } else {
+        // ====================================== transform warps ======================================
+#if FS4_NTW == 8
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FS4_REGT));
+#endif
+        const int fw = warp - 8;
+        const int njobs = nseg * NP;
+        H16Tw htw;
+        h16_init(htw, hl);
+        const bool wrap1 = (a.N0 >= FS3_M);               // at most one wrap per window (uniform)
+        int seenL = 0;                                    // window-ring phases (global segment numbers) this warp has seen land
+        for (int k1 = blockIdx.x; k1 < a.NH; k1 += gridDim.x, g += nseg) {
+            cd* kaprow = kap + (size_t)k1 * fa.nrows;
+            // this warp's half h works on job id0 + h; the halves run in lockstep, so the warp waits for the windows and the
+            // ring slots of both jobs (they belong to the same or to consecutive segments)
+#ifdef FS4_DEBUG
+            long long fWaitL = 0, fWaitC = 0, fWork = 0, fT0 = clock64(); int fJobs = 0;
+#endif
+            for (int id0 = 2 * fw; id0 < njobs; id0 += FS4_NWK) {
+                const bool active = id0 + half < njobs;
+#ifdef FS4_DEBUG
+                long long f0 = clock64();
+#endif
+                const int id = active ? id0 + half : id0;
+                const int s = id / NP, p = id - s * NP;
+                const int gs = g + s, slot = gs & 1;
+                const int gsB = g + min(id0 + 1, njobs - 1) / NP;
+                const bool roleA = p < NA, isJ = p == PJ;
+                const int pl = roleA ? A0 + p : (isJ ? 0 : A0 + (p - NA));
+                const int my_i = isJ ? 0 : a.pl_i[pl];
+                const int my_src = isJ ? DK + 1 : a.pl_j[pl];
+                const int c0 = s * S, Sc = min(S, a.N0 - c0);
+                // every phase of the window ring is observed in order: a parity wait is only unambiguous within one phase, and
+                // with few spectra per segment the consecutive jobs of a warp lie more than a ring length apart
+                while (seenL <= gsB) { fs3_mbar_wait(landed + (seenL & (NSTG - 1)), (seenL >> LOG2STG) & 1); ++seenL; }
+#ifdef FS4_DEBUG
+                long long f1 = clock64(); fWaitL += f1 - f0;
+#endif
+                if (gsB >= 2) fs3_wait_consumed(cons, (unsigned)(gsB - 1));    // segment gs - 2 (same slot) consumed by every product warp
+#ifdef FS4_DEBUG
+                long long f2 = clock64(); fWaitC += f2 - f1;
+#endif
+                const TSt* src = stage + ((size_t)(gs & (NSTG - 1)) * NSRC + my_src) * FS3_M;
+                cd* plane = spec + ((size_t)slot * NP + p) * FS3_PITCH;
+                cd v[16];
+                // Branch-free load (the two halves of the warp differ in role and power, and a divergent branch per element
+                // costs an instruction fetch each): v = g * s with s = keep * cx^i, cx^i by Horner on the indicator of i.
+                // cx of window position n = hl + 16 q: one int->double conversion per job, the rest by FMA; rows that wrapped
+                // around the column ends (first / last segments only) are shifted by one period.
+                const int row_l = c0 - h + hl;
+                const double cx_l = (double)(row_l + 1) * inv0;
+                const double e0 = my_i == 0 ? 1.0 : 0.0, e1 = my_i == 1 ? 1.0 : 0.0, e2 = my_i == 2 ? 1.0 : 0.0, e3 = my_i == 3 ? 1.0 : 0.0;
+                const int klo = (roleA ? h : 0) - hl, khi = (active ? (roleA ? h + Sc : FS3_M) : 0) - hl;   // keep <=> klo <= 16 q < khi
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const cd gg = load_c(src + hl + 16 * q);
+                    const int row = row_l + 16 * q;
+                    double cx = fma((double)(16 * q), inv0, cx_l);
+                    if (wrap1) cx += (row < 0) ? 1.0 : ((row >= a.N0) ? -1.0 : 0.0);
+                    else cx -= floor(fma(-0.5, inv0, cx));       // columns shorter than the window: any number of wraps, no integer division
+                                                                 // ((row + 0.5) / N0 is never within 0.5 / N0 of an integer)
+                    double sc = fma(cx, fma(cx, fma(cx, e3, e2), e1), e0);
+                    sc = (16 * q >= klo && 16 * q < khi) ? sc : 0.0;
+                    v[q] = cmake(gg.x * sc, gg.y * sc);
+                }
+                hfft256(v, plane, hl, htw, -1.0, active);
+                if (active) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) plane[HPAD(hl + 16 * q)] = v[q];
+                }
+                __syncwarp();
+                if (hl == 0 && active) fs3_mbar_arrive(full + slot);
+#ifdef FS4_DEBUG
+                fWork += clock64() - f2; ++fJobs;
+#endif
+            }
+#ifdef FS4_DEBUG
+            if (blockIdx.x == 0 && k1 == blockIdx.x + gridDim.x && lane == 0)
+                printf("F warp %d: loop %lld cycles, %d job pairs, wait_landed %lld, wait_consumed %lld, work %lld\n", fw, clock64() - fT0, fJobs, fWaitL, fWaitC, fWork);
+            long long fI0 = clock64();
+#endif
+            fs3_bar0();                                    // (A)
+            fs3_bar0();
+            {
+                const int wk = 2 * warp + half;
+                const bool act = wk < NACC;
+                if (__any_sync(0xffffffffu, act))
+                    fs4_inverse_job<NPAIR>(fa, htw, spec + (act ? wk : 0) * FS3_PITCH, job_of(act ? wk : 0), hl, act, kaprow);
+            }
+            fs3_bar0();
+#ifdef FS4_DEBUG
+            if (blockIdx.x == 0 && k1 == blockIdx.x + gridDim.x && lane == 0 && fw == 0) printf("F warp 0: inverse phase %lld cycles\n", clock64() - fI0);
+#endif
+        }
+    }
+}

@@ -16,6 +16,7 @@
 #include "kernels_row_v8.cuh"
 #include "kernels_fit_seg.cuh"
 #include "kernels_fit_seg3.cuh"
+#include "kernels_fit_seg4.cuh"
 #include "kernels_reader.cuh"
 #include "kernels_fitsio.cuh"
 #include "kernels_gen.cuh"
@@ -128,6 +129,7 @@ struct sfftb_plan {
     int fit_generic_ok;          // the folded-slice kernel has a valid geometry for this shape
     int grid_sfit;
     cd* kap2;                    // [NH][nrows]
+    cd* momg;                    // [NH][5 * SFFTB_MAXE] column moments of the stored planes
     double* part;                // [ksplit][nrows][4 w1 + 1]
     LagReduce2Args red2;
     LagFinishArgs fin2;

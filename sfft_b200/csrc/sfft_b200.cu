@@ -175,7 +175,7 @@ static int plan_free(sfftb_plan* p) {
     cudaSetDevice(p->device);
     gen_free(p);
     void* ptrs[] = {p->vt8_8, p->vt64_8, p->vt64_4, p->vt256_4, p->vt512_4, p->tabA, p->tabB_row, p->tabC_row, p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
-                    p->kap, p->lam, p->nuJ, p->kap2, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->substMsg, p->solEff, p->regC, p->regD, p->regSST, p->regI, p->bluTw, p->bluC, p->bluB, p->firTaps, p->firCA, p->tstate, p->stC, p->stD, p->deltaIdx, p->deltaVal};
+                    p->kap, p->lam, p->nuJ, p->kap2, p->momg, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->substMsg, p->solEff, p->regC, p->regD, p->regSST, p->regI, p->bluTw, p->bluC, p->bluB, p->firTaps, p->firCA, p->tstate, p->stC, p->stD, p->deltaIdx, p->deltaVal};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->gIa && p->gIa != p->gI) cudaFree(p->gIa);
     if (p->gJa && p->gJa != p->gJ) cudaFree(p->gJa);
@@ -448,6 +448,8 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         sf.Q = p->Q;
         memcpy(sf.pq_of, pa.pq_of, sizeof sf.pq_of);
         CK(cudaMalloc(&p->kap2, sizeof(cd) * (size_t)NH * sf.nrows));
+        CK(cudaMalloc(&p->momg, sizeof(cd) * (size_t)NH * 5 * SFFTB_MAXE));
+        sf.momg = p->momg;
         LagReduce2Args& r2 = p->red2;
         r2.N1 = N1; r2.NH = NH; r2.nrows = sf.nrows; r2.w1 = d.w1; r2.tw1 = p->tw1; r2.rb0 = 0;
         const int rowblocks = (sf.nrows + 15) / 16;

@@ -19,16 +19,16 @@ int fit_setup(sfftb_plan* p) {
     if (p->fit_seg) {
         if (set_smem(lag_reduce2_kernel, sizeof(cd) * LR2_KC * LR2_LB)) return SFFTB_ECUDA;
         if (d.DK == 3) {
-            const bool bad = f32 ? (set_smem(fit_seg3_kernel<float2, 3, false, 0, 2>, p->smem_sfit3) || set_smem(fit_seg3_kernel<float2, 3, false, 2, 5>, p->smem_sfit3) ||
-                                    set_smem(fit_seg3_kernel<float2, 3, false, 5, 10>, p->smem_sfit3))
-                                 : (set_smem(fit_seg3_kernel<double2, 3, false, 0, 2>, p->smem_sfit3) || set_smem(fit_seg3_kernel<double2, 3, false, 2, 5>, p->smem_sfit3) ||
-                                    set_smem(fit_seg3_kernel<double2, 3, false, 5, 10>, p->smem_sfit3));
+            const bool bad = f32 ? (set_smem(fit_seg4_kernel<float2, 3, false, 0, 2>, p->smem_sfit3) || set_smem(fit_seg4_kernel<float2, 3, false, 2, 5>, p->smem_sfit3) ||
+                                    set_smem(fit_seg4_kernel<float2, 3, false, 5, 10>, p->smem_sfit3))
+                                 : (set_smem(fit_seg4_kernel<double2, 3, false, 0, 2>, p->smem_sfit3) || set_smem(fit_seg4_kernel<double2, 3, false, 2, 5>, p->smem_sfit3) ||
+                                    set_smem(fit_seg4_kernel<double2, 3, false, 5, 10>, p->smem_sfit3));
             if (bad) return SFFTB_ECUDA;
         }
 #define SET_SFIT3(DKK)                                                                                            \
         if (d.DK == DKK) {                                                                                            \
-            if (f32) { if (set_smem(fit_seg3_kernel<float2, DKK>, p->smem_sfit3) || set_smem(fit_seg3_kernel<float2, DKK, true>, p->smem_sfit3)) return SFFTB_ECUDA; }       \
-            else     { if (set_smem(fit_seg3_kernel<double2, DKK>, p->smem_sfit3) || set_smem(fit_seg3_kernel<double2, DKK, true>, p->smem_sfit3)) return SFFTB_ECUDA; }      \
+            if (f32) { if (set_smem(fit_seg4_kernel<float2, DKK>, p->smem_sfit3) || set_smem(fit_seg4_kernel<float2, DKK, true>, p->smem_sfit3)) return SFFTB_ECUDA; }       \
+            else     { if (set_smem(fit_seg4_kernel<double2, DKK>, p->smem_sfit3) || set_smem(fit_seg4_kernel<double2, DKK, true>, p->smem_sfit3)) return SFFTB_ECUDA; }      \
         }
         SET_SFIT3(0) SET_SFIT3(1) SET_SFIT3(2)
 #undef SET_SFIT3
@@ -43,21 +43,27 @@ int launch_fit_cols(sfftb_plan* p, const TSt* gIsrc, bool jonly) {
     const sfftb_dims& d = p->d;
     const int DK = d.DK;
     const int grid_sfit = std::min(p->grid_sfit, work_sms(p));
+    if (p->fit_seg) {
+        const int NH = d.N1 / 2 + 1, nms = (DK == 3 ? 5 : 4) * SFFTB_MAXE;
+        const int nwarps = NH * (DK + 2);
+        col_moments_kernel<TSt><<<(nwarps + 7) / 8, 256, 0, p->stream>>>(d.N0, NH, DK, d.DB, nms, jonly ? 1 : 0, gIsrc, (const TSt*)p->gJ, p->momg);
+        CKL(p);
+    }
     if (jonly) {
-        if (DK == 0) fit_seg3_kernel<TSt, 0, true><<<grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
-        else if (DK == 1) fit_seg3_kernel<TSt, 1, true><<<grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
-        else fit_seg3_kernel<TSt, 2, true><<<grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        if (DK == 0) fit_seg4_kernel<TSt, 0, true><<<grid_sfit, FS4_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else if (DK == 1) fit_seg4_kernel<TSt, 1, true><<<grid_sfit, FS4_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else fit_seg4_kernel<TSt, 2, true><<<grid_sfit, FS4_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
     } else if (p->fit_seg) {
-        if (DK == 0) fit_seg3_kernel<TSt, 0><<<grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
-        else if (DK == 1) fit_seg3_kernel<TSt, 1><<<grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
-        else if (DK == 2) fit_seg3_kernel<TSt, 2><<<grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        if (DK == 0) fit_seg4_kernel<TSt, 0><<<grid_sfit, FS4_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else if (DK == 1) fit_seg4_kernel<TSt, 1><<<grid_sfit, FS4_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+        else if (DK == 2) fit_seg4_kernel<TSt, 2><<<grid_sfit, FS4_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
         else {
             // KerPolyOrder = 3: 65 accumulators do not fit the product threads' registers; three launches over plane ranges
-            fit_seg3_kernel<TSt, 3, false, 0, 2><<<grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+            fit_seg4_kernel<TSt, 3, false, 0, 2><<<grid_sfit, FS4_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
             CKL(p);
-            fit_seg3_kernel<TSt, 3, false, 2, 5><<<grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+            fit_seg4_kernel<TSt, 3, false, 2, 5><<<grid_sfit, FS4_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
             CKL(p);
-            fit_seg3_kernel<TSt, 3, false, 5, 10><<<grid_sfit, FS3_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
+            fit_seg4_kernel<TSt, 3, false, 5, 10><<<grid_sfit, FS4_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
         }
     } else
         fit_col_kernel<TSt><<<p->grid_fit, NT_COL, p->smem_fit, p->stream>>>(p->cfit, gIsrc, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
