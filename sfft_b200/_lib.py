@@ -9,7 +9,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, 'libsfft_b200.so')
+LIBPATH = os.environ.get('SFFTB_LIB') or os.path.join(HERE, 'libsfft_b200.so')     # SFFTB_LIB: A/B builds of the library
 
 MEM_HOST, MEM_DEVICE = 0, 1
 F64, F32 = 0, 1

@@ -25,6 +25,11 @@ __device__ __forceinline__ void h16_init(H16Tw& t, int hl) {
     sincospi(-16.0 * (double)hl / 256.0, &s, &c); t.w8 = cmake(c, s);
 }
 
+// the same four powers from the engine table tabA[(r - 1) * 16 + k] = exp(-2 pi i r k / 256) (upload_engine_table(16, 16))
+__device__ __forceinline__ void h16_load(H16Tw& t, const cd* __restrict__ tabA, int hl) {
+    t.w1 = tabA[hl]; t.w2 = tabA[16 + hl]; t.w4 = tabA[48 + hl]; t.w8 = tabA[112 + hl];
+}
+
 // sgn = -1 forward, +1 unnormalised inverse.  scratch: H16_SCRATCH elements private to this half warp.
 // live = false: a half warp without a job keeps the lockstep (same instruction stream, __syncwarp) but touches no memory.
 __device__ __forceinline__ void hfft256(cd (&v)[16], cd* scratch, int hl, const H16Tw& tw, double sgn, bool live = true) {

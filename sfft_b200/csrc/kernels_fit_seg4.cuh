@@ -27,6 +27,28 @@
 #define FS4_NWK (2 * FS4_NTW)     // half-warp transform workers
 #define FS4_NHW (2 * (FS4_NT / 32))   // half warps of the CTA (inverse phase)
 
+// Wait until window `seg` (global segment number) of the cp.async ring has landed.  The mbarrier answers "has the phase
+// of this parity completed", which is ambiguous once the barrier is two phases away from the question: a worker whose
+// consecutive jobs lie more than a ring length apart (few spectra per segment) may ask about a window that landed two
+// phases ago and would be told "not yet" until the phase after next.  The product warps' monotonic consumed counters
+// settle that case: a consumed segment has certainly landed.  (The other direction -- a stale "yes" -- cannot happen
+// because every worker walks through the windows in order.)
+__device__ __forceinline__ void fs4_wait_landed(unsigned long long* b, unsigned parity, const unsigned* cons, unsigned seg) {
+    int spins = 0;
+    while (true) {
+        unsigned done = 0;
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(fs3_saddr(b)), "r"(parity) : "memory");
+        if (done) break;
+        unsigned a0, a1, a2, a3, b0, b1, b2, b3;
+        asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(fs3_saddr(cons)) : "memory");
+        asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(fs3_saddr(cons + 4)) : "memory");
+        if (min(min(min(a0, a1), min(a2, a3)), min(min(b0, b1), min(b2, b3))) > seg) break;
+        __nanosleep(FS3_SLEEP_NS);
+        if (++spins > (1 << 22)) __trap();
+    }
+}
+
 // inverse transform of one accumulated cross spectrum (plane of the ring) by one half warp; keeps the lags of pair `job`
 template <int NPAIR>
 __device__ __forceinline__ void fs4_inverse_job(const SegFitArgs& fa, const H16Tw& tw, cd* plane, int job, int hl, bool active,
@@ -155,23 +177,35 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
 #if FS4_NTW == 8
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FS4_REGP));
 #endif
+        int kprev = -1;
         for (int k1 = blockIdx.x; k1 < a.NH; k1 += gridDim.x, g += nseg) {
             cd acc[NACC];
 #pragma unroll
             for (int q = 0; q < NACC; ++q) acc[q] = cmake(0.0, 0.0);
             cd* kaprow = kap + (size_t)k1 * fa.nrows;
-            // window prefetch: element tid of every stored plane, two segments ahead
-            auto issue = [&](int s) {
-                const int buf = (g + s) & (NSTG - 1);
+            // window prefetch: element tid of every stored plane, PF segments ahead; the ring runs on across the column
+            // boundary (the first windows of the CTA's next column are requested during the last segments of this one)
+            auto issue = [&](int kx, int gx, int s) {
+                const int buf = (gx + s) & (NSTG - 1);
                 const int r = wrap_row(s * S - h + tid, a.N0);
 #pragma unroll
                 for (int jj = 0; jj < NSRC; ++jj) {
-                    const TSt* col = (jj == DK + 1) ? gJ + (size_t)k1 * a.N0 : gI + ((size_t)jj * a.NH + k1) * a.N0;
+                    const TSt* col = (jj == DK + 1) ? gJ + (size_t)kx * a.N0 : gI + ((size_t)jj * a.NH + kx) * a.N0;
                     cp_async_elem(stage + ((size_t)buf * NSRC + jj) * FS3_M + tid, col + r);
                 }
                 fs3_cp_async_arrive(landed + buf);
             };
-            for (int s = 0; s < PFD && s < nseg; ++s) issue(s);
+            const int PF = min(PFD, nseg);
+            if (k1 == (int)blockIdx.x) for (int s = 0; s < PF; ++s) issue(k1, g, s);
+            // background cross-term rows of the PREVIOUS column: off the critical path (the transform warps are busy with the
+            // first segments of this column)
+            if constexpr (DO_MOM) {
+                if (kprev >= 0) {
+                    if (tid < NMS) mom[tid] = fa.momg[(size_t)kprev * NMS + tid];
+                    fs3_barP();
+                    column_poly_rows_sub(fa, gI, kprev, mom, kap + (size_t)kprev * fa.nrows, tid, 256, JONLY);
+                }
+            }
 #ifdef FS4_DEBUG
             long long dWaitFull = 0, dProd = 0, dMom = 0, dT0 = clock64();
 #endif
@@ -217,22 +251,17 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
                 // transform warps start on segment gs + 2 while the moments of gs are still being summed
                 __syncwarp();
                 if (lane == 0) fs3_publish(cons + warp, (unsigned)(gs + 1));
-                if (s + PFD < nseg) issue(s + PFD);
+                if (s + PF < nseg) issue(k1, g, s + PF);
+                else if (k1 + (int)gridDim.x < a.NH) issue(k1 + gridDim.x, g + nseg, s + PF - nseg);
             }
 #ifdef FS4_DEBUG
             if (blockIdx.x == 0 && k1 == blockIdx.x + gridDim.x && (tid == 0 || tid == 128))
                 printf("P tid %d: loop %lld cycles, wait_full %lld, product %lld, moments %lld (nseg %d)\n", tid, clock64() - dT0, dWaitFull, dProd, dMom, nseg);
 #endif
             // ---- column moments -> background cross-term rows (product warps only) ----
-            if constexpr (DO_MOM) {
-                // the column moments come from col_moments_kernel (one warp per column and stored plane, before this launch)
-                if (tid < NMS) mom[tid] = fa.momg[(size_t)k1 * NMS + tid];
-                fs3_barP();
-                column_poly_rows_sub(fa, gI, k1, mom, kaprow, tid, 256, JONLY);
-            }
             fs3_bar0();                                    // (A) all transforms and products of the column are done
-            H16Tw htw;                                     // (recomputed per column: 16 registers the product loop cannot spare)
-            h16_init(htw, hl);
+            H16Tw htw;                                     // (reloaded per column: 16 registers the product loop cannot spare)
+            h16_load(htw, fa.tabA, hl);
 #pragma unroll
             for (int q = 0; q < NACC; ++q) spec[q * FS3_PITCH + HPAD(tid)] = acc[q];
             fs3_bar0();
@@ -243,6 +272,15 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
                     fs4_inverse_job<NPAIR>(fa, htw, spec + (act ? wk : 0) * FS3_PITCH, job_of(act ? wk : 0), hl, act, kaprow);
             }
             fs3_bar0();
+            kprev = k1;
+        }
+        if constexpr (DO_MOM) {
+            // (the column moments come from col_moments_kernel, one warp per column and stored plane, before this launch)
+            if (kprev >= 0) {
+                if (tid < NMS) mom[tid] = fa.momg[(size_t)kprev * NMS + tid];
+                fs3_barP();
+                column_poly_rows_sub(fa, gI, kprev, mom, kap + (size_t)kprev * fa.nrows, tid, 256, JONLY);
+            }
         }
     } else {
         // ====================================== transform warps ======================================
@@ -252,7 +290,7 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
         const int fw = warp - 8;
         const int njobs = nseg * NP;
         H16Tw htw;
-        h16_init(htw, hl);
+        h16_load(htw, fa.tabA, hl);
         const bool wrap1 = (a.N0 >= FS3_M);               // at most one wrap per window (uniform)
         int seenL = 0;                                    // window-ring phases (global segment numbers) this warp has seen land
         for (int k1 = blockIdx.x; k1 < a.NH; k1 += gridDim.x, g += nseg) {
@@ -278,7 +316,7 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
                 const int c0 = s * S, Sc = min(S, a.N0 - c0);
                 // every phase of the window ring is observed in order: a parity wait is only unambiguous within one phase, and
                 // with few spectra per segment the consecutive jobs of a warp lie more than a ring length apart
-                while (seenL <= gsB) { fs3_mbar_wait(landed + (seenL & (NSTG - 1)), (seenL >> LOG2STG) & 1); ++seenL; }
+                while (seenL <= gsB) { fs4_wait_landed(landed + (seenL & (NSTG - 1)), (seenL >> LOG2STG) & 1, cons, (unsigned)seenL); ++seenL; }
 #ifdef FS4_DEBUG
                 long long f1 = clock64(); fWaitL += f1 - f0;
 #endif
