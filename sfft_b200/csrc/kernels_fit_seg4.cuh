@@ -26,6 +26,23 @@
 #define FS4_NTW_UNUSED                 // transform warps
 #define FS4_NWK (2 * FS4_NTW)     // half-warp transform workers
 #define FS4_NHW (2 * (FS4_NT / 32))   // half warps of the CTA (inverse phase)
+#define FS4_PITCH H16_SCRATCH         // elements per spectrum plane
+#ifndef FS4_NSTG
+#define FS4_NSTG 8                    // window ring depth (prefetch distance NSTG - 2 segments)
+#endif
+#ifndef FS4_NSLOT32
+#define FS4_NSLOT32 2
+#endif
+// spectrum ring slots (a third slot for fp32-stored spectra fits with FS4_NSTG 4 but measured slower: 1.00 vs 0.93 ms at C2)
+template <typename TSt> struct Fs4Ring { static const int nslot = sizeof(TSt) == 8 ? FS4_NSLOT32 : 2; };
+// dynamic shared memory of fit_seg4_kernel for the largest instantiation of a plan (host side)
+static inline size_t fs4_smem_bytes(int DK, bool f32) {
+    const int Fij = (DK + 1) * (DK + 2) / 2;
+    const int NP = DK == 3 ? 13 : 2 * Fij + 1, NACC = DK == 3 ? 24 : Fij * (Fij + 1) / 2 + Fij;
+    const int planes = std::max((f32 ? FS4_NSLOT32 : 2) * NP, NACC);
+    return sizeof(cd) * ((size_t)planes * FS4_PITCH + (DK == 3 ? 5 : 4) * SFFTB_MAXE) + 128 +
+           (f32 ? sizeof(float2) : sizeof(double2)) * (size_t)FS4_NSTG * (DK + 2) * FS3_M;
+}
 
 // Wait until window `seg` (global segment number) of the cp.async ring has landed.  The mbarrier answers "has the phase
 // of this parity completed", which is ambiguous once the barrier is two phases away from the question: a worker whose
@@ -143,25 +160,26 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
         return A * Fij - A * (A - 1) / 2 + q;
     };
     constexpr int NSRC = DK + 2;
-    constexpr int NPL = 2 * NP;                       // planes in the ring (two slots)
-    constexpr int NSTG = Fs3Ring<TSt>::depth, LOG2STG = NSTG == 8 ? 3 : 2, PFD = NSTG - 2;
+    constexpr int NSLOT = Fs4Ring<TSt>::nslot;
+    constexpr int NPL = NSLOT * NP;                   // planes in the spectrum ring
+    constexpr int NSTG = FS4_NSTG, LOG2STG = NSTG == 8 ? 3 : 2, PFD = NSTG - 2;
     static_assert(NACC <= FS4_NHW, "one half warp per accumulator in the inverse phase");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const ColArgs& a = fa.c;
     cd* spec = reinterpret_cast<cd*>(smem_raw);                                   // NPL (>= 16) planes
     constexpr int NPLA = NPL > NACC ? NPL : NACC;     // every accumulator gets a plane: ONE inverse batch per column
-    cd* mom = spec + NPLA * FS3_PITCH;
+    cd* mom = spec + NPLA * FS4_PITCH;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(mom + NMS);     // (less than the fit_seg3 layout the host sizes)
     unsigned* cons = reinterpret_cast<unsigned*>(bars + 12);      // [8] segments consumed by product warp w (fs3_publish)
     TSt* stage = reinterpret_cast<TSt*>(bars + 16);
-    unsigned long long* full = bars;          // [2]  count NP   (one arrive per transform job)
+    unsigned long long* full = bars;          // [NSLOT] count NP (one arrive per transform job)
     unsigned long long* landed = bars + 4;    // [NSTG] count 256  (cp.async arrivals of the product threads)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double inv0 = 1.0 / (double)a.N0;
     const int h = fa.h, S = fa.S, nseg = fa.nseg;
 
     if (tid == 0) {
-        fs3_mbar_init(full + 0, NP); fs3_mbar_init(full + 1, NP);
+        for (int b = 0; b < NSLOT; ++b) fs3_mbar_init(full + b, NP);
         for (int b = 0; b < NSTG; ++b) fs3_mbar_init(landed + b, 256);
     }
     if (tid < 8) cons[tid] = 0u;
@@ -210,24 +228,24 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
             long long dWaitFull = 0, dProd = 0, dMom = 0, dT0 = clock64();
 #endif
             for (int s = 0; s < nseg; ++s) {
-                const int gs = g + s, slot = gs & 1;
+                const int gs = g + s, slot = gs % NSLOT;
 #ifdef FS4_DEBUG
                 long long q0 = clock64();
 #endif
-                fs3_mbar_wait(full + slot, (gs >> 1) & 1);
+                fs3_mbar_wait(full + slot, (gs / NSLOT) & 1);
 #ifdef FS4_DEBUG
                 long long q1 = clock64(); dWaitFull += q1 - q0;
 #endif
                 {
-                    const cd* sp = spec + (size_t)slot * NP * FS3_PITCH + HPAD(tid);
+                    const cd* sp = spec + (size_t)slot * NP * FS4_PITCH + HPAD(tid);
                     cd fA[NA];
 #pragma unroll
-                    for (int A = 0; A < NA; ++A) fA[A] = sp[A * FS3_PITCH];
-                    const cd fJ = sp[PJ * FS3_PITCH];
+                    for (int A = 0; A < NA; ++A) fA[A] = sp[A * FS4_PITCH];
+                    const cd fJ = sp[PJ * FS4_PITCH];
                     if constexpr (!JONLY) {
                         cd fB[NB];                    // fB[bi] is plane A0 + bi, fA[ai] plane A0 + ai: B >= A <=> bi >= ai
 #pragma unroll
-                        for (int B = 0; B < NB; ++B) fB[B] = sp[(NA + B) * FS3_PITCH];
+                        for (int B = 0; B < NB; ++B) fB[B] = sp[(NA + B) * FS4_PITCH];
                         int q = 0;
 #pragma unroll
                         for (int A = 0; A < NA; ++A)
@@ -263,13 +281,13 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
             H16Tw htw;                                     // (reloaded per column: 16 registers the product loop cannot spare)
             h16_load(htw, fa.tabA, hl);
 #pragma unroll
-            for (int q = 0; q < NACC; ++q) spec[q * FS3_PITCH + HPAD(tid)] = acc[q];
+            for (int q = 0; q < NACC; ++q) spec[q * FS4_PITCH + HPAD(tid)] = acc[q];
             fs3_bar0();
             {
                 const int wk = 2 * warp + half;
                 const bool act = wk < NACC;
                 if (__any_sync(0xffffffffu, act))
-                    fs4_inverse_job<NPAIR>(fa, htw, spec + (act ? wk : 0) * FS3_PITCH, job_of(act ? wk : 0), hl, act, kaprow);
+                    fs4_inverse_job<NPAIR>(fa, htw, spec + (act ? wk : 0) * FS4_PITCH, job_of(act ? wk : 0), hl, act, kaprow);
             }
             fs3_bar0();
             kprev = k1;
@@ -307,7 +325,7 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
 #endif
                 const int id = active ? id0 + half : id0;
                 const int s = id / NP, p = id - s * NP;
-                const int gs = g + s, slot = gs & 1;
+                const int gs = g + s, slot = gs % NSLOT;
                 const int gsB = g + min(id0 + 1, njobs - 1) / NP;
                 const bool roleA = p < NA, isJ = p == PJ;
                 const int pl = roleA ? A0 + p : (isJ ? 0 : A0 + (p - NA));
@@ -320,12 +338,12 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
 #ifdef FS4_DEBUG
                 long long f1 = clock64(); fWaitL += f1 - f0;
 #endif
-                if (gsB >= 2) fs3_wait_consumed(cons, (unsigned)(gsB - 1));    // segment gs - 2 (same slot) consumed by every product warp
+                if (gsB >= NSLOT) fs3_wait_consumed(cons, (unsigned)(gsB - NSLOT + 1));    // segment gs - NSLOT (same slot) consumed by every product warp
 #ifdef FS4_DEBUG
                 long long f2 = clock64(); fWaitC += f2 - f1;
 #endif
                 const TSt* src = stage + ((size_t)(gs & (NSTG - 1)) * NSRC + my_src) * FS3_M;
-                cd* plane = spec + ((size_t)slot * NP + p) * FS3_PITCH;
+                cd* plane = spec + ((size_t)slot * NP + p) * FS4_PITCH;
                 cd v[16];
                 // Branch-free load (the two halves of the warp differ in role and power, and a divergent branch per element
                 // costs an instruction fetch each): v = g * s with s = keep * cx^i, cx^i by Horner on the indicator of i.
@@ -369,7 +387,7 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
                 const int wk = 2 * warp + half;
                 const bool act = wk < NACC;
                 if (__any_sync(0xffffffffu, act))
-                    fs4_inverse_job<NPAIR>(fa, htw, spec + (act ? wk : 0) * FS3_PITCH, job_of(act ? wk : 0), hl, act, kaprow);
+                    fs4_inverse_job<NPAIR>(fa, htw, spec + (act ? wk : 0) * FS4_PITCH, job_of(act ? wk : 0), hl, act, kaprow);
             }
             fs3_bar0();
 #ifdef FS4_DEBUG

@@ -461,11 +461,7 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         f2.R = p->R; f2.RJ = p->RJ; f2.RT = p->RT; f2.RJT = p->RJT;
         p->grid_sfit = std::min(NH, p->nsm);
         {
-            const int NPs = d.DK == 3 ? 13 : 2 * d.Fij + 1;      // DK = 3: the largest of the three passes (2 + 10 + 1)
-            const int npla = std::max(2 * NPs, 16);
-            const int nms = (d.DK == 3 ? 5 : 4) * SFFTB_MAXE, nmt = d.DK == 3 ? 32 : 64;
-            p->smem_sfit3 = sizeof(cd) * ((size_t)npla * FS3_PITCH + nms + (size_t)nms * nmt + 56 + 192) + 128 +
-                            csz * (f32 ? 8 : 4) * (size_t)(d.DK + 2) * FS3_M;
+            p->smem_sfit3 = fs4_smem_bytes(d.DK, f32);
             if (p->smem_sfit3 <= p->max_smem) p->fit_seg = 2;
         }
         if (p->fit_seg) { d.fold = sf.nseg; d.sub_len = sf.S; }
