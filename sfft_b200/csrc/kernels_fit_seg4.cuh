@@ -28,7 +28,7 @@
 #define FS4_NHW (2 * (FS4_NT / 32))   // half warps of the CTA (inverse phase)
 #define FS4_PITCH H16_SCRATCH         // elements per spectrum plane
 #ifndef FS4_NSTG
-#define FS4_NSTG 8                    // window ring depth (prefetch distance NSTG - 2 segments)
+#define FS4_NSTG 8                    // window ring depth for fp32-stored spectra (prefetch distance NSTG - 2 segments); fp64: 4
 #endif
 #ifndef FS4_NSLOT32
 #define FS4_NSLOT32 2
@@ -41,7 +41,7 @@ static inline size_t fs4_smem_bytes(int DK, bool f32) {
     const int NP = DK == 3 ? 13 : 2 * Fij + 1, NACC = DK == 3 ? 24 : Fij * (Fij + 1) / 2 + Fij;
     const int planes = std::max((f32 ? FS4_NSLOT32 : 2) * NP, NACC);
     return sizeof(cd) * ((size_t)planes * FS4_PITCH + (DK == 3 ? 5 : 4) * SFFTB_MAXE) + 128 +
-           (f32 ? sizeof(float2) : sizeof(double2)) * (size_t)FS4_NSTG * (DK + 2) * FS3_M;
+           (f32 ? sizeof(float2) * FS4_NSTG : sizeof(double2) * 4) * (size_t)(DK + 2) * FS3_M;
 }
 
 // Wait until window `seg` (global segment number) of the cp.async ring has landed.  The mbarrier answers "has the phase
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
     constexpr int NSRC = DK + 2;
     constexpr int NSLOT = Fs4Ring<TSt>::nslot;
     constexpr int NPL = NSLOT * NP;                   // planes in the spectrum ring
-    constexpr int NSTG = FS4_NSTG, LOG2STG = NSTG == 8 ? 3 : 2, PFD = NSTG - 2;
+    constexpr int NSTG = sizeof(TSt) == 8 ? FS4_NSTG : 4, LOG2STG = NSTG == 8 ? 3 : 2, PFD = NSTG - 2;   // fp64 windows: 4 buffers
     static_assert(NACC <= FS4_NHW, "one half warp per accumulator in the inverse phase");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const ColArgs& a = fa.c;
