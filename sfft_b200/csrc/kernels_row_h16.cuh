@@ -1,0 +1,164 @@
+// kernels_row_h16.cuh -- forward row pass as R x 256: one thread-local radix-R pass, ONE group-wide exchange, then every half
+// warp runs a 256-point transform on the half-warp engine (fft_h16.cuh: one more exchange, __syncwarp only).
+//
+// Same contract as row_fwd_v8_kernel (kernels_row_v8.cuh): real rows -> half spectra along axis 1 with cy(c)^j (or a column
+// table of a general-basis plan) fused into the load (SpatialPoly + fft2, sfft/sfftcore/SFFTConfigure.py:112-145,
+// SFFTSubtract.py:127-161), two real samples packed per complex point, output stored TRANSPOSED g[j][k1][r].
+// H = N1 / 2 = 256 R complex points per row, R in {4, 8, 16} (N1 = 2048, 4096, 8192), T = H / 16 threads per row:
+//   n = 256 a + b,  k = c + R d:   X[c + R d] = sum_b W_256^{b d} [ W_H^{b c} sum_a W_R^{a c} x[256 a + b] ]
+//   pass A : thread t owns b = t + T i (i < 16 / R): radix-R butterflies over a, twiddles W_H^{b c} (the powers c = 1, 2, 4, 8
+//            from a shared-memory table, the others by one or two multiplications), written to plane c of the row buffer;
+//   pass B : half warp c transforms plane c (hfft256) -> X[c + R d] at position d of plane c.
+// Against the 8-values engine (radix 8 / 8 / 8 / 4 on named barriers) a row crosses its 256-thread group barrier once instead
+// of six times and moves through shared memory three times instead of four; RBI = 512 / T rows are in flight per CTA, so the
+// transposed stores write RBI consecutive rows of a column: full 32-byte sectors for fp32 spectra at N1 = 4096.
+// The plane pitch is 273 elements (= 1 mod 8): the untangle step reads k and H - k of all planes without bank conflicts.
+#pragma once
+#include "fft_h16.cuh"
+#include "kernels_row_v8.cuh"
+
+#define ROWH_NT 512
+#define ROWH_PP 273
+
+struct RowH16Args {
+    int N0, N1, NH, H;
+    const cd* tabA;          // half-warp engine powers: exp(-2 pi i r k / 256), [(r-1) 16 + k]
+    const cd* twP;           // exp(-2 pi i r k / H), [(r-1) 256 + k], r = 1 .. R-1 (upload_engine_table(256, R))
+    const cd* tw1;           // exp(-2 pi i e / N1)
+    const double* vtab;      // general-basis plans: column tables instead of cy^j (or NULL)
+};
+
+static inline size_t rowh_smem_bytes(int H) {
+    const int R = H / 256, T = H / 16, RBI = ROWH_NT / T;     // rows in flight per CTA (all sets)
+    int LR = 0;
+    while ((1 << LR) < R) ++LR;
+    return sizeof(cd) * ((size_t)RBI * R * ROWH_PP + (size_t)LR * 256 + H / 2 + 1);
+}
+
+// SETS: the CTA works as SETS independent sets of 512 / SETS threads (own named barrier, own row groups), so that the untangle /
+// store phase of one set runs under the transform phase of the other
+template <typename TIn, typename TSt, int R, int SETS = 1>
+__global__ void __launch_bounds__(ROWH_NT, 1) row_fwd_h16_kernel(RowH16Args a, const TIn* __restrict__ img, TSt* __restrict__ out, int nj)
+{
+    constexpr int H = 256 * R, T = H / 16, NB = 16 / R;
+    constexpr int TS = ROWH_NT / SETS, RBI = TS / T;          // threads per set, rows per set
+    constexpr int LR = R == 4 ? 2 : (R == 8 ? 3 : 4);
+    constexpr int ROWP = R * ROWH_PP;
+    typedef typename In2<TIn>::type TIn2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd* zbuf = reinterpret_cast<cd*>(smem_raw);              // [RBI][R planes][ROWH_PP]
+    cd* twp = zbuf + (size_t)(ROWH_NT / T) * ROWP;           // [LR][256]: W_H^{b 2^l}
+    cd* tw1s = twp + LR * 256;                               // [H/2 + 1] untangle factors
+    const int tid = threadIdx.x;
+    for (int i = tid; i < LR * 256; i += ROWH_NT) {
+        const int l = i >> 8, b = i & 255;
+        twp[i] = a.twP[(size_t)((1 << l) - 1) * 256 + b];
+    }
+    for (int i = tid; i <= H / 2; i += ROWH_NT) tw1s[i] = a.tw1[i];
+    const int grp = tid / T, t = tid - grp * T;               // row slot of the CTA, thread of the row
+    const int set = tid / TS, ts = tid - set * TS, gs = grp - set * RBI;     // set, thread of the set, row of the set
+    const int lane = tid & 31, half = lane >> 4, hl = lane & 15;
+    const int csub = 2 * (t >> 5) + half;                    // plane / sub-transform of this half warp
+    cd* zrow = zbuf + (size_t)grp * ROWP;
+    H16Tw htw;
+    h16_load(htw, a.tabA, hl);
+    __syncthreads();
+    const double inv1 = 1.0 / (double)a.N1;
+    const int ngroups = (a.N0 + RBI - 1) / RBI;              // row groups of RBI rows; set s of CTA c takes groups c SETS + s + m gridDim SETS
+    cd* zset = zbuf + (size_t)set * RBI * ROWP;
+    auto set_sync = [&]() {
+        if (SETS == 1) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + set), "n"(TS) : "memory");
+    };
+    const int gb0 = blockIdx.x * SETS + set, gstep = gridDim.x * SETS;
+    const bool aligned = (a.N0 % 2 == 0);
+
+    // fp32 images: the 16 packed samples of a thread stay in registers for all planes j and the next row group is requested
+    // under the last untangle step; fp64 images (64 registers) are re-read per plane instead (L2 hits)
+    constexpr bool KEEP = sizeof(TIn) == 4;
+    TIn2 x[16];
+    auto load_row = [&](int gb) {
+        const int r = gb * RBI + gs;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            if (r < a.N0) x[q] = *reinterpret_cast<const TIn2*>(img + (size_t)r * a.N1 + 2 * (t + q * T));
+            else { x[q].x = 0; x[q].y = 0; }
+        }
+    };
+    if (KEEP && gb0 < ngroups) load_row(gb0);
+    for (int gb = gb0; gb < ngroups; gb += gstep) {
+        const int r0 = gb * RBI;
+        for (int j = 0; j < nj; ++j) {
+            if (!KEEP) load_row(gb);
+            cd v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int n = t + q * T;
+                double x0 = (double)x[q].x, x1 = (double)x[q].y;
+                if (a.vtab) {
+                    const double2 vv = *reinterpret_cast<const double2*>(a.vtab + (size_t)j * a.N1 + 2 * n);
+                    x0 *= vv.x; x1 *= vv.y;
+                } else if (j > 0) {
+                    const double c0 = (2 * n + 1) * inv1, c1 = (2 * n + 2) * inv1;
+                    x0 *= (j == 1) ? c0 : (j == 2 ? c0 * c0 : c0 * c0 * c0);
+                    x1 *= (j == 1) ? c1 : (j == 2 ? c1 * c1 : c1 * c1 * c1);
+                }
+                v[q] = cmake(x0, x1);
+            }
+            // ---- pass A: radix-R butterflies over a (element q = NB a + i belongs to butterfly i, b = t + T i) ----
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                const int b = t + T * i;
+                cd y[R];
+#pragma unroll
+                for (int aa = 0; aa < R; ++aa) y[aa] = v[NB * aa + i];
+                bfly_r<R>(y, -1.0);
+                cd w[R];
+#pragma unroll
+                for (int l = 0; l < LR; ++l) w[1 << l] = twp[l * 256 + b];
+#pragma unroll
+                for (int c = 3; c < R; ++c) {
+                    const int hi = c >= 8 ? 8 : (c >= 4 ? 4 : 2);
+                    if (c != hi) w[c] = cmul(w[hi], w[c - hi]);
+                }
+                zrow[HPAD(b)] = y[0];
+#pragma unroll
+                for (int c = 1; c < R; ++c) zrow[c * ROWH_PP + HPAD(b)] = cmul(y[c], w[c]);
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + SETS + grp), "n"(T) : "memory");
+            // ---- pass B: 256-point transform of plane csub by this half warp ----
+            cd* plane = zrow + csub * ROWH_PP;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = plane[HPAD(hl + 16 * q)];
+            __syncwarp();
+            hfft256(v, plane, hl, htw, -1.0);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) plane[HPAD(hl + 16 * q)] = v[q];        // X[csub + R (hl + 16 q)]
+            // the next row group's samples are requested now and arrive under the untangle step of the last plane
+            if (KEEP && j == nj - 1 && gb + gstep < ngroups) load_row(gb + gstep);
+            set_sync();
+            // ---- untangle k and H - k together for all RBI rows of the group; Z[k] sits at plane k % R, position k / R ----
+            const int nvalid = min(RBI, a.N0 - r0);
+            for (int k = ts; k <= H / 2; k += TS) {
+                const cd w = tw1s[k];
+                const int km = (H - k) & (H - 1);
+                const int ia = (k & (R - 1)) * ROWH_PP + HPAD(k / R), ib = (km & (R - 1)) * ROWH_PP + HPAD(km / R);
+                cd gk[RBI], gm[RBI];
+#pragma unroll
+                for (int p = 0; p < RBI; ++p) {
+                    const cd A = zset[(size_t)p * ROWP + ia];
+                    const cd B = zset[(size_t)p * ROWP + ib];
+                    // G[k]   = 0.5 (A + conj B) - 0.5 i W^k (A - conj B)
+                    // G[H-k] = 0.5 (B + conj A) + 0.5 i conj(W^k) (B - conj A)
+                    const cd s = cmake(A.x + B.x, A.y - B.y), d = cmake(A.x - B.x, A.y + B.y);
+                    const cd wd = cmul(w, d);
+                    gk[p] = cmake(0.5 * (s.x + wd.y), 0.5 * (s.y - wd.x));
+                    gm[p] = cmake(0.5 * (s.x - wd.y), 0.5 * (-s.y - wd.x));
+                }
+                store_rows<TSt, RBI>(out + ((size_t)j * a.NH + k) * a.N0 + r0, gk, nvalid, aligned);
+                if (k != H - k) store_rows<TSt, RBI>(out + ((size_t)j * a.NH + (H - k)) * a.N0 + r0, gm, nvalid, aligned);
+            }
+            set_sync();
+        }
+    }
+}

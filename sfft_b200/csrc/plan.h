@@ -14,6 +14,7 @@
 #include "kernels_apply.cuh"
 #include "kernels_row_fast.cuh"
 #include "kernels_row_v8.cuh"
+#include "kernels_row_h16.cuh"
 #include "kernels_fit_seg.cuh"
 #include "kernels_fit_seg3.cuh"
 #include "kernels_fit_seg4.cuh"
@@ -76,6 +77,8 @@ struct sfftb_plan {
     VTabs vtabs;
     size_t smem_sfit3;
     int row_v8;                  // 0 or the engine length H
+    int row_h16;                 // 0 or H: R x 256 forward row pass on the half-warp engine (kernels_row_h16.cuh)
+    RowH16Args rowh;
     size_t smem_rowv;
     double* PHI;
     int *idxmap, *ident;
