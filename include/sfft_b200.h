@@ -173,6 +173,29 @@ int  sfftb_nan_union_fill(int device, void* cuda_stream, void* A, void* B, const
                           unsigned char* mask, int* flags);
 int  sfftb_nan_mask_apply(int device, void* cuda_stream, void* D, int dtype, const unsigned char* mask, size_t n, double sign);
 
+/* Noise decorrelation, the step right after the subtraction in the Roman / JWST pipelines:
+ * PureCupy_DeCorrelation_Calculator.PCDC (sfft/utils/PureCupyDeCorrelationCalculator.py:46-125), DeCorrelation_Calculator.DCC
+ * (sfft/utils/DeCorrelationCalculator.py:11-103) and BSpline_DeCorrelation.BDC (sfft/BSplineSFFT.py:4757-4868).
+ * `nker` match kernels are packed in `kdata` (row-major (L0, L1) stamps one after the other, odd sizes), kshape = {L0, L1} per
+ * kernel, role = 0 (J queue) / 1 (I queue) / 2 (the match kernel of the subtraction; at most one), sig = background sigma per
+ * kernel (unused for role 2); a missing kernel (None in the reference) is passed as the 3 x 3 delta by the caller.  All HOST.
+ *   DeNo = sum_J sig^2 |FK_J|^2 / NJ^2 + |FMK|^2 sum_I sig^2 |FK_I|^2 / NI^2 on the (N0, N1) Fourier grid, clipped from below at
+ *   max(DeNo) / clip_ratio when clip_ratio > 0 (BDC), FKDECO = 1 / sqrt(DeNo).
+ * out_mode 0: `out` receives FKDECO, N0 * N1 doubles (normalize: divided by its [0, 0] value, PCDC REAL_OUTPUT=False);
+ * out_mode 1: `out` receives the real-space kernel of shape (LO0, LO1): ifft2(FKDECO).real, inverse circular shift and tail
+ *             truncation (KERNEL_CSZ_INV / iCSZ; normalize: unit sum); *lost_weight = 1 - sum|K| / sum|ifft2(FKDECO)| for grids
+ *             of at most 65536 points (the sizes DCC / BDC use), NaN otherwise.
+ * The kernels' spectra are evaluated in closed form from their taps: no image-sized transform is computed. */
+int  sfftb_decorr(int device, void* cuda_stream, int N0, int N1, int nker, const double* kdata, const int* kshape, const int* role,
+                  const double* sig, double clip_ratio, int out_mode, int LO0, int LO1, int normalize, double* out, int out_memkind,
+                  double* lost_weight);
+/* PureCupy_FFTKits.FFT_CONVOLVE (sfft/utils/PureCupyFFTKits.py:71-105), the convolution that applies a decorrelation kernel:
+ * out = img (*) kernel with the image extended by `pad_fill` and NaN samples replaced by `nan_fill` (fill_nan = 0 keeps them,
+ * NAN_FILL_VALUE=None), evaluated directly in real space (same result as the zero-padded FFT product, cropped).  `kernel`
+ * (L0, L1) odd, HOST; img / out: `memkind`, `dtype`. */
+int  sfftb_convolve(int device, void* cuda_stream, const void* img, int dtype, int N0, int N1, const double* kernel, int L0, int L1,
+                    double pad_fill, double nan_fill, int fill_nan, int normalize_kernel, void* out, int memkind);
+
 /* Kernel regularisation (sfft/BSplineSFFT.py:3570-3700, REGULARIZE_KERNEL / LAMBDA_REGULARIZE): every following fit solves
  * (LHMAT + lambda * REGMAT) x = RHb with REGMAT[(k,c),(k',c')] = SCALE^2 * SST[k,k'] * iREG[c,c'] (fill_regmat, :2091-2119).
  * SST is the (Fij x Fij) Gram matrix of the kernel basis at the regularisation coordinates, iREG the (Fab x Fab)

@@ -32,7 +32,7 @@ static inline size_t rowh_smem_bytes(int H) {
     const int R = H / 256, T = H / 16, RBI = ROWH_NT / T;     // rows in flight per CTA (all sets)
     int LR = 0;
     while ((1 << LR) < R) ++LR;
-    return sizeof(cd) * ((size_t)RBI * R * ROWH_PP + (size_t)LR * 256 + H / 2 + 1);
+    return sizeof(cd) * ((size_t)RBI * (R * ROWH_PP + 4) + (size_t)LR * 256 + H / 2 + 1);
 }
 
 // SETS: the CTA works as SETS independent sets of 512 / SETS threads (own named barrier, own row groups), so that the untangle /
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(ROWH_NT, 1) row_fwd_h16_kernel(RowH16Args a, c
     constexpr int H = 256 * R, T = H / 16, NB = 16 / R;
     constexpr int TS = ROWH_NT / SETS, RBI = TS / T;          // threads per set, rows per set
     constexpr int LR = R == 4 ? 2 : (R == 8 ? 3 : 4);
-    constexpr int ROWP = R * ROWH_PP;
+    constexpr int ROWP = R * ROWH_PP + (sizeof(TSt) == 8 ? 4 : 2);     // row pitch: the LPC lanes of a column read different bank groups
     typedef typename In2<TIn>::type TIn2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd* zbuf = reinterpret_cast<cd*>(smem_raw);              // [RBI][R planes][ROWH_PP]
@@ -137,17 +137,21 @@ __global__ void __launch_bounds__(ROWH_NT, 1) row_fwd_h16_kernel(RowH16Args a, c
             // the next row group's samples are requested now and arrive under the untangle step of the last plane
             if (KEEP && j == nj - 1 && gb + gstep < ngroups) load_row(gb + gstep);
             set_sync();
-            // ---- untangle k and H - k together for all RBI rows of the group; Z[k] sits at plane k % R, position k / R ----
+            // ---- untangle k and H - k together; Z[k] sits at plane k % R, position k / R.  A lane owns EPL consecutive rows of a
+            // column (16 bytes of the transposed output), LPC adjacent lanes own the RBI rows of the same column, so every store
+            // instruction writes whole 32-byte sectors (a lane per column would leave every sector half written per instruction)
+            constexpr int EPL = 16 / (int)sizeof(TSt) < RBI ? 16 / (int)sizeof(TSt) : RBI, LPC = RBI / EPL;
             const int nvalid = min(RBI, a.N0 - r0);
-            for (int k = ts; k <= H / 2; k += TS) {
+            for (int idx = ts; idx < (H / 2 + 1) * LPC; idx += TS) {
+                const int k = idx / LPC, p0 = (idx - k * LPC) * EPL;
                 const cd w = tw1s[k];
                 const int km = (H - k) & (H - 1);
                 const int ia = (k & (R - 1)) * ROWH_PP + HPAD(k / R), ib = (km & (R - 1)) * ROWH_PP + HPAD(km / R);
-                cd gk[RBI], gm[RBI];
+                cd gk[EPL], gm[EPL];
 #pragma unroll
-                for (int p = 0; p < RBI; ++p) {
-                    const cd A = zset[(size_t)p * ROWP + ia];
-                    const cd B = zset[(size_t)p * ROWP + ib];
+                for (int p = 0; p < EPL; ++p) {
+                    const cd A = zset[(size_t)(p0 + p) * ROWP + ia];
+                    const cd B = zset[(size_t)(p0 + p) * ROWP + ib];
                     // G[k]   = 0.5 (A + conj B) - 0.5 i W^k (A - conj B)
                     // G[H-k] = 0.5 (B + conj A) + 0.5 i conj(W^k) (B - conj A)
                     const cd s = cmake(A.x + B.x, A.y - B.y), d = cmake(A.x - B.x, A.y + B.y);
@@ -155,8 +159,9 @@ __global__ void __launch_bounds__(ROWH_NT, 1) row_fwd_h16_kernel(RowH16Args a, c
                     gk[p] = cmake(0.5 * (s.x + wd.y), 0.5 * (s.y - wd.x));
                     gm[p] = cmake(0.5 * (s.x - wd.y), 0.5 * (-s.y - wd.x));
                 }
-                store_rows<TSt, RBI>(out + ((size_t)j * a.NH + k) * a.N0 + r0, gk, nvalid, aligned);
-                if (k != H - k) store_rows<TSt, RBI>(out + ((size_t)j * a.NH + (H - k)) * a.N0 + r0, gm, nvalid, aligned);
+                const int nv = max(0, min(EPL, nvalid - p0));
+                store_rows<TSt, EPL>(out + ((size_t)j * a.NH + k) * a.N0 + r0 + p0, gk, nv, aligned);
+                if (k != H - k) store_rows<TSt, EPL>(out + ((size_t)j * a.NH + (H - k)) * a.N0 + r0 + p0, gm, nv, aligned);
             }
             set_sync();
         }
