@@ -32,7 +32,8 @@ from .plan import Plan
 from .sfftcore.SFFTConfigure import _current_device
 from .sfftcore.SFFTSubtract import ElementalSFFTSubtract as _ESS, GeneralSFFTSubtract as _GSS
 
-__all__ = ['SingleSFFTConfigure', 'ElementalSFFTSubtract', 'GeneralSFFTSubtract', 'BSpline_Packet', 'regularizer_factors']
+__all__ = ['SingleSFFTConfigure', 'ElementalSFFTSubtract', 'GeneralSFFTSubtract', 'BSpline_Packet', 'regularizer_factors',
+           'Read_SFFTSolution', 'BSpline_MatchingKernel', 'ConvKernel_Convertion', 'BSpline_DeCorrelation']
 
 
 def _laplacian_penalty(w0, w1, IGNORE_LAPLACIAN_KERCENT):
@@ -266,10 +267,32 @@ class BSpline_Packet:
                 ('KSPTYPE', str(KerSpType), 'MeLOn: SFFT'), ('KSPDEG', KerSpDegree, 'MeLOn: SFFT'),
                 ('BSPTYPE', str(BkgSpType), 'MeLOn: SFFT'), ('BSPDEG', BkgSpDegree, 'MeLOn: SFFT'),
                 ('SEPSCA', str(SEPARATE_SCALING), 'MeLOn: SFFT'), ('REGKER', str(REGULARIZE_KERNEL), 'MeLOn: SFFT')])
-        if FITS_Solution is not None:                                                  # :4238-4258
+        if FITS_Solution is not None:                                                  # :4277-4354 (same header keys)
             P = SFFTConfig[0]
-            ups = [(k, P[v], 'MeLOn: SFFT') for k, v in (('N0', 'N0'), ('N1', 'N1'), ('DK', 'DK'), ('DB', 'DB'), ('L0', 'L0'),
-                   ('L1', 'L1'), ('FIJ', 'Fij'), ('FAB', 'Fab'), ('FPQ', 'Fpq'), ('FIJAB', 'Fijab'))]
+            C = 'SFFT'
+            ups = [('NAME_REF', pa.basename(FITS_REF), C), ('NAME_SCI', pa.basename(FITS_SCI), C), ('BEND4SUB', BACKEND_4SUBTRACT, C),
+                   ('CONVD', ForceConv, C), ('KERHW', GKerHW, C), ('KSPTYPE', str(KerSpType), C), ('KSPDEG', KerSpDegree, C),
+                   ('NKIKX', len(KerIntKnotX), C)]
+            ups += [('KIKX%d' % i, float(k), C) for i, k in enumerate(KerIntKnotX)] + [('NKIKY', len(KerIntKnotY), C)]
+            ups += [('KIKY%d' % i, float(k), C) for i, k in enumerate(KerIntKnotY)] + [('SEPSCA', str(SEPARATE_SCALING), C)]
+            if SEPARATE_SCALING:
+                ups += [('SSPTYPE', str(ScaSpType), C), ('SSPDEG', ScaSpDegree, C), ('NSIKX', len(ScaIntKnotX), C)]
+                ups += [('SIKX%d' % i, float(k), C) for i, k in enumerate(ScaIntKnotX)] + [('NSIKY', len(ScaIntKnotY), C)]
+                ups += [('SIKY%d' % i, float(k), C) for i, k in enumerate(ScaIntKnotY)]
+            ups += [('BSPTYPE', str(BkgSpType), C), ('BSPDEG', BkgSpDegree, C), ('NBIKX', len(BkgIntKnotX), C)]
+            ups += [('BIKX%d' % i, float(k), C) for i, k in enumerate(BkgIntKnotX)] + [('NBIKY', len(BkgIntKnotY), C)]
+            ups += [('BIKY%d' % i, float(k), C) for i, k in enumerate(BkgIntKnotY)]
+            ups += [('REGKER', str(REGULARIZE_KERNEL), C), ('ILKC', str(IGNORE_LAPLACIAN_KERCENT), C),
+                    ('NREG', -1 if XY_REGULARIZE is None else int(np.asarray(XY_REGULARIZE).shape[0]), C),
+                    ('REGW', 'UNIFORM' if WEIGHT_REGULARIZE is None else 'SPECIFIED', C), ('REGLAMB', LAMBDA_REGULARIZE, C)]
+            ups += [(k, P[v], C) for k, v in (('N0', 'N0'), ('N1', 'N1'), ('W0', 'w0'), ('W1', 'w1'), ('DK', 'DK'), ('DB', 'DB'))]
+            if SEPARATE_SCALING:
+                ups += [('DS', P['DS'], C)]
+            ups += [(k, P[v], C) for k, v in (('L0', 'L0'), ('L1', 'L1'), ('FAB', 'Fab'), ('FI', 'Fi'), ('FJ', 'Fj'), ('FIJ', 'Fij'),
+                                              ('FP', 'Fp'), ('FQ', 'Fq'), ('FPQ', 'Fpq'))]
+            if SEPARATE_SCALING and ScaSpDegree > 0:
+                ups += [('SCAFI', P['ScaFi'], C), ('SCAFJ', P['ScaFj'], C), ('SCAFIJ', P['ScaFij'], C)]
+            ups += [('FIJAB', P['Fijab'], C), ('NEQ', P['NEQ'], C), ('NEQT', P['NEQt'], C)]
             fitsio.writeto(FITS_Solution, Solution.reshape((-1, 1)).T, base_cards=None, updates=ups)
         return Solution, PixA_DIFF
 
@@ -310,3 +333,128 @@ class BSpline_Packet:
         if _return_config:
             return Solution, PixA_DIFF, SFFTConfig
         return Solution, PixA_DIFF
+
+
+# ---- consumers of the Solution (:4358-4723) and the decorrelation step (:4725-4868) -------------------------------------------
+def _solution_header(FITS_Solution):
+    cards, _ = fitsio.read_header(FITS_Solution)
+    h = fitsio.header_dict(cards)
+    sep = str(h['SEPSCA']).strip() == 'True'
+    d = dict(KerHW=int(h['KERHW']), KerSpType=str(h['KSPTYPE']).strip(),
+             KerIntKnotX=[float(h['KIKX%d' % i]) for i in range(int(h['NKIKX']))],
+             KerIntKnotY=[float(h['KIKY%d' % i]) for i in range(int(h['NKIKY']))],
+             N0=int(h['N0']), N1=int(h['N1']), DK=int(h['DK']), L0=int(h['L0']), L1=int(h['L1']), Fi=int(h['FI']), Fj=int(h['FJ']),
+             Fpq=int(h['FPQ']), SEPARATE_SCALING=sep, ScaSpType=None, DS=None, ScaIntKnotX=None, ScaIntKnotY=None, ScaFi=None, ScaFj=None)
+    if sep:
+        d.update(ScaSpType=str(h['SSPTYPE']).strip(), DS=int(h['SSPDEG']),
+                 ScaIntKnotX=[float(h['SIKX%d' % i]) for i in range(int(h['NSIKX']))],
+                 ScaIntKnotY=[float(h['SIKY%d' % i]) for i in range(int(h['NSIKY']))])
+        if d['DS'] > 0:
+            d.update(ScaFi=int(h['SCAFI']), ScaFj=int(h['SCAFJ']))
+    Solution = np.asarray(fitsio.getdata(FITS_Solution), np.float64)[0]
+    return Solution, d
+
+
+class Read_SFFTSolution:
+    """(SfftKerDict, SfftScaDict) of a BSplineSFFT Solution (:4358-4553): SfftKerDict[(i, j)][a + w0, b + w1] = ac_ijab in the
+    modified-delta basis (ac = a / (N0 N1)); in SEPARATE-VARYING mode the centre taps are NaN there and SfftScaDict[(i, j)]
+    holds the coefficients of the scaling basis."""
+
+    def FromArray(self, Solution, KerSpType, N0, N1, DK, L0, L1, Fi, Fj, Fpq, SEPARATE_SCALING, ScaSpType, DS, ScaFi, ScaFj):
+        varying = bool(SEPARATE_SCALING) and DS != 0
+        w0, w1 = (L0 - 1) // 2, (L1 - 1) // 2
+        if KerSpType == 'Polynomial':
+            REF_ij = [(i, j) for i in range(DK + 1) for j in range(DK + 1 - i)]
+        else:
+            REF_ij = [(i, j) for i in range(Fi) for j in range(Fj)]
+        Fij = len(REF_ij)
+        ac = (np.asarray(Solution, np.float64)[:-Fpq] / (N0 * N1)).reshape(Fij, L0, L1)
+        SfftKerDict = {ij: ac[k].copy() for k, ij in enumerate(REF_ij)}
+        SfftScaDict = None
+        if varying:
+            if ScaSpType == 'Polynomial':
+                ScaREF_ij = [(i, j) for i in range(DS + 1) for j in range(DS + 1 - i)]
+            else:
+                ScaREF_ij = [(i, j) for i in range(ScaFi) for j in range(ScaFj)]
+            # (the reference initialises the dictionary from KerSpType, :4478-4488; the keys it then fills are these)
+            SfftScaDict = {ij: 0.0 for ij in ScaREF_ij}
+            for k, ij in enumerate(REF_ij):
+                if k < len(ScaREF_ij):
+                    SfftScaDict[ScaREF_ij[k]] = float(ac[k, w0, w1])
+                SfftKerDict[ij][w0, w1] = np.nan
+        return SfftKerDict, SfftScaDict
+
+    def FromFITS(self, FITS_Solution):
+        Solution, d = _solution_header(FITS_Solution)
+        return self.FromArray(Solution=Solution, KerSpType=d['KerSpType'], N0=d['N0'], N1=d['N1'], DK=d['DK'], L0=d['L0'], L1=d['L1'],
+                              Fi=d['Fi'], Fj=d['Fj'], Fpq=d['Fpq'], SEPARATE_SCALING=d['SEPARATE_SCALING'], ScaSpType=d['ScaSpType'],
+                              DS=d['DS'], ScaFi=d['ScaFi'], ScaFj=d['ScaFj'])
+
+
+class BSpline_MatchingKernel:
+    """Matching kernels realised at the requested FortranCoor positions XY_q, shape (NPOINT, L0, L1), Cartesian-delta basis
+    (:4555-4723)."""
+
+    def __init__(self, XY_q, VERBOSE_LEVEL=2):
+        self.XY_q = XY_q
+        self.VERBOSE_LEVEL = VERBOSE_LEVEL
+
+    def FromArray(self, Solution, KerSpType, KerIntKnotX, KerIntKnotY, N0, N1, DK, L0, L1, Fi, Fj, Fpq,
+                  SEPARATE_SCALING, ScaSpType, ScaIntKnotX, ScaIntKnotY, DS, ScaFi, ScaFj):
+        sXY_q = np.asarray(self.XY_q).astype(float)
+        sXY_q[:, 0] /= N0
+        sXY_q[:, 1] /= N1
+        SfftKerDict, SfftScaDict = Read_SFFTSolution().FromArray(
+            Solution=Solution, KerSpType=KerSpType, N0=N0, N1=N1, DK=DK, L0=L0, L1=L1, Fi=Fi, Fj=Fj, Fpq=Fpq,
+            SEPARATE_SCALING=SEPARATE_SCALING, ScaSpType=ScaSpType, DS=DS, ScaFi=ScaFi, ScaFj=ScaFj)
+        w0, w1 = (L0 - 1) // 2, (L1 - 1) // 2
+        U, V, fu, fv = _basis_tables(KerSpType, DK, KerIntKnotX, KerIntKnotY, N0, N1, sXY_q[:, 0], sXY_q[:, 1])
+        KerBASE = U[fu] * V[fv]                                                        # (Fij, NPOINT)
+        KerCOEFF = np.array([SfftKerDict[(int(i), int(j))] for i, j in zip(fu, fv)])   # (Fij, L0, L1)
+        KerStack = np.tensordot(KerBASE, KerCOEFF, (0, 0))                             # (NPOINT, L0, L1)
+        # modified-delta -> kernel pixels: every non-centre tap also subtracts from the centre (:4619-4660)
+        if SfftScaDict is None:
+            KerCENT = KerStack[:, w0, w1].copy()
+            KerCENT -= np.sum(KerStack, axis=(1, 2)) - KerStack[:, w0, w1]
+            KerStack[:, w0, w1] = KerCENT
+        else:
+            U, V, fu, fv = _basis_tables(ScaSpType, DS, ScaIntKnotX, ScaIntKnotY, N0, N1, sXY_q[:, 0], sXY_q[:, 1])
+            ScaBASE = U[fu] * V[fv]
+            ScaCOEFF = np.array([SfftScaDict[(int(i), int(j))] for i, j in zip(fu, fv)])
+            KerCENT = np.matmul(ScaCOEFF.reshape((1, -1)), ScaBASE)[0]
+            KerCENT -= np.nansum(KerStack, axis=(1, 2))
+            KerStack[:, w0, w1] = KerCENT
+        return KerStack
+
+    def FromFITS(self, FITS_Solution):
+        Solution, d = _solution_header(FITS_Solution)
+        return self.FromArray(Solution=Solution, KerSpType=d['KerSpType'], KerIntKnotX=d['KerIntKnotX'], KerIntKnotY=d['KerIntKnotY'],
+                              N0=d['N0'], N1=d['N1'], DK=d['DK'], L0=d['L0'], L1=d['L1'], Fi=d['Fi'], Fj=d['Fj'], Fpq=d['Fpq'],
+                              SEPARATE_SCALING=d['SEPARATE_SCALING'], ScaSpType=d['ScaSpType'], ScaIntKnotX=d['ScaIntKnotX'],
+                              ScaIntKnotY=d['ScaIntKnotY'], DS=d['DS'], ScaFi=d['ScaFi'], ScaFj=d['ScaFj'])
+
+
+class ConvKernel_Convertion:
+    """CSZ / iCSZ of :4725-4753 (iCSZ returns the lost weight here, unlike sfft/utils/ConvKernelConvertion.py)."""
+
+    def CSZ(ConvKernel, N0, N1):
+        L0, L1 = ConvKernel.shape
+        w0, w1 = (L0 - 1) // 2, (L1 - 1) // 2
+        TailZP = np.pad(ConvKernel, ((0, N0 - L0), (0, N1 - L1)), 'constant', constant_values=(0, 0))
+        return np.roll(np.roll(TailZP, -w0, axis=0), -w1, axis=1)
+
+    def iCSZ(KIMG, L0, L1):
+        w0, w1 = (L0 - 1) // 2, (L1 - 1) // 2
+        KIMG_iCSZ = np.roll(np.roll(KIMG, w1, axis=1), w0, axis=0)
+        ConvKernel = KIMG_iCSZ[:L0, :L1]
+        return ConvKernel, 1.0 - np.sum(np.abs(ConvKernel)) / np.sum(np.abs(KIMG_iCSZ))
+
+
+class BSpline_DeCorrelation:
+    @staticmethod
+    def BDC(MK_JLst, SkySig_JLst, MK_ILst=[], SkySig_ILst=[], MK_Fin=None, KERatio=2.0, DENO_CLIP_RATIO=100000.0, VERBOSE_LEVEL=2,
+            CUDA_DEVICE='0'):
+        """DeCorrelation_Calculator.DCC with the denominator clipped from below at max / DENO_CLIP_RATIO (:4757-4868)."""
+        from .utils.DeCorrelationCalculator import DeCorrelation_Calculator
+        return DeCorrelation_Calculator.DCC(MK_JLst, SkySig_JLst, MK_ILst=MK_ILst, SkySig_ILst=SkySig_ILst, MK_Fin=MK_Fin, KERatio=KERatio,
+                                            VERBOSE_LEVEL=VERBOSE_LEVEL, CUDA_DEVICE=CUDA_DEVICE, _CLIP_RATIO=float(DENO_CLIP_RATIO))
