@@ -1,6 +1,8 @@
 """PureCupy_FFTKits (sfft/utils/PureCupyFFTKits.py:37-105) for device-resident arrays (torch CUDA tensors stand where the
 reference has CuPy arrays): KERNEL_CSZ / KERNEL_CSZ_INV are index bookkeeping, FFT_CONVOLVE runs sfftb_convolve -- the
-convolution with the zero (constant) padding and NaN fill of the reference, evaluated directly in real space."""
+convolution with the zero (constant) padding and NaN fill of the reference, evaluated directly in real space.  One
+difference by construction: with NAN_FILL_VALUE=None a NaN sample spoils only the kernel footprint around it, where the
+reference's FFT product returns an all-NaN image."""
 import numpy as np
 
 from .. import _lib as B
