@@ -27,6 +27,9 @@
 #define FS4_NWK (2 * FS4_NTW)     // half-warp transform workers
 #define FS4_NHW (2 * (FS4_NT / 32))   // half warps of the CTA (inverse phase)
 #define FS4_PITCH H16_SCRATCH         // elements per spectrum plane
+#ifndef FS4_BULK
+#define FS4_BULK 1                    // window ring filled by cp.async.bulk (0: per-element cp.async of the product threads)
+#endif
 #ifndef FS4_NSTG
 #define FS4_NSTG 8                    // window ring depth for fp32-stored spectra (prefetch distance NSTG - 2 segments); fp64: 4
 #endif
@@ -42,6 +45,18 @@ static inline size_t fs4_smem_bytes(int DK, bool f32) {
     const int planes = std::max((f32 ? FS4_NSLOT32 : 2) * NP, NACC);
     return sizeof(cd) * ((size_t)planes * FS4_PITCH + (DK == 3 ? 5 : 4) * SFFTB_MAXE) + 128 +
            (f32 ? sizeof(float2) * FS4_NSTG : sizeof(double2) * 4) * (size_t)(DK + 2) * FS3_M;
+}
+
+// TMA-style bulk copies (cp.async.bulk, the 1-D form of the tensor memory accelerator's copy engine): a 256-row window of a
+// stored plane is one contiguous 2 KB (fp32) / 4 KB (fp64) piece of a column, so ONE elected thread requests the whole window
+// ring slot -- (DK + 2) planes, two pieces where the window wraps around the column ends -- and the bytes are counted on the
+// slot's mbarrier (expect_tx / complete_tx).  The product warps issue no per-element cp.async any more.
+__device__ __forceinline__ void fs4_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fs3_saddr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fs4_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(fs3_saddr(dst)), "l"(src), "r"(bytes), "r"(fs3_saddr(b)) : "memory");
 }
 
 // Wait until window `seg` (global segment number) of the cp.async ring has landed.  The mbarrier answers "has the phase
@@ -178,9 +193,13 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
     const double inv0 = 1.0 / (double)a.N0;
     const int h = fa.h, S = fa.S, nseg = fa.nseg;
 
+    // bulk window copies need 16-byte aligned pieces (even N0 for 8-byte elements) and at most one wrap per window
+    const bool bulk = a.N0 >= FS3_M && (sizeof(TSt) == 16 || a.N0 % 2 == 0) && FS4_BULK;
     if (tid == 0) {
         for (int b = 0; b < NSLOT; ++b) fs3_mbar_init(full + b, NP);
-        for (int b = 0; b < NSTG; ++b) fs3_mbar_init(landed + b, 256);
+        for (int b = 0; b < NSTG; ++b) fs3_mbar_init(landed + b, bulk ? 1 : 256);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");       // the copy engine (async proxy) completes bytes on them
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (tid < 8) cons[tid] = 0u;
     // the engine's twiddle tables live in shared memory: with ~200 KB of shared memory carved out there is next to
@@ -205,6 +224,28 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
             // boundary (the first windows of the CTA's next column are requested during the last segments of this one)
             auto issue = [&](int kx, int gx, int s) {
                 const int buf = (gx + s) & (NSTG - 1);
+                if (bulk) {
+                    if (tid == 0) {
+                        const int r0 = s * S - h;
+                        fs4_expect_tx(landed + buf, (unsigned)(NSRC * FS3_M * sizeof(TSt)));
+#pragma unroll
+                        for (int jj = 0; jj < NSRC; ++jj) {
+                            const TSt* col = (jj == DK + 1) ? gJ + (size_t)kx * a.N0 : gI + ((size_t)jj * a.NH + kx) * a.N0;
+                            TSt* dst = stage + ((size_t)buf * NSRC + jj) * FS3_M;
+                            if (r0 < 0) {
+                                fs4_bulk_g2s(dst, col + a.N0 + r0, (unsigned)(-r0 * (int)sizeof(TSt)), landed + buf);
+                                fs4_bulk_g2s(dst - r0, col, (unsigned)((FS3_M + r0) * (int)sizeof(TSt)), landed + buf);
+                            } else if (r0 + FS3_M > a.N0) {
+                                const int n1 = a.N0 - r0;
+                                fs4_bulk_g2s(dst, col + r0, (unsigned)(n1 * (int)sizeof(TSt)), landed + buf);
+                                fs4_bulk_g2s(dst + n1, col, (unsigned)((FS3_M - n1) * (int)sizeof(TSt)), landed + buf);
+                            } else {
+                                fs4_bulk_g2s(dst, col + r0, (unsigned)(FS3_M * sizeof(TSt)), landed + buf);
+                            }
+                        }
+                    }
+                    return;
+                }
                 const int r = wrap_row(s * S - h + tid, a.N0);
 #pragma unroll
                 for (int jj = 0; jj < NSRC; ++jj) {
