@@ -51,8 +51,8 @@ def c3_spec(N0, N1):
                 SEPARATE_SCALING=True, ScaSpType='Polynomial', ScaSpDegree=2, BkgSpType='Polynomial', BkgSpDegree=2)
 DEFAULT_WORKLOAD = 'c2_4096_w8_dk2_db2_fp32'
 # device leg: pairs in flight (one plan + stream each) and the SMs set aside for the Cholesky (sfftb_plan_set_partition)
-PIPE_DEPTH = int(os.environ.get('SFFTB_BENCH_DEPTH', '3'))
-SOLVER_SMS = int(os.environ.get('SFFTB_BENCH_SOLVER_SMS', '16'))
+PIPE_DEPTH = int(os.environ.get('SFFTB_BENCH_DEPTH', '4'))
+SOLVER_SMS = int(os.environ.get('SFFTB_BENCH_SOLVER_SMS', '20'))
 HBM_FALLBACK_GBS = 6650.0     # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
@@ -749,13 +749,14 @@ def main():
     ms_e2e_full, ms_e2e_delta, delta_bytes = None, None, 0
     if not shared and not args.no_pipeline:
         from sfft_b200.batch import PairPipeline
-        pipe = PairPipeline(N0, N1, w, DK, DB, True, device=local, storage=storage, stream_ptr=stream.cuda_stream)
-        diff_hs = [diff_h, torch.empty((N0, N1), dtype=tdt).pin_memory()]
-        sol_hs = [torch.empty(plan.NEQ, dtype=torch.float64).pin_memory() for _ in range(2)]
+        E2E_DEPTH = int(os.environ.get('SFFTB_BENCH_E2E_DEPTH', '3'))
+        pipe = PairPipeline(N0, N1, w, DK, DB, True, device=local, storage=storage, depth=E2E_DEPTH, solver_sms=SOLVER_SMS)
+        diff_hs = [diff_h] + [torch.empty((N0, N1), dtype=tdt).pin_memory() for _ in range(E2E_DEPTH - 1)]
+        sol_hs = [torch.empty(plan.NEQ, dtype=torch.float64).pin_memory() for _ in range(E2E_DEPTH)]
 
         def step_pipe(k):
-            pipe.submit(host['REF'], host['SCI'], host['mREF'], host['mSCI'], Solution_out=sol_hs[k % 2], DIFF_out=diff_hs[k % 2])
-        for k in range(3):
+            pipe.submit(host['REF'], host['SCI'], host['mREF'], host['mSCI'], Solution_out=sol_hs[k % E2E_DEPTH], DIFF_out=diff_hs[k % E2E_DEPTH])
+        for k in range(E2E_DEPTH + 1):
             step_pipe(k)
         pipe.drain()
         barrier()
@@ -770,7 +771,7 @@ def main():
         # the copies run on the plans' copy streams, so the honest clock is the host's (submit of the first step ->
         # last result in host memory); the events on the compute stream are kept as a cross-check
         ms_e2e_full = max(wall_ms, e2.elapsed_time(e3) / KE)
-        ms_e2e, e2e_mode = ms_e2e_full, 'PairPipeline: sfftb_gss_submit/finish on two plans, copies of step k+1 under step k'
+        ms_e2e, e2e_mode = ms_e2e_full, 'PairPipeline: sfftb_gss_submit/finish on %d plans (own streams, SM partition), copies of step k+1 under step k' % E2E_DEPTH
         # the same steps with the masked pair sent as sparse deltas against the unmasked pair (sfftb_gss_submit_delta): the
         # masked images differ from the unmasked ones only inside the masked stamps, so two images instead of four cross
         # the link; the deltas are part of the step's input and are copied inside the timed region like the images
@@ -782,8 +783,8 @@ def main():
         delta_bytes = sum(a.nbytes for a in dI + dJ)
 
         def step_delta(k):
-            pipe.submit_delta(host['REF'], host['SCI'], dI, dJ, Solution_out=sol_hs[k % 2], DIFF_out=diff_hs[k % 2])
-        for k in range(3):
+            pipe.submit_delta(host['REF'], host['SCI'], dI, dJ, Solution_out=sol_hs[k % E2E_DEPTH], DIFF_out=diff_hs[k % E2E_DEPTH])
+        for k in range(E2E_DEPTH + 1):
             step_delta(k)
         pipe.drain()
         barrier()
@@ -871,7 +872,7 @@ def main():
         if ms_e2e_delta:
             h2d_delta = 2 * N0 * N1 * esz + delta_bytes
             e2e_obj = {'value': world * mpix / (ms_e2e_delta / 1e3), 'unit': 'Mpix/s', 'ms_per_step': ms_e2e_delta,
-                       'mode': 'PairPipeline.submit_delta: sfftb_gss_submit_delta / sfftb_gss_finish on two plans (I, J + sparse deltas of '
+                       'mode': 'PairPipeline.submit_delta: sfftb_gss_submit_delta / sfftb_gss_finish on %d plans, own streams, SM partition (I, J + sparse deltas of ' % E2E_DEPTH +
                                'mI, mJ in, DIFF + Solution out; copies of step k+1 under step k)',
                        'h2d_bytes_per_step': h2d_delta, 'd2h_bytes_per_step': d2h}
             if probe:

@@ -34,7 +34,11 @@ def run(depth, sms, K=24, env=None, timing=False):
     pipe.close()
     for k in (env or {}): os.environ.pop(k)
 import sys as _s
-if len(_s.argv) > 1 and _s.argv[1] == 'timing':
+if len(_s.argv) > 1 and _s.argv[1] == 'sweep2':
+    for sms in (11, 18, 19, 20, 21, 22, 24, 28, 32):
+        run(3, sms)
+    run(4, 20); run(2, 20)
+elif len(_s.argv) > 1 and _s.argv[1] == 'timing':
     run(2, 0); run(3, 16); run(3, 16, timing=True); run(2, 16, timing=True); run(1, 0, timing=True)
     print(pipe_t if 0 else '')
 else:
