@@ -111,6 +111,23 @@ __device__ __forceinline__ void fs4_inverse_job(const SegFitArgs& fa, const H16T
 // reduction.  fit_seg3_kernel sums them from the staged windows inside its product warps; here they are a kernel of their own
 // (0.05 ms at 4096^2), which takes 40 % of the instructions, 42 registers and the read-modify-write traffic out of the product
 // loop.  nms = planes-per-column stride * SFFTB_MAXE of the fit kernel's layout; jonly: the moments of J only.
+template <int NE, typename TSt>
+__device__ __forceinline__ void col_moments_sum(const TSt* __restrict__ col, int N0, int lane, cd (&m)[SFFTB_MAXE]) {
+    const double inv0 = 1.0 / (double)N0;
+    double rd = (double)(lane + 1);                      // r + 1 as a double: exact, and no int -> double conversion per row
+#pragma unroll 4
+    for (int r = lane; r < N0; r += 32, rd += 32.0) {
+        const cd g = load_c(col + r);
+        const double cx = rd * inv0;
+        double pw = 1.0;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            m[e].x = fma(g.x, pw, m[e].x); m[e].y = fma(g.y, pw, m[e].y);
+            if (e + 1 < NE) pw *= cx;
+        }
+    }
+}
+
 template <typename TSt>
 __global__ void __launch_bounds__(256) col_moments_kernel(int N0, int NH, int DK, int DB, int nms, int jonly, const TSt* __restrict__ gI,
                                                           const TSt* __restrict__ gJ, cd* __restrict__ momg)
@@ -121,20 +138,18 @@ __global__ void __launch_bounds__(256) col_moments_kernel(int N0, int NH, int DK
     const int k1 = gw / nsrc, jj = gw - k1 * nsrc;
     if (jonly && jj != DK + 1) return;
     const TSt* col = (jj == DK + 1) ? gJ + (size_t)k1 * N0 : gI + ((size_t)jj * NH + k1) * N0;
-    const int ne = (jj == DK + 1) ? DB + 1 : DK - jj + DB + 1;
-    const double inv0 = 1.0 / (double)N0;
+    const int ne = (jj == DK + 1) ? DB + 1 : DK - jj + DB + 1;      // uniform per warp: the row loop is compiled per count
     cd m[SFFTB_MAXE];
 #pragma unroll
     for (int e = 0; e < SFFTB_MAXE; ++e) m[e] = cmake(0.0, 0.0);
-#pragma unroll 4
-    for (int r = lane; r < N0; r += 32) {
-        const cd g = load_c(col + r);
-        const double cx = (double)(r + 1) * inv0;
-        double pw = 1.0;
-#pragma unroll
-        for (int e = 0; e < SFFTB_MAXE; ++e) {
-            if (e < ne) { m[e].x = fma(g.x, pw, m[e].x); m[e].y = fma(g.y, pw, m[e].y); pw *= cx; }
-        }
+    switch (ne) {
+        case 1: col_moments_sum<1>(col, N0, lane, m); break;
+        case 2: col_moments_sum<2>(col, N0, lane, m); break;
+        case 3: col_moments_sum<3>(col, N0, lane, m); break;
+        case 4: col_moments_sum<4>(col, N0, lane, m); break;
+        case 5: col_moments_sum<5>(col, N0, lane, m); break;
+        case 6: col_moments_sum<6>(col, N0, lane, m); break;
+        default: col_moments_sum<7>(col, N0, lane, m); break;
     }
 #pragma unroll
     for (int e = 0; e < SFFTB_MAXE; ++e) {
