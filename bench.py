@@ -284,6 +284,7 @@ def c3_make(name, rank):
 def run_c3(args, world, rank, local, numa):
     """BASELINE config 3: 6144^2 pair, B-spline spatially varying kernel through sfft_b200.BSplineSFFT (general-basis
     plan).  Same JSON contract as the default workload; every rank owns a pair (weak scaling, no collective)."""
+    stage_overlapped, serial_ms = None, None           # (general-basis plans run one pair at a time)
     import torch
     import torch.distributed as dist
     from sfft_b200 import _lib as B
@@ -629,7 +630,10 @@ def main():
     # Cholesky of pair k runs on SOLVER_SMS SMs while the row and column passes of pair k + 1 run on the others.  Every pair
     # is a complete GSS (fit + apply) with its own outputs; results are bit-identical to one pair at a time.
     ppipe = None
-    if not shared and not args.no_pipeline:
+    global PIPE_DEPTH, SOLVER_SMS
+    big = N0 * N1 > 8192 * 8192 and 'SFFTB_BENCH_DEPTH' not in os.environ
+    # (16384^2: the solve is < 10 % of a pair, a plan holds ~25 GB, and two pairs in flight measured slower: 110 vs 88 ms)
+    if not shared and not args.no_pipeline and not big:
         plans = [plan] + [Plan(N0, N1, w, w, DK, DB, True, device=local, storage=storage) for _ in range(PIPE_DEPTH - 1)]
         for pl in plans:
             pl.set_stream(0)
