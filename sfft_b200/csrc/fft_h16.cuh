@@ -30,6 +30,17 @@ __device__ __forceinline__ void h16_load(H16Tw& t, const cd* __restrict__ tabA, 
     t.w1 = tabA[hl]; t.w2 = tabA[16 + hl]; t.w4 = tabA[48 + hl]; t.w8 = tabA[112 + hl];
 }
 
+// v[r] *= w^r, r = 1 .. 15, from the powers w^1, w^2, w^4, w^8: eleven more products, at most two per power
+__device__ __forceinline__ void h16_twiddle(cd (&v)[16], cd w1, cd w2, cd w4, cd w8) {
+    const cd w3 = cmul(w1, w2);
+    v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
+    const cd w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
+    v[5] = cmul(v[5], w5); v[6] = cmul(v[6], w6); v[7] = cmul(v[7], w7); v[8] = cmul(v[8], w8);
+    v[9] = cmul(v[9], cmul(w8, w1)); v[10] = cmul(v[10], cmul(w8, w2)); v[11] = cmul(v[11], cmul(w8, w3));
+    v[12] = cmul(v[12], cmul(w8, w4)); v[13] = cmul(v[13], cmul(w8, w5)); v[14] = cmul(v[14], cmul(w8, w6));
+    v[15] = cmul(v[15], cmul(w8, w7));
+}
+
 // sgn = -1 forward, +1 unnormalised inverse.  scratch: H16_SCRATCH elements private to this half warp.
 // live = false: a half warp without a job keeps the lockstep (same instruction stream, __syncwarp) but touches no memory.
 __device__ __forceinline__ void hfft256(cd (&v)[16], cd* scratch, int hl, const H16Tw& tw, double sgn, bool live = true) {
@@ -44,16 +55,6 @@ __device__ __forceinline__ void hfft256(cd (&v)[16], cd* scratch, int hl, const 
         for (int q = 0; q < 16; ++q) v[q] = scratch[HPAD(hl + 16 * q)];
     }
     __syncwarp();
-    const cd w1 = cmake(tw.w1.x, -sgn * tw.w1.y), w2 = cmake(tw.w2.x, -sgn * tw.w2.y);
-    const cd w4 = cmake(tw.w4.x, -sgn * tw.w4.y), w8 = cmake(tw.w8.x, -sgn * tw.w8.y);
-    const cd w3 = cmul(w1, w2);
-    v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
-    {
-        const cd w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
-        v[5] = cmul(v[5], w5); v[6] = cmul(v[6], w6); v[7] = cmul(v[7], w7); v[8] = cmul(v[8], w8);
-        v[9] = cmul(v[9], cmul(w8, w1)); v[10] = cmul(v[10], cmul(w8, w2)); v[11] = cmul(v[11], cmul(w8, w3));
-        v[12] = cmul(v[12], cmul(w8, w4)); v[13] = cmul(v[13], cmul(w8, w5)); v[14] = cmul(v[14], cmul(w8, w6));
-        v[15] = cmul(v[15], cmul(w8, w7));
-    }
+    h16_twiddle(v, cmake(tw.w1.x, -sgn * tw.w1.y), cmake(tw.w2.x, -sgn * tw.w2.y), cmake(tw.w4.x, -sgn * tw.w4.y), cmake(tw.w8.x, -sgn * tw.w8.y));
     butterfly16(v, sgn);
 }

@@ -167,3 +167,97 @@ __global__ void __launch_bounds__(ROWH_NT, 1) row_fwd_h16_kernel(RowH16Args a, c
         }
     }
 }
+
+// ---- H = 8192 (N1 = 16384): 32 x 256 ---------------------------------------------------------------------------------------------
+// One row per CTA (512 threads).  Thread t owns b = t >> 1 and the sixteen a = 2 a' + p of parity p = t & 1: a thread-local
+// radix-16 over a', then the radix-2 step X[c'] = E_0[c'] + W32^{c'} E_1[c'], X[c' + 16] = E_0[c'] - W32^{c'} E_1[c'] with the
+// neighbouring lane (shuffles), twiddles W_H^{b c}, planes c = c' + 16 p; pass B and the untangle step as above (32 half warps,
+// 32 planes).  The untangle factors are read from global memory (the planes take the shared memory).
+// cos / sin of 2 pi c / 32, c = 0 .. 15 (compile-time constants of the unrolled radix-2 step)
+__device__ constexpr double ROWH_W32C[16] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708, 0.70710678118654752440,
+                                  0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785, 0.0, -0.19509032201612826785,
+                                  -0.38268343236508977173, -0.55557023301960222474, -0.70710678118654752440, -0.83146961230254523708,
+                                  -0.92387953251128675613, -0.98078528040323044913};
+__device__ constexpr double ROWH_W32S[16] = {0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474, 0.70710678118654752440,
+                                  0.83146961230254523708, 0.92387953251128675613, 0.98078528040323044913, 1.0, 0.98078528040323044913,
+                                  0.92387953251128675613, 0.83146961230254523708, 0.70710678118654752440, 0.55557023301960222474,
+                                  0.38268343236508977173, 0.19509032201612826785};
+static inline size_t rowh32_smem_bytes() { return sizeof(cd) * ((size_t)32 * ROWH_PP + 4 + 5 * 256); }
+
+template <typename TIn, typename TSt>
+__global__ void __launch_bounds__(ROWH_NT, 1) row_fwd_h16x32_kernel(RowH16Args a, const TIn* __restrict__ img, TSt* __restrict__ out, int nj)
+{
+    constexpr int R = 32, H = 8192;
+    typedef typename In2<TIn>::type TIn2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd* zrow = reinterpret_cast<cd*>(smem_raw);              // [32 planes][ROWH_PP]
+    cd* twp = zrow + (size_t)R * ROWH_PP + 4;                // [5][256]: W_H^{b 2^l}
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 5 * 256; i += ROWH_NT) {
+        const int l = i >> 8, b = i & 255;
+        twp[i] = a.twP[(size_t)((1 << l) - 1) * 256 + b];
+    }
+    const int b = tid >> 1, par = tid & 1;
+    const int lane = tid & 31, half = lane >> 4, hl = lane & 15;
+    const int cpl = 2 * (tid >> 5) + half;                   // plane / sub-transform of this half warp
+    H16Tw htw;
+    h16_load(htw, a.tabA, hl);
+    __syncthreads();
+    const double inv1 = 1.0 / (double)a.N1;
+    for (int r = blockIdx.x; r < a.N0; r += gridDim.x) {
+        for (int j = 0; j < nj; ++j) {
+            cd v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int n = 256 * (2 * q + par) + b;
+                const TIn2 x = *reinterpret_cast<const TIn2*>(img + (size_t)r * a.N1 + 2 * n);
+                double x0 = (double)x.x, x1 = (double)x.y;
+                if (a.vtab) {
+                    const double2 vv = *reinterpret_cast<const double2*>(a.vtab + (size_t)j * a.N1 + 2 * n);
+                    x0 *= vv.x; x1 *= vv.y;
+                } else if (j > 0) {
+                    const double c0 = (2 * n + 1) * inv1, c1 = (2 * n + 2) * inv1;
+                    x0 *= (j == 1) ? c0 : (j == 2 ? c0 * c0 : c0 * c0 * c0);
+                    x1 *= (j == 1) ? c1 : (j == 2 ? c1 * c1 : c1 * c1 * c1);
+                }
+                v[q] = cmake(x0, x1);
+            }
+            butterfly16(v, -1.0);                                  // E_par[c'], c' = 0 .. 15
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const double ox = __shfl_xor_sync(0xffffffffu, v[c].x, 1), oy = __shfl_xor_sync(0xffffffffu, v[c].y, 1);
+                const cd e0 = par ? cmake(ox, oy) : v[c], e1 = par ? v[c] : cmake(ox, oy);
+                const cd we = cmake(e1.x * ROWH_W32C[c] + e1.y * ROWH_W32S[c], e1.y * ROWH_W32C[c] - e1.x * ROWH_W32S[c]);     // e1 * exp(-2 pi i c / 32)
+                v[c] = par ? csub(e0, we) : cadd(e0, we);          // X[c] (par = 0) or X[c + 16] (par = 1)
+            }
+            if (par) {
+                const cd w16 = twp[4 * 256 + b];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) v[c] = cmul(v[c], w16);
+            }
+            h16_twiddle(v, twp[b], twp[256 + b], twp[512 + b], twp[768 + b]);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) zrow[(c + 16 * par) * ROWH_PP + HPAD(b)] = v[c];
+            __syncthreads();
+            cd* plane = zrow + cpl * ROWH_PP;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = plane[HPAD(hl + 16 * q)];
+            __syncwarp();
+            hfft256(v, plane, hl, htw, -1.0);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) plane[HPAD(hl + 16 * q)] = v[q];        // X[cpl + 32 (hl + 16 q)]
+            __syncthreads();
+            for (int k = tid; k <= H / 2; k += ROWH_NT) {
+                const cd w = a.tw1[k];
+                const int km = (H - k) & (H - 1);
+                const cd A = zrow[(k & (R - 1)) * ROWH_PP + HPAD(k / R)];
+                const cd B = zrow[(km & (R - 1)) * ROWH_PP + HPAD(km / R)];
+                const cd s = cmake(A.x + B.x, A.y - B.y), d = cmake(A.x - B.x, A.y + B.y);
+                const cd wd = cmul(w, d);
+                store_c(out + ((size_t)j * a.NH + k) * a.N0 + r, cmake(0.5 * (s.x + wd.y), 0.5 * (s.y - wd.x)));
+                if (k != H - k) store_c(out + ((size_t)j * a.NH + (H - k)) * a.N0 + r, cmake(0.5 * (s.x - wd.y), 0.5 * (-s.y - wd.x)));
+            }
+            __syncthreads();
+        }
+    }
+}

@@ -72,6 +72,7 @@ struct sfftb_plan {
     // tables
     cd *tw0, *tw1, *twMf, *twH, *Q;
     cd *tabA, *tabB_row, *tabC_row;   // register-engine twiddle tables
+    cd* tabC_row32;                   // exp(-2 pi i r k / 8192), [(r-1) 256 + k]: pass-A twiddles of the 32 x 256 row pass
     cd *vt8_8, *vt64_8, *vt64_4, *vt256_4, *vt512_4;   // 8-values-per-thread engine tables
     RowV8Args rowv;
     VTabs vtabs;

@@ -48,6 +48,16 @@ int rows_setup(sfftb_plan* p) {
         p->row_v8 = r.H;
     }
     p->row_h16 = 0;
+    if (p->row_fast && !env_int("SFFTB_ROW_NOH16", 0) && r.H == 8192 && rowh32_smem_bytes() <= p->max_smem) {
+        RowH16Args& rh = p->rowh;
+        rh.N0 = d.N0; rh.N1 = d.N1; rh.NH = d.N1 / 2 + 1; rh.H = r.H;
+        if (upload_engine_table(256, 32, &p->tabC_row32)) return SFFTB_ECUDA;
+        rh.tabA = p->tabA; rh.twP = p->tabC_row32; rh.tw1 = p->tw1; rh.vtab = nullptr;
+        const size_t smh = rowh32_smem_bytes();
+        if (f32 && (set_smem(row_fwd_h16x32_kernel<float, float2>, smh) || set_smem(row_fwd_h16x32_kernel<double, float2>, smh))) return SFFTB_ECUDA;
+        if (set_smem(row_fwd_h16x32_kernel<float, double2>, smh) || set_smem(row_fwd_h16x32_kernel<double, double2>, smh)) return SFFTB_ECUDA;
+        p->row_h16 = r.H;
+    }
     if (p->row_fast && !env_int("SFFTB_ROW_NOH16", 0) && (r.H == 1024 || r.H == 2048 || r.H == 4096) && rowh_smem_bytes(r.H) <= p->max_smem) {
         RowH16Args& rh = p->rowh;
         rh.N0 = d.N0; rh.N1 = d.N1; rh.NH = d.N1 / 2 + 1; rh.H = r.H;
@@ -83,6 +93,15 @@ int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj, 
     RowFastArgs rowf = p->rowf; rowf.vtab = vtab;
     RowArgs rowg = p->row; rowg.vtab = vtab;
     const size_t esz2 = dtype == SFFTB_F64 ? 16 : 8;
+    if (p->row_h16 == 8192 && ((uintptr_t)img % esz2) == 0) {
+        RowH16Args rowh = p->rowh; rowh.vtab = vtab;
+        const int grid = std::min(p->d.N0, (p->row_grid_limit > 0 ? p->row_grid_limit : work_sms(p)));
+        const size_t smh = rowh32_smem_bytes();
+        if (dtype == SFFTB_F64) row_fwd_h16x32_kernel<double, TSt><<<grid, ROWH_NT, smh, p->stream>>>(rowh, (const double*)img, out, nj);
+        else row_fwd_h16x32_kernel<float, TSt><<<grid, ROWH_NT, smh, p->stream>>>(rowh, (const float*)img, out, nj);
+        CKL(p);
+        return 0;
+    }
     if (p->row_h16 && ((uintptr_t)img % esz2) == 0) {
         RowH16Args rowh = p->rowh; rowh.vtab = vtab;
         const int H = p->row_h16, RBI = ROWH_NT / (H / 16);
