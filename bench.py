@@ -883,6 +883,15 @@ def main():
                 b2 = max(h2d_delta / (probe['h2d_gbs_per_gpu'] * 1e6), d2h / (probe['d2h_gbs_per_gpu'] * 1e6))
                 e2e_obj['link_bound_ms_per_step'] = b2
                 e2e_obj['frac_of_link_bound'] = b2 / ms_e2e_delta
+                # both directions are busy in a pipeline: while the difference image goes home each way only gets the duplex
+                # rate the probe measured (at N = 8 the host side of this box gives 8 GB/s each way per GPU against 23 / 12
+                # one way), the rest of the input then moves at the one-way rate
+                dup = probe['duplex_each_way_gbs_per_gpu'] * 1e6
+                small, big_ = min(h2d_delta, d2h), max(h2d_delta, d2h)
+                one_way = (probe['h2d_gbs_per_gpu'] if h2d_delta >= d2h else probe['d2h_gbs_per_gpu']) * 1e6
+                b3 = small / dup + (big_ - small) / one_way
+                e2e_obj['duplex_link_bound_ms_per_step'] = b3
+                e2e_obj['frac_of_duplex_link_bound'] = b3 / ms_e2e_delta
             e2e_obj['four_image_form'] = four
         e2e_obj.update({'steps': KE, 'single_call_ms': ms_e2e_single, 'single_call_value': world * mpix / (ms_e2e_single / 1e3),
                         'host_numa_node': numa})
