@@ -395,7 +395,7 @@ def run_c3(args, world, rank, local, numa):
                     'mode': 'one blocking sfftb_gss call per step (host buffers)', 'h2d_bytes_per_step': 4 * N0 * N1 * esz,
                     'd2h_bytes_per_step': N0 * N1 * esz + plan.NEQ * 8, 'host_numa_node': numa},
             'gpu_launches': launches,
-            'roofline': {'bound': 'hbm', 'kernel': 'fit_gen_kernel', 'achieved': achieved, 'peak': peak, 'peak_source': which, 'unit': 'GB/s',
+            'roofline': {'bound': 'hbm', 'kernel': 'fit_gen4_kernel', 'achieved': achieved, 'peak': peak, 'peak_source': which, 'unit': 'GB/s',
                          'frac': (achieved / peak) if achieved else None, 'traffic': None,
                          'algorithmic_bytes_per_launch': alg_bytes / max(1, info['passes']), 'launches_per_step_of_kernel': info['passes'],
                          'kernel_ms': stage.get('fit_cols'), 'step_algorithmic_bytes': step_bytes,

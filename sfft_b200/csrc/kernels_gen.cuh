@@ -15,7 +15,7 @@
 // The background planes T_pq = P_p(r) Q_q(c) are never transformed: the B-role spectrum of the real sequence P_p is the
 // same for every column and comes from a table computed at plan creation; the factor DFT(Q_q)[k1] multiplies the lags.
 #pragma once
-#include "kernels_fit_seg3.cuh"
+#include "kernels_fit_seg4.cuh"
 
 #define GEN_NA 5
 #define GEN_NB 5
@@ -48,25 +48,61 @@ struct GenFitArgs {
     size_t plane_stride;             // elements between stored planes
 };
 
-// one pass of the general fit column kernel; same structure and synchronisation as fit_seg3_kernel
+// ---- one pass of the general fit column kernel on the half-warp FFT engine (fft_h16.cuh), structure of fit_seg4_kernel ----------------------------------------
+// 8 product warps (thread = frequency bin, GEN_NA x GEN_NB accumulators) + 8 transform warps = 16 half-warp workers; one
+// shared-memory exchange per 256-point transform instead of two; the window load is branch-free (the halves of a warp differ in
+// role and table); every needed accumulator gets a plane, so a column ends with ONE inverse batch on the 32 half warps.
+#define GEN_NPLANES 26               // >= 2 (GEN_NA + GEN_NB) ring planes and >= GEN_NA GEN_NB inverse planes
+static_assert(GEN_NPLANES >= 2 * (GEN_NA + GEN_NB) && GEN_NPLANES >= GEN_NA * GEN_NB, "planes of the general fit kernel");
+static inline size_t gen_fit4_smem_bytes(bool f32) {
+    return sizeof(cd) * (size_t)GEN_NPLANES * FS3_PITCH + 128 + (f32 ? sizeof(float2) * 8 : sizeof(double2) * 4) * (size_t)GEN_MAXSRC * FS3_M;
+}
+
+__device__ __forceinline__ void gen4_inverse_job(const GenFitArgs& fa, const GenPass& ps, const H16Tw& tw, cd* plane, int jb, int hl, bool active,
+                                                 int k1, cd* __restrict__ kaprow)
+{
+    cd v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = active ? plane[HPAD(hl + 16 * q)] : cmake(0.0, 0.0);
+    __syncwarp();
+    hfft256(v, plane, hl, tw, +1.0, active);
+    if (!active) return;
+    const int qq = ps.inv_q[jb];
+    const int b = qq % GEN_NB;
+    const int bt = ps.b_type[b];
+    const int lim = bt == 0 ? 2 * fa.w0 : fa.w0;
+    const int rowb = ps.rowbase[qq];
+    const double invM = 1.0 / (double)FS3_M;
+    const int p = ps.b_u[b], nlj0 = 2 * fa.w0 + 1;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int idx = hl + 16 * q;
+        const int m0 = idx < FS3_M / 2 ? idx : idx - FS3_M;
+        if (m0 >= -lim && m0 <= lim) {
+            const cd lam = cscale(v[q], invM);
+            if (bt != 2) kaprow[rowb + m0 + lim] = lam;
+            else
+                for (int t = 0; t < fa.tq_n[p]; ++t)
+                    kaprow[rowb + t * nlj0 + m0 + lim] = cmul(lam, fa.Q[(size_t)fa.tq_q[p][t] * fa.NH + k1]);
+        }
+    }
+}
+
 template <typename TSt>
-__global__ void __launch_bounds__(FS3_NT, 1) fit_gen_kernel(GenFitArgs fa, GenPass ps, VTabs vt_g, const TSt* __restrict__ gP,
-                                                            const TSt* __restrict__ gJ, cd* __restrict__ kap)
+__global__ void __launch_bounds__(FS4_NT, 1) fit_gen4_kernel(GenFitArgs fa, GenPass ps, const cd* __restrict__ tabA, const TSt* __restrict__ gP,
+                                                             const TSt* __restrict__ gJ, cd* __restrict__ kap)
 {
     constexpr int NA = GEN_NA, NB = GEN_NB, NACC = NA * NB;
-    constexpr int NPMAX = NA + NB, NPL = 2 * NPMAX;
+    constexpr int NPMAX = NA + NB;
     constexpr int NSTG = Fs3Ring<TSt>::depth, LOG2STG = NSTG == 8 ? 3 : 2, PFD = NSTG - 2;
-    static_assert(NPL >= 16, "ring too small for the inverse batches");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cd* spec = reinterpret_cast<cd*>(smem_raw);                                   // NPL planes
-    cd* tw8 = spec + NPL * FS3_PITCH;               // 56 entries  (Ns = 8,  R = 8)
-    cd* tw64 = tw8 + 56;                            // 192 entries (Ns = 64, R = 4)
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tw64 + 192);
+    cd* spec = reinterpret_cast<cd*>(smem_raw);                                   // GEN_NPLANES planes
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(spec + GEN_NPLANES * FS3_PITCH);
     unsigned* cons = reinterpret_cast<unsigned*>(bars + 12);      // [8] segments consumed by product warp w (fs3_publish)
     TSt* stage = reinterpret_cast<TSt*>(bars + 16);
     unsigned long long* full = bars;          // [2]  count NP   (one arrive per transform job)
     unsigned long long* landed = bars + 4;    // [NSTG] count 256  (cp.async arrivals of the product threads)
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, half = lane >> 4, hl = lane & 15;
     const int h = fa.h, S = fa.S, nseg = fa.nseg, N0 = fa.N0;
     const int NP = ps.na + ps.nbt;            // spectra per segment: A roles | transformed B roles
     const int nsrc = ps.nsrc;
@@ -76,17 +112,13 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_gen_kernel(GenFitArgs fa, GenPa
         for (int b = 0; b < NSTG; ++b) fs3_mbar_init(landed + b, 256);
     }
     if (tid < 8) cons[tid] = 0u;
-    for (int i = tid; i < 56; i += FS3_NT) tw8[i] = vt_g.t8_8[i];
-    for (int i = tid; i < 192; i += FS3_NT) tw64[i] = vt_g.t64_4[i];
-    for (int i = tid; i < NPL * FS3_PITCH; i += FS3_NT) spec[i] = cmake(0.0, 0.0);   // unused slots must stay finite
-    VTabs vt = vt_g;
-    vt.t8_8 = tw8; vt.t64_4 = tw64;
+    for (int i = tid; i < GEN_NPLANES * FS3_PITCH; i += FS4_NT) spec[i] = cmake(0.0, 0.0);   // unused slots must stay finite
     __syncthreads();
     int g = 0;                                // global segment counter (ring phases continue across columns)
 
     if (warp < 8) {
         // ======================================= product warps =======================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FS4_REGP));
         for (int k1 = blockIdx.x; k1 < fa.NH; k1 += gridDim.x, g += nseg) {
             cd acc[NACC];
 #pragma unroll
@@ -112,7 +144,7 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_gen_kernel(GenFitArgs fa, GenPa
                     fB[b] = (b < ps.nb && ps.b_type[b] == 2) ? fa.TF[((size_t)s * fa.Fp + ps.b_u[b]) * FS3_M + tid] : cmake(0.0, 0.0);
                 fs3_mbar_wait(full + slot, (gs >> 1) & 1);
                 {
-                    const cd* sp = spec + (size_t)slot * NPMAX * FS3_PITCH + VPAD(tid);
+                    const cd* sp = spec + (size_t)slot * NPMAX * FS3_PITCH + HPAD(tid);
                     cd fA[NA];
 #pragma unroll
                     for (int A = 0; A < NA; ++A) fA[A] = (A < ps.na) ? sp[A * FS3_PITCH] : cmake(0.0, 0.0);   // unused slots hold inverse-phase scratch
@@ -133,122 +165,78 @@ __global__ void __launch_bounds__(FS3_NT, 1) fit_gen_kernel(GenFitArgs fa, GenPa
                 if (s + PFD < nseg) issue(s + PFD);
             }
             fs3_bar0();                                    // (A) all transforms and products of the column are done
-            for (int b0 = 0; b0 < ps.ninv; b0 += 16) {
+            {
                 int pos = 0;
 #pragma unroll
                 for (int q = 0; q < NACC; ++q) {
-                    if (ps.rowbase[q] >= 0) {
-                        if (pos >= b0 && pos < b0 + 16) spec[(pos - b0) * FS3_PITCH + VPAD(tid)] = acc[q];
-                        ++pos;
-                    }
+                    if (ps.rowbase[q] >= 0) { spec[pos * FS3_PITCH + HPAD(tid)] = acc[q]; ++pos; }
                 }
-                fs3_bar0();
-                // (the inverse jobs are done by all 16 warps below)
-                {
-                    const int jb = b0 + warp;
-                    if (jb < ps.ninv) {
-                        cd* plane = spec + warp * FS3_PITCH;
-                        cd v[8];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] = plane[VPAD(lane + 32 * q)];
-                        __syncwarp();
-                        vfft<FS3_M>(v, plane, lane, vt, +1.0, 0);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) plane[VPAD(lane + 32 * q)] = v[q];
-                        __syncwarp();
-                        const int qq = ps.inv_q[jb];
-                        const int b = qq % NB;
-                        const int bt = ps.b_type[b];
-                        const int lim = bt == 0 ? 2 * fa.w0 : fa.w0;
-                        const int rowb = ps.rowbase[qq];
-                        const double invM = 1.0 / (double)FS3_M;
-                        if (bt != 2) {
-                            for (int l = lane; l <= 2 * lim; l += 32)
-                                kaprow[rowb + l] = cscale(plane[VPAD((l - lim) & (FS3_M - 1))], invM);
-                        } else {
-                            const int p = ps.b_u[b], nlj0 = 2 * fa.w0 + 1;
-                            for (int l = lane; l <= 2 * lim; l += 32) {
-                                const cd lam = cscale(plane[VPAD((l - lim) & (FS3_M - 1))], invM);
-                                for (int t = 0; t < fa.tq_n[p]; ++t)
-                                    kaprow[rowb + t * nlj0 + l] = cmul(lam, fa.Q[(size_t)fa.tq_q[p][t] * fa.NH + k1]);
-                            }
-                        }
-                    }
-                }
-                fs3_bar0();
             }
+            fs3_bar0();
+            {
+                H16Tw htw;
+                h16_load(htw, tabA, hl);
+                const int wk = 2 * warp + half;
+                const bool act = wk < ps.ninv;
+                if (__any_sync(0xffffffffu, act)) gen4_inverse_job(fa, ps, htw, spec + (act ? wk : 0) * FS3_PITCH, act ? wk : 0, hl, act, k1, kaprow);
+            }
+            fs3_bar0();
         }
     } else {
         // ====================================== transform warps ======================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FS4_REGT));
         const int fw = warp - 8;
+        const int njobs = nseg * NP;
+        H16Tw htw;
+        h16_load(htw, tabA, hl);
+        int seenL = 0;
         for (int k1 = blockIdx.x; k1 < fa.NH; k1 += gridDim.x, g += nseg) {
             cd* kaprow = kap + (size_t)k1 * fa.nrows;
-            for (int id = fw; id < nseg * NP; id += 8) {
+            for (int id0 = 2 * fw; id0 < njobs; id0 += FS4_NWK) {
+                const bool active = id0 + half < njobs;
+                const int id = active ? id0 + half : id0;
                 const int s = id / NP, p = id - s * NP;
                 const int gs = g + s, slot = gs & 1;
+                const int gsB = g + min(id0 + 1, njobs - 1) / NP;
                 const bool roleA = p < ps.na;
                 const int bs = p - ps.na;
                 const bool isJ = !roleA && ps.b_type[bs] == 1;
                 const int my_u = roleA ? ps.a_u[p] : ps.b_u[bs];
                 const int my_src = roleA ? ps.a_src[p] : ps.b_src[bs];
                 const int c0 = s * S, Sc = min(S, N0 - c0);
-                fs3_mbar_wait(landed + (gs & (NSTG - 1)), (gs >> LOG2STG) & 1);
-                if (gs >= 2) fs3_wait_consumed(cons, (unsigned)(gs - 1));
+                while (seenL <= gsB) { fs4_wait_landed(landed + (seenL & (NSTG - 1)), (seenL >> LOG2STG) & 1, cons, (unsigned)seenL); ++seenL; }
+                if (gsB >= 2) fs3_wait_consumed(cons, (unsigned)(gsB - 1));
                 const TSt* src = stage + ((size_t)(gs & (NSTG - 1)) * GEN_MAXSRC + my_src) * FS3_M;
                 cd* plane = spec + ((size_t)slot * NPMAX + (roleA ? p : NA + bs)) * FS3_PITCH;
-                const double* urow = fa.U + (size_t)my_u * N0;
-                cd v[8];
+                const double* urow = fa.U + (size_t)(isJ ? 0 : my_u) * N0;
+                const int klo = (roleA ? h : 0) - hl, khi = (active ? (roleA ? h + Sc : FS3_M) : 0) - hl;   // keep <=> klo <= 16 q < khi
+                cd v[16];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int n = lane + 32 * q;
-                    cd gg = load_c(src + n);
-                    if (!isJ) gg = cscale(gg, __ldg(urow + wrap_row(c0 - h + n, N0)));
-                    const bool keep = !roleA || (n >= h && n < h + Sc);
-                    v[q] = keep ? gg : cmake(0.0, 0.0);
+                for (int q = 0; q < 16; ++q) {
+                    const cd gg = load_c(src + hl + 16 * q);
+                    int r = c0 - h + hl + 16 * q;
+                    while (r < 0) r += N0;
+                    while (r >= N0) r -= N0;
+                    double sc = isJ ? 1.0 : __ldg(urow + r);
+                    sc = (16 * q >= klo && 16 * q < khi) ? sc : 0.0;
+                    v[q] = cmake(gg.x * sc, gg.y * sc);
                 }
-                vfft<FS3_M>(v, plane, lane, vt, -1.0, 0);
+                hfft256(v, plane, hl, htw, -1.0, active);
+                if (active) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) plane[VPAD(lane + 32 * q)] = v[q];
+                    for (int q = 0; q < 16; ++q) plane[HPAD(hl + 16 * q)] = v[q];
+                }
                 __syncwarp();
-                if (lane == 0) fs3_mbar_arrive(full + slot);
+                if (hl == 0 && active) fs3_mbar_arrive(full + slot);
             }
             fs3_bar0();                                    // (A)
-            for (int b0 = 0; b0 < ps.ninv; b0 += 16) {
-                fs3_bar0();
-                {
-                    const int jb = b0 + warp;
-                    if (jb < ps.ninv) {
-                        cd* plane = spec + warp * FS3_PITCH;
-                        cd v[8];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] = plane[VPAD(lane + 32 * q)];
-                        __syncwarp();
-                        vfft<FS3_M>(v, plane, lane, vt, +1.0, 0);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) plane[VPAD(lane + 32 * q)] = v[q];
-                        __syncwarp();
-                        const int qq = ps.inv_q[jb];
-                        const int b = qq % NB;
-                        const int bt = ps.b_type[b];
-                        const int lim = bt == 0 ? 2 * fa.w0 : fa.w0;
-                        const int rowb = ps.rowbase[qq];
-                        const double invM = 1.0 / (double)FS3_M;
-                        if (bt != 2) {
-                            for (int l = lane; l <= 2 * lim; l += 32)
-                                kaprow[rowb + l] = cscale(plane[VPAD((l - lim) & (FS3_M - 1))], invM);
-                        } else {
-                            const int p = ps.b_u[b], nlj0 = 2 * fa.w0 + 1;
-                            for (int l = lane; l <= 2 * lim; l += 32) {
-                                const cd lam = cscale(plane[VPAD((l - lim) & (FS3_M - 1))], invM);
-                                for (int t = 0; t < fa.tq_n[p]; ++t)
-                                    kaprow[rowb + t * nlj0 + l] = cmul(lam, fa.Q[(size_t)fa.tq_q[p][t] * fa.NH + k1]);
-                            }
-                        }
-                    }
-                }
-                fs3_bar0();
+            fs3_bar0();
+            {
+                const int wk = 2 * warp + half;
+                const bool act = wk < ps.ninv;
+                if (__any_sync(0xffffffffu, act)) gen4_inverse_job(fa, ps, htw, spec + (act ? wk : 0) * FS3_PITCH, act ? wk : 0, hl, act, k1, kaprow);
             }
+            fs3_bar0();
         }
     }
 }

@@ -19,6 +19,9 @@
 
 #define ROWH_NT 512
 #define ROWH_PP 273
+#ifndef ROWH_SETS
+#define ROWH_SETS(R) 1
+#endif
 
 struct RowH16Args {
     int N0, N1, NH, H;
@@ -37,7 +40,7 @@ static inline size_t rowh_smem_bytes(int H) {
 
 // SETS: the CTA works as SETS independent sets of 512 / SETS threads (own named barrier, own row groups), so that the untangle /
 // store phase of one set runs under the transform phase of the other
-template <typename TIn, typename TSt, int R, int SETS = 1>
+template <typename TIn, typename TSt, int R, int SETS = ROWH_SETS(R)>
 __global__ void __launch_bounds__(ROWH_NT, 1) row_fwd_h16_kernel(RowH16Args a, const TIn* __restrict__ img, TSt* __restrict__ out, int nj)
 {
     constexpr int H = 256 * R, T = H / 16, NB = 16 / R;

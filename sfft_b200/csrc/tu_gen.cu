@@ -277,10 +277,10 @@ int gen_plan_create(sfftb_plan* p, const sfftb_config* cfg, const sfftb_basis* k
     r2.ksplit = (NH + LR2_KC - 1) / LR2_KC;
     if (dev_alloc(g, (size_t)r2.ksplit * nrows * nl1, &g->part) || dev_alloc(g, (size_t)nrows * nl1, &g->Rall) ||
         dev_alloc(g, (size_t)GEN_MAXP * GEN_MAXQ, &g->PQ)) return SFFTB_ECUDA;
-    g->smem_fit = sizeof(cd) * ((size_t)2 * (GEN_NA + GEN_NB) * FS3_PITCH + 56 + 192) + 128 + csz * (f32 ? 8 : 4) * (size_t)GEN_MAXSRC * FS3_M;
+    g->smem_fit = gen_fit4_smem_bytes(f32);
     if (g->smem_fit > p->max_smem) return fail(SFFTB_EINVAL, "the general fit kernel needs %zu bytes of shared memory", g->smem_fit);
-    if (f32) { if (set_smem(fit_gen_kernel<float2>, g->smem_fit)) return SFFTB_ECUDA; }
-    else     { if (set_smem(fit_gen_kernel<double2>, g->smem_fit)) return SFFTB_ECUDA; }
+    if (f32) { if (set_smem(fit_gen4_kernel<float2>, g->smem_fit)) return SFFTB_ECUDA; }
+    else     { if (set_smem(fit_gen4_kernel<double2>, g->smem_fit)) return SFFTB_ECUDA; }
     if (lag_reduce2_setup()) return SFFTB_ECUDA;
 
     // ---- unknowns of the solved system (TweakLS, :2171-2338, 3702-3747) ----
@@ -414,7 +414,7 @@ template <typename TSt>
 int gen_fit_cols(sfftb_plan* p) {
     GenState* g = (GenState*)p->gen;
     for (const GenPass& ps : g->passes) {
-        fit_gen_kernel<TSt><<<p->grid_sfit, FS3_NT, g->smem_fit, p->stream>>>(g->fit, ps, p->vtabs, (const TSt*)g->gP, (const TSt*)p->gJ, g->kap);
+        fit_gen4_kernel<TSt><<<p->grid_sfit, FS4_NT, g->smem_fit, p->stream>>>(g->fit, ps, p->tabA, (const TSt*)g->gP, (const TSt*)p->gJ, g->kap);
         CKL(p);
     }
     EVREC(p, EV_COL);
