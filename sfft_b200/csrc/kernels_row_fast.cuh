@@ -1,4 +1,5 @@
-// kernels_row_fast.cuh -- row passes on the register-resident FFT engine (even N1 with N1/2 in {512,...,8192}).
+// kernels_row_fast.cuh -- INVERSE row pass on the register-resident 16-values-per-thread FFT engine (even N1 with N1/2 in
+// {512,...,8192}); the forward pass of this family was replaced by kernels_row_h16.cuh / kernels_row_v8.cuh.
 // Same contract as kernels_row.cuh: packed real-to-complex rows with the cy^j factor fused into the load, half
 // spectra stored transposed g[j][k1][r]; and the inverse (transposed half spectra -> real rows - background).
 // A CTA of 512 threads owns RB = 512 / T rows (T = H / 16 threads per row), so the transposed stores/loads move
@@ -29,61 +30,6 @@ __device__ __forceinline__ GroupSync row_group_sync(int grp, int lane_in_warp_gr
     gs.bar_id = 1 + grp;
     gs.count = T;
     return gs;
-}
-
-template <typename TIn, typename TSt, int H>
-__global__ void __launch_bounds__(ROWF_NT) row_fwd_fast_kernel(RowFastArgs a, const TIn* __restrict__ img, TSt* __restrict__ out, int nj)
-{
-    constexpr int T = H / 16, RB = ROWF_NT / T, PITCH = H + H / 16;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cd* buf = reinterpret_cast<cd*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int grp = tid / T, lane = tid - grp * T;
-    const int r0 = blockIdx.x * RB;
-    const int r = r0 + grp;
-    cd* scratch = buf + (size_t)grp * PITCH;
-    const GroupSync gs = row_group_sync<H>(grp, lane);
-    const double inv1 = 1.0 / (double)a.N1;
-
-    for (int j = 0; j < nj; ++j) {
-        cd v[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int n = lane + q * T;
-            cd z = cmake(0.0, 0.0);
-            if (r < a.N0) {
-                const TIn* p = img + (size_t)r * a.N1 + 2 * n;
-                double x0, x1;
-                load2(p, x0, x1);
-                if (a.vtab) {
-                    const double* vt = a.vtab + (size_t)j * a.N1 + 2 * n;
-                    x0 *= vt[0]; x1 *= vt[1];
-                } else if (j > 0) {
-                    x0 *= ipow((2 * n + 1) * inv1, j);
-                    x1 *= ipow((2 * n + 2) * inv1, j);
-                }
-                z = cmake(x0, x1);
-            }
-            v[q] = z;
-        }
-        reg_fft<H>(v, scratch, lane, a.tabA, a.tabB, a.tabC, -1.0, gs);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) scratch[RPAD(lane + q * T)] = v[q];
-        __syncthreads();
-        for (int idx = tid; idx < RB * a.NH; idx += ROWF_NT) {
-            const int k = idx / RB, row = idx - k * RB;
-            const int rr = r0 + row;
-            if (rr >= a.N0) continue;
-            const cd* pl = buf + (size_t)row * PITCH;
-            const int ka = (k == H) ? 0 : k, kb = (k == 0) ? 0 : H - k;
-            const cd zk = pl[RPAD(ka)];
-            const cd zm = cconj(pl[RPAD(kb)]);
-            const cd s = cadd(zk, zm), d = csub(zk, zm);
-            const cd wd = cmul(a.tw1[k], d);
-            store_c(out + ((size_t)j * a.NH + k) * a.N0 + rr, cmake(0.5 * (s.x + wd.y), 0.5 * (s.y - wd.x)));
-        }
-        __syncthreads();
-    }
 }
 
 struct RowInvFastArgs {

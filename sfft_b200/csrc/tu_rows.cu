@@ -76,9 +76,7 @@ int rows_setup(sfftb_plan* p) {
         const size_t sm = sizeof(cd) * (size_t)(ROWF_NT / (r.H / 16)) * (r.H + r.H / 16);
 #define SET_ROWF(HH)                                                                                              \
         if (r.H == HH) {                                                                                              \
-            if (f32 && (set_smem(row_fwd_fast_kernel<float, float2, HH>, sm) || set_smem(row_fwd_fast_kernel<double, float2, HH>, sm))) return SFFTB_ECUDA; \
-            if (set_smem(row_fwd_fast_kernel<float, double2, HH>, sm) || set_smem(row_fwd_fast_kernel<double, double2, HH>, sm) || \
-                set_smem(row_inv_fast_kernel<double2, float, HH>, sm) || set_smem(row_inv_fast_kernel<double2, double, HH>, sm)) return SFFTB_ECUDA; \
+            if (set_smem(row_inv_fast_kernel<double2, float, HH>, sm) || set_smem(row_inv_fast_kernel<double2, double, HH>, sm)) return SFFTB_ECUDA; \
         }
         SET_ROWF(512) SET_ROWF(1024) SET_ROWF(2048) SET_ROWF(4096) SET_ROWF(8192)
 #undef SET_ROWF
@@ -130,20 +128,6 @@ int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj, 
         }
         RUN_ROWV(256) RUN_ROWV(512) RUN_ROWV(1024) RUN_ROWV(2048)
 #undef RUN_ROWV
-        CKL(p);
-        return 0;
-    }
-    if (p->row_fast && ((uintptr_t)img % esz2) == 0) {
-        const int H = p->row_fast, RB = ROWF_NT / (H / 16);
-        const int grid = (p->d.N0 + RB - 1) / RB;
-        const size_t sm = sizeof(cd) * (size_t)RB * (H + H / 16);
-#define RUN_ROWF(HH)                                                                                                   \
-        if (H == HH) {                                                                                                 \
-            if (dtype == SFFTB_F64) row_fwd_fast_kernel<double, TSt, HH><<<grid, ROWF_NT, sm, p->stream>>>(rowf, (const double*)img, out, nj); \
-            else row_fwd_fast_kernel<float, TSt, HH><<<grid, ROWF_NT, sm, p->stream>>>(rowf, (const float*)img, out, nj);                     \
-        }
-        RUN_ROWF(512) RUN_ROWF(1024) RUN_ROWF(2048) RUN_ROWF(4096) RUN_ROWF(8192)
-#undef RUN_ROWF
         CKL(p);
         return 0;
     }
