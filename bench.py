@@ -370,7 +370,7 @@ def run_c3(args, world, rank, local, numa):
         # dominant kernel: the block passes of fit_gen_kernel.  Per launch a pass must read the stored planes it stages once
         # and write its lag rows; summed over the passes of one fit: staged planes total x NH x N0 complex + all lag rows
         alg_bytes = info['staged_planes_total'] * NH * N0 * csz + info['lag_rows'] * NH * 16
-        t_kernel = stage.get('fit_cols', 0.0) / 1e3
+        t_kernel = stage.get('fit_cols', 0.0) / 1e3                  # all passes of the kernel (bytes and time both summed over the passes)
         achieved = alg_bytes / t_kernel / 1e9 if t_kernel > 0 else None
         n_pl = P['Fij'] + P.get('ScaFij', 0) + 1
         step_bytes = (4 * n_pl + 7) * N0 * N1 * esz                  # SURVEY.md 8d, SEPARATE-VARYING: n_pl = Fij + ScaFij + 1
@@ -398,7 +398,7 @@ def run_c3(args, world, rank, local, numa):
             'roofline': {'bound': 'hbm', 'kernel': 'fit_gen4_kernel', 'achieved': achieved, 'peak': peak, 'peak_source': which, 'unit': 'GB/s',
                          'frac': (achieved / peak) if achieved else None, 'traffic': None,
                          'algorithmic_bytes_per_launch': alg_bytes / max(1, info['passes']), 'launches_per_step_of_kernel': info['passes'],
-                         'kernel_ms': stage.get('fit_cols'), 'step_algorithmic_bytes': step_bytes,
+                         'kernel_ms': t_kernel * 1e3, 'step_algorithmic_bytes': step_bytes,
                          'step_frac': step_bytes / (ms / 1e3) / 1e9 / peak,
                          'note': 'fp64-issue / shared-memory bound like the polynomial fit kernel (DESIGN.md section 4); %d passes of up to '
                                  '5 x 5 pair accumulators, n = %d Cholesky' % (info['passes'], info['unknowns'])},
@@ -856,8 +856,8 @@ def main():
         nrowsL = (Fij * Fpq * (2 * w + 1) + Fpq) if seg_path else (Fij * (DB + 1) * (2 * w + 1) + (DB + 1))
         kname = 'fit_seg4_kernel' if seg_path else 'fit_col_kernel'
         npass = 3 if (seg_path and DK == 3) else 1          # every plane-range launch streams the stored planes once
-        alg_bytes = npass * (DK + 2) * NH * N0 * csz + (nrowsK + nrowsL) * NH * 16
-        t_kernel = stage.get('fit_cols', 0.0) / 1e3
+        alg_bytes = (DK + 2) * NH * N0 * csz + (nrowsK + nrowsL) * NH * 16 / npass       # per launch
+        t_kernel = (stage.get('fit_cols_kernel') or stage.get('fit_cols', 0.0)) / 1e3 / npass      # average launch duration of the kernel
         achieved = alg_bytes / t_kernel / 1e9 if t_kernel > 0 else None      # = bytes per launch / average launch time
         # whole-step algorithmic bytes: (4 n_pl + 7) * N0 * N1 * s with n_pl = Fij + 1
         step_bytes = (4 * (Fij + 1) + 7) * N0 * N1 * esz
@@ -928,8 +928,8 @@ def main():
                          'note': 'the path is fp64-issue bound on B200 (64 DFMA/clk/SM, DESIGN.md section 4); the HBM '
                                  'fraction is reported as the contract asks',
                          'peak_source': which, 'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None,
-                         'traffic': None, 'algorithmic_bytes_per_launch': alg_bytes / npass, 'launches_per_step_of_kernel': npass,
-                         'kernel_ms': stage.get('fit_cols'),
+                         'traffic': None, 'algorithmic_bytes_per_launch': alg_bytes, 'launches_per_step_of_kernel': npass,
+                         'kernel_ms': t_kernel * 1e3,
                          'step_algorithmic_bytes': step_bytes,
                          'step_frac': step_bytes / (ms / 1e3) / 1e9 / peak},
         }

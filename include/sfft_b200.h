@@ -245,7 +245,8 @@ int  sfftb_export_normal_eq(sfftb_plan* plan, double* LHMAT, double* RHb);
 
 /* Device-event stage timings of the last fit/apply, milliseconds.
  * ms[0] row spectra (fit), [1] column pass (fit), [2] lag reductions + fill, [3] solve,
- * [4] row spectra (apply), [5] column pass (apply), [6] inverse rows.  Enabled by sfftb_plan_set_timing. */
+ * [4] row spectra (apply), [5] column pass (apply), [6] inverse rows, [7] the fit column kernel alone (segmented path; [1] also
+ * holds the column-moment kernel).  Enabled by sfftb_plan_set_timing. */
 int  sfftb_plan_set_timing(sfftb_plan* plan, int enable);
 int  sfftb_timings(sfftb_plan* plan, float* ms, int n);
 

@@ -53,7 +53,7 @@ int sfftb_fail(int code, const char* fmt, ...);
             return fail(SFFTB_ECUDA, "kernel launch failed: %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-enum { EV_START = 0, EV_ROWS, EV_COL, EV_RED, EV_SOLVE, EV_A0, EV_AROWS, EV_ACOL, EV_AINV, EV_COUNT };
+enum { EV_START = 0, EV_ROWS, EV_COL, EV_RED, EV_SOLVE, EV_A0, EV_AROWS, EV_ACOL, EV_AINV, EV_KFIT0, EV_KFIT1, EV_COUNT };
 
 struct sfftb_plan {
     sfftb_config cfg;
@@ -152,7 +152,7 @@ struct sfftb_plan {
     // state
     cudaEvent_t ev[EV_COUNT];
     int timing;
-    float ms[7];
+    float ms[8];                 // [7]: the fit column kernel alone (the launches between EV_KFIT0 and EV_KFIT1)
     long long launches;
     int last_solver;
     int have_fit;

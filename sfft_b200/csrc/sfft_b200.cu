@@ -744,6 +744,7 @@ static int collect_timings(sfftb_plan* p, bool fit, bool app) {
         CK(cudaEventElapsedTime(&p->ms[1], p->ev[EV_ROWS], p->ev[EV_COL]));
         CK(cudaEventElapsedTime(&p->ms[2], p->ev[EV_COL], p->ev[EV_RED]));
         CK(cudaEventElapsedTime(&p->ms[3], p->ev[EV_RED], p->ev[EV_SOLVE]));
+        if (p->fit_seg && !p->gen) CK(cudaEventElapsedTime(&p->ms[7], p->ev[EV_KFIT0], p->ev[EV_KFIT1]));
     }
     if (app) {
         CK(cudaEventElapsedTime(&p->ms[4], p->ev[EV_A0], p->ev[EV_AROWS]));
@@ -755,7 +756,7 @@ static int collect_timings(sfftb_plan* p, bool fit, bool app) {
 
 extern "C" int sfftb_timings(sfftb_plan* p, float* ms, int n) {
     if (!p || !ms) return fail(SFFTB_EINVAL, "null argument");
-    for (int k = 0; k < n && k < 7; ++k) ms[k] = p->ms[k];
+    for (int k = 0; k < n && k < 8; ++k) ms[k] = p->ms[k];
     return 0;
 }
 

@@ -49,6 +49,7 @@ int launch_fit_cols(sfftb_plan* p, const TSt* gIsrc, bool jonly) {
         col_moments_kernel<TSt><<<(nwarps + 7) / 8, 256, 0, p->stream>>>(d.N0, NH, DK, d.DB, nms, jonly ? 1 : 0, gIsrc, (const TSt*)p->gJ, p->momg);
         CKL(p);
     }
+    if (p->fit_seg) EVREC(p, EV_KFIT0);
     if (jonly) {
         if (DK == 0) fit_seg4_kernel<TSt, 0, true><<<grid_sfit, FS4_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
         else if (DK == 1) fit_seg4_kernel<TSt, 1, true><<<grid_sfit, FS4_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
@@ -68,6 +69,7 @@ int launch_fit_cols(sfftb_plan* p, const TSt* gIsrc, bool jonly) {
     } else
         fit_col_kernel<TSt><<<p->grid_fit, NT_COL, p->smem_fit, p->stream>>>(p->cfit, gIsrc, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
     CKL(p);
+    if (p->fit_seg) EVREC(p, EV_KFIT1);
     EVREC(p, EV_COL);
     if (p->fit_seg) {
         // (one launch over all rows also for shared-template tiles: the reduction is a single latency-bound wave, and

@@ -115,9 +115,10 @@ class Plan:
         B.check(self._L.sfftb_plan_set_timing(self._h, int(bool(on))))
 
     def timings(self):
-        ms = (C.c_float * 7)()
-        B.check(self._L.sfftb_timings(self._h, ms, 7))
-        keys = ('fit_rows', 'fit_cols', 'fit_reduce_fill', 'fit_solve', 'apply_rows', 'apply_cols', 'apply_inv_rows')
+        ms = (C.c_float * 8)()
+        B.check(self._L.sfftb_timings(self._h, ms, 8))
+        # 'fit_cols' = column moments + fit column kernel(s); 'fit_cols_kernel' = the fit column kernel(s) alone (segmented path)
+        keys = ('fit_rows', 'fit_cols', 'fit_reduce_fill', 'fit_solve', 'apply_rows', 'apply_cols', 'apply_inv_rows', 'fit_cols_kernel')
         return dict(zip(keys, [float(v) for v in ms]))
 
     @property
