@@ -31,8 +31,17 @@ struct RowH16Args {
     const double* vtab;      // general-basis plans: column tables instead of cy^j (or NULL)
 };
 
-static inline size_t rowh_smem_bytes(int H) {
-    const int R = H / 256, T = H / 16, RBI = ROWH_NT / T;     // rows in flight per CTA (all sets)
+// threads per CTA: 512 (four rows of 2048 points in flight).  fp64 spectra fill a 32-byte sector with TWO rows, so the apply-step
+// pass could run 256-thread CTAs, two per SM, whose transform and store phases interleave (ROWH_NT64 256); measured slightly
+// slower (2.22 against 2.20 ms per pair), so both storage types use 512
+#ifndef ROWH_NT64
+#define ROWH_NT64 512
+#endif
+template <typename TSt, int R> struct RowhCfg { static const int nt = (sizeof(TSt) == 16 && R <= 8) ? ROWH_NT64 : ROWH_NT; };
+static inline int rowh_threads(int H, bool st64) { return (st64 && H <= 2048) ? ROWH_NT64 : ROWH_NT; }
+
+static inline size_t rowh_smem_bytes(int H, int nt = ROWH_NT) {
+    const int R = H / 256, T = H / 16, RBI = nt / T;          // rows in flight per CTA (all sets)
     int LR = 0;
     while ((1 << LR) < R) ++LR;
     return sizeof(cd) * ((size_t)RBI * (R * ROWH_PP + 4) + (size_t)LR * 256 + H / 2 + 1);
@@ -41,23 +50,23 @@ static inline size_t rowh_smem_bytes(int H) {
 // SETS: the CTA works as SETS independent sets of 512 / SETS threads (own named barrier, own row groups), so that the untangle /
 // store phase of one set runs under the transform phase of the other
 template <typename TIn, typename TSt, int R, int SETS = ROWH_SETS(R)>
-__global__ void __launch_bounds__(ROWH_NT, 1) row_fwd_h16_kernel(RowH16Args a, const TIn* __restrict__ img, TSt* __restrict__ out, int nj)
+__global__ void __launch_bounds__(RowhCfg<TSt, R>::nt, ROWH_NT / RowhCfg<TSt, R>::nt) row_fwd_h16_kernel(RowH16Args a, const TIn* __restrict__ img, TSt* __restrict__ out, int nj)
 {
-    constexpr int H = 256 * R, T = H / 16, NB = 16 / R;
-    constexpr int TS = ROWH_NT / SETS, RBI = TS / T;          // threads per set, rows per set
+    constexpr int H = 256 * R, T = H / 16, NB = 16 / R, NT = RowhCfg<TSt, R>::nt;
+    constexpr int TS = NT / SETS, RBI = TS / T;          // threads per set, rows per set
     constexpr int LR = R == 4 ? 2 : (R == 8 ? 3 : 4);
     constexpr int ROWP = R * ROWH_PP + (sizeof(TSt) == 8 ? 4 : 2);     // row pitch: the LPC lanes of a column read different bank groups
     typedef typename In2<TIn>::type TIn2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd* zbuf = reinterpret_cast<cd*>(smem_raw);              // [RBI][R planes][ROWH_PP]
-    cd* twp = zbuf + (size_t)(ROWH_NT / T) * ROWP;           // [LR][256]: W_H^{b 2^l}
+    cd* twp = zbuf + (size_t)(NT / T) * ROWP;           // [LR][256]: W_H^{b 2^l}
     cd* tw1s = twp + LR * 256;                               // [H/2 + 1] untangle factors
     const int tid = threadIdx.x;
-    for (int i = tid; i < LR * 256; i += ROWH_NT) {
+    for (int i = tid; i < LR * 256; i += NT) {
         const int l = i >> 8, b = i & 255;
         twp[i] = a.twP[(size_t)((1 << l) - 1) * 256 + b];
     }
-    for (int i = tid; i <= H / 2; i += ROWH_NT) tw1s[i] = a.tw1[i];
+    for (int i = tid; i <= H / 2; i += NT) tw1s[i] = a.tw1[i];
     const int grp = tid / T, t = tid - grp * T;               // row slot of the CTA, thread of the row
     const int set = tid / TS, ts = tid - set * TS, gs = grp - set * RBI;     // set, thread of the set, row of the set
     const int lane = tid & 31, half = lane >> 4, hl = lane & 15;

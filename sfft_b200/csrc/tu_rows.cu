@@ -62,11 +62,11 @@ int rows_setup(sfftb_plan* p) {
         RowH16Args& rh = p->rowh;
         rh.N0 = d.N0; rh.N1 = d.N1; rh.NH = d.N1 / 2 + 1; rh.H = r.H;
         rh.tabA = p->tabA; rh.twP = p->tabB_row; rh.tw1 = p->tw1; rh.vtab = nullptr;
-        const size_t smh = rowh_smem_bytes(r.H);
+        const size_t smh = rowh_smem_bytes(r.H), smh64 = rowh_smem_bytes(r.H, rowh_threads(r.H, true));
 #define SET_ROWH(RR)                                                                                              \
         if (r.H == 256 * RR) {                                                                                        \
             if (f32 && (set_smem(row_fwd_h16_kernel<float, float2, RR>, smh) || set_smem(row_fwd_h16_kernel<double, float2, RR>, smh))) return SFFTB_ECUDA; \
-            if (set_smem(row_fwd_h16_kernel<float, double2, RR>, smh) || set_smem(row_fwd_h16_kernel<double, double2, RR>, smh)) return SFFTB_ECUDA; \
+            if (set_smem(row_fwd_h16_kernel<float, double2, RR>, smh64) || set_smem(row_fwd_h16_kernel<double, double2, RR>, smh64)) return SFFTB_ECUDA; \
         }
         SET_ROWH(4) SET_ROWH(8) SET_ROWH(16)
 #undef SET_ROWH
@@ -102,14 +102,14 @@ int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj, 
     }
     if (p->row_h16 && ((uintptr_t)img % esz2) == 0) {
         RowH16Args rowh = p->rowh; rowh.vtab = vtab;
-        const int H = p->row_h16, RBI = ROWH_NT / (H / 16);
+        const int H = p->row_h16, NTH = rowh_threads(H, sizeof(TSt) == 16), RBI = NTH / (H / 16);
         const int ngroups = (p->d.N0 + RBI - 1) / RBI;
-        const int grid = std::min(ngroups, p->row_grid_limit > 0 ? p->row_grid_limit : work_sms(p));
-        const size_t smh = rowh_smem_bytes(H);
+        const int grid = std::min(ngroups, (p->row_grid_limit > 0 ? p->row_grid_limit : work_sms(p)) * (ROWH_NT / NTH));
+        const size_t smh = rowh_smem_bytes(H, NTH);
 #define RUN_ROWH(RR)                                                                                                   \
         if (H == 256 * RR) {                                                                                           \
-            if (dtype == SFFTB_F64) row_fwd_h16_kernel<double, TSt, RR><<<grid, ROWH_NT, smh, p->stream>>>(rowh, (const double*)img, out, nj); \
-            else row_fwd_h16_kernel<float, TSt, RR><<<grid, ROWH_NT, smh, p->stream>>>(rowh, (const float*)img, out, nj);                     \
+            if (dtype == SFFTB_F64) row_fwd_h16_kernel<double, TSt, RR><<<grid, NTH, smh, p->stream>>>(rowh, (const double*)img, out, nj); \
+            else row_fwd_h16_kernel<float, TSt, RR><<<grid, NTH, smh, p->stream>>>(rowh, (const float*)img, out, nj);                     \
         }
         RUN_ROWH(4) RUN_ROWH(8) RUN_ROWH(16)
 #undef RUN_ROWH
