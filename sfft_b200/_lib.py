@@ -47,7 +47,7 @@ class Dims(C.Structure):
 
 def build(verbose=False):
     """Compile libsfft_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
-    cmd = ['make', '-C', os.path.join(HERE, 'csrc')]
+    cmd = ['make', '-j%d' % max(1, min(8, os.cpu_count() or 1)), '-C', os.path.join(HERE, 'csrc')]     # one translation unit per kernel family
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or r.returncode:
         print(r.stdout)
