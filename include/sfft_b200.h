@@ -196,6 +196,13 @@ int  sfftb_decorr(int device, void* cuda_stream, int N0, int N1, int nker, const
 int  sfftb_convolve(int device, void* cuda_stream, const void* img, int dtype, int N0, int N1, const double* kernel, int L0, int L1,
                     double pad_fill, double nan_fill, int fill_nan, int normalize_kernel, void* out, int memkind);
 
+/* BSpline_GridConvolve.GSVC_GPU / GSVC_CPU (sfft/BSplineSFFT.py:4870-5010): grid-wise spatially varying convolution.  `labels`
+ * (N0, N1) int32 gives every pixel the index of its grid cell (AllocatedL), `kerstack` (nseg, L0, L1) the kernel of every cell
+ * (HOST, odd sizes; normalize_kernel divides each by its sum); out[r, c] = image convolved with the kernel of the pixel's cell,
+ * zero outside the image, NaN samples replaced by `nan_fill`.  img / labels / out: `memkind`; img / out: `dtype`. */
+int  sfftb_convolve_grid(int device, void* cuda_stream, const void* img, int dtype, int N0, int N1, const int* labels, int nseg,
+                         const double* kerstack, int L0, int L1, double nan_fill, int normalize_kernel, void* out, int memkind);
+
 /* Kernel regularisation (sfft/BSplineSFFT.py:3570-3700, REGULARIZE_KERNEL / LAMBDA_REGULARIZE): every following fit solves
  * (LHMAT + lambda * REGMAT) x = RHb with REGMAT[(k,c),(k',c')] = SCALE^2 * SST[k,k'] * iREG[c,c'] (fill_regmat, :2091-2119).
  * SST is the (Fij x Fij) Gram matrix of the kernel basis at the regularisation coordinates, iREG the (Fab x Fab)

@@ -132,3 +132,30 @@ def fft_convolve(PixA_Inp, KERNEL, PAD_FILL_VALUE=0.0, NAN_FILL_VALUE=0.0, NORMA
     kimg = csz(k, N0 + 2 * W0, N1 + 2 * W1)
     out = np.fft.ifft2(np.fft.fft2(e) * np.fft.fft2(kimg)).real
     return out[W0: W0 + N0, W1: W1 + N1]
+
+
+def gsvc(PixA_obj, AllocatedL, KerStack, nan_fill_value=0.0, normalize_kernel=True):
+    """BSpline_GridConvolve.GSVC_GPU with use_fft=False (sfft/BSplineSFFT.py:4951-5008): per cell, the mini image (cell extended by
+    w + 1, clipped to the image) convolved with scipy's convolve2d(mode='same', boundary='fill', fillvalue=0) -- cupyx's convolve2d
+    is its mirror -- and the cell pasted back.  Parity unpinned (the reference needs CuPy / astropy); restated line by line."""
+    from scipy.signal import convolve2d
+    PixA_in = np.array(PixA_obj, dtype=float)
+    PixA_in[np.isnan(PixA_in)] = nan_fill_value
+    N0, N1 = PixA_in.shape
+    Nseg, L0, L1 = KerStack.shape
+    w0, w1 = int((L0 - 1) / 2), int((L1 - 1) / 2)
+    IBx, IBy = w0 + 1, w1 + 1
+    K = np.asarray(KerStack, float)
+    if normalize_kernel:
+        K = K / np.sum(K, axis=(1, 2))[:, np.newaxis, np.newaxis]
+    out = np.zeros((N0, N1))
+    for idx in range(Nseg):
+        lX, lY = np.where(AllocatedL == idx)
+        if lX.size == 0:
+            continue
+        xs, xe, ys, ye = lX.min(), lX.max(), lY.min(), lY.max()
+        xEs, xEe = max([0, xs - IBx]), min([N0 - 1, xe + IBx])
+        yEs, yEe = max([0, ys - IBy]), min([N1 - 1, ye + IBy])
+        c = convolve2d(PixA_in[xEs: xEe + 1, yEs: yEe + 1], K[idx], mode='same', boundary='fill', fillvalue=0.0)
+        out[xs: xe + 1, ys: ye + 1] = c[xs - xEs: (xs - xEs) + (xe + 1 - xs), ys - yEs: (ys - yEs) + (ye + 1 - ys)]
+    return out

@@ -33,7 +33,7 @@ from .sfftcore.SFFTConfigure import _current_device
 from .sfftcore.SFFTSubtract import ElementalSFFTSubtract as _ESS, GeneralSFFTSubtract as _GSS
 
 __all__ = ['SingleSFFTConfigure', 'ElementalSFFTSubtract', 'GeneralSFFTSubtract', 'BSpline_Packet', 'regularizer_factors',
-           'Read_SFFTSolution', 'BSpline_MatchingKernel', 'ConvKernel_Convertion', 'BSpline_DeCorrelation']
+           'Read_SFFTSolution', 'BSpline_MatchingKernel', 'ConvKernel_Convertion', 'BSpline_DeCorrelation', 'BSpline_GridConvolve']
 
 
 def _laplacian_penalty(w0, w1, IGNORE_LAPLACIAN_KERCENT):
@@ -458,3 +458,35 @@ class BSpline_DeCorrelation:
         from .utils.DeCorrelationCalculator import DeCorrelation_Calculator
         return DeCorrelation_Calculator.DCC(MK_JLst, SkySig_JLst, MK_ILst=MK_ILst, SkySig_ILst=SkySig_ILst, MK_Fin=MK_Fin, KERatio=KERatio,
                                             VERBOSE_LEVEL=VERBOSE_LEVEL, CUDA_DEVICE=CUDA_DEVICE, _CLIP_RATIO=float(DENO_CLIP_RATIO))
+
+
+class BSpline_GridConvolve:
+    """Grid-wise spatially varying convolution (:4870-5010): every pixel is convolved with the kernel of its grid cell
+    (`AllocatedL` labels, `KerStack[label]`), zero outside the image, NaN samples replaced by `nan_fill_value`.  The reference
+    convolves a mini image per cell on the CPU (astropy) or the GPU (cupyx convolve2d / fftconvolve, `use_fft`); here one CUDA
+    kernel evaluates the same sums for all cells (sfftb_convolve_grid) -- `use_fft` is accepted and changes nothing but rounding
+    in the reference.  Cells are assumed to be what the reference builds (rectangular tiles, :4876-4893): it pastes bounding boxes."""
+
+    def __init__(self, PixA_obj, AllocatedL, KerStack, nan_fill_value=0.0, use_fft=False, normalize_kernel=True):
+        self.PixA_in = np.ascontiguousarray(PixA_obj, np.float64)
+        self.nan_fill_value = float(nan_fill_value)
+        self.AllocatedL = np.ascontiguousarray(AllocatedL, np.int32)
+        self.KerStack = np.ascontiguousarray(KerStack, np.float64)
+        self.use_fft = use_fft
+        self.normalize_kernel = normalize_kernel
+        if self.AllocatedL.shape != self.PixA_in.shape or self.KerStack.ndim != 3:
+            raise Exception('MeLOn ERROR: AllocatedL must have the image shape and KerStack the shape (Nseg, L0, L1)')
+
+    def GSVC_GPU(self, CUDA_DEVICE='0', CLEAN_GPU_MEMORY=False, nproc=32):
+        from . import _lib as B
+        N0, N1 = self.PixA_in.shape
+        Nseg, L0, L1 = self.KerStack.shape
+        out = np.empty((N0, N1), np.float64)
+        B.check(B.lib().sfftb_convolve_grid(int(CUDA_DEVICE), 0, self.PixA_in.ctypes.data, B.F64, N0, N1, self.AllocatedL.ctypes.data, Nseg,
+                                            self.KerStack.ctypes.data, L0, L1, self.nan_fill_value, int(bool(self.normalize_kernel)),
+                                            out.ctypes.data, B.MEM_HOST))
+        return out
+
+    def GSVC_CPU(self, nproc=32):
+        """The reference's multiprocessing CPU variant (:4912-4949); this package has no CPU path, the same CUDA routine serves it."""
+        return self.GSVC_GPU()

@@ -22,7 +22,7 @@ EXPORTS = ['sfftb_version', 'sfftb_last_error', 'sfftb_plan_create', 'sfftb_plan
            'sfftb_template_mark_ready', 'sfftb_gss_template', 'sfftb_realize', 'sfftb_fits_decode', 'sfftb_fits_encode', 'sfftb_nan_union_fill', 'sfftb_nan_mask_apply',
            'sfftb_set_regularizer', 'sfftb_set_regularizer_varying', 'sfftb_gss_submit', 'sfftb_gss_template_submit', 'sfftb_gss_finish', 'sfftb_dbg_fft1d',
            'sfftb_dbg_row_spectra', 'sfftb_dbg_lag_tables', 'sfftb_plan_create_general', 'sfftb_export_solved_system',
-           'sfftb_gss_submit_device', 'sfftb_gss_submit_delta', 'sfftb_gen_info', 'sfftb_plan_set_partition', 'sfftb_decorr', 'sfftb_convolve']
+           'sfftb_gss_submit_device', 'sfftb_gss_submit_delta', 'sfftb_gen_info', 'sfftb_plan_set_partition', 'sfftb_decorr', 'sfftb_convolve', 'sfftb_convolve_grid']
 
 
 class Config(C.Structure):
@@ -109,6 +109,7 @@ def lib():
     L.sfftb_plan_set_partition.argtypes = [vp, ip]
     L.sfftb_decorr.argtypes = [ip, vp, ip, ip, ip, vp, vp, vp, vp, C.c_double, ip, ip, ip, ip, vp, ip, vp]
     L.sfftb_convolve.argtypes = [ip, vp, vp, ip, ip, ip, vp, ip, ip, C.c_double, C.c_double, ip, ip, vp, ip]
+    L.sfftb_convolve_grid.argtypes = [ip, vp, vp, ip, ip, ip, vp, ip, vp, ip, ip, C.c_double, ip, vp, ip]
     for name in EXPORTS:
         if name not in ('sfftb_last_error', 'sfftb_launch_count'):
             getattr(L, name).restype = ip

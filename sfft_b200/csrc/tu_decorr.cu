@@ -327,3 +327,96 @@ done:
     return rc;
 #undef CVK
 }
+
+// ---- grid-wise spatially varying convolution: BSpline_GridConvolve.GSVC_GPU (sfft/BSplineSFFT.py:4870-5010) ------------------------
+// Every pixel carries the label of its grid cell (AllocatedL); the output pixel is the image convolved with THAT cell's kernel,
+// zero outside the image.  The reference cuts a mini image per cell (the cell extended by w + 1 pixels), convolves it with
+// scipy's convolve2d(mode='same', fillvalue=0) and pastes the cell back -- the extension covers the kernel footprint, so this is
+// the same sum evaluated per pixel.  32 x 32 output tile per CTA, halo tile in shared memory; the kernel stack stays in global
+// memory (a warp usually sits inside one cell, so its tap loads are broadcasts).
+template <typename T>
+__global__ void __launch_bounds__(256) conv_grid_kernel(int N0, int N1, int L0, int L1, int nseg, const T* __restrict__ in, const int* __restrict__ lab,
+                                                        const double* __restrict__ K, double nan_fill, T* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* tile = reinterpret_cast<double*>(smem_raw);
+    const int TH = CV_T + L0 - 1, TW = CV_T + L1 - 1, TP = TW | 1;
+    const int w0 = (L0 - 1) / 2, w1 = (L1 - 1) / 2;
+    const int r0 = blockIdx.y * CV_T, c0 = blockIdx.x * CV_T;
+    for (int i = threadIdx.x; i < TH * TW; i += 256) {
+        const int tr = i / TW, tc = i - tr * TW;
+        const int r = r0 + tr - (L0 - 1 - w0), c = c0 + tc - (L1 - 1 - w1);
+        double v = 0.0;
+        if (r >= 0 && r < N0 && c >= 0 && c < N1) {
+            v = (double)in[(size_t)r * N1 + c];
+            if (isnan(v)) v = nan_fill;
+        }
+        tile[tr * TP + tc] = v;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int r = r0 + ty * 4 + q, c = c0 + tx;
+        if (r >= N0 || c >= N1) continue;
+        const int l = lab[(size_t)r * N1 + c];
+        double acc = 0.0;
+        if (l >= 0 && l < nseg) {
+            const double* k = K + (size_t)l * L0 * L1;
+            // out[r, c] = sum_{a, b} K[a, b] in[r + w0 - a, c + w1 - b]: tile row (r - r0) + (L0 - 1 - a)
+            for (int a = 0; a < L0; ++a)
+                for (int b = 0; b < L1; ++b)
+                    acc = fma(__ldg(k + a * L1 + b), tile[(ty * 4 + q + L0 - 1 - a) * TP + tx + L1 - 1 - b], acc);
+        }
+        out[(size_t)r * N1 + c] = (T)acc;
+    }
+}
+
+extern "C" int sfftb_convolve_grid(int device, void* cuda_stream, const void* img, int dtype, int N0, int N1, const int* labels, int nseg,
+                                   const double* kerstack, int L0, int L1, double nan_fill, int normalize_kernel, void* out, int memkind) {
+    if (!img || !labels || !kerstack || !out) return fail(SFFTB_EINVAL, "null argument");
+    if (dtype != SFFTB_F64 && dtype != SFFTB_F32) return fail(SFFTB_EINVAL, "bad dtype");
+    if (nseg < 1 || L0 < 1 || L1 < 1 || L0 % 2 == 0 || L1 % 2 == 0) return fail(SFFTB_EINVAL, "only odd-sized kernels are supported");
+    CK(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t esz = dtype == SFFTB_F64 ? 8 : 4, npix = (size_t)N0 * N1, bytes = npix * esz, nk = (size_t)nseg * L0 * L1;
+    const int TW = CV_T + L1 - 1, TP = TW | 1;
+    const size_t smem = sizeof(double) * (size_t)(CV_T + L0 - 1) * TP;
+    int maxsm = 0;
+    CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    if (smem > (size_t)maxsm) return fail(SFFTB_EINVAL, "kernels of shape (%d, %d) too large for the grid convolution", L0, L1);
+    std::vector<double> hk(kerstack, kerstack + nk);
+    if (normalize_kernel)
+        for (int s = 0; s < nseg; ++s) {
+            double sum = 0.0;
+            for (int i = 0; i < L0 * L1; ++i) sum += hk[(size_t)s * L0 * L1 + i];
+            for (int i = 0; i < L0 * L1; ++i) hk[(size_t)s * L0 * L1 + i] /= sum;
+        }
+    void *din = nullptr, *dout = nullptr; double* dk = nullptr; int* dl = nullptr;
+    int rc = 0;
+#define CGK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(SFFTB_ECUDA, "CUDA error %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); goto done; } } while (0)
+    CGK(cudaMalloc(&dk, sizeof(double) * nk));
+    CGK(cudaMemcpyAsync(dk, hk.data(), sizeof(double) * nk, cudaMemcpyHostToDevice, st));
+    if (memkind == SFFTB_MEM_HOST) {
+        CGK(cudaMalloc(&din, bytes)); CGK(cudaMalloc(&dout, bytes)); CGK(cudaMalloc(&dl, sizeof(int) * npix));
+        CGK(cudaMemcpyAsync(din, img, bytes, cudaMemcpyHostToDevice, st));
+        CGK(cudaMemcpyAsync(dl, labels, sizeof(int) * npix, cudaMemcpyHostToDevice, st));
+    } else { din = const_cast<void*>(img); dout = out; dl = const_cast<int*>(labels); }
+    {
+        dim3 grd((N1 + CV_T - 1) / CV_T, (N0 + CV_T - 1) / CV_T);
+        if (dtype == SFFTB_F64) {
+            if (set_smem(conv_grid_kernel<double>, smem)) { rc = SFFTB_ECUDA; goto done; }
+            conv_grid_kernel<double><<<grd, 256, smem, st>>>(N0, N1, L0, L1, nseg, (const double*)din, dl, dk, nan_fill, (double*)dout);
+        } else {
+            if (set_smem(conv_grid_kernel<float>, smem)) { rc = SFFTB_ECUDA; goto done; }
+            conv_grid_kernel<float><<<grd, 256, smem, st>>>(N0, N1, L0, L1, nseg, (const float*)din, dl, dk, nan_fill, (float*)dout);
+        }
+    }
+    CGK(cudaGetLastError());
+    if (memkind == SFFTB_MEM_HOST) CGK(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, st));
+    CGK(cudaStreamSynchronize(st));
+done:
+    cudaFree(dk);
+    if (memkind == SFFTB_MEM_HOST) { cudaFree(din); cudaFree(dout); cudaFree(dl); }
+    return rc;
+#undef CGK
+}

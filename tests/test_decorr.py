@@ -120,3 +120,39 @@ def test_pcdc_and_fft_convolve_on_device_match_oracle():
     kc = K.KERNEL_CSZ(fin, 64, 48)
     assert np.array_equal(kc.cpu().numpy(), do.csz(G['mkfin'], 64, 48))
     assert np.array_equal(K.KERNEL_CSZ_INV(kc, 21, 21, VERBOSE_LEVEL=0).cpu().numpy(), G['mkfin'])
+
+
+def _grid_case(N0=150, N1=131, TiHW=12, L=7, seed=11):
+    rng = np.random.default_rng(seed)
+    img = rng.normal(size=(N0, N1)) * 5 + 50
+    img[10, 20] = np.nan
+    TiN = 2 * TiHW + 1
+    lab, AllocatedL = 0, np.zeros((N0, N1), dtype=int)
+    for xs in np.arange(0, N0, TiN):
+        for ys in np.arange(0, N1, TiN):
+            AllocatedL[xs: min(xs + TiN, N0), ys: min(ys + TiN, N1)] = lab       # the tiling of :4876-4893
+            lab += 1
+    K = rng.normal(size=(lab, L, L)) + 2.0
+    return img, AllocatedL, K
+
+
+def test_oracle_gsvc_is_a_per_pixel_label_convolution():
+    img, AL, K = _grid_case()
+    out = do.gsvc(img, AL, K, nan_fill_value=1.5, normalize_kernel=True)
+    src = np.where(np.isnan(img), 1.5, img)
+    e = np.pad(src, 3)
+    Kn = K / K.sum(axis=(1, 2))[:, None, None]
+    for (r, c) in [(0, 0), (24, 25), (25, 24), (77, 130), (149, 0), (60, 60)]:
+        k = Kn[AL[r, c]]
+        want = sum(k[a, b] * e[r + 3 + 3 - a, c + 3 + 3 - b] for a in range(7) for b in range(7))
+        assert abs(out[r, c] - want) < 1e-12
+
+
+@pytest.mark.gpu
+def test_grid_convolve_on_device_matches_oracle():
+    from sfft_b200.BSplineSFFT import BSpline_GridConvolve
+    for norm in (True, False):
+        img, AL, K = _grid_case(seed=12 + norm)
+        got = BSpline_GridConvolve(img, AL, K, nan_fill_value=0.25, normalize_kernel=norm).GSVC_GPU()
+        want = do.gsvc(img, AL, K, nan_fill_value=0.25, normalize_kernel=norm)
+        assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
