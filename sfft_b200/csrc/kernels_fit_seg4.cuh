@@ -20,7 +20,7 @@
 #endif
 #define FS4_NT (256 + 32 * FS4_NTW)
 #ifndef FS4_REGT
-#define FS4_REGT 112
+#define FS4_REGT 120
 #endif
 #define FS4_REGP (256 - FS4_REGT)
 #define FS4_NTW_UNUSED                 // transform warps
