@@ -27,6 +27,9 @@
 #define FS4_NWK (2 * FS4_NTW)     // half-warp transform workers
 #define FS4_NHW (2 * (FS4_NT / 32))   // half warps of the CTA (inverse phase)
 #define FS4_PITCH H16_SCRATCH         // elements per spectrum plane
+#ifndef FS4_INV_ALL
+#define FS4_INV_ALL 0                 // 1: the inverse phase of a column uses all 32 half warps (one round)
+#endif
 #ifndef FS4_BULK
 #define FS4_BULK 1                    // window ring filled by cp.async.bulk (0: per-element cp.async of the product threads)
 #endif
@@ -334,17 +337,19 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
 #endif
             // ---- column moments -> background cross-term rows (product warps only) ----
             fs3_bar0();                                    // (A) all transforms and products of the column are done
-            H16Tw htw;                                     // (reloaded per column: 16 registers the product loop cannot spare)
-            h16_load(htw, fa.tabA, hl);
 #pragma unroll
             for (int q = 0; q < NACC; ++q) spec[q * FS4_PITCH + HPAD(tid)] = acc[q];
             fs3_bar0();
+#if FS4_INV_ALL
             {
+                H16Tw htw;                                 // (reloaded per column: 16 registers the product loop cannot spare)
+                h16_load(htw, fa.tabA, hl);
                 const int wk = 2 * warp + half;
                 const bool act = wk < NACC;
                 if (__any_sync(0xffffffffu, act))
                     fs4_inverse_job<NPAIR>(fa, htw, spec + (act ? wk : 0) * FS4_PITCH, job_of(act ? wk : 0), hl, act, kaprow);
             }
+#endif
             fs3_bar0();
             kprev = k1;
         }
@@ -439,12 +444,22 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
 #endif
             fs3_bar0();                                    // (A)
             fs3_bar0();
+#if FS4_INV_ALL
             {
                 const int wk = 2 * warp + half;
                 const bool act = wk < NACC;
                 if (__any_sync(0xffffffffu, act))
                     fs4_inverse_job<NPAIR>(fa, htw, spec + (act ? wk : 0) * FS4_PITCH, job_of(act ? wk : 0), hl, act, kaprow);
             }
+#else
+            // the inverse transforms run on the 16 half-warp workers of the transform warps only (two rounds for 27 pairs): the
+            // product warps carry no copy of the transform code, and the cold code executed once per column is halved
+#pragma unroll 1
+            for (int jb = 2 * fw + half; jb - half < NACC; jb += FS4_NWK) {
+                const bool act = jb < NACC;
+                fs4_inverse_job<NPAIR>(fa, htw, spec + (act ? jb : 0) * FS4_PITCH, job_of(act ? jb : 0), hl, act, kaprow);
+            }
+#endif
             fs3_bar0();
 #ifdef FS4_DEBUG
             if (blockIdx.x == 0 && k1 == blockIdx.x + gridDim.x && lane == 0 && fw == 0) printf("F warp 0: inverse phase %lld cycles\n", clock64() - fI0);
