@@ -229,26 +229,27 @@ def run_config4(torch, dist, B, world, rank, local, dev, ntiles=64, side=2048, w
         if rank != 0:
             plan.template_mark_ready()
     t_bcast = time.perf_counter() - t1
-    tp = TemplatePipeline(side, side, w, DK, DB, True, device=local, storage=storage, stream_ptr=None, first_plan=plan)
+    TD = int(os.environ.get('SFFTB_BENCH_TILE_DEPTH', '4'))          # tiles in flight (one plan + stream each)
+    tp = TemplatePipeline(side, side, w, DK, DB, True, device=local, storage=storage, stream_ptr=None, first_plan=plan, depth=TD)
     tp.set_template()
     mine = list(shard_indices(ntiles, rank, world))
-    diffs = [torch.empty((side, side), dtype=tdt, device=dev) for _ in range(2)]
-    sols = [torch.empty(plan.NEQ, dtype=torch.float64, device=dev) for _ in range(2)]
-    busy = [False, False]
+    diffs = [torch.empty((side, side), dtype=tdt, device=dev) for _ in range(TD)]
+    sols = [torch.empty(plan.NEQ, dtype=torch.float64, device=dev) for _ in range(TD)]
+    busy = [False] * TD
 
     def run_tiles(idxs):
         for n_, k in enumerate(idxs):
-            slot = n_ % 2
+            slot = n_ % TD
             if busy[slot]:
                 tp.plans[slot].gss_finish()
             J, mJ = tiles[k % 2]
             tp.plans[slot].gss_template_submit_device(J.data_ptr(), mJ.data_ptr(), code, sols[slot].data_ptr(), diffs[slot].data_ptr(), code)
             busy[slot] = True
-        for slot in range(2):
+        for slot in range(TD):
             if busy[slot]:
                 tp.plans[slot].gss_finish()
                 busy[slot] = False
-    run_tiles(range(4))                                              # first (factorising) tile of each plan + warm-up
+    run_tiles(range(2 * TD))                                         # first (factorising) tile of each plan + warm-up
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
@@ -267,7 +268,7 @@ def run_config4(torch, dist, B, world, rank, local, dev, ntiles=64, side=2048, w
     dt, t_bcast = float(t[0]), float(t[1])
     return {'workload': 'c4: %d science tiles of %dx%d against one shared template, KerHW=%d DK=%d DB=%d, %s storage' % (ntiles, side, side, w, DK, DB, storage),
             'value': ntiles * side * side / 1e6 / dt, 'unit': 'Mpix/s', 'n_gpus': world, 'tiles': ntiles,
-            'tiles_per_gpu': len(mine), 'ms_per_tile_per_gpu': dt * 1e3 / max(1, len(mine)), 'tiles_in_flight': 2,
+            'tiles_per_gpu': len(mine), 'ms_per_tile_per_gpu': dt * 1e3 / max(1, len(mine)), 'tiles_in_flight': TD,
             'template_prepare_ms': float(t[2]) * 1e3, 'template_broadcast_ms': t_bcast * 1e3 if world > 1 else None,
             'template_state_bytes': state_bytes,
             'collective': 'one torch.distributed.broadcast (NCCL) of the template row spectra, timed after a warm-up collective' if world > 1 else None,

@@ -175,19 +175,20 @@ class PairPipeline:
 
 
 class TemplatePipeline:
-    """Science tiles against ONE shared template on one GPU (BASELINE config 4): two plans hold the same template state;
+    """Science tiles against ONE shared template on one GPU (BASELINE config 4): `depth` plans hold the same template state;
     tiles go through sfftb_gss_template_submit / sfftb_gss_finish alternately, so the copies (host tiles) and kernels of
     tile k + 1 run under the kernels and the device-to-host copy of tile k.  Under torch.distributed the first plan is
     the one that received TemplateBatch's single broadcast (`first_plan`)."""
 
     def __init__(self, N0, N1, KerHW, KerPolyOrder=2, BGPolyOrder=2, ConstPhotRatio=True, device=0, storage='fp64',
-                 stream_ptr=None, first_plan=None):
+                 stream_ptr=None, first_plan=None, depth=2):
         import torch
         from .plan import Plan
         self.device = device
+        depth = max(2, int(depth))
         mk = lambda: Plan(N0, N1, KerHW, KerHW, KerPolyOrder, BGPolyOrder, ConstPhotRatio, device=device, storage=storage)
-        self.plans = [first_plan if first_plan is not None else mk(), mk()]
-        self._own = [first_plan is None, True]
+        self.plans = [first_plan if first_plan is not None else mk()] + [mk() for _ in range(depth - 1)]
+        self._own = [first_plan is None] + [True] * (depth - 1)
         # stream_ptr given: both plans queue on it (tiles strictly one after the other).  None / 0: every plan keeps its OWN
         # stream, so the kernels of tile k + 1 also overlap the latency-bound substitutions of tile k; that is safe because
         # the only cooperative kernel of a cached-factor tile is the substitution kernel, whose grid is capped at half of the
@@ -195,7 +196,7 @@ class TemplatePipeline:
         if stream_ptr:
             for pl in self.plans:
                 pl.set_stream(stream_ptr)
-        self._busy = [False, False]
+        self._busy = [False] * depth
         self._k = 0
 
     def set_template(self, PixA_I=None, PixA_mI=None):
@@ -204,12 +205,14 @@ class TemplatePipeline:
         import torch
         if PixA_I is not None:
             self.plans[0].template_prepare(PixA_I, PixA_mI)
-        self.plans[1].template_state_tensor().copy_(self.plans[0].template_state_tensor())
+        for pl in self.plans[1:]:
+            pl.template_state_tensor().copy_(self.plans[0].template_state_tensor())
         torch.cuda.synchronize(torch.device('cuda', self.device))
-        self.plans[1].template_mark_ready()
+        for pl in self.plans[1:]:
+            pl.template_mark_ready()
 
     def submit(self, PixA_J, PixA_mJ, out_dtype=np.float64, Solution_out=None, DIFF_out=None):
-        slot = self._k % 2
+        slot = self._k % len(self.plans)
         done = None
         if self._busy[slot]:
             done = self.plans[slot].gss_finish()
@@ -220,8 +223,9 @@ class TemplatePipeline:
 
     def drain(self):
         out = []
-        for d in range(2):
-            slot = (self._k + d) % 2
+        n = len(self.plans)
+        for d in range(n):
+            slot = (self._k + d) % n
             if self._busy[slot]:
                 out.append(self.plans[slot].gss_finish())
                 self._busy[slot] = False
