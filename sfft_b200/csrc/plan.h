@@ -15,6 +15,7 @@
 #include "kernels_row_fast.cuh"
 #include "kernels_row_v8.cuh"
 #include "kernels_row_h16.cuh"
+#include "kernels_row_g16.cuh"
 #include "kernels_fit_seg.cuh"
 #include "kernels_fit_seg3.cuh"
 #include "kernels_fit_seg4.cuh"
@@ -80,6 +81,7 @@ struct sfftb_plan {
     int row_v8;                  // 0 or the engine length H
     int row_h16;                 // 0 or H: R x 256 forward row pass on the half-warp engine (kernels_row_h16.cuh)
     RowH16Args rowh;
+    int row_g16;                 // 0 or R: N1 = 512 R with R in {3, 5, 6, 10, 12} (kernels_row_g16.cuh), forward and inverse
     size_t smem_rowv;
     double* PHI;
     int *idxmap, *ident;

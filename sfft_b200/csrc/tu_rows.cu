@@ -72,6 +72,30 @@ int rows_setup(sfftb_plan* p) {
 #undef SET_ROWH
         p->row_h16 = r.H;
     }
+    p->row_g16 = 0;
+    if (r.packed && !p->row_fast && !env_int("SFFTB_ROW_GENERIC", 0) && !env_int("SFFTB_ROW_NOG16", 0) && r.H % 256 == 0 &&
+        rowg_supported(r.H / 256) && rowg_smem_bytes(r.H / 256) <= p->max_smem) {
+        const int R = r.H / 256;
+        if (upload_engine_table(256, R, &p->tabB_row)) return SFFTB_ECUDA;
+        RowH16Args& rh = p->rowh;
+        rh.N0 = d.N0; rh.N1 = d.N1; rh.NH = d.N1 / 2 + 1; rh.H = r.H;
+        rh.tabA = p->tabA; rh.twP = p->tabB_row; rh.tw1 = p->tw1; rh.vtab = nullptr;
+        RowFastArgs& rf = p->rowf;
+        rf.N0 = d.N0; rf.N1 = d.N1; rf.NH = d.N1 / 2 + 1; rf.H = r.H;
+        rf.tabA = p->tabA; rf.tabB = p->tabB_row; rf.tabC = nullptr; rf.tw1 = p->tw1;
+        p->rinvf.r = rf; p->rinvf.scale = p->rinv.scale; p->rinvf.Fpq = d.Fpq; p->rinvf.row0 = 0;
+        memcpy(p->rinvf.p_of, p->rinv.p_of, 16); memcpy(p->rinvf.q_of, p->rinv.q_of, 16);
+        const size_t smg = rowg_smem_bytes(R);
+#define SET_ROWG(RR)                                                                                              \
+        if (R == RR) {                                                                                                \
+            if (f32 && (set_smem(row_fwd_g16_kernel<float, float2, RR>, smg) || set_smem(row_fwd_g16_kernel<double, float2, RR>, smg))) return SFFTB_ECUDA; \
+            if (set_smem(row_fwd_g16_kernel<float, double2, RR>, smg) || set_smem(row_fwd_g16_kernel<double, double2, RR>, smg)) return SFFTB_ECUDA; \
+            if (set_smem(row_inv_g16_kernel<double2, float, RR>, smg) || set_smem(row_inv_g16_kernel<double2, double, RR>, smg)) return SFFTB_ECUDA; \
+        }
+        SET_ROWG(3) SET_ROWG(5) SET_ROWG(6) SET_ROWG(10) SET_ROWG(12)
+#undef SET_ROWG
+        p->row_g16 = R;
+    }
     if (p->row_fast) {
         const size_t sm = sizeof(cd) * (size_t)(ROWF_NT / (r.H / 16)) * (r.H + r.H / 16);
 #define SET_ROWF(HH)                                                                                              \
@@ -91,6 +115,22 @@ int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj, 
     RowFastArgs rowf = p->rowf; rowf.vtab = vtab;
     RowArgs rowg = p->row; rowg.vtab = vtab;
     const size_t esz2 = dtype == SFFTB_F64 ? 16 : 8;
+    if (p->row_g16 && ((uintptr_t)img % esz2) == 0) {
+        RowH16Args rowh = p->rowh; rowh.vtab = vtab;
+        const int R = p->row_g16, RBI = rowg_rbi(R);
+        const int ngroups = (p->d.N0 + RBI - 1) / RBI;
+        const int grid = std::min(ngroups, p->row_grid_limit > 0 ? p->row_grid_limit : work_sms(p));
+        const size_t smg = rowg_smem_bytes(R);
+#define RUN_ROWG(RR)                                                                                                   \
+        if (R == RR) {                                                                                                 \
+            if (dtype == SFFTB_F64) row_fwd_g16_kernel<double, TSt, RR><<<grid, RowgCfg<RR>::nt, smg, p->stream>>>(rowh, (const double*)img, out, nj); \
+            else row_fwd_g16_kernel<float, TSt, RR><<<grid, RowgCfg<RR>::nt, smg, p->stream>>>(rowh, (const float*)img, out, nj);                     \
+        }
+        RUN_ROWG(3) RUN_ROWG(5) RUN_ROWG(6) RUN_ROWG(10) RUN_ROWG(12)
+#undef RUN_ROWG
+        CKL(p);
+        return 0;
+    }
     if (p->row_h16 == 8192 && ((uintptr_t)img % esz2) == 0) {
         RowH16Args rowh = p->rowh; rowh.vtab = vtab;
         const int grid = std::min(p->d.N0, (p->row_grid_limit > 0 ? p->row_grid_limit : work_sms(p)));
@@ -179,6 +219,22 @@ int launch_row_inv(sfftb_plan* p, const double* bpq, void* ddiff, int diff_dtype
             CK(cudaEventRecord(p->evJoin, p->stream2));
             if (!p->defer_join) CK(cudaStreamWaitEvent(p->stream, p->evJoin, 0));
         }
+        return 0;
+    }
+    if (p->row_g16 && ((uintptr_t)ddiff % osz2) == 0) {
+        const int R = p->row_g16, RBI = rowg_rbi(R);
+        const int ngroups = (d.N0 + RBI - 1) / RBI;
+        const int grid = std::min(ngroups, p->row_grid_limit > 0 ? p->row_grid_limit : work_sms(p));
+        const size_t smg = rowg_smem_bytes(R);
+        p->rinvf.Fpq = p->rinv.Fpq;
+#define RUN_RINVG(RR)                                                                                                  \
+        if (R == RR) {                                                                                                 \
+            if (diff_dtype == SFFTB_F64) row_inv_g16_kernel<TSt, double, RR><<<grid, RowgCfg<RR>::nt, smg, p->stream>>>(p->rinvf, p->tabB_row, (const TSt*)p->gJa, bpq, (double*)ddiff); \
+            else row_inv_g16_kernel<TSt, float, RR><<<grid, RowgCfg<RR>::nt, smg, p->stream>>>(p->rinvf, p->tabB_row, (const TSt*)p->gJa, bpq, (float*)ddiff);                            \
+        }
+        RUN_RINVG(3) RUN_RINVG(5) RUN_RINVG(6) RUN_RINVG(10) RUN_RINVG(12)
+#undef RUN_RINVG
+        CKL(p);
         return 0;
     }
     const int grid = (d.N0 + p->row.RB - 1) / p->row.RB;
