@@ -33,6 +33,15 @@ struct GenPass {
     int rowbase[GEN_NA * GEN_NB];    // first kap row of pair (a, b), -1 = pair not needed
     int ninv;                        // number of needed pairs
     unsigned char inv_q[GEN_NA * GEN_NB];        // their accumulator indices a * GEN_NB + b, ascending
+    // Local support of the 1-D functions (B-splines vanish outside a few knot intervals; BSplineSFFT.py:2624-2634): a window
+    // whose U factor is identically zero has a zero spectrum, so its transform and every product with it are skipped.
+    //   jobs[]    : the transforms that are really run, (segment << 4) | spectrum index p (A roles, then transformed B roles),
+    //               ascending; every segment keeps at least one (the ring protocol walks through all segments);
+    //   seginfo[] : per segment, bits 0..4 = A slots with a non-zero window, bits 5..9 = B slots to multiply with (transformed
+    //               ones with a non-zero window, background row functions always), bits 16.. = number of jobs of the segment.
+    const unsigned short* jobs;
+    const unsigned* seginfo;
+    int njobs;
 };
 
 struct GenFitArgs {
@@ -138,6 +147,7 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_gen4_kernel(GenFitArgs fa, GenP
             for (int s = 0; s < nseg; ++s) {
                 const int gs = g + s, slot = gs & 1;
                 // background B slots: their spectrum is a table, independent of the column (loaded before the wait)
+                const unsigned sm = __ldg(ps.seginfo + s);                  // non-zero A slots | B slots (uniform over the CTA)
                 cd fB[NB];
 #pragma unroll
                 for (int b = 0; b < NB; ++b)
@@ -145,20 +155,22 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_gen4_kernel(GenFitArgs fa, GenP
                 fs3_mbar_wait(full + slot, (gs >> 1) & 1);
                 {
                     const cd* sp = spec + (size_t)slot * NPMAX * FS3_PITCH + HPAD(tid);
-                    cd fA[NA];
-#pragma unroll
-                    for (int A = 0; A < NA; ++A) fA[A] = (A < ps.na) ? sp[A * FS3_PITCH] : cmake(0.0, 0.0);   // unused slots hold inverse-phase scratch
+                    // slots that are unused or skipped hold stale spectra / inverse-phase scratch and are never read
 #pragma unroll
                     for (int b = 0; b < NB; ++b)
-                        if (b < ps.nbt) fB[b] = sp[(NA + b) * FS3_PITCH];
+                        if (b < ps.nbt && ((sm >> (5 + b)) & 1u)) fB[b] = sp[(NA + b) * FS3_PITCH];
 #pragma unroll
-                    for (int A = 0; A < NA; ++A)
+                    for (int A = 0; A < NA; ++A) {
+                        if (!((sm >> A) & 1u)) continue;
+                        const cd fA = sp[A * FS3_PITCH];
 #pragma unroll
                         for (int b = 0; b < NB; ++b) {
+                            if (!((sm >> (5 + b)) & 1u)) continue;
                             cd& c = acc[A * NB + b];
-                            c.x = fma(fA[A].x, fB[b].x, c.x); c.x = fma(fA[A].y, fB[b].y, c.x);
-                            c.y = fma(fA[A].x, fB[b].y, c.y); c.y = fma(-fA[A].y, fB[b].x, c.y);
+                            c.x = fma(fA.x, fB[b].x, c.x); c.x = fma(fA.y, fB[b].y, c.x);
+                            c.y = fma(fA.x, fB[b].y, c.y); c.y = fma(-fA.y, fB[b].x, c.y);
                         }
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) fs3_publish(cons + warp, (unsigned)(gs + 1));
@@ -186,7 +198,7 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_gen4_kernel(GenFitArgs fa, GenP
         // ====================================== transform warps ======================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FS4_REGT));
         const int fw = warp - 8;
-        const int njobs = nseg * NP;
+        const int njobs = ps.njobs;               // the transforms with a non-zero window
         H16Tw htw;
         h16_load(htw, tabA, hl);
         int seenL = 0;
@@ -195,31 +207,43 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_gen4_kernel(GenFitArgs fa, GenP
             for (int id0 = 2 * fw; id0 < njobs; id0 += FS4_NWK) {
                 const bool active = id0 + half < njobs;
                 const int id = active ? id0 + half : id0;
-                const int s = id / NP, p = id - s * NP;
+                const unsigned jb = __ldg(ps.jobs + id);
+                const int s = (int)(jb >> 4), p = (int)(jb & 15u);
                 const int gs = g + s, slot = gs & 1;
-                const int gsB = g + min(id0 + 1, njobs - 1) / NP;
+                const int gsB = g + (int)(__ldg(ps.jobs + min(id0 + 1, njobs - 1)) >> 4);
+                // the first job of a segment also stands in for the skipped ones on the slot's barrier
+                const bool first = id == 0 || (int)(__ldg(ps.jobs + id - 1) >> 4) != s;
+                const unsigned narrive = 1u + (first ? (unsigned)NP - (__ldg(ps.seginfo + s) >> 16) : 0u);
                 const bool roleA = p < ps.na;
                 const int bs = p - ps.na;
                 const bool isJ = !roleA && ps.b_type[bs] == 1;
                 const int my_u = roleA ? ps.a_u[p] : ps.b_u[bs];
                 const int my_src = roleA ? ps.a_src[p] : ps.b_src[bs];
                 const int c0 = s * S, Sc = min(S, N0 - c0);
+                // the U factors of the window do not depend on the staged data: request them before the waits, so that their
+                // latency (L2: the tables of a pass do not fit the small L1 left beside 185 KB of shared memory) is hidden
+                const double* urow = fa.U + (size_t)(isJ ? 0 : my_u) * N0;
+                const int klo = (roleA ? h : 0) - hl, khi = (active ? (roleA ? h + Sc : FS3_M) : 0) - hl;   // keep <=> klo <= 16 q < khi
+                double uu[16];
+                {
+                    int r = wrap_row(c0 - h + hl, N0);
+                    const int step = 16 % N0;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        uu[q] = (16 * q >= klo && 16 * q < khi) ? (isJ ? 1.0 : __ldg(urow + r)) : 0.0;
+                        r += step;
+                        if (r >= N0) r -= N0;
+                    }
+                }
                 while (seenL <= gsB) { fs4_wait_landed(landed + (seenL & (NSTG - 1)), (seenL >> LOG2STG) & 1, cons, (unsigned)seenL); ++seenL; }
                 if (gsB >= 2) fs3_wait_consumed(cons, (unsigned)(gsB - 1));
                 const TSt* src = stage + ((size_t)(gs & (NSTG - 1)) * GEN_MAXSRC + my_src) * FS3_M;
                 cd* plane = spec + ((size_t)slot * NPMAX + (roleA ? p : NA + bs)) * FS3_PITCH;
-                const double* urow = fa.U + (size_t)(isJ ? 0 : my_u) * N0;
-                const int klo = (roleA ? h : 0) - hl, khi = (active ? (roleA ? h + Sc : FS3_M) : 0) - hl;   // keep <=> klo <= 16 q < khi
                 cd v[16];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const cd gg = load_c(src + hl + 16 * q);
-                    int r = c0 - h + hl + 16 * q;
-                    while (r < 0) r += N0;
-                    while (r >= N0) r -= N0;
-                    double sc = isJ ? 1.0 : __ldg(urow + r);
-                    sc = (16 * q >= klo && 16 * q < khi) ? sc : 0.0;
-                    v[q] = cmake(gg.x * sc, gg.y * sc);
+                    v[q] = cmake(gg.x * uu[q], gg.y * uu[q]);
                 }
                 hfft256(v, plane, hl, htw, -1.0, active);
                 if (active) {
@@ -227,7 +251,8 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_gen4_kernel(GenFitArgs fa, GenP
                     for (int q = 0; q < 16; ++q) plane[HPAD(hl + 16 * q)] = v[q];
                 }
                 __syncwarp();
-                if (hl == 0 && active) fs3_mbar_arrive(full + slot);
+                if (hl == 0 && active)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(fs3_saddr(full + slot)), "r"(narrive) : "memory");
             }
             fs3_bar0();                                    // (A)
             fs3_bar0();

@@ -14,6 +14,7 @@ struct GenState {
     cd *dQ, *dTF;
     int *d_fu, *d_fv;
     std::vector<GenPass> passes;
+    long long jobs_run, jobs_dense;  // transforms per column over all passes: really run / without the local-support skip
     GenFitArgs fit;
     size_t smem_fit;
     int nrows;
@@ -269,6 +270,56 @@ int gen_plan_create(sfftb_plan* p, const sfftb_config* cfg, const sfftb_basis* k
             for (int q = 0; q < GEN_NA * GEN_NB; ++q) if (ps.rowbase[q] >= 0) ps.inv_q[ps.ninv++] = (unsigned char)q;
             g->passes.push_back(ps);
         }
+    // ---- local support: per pass, the transforms that are really run and the per-segment slot masks (GenPass::jobs) ----
+    {
+        const int M = FS3_M, nseg = fa.nseg, S = fa.S, h = fa.h;
+        const int nUall = (int)(hU.size() / (size_t)N0);
+        // zA[u][s]: U_u is non-zero somewhere in the core rows of segment s; zB[u][s]: ... in its 256-row window (halo included)
+        const bool dense = env_int("SFFTB_GEN_DENSE", 0) != 0;       // parity hook: no skipping
+        std::vector<char> zA((size_t)nUall * nseg, dense ? 1 : 0), zB((size_t)nUall * nseg, dense ? 1 : 0);
+        for (int u = 0; u < nUall && !dense; ++u)
+            for (int sg = 0; sg < nseg; ++sg) {
+                const int c0 = sg * S, Sc = std::min(S, N0 - c0);
+                for (int n = 0; n < M; ++n) {
+                    if (hU[(size_t)u * N0 + host_wrap(c0 - h + n, N0)] == 0.0) continue;
+                    zB[(size_t)u * nseg + sg] = 1;
+                    if (n >= h && n < h + Sc) zA[(size_t)u * nseg + sg] = 1;
+                }
+            }
+        std::vector<unsigned short> hjobs;
+        std::vector<unsigned> hseg;
+        std::vector<size_t> joff, soff;
+        size_t njobs_all = 0, njobs_dense = 0;
+        if (nseg > 4095) return fail(SFFTB_EINVAL, "too many column segments (%d)", nseg);
+        for (GenPass& ps : g->passes) {
+            joff.push_back(hjobs.size()); soff.push_back(hseg.size());
+            const int NP = ps.na + ps.nbt;
+            int nj = 0;
+            for (int sg = 0; sg < nseg; ++sg) {
+                unsigned am = 0, bm = 0;
+                for (int a = 0; a < ps.na; ++a) if (zA[(size_t)ps.a_u[a] * nseg + sg]) am |= 1u << a;
+                for (int b = 0; b < ps.nb; ++b) {
+                    const bool nz = ps.b_type[b] == 0 ? zB[(size_t)ps.b_u[b] * nseg + sg] != 0 : true;     // J and the background tables: always
+                    if (nz) bm |= 1u << b;
+                }
+                if (am == 0 || bm == 0) { am = 0; bm = 0; }               // nothing to accumulate in this segment
+                unsigned cnt = 0;
+                for (int pp = 0; pp < NP; ++pp) {
+                    const bool run = pp < ps.na ? ((am >> pp) & 1u) : ((bm >> (pp - ps.na)) & 1u);
+                    if (run) { hjobs.push_back((unsigned short)((sg << 4) | pp)); ++cnt; }
+                }
+                if (cnt == 0) { hjobs.push_back((unsigned short)(sg << 4)); cnt = 1; }    // keeps the ring protocol walking
+                hseg.push_back(am | (bm << 5) | (cnt << 16));
+                nj += (int)cnt;
+            }
+            ps.njobs = nj;
+            njobs_all += (size_t)nj; njobs_dense += (size_t)NP * nseg;
+        }
+        unsigned short* djobs = nullptr; unsigned* dseg = nullptr;
+        if (dev_upload(g, hjobs, &djobs) || dev_upload(g, hseg, &dseg)) return SFFTB_ECUDA;
+        for (size_t i = 0; i < g->passes.size(); ++i) { g->passes[i].jobs = djobs + joff[i]; g->passes[i].seginfo = dseg + soff[i]; }
+        g->jobs_run = (long long)njobs_all; g->jobs_dense = (long long)njobs_dense;
+    }
     g->nrows = nrows;
     fa.nrows = nrows;
     if (dev_alloc(g, (size_t)NH * nrows, &g->kap)) return SFFTB_ECUDA;

@@ -162,3 +162,36 @@ def test_bspline_packet_arrays_nan_union(bs):
     od[U] = np.nan
     assert np.array_equal(np.isnan(d), np.isnan(od))
     assert relrms(d, od) < 1e-6
+
+
+def test_local_support_skip_is_exact(bs, monkeypatch):
+    """Several column segments (N0 = 520 -> three), B-spline row functions with knots inside the image: the fit column pass skips the
+    transforms and products of windows on which a basis function vanishes (GenPass::jobs / seginfo).  The result must be the one of
+    the dense pass bit for bit (skipped terms are exact zeros), and match the design-matrix oracle."""
+    N0, N1, w = 520, 48, 2
+    I, J, mI, mJ = _pair(N0, N1, 4242)
+    kw = dict(KerSpType='B-Spline', KerSpDegree=2, KerIntKnotX=[180.0, 340.0], KerIntKnotY=[20.0], SEPARATE_SCALING=True,
+              ScaSpType='Polynomial', ScaSpDegree=1, BkgSpType='Polynomial', BkgSpDegree=2)
+    out = []
+    for dense in ('0', '1'):
+        monkeypatch.setenv('SFFTB_GEN_DENSE', dense)
+        cfg = bs.SingleSFFTConfigure.SSC(NX=N0, NY=N1, KerHW=w, VERBOSE_LEVEL=0, FORCE_GENERAL_PLAN=True, **kw)
+        sol, diff, _ = bs.GeneralSFFTSubtract.GSS(I, J, mI, mJ, cfg, VERBOSE_LEVEL=0)
+        L, b = cfg[1]['plan'].export_solved_system()
+        out.append((sol, diff, L, b, cfg))
+    monkeypatch.delenv('SFFTB_GEN_DENSE')
+    # LHMAT comes from the lag tables alone: identical bit for bit.  The J x background entries of the right-hand side are summed
+    # with atomics (gen_rjt_kernel), so they -- and with them Solution and DIFF -- repeat only to rounding from run to run.
+    assert np.array_equal(out[0][2], out[1][2])
+    b0, b1 = out[0][3], out[1][3]
+    assert np.count_nonzero(b0 != b1) <= cfg[0]['Fpq'] and np.max(np.abs(b0 - b1)) <= 1e-13 * np.max(np.abs(b0))
+    assert np.max(np.abs(out[0][0] - out[1][0])) <= 1e-8 * np.max(np.abs(out[0][0]))
+    assert relrms(out[0][1], out[1][1]) < 1e-10
+    P = bo.ssc_params(N0, N1, w, **kw)
+    ex = {}
+    osol, _ = bo.ess(mI, mJ, P, None, False, export=ex)
+    L, b = out[0][2], out[0][3]
+    assert np.max(np.abs(b - ex['RHb_tweaked'])) <= 1e-9 * np.max(np.abs(ex['RHb_tweaked']))
+    assert np.max(np.abs(L - ex['LHMAT_tweaked'])) <= 1e-9 * np.max(np.abs(ex['LHMAT_tweaked']))
+    _, od = bo.ess(I, J, P, osol, True)
+    assert relrms(out[0][1], od) < 1e-6
