@@ -61,8 +61,11 @@ struct GenFitArgs {
 // 8 product warps (thread = frequency bin, GEN_NA x GEN_NB accumulators) + 8 transform warps = 16 half-warp workers; one
 // shared-memory exchange per 256-point transform instead of two; the window load is branch-free (the halves of a warp differ in
 // role and table); every needed accumulator gets a plane, so a column ends with ONE inverse batch on the 32 half warps.
-#define GEN_NPLANES 26               // >= 2 (GEN_NA + GEN_NB) ring planes and >= GEN_NA GEN_NB inverse planes
-static_assert(GEN_NPLANES >= 2 * (GEN_NA + GEN_NB) && GEN_NPLANES >= GEN_NA * GEN_NB, "planes of the general fit kernel");
+#ifndef GEN_NSLOT
+#define GEN_NSLOT 3                  // spectrum ring slots: the transforms of segment s + 2 start while the products of s still run
+#endif
+#define GEN_NPLANES (GEN_NSLOT * (GEN_NA + GEN_NB) > 26 ? GEN_NSLOT * (GEN_NA + GEN_NB) : 26)   // ring planes, and >= GEN_NA GEN_NB inverse planes
+static_assert(GEN_NPLANES >= GEN_NSLOT * (GEN_NA + GEN_NB) && GEN_NPLANES >= GEN_NA * GEN_NB, "planes of the general fit kernel");
 static inline size_t gen_fit4_smem_bytes(bool f32) {
     return sizeof(cd) * (size_t)GEN_NPLANES * FS3_PITCH + 128 + (f32 ? sizeof(float2) * 8 : sizeof(double2) * 4) * (size_t)GEN_MAXSRC * FS3_M;
 }
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_gen4_kernel(GenFitArgs fa, GenP
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(spec + GEN_NPLANES * FS3_PITCH);
     unsigned* cons = reinterpret_cast<unsigned*>(bars + 12);      // [8] segments consumed by product warp w (fs3_publish)
     TSt* stage = reinterpret_cast<TSt*>(bars + 16);
-    unsigned long long* full = bars;          // [2]  count NP   (one arrive per transform job)
+    unsigned long long* full = bars;          // [GEN_NSLOT]  count NP   (one arrive per transform job, skipped ones included)
     unsigned long long* landed = bars + 4;    // [NSTG] count 256  (cp.async arrivals of the product threads)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, half = lane >> 4, hl = lane & 15;
     const int h = fa.h, S = fa.S, nseg = fa.nseg, N0 = fa.N0;
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_gen4_kernel(GenFitArgs fa, GenP
     const int nsrc = ps.nsrc;
 
     if (tid == 0) {
-        fs3_mbar_init(full + 0, NP); fs3_mbar_init(full + 1, NP);
+        for (int b = 0; b < GEN_NSLOT; ++b) fs3_mbar_init(full + b, NP);
         for (int b = 0; b < NSTG; ++b) fs3_mbar_init(landed + b, 256);
     }
     if (tid < 8) cons[tid] = 0u;
@@ -145,27 +148,27 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_gen4_kernel(GenFitArgs fa, GenP
             };
             for (int s = 0; s < PFD && s < nseg; ++s) issue(s);
             for (int s = 0; s < nseg; ++s) {
-                const int gs = g + s, slot = gs & 1;
+                const int gs = g + s, gq = gs / GEN_NSLOT, slot = gs - gq * GEN_NSLOT;
                 // background B slots: their spectrum is a table, independent of the column (loaded before the wait)
                 const unsigned sm = __ldg(ps.seginfo + s);                  // non-zero A slots | B slots (uniform over the CTA)
                 cd fB[NB];
 #pragma unroll
                 for (int b = 0; b < NB; ++b)
                     fB[b] = (b < ps.nb && ps.b_type[b] == 2) ? fa.TF[((size_t)s * fa.Fp + ps.b_u[b]) * FS3_M + tid] : cmake(0.0, 0.0);
-                fs3_mbar_wait(full + slot, (gs >> 1) & 1);
+                fs3_mbar_wait(full + slot, gq & 1);
                 {
                     const cd* sp = spec + (size_t)slot * NPMAX * FS3_PITCH + HPAD(tid);
-                    // slots that are unused or skipped hold stale spectra / inverse-phase scratch and are never read
+                    // slots that are unused or skipped hold stale spectra / inverse-phase scratch and are never read: a skipped B
+                    // slot enters the products as an exact zero, a skipped A slot skips its row of products
 #pragma unroll
                     for (int b = 0; b < NB; ++b)
-                        if (b < ps.nbt && ((sm >> (5 + b)) & 1u)) fB[b] = sp[(NA + b) * FS3_PITCH];
+                        if (b < ps.nbt) fB[b] = ((sm >> (5 + b)) & 1u) ? sp[(NA + b) * FS3_PITCH] : cmake(0.0, 0.0);
 #pragma unroll
                     for (int A = 0; A < NA; ++A) {
                         if (!((sm >> A) & 1u)) continue;
                         const cd fA = sp[A * FS3_PITCH];
 #pragma unroll
                         for (int b = 0; b < NB; ++b) {
-                            if (!((sm >> (5 + b)) & 1u)) continue;
                             cd& c = acc[A * NB + b];
                             c.x = fma(fA.x, fB[b].x, c.x); c.x = fma(fA.y, fB[b].y, c.x);
                             c.y = fma(fA.x, fB[b].y, c.y); c.y = fma(-fA.y, fB[b].x, c.y);
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_gen4_kernel(GenFitArgs fa, GenP
                 const int id = active ? id0 + half : id0;
                 const unsigned jb = __ldg(ps.jobs + id);
                 const int s = (int)(jb >> 4), p = (int)(jb & 15u);
-                const int gs = g + s, slot = gs & 1;
+                const int gs = g + s, slot = gs % GEN_NSLOT;
                 const int gsB = g + (int)(__ldg(ps.jobs + min(id0 + 1, njobs - 1)) >> 4);
                 // the first job of a segment also stands in for the skipped ones on the slot's barrier
                 const bool first = id == 0 || (int)(__ldg(ps.jobs + id - 1) >> 4) != s;
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_gen4_kernel(GenFitArgs fa, GenP
                     }
                 }
                 while (seenL <= gsB) { fs4_wait_landed(landed + (seenL & (NSTG - 1)), (seenL >> LOG2STG) & 1, cons, (unsigned)seenL); ++seenL; }
-                if (gsB >= 2) fs3_wait_consumed(cons, (unsigned)(gsB - 1));
+                if (gsB >= GEN_NSLOT) fs3_wait_consumed(cons, (unsigned)(gsB - (GEN_NSLOT - 1)));
                 const TSt* src = stage + ((size_t)(gs & (NSTG - 1)) * GEN_MAXSRC + my_src) * FS3_M;
                 cd* plane = spec + ((size_t)slot * NPMAX + (roleA ? p : NA + bs)) * FS3_PITCH;
                 cd v[16];
