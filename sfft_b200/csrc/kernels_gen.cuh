@@ -516,7 +516,16 @@ __global__ void __launch_bounds__(128) gen_taps_kernel(GenFirArgs a, const doubl
 }
 #endif
 
-// smem: h[nap][L0] cd | cA[nap] double | uw[nU][W] double | st[nvs][W] cd,  W = GFIR_CH + 2 w0
+// smem: h[nap][L0] cd | cA[nap] double | uw[nU][W] double | st[nvs][W] cd | uflag[nU] | jfirst[nvs + 1] | alist[nap],  W = GFIR_CH + 2 w0
+// Local support: a B-spline row function that vanishes on the whole staged window of this chunk contributes nothing; the CTA
+// compacts the apply planes with a non-zero window into alist (per stored plane j: entries jfirst[j] .. jfirst[j + 1] - 1) and
+// loops over those only.  The GFIR_R output rows of a thread share every tap load.
+static inline size_t gen_fir_smem_bytes(int nap, int L0, int nU, int nvs, int w0) {
+    const size_t W = GFIR_CH + 2 * (size_t)w0, nuw = (size_t)nU * W;
+    return sizeof(cd) * (size_t)nap * L0 + sizeof(double) * (((size_t)nap + 1) & ~(size_t)1) + sizeof(double) * (nuw + (nuw & 1)) +
+           sizeof(cd) * (size_t)nvs * W + sizeof(int) * (size_t)(((nU + 3) & ~3) + ((nvs + 1 + 3) & ~3)) + sizeof(int4) * (size_t)nap;
+}
+
 template <typename TSt>
 __global__ void __launch_bounds__(GFIR_NT) gen_fir_kernel(GenFirArgs a, const TSt* __restrict__ gP, const TSt* gJ,
                                                           const cd* __restrict__ taps, const double* __restrict__ cAin, TSt* outD)
@@ -527,47 +536,92 @@ __global__ void __launch_bounds__(GFIR_NT) gen_fir_kernel(GenFirArgs a, const TS
     double* cA = reinterpret_cast<double*>(h + (size_t)a.nap * L0);
     double* uw = cA + ((a.nap + 1) & ~1);
     cd* st = reinterpret_cast<cd*>(uw + (size_t)a.nU * W + (((size_t)a.nU * W) & 1));
+    int* uflag = reinterpret_cast<int*>(st + (size_t)a.nvs * W);
+    int* jfirst = uflag + ((a.nU + 3) & ~3);
+    int4* alist = reinterpret_cast<int4*>(jfirst + ((a.nvs + 1 + 3) & ~3));         // {U row offset, tap offset, apply plane, -}
     const int tid = threadIdx.x, k1 = blockIdx.x, rbeg = blockIdx.y * GFIR_CH;
 
+    for (int u = tid; u < a.nU; u += GFIR_NT) uflag[u] = 0;
+    __syncthreads();
     for (int idx = tid; idx < W; idx += GFIR_NT) {
         int r = (rbeg - a.w0 + idx) % a.N0; if (r < 0) r += a.N0;
-        for (int u = 0; u < a.nU; ++u) uw[(size_t)u * W + idx] = a.U[(size_t)u * a.N0 + r];
+        for (int u = 0; u < a.nU; ++u) {
+            const double v = a.U[(size_t)u * a.N0 + r];
+            uw[(size_t)u * W + idx] = v;
+            if (v != 0.0) uflag[u] = 1;
+        }
         for (int j = 0; j < a.nvs; ++j) st[(size_t)j * W + idx] = load_c(gP + (size_t)a.vs_id[j] * a.plane_stride + (size_t)k1 * a.N0 + r);
     }
     for (int idx = tid; idx < a.nap * L0; idx += GFIR_NT) h[idx] = taps[(size_t)k1 * a.nap * L0 + idx];
     for (int idx = tid; idx < a.nap; idx += GFIR_NT) cA[idx] = cAin[idx];
     __syncthreads();
-
-#pragma unroll
-    for (int o = 0; o < GFIR_R; ++o) {
-        const int lo = tid + o * GFIR_NT;                  // output row within the chunk
-        const int r = rbeg + lo;
-        if (r >= a.N0) continue;
-        cd acc = load_c(gJ + (size_t)k1 * a.N0 + r);
-        const int nc = lo + a.w0;                          // staged index of the output row itself
+    if (tid == 0) {
+        int n = 0;
         for (int j = 0; j < a.nvs; ++j) {
-            const cd* sj = st + (size_t)j * W;
-            const int A0 = a.vs_first[j], A1 = a.vs_first[j + 1];
-            {   // + c_A U_A(r) g[r]
-                double t = 0.0;
-                for (int A = A0; A < A1; ++A) t = fma(cA[A], uw[(size_t)a.ap_u[A] * W + nc], t);
-                const cd g = sj[nc];
-                acc.x = fma(t, g.x, acc.x); acc.y = fma(t, g.y, acc.y);
-            }
-            for (int ia = 0; ia < L0; ++ia) {
-                const int n = nc - (ia - a.w0);            // source row r - a
-                cd t = cmake(0.0, 0.0);
-                for (int A = A0; A < A1; ++A) {
-                    const double uu = uw[(size_t)a.ap_u[A] * W + n];
-                    const cd hh = h[A * L0 + ia];
-                    t.x = fma(hh.x, uu, t.x); t.y = fma(hh.y, uu, t.y);
-                }
-                const cd g = sj[n];
-                acc.x = fma(-t.x, g.x, acc.x); acc.x = fma(t.y, g.y, acc.x);
-                acc.y = fma(-t.x, g.y, acc.y); acc.y = fma(-t.y, g.x, acc.y);
+            jfirst[j] = n;
+            for (int A = a.vs_first[j]; A < a.vs_first[j + 1]; ++A) {
+                const int u = a.ap_u[A];
+                if (uflag[u]) alist[n++] = make_int4(u * W, A * L0, A, 0);
             }
         }
-        store_c(outD + (size_t)k1 * a.N0 + r, acc);
+        jfirst[a.nvs] = n;
+    }
+    __syncthreads();
+
+    cd acc[GFIR_R];
+    int nc[GFIR_R];                                        // staged index of the output row itself
+#pragma unroll
+    for (int o = 0; o < GFIR_R; ++o) {
+        const int lo = tid + o * GFIR_NT, r = rbeg + lo;
+        nc[o] = lo + a.w0;
+        acc[o] = r < a.N0 ? load_c(gJ + (size_t)k1 * a.N0 + r) : cmake(0.0, 0.0);
+    }
+    for (int j = 0; j < a.nvs; ++j) {
+        const cd* sj = st + (size_t)j * W;
+        const int x0 = jfirst[j], x1 = jfirst[j + 1];
+        if (x0 == x1) continue;
+        {   // + c_A U_A(r) g[r]
+            double t[GFIR_R];
+#pragma unroll
+            for (int o = 0; o < GFIR_R; ++o) t[o] = 0.0;
+            for (int x = x0; x < x1; ++x) {
+                const int4 e = alist[x];
+                const double c = cA[e.z];
+#pragma unroll
+                for (int o = 0; o < GFIR_R; ++o) t[o] = fma(c, uw[e.x + nc[o]], t[o]);
+            }
+#pragma unroll
+            for (int o = 0; o < GFIR_R; ++o) {
+                const cd g = sj[nc[o]];
+                acc[o].x = fma(t[o], g.x, acc[o].x); acc[o].y = fma(t[o], g.y, acc[o].y);
+            }
+        }
+        for (int ia = 0; ia < L0; ++ia) {
+            const int sh = ia - a.w0;                      // source row r - a
+            cd t[GFIR_R];
+#pragma unroll
+            for (int o = 0; o < GFIR_R; ++o) t[o] = cmake(0.0, 0.0);
+            for (int x = x0; x < x1; ++x) {
+                const int4 e = alist[x];
+                const cd hh = h[e.y + ia];
+#pragma unroll
+                for (int o = 0; o < GFIR_R; ++o) {
+                    const double uu = uw[e.x + nc[o] - sh];
+                    t[o].x = fma(hh.x, uu, t[o].x); t[o].y = fma(hh.y, uu, t[o].y);
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < GFIR_R; ++o) {
+                const cd g = sj[nc[o] - sh];
+                acc[o].x = fma(-t[o].x, g.x, acc[o].x); acc[o].x = fma(t[o].y, g.y, acc[o].x);
+                acc[o].y = fma(-t[o].x, g.y, acc[o].y); acc[o].y = fma(-t[o].y, g.x, acc[o].y);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < GFIR_R; ++o) {
+        const int r = rbeg + tid + o * GFIR_NT;
+        if (r < a.N0) store_c(outD + (size_t)k1 * a.N0 + r, acc[o]);
     }
 }
 

@@ -418,10 +418,7 @@ int gen_plan_create(sfftb_plan* p, const sfftb_config* cfg, const sfftb_basis* k
     }
     if (dev_alloc(g, (size_t)NH * fr.nap * d.L0, &g->taps) || dev_alloc(g, (size_t)fr.nap + 1, &g->cA)) return SFFTB_ECUDA;
     {
-        const size_t W = GFIR_CH + 2 * (size_t)w0;
-        const size_t nuw = (size_t)fr.nU * W;
-        g->smem_fir = sizeof(cd) * (size_t)fr.nap * d.L0 + sizeof(double) * (((size_t)fr.nap + 1) & ~(size_t)1) + sizeof(double) * (nuw + (nuw & 1)) +
-                      sizeof(cd) * (size_t)fr.nvs * W;
+        g->smem_fir = gen_fir_smem_bytes(fr.nap, d.L0, fr.nU, fr.nvs, w0);
         if (g->smem_fir > p->max_smem) return fail(SFFTB_EINVAL, "the general FIR kernel needs %zu bytes of shared memory", g->smem_fir);
         if (set_smem(gen_fir_kernel<double2>, g->smem_fir)) return SFFTB_ECUDA;
     }
