@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
     constexpr int NSRC = DK + 2;
     constexpr int NSLOT = Fs4Ring<TSt>::nslot;
     constexpr int NPL = NSLOT * NP;                   // planes in the spectrum ring
-    constexpr int NSTG = sizeof(TSt) == 8 ? FS4_NSTG : 4, LOG2STG = NSTG == 8 ? 3 : 2, PFD = NSTG - 2;   // fp64 windows: 4 buffers
+    constexpr int NSTG = sizeof(TSt) == 8 ? FS4_NSTG : 4, PFD = NSTG - 2;   // fp64 windows: 4 buffers (any depth, not only powers of two)
     static_assert(NACC <= FS4_NHW, "one half warp per accumulator in the inverse phase");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const ColArgs& a = fa.c;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
             // window prefetch: element tid of every stored plane, PF segments ahead; the ring runs on across the column
             // boundary (the first windows of the CTA's next column are requested during the last segments of this one)
             auto issue = [&](int kx, int gx, int s) {
-                const int buf = (gx + s) & (NSTG - 1);
+                const int buf = (int)((unsigned)(gx + s) % (unsigned)NSTG);
                 if (bulk) {
                     if (tid == 0) {
                         const int r0 = s * S - h;
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
                 const int c0 = s * S, Sc = min(S, a.N0 - c0);
                 // every phase of the window ring is observed in order: a parity wait is only unambiguous within one phase, and
                 // with few spectra per segment the consecutive jobs of a warp lie more than a ring length apart
-                while (seenL <= gsB) { fs4_wait_landed(landed + (seenL & (NSTG - 1)), (seenL >> LOG2STG) & 1, cons, (unsigned)seenL); ++seenL; }
+                while (seenL <= gsB) { fs4_wait_landed(landed + (unsigned)seenL % (unsigned)NSTG, ((unsigned)seenL / (unsigned)NSTG) & 1u, cons, (unsigned)seenL); ++seenL; }
 #ifdef FS4_DEBUG
                 long long f1 = clock64(); fWaitL += f1 - f0;
 #endif
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
 #ifdef FS4_DEBUG
                 long long f2 = clock64(); fWaitC += f2 - f1;
 #endif
-                const TSt* src = stage + ((size_t)(gs & (NSTG - 1)) * NSRC + my_src) * FS3_M;
+                const TSt* src = stage + ((size_t)((unsigned)gs % (unsigned)NSTG) * NSRC + my_src) * FS3_M;
                 cd* plane = spec + ((size_t)slot * NP + p) * FS4_PITCH;
                 cd v[16];
                 // Branch-free load (the two halves of the warp differ in role and power, and a divergent branch per element
