@@ -19,6 +19,7 @@
 #include "kernels_fit_seg.cuh"
 #include "kernels_fit_seg3.cuh"
 #include "kernels_fit_seg4.cuh"
+#include "kernels_fit_jcache.cuh"
 #include "kernels_reader.cuh"
 #include "kernels_fitsio.cuh"
 #include "kernels_gen.cuh"
@@ -129,6 +130,12 @@ struct sfftb_plan {
     RowFastArgs rowf;
     RowInvFastArgs rinvf;
     int row_fast;                // 0 or the engine length H
+    // shared-template tiles: A-role segment spectra of the template cached in HBM (kernels_fit_jcache.cuh)
+    cd* aspec; size_t aspec_elems;   // [NH][nseg][Fij][256]
+    long long aspec_epoch;           // template epoch the cache was built from (-1 = none)
+    long long tmpl_epoch;            // bumped whenever the template state changes
+    int aspec_off;                   // 1: allocation failed or switched off -> JONLY instantiation of fit_seg4_kernel
+    int grid_jc;                     // CTAs per SM of fit_jonly_cached_kernel
     // segmented fit path
     SegFitArgs sfit;
     int fit_seg;                 // 2: fit_seg3_kernel + lag_reduce2 path, 0: folded-slice generic kernel

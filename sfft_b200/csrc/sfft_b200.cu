@@ -175,7 +175,7 @@ static int plan_free(sfftb_plan* p) {
     cudaSetDevice(p->device);
     gen_free(p);
     void* ptrs[] = {p->vt8_8, p->vt64_8, p->vt64_4, p->vt256_4, p->vt512_4, p->tabA, p->tabB_row, p->tabC_row, p->tabC_row32, p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
-                    p->kap, p->lam, p->nuJ, p->kap2, p->momg, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->substMsg, p->solEff, p->regC, p->regD, p->regSST, p->regI, p->bluTw, p->bluC, p->bluB, p->firTaps, p->firCA, p->tstate, p->stC, p->stD, p->deltaIdx, p->deltaVal};
+                    p->kap, p->lam, p->nuJ, p->kap2, p->momg, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->substMsg, p->solEff, p->regC, p->regD, p->regSST, p->regI, p->bluTw, p->bluC, p->bluB, p->firTaps, p->firCA, p->tstate, p->stC, p->stD, p->deltaIdx, p->deltaVal, p->aspec};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->gIa && p->gIa != p->gI) cudaFree(p->gIa);
     if (p->gJa && p->gJa != p->gJ) cudaFree(p->gJa);
@@ -1185,6 +1185,7 @@ extern "C" int sfftb_template_prepare(sfftb_plan* p, const void* I, const void* 
     CK(cudaStreamSynchronize(p->stream));
     p->have_template = 1;
     p->factor_cached = 0;
+    p->tmpl_epoch++;
     return 0;
 }
 
@@ -1201,6 +1202,7 @@ extern "C" int sfftb_template_mark_ready(sfftb_plan* p) {
     if (!p || !p->tstate) return fail(SFFTB_ESTATE, "template state was never allocated");
     p->have_template = 1;
     p->factor_cached = 0;
+    p->tmpl_epoch++;
     return 0;
 }
 

@@ -32,8 +32,52 @@ int fit_setup(sfftb_plan* p) {
         }
         SET_SFIT3(0) SET_SFIT3(1) SET_SFIT3(2)
 #undef SET_SFIT3
+        // shared-template tiles with cached template spectra (kernels_fit_jcache.cuh)
+        p->grid_jc = 0;
+        if (d.DK <= 2 && !env_int("SFFTB_NO_ASPEC_CACHE", 0) && jcache_smem_bytes() <= p->max_smem) {
+            const size_t smj = jcache_smem_bytes();
+            int occ = 0;
+#define SET_JC(DKK)                                                                                               \
+            if (d.DK == DKK) {                                                                                        \
+                if (f32) { if (set_smem(aspec_cache_kernel<float2, DKK>, smj) || set_smem(fit_jonly_cached_kernel<float2, DKK>, smj)) return SFFTB_ECUDA;      \
+                           CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_jonly_cached_kernel<float2, DKK>, JC_NT, smj)); }                     \
+                else     { if (set_smem(aspec_cache_kernel<double2, DKK>, smj) || set_smem(fit_jonly_cached_kernel<double2, DKK>, smj)) return SFFTB_ECUDA;    \
+                           CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_jonly_cached_kernel<double2, DKK>, JC_NT, smj)); }                    \
+            }
+            SET_JC(0) SET_JC(1) SET_JC(2)
+#undef SET_JC
+            p->grid_jc = std::max(1, occ);
+        }
     }
     return 0;
+}
+
+// Cached A-role spectra of the template for the J-only column pass; returns false when the cache cannot be used (the caller
+// falls back to fit_seg4_kernel<JONLY>).
+template <typename TSt>
+static bool jcache_ready(sfftb_plan* p, const TSt* gIsrc) {
+    if (!p->grid_jc || p->aspec_off) return false;
+    const sfftb_dims& d = p->d;
+    const int NH = d.N1 / 2 + 1, Fij = d.Fij;
+    const size_t need = (size_t)NH * p->sfit.nseg * Fij * FS3_M;
+    if (!p->aspec || p->aspec_elems < need) {
+        if (p->aspec) { cudaFree(p->aspec); p->aspec = nullptr; }
+        if (cudaMalloc(&p->aspec, sizeof(cd) * need) != cudaSuccess) { cudaGetLastError(); p->aspec = nullptr; p->aspec_off = 1; return false; }
+        p->aspec_elems = need;
+        p->aspec_epoch = -1;
+    }
+    if (p->aspec_epoch != p->tmpl_epoch) {
+        const long long njobs = (long long)NH * p->sfit.nseg * Fij;
+        const int grid = (int)std::min<long long>((njobs + JC_NHW - 1) / JC_NHW, (long long)work_sms(p) * p->grid_jc);
+        const size_t smj = jcache_smem_bytes();
+        if (d.DK == 0) aspec_cache_kernel<TSt, 0><<<grid, JC_NT, smj, p->stream>>>(p->sfit, gIsrc, p->aspec);
+        else if (d.DK == 1) aspec_cache_kernel<TSt, 1><<<grid, JC_NT, smj, p->stream>>>(p->sfit, gIsrc, p->aspec);
+        else aspec_cache_kernel<TSt, 2><<<grid, JC_NT, smj, p->stream>>>(p->sfit, gIsrc, p->aspec);
+        if (cudaGetLastError() != cudaSuccess) { p->aspec_off = 1; return false; }
+        p->launches++;
+        p->aspec_epoch = p->tmpl_epoch;
+    }
+    return true;
 }
 
 // Column pass + contraction over k1 into the lag tables R, RJ, RT, RJT.
@@ -50,7 +94,14 @@ int launch_fit_cols(sfftb_plan* p, const TSt* gIsrc, bool jonly) {
         CKL(p);
     }
     if (p->fit_seg) EVREC(p, EV_KFIT0);
-    if (jonly) {
+    if (jonly && jcache_ready<TSt>(p, gIsrc)) {
+        const int NHj = d.N1 / 2 + 1;
+        const int grid = std::min(NHj, work_sms(p) * p->grid_jc);
+        const size_t smj = jcache_smem_bytes();
+        if (DK == 0) fit_jonly_cached_kernel<TSt, 0><<<grid, JC_NT, smj, p->stream>>>(p->sfit, gIsrc, (const TSt*)p->gJ, p->aspec, p->kap2);
+        else if (DK == 1) fit_jonly_cached_kernel<TSt, 1><<<grid, JC_NT, smj, p->stream>>>(p->sfit, gIsrc, (const TSt*)p->gJ, p->aspec, p->kap2);
+        else fit_jonly_cached_kernel<TSt, 2><<<grid, JC_NT, smj, p->stream>>>(p->sfit, gIsrc, (const TSt*)p->gJ, p->aspec, p->kap2);
+    } else if (jonly) {
         if (DK == 0) fit_seg4_kernel<TSt, 0, true><<<grid_sfit, FS4_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
         else if (DK == 1) fit_seg4_kernel<TSt, 1, true><<<grid_sfit, FS4_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
         else fit_seg4_kernel<TSt, 2, true><<<grid_sfit, FS4_NT, p->smem_sfit3, p->stream>>>(p->sfit, p->vtabs, gIsrc, (const TSt*)p->gJ, p->kap2);
