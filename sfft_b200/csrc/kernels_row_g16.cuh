@@ -72,9 +72,16 @@ template <int R> struct RowgCfg {
 };
 static inline bool rowg_supported(int R) { return R == 3 || R == 5 || R == 6 || R == 10 || R == 12; }
 static inline int rowg_rbi(int R) { return R <= 3 ? 8 : (R <= 6 ? 4 : 2); }
-static inline size_t rowg_smem_bytes(int R) {
+// vt: the plan has column tables (general-basis plans): one table row (N1 = 512 R doubles) is staged in shared memory
+static inline size_t rowg_smem_bytes(int R, bool vt = false) {
     const int lr = R > 8 ? 4 : (R > 4 ? 3 : (R > 2 ? 2 : 1));
-    return sizeof(cd) * ((size_t)rowg_rbi(R) * (R * ROWH_PP + 4) + (size_t)lr * 256 + 128 * R + 1);
+    return sizeof(cd) * ((size_t)rowg_rbi(R) * (R * ROWH_PP + 4) + (size_t)lr * 256 + 128 * R + 2) + (vt ? sizeof(double) * 512 * (size_t)R : 0);
+}
+// loads that stay where they are written (plain loads are sunk to their first use, i.e. behind the untangle step they should overlap)
+__device__ __forceinline__ float2 rowg_ld_early(const float2* p) { float2 v; asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p)); return v; }
+__device__ __forceinline__ double2 rowg_ld_early(const double2* p) { double2 v; asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p)); return v; }
+__device__ __forceinline__ void rowg_cp16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
 // W_H^{b c}, c = 1 .. R-1, from the stored powers c = 1, 2, 4, 8 (at most two more products each)
@@ -100,12 +107,21 @@ __global__ void __launch_bounds__(RowgCfg<R>::nt, 1) row_fwd_g16_kernel(RowH16Ar
     cd* zbuf = reinterpret_cast<cd*>(smem_raw);              // [RBI][R planes][ROWH_PP]
     cd* twp = zbuf + (size_t)RBI * ROWP;                     // [LR][256]: W_H^{b 2^l}
     cd* tw1s = twp + LR * 256;                               // [H/2 + 1] untangle factors
+    double* vts = reinterpret_cast<double*>(tw1s + H / 2 + 2);     // [N1] column table of the current plane (general-basis plans only)
     const int tid = threadIdx.x;
     for (int i = tid; i < LR * 256; i += NT) {
         const int l = i >> 8, b = i & 255;
         twp[i] = a.twP[(size_t)((1 << l) - 1) * 256 + b];
     }
     for (int i = tid; i <= H / 2; i += NT) tw1s[i] = a.tw1[i];
+    // the column table of plane j sits in shared memory; the row of the next plane is copied (cp.async) under pass B and the
+    // untangle step of this one -- read from global memory inside pass A its L2 latency was exposed once per plane
+    auto stage_vtab = [&](int j) {
+        const double* src = a.vtab + (size_t)j * a.N1;
+        for (int i = tid; i < H; i += NT) rowg_cp16(vts + 2 * i, src + 2 * i);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (a.vtab) { stage_vtab(0); asm volatile("cp.async.wait_group 0;" ::: "memory"); }
     const int grp = tid / T, t = tid - grp * T;              // row slot of the CTA, thread of the row
     const int hw = t >> 4, hl = tid & 15;                    // plane of this half warp (T is a multiple of 16)
     cd* zrow = zbuf + (size_t)grp * ROWP;
@@ -115,6 +131,22 @@ __global__ void __launch_bounds__(RowgCfg<R>::nt, 1) row_fwd_g16_kernel(RowH16Ar
     const double inv1 = 1.0 / (double)a.N1;
     const int ngroups = (a.N0 + RBI - 1) / RBI;
     const bool aligned = (a.N0 % 2 == 0);
+    // fp32 images: the packed samples of a thread stay in registers for all planes j, and the next row group is requested under the
+    // last untangle step; fp64 images are re-read per plane (L2 hits)
+    constexpr bool KEEP = sizeof(TIn) == 4;
+    TIn2 xk[KEEP ? NBF * R : 1];
+    auto load_group = [&](int gb) {
+        const int r = gb * RBI + grp;
+#pragma unroll
+        for (int i = 0; i < NBF; ++i)
+#pragma unroll
+            for (int aa = 0; aa < R; ++aa) {
+                const int b = t + T * i;
+                if (b < 256 && r < a.N0) xk[(KEEP ? i * R + aa : 0)] = rowg_ld_early(reinterpret_cast<const TIn2*>(img + (size_t)r * a.N1 + 2 * (256 * aa + b)));
+                else { xk[(KEEP ? i * R + aa : 0)].x = 0; xk[(KEEP ? i * R + aa : 0)].y = 0; }
+            }
+    };
+    if (KEEP && (int)blockIdx.x < ngroups) load_group(blockIdx.x);
     for (int gb = blockIdx.x; gb < ngroups; gb += gridDim.x) {
         const int r0 = gb * RBI, r = r0 + grp;
         for (int j = 0; j < nj; ++j) {
@@ -128,11 +160,12 @@ __global__ void __launch_bounds__(RowgCfg<R>::nt, 1) row_fwd_g16_kernel(RowH16Ar
                     for (int aa = 0; aa < R; ++aa) {
                         const int n = 256 * aa + b;
                         TIn2 x;
-                        if (r < a.N0) x = *reinterpret_cast<const TIn2*>(img + (size_t)r * a.N1 + 2 * n);
+                        if (KEEP) x = xk[KEEP ? i * R + aa : 0];
+                        else if (r < a.N0) x = *reinterpret_cast<const TIn2*>(img + (size_t)r * a.N1 + 2 * n);
                         else { x.x = 0; x.y = 0; }
                         double x0 = (double)x.x, x1 = (double)x.y;
                         if (a.vtab) {
-                            const double2 vv = *reinterpret_cast<const double2*>(a.vtab + (size_t)j * a.N1 + 2 * n);
+                            const double2 vv = *reinterpret_cast<const double2*>(vts + 2 * n);
                             x0 *= vv.x; x1 *= vv.y;
                         } else if (j > 0) {
                             const double c0 = (2 * n + 1) * inv1, c1 = (2 * n + 2) * inv1;
@@ -150,6 +183,7 @@ __global__ void __launch_bounds__(RowgCfg<R>::nt, 1) row_fwd_g16_kernel(RowH16Ar
                 }
             }
             __syncthreads();
+            if (a.vtab && nj > 1) stage_vtab(j + 1 < nj ? j + 1 : 0);          // pass A of this plane has consumed the table row
             // ---- pass B: 256-point transform of plane hw by this half warp ----
             {
                 cd* plane = zrow + hw * ROWH_PP;
@@ -161,6 +195,7 @@ __global__ void __launch_bounds__(RowgCfg<R>::nt, 1) row_fwd_g16_kernel(RowH16Ar
 #pragma unroll
                 for (int q = 0; q < 16; ++q) plane[HPAD(hl + 16 * q)] = v[q];        // X[hw + R (hl + 16 q)]
             }
+            if (KEEP && j == nj - 1 && gb + (int)gridDim.x < ngroups) load_group(gb + gridDim.x);
             __syncthreads();
             // ---- untangle k and H - k together; Z[k] sits at plane k % R, position k / R ----
             constexpr int EPL = 16 / (int)sizeof(TSt) < RBI ? 16 / (int)sizeof(TSt) : RBI, LPC = RBI / EPL;
@@ -184,6 +219,7 @@ __global__ void __launch_bounds__(RowgCfg<R>::nt, 1) row_fwd_g16_kernel(RowH16Ar
                 store_rows<TSt, EPL>(out + ((size_t)j * a.NH + k) * a.N0 + r0 + p0, gk, nv, aligned);
                 if (k != H - k) store_rows<TSt, EPL>(out + ((size_t)j * a.NH + (H - k)) * a.N0 + r0 + p0, gm, nv, aligned);
             }
+            if (a.vtab) asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
         }
     }

@@ -74,7 +74,7 @@ int rows_setup(sfftb_plan* p) {
     }
     p->row_g16 = 0;
     if (r.packed && !p->row_fast && !env_int("SFFTB_ROW_GENERIC", 0) && !env_int("SFFTB_ROW_NOG16", 0) && r.H % 256 == 0 &&
-        rowg_supported(r.H / 256) && rowg_smem_bytes(r.H / 256) <= p->max_smem) {
+        rowg_supported(r.H / 256) && rowg_smem_bytes(r.H / 256, p->vtab != nullptr) <= p->max_smem) {
         const int R = r.H / 256;
         if (upload_engine_table(256, R, &p->tabB_row)) return SFFTB_ECUDA;
         RowH16Args& rh = p->rowh;
@@ -85,7 +85,7 @@ int rows_setup(sfftb_plan* p) {
         rf.tabA = p->tabA; rf.tabB = p->tabB_row; rf.tabC = nullptr; rf.tw1 = p->tw1;
         p->rinvf.r = rf; p->rinvf.scale = p->rinv.scale; p->rinvf.Fpq = d.Fpq; p->rinvf.row0 = 0;
         memcpy(p->rinvf.p_of, p->rinv.p_of, 16); memcpy(p->rinvf.q_of, p->rinv.q_of, 16);
-        const size_t smg = rowg_smem_bytes(R);
+        const size_t smg = rowg_smem_bytes(R, p->vtab != nullptr);
 #define SET_ROWG(RR)                                                                                              \
         if (R == RR) {                                                                                                \
             if (f32 && (set_smem(row_fwd_g16_kernel<float, float2, RR>, smg) || set_smem(row_fwd_g16_kernel<double, float2, RR>, smg))) return SFFTB_ECUDA; \
@@ -120,7 +120,7 @@ int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj, 
         const int R = p->row_g16, RBI = rowg_rbi(R);
         const int ngroups = (p->d.N0 + RBI - 1) / RBI;
         const int grid = std::min(ngroups, p->row_grid_limit > 0 ? p->row_grid_limit : work_sms(p));
-        const size_t smg = rowg_smem_bytes(R);
+        const size_t smg = rowg_smem_bytes(R, p->vtab != nullptr);
 #define RUN_ROWG(RR)                                                                                                   \
         if (R == RR) {                                                                                                 \
             if (dtype == SFFTB_F64) row_fwd_g16_kernel<double, TSt, RR><<<grid, RowgCfg<RR>::nt, smg, p->stream>>>(rowh, (const double*)img, out, nj); \
@@ -225,7 +225,7 @@ int launch_row_inv(sfftb_plan* p, const double* bpq, void* ddiff, int diff_dtype
         const int R = p->row_g16, RBI = rowg_rbi(R);
         const int ngroups = (d.N0 + RBI - 1) / RBI;
         const int grid = std::min(ngroups, p->row_grid_limit > 0 ? p->row_grid_limit : work_sms(p));
-        const size_t smg = rowg_smem_bytes(R);
+        const size_t smg = rowg_smem_bytes(R, p->vtab != nullptr);
         p->rinvf.Fpq = p->rinv.Fpq;
 #define RUN_RINVG(RR)                                                                                                  \
         if (R == RR) {                                                                                                 \
