@@ -61,13 +61,23 @@ struct GenFitArgs {
 // 8 product warps (thread = frequency bin, GEN_NA x GEN_NB accumulators) + 8 transform warps = 16 half-warp workers; one
 // shared-memory exchange per 256-point transform instead of two; the window load is branch-free (the halves of a warp differ in
 // role and table); every needed accumulator gets a plane, so a column ends with ONE inverse batch on the 32 half warps.
-#ifndef GEN_NSLOT
-#define GEN_NSLOT 3                  // spectrum ring slots: the transforms of segment s + 2 start while the products of s still run
+// spectrum ring slots (the transforms of segment s + 2, s + 3 start while the products of s still run) and window ring depth (any
+// number, not only powers of two).  fp32-stored spectra: GEN_NSLOT32 slots, GEN_NSTG32 windows of 4 sources; fp64: 3 slots, 4 windows.
+#ifndef GEN_NSLOT32
+#define GEN_NSLOT32 3
 #endif
-#define GEN_NPLANES (GEN_NSLOT * (GEN_NA + GEN_NB) > 26 ? GEN_NSLOT * (GEN_NA + GEN_NB) : 26)   // ring planes, and >= GEN_NA GEN_NB inverse planes
-static_assert(GEN_NPLANES >= GEN_NSLOT * (GEN_NA + GEN_NB) && GEN_NPLANES >= GEN_NA * GEN_NB, "planes of the general fit kernel");
+#ifndef GEN_NSTG32
+#define GEN_NSTG32 8
+#endif
+template <typename TSt> struct GenRing {
+    static const int depth = sizeof(TSt) == 8 ? GEN_NSTG32 : 4;
+    static const int nslot = sizeof(TSt) == 8 ? GEN_NSLOT32 : 3;
+    static const int nplanes = nslot * (GEN_NA + GEN_NB) > 26 ? nslot * (GEN_NA + GEN_NB) : 26;     // ring planes, and >= GEN_NA GEN_NB inverse planes
+};
+static_assert(26 >= GEN_NA * GEN_NB, "planes of the general fit kernel");
 static inline size_t gen_fit4_smem_bytes(bool f32) {
-    return sizeof(cd) * (size_t)GEN_NPLANES * FS3_PITCH + 128 + (f32 ? sizeof(float2) * 8 : sizeof(double2) * 4) * (size_t)GEN_MAXSRC * FS3_M;
+    const int np = f32 ? GenRing<float2>::nplanes : GenRing<double2>::nplanes;
+    return sizeof(cd) * (size_t)np * FS3_PITCH + 128 + (f32 ? sizeof(float2) * GEN_NSTG32 : sizeof(double2) * 4) * (size_t)GEN_MAXSRC * FS3_M;
 }
 
 __device__ __forceinline__ void gen4_inverse_job(const GenFitArgs& fa, const GenPass& ps, const H16Tw& tw, cd* plane, int jb, int hl, bool active,
@@ -106,7 +116,7 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_gen4_kernel(GenFitArgs fa, GenP
 {
     constexpr int NA = GEN_NA, NB = GEN_NB, NACC = NA * NB;
     constexpr int NPMAX = NA + NB;
-    constexpr int NSTG = Fs3Ring<TSt>::depth, LOG2STG = NSTG == 8 ? 3 : 2, PFD = NSTG - 2;
+    constexpr int NSTG = GenRing<TSt>::depth, PFD = NSTG - 2, GEN_NSLOT = GenRing<TSt>::nslot, GEN_NPLANES = GenRing<TSt>::nplanes;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd* spec = reinterpret_cast<cd*>(smem_raw);                                   // GEN_NPLANES planes
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(spec + GEN_NPLANES * FS3_PITCH);
@@ -137,7 +147,7 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_gen4_kernel(GenFitArgs fa, GenP
             for (int q = 0; q < NACC; ++q) acc[q] = cmake(0.0, 0.0);
             cd* kaprow = kap + (size_t)k1 * fa.nrows;
             auto issue = [&](int s) {
-                const int buf = (g + s) & (NSTG - 1);
+                const int buf = (int)((unsigned)(g + s) % (unsigned)NSTG);
                 const int r = wrap_row(s * S - h + tid, N0);
                 for (int jj = 0; jj < nsrc; ++jj) {
                     const int pl = ps.src_plane[jj];
@@ -238,9 +248,9 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_gen4_kernel(GenFitArgs fa, GenP
                         if (r >= N0) r -= N0;
                     }
                 }
-                while (seenL <= gsB) { fs4_wait_landed(landed + (seenL & (NSTG - 1)), (seenL >> LOG2STG) & 1, cons, (unsigned)seenL); ++seenL; }
+                while (seenL <= gsB) { fs4_wait_landed(landed + (unsigned)seenL % (unsigned)NSTG, ((unsigned)seenL / (unsigned)NSTG) & 1u, cons, (unsigned)seenL); ++seenL; }
                 if (gsB >= GEN_NSLOT) fs3_wait_consumed(cons, (unsigned)(gsB - (GEN_NSLOT - 1)));
-                const TSt* src = stage + ((size_t)(gs & (NSTG - 1)) * GEN_MAXSRC + my_src) * FS3_M;
+                const TSt* src = stage + ((size_t)((unsigned)gs % (unsigned)NSTG) * GEN_MAXSRC + my_src) * FS3_M;
                 cd* plane = spec + ((size_t)slot * NPMAX + (roleA ? p : NA + bs)) * FS3_PITCH;
                 cd v[16];
 #pragma unroll
