@@ -16,6 +16,7 @@
 #include "kernels_row_v8.cuh"
 #include "kernels_row_h16.cuh"
 #include "kernels_row_g16.cuh"
+#include "kernels_row_blu.cuh"
 #include "kernels_fit_seg.cuh"
 #include "kernels_fit_seg3.cuh"
 #include "kernels_fit_seg4.cuh"
@@ -82,6 +83,9 @@ struct sfftb_plan {
     int row_v8;                  // 0 or the engine length H
     int row_h16;                 // 0 or H: R x 256 forward row pass on the half-warp engine (kernels_row_h16.cuh)
     RowH16Args rowh;
+    int row_blu;                 // 0 or R: chirp-z row passes on the half-warp engine for any other even N1 <= 4096 (kernels_row_blu.cuh)
+    RowBluArgs rowb;
+    cd *bluC16, *bluB16, *bluBp16, *bluTwP16;
     int row_g16;                 // 0 or R: N1 = 512 R with R in {3, 5, 6, 10, 12} (kernels_row_g16.cuh), forward and inverse
     size_t smem_rowv;
     double* PHI;
@@ -229,6 +233,7 @@ int launch_fir(sfftb_plan* p, const double2* gIsrc, const double* dsol);
 // sfft_b200.cu
 int upload_twiddles(int n, cd** out);
 int upload_engine_table(int Ns, int R, cd** out);
+int upload_bluestein(int H, int M, cd** outC, cd** outB);
 int plan_init_common(sfftb_plan* p, const sfftb_config* cfg);
 // tu_fit.cu (shared with the general-basis path)
 int lag_reduce2_setup();

@@ -70,7 +70,7 @@ int upload_engine_table(int Ns, int R, cd** out) {
 
 // Bluestein tables for length H through a power-of-two M >= 2 H - 1: chirp c[n] = exp(-pi i n^2 / H) with n^2 reduced
 // mod 2 H in integers, and B = FFT_M(conj(c) wrapped) / M (radix-2 in long double on the host; once per plan).
-static int upload_bluestein(int H, int M, cd** outC, cd** outB) {
+int upload_bluestein(int H, int M, cd** outC, cd** outB) {
     typedef long double ld;
     const ld pi = 3.141592653589793238462643383279502884L;
     std::vector<cd> c((size_t)H);
@@ -175,7 +175,7 @@ static int plan_free(sfftb_plan* p) {
     cudaSetDevice(p->device);
     gen_free(p);
     void* ptrs[] = {p->vt8_8, p->vt64_8, p->vt64_4, p->vt256_4, p->vt512_4, p->tabA, p->tabB_row, p->tabC_row, p->tabC_row32, p->tw0, p->tw1, p->twMf, p->twH, p->Q, p->PHI, p->idxmap, p->ident, p->gI, p->gJ, p->stA, p->stB,
-                    p->kap, p->lam, p->nuJ, p->kap2, p->momg, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->substMsg, p->solEff, p->regC, p->regD, p->regSST, p->regI, p->bluTw, p->bluC, p->bluB, p->firTaps, p->firCA, p->tstate, p->stC, p->stD, p->deltaIdx, p->deltaVal, p->aspec};
+                    p->kap, p->lam, p->nuJ, p->kap2, p->momg, p->part, p->R, p->RJ, p->RT, p->RJT, p->Aug, p->sc, p->diagU, p->sol, p->exportbuf, p->info, p->cholW, p->cholY, p->cholX, p->cholBar, p->substFlags, p->substMsg, p->solEff, p->regC, p->regD, p->regSST, p->regI, p->bluTw, p->bluC, p->bluB, p->firTaps, p->firCA, p->tstate, p->stC, p->stD, p->deltaIdx, p->deltaVal, p->aspec, p->bluC16, p->bluB16, p->bluBp16, p->bluTwP16};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->gIa && p->gIa != p->gI) cudaFree(p->gIa);
     if (p->gJa && p->gJa != p->gJ) cudaFree(p->gJa);
@@ -632,7 +632,7 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, 
         p->factor_cached = 0;            // Aug is about to be overwritten
         if (fill_system(p)) return SFFTB_ECUDA;
         EVREC(p, EV_RED);
-        const bool ov = ovI && ovJ && (p->row_v8 || p->row_h16 || p->row_g16) && p->chol_coop && p->nsm >= 8;
+        const bool ov = ovI && ovJ && (p->row_v8 || p->row_h16 || p->row_g16 || p->row_blu) && p->chol_coop && p->nsm >= 8;
         if (ov) {
             CK(cudaEventRecord(p->evFork, p->stream));
             CK(cudaStreamWaitEvent(p->stream2, p->evFork, 0));
@@ -863,7 +863,7 @@ extern "C" int sfftb_gss(sfftb_plan* p, const void* I, const void* J, const void
     }
     if ((rc = stage_in(p, mI, memkind, dtype, p->stA, &dI))) return rc;
     if ((rc = stage_in(p, mJ, memkind, dtype, p->stB, &dJ))) return rc;
-    const bool ov = p->overlap && memkind == SFFTB_MEM_DEVICE && I && J && (p->row_v8 || p->row_h16 || p->row_g16) && p->chol_coop && p->nsm >= 8 && !p->gen;
+    const bool ov = p->overlap && memkind == SFFTB_MEM_DEVICE && I && J && (p->row_v8 || p->row_h16 || p->row_g16 || p->row_blu) && p->chol_coop && p->nsm >= 8 && !p->gen;
     rc = f32 ? fit_device<float2>(p, dI, dJ, dtype, nullptr, ov ? I : nullptr, ov ? J : nullptr)
              : fit_device<double2>(p, dI, dJ, dtype, nullptr, ov ? I : nullptr, ov ? J : nullptr);
     if (rc) return rc;
@@ -925,7 +925,7 @@ static int gss_submit_impl(sfftb_plan* p, const void* I, const void* J, const vo
     int rc;
     p->pend_mem = memkind;
     if (memkind == SFFTB_MEM_DEVICE) {
-        const bool ov = p->overlap && (p->row_v8 || p->row_h16 || p->row_g16) && p->chol_coop && p->nsm >= 8;
+        const bool ov = p->overlap && (p->row_v8 || p->row_h16 || p->row_g16 || p->row_blu) && p->chol_coop && p->nsm >= 8;
         p->pendI = nullptr; p->pendJ = nullptr;
         rc = f32 ? fit_device<float2>(p, mI, mJ, dtype, nullptr, ov ? I : nullptr, ov ? J : nullptr)
                  : fit_device<double2>(p, mI, mJ, dtype, nullptr, ov ? I : nullptr, ov ? J : nullptr);
@@ -998,7 +998,7 @@ static int gss_submit_impl(sfftb_plan* p, const void* I, const void* J, const vo
     }
     // the forward row pass of the apply pair runs on the copy stream (behind the copies of I and J, which were queued there
     // first) while the Cholesky runs on the compute stream, like in sfftb_gss
-    const bool ovh = p->overlap && (p->row_v8 || p->row_h16 || p->row_g16) && p->chol_coop && p->nsm >= 8;
+    const bool ovh = p->overlap && (p->row_v8 || p->row_h16 || p->row_g16 || p->row_blu) && p->chol_coop && p->nsm >= 8;
     rc = f32 ? fit_device<float2>(p, p->stA, p->stB, dtype, nullptr, ovh ? p->stC : nullptr, ovh ? p->stD : nullptr)
              : fit_device<double2>(p, p->stA, p->stB, dtype, nullptr, ovh ? p->stC : nullptr, ovh ? p->stD : nullptr);
     if (rc) return rc;

@@ -2,6 +2,14 @@
 #define SFFTB_TU_ROWS
 #include "plan.h"
 
+// Bp[c * 256 + d] = B[c + R d]: the chirp filter in the plane layout of the R x 256 decomposition
+__global__ void blu_permute_kernel(int R, const cd* __restrict__ B, cd* __restrict__ Bp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 256 * R) return;
+    const int c = i >> 8, d = i & 255;
+    Bp[i] = B[c + R * d];
+}
+
 int rows_setup(sfftb_plan* p) {
     const sfftb_dims& d = p->d;
     const RowArgs& r = p->row;
@@ -96,6 +104,33 @@ int rows_setup(sfftb_plan* p) {
 #undef SET_ROWG
         p->row_g16 = R;
     }
+    p->row_blu = 0;
+    if (r.packed && !p->row_fast && !p->row_g16 && !p->row_v8 && r.H > 128 && blu_radix(r.H) && !env_int("SFFTB_ROW_GENERIC", 0) &&
+        !env_int("SFFTB_ROW_NOBLU16", 0) && blu_smem_bytes(blu_radix(r.H)) <= p->max_smem) {
+        const int R = blu_radix(r.H), M = 256 * R;
+        if (upload_engine_table(256, R, &p->bluTwP16) || upload_bluestein(r.H, M, &p->bluC16, &p->bluB16)) return SFFTB_ECUDA;
+        CK(cudaMalloc(&p->bluBp16, sizeof(cd) * M));
+        blu_permute_kernel<<<(M + 255) / 256, 256, 0, p->stream>>>(R, p->bluB16, p->bluBp16);
+        CKL(p);
+        RowBluArgs& rb = p->rowb;
+        rb.N0 = d.N0; rb.N1 = d.N1; rb.NH = d.N1 / 2 + 1; rb.H = r.H;
+        rb.tabA = p->tabA; rb.twP = p->bluTwP16; rb.tw1 = p->tw1; rb.chirp = p->bluC16; rb.Bp = p->bluBp16; rb.vtab = nullptr;
+        RowFastArgs& rf = p->rowf;
+        rf.N0 = d.N0; rf.N1 = d.N1; rf.NH = d.N1 / 2 + 1; rf.H = r.H;
+        rf.tabA = p->tabA; rf.tabB = nullptr; rf.tabC = nullptr; rf.tw1 = p->tw1;
+        p->rinvf.r = rf; p->rinvf.scale = p->rinv.scale; p->rinvf.Fpq = d.Fpq; p->rinvf.row0 = 0;
+        memcpy(p->rinvf.p_of, p->rinv.p_of, 16); memcpy(p->rinvf.q_of, p->rinv.q_of, 16);
+        const size_t smb = blu_smem_bytes(R);
+#define SET_BLU(RR)                                                                                               \
+        if (R == RR) {                                                                                                \
+            if (f32 && (set_smem(row_fwd_blu_kernel<float, float2, RR>, smb) || set_smem(row_fwd_blu_kernel<double, float2, RR>, smb))) return SFFTB_ECUDA; \
+            if (set_smem(row_fwd_blu_kernel<float, double2, RR>, smb) || set_smem(row_fwd_blu_kernel<double, double2, RR>, smb)) return SFFTB_ECUDA; \
+            if (set_smem(row_inv_blu_kernel<double2, float, RR>, smb) || set_smem(row_inv_blu_kernel<double2, double, RR>, smb)) return SFFTB_ECUDA; \
+        }
+        SET_BLU(4) SET_BLU(8) SET_BLU(16)
+#undef SET_BLU
+        p->row_blu = R;
+    }
     if (p->row_fast) {
         const size_t sm = sizeof(cd) * (size_t)(ROWF_NT / (r.H / 16)) * (r.H + r.H / 16);
 #define SET_ROWF(HH)                                                                                              \
@@ -115,6 +150,22 @@ int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj, 
     RowFastArgs rowf = p->rowf; rowf.vtab = vtab;
     RowArgs rowg = p->row; rowg.vtab = vtab;
     const size_t esz2 = dtype == SFFTB_F64 ? 16 : 8;
+    if (p->row_blu && ((uintptr_t)img % esz2) == 0) {
+        RowBluArgs rowb = p->rowb; rowb.vtab = vtab;
+        const int R = p->row_blu, RBI = BLU_NT / (16 * R);
+        const int ngroups = (p->d.N0 + RBI - 1) / RBI;
+        const int grid = std::min(ngroups, p->row_grid_limit > 0 ? p->row_grid_limit : work_sms(p));
+        const size_t smb = blu_smem_bytes(R);
+#define RUN_BLU(RR)                                                                                                    \
+        if (R == RR) {                                                                                                 \
+            if (dtype == SFFTB_F64) row_fwd_blu_kernel<double, TSt, RR><<<grid, BLU_NT, smb, p->stream>>>(rowb, (const double*)img, out, nj); \
+            else row_fwd_blu_kernel<float, TSt, RR><<<grid, BLU_NT, smb, p->stream>>>(rowb, (const float*)img, out, nj);                     \
+        }
+        RUN_BLU(4) RUN_BLU(8) RUN_BLU(16)
+#undef RUN_BLU
+        CKL(p);
+        return 0;
+    }
     if (p->row_g16 && ((uintptr_t)img % esz2) == 0) {
         RowH16Args rowh = p->rowh; rowh.vtab = vtab;
         const int R = p->row_g16, RBI = rowg_rbi(R);
@@ -219,6 +270,22 @@ int launch_row_inv(sfftb_plan* p, const double* bpq, void* ddiff, int diff_dtype
             CK(cudaEventRecord(p->evJoin, p->stream2));
             if (!p->defer_join) CK(cudaStreamWaitEvent(p->stream, p->evJoin, 0));
         }
+        return 0;
+    }
+    if (p->row_blu && ((uintptr_t)ddiff % osz2) == 0) {
+        const int R = p->row_blu, RBI = BLU_NT / (16 * R);
+        const int ngroups = (d.N0 + RBI - 1) / RBI;
+        const int grid = std::min(ngroups, p->row_grid_limit > 0 ? p->row_grid_limit : work_sms(p));
+        const size_t smb = blu_smem_bytes(R);
+        p->rinvf.Fpq = p->rinv.Fpq;
+#define RUN_RINVB(RR)                                                                                                  \
+        if (R == RR) {                                                                                                 \
+            if (diff_dtype == SFFTB_F64) row_inv_blu_kernel<TSt, double, RR><<<grid, BLU_NT, smb, p->stream>>>(p->rowb, p->rinvf, (const TSt*)p->gJa, bpq, (double*)ddiff); \
+            else row_inv_blu_kernel<TSt, float, RR><<<grid, BLU_NT, smb, p->stream>>>(p->rowb, p->rinvf, (const TSt*)p->gJa, bpq, (float*)ddiff);                            \
+        }
+        RUN_RINVB(4) RUN_RINVB(8) RUN_RINVB(16)
+#undef RUN_RINVB
+        CKL(p);
         return 0;
     }
     if (p->row_g16 && ((uintptr_t)ddiff % osz2) == 0) {
