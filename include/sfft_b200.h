@@ -143,10 +143,15 @@ int  sfftb_gss_finish(sfftb_plan* plan);
  *   sfftb_template_prepare : row spectra of (PixA_I, PixA_mI) into the plan's template state;
  *   sfftb_template_state   : device pointer + size of that state (allocated on first use) -- the buffer a caller
  *                            broadcasts to the other GPUs with ONE ncclBroadcast / torch.distributed.broadcast;
- *   sfftb_template_mark_ready : on a receiving rank, after the broadcast landed in the state buffer;
+ *   sfftb_template_mark_ready : on a receiving rank, after the broadcast landed in the state buffer (every change of the
+ *                            state buffer must be followed by prepare or mark_ready: they invalidate the cached factor and
+ *                            the cached segment spectra below);
  *   sfftb_gss_template     : GSS for one science image (PixA_J, PixA_mJ) against the cached template.  LHMAT = D^T D / N
  *                            involves the masked template only, so its Cholesky factor is kept from the first tile
- *                            and later tiles assemble the right-hand side and run the two substitutions. */
+ *                            and later tiles assemble the right-hand side and run the two substitutions; the segment
+ *                            spectra of the template that the right-hand side needs are kept in device memory as well
+ *                            (NH * segments * Fij * 4 KB, 252 MB for a 2048^2 template with KerPolyOrder 2; built by the
+ *                            second tile, SFFTB_NO_ASPEC_CACHE=1 switches it off), so a tile transforms only J. */
 int  sfftb_template_prepare(sfftb_plan* plan, const void* PixA_I, const void* PixA_mI, int img_memkind, int img_dtype);
 int  sfftb_template_state(sfftb_plan* plan, void** device_ptr, size_t* bytes);
 int  sfftb_template_mark_ready(sfftb_plan* plan);
