@@ -299,9 +299,11 @@ struct GenBkg {
     const int* fu; const int* fv;    // [Fpq]
 };
 
-// grid: CTAs stride over rows; smem: Fq doubles per warp partial + Fp*Fq accumulators
+// grid: CTAs stride over rows; smem: Fq doubles per warp partial + Fp*Fq accumulators.  Every CTA writes its partial sums to
+// PQpart[blockIdx.x][Fp * Fq]; gen_rjt_finish_kernel adds them in CTA order (no atomics: the right-hand side -- and with it Solution
+// and DIFF -- repeats bit for bit from run to run, like the reference's).
 template <typename TIn>
-__global__ void __launch_bounds__(256) gen_rjt_kernel(GenBkg a, const TIn* __restrict__ J, double* __restrict__ PQ /* [Fp][Fq], zeroed */)
+__global__ void __launch_bounds__(256) gen_rjt_kernel(GenBkg a, const TIn* __restrict__ J, double* __restrict__ PQpart)
 {
     __shared__ double sq[8][GEN_MAXQ];
     __shared__ double accs[GEN_MAXP * GEN_MAXQ];
@@ -336,8 +338,19 @@ __global__ void __launch_bounds__(256) gen_rjt_kernel(GenBkg a, const TIn* __res
         }
         __syncthreads();
     }
-    if (tid < a.Fp * a.Fq) atomicAdd(&PQ[tid], accs[tid]);
+    if (tid < a.Fp * a.Fq) PQpart[(size_t)blockIdx.x * (a.Fp * a.Fq) + tid] = accs[tid];
 }
+
+#ifdef SFFTB_TU_GEN
+__global__ void gen_rjt_finish_kernel(int nparts, int n, const double* __restrict__ PQpart, double* __restrict__ PQ)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int b = 0; b < nparts; ++b) s += PQpart[(size_t)b * n + i];
+    PQ[i] = s;
+}
+#endif
 
 // ---- normal-equation fill for arbitrary unknown descriptors ------------------------------------------------------------
 // Unknown u of the solved (tweaked) system: a design-matrix column SCALE * (roll(X_plane, (a, b)) - mod * X_plane) with

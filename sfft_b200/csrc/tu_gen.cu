@@ -18,7 +18,7 @@ struct GenState {
     GenFitArgs fit;
     size_t smem_fit;
     int nrows;
-    cd* kap; double* part; double* Rall; double* PQ;
+    cd* kap; double* part; double* Rall; double* PQ; double* PQpart;
     LagReduce2Args red2;
     GenFillArgs fill;
     std::vector<void*> owned;        // device allocations released with the plan
@@ -327,7 +327,7 @@ int gen_plan_create(sfftb_plan* p, const sfftb_config* cfg, const sfftb_basis* k
     r2.N1 = N1; r2.NH = NH; r2.nrows = nrows; r2.w1 = w1; r2.tw1 = p->tw1; r2.rb0 = 0;
     r2.ksplit = (NH + LR2_KC - 1) / LR2_KC;
     if (dev_alloc(g, (size_t)r2.ksplit * nrows * nl1, &g->part) || dev_alloc(g, (size_t)nrows * nl1, &g->Rall) ||
-        dev_alloc(g, (size_t)GEN_MAXP * GEN_MAXQ, &g->PQ)) return SFFTB_ECUDA;
+        dev_alloc(g, (size_t)GEN_MAXP * GEN_MAXQ, &g->PQ) || dev_alloc(g, (size_t)GEN_MAXP * GEN_MAXQ * 4 * (size_t)p->nsm, &g->PQpart)) return SFFTB_ECUDA;
     g->smem_fit = gen_fit4_smem_bytes(f32);
     if (g->smem_fit > p->max_smem) return fail(SFFTB_EINVAL, "the general fit kernel needs %zu bytes of shared memory", g->smem_fit);
     if (f32) { if (set_smem(fit_gen4_kernel<float2>, g->smem_fit)) return SFFTB_ECUDA; }
@@ -449,10 +449,11 @@ int gen_set_regularizer(sfftb_plan* p) {
 // J x T moments in real space (the image of J is still on the device when the fit runs)
 int gen_rjt(sfftb_plan* p, const void* dJ, int dtype) {
     GenState* g = (GenState*)p->gen;
-    CK(cudaMemsetAsync(g->PQ, 0, sizeof(double) * GEN_MAXP * GEN_MAXQ, p->stream));
-    const int grid = std::min(p->d.N0, 4 * p->nsm);
-    if (dtype == SFFTB_F64) gen_rjt_kernel<double><<<grid, 256, 0, p->stream>>>(g->bkg, (const double*)dJ, g->PQ);
-    else gen_rjt_kernel<float><<<grid, 256, 0, p->stream>>>(g->bkg, (const float*)dJ, g->PQ);
+    const int grid = std::min(p->d.N0, 4 * p->nsm), n = g->Fp * g->Fq;
+    if (dtype == SFFTB_F64) gen_rjt_kernel<double><<<grid, 256, 0, p->stream>>>(g->bkg, (const double*)dJ, g->PQpart);
+    else gen_rjt_kernel<float><<<grid, 256, 0, p->stream>>>(g->bkg, (const float*)dJ, g->PQpart);
+    CKL(p);
+    gen_rjt_finish_kernel<<<(n + 127) / 128, 128, 0, p->stream>>>(grid, n, g->PQpart, g->PQ);
     CKL(p);
     return 0;
 }
