@@ -632,7 +632,7 @@ static int fit_device(sfftb_plan* p, const void* dI, const void* dJ, int dtype, 
         p->factor_cached = 0;            // Aug is about to be overwritten
         if (fill_system(p)) return SFFTB_ECUDA;
         EVREC(p, EV_RED);
-        const bool ov = ovI && ovJ && (p->row_v8 || p->row_h16 || p->row_g16 || p->row_blu) && p->chol_coop && p->nsm >= 8;
+        const bool ov = ovI && ovJ && (p->row_v8 || p->row_h16 || p->row_g16 || (p->row_blu && p->row_blu <= 16)) && p->chol_coop && p->nsm >= 8;
         if (ov) {
             CK(cudaEventRecord(p->evFork, p->stream));
             CK(cudaStreamWaitEvent(p->stream2, p->evFork, 0));
@@ -863,7 +863,7 @@ extern "C" int sfftb_gss(sfftb_plan* p, const void* I, const void* J, const void
     }
     if ((rc = stage_in(p, mI, memkind, dtype, p->stA, &dI))) return rc;
     if ((rc = stage_in(p, mJ, memkind, dtype, p->stB, &dJ))) return rc;
-    const bool ov = p->overlap && memkind == SFFTB_MEM_DEVICE && I && J && (p->row_v8 || p->row_h16 || p->row_g16 || p->row_blu) && p->chol_coop && p->nsm >= 8 && !p->gen;
+    const bool ov = p->overlap && memkind == SFFTB_MEM_DEVICE && I && J && (p->row_v8 || p->row_h16 || p->row_g16 || (p->row_blu && p->row_blu <= 16)) && p->chol_coop && p->nsm >= 8 && !p->gen;
     rc = f32 ? fit_device<float2>(p, dI, dJ, dtype, nullptr, ov ? I : nullptr, ov ? J : nullptr)
              : fit_device<double2>(p, dI, dJ, dtype, nullptr, ov ? I : nullptr, ov ? J : nullptr);
     if (rc) return rc;
@@ -925,7 +925,7 @@ static int gss_submit_impl(sfftb_plan* p, const void* I, const void* J, const vo
     int rc;
     p->pend_mem = memkind;
     if (memkind == SFFTB_MEM_DEVICE) {
-        const bool ov = p->overlap && (p->row_v8 || p->row_h16 || p->row_g16 || p->row_blu) && p->chol_coop && p->nsm >= 8;
+        const bool ov = p->overlap && (p->row_v8 || p->row_h16 || p->row_g16 || (p->row_blu && p->row_blu <= 16)) && p->chol_coop && p->nsm >= 8;
         p->pendI = nullptr; p->pendJ = nullptr;
         rc = f32 ? fit_device<float2>(p, mI, mJ, dtype, nullptr, ov ? I : nullptr, ov ? J : nullptr)
                  : fit_device<double2>(p, mI, mJ, dtype, nullptr, ov ? I : nullptr, ov ? J : nullptr);
@@ -998,7 +998,7 @@ static int gss_submit_impl(sfftb_plan* p, const void* I, const void* J, const vo
     }
     // the forward row pass of the apply pair runs on the copy stream (behind the copies of I and J, which were queued there
     // first) while the Cholesky runs on the compute stream, like in sfftb_gss
-    const bool ovh = p->overlap && (p->row_v8 || p->row_h16 || p->row_g16 || p->row_blu) && p->chol_coop && p->nsm >= 8;
+    const bool ovh = p->overlap && (p->row_v8 || p->row_h16 || p->row_g16 || (p->row_blu && p->row_blu <= 16)) && p->chol_coop && p->nsm >= 8;
     rc = f32 ? fit_device<float2>(p, p->stA, p->stB, dtype, nullptr, ovh ? p->stC : nullptr, ovh ? p->stD : nullptr)
              : fit_device<double2>(p, p->stA, p->stB, dtype, nullptr, ovh ? p->stC : nullptr, ovh ? p->stD : nullptr);
     if (rc) return rc;

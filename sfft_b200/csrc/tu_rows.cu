@@ -129,6 +129,11 @@ int rows_setup(sfftb_plan* p) {
         }
         SET_BLU(4) SET_BLU(8) SET_BLU(16)
 #undef SET_BLU
+        if (R == 32) {
+            if (f32 && (set_smem(row_fwd_blu32_kernel<float, float2>, smb) || set_smem(row_fwd_blu32_kernel<double, float2>, smb))) return SFFTB_ECUDA;
+            if (set_smem(row_fwd_blu32_kernel<float, double2>, smb) || set_smem(row_fwd_blu32_kernel<double, double2>, smb)) return SFFTB_ECUDA;
+            if (set_smem(row_inv_blu32_kernel<double2, float>, smb) || set_smem(row_inv_blu32_kernel<double2, double>, smb)) return SFFTB_ECUDA;
+        }
         p->row_blu = R;
     }
     if (p->row_fast) {
@@ -152,10 +157,14 @@ int launch_row_fwd(sfftb_plan* p, const void* img, int dtype, TSt* out, int nj, 
     const size_t esz2 = dtype == SFFTB_F64 ? 16 : 8;
     if (p->row_blu && ((uintptr_t)img % esz2) == 0) {
         RowBluArgs rowb = p->rowb; rowb.vtab = vtab;
-        const int R = p->row_blu, RBI = BLU_NT / (16 * R);
+        const int R = p->row_blu, RBI = R == 32 ? 1 : BLU_NT / (16 * R);
         const int ngroups = (p->d.N0 + RBI - 1) / RBI;
         const int grid = std::min(ngroups, p->row_grid_limit > 0 ? p->row_grid_limit : work_sms(p));
         const size_t smb = blu_smem_bytes(R);
+        if (R == 32) {
+            if (dtype == SFFTB_F64) row_fwd_blu32_kernel<double, TSt><<<grid, BLU32_NT, smb, p->stream>>>(rowb, (const double*)img, out, nj);
+            else row_fwd_blu32_kernel<float, TSt><<<grid, BLU32_NT, smb, p->stream>>>(rowb, (const float*)img, out, nj);
+        }
 #define RUN_BLU(RR)                                                                                                    \
         if (R == RR) {                                                                                                 \
             if (dtype == SFFTB_F64) row_fwd_blu_kernel<double, TSt, RR><<<grid, BLU_NT, smb, p->stream>>>(rowb, (const double*)img, out, nj); \
@@ -273,11 +282,15 @@ int launch_row_inv(sfftb_plan* p, const double* bpq, void* ddiff, int diff_dtype
         return 0;
     }
     if (p->row_blu && ((uintptr_t)ddiff % osz2) == 0) {
-        const int R = p->row_blu, RBI = BLU_NT / (16 * R);
+        const int R = p->row_blu, RBI = R == 32 ? 1 : BLU_NT / (16 * R);
         const int ngroups = (d.N0 + RBI - 1) / RBI;
         const int grid = std::min(ngroups, p->row_grid_limit > 0 ? p->row_grid_limit : work_sms(p));
         const size_t smb = blu_smem_bytes(R);
         p->rinvf.Fpq = p->rinv.Fpq;
+        if (R == 32) {
+            if (diff_dtype == SFFTB_F64) row_inv_blu32_kernel<TSt, double><<<grid, BLU32_NT, smb, p->stream>>>(p->rowb, p->rinvf, (const TSt*)p->gJa, bpq, (double*)ddiff);
+            else row_inv_blu32_kernel<TSt, float><<<grid, BLU32_NT, smb, p->stream>>>(p->rowb, p->rinvf, (const TSt*)p->gJa, bpq, (float*)ddiff);
+        }
 #define RUN_RINVB(RR)                                                                                                  \
         if (R == RR) {                                                                                                 \
             if (diff_dtype == SFFTB_F64) row_inv_blu_kernel<TSt, double, RR><<<grid, BLU_NT, smb, p->stream>>>(p->rowb, p->rinvf, (const TSt*)p->gJa, bpq, (double*)ddiff); \
