@@ -229,7 +229,7 @@ def run_config4(torch, dist, B, world, rank, local, dev, ntiles=64, side=2048, w
         if rank != 0:
             plan.template_mark_ready()
     t_bcast = time.perf_counter() - t1
-    TD = int(os.environ.get('SFFTB_BENCH_TILE_DEPTH', '4'))          # tiles in flight (one plan + stream each)
+    TD = int(os.environ.get('SFFTB_BENCH_TILE_DEPTH', '6'))          # tiles in flight (one plan + stream each)
     tp = TemplatePipeline(side, side, w, DK, DB, True, device=local, storage=storage, stream_ptr=None, first_plan=plan, depth=TD)
     tp.set_template()
     mine = list(shard_indices(ntiles, rank, world))
