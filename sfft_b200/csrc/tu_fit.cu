@@ -60,6 +60,9 @@ static bool jcache_ready(sfftb_plan* p, const TSt* gIsrc) {
     const sfftb_dims& d = p->d;
     const int NH = d.N1 / 2 + 1, Fij = d.Fij;
     const size_t need = (size_t)NH * p->sfit.nseg * Fij * FS3_M;
+    // the cache is worth its memory for tile-sized templates (252 MB at 2048^2, 1 GB at 4096^2); beyond SFFTB_ASPEC_MAX_MB (4096) the
+    // recomputing kernel stays
+    if (sizeof(cd) * need > (size_t)env_int("SFFTB_ASPEC_MAX_MB", 4096) * 1048576ull) { p->aspec_off = 1; return false; }
     if (!p->aspec || p->aspec_elems < need) {
         if (p->aspec) { cudaFree(p->aspec); p->aspec = nullptr; }
         if (cudaMalloc(&p->aspec, sizeof(cd) * need) != cudaSuccess) { cudaGetLastError(); p->aspec = nullptr; p->aspec_off = 1; return false; }
