@@ -249,7 +249,14 @@ def run_config4(torch, dist, B, world, rank, local, dev, ntiles=64, side=2048, w
             if busy[slot]:
                 tp.plans[slot].gss_finish()
                 busy[slot] = False
-    run_tiles(range(2 * TD))                                         # first (factorising) tile of each plan + warm-up
+    # ONE factorisation and ONE spectra cache per template and GPU: two tiles on the first plan, whose state (factor, lag rows, cached
+    # segment spectra) is then copied into the other plans (sfftb_template_clone)
+    for k in range(2):
+        J, mJ = tiles[k % 2]
+        tp.plans[0].gss_template_submit_device(J.data_ptr(), mJ.data_ptr(), code, sols[0].data_ptr(), diffs[0].data_ptr(), code)
+        tp.plans[0].gss_finish()
+    tp.share_state()
+    run_tiles(range(2 * TD))                                         # warm-up of every plan (all served from the shared state)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()

@@ -155,6 +155,11 @@ int  sfftb_gss_finish(sfftb_plan* plan);
 int  sfftb_template_prepare(sfftb_plan* plan, const void* PixA_I, const void* PixA_mI, int img_memkind, int img_dtype);
 int  sfftb_template_state(sfftb_plan* plan, void** device_ptr, size_t* bytes);
 int  sfftb_template_mark_ready(sfftb_plan* plan);
+/* Copy the whole shared-template state of `src` (row spectra; Cholesky factor, lag rows and cached segment spectra once `src` has
+ * processed its first tiles) into `dst`, a plan of the same configuration on the same device: the plans of a multi-stream pipeline
+ * (batch.TemplatePipeline) then share ONE factorisation per template instead of one per plan.  The reference has no counterpart
+ * (it refits every pair from scratch, sfft/MultiEasySparsePacket.py:568-649). */
+int  sfftb_template_clone(sfftb_plan* dst, sfftb_plan* src);
 int  sfftb_gss_template(sfftb_plan* plan, const void* PixA_J, const void* PixA_mJ, int img_memkind, int img_dtype,
                         double* solution, int sol_memkind, void* diff, int diff_memkind, int diff_dtype);
 

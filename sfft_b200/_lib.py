@@ -19,7 +19,7 @@ EXPORTS = ['sfftb_version', 'sfftb_last_error', 'sfftb_plan_create', 'sfftb_plan
            'sfftb_plan_set_stream', 'sfftb_plan_sync', 'sfftb_fit', 'sfftb_apply', 'sfftb_gss',
            'sfftb_export_normal_eq', 'sfftb_plan_set_timing', 'sfftb_timings', 'sfftb_last_solver',
            'sfftb_launch_count', 'sfftb_template_prepare', 'sfftb_template_state',
-           'sfftb_template_mark_ready', 'sfftb_gss_template', 'sfftb_realize', 'sfftb_fits_decode', 'sfftb_fits_encode', 'sfftb_nan_union_fill', 'sfftb_nan_mask_apply',
+           'sfftb_template_mark_ready', 'sfftb_template_clone', 'sfftb_gss_template', 'sfftb_realize', 'sfftb_fits_decode', 'sfftb_fits_encode', 'sfftb_nan_union_fill', 'sfftb_nan_mask_apply',
            'sfftb_set_regularizer', 'sfftb_set_regularizer_varying', 'sfftb_gss_submit', 'sfftb_gss_template_submit', 'sfftb_gss_finish', 'sfftb_dbg_fft1d',
            'sfftb_dbg_row_spectra', 'sfftb_dbg_lag_tables', 'sfftb_plan_create_general', 'sfftb_export_solved_system',
            'sfftb_gss_submit_device', 'sfftb_gss_submit_delta', 'sfftb_gen_info', 'sfftb_plan_set_partition', 'sfftb_decorr', 'sfftb_convolve', 'sfftb_convolve_grid']
@@ -82,6 +82,7 @@ def lib():
     L.sfftb_template_prepare.argtypes = [vp, vp, vp, ip, ip]
     L.sfftb_template_state.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.sfftb_template_mark_ready.argtypes = [vp]
+    L.sfftb_template_clone.argtypes = [vp, vp]
     L.sfftb_gss_template.argtypes = [vp, vp, vp, ip, ip, vp, ip, vp, ip, ip]
     L.sfftb_plan_set_timing.argtypes = [vp, ip]
     L.sfftb_timings.argtypes = [vp, C.POINTER(C.c_float), ip]

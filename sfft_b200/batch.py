@@ -198,20 +198,47 @@ class TemplatePipeline:
                 pl.set_stream(stream_ptr)
         self._busy = [False] * depth
         self._k = 0
+        self._shared = False
+        self._warm = 0
 
     def set_template(self, PixA_I=None, PixA_mI=None):
-        """Prepare the template on the first plan (unless it already holds one, e.g. received by broadcast) and clone
-        its state into the second (device-to-device)."""
-        import torch
+        """Prepare the template on the first plan (unless it already holds one, e.g. received by broadcast).  The other plans
+        receive its state by share_state(): submit() does that after the first plan has processed two tiles, so that the
+        Cholesky factor of the template's normal equations and the cached segment spectra are computed ONCE per template
+        and copied (device-to-device), not once per plan."""
         if PixA_I is not None:
             self.plans[0].template_prepare(PixA_I, PixA_mI)
+        self._shared = False
+        self._warm = 0
         for pl in self.plans[1:]:
-            pl.template_state_tensor().copy_(self.plans[0].template_state_tensor())
-        torch.cuda.synchronize(torch.device('cuda', self.device))
+            pl.template_clone(self.plans[0])               # spectra only at this point: every plan is usable right away
+
+    def share_state(self):
+        """Copy the first plan's template state (spectra + factor + lag rows + cached segment spectra, whatever it holds) into
+        the other plans.  Call with no tile in flight."""
         for pl in self.plans[1:]:
-            pl.template_mark_ready()
+            pl.template_clone(self.plans[0])
+        self._shared = True
 
     def submit(self, PixA_J, PixA_mJ, out_dtype=np.float64, Solution_out=None, DIFF_out=None):
+        if not self._shared:
+            # start-up: the first two tiles go through the first plan one after the other (factorisation, then the tile that
+            # builds the spectra cache); the third submission copies that state to the other plans
+            done = self.plans[0].gss_finish() if self._busy[0] else None
+            self._busy[0] = False
+            if self._warm == 2:
+                self.share_state()
+            else:
+                self.plans[0].gss_template_submit(PixA_J, PixA_mJ, out_dtype, Solution_out, DIFF_out)
+                self._busy[0] = True
+                self._warm += 1
+                return done
+            # (falls through: this submission is the first of the round-robin phase; `done` is the second tile's result)
+            slot = self._k % len(self.plans)
+            self.plans[slot].gss_template_submit(PixA_J, PixA_mJ, out_dtype, Solution_out, DIFF_out)
+            self._busy[slot] = True
+            self._k += 1
+            return done
         slot = self._k % len(self.plans)
         done = None
         if self._busy[slot]:

@@ -1198,6 +1198,51 @@ extern "C" int sfftb_template_state(sfftb_plan* p, void** dptr, size_t* bytes) {
     return 0;
 }
 
+// Copy the complete shared-template state of `src` into `dst` (same configuration, same device): the template row spectra and, when
+// `src` already holds them, the Cholesky factor of the template's normal equations, its lag rows and the cached segment spectra --
+// device-to-device copies (about 0.3 GB at 2048^2, 0.1 ms) instead of one factorisation and one cache build per plan of a pipeline.
+extern "C" int sfftb_template_clone(sfftb_plan* dst, sfftb_plan* src) {
+    if (!dst || !src || dst == src) return fail(SFFTB_EINVAL, "sfftb_template_clone: two different plans are needed");
+    if (dst->gen || src->gen) return fail(SFFTB_EINVAL, "the shared-template path is not available for general-basis plans");
+    const sfftb_dims &a = dst->d, &b = src->d;
+    if (dst->device != src->device || a.N0 != b.N0 || a.N1 != b.N1 || a.w0 != b.w0 || a.w1 != b.w1 || a.DK != b.DK || a.DB != b.DB ||
+        dst->cfg.storage != src->cfg.storage || dst->nsolve != src->nsolve || dst->ld != src->ld || dst->fit_seg != src->fit_seg ||
+        dst->chol_coop != src->chol_coop)
+        return fail(SFFTB_EINVAL, "sfftb_template_clone: the two plans differ in configuration or device");
+    if (!src->have_template || !src->tstate) return fail(SFFTB_ESTATE, "no template has been prepared on the source plan");
+    if (dst->pending || src->pending) return fail(SFFTB_ESTATE, "sfftb_template_clone: a submission is still in flight");
+    CK(cudaSetDevice(dst->device));
+    int rc;
+    if ((rc = template_alloc(dst))) return rc;
+    CK(cudaStreamSynchronize(src->stream));
+    cudaStream_t st = dst->stream;
+    CK(cudaMemcpyAsync(dst->tstate, src->tstate, src->tstate_bytes, cudaMemcpyDeviceToDevice, st));
+    dst->have_template = 1;
+    dst->factor_cached = 0;
+    dst->tmpl_epoch++;
+    if (src->factor_cached && src->chol_coop && src->fit_seg == 2) {
+        const int n = src->nsolve, nblk = (n + CC_NB - 1) / CC_NB;
+        CK(cudaMemcpyAsync(dst->Aug, src->Aug, sizeof(double) * (size_t)(n + 1) * src->ld, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(dst->sc, src->sc, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(dst->cholW, src->cholW, sizeof(double) * (size_t)nblk * CC_NB * CC_NB, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(dst->kap2, src->kap2, sizeof(cd) * (size_t)(a.N1 / 2 + 1) * src->sfit.nrows, cudaMemcpyDeviceToDevice, st));
+        dst->factor_cached = 1;
+        if (src->aspec && src->aspec_epoch == src->tmpl_epoch && !dst->aspec_off && dst->grid_jc) {
+            if (!dst->aspec || dst->aspec_elems < src->aspec_elems) {
+                if (dst->aspec) { cudaFree(dst->aspec); dst->aspec = nullptr; }
+                if (cudaMalloc(&dst->aspec, sizeof(cd) * src->aspec_elems) != cudaSuccess) { cudaGetLastError(); dst->aspec = nullptr; dst->aspec_elems = 0; }
+                else dst->aspec_elems = src->aspec_elems;
+            }
+            if (dst->aspec) {
+                CK(cudaMemcpyAsync(dst->aspec, src->aspec, sizeof(cd) * src->aspec_elems, cudaMemcpyDeviceToDevice, st));
+                dst->aspec_epoch = dst->tmpl_epoch;
+            }
+        }
+    }
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
 extern "C" int sfftb_template_mark_ready(sfftb_plan* p) {
     if (!p || !p->tstate) return fail(SFFTB_ESTATE, "template state was never allocated");
     p->have_template = 1;

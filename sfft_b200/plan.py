@@ -297,6 +297,11 @@ class Plan:
     def template_mark_ready(self):
         B.check(self._L.sfftb_template_mark_ready(self._h))
 
+    def template_clone(self, src):
+        """Copy the shared-template state of `src` (spectra, and -- once src has them -- Cholesky factor, lag rows, cached segment
+        spectra) into this plan: one factorisation per template for all plans of a pipeline."""
+        B.check(self._L.sfftb_template_clone(self._h, src._h))
+
     def gss_template(self, PixA_J, PixA_mJ, out_dtype=np.float64):
         self._check_pair(PixA_J, PixA_mJ)
         pJ, mk, dt, kJ = _ptr_of(PixA_J)
