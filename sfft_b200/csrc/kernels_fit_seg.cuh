@@ -28,6 +28,7 @@ struct SegFitArgs {
     const cd* Q;                     // Q[q][k1] = DFT_c(cy(c)^q), q = 0..DB
     signed char pq_of[4][4];
     const cd* momg;                  // column moments [NH][planes * SFFTB_MAXE] (col_moments_kernel -> fit_seg4_kernel)
+    int mom_external;                // 1: the background cross-term rows are written by col_poly_rows_kernel, not inside fit_seg4_kernel
 };
 
 // asynchronous element copy global -> shared (LDGSTS); 8 bytes for fp32 spectra, 16 for fp64

@@ -39,15 +39,25 @@
 #ifndef FS4_NSLOT32
 #define FS4_NSLOT32 2
 #endif
-// spectrum ring slots (a third slot for fp32-stored spectra fits with FS4_NSTG 4 but measured slower: 1.00 vs 0.93 ms at C2)
-template <typename TSt> struct Fs4Ring { static const int nslot = sizeof(TSt) == 8 ? FS4_NSLOT32 : 2; };
+// ring geometry: fp32-stored spectra with KerPolyOrder <= 2 take THREE spectrum slots (the transforms of segment s + 2 start under the
+// products of s) and six windows (219 KB; with four windows the third slot measured slower, with six 0.73 against 0.75 ms at C2); every
+// other case two slots, fp32 eight / fp64 four windows (their planes or windows are larger)
+#ifndef FS4_RING3
+#define FS4_RING3 1
+#endif
+template <typename TSt, int DK = 3> struct Fs4Ring {
+    static const bool three = FS4_RING3 && sizeof(TSt) == 8 && DK <= 2;
+    static const int nslot = three ? 3 : (sizeof(TSt) == 8 ? FS4_NSLOT32 : 2);
+    static const int depth = sizeof(TSt) == 8 ? (three ? 6 : FS4_NSTG) : 4;
+};
 // dynamic shared memory of fit_seg4_kernel for the largest instantiation of a plan (host side)
 static inline size_t fs4_smem_bytes(int DK, bool f32) {
     const int Fij = (DK + 1) * (DK + 2) / 2;
     const int NP = DK == 3 ? 13 : 2 * Fij + 1, NACC = DK == 3 ? 24 : Fij * (Fij + 1) / 2 + Fij;
-    const int planes = std::max((f32 ? FS4_NSLOT32 : 2) * NP, NACC);
+    const bool three = FS4_RING3 && f32 && DK <= 2;
+    const int planes = std::max((three ? 3 : (f32 ? FS4_NSLOT32 : 2)) * NP, NACC);
     return sizeof(cd) * ((size_t)planes * FS4_PITCH + (DK == 3 ? 5 : 4) * SFFTB_MAXE) + 128 +
-           (f32 ? sizeof(float2) * FS4_NSTG : sizeof(double2) * 4) * (size_t)(DK + 2) * FS3_M;
+           (f32 ? sizeof(float2) * (three ? 6 : FS4_NSTG) : sizeof(double2) * 4) * (size_t)(DK + 2) * FS3_M;
 }
 
 // TMA-style bulk copies (cp.async.bulk, the 1-D form of the tensor memory accelerator's copy engine): a 256-row window of a
@@ -163,6 +173,24 @@ __global__ void __launch_bounds__(256) col_moments_kernel(int N0, int NH, int DK
     }
 }
 
+// Background cross-term rows (I x T, J x T) of every column from the column moments: one CTA per column.  Inside fit_seg4_kernel this
+// work sat at the start of every column on the product warps (wrap-row corrections read the column ends from global memory, an L2
+// round trip per row, while the transform warps had filled their two ring slots and waited); as a kernel of its own it costs the
+// product warps nothing.
+template <typename TSt, int DK>
+__global__ void __launch_bounds__(256) col_poly_rows_kernel(SegFitArgs fa, const TSt* __restrict__ gI, cd* __restrict__ kap, int jonly)
+{
+    constexpr int NMS = Fs3Mom<DK>::npl * SFFTB_MAXE;
+    __shared__ cd mom[NMS];
+    const int tid = threadIdx.x;
+    for (int k1 = blockIdx.x; k1 < fa.c.NH; k1 += gridDim.x) {
+        if (tid < NMS) mom[tid] = fa.momg[(size_t)k1 * NMS + tid];
+        __syncthreads();
+        column_poly_rows_sub(fa, gI, k1, mom, kap + (size_t)k1 * fa.nrows, tid, 256, jonly != 0);
+        __syncthreads();
+    }
+}
+
 // JONLY (shared-template tiles after the first): the template is unchanged, so only the cross spectra with J and the
 // moments of J are recomputed -- Fij "A role" transforms + one of J per segment, Fij accumulators; the rows of the other
 // pairs and of the I x T terms stay in `kap` from the first tile of the batch.
@@ -193,9 +221,9 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
         return A * Fij - A * (A - 1) / 2 + q;
     };
     constexpr int NSRC = DK + 2;
-    constexpr int NSLOT = Fs4Ring<TSt>::nslot;
+    constexpr int NSLOT = Fs4Ring<TSt, DK>::nslot;
     constexpr int NPL = NSLOT * NP;                   // planes in the spectrum ring
-    constexpr int NSTG = sizeof(TSt) == 8 ? FS4_NSTG : 4, PFD = NSTG - 2;   // fp64 windows: 4 buffers (any depth, not only powers of two)
+    constexpr int NSTG = Fs4Ring<TSt, DK>::depth, PFD = NSTG - 2;   // any depth, not only powers of two
     static_assert(NACC <= FS4_NHW, "one half warp per accumulator in the inverse phase");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const ColArgs& a = fa.c;
@@ -277,7 +305,7 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
             // background cross-term rows of the PREVIOUS column: off the critical path (the transform warps are busy with the
             // first segments of this column)
             if constexpr (DO_MOM) {
-                if (kprev >= 0) {
+                if (kprev >= 0 && !fa.mom_external) {
                     if (tid < NMS) mom[tid] = fa.momg[(size_t)kprev * NMS + tid];
                     fs3_barP();
                     column_poly_rows_sub(fa, gI, kprev, mom, kap + (size_t)kprev * fa.nrows, tid, 256, JONLY);
@@ -355,7 +383,7 @@ __global__ void __launch_bounds__(FS4_NT, 1) fit_seg4_kernel(SegFitArgs fa, VTab
         }
         if constexpr (DO_MOM) {
             // (the column moments come from col_moments_kernel, one warp per column and stored plane, before this launch)
-            if (kprev >= 0) {
+            if (kprev >= 0 && !fa.mom_external) {
                 if (tid < NMS) mom[tid] = fa.momg[(size_t)kprev * NMS + tid];
                 fs3_barP();
                 column_poly_rows_sub(fa, gI, kprev, mom, kap + (size_t)kprev * fa.nrows, tid, 256, JONLY);

@@ -449,7 +449,7 @@ static int plan_create_impl(sfftb_plan* p, const sfftb_config* cfg) {
         memcpy(sf.pq_of, pa.pq_of, sizeof sf.pq_of);
         CK(cudaMalloc(&p->kap2, sizeof(cd) * (size_t)NH * sf.nrows));
         CK(cudaMalloc(&p->momg, sizeof(cd) * (size_t)NH * 5 * SFFTB_MAXE));
-        sf.momg = p->momg;
+        sf.momg = p->momg; sf.mom_external = env_int("SFFTB_MOM_EXTERNAL", 1);
         LagReduce2Args& r2 = p->red2;
         r2.N1 = N1; r2.NH = NH; r2.nrows = sf.nrows; r2.w1 = d.w1; r2.tw1 = p->tw1; r2.rb0 = 0;
         const int rowblocks = (sf.nrows + 15) / 16;

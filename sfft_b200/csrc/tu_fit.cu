@@ -97,7 +97,8 @@ int launch_fit_cols(sfftb_plan* p, const TSt* gIsrc, bool jonly) {
         CKL(p);
     }
     if (p->fit_seg) EVREC(p, EV_KFIT0);
-    if (jonly && jcache_ready<TSt>(p, gIsrc)) {
+    const bool jc = jonly && jcache_ready<TSt>(p, gIsrc);
+    if (jc) {
         const int NHj = d.N1 / 2 + 1;
         const int grid = std::min(NHj, work_sms(p) * p->grid_jc);
         const size_t smj = jcache_smem_bytes();
@@ -123,6 +124,15 @@ int launch_fit_cols(sfftb_plan* p, const TSt* gIsrc, bool jonly) {
     } else
         fit_col_kernel<TSt><<<p->grid_fit, NT_COL, p->smem_fit, p->stream>>>(p->cfit, gIsrc, (const TSt*)p->gJ, p->kap, p->lam, p->nuJ);
     CKL(p);
+    if (p->fit_seg && p->sfit.mom_external && !(jonly && jc)) {
+        const int NHm = d.N1 / 2 + 1;
+        const int gridm = std::min(NHm, 8 * work_sms(p));
+        if (DK == 0) col_poly_rows_kernel<TSt, 0><<<gridm, 256, 0, p->stream>>>(p->sfit, gIsrc, p->kap2, jonly ? 1 : 0);
+        else if (DK == 1) col_poly_rows_kernel<TSt, 1><<<gridm, 256, 0, p->stream>>>(p->sfit, gIsrc, p->kap2, jonly ? 1 : 0);
+        else if (DK == 2) col_poly_rows_kernel<TSt, 2><<<gridm, 256, 0, p->stream>>>(p->sfit, gIsrc, p->kap2, jonly ? 1 : 0);
+        else col_poly_rows_kernel<TSt, 3><<<gridm, 256, 0, p->stream>>>(p->sfit, gIsrc, p->kap2, jonly ? 1 : 0);
+        CKL(p);
+    }
     if (p->fit_seg) EVREC(p, EV_KFIT1);
     EVREC(p, EV_COL);
     if (p->fit_seg) {
