@@ -111,3 +111,62 @@ def test_template_batch_world2_gloo():
         J = base['SCI'] + rng.normal(0, 0.5, (N, N))
         sol, diff, _ = orc.gss(base['REF'], J, base['mREF'], J, P)
         np.testing.assert_allclose(out[0][3][k], [diff.sum(), sol[0]], rtol=1e-9, atol=1e-9)
+
+
+class _FakePlan:
+    """Records what a TemplatePipeline asks of its plans (no GPU): a tile's 'result' is (plan id, tile tag)."""
+    count = 0
+
+    def __init__(self, *a, **k):
+        self.id = _FakePlan.count
+        _FakePlan.count += 1
+        self.log, self.pending, self.factor, self.cache, self.tiles = [], None, False, False, 0
+
+    def template_prepare(self, I, mI):
+        self.log.append('prepare'); self.factor = self.cache = False; self.tiles = 0
+
+    def template_clone(self, src):
+        self.log.append(('clone', src.id, src.factor, src.cache)); self.factor, self.cache = src.factor, src.cache
+
+    def gss_template_submit(self, J, mJ, out_dtype=None, Solution_out=None, DIFF_out=None):
+        assert self.pending is None
+        self.pending = (self.id, J, 'cached' if self.factor else 'factorised')
+        if self.factor:
+            self.cache = True                # first cached-factor tile builds the spectra cache
+        self.factor = True
+        self.tiles += 1
+
+    def gss_finish(self):
+        r, self.pending = self.pending, None
+        assert r is not None
+        return r
+
+    def close(self):
+        pass
+
+
+def test_template_pipeline_start_up_and_order(monkeypatch):
+    """Host logic of batch.TemplatePipeline without a GPU: the first two tiles of a template go through the first plan (factorisation,
+    spectra cache), the third submission copies that state to the other plans (one clone each, of a plan that holds factor AND cache),
+    every later tile runs from a cached factor round-robin, results come back in submission order, a new template starts over."""
+    import sfft_b200.plan as planmod
+    from sfft_b200.batch import TemplatePipeline
+    monkeypatch.setattr(planmod, 'Plan', _FakePlan)
+    _FakePlan.count = 0
+    pipe = TemplatePipeline(64, 64, 2, depth=3)
+    assert [p.id for p in pipe.plans] == [0, 1, 2]
+    for rnd in range(2):
+        pipe.set_template('I%d' % rnd, 'mI%d' % rnd)
+        for p in pipe.plans[1:]:
+            assert p.log[-1] == ('clone', 0, False, False)           # spectra only so far
+        got = pipe.run([(t, t) for t in range(8)])
+        assert [g[1] for g in got] == list(range(8))                 # submission order
+        assert [g[0] for g in got] == [0, 0, 0, 1, 2, 0, 1, 2]        # two start-up tiles on plan 0, then round-robin
+        assert [g[2] for g in got] == ['factorised'] + ['cached'] * 7
+        for p in pipe.plans[1:]:
+            assert p.log[-1] == ('clone', 0, True, True)             # shared once, after factor and cache existed
+            assert sum(1 for e in p.log if isinstance(e, tuple)) == 2 * (rnd + 1)
+    # a short batch never needs the other plans
+    pipe.set_template('I', 'mI')
+    assert [g[0] for g in pipe.run([(0, 0), (1, 1)])] == [0, 0]
+    pipe.close()
